@@ -1,0 +1,418 @@
+// dg_core.cuh -- per-item arithmetic of the hot path, shared by every kernel.
+//
+// Everything here is a plain inline function over raw pointers so that the same source is
+// (a) inlined into the sm_100a kernels of dg_search.cu / dg_build.cu and (b) compiled by g++
+// into tests/hostsim (unit tests of the arithmetic against the reference on a box without a
+// GPU).  The product library contains the device instantiation only.
+//
+// What of the reference each part replaces:
+//   OccBlock / rank_acgt / lf_step      SDSL wt_pc::rank + rank_support_v::rank (wt_pc.hpp:325-347,
+//                                       rank_support_v.hpp:104-115), inverse_select (wt_pc.hpp:359-374)
+//   backward_step                       backward_search (suffix_array_algorithm.hpp:151-179)
+//   sa_value                            csa_wt::operator[] (csa_wt.hpp:340-354)
+//   Script / script_rtl / script_ltr    the DFS of neighbors.h:47-83, unrolled into edit scripts
+//   restricted_distance / is_minimal    the antichain rule of _insert (neighbors.h:29-45)
+//   needle_align                        needle() (needle.h:59-138) for AlignConfig<false,true>,
+//                                       DnaScore(0,-1,-1,-1), plus the gap stripping of
+//                                       hunter.h:391-401 / silica.h:527-532
+//   locate_record                       hunter.h:358-362 (text position -> refIndex, chrpos)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DG_HD __host__ __device__ __forceinline__
+#else
+#define DG_HD inline
+struct uint2 { uint32_t x, y; };  // host-side stand-in for the CUDA vector type (tests/hostsim)
+#endif
+
+namespace dg {
+
+constexpr int kMaxQuery = 255;     // longest query the device path accepts
+constexpr int kMaxDist = 2;        // largest distance the device path enumerates
+constexpr int kFlagShift = 12;     // one exception-flag bit per 4096 BWT rows
+constexpr int kSaSample = 32;      // csa_wt<> t_dens
+
+// ------------------------------------------------------------------------------------------
+// Occurrence blocks: 64 BWT symbols per 32-byte block (one DRAM sector).  cnt[c] = number of
+// symbol c (A,C,G,T = 0..3) in BWT[0, 64*b); lo/hi = bit planes of the 2-bit codes.  BWT
+// symbols outside ACGT are stored as code 0 and listed in the exception arrays.
+struct OccBlock {
+  uint32_t cnt[4];
+  uint64_t lo, hi;
+};
+
+struct IndexView {
+  const OccBlock* occ;
+  uint64_t n;                 // text length incl. sentinel; rows are 0..n-1
+  const uint32_t* excflag;    // bit (row >> kFlagShift): region holds a non-ACGT BWT symbol
+  const uint32_t* exc_pos;    // rows of non-ACGT BWT symbols, ascending
+  const uint8_t* exc_sym;     // their byte values
+  uint32_t n_exc;
+  const uint32_t* rare_pos;   // the same rows grouped by symbol (ascending inside a group)
+  const uint32_t* rare_off;   // 257 entries: group of byte s is [rare_off[s], rare_off[s+1])
+  const uint32_t* Cb;         // 256 entries: number of text symbols smaller than byte s
+  const uint8_t* present;     // 256 entries: byte s occurs in the text
+  uint32_t C4[4];             // Cb['A'], Cb['C'], Cb['G'], Cb['T']
+  const uint2* kmer;          // 4^K half-open SA intervals [x, y) of the ACGT K-mers
+  uint32_t K;
+  const uint32_t* sa_samples; // SA[32 k]
+  const uint8_t* text;        // the n text bytes (sentinel included)
+  const uint64_t* cum;        // nseq + 1 cumulative seqlen (util.h:201 lengths)
+  uint32_t nseq;
+};
+
+DG_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+
+// A,C,G,T -> 0..3; anything else -> 4.
+DG_HD int base_code(uint8_t b) {
+  if (b == 'A') return 0;
+  if (b == 'C') return 1;
+  if (b == 'G') return 2;
+  if (b == 'T') return 3;
+  return 4;
+}
+DG_HD uint8_t code_base(int c) { return (uint8_t)("ACGT"[c & 3]); }
+
+DG_HD uint32_t lower_bound_u32(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t key) {
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+DG_HD uint32_t upper_bound_u64(const uint64_t* a, uint32_t lo, uint32_t hi, uint64_t key) {
+  while (lo < hi) {  // first index with a[idx] > key
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] <= key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+DG_HD OccBlock load_block(const OccBlock* p) {
+#if defined(__CUDA_ARCH__)
+  // one 32-byte sector, two 128-bit read-only loads
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  OccBlock o;
+  o.cnt[0] = a.x; o.cnt[1] = a.y; o.cnt[2] = a.z; o.cnt[3] = a.w;
+  o.lo = ((uint64_t)b.y << 32) | b.x;
+  o.hi = ((uint64_t)b.w << 32) | b.z;
+  return o;
+#else
+  return *p;
+#endif
+}
+
+DG_HD bool region_flag(const IndexView& ix, uint64_t row) {
+  uint64_t g = row >> kFlagShift;
+  return (ix.excflag[g >> 5] >> (g & 31)) & 1u;
+}
+
+// occurrences of code c (0..3) in BWT[0, i), 0 <= i <= n, given the loaded block of i.
+DG_HD uint32_t rank_in_block(const IndexView& ix, const OccBlock& b, uint64_t i, int c) {
+  uint32_t o = (uint32_t)(i & 63);
+  uint64_t mask = o ? (~0ULL >> (64 - o)) : 0ULL;
+  uint64_t m = ((c & 1) ? b.lo : ~b.lo) & ((c & 2) ? b.hi : ~b.hi) & mask;
+  uint32_t r = b.cnt[c] + (uint32_t)popc64(m);
+  if (c == 0 && o && region_flag(ix, i - 1)) {
+    // non-ACGT symbols are stored as code 0: take those inside [64*blk, i) back out
+    uint32_t base = (uint32_t)(i & ~63ULL);
+    uint32_t a = lower_bound_u32(ix.exc_pos, 0, ix.n_exc, base);
+    uint32_t e = lower_bound_u32(ix.exc_pos, a, ix.n_exc, (uint32_t)i);
+    r -= (e - a);
+  }
+  return r;
+}
+DG_HD uint32_t rank_acgt(const IndexView& ix, uint64_t i, int c) {
+  OccBlock b = load_block(ix.occ + (i >> 6));
+  return rank_in_block(ix, b, i, c);
+}
+// occurrences of an arbitrary byte s in BWT[0, i)
+DG_HD uint32_t rank_byte(const IndexView& ix, uint64_t i, uint8_t s) {
+  int c = base_code(s);
+  if (c < 4) return rank_acgt(ix, i, c);
+  uint32_t a = ix.rare_off[s], e = ix.rare_off[s + 1];
+  return lower_bound_u32(ix.rare_pos, a, e, (uint32_t)(i > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : i)) - a;
+}
+
+// One backward-search step on the half-open interval [l, r): suffix_array_algorithm.hpp:151-179.
+// (The reference special-cases the full range; rank(0) = 0 and rank(n) = count make the general
+// formula give the same interval.)  A byte that does not occur in the text empties the interval.
+DG_HD void backward_step(const IndexView& ix, uint32_t& l, uint32_t& r, uint8_t s) {
+  int c = base_code(s);
+  if (c < 4) {
+    OccBlock bl = load_block(ix.occ + (l >> 6));
+    uint32_t nl = ix.C4[c] + rank_in_block(ix, bl, l, c);
+    uint32_t nr;
+    if ((r >> 6) == (l >> 6)) nr = ix.C4[c] + rank_in_block(ix, bl, r, c);
+    else nr = ix.C4[c] + rank_acgt(ix, r, c);
+    l = nl; r = nr;
+  } else {
+    if (!ix.present[s]) { r = l; return; }
+    uint32_t nl = ix.Cb[s] + rank_byte(ix, l, s);
+    uint32_t nr = ix.Cb[s] + rank_byte(ix, r, s);
+    l = nl; r = nr;
+  }
+}
+
+// BWT[row] and LF(row): traverse_csa_wt_traits::access -> wt_pc::inverse_select
+// (suffix_array_helper.hpp:280-292, wt_pc.hpp:359-374).
+DG_HD uint32_t lf_step(const IndexView& ix, uint32_t row, uint8_t* sym) {
+  OccBlock b = load_block(ix.occ + (row >> 6));
+  uint32_t o = row & 63;
+  int c = (int)(((b.hi >> o) & 1) << 1 | ((b.lo >> o) & 1));
+  if (c == 0 && region_flag(ix, row)) {
+    uint32_t k = lower_bound_u32(ix.exc_pos, 0, ix.n_exc, row);
+    if (k < ix.n_exc && ix.exc_pos[k] == row) {
+      uint8_t s = ix.exc_sym[k];
+      if (sym) *sym = s;
+      uint32_t a = ix.rare_off[s], e = ix.rare_off[s + 1];
+      return ix.Cb[s] + (lower_bound_u32(ix.rare_pos, a, e, row) - a);
+    }
+  }
+  if (sym) *sym = code_base(c);
+  return ix.C4[c] + rank_in_block(ix, b, row, c);
+}
+
+// SA[row]: csa_wt::operator[] (csa_wt.hpp:340-354) with sa_order_sa_sampling, t_dens = 32.
+DG_HD uint32_t sa_value(const IndexView& ix, uint32_t row) {
+  uint32_t off = 0;
+  while (row & (kSaSample - 1)) { row = lf_step(ix, row, nullptr); ++off; }
+  uint64_t v = (uint64_t)ix.sa_samples[row / kSaSample] + off;
+  if (v >= ix.n) v -= ix.n;
+  return (uint32_t)v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Edit scripts.  The reference DFS (neighbors.h:47-83) walks the query left to right and at
+// each position may delete the base, keep it, substitute one of the other alphabet letters, or
+// insert one of the 4 letters before it; a string is recorded when at least one edit was spent.
+// Every recorded string is therefore "query + a list of <= d events sorted by position, where
+// several insertions (ordered) may precede one substitution/deletion at the same position".
+// An event is a slot number e = pos * slots + k; edit mode has 9 slots per position
+// (k 0..3 substitute ACGT[k], 4 delete, 5..8 insert ACGT[k-5] before pos), Hamming mode 4.
+struct Script {
+  int nev;      // 0..2
+  int pos[2];
+  int k[2];
+};
+
+DG_HD int slots_per_pos(bool indel) { return indel ? 9 : 4; }
+
+// Decodes slot e and checks it against the base string (a substitution must change the base).
+DG_HD bool decode_event(const uint8_t* base, int m, bool indel, int e, int& pos, int& k) {
+  int s = indel ? 9 : 4;
+  pos = e / s;
+  k = e - pos * s;
+  if (pos >= m) return false;
+  if (k < 4 && code_base(k) == base[pos]) return false;
+  return true;
+}
+// Is (e1, e2) an admissible ordered pair?  pos1 < pos2, or equal positions with e1 an insertion.
+DG_HD bool pair_ok(int pos1, int k1, int pos2) { return pos1 < pos2 || (pos1 == pos2 && k1 >= 5); }
+// First slot a second event may take after first event (pos1, k1).
+DG_HD int second_event_start(int pos1, int k1, bool indel) {
+  int s = indel ? 9 : 4;
+  return (k1 >= 5 ? pos1 : pos1 + 1) * s;
+}
+
+// Calls f(byte) for every character of the edited string from the LAST to the first; f returns
+// false to stop early.  Returns false if stopped.
+template <typename F>
+DG_HD bool script_rtl(const uint8_t* base, int m, const Script& sc, F&& f) {
+  int ev = sc.nev - 1;
+  for (int p = m - 1; p >= 0; --p) {
+    uint8_t x = base[p];
+    bool emit = true;
+    if (ev >= 0 && sc.pos[ev] == p && sc.k[ev] <= 4) {
+      if (sc.k[ev] == 4) emit = false; else x = code_base(sc.k[ev]);
+      --ev;
+    }
+    if (emit && !f(x)) return false;
+    while (ev >= 0 && sc.pos[ev] == p) {
+      if (!f(code_base(sc.k[ev] - 5))) return false;
+      --ev;
+    }
+    if (ev < 0 && p > 0) {
+      // no events left: the rest is the unedited prefix
+      for (int t = p - 1; t >= 0; --t) if (!f(base[t])) return false;
+      return true;
+    }
+  }
+  return true;
+}
+// Left-to-right materialisation; returns the length (<= m + nev).
+DG_HD int script_ltr(const uint8_t* base, int m, const Script& sc, uint8_t* out) {
+  int ev = 0, L = 0;
+  for (int p = 0; p < m; ++p) {
+    while (ev < sc.nev && sc.pos[ev] == p && sc.k[ev] >= 5) { out[L++] = code_base(sc.k[ev] - 5); ++ev; }
+    uint8_t x = base[p];
+    bool emit = true;
+    if (ev < sc.nev && sc.pos[ev] == p) {
+      if (sc.k[ev] == 4) emit = false; else x = code_base(sc.k[ev]);
+      ++ev;
+    }
+    if (emit) out[L++] = x;
+  }
+  return L;
+}
+DG_HD int script_len(int m, const Script& sc) {
+  int L = m;
+  for (int i = 0; i < sc.nev; ++i) { if (sc.k[i] == 4) --L; else if (sc.k[i] >= 5) ++L; }
+  return L;
+}
+
+// Packed script code carried by a candidate: strand | nev | e1 | e2.
+DG_HD uint32_t pack_script(int strand, int nev, int e1, int e2) {
+  return (uint32_t)strand | ((uint32_t)nev << 1) | ((uint32_t)e1 << 3) | ((uint32_t)e2 << 15);
+}
+DG_HD void unpack_script(uint32_t code, bool indel, int& strand, Script& sc) {
+  strand = code & 1;
+  sc.nev = (code >> 1) & 3;
+  int s = indel ? 9 : 4;
+  int e1 = (code >> 3) & 0xFFF, e2 = (code >> 15) & 0xFFF;
+  sc.pos[0] = e1 / s; sc.k[0] = e1 - sc.pos[0] * s;
+  sc.pos[1] = e2 / s; sc.k[1] = e2 - sc.pos[1] * s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Membership in the generated set G_d(q) of neighbors.h: minimum number of DFS edits turning q
+// into u, where an insertion is only possible while a query base is still pending (the DFS
+// never inserts after the last base, neighbors.h:49,71-77) and only ACGT can be written.
+// Returns min(cost, cap + 1).  row/prev are caller scratch of >= ulen + 1 entries.
+DG_HD int restricted_distance(const uint8_t* q, int m, const uint8_t* u, int ulen, int cap,
+                              uint8_t* prev, uint8_t* row) {
+  const int INF = 100;
+  for (int j = 0; j <= ulen; ++j) {
+    // D[0][j]: j insertions before q[0] (needs m > 0 and ACGT letters)
+    int v = (j == 0) ? 0 : ((m > 0 && prev[j - 1] < INF && base_code(u[j - 1]) < 4) ? prev[j - 1] + 1 : INF);
+    prev[j] = (uint8_t)(v > INF ? INF : v);
+  }
+  for (int i = 1; i <= m; ++i) {
+    row[0] = (uint8_t)(i > INF ? INF : i);
+    int best = row[0];
+    for (int j = 1; j <= ulen; ++j) {
+      int sub = prev[j - 1];
+      if (q[i - 1] != u[j - 1]) sub = (base_code(u[j - 1]) < 4) ? sub + 1 : INF;
+      int del = prev[j] + 1;
+      int ins = (i < m && base_code(u[j - 1]) < 4) ? row[j - 1] + 1 : INF;
+      int v = sub < del ? sub : del;
+      if (ins < v) v = ins;
+      if (v > INF) v = INF;
+      row[j] = (uint8_t)v;
+      if (v < best) best = v;
+    }
+    if (best > cap) return cap + 1;
+    uint8_t* t = prev; prev = row; row = t;
+  }
+  int r = prev[ulen];
+  return r > cap ? cap + 1 : r;
+}
+
+// _insert (neighbors.h:29-45) keeps exactly the substring-minimal strings of everything the DFS
+// generates (plus the query).  t (length L) is kept iff no proper substring of it is generated.
+// Generated strings have length >= m - d, so only those substrings are tried.
+DG_HD bool is_minimal(const uint8_t* q, int m, int d, const uint8_t* t, int L, uint8_t* s0, uint8_t* s1) {
+  int minlen = m - d;
+  if (minlen < 1) minlen = 1;
+  for (int len = minlen; len < L; ++len)
+    for (int a = 0; a + len <= L; ++a)
+      if (restricted_distance(q, m, t + a, len, d, s0, s1) <= d) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// needle() for std::string x std::string, AlignConfig<false,true>, DnaScore(0,-1,-1,-1)
+// (needle.h:59-138, align.h:52-80): rows = genomic g (length mg), columns = query s (length n).
+// trace: caller scratch of >= ((mg+1)*(n+1)+3)/4 bytes (2 bits per cell: 1 = bit3, 2 = bit4);
+// srow: >= n+1 ints; ops: >= mg+n bytes.  Outputs the alignment with leading / trailing
+// query-gap columns stripped (hunter.h:391-401), the number of stripped leading columns, and
+// the score.  Returns the number of kept columns.
+DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, uint8_t* trace, int* srow,
+                       uint8_t* ops, uint8_t* refalign, uint8_t* queryalign, int* lead_out, int* score_out) {
+  const int mf = n + 1;
+  auto setbits = [&](int cell, int v) {
+    int sh = (cell & 3) * 2;
+    trace[cell >> 2] = (uint8_t)((trace[cell >> 2] & ~(3 << sh)) | (v << sh));
+  };
+  auto getbits = [&](int cell) { return (trace[cell >> 2] >> ((cell & 3) * 2)) & 3; };
+  int prevsub = 0;
+  for (int row = 0; row <= mg; ++row) {
+    for (int col = 0; col <= n; ++col) {
+      int cell = row * mf + col;
+      if (row == 0 && col == 0) {
+        srow[0] = 0; prevsub = 0; setbits(cell, 0);
+      } else if (row == 0) {
+        srow[col] = -col;            // _horizontalGap(AlignConfig<false,*>) = col * ge
+        setbits(cell, 1);
+      } else if (col == 0) {
+        srow[0] = 0;                 // _verticalGap(AlignConfig<*,true>, 0, n, ..) = 0
+        prevsub = 0;
+        setbits(cell, 2);
+      } else {
+        int prevprevsub = prevsub;
+        prevsub = srow[col];
+        int vg = (col == n) ? 0 : -1;  // _verticalGap: free at col == 0 or col == n
+        int diag = prevprevsub + (g[row - 1] == s[col - 1] ? 0 : -1);
+        int up = prevsub + vg;
+        int left = srow[col - 1] - 1;
+        int v = diag > up ? diag : up;
+        if (left > v) v = left;
+        srow[col] = v;
+        setbits(cell, v == left ? 1 : (v == up ? 2 : 0));
+      }
+    }
+  }
+  *score_out = srow[n];
+  // traceback (needle.h:114-131): bit3 -> 'h', bit4 -> 'v', else 's'
+  int row = mg, col = n, nops = 0;
+  while (row > 0 || col > 0) {
+    int b = getbits(row * mf + col);
+    if (b == 1) { --col; ops[nops++] = 'h'; }
+    else if (b == 2) { --row; ops[nops++] = 'v'; }
+    else { --row; --col; ops[nops++] = 's'; }
+  }
+  // _createAlignment (align.h:176-203) read left to right = ops back to front.
+  // trailing columns whose query row is '-' are dropped (_trailGap, hunter.h:69-77) ...
+  int last_aligned = nops - 1;   // column index of the last column with a query character
+  {
+    int j = 0, found = -1;
+    for (int t = nops - 1; t >= 0; --t, ++j) if (ops[t] != 'v') found = j;
+    if (found >= 0) last_aligned = found;
+  }
+  int ncols = last_aligned + 1;
+  // ... and leading ones advance chrpos instead of being copied (hunter.h:393-400).
+  int r = 0, c = 0, kept = 0, lead = 0;
+  bool leadGap = true;
+  for (int j = 0, t = nops - 1; j < ncols; ++j, --t) {
+    uint8_t a0, a1;
+    if (ops[t] == 's') { a0 = g[r++]; a1 = s[c++]; }
+    else if (ops[t] == 'h') { a0 = '-'; a1 = s[c++]; }
+    else { a0 = g[r++]; a1 = '-'; }
+    if (a1 != '-') leadGap = false;
+    if (!leadGap) { refalign[kept] = a0; queryalign[kept] = a1; ++kept; }
+    else ++lead;
+  }
+  *lead_out = lead;
+  return kept;
+}
+
+// hunter.h:358-362 / silica.h:475-479: text position -> (refIndex, chrpos).
+DG_HD void locate_record(const uint64_t* cum, uint32_t nseq, uint64_t pos, uint32_t& refIndex, uint32_t& chrpos) {
+  if (nseq == 0) { refIndex = 0; chrpos = (uint32_t)pos; return; }
+  // largest r with cum[r] <= pos, clamped to the last record
+  uint32_t r = upper_bound_u64(cum, 0, nseq + 1, pos);  // first cum[idx] > pos
+  r = r ? r - 1 : 0;
+  if (r > nseq - 1) r = nseq - 1;
+  refIndex = r;
+  chrpos = (uint32_t)((int64_t)pos - (int64_t)cum[r]);
+}
+
+}  // namespace dg

@@ -1,0 +1,204 @@
+/* dicey_b200.h -- C ABI of the B200-native FM-index primer-matching engine.
+ *
+ * The reference (gear-genomics/dicey) has no plugin / FFI seam; the boundary is the set of
+ * C++ calls its three driver loops make into SDSL and its own neighbors.h / needle.h
+ * (SURVEY.md section 8b).  Each entry point below names the reference call sites it replaces.
+ * Plain pointers and sizes only; no C++ or torch types; no exceptions cross this boundary.
+ *
+ * Ownership: the caller owns every input buffer (borrowed for the duration of the call);
+ * the library owns dg_index / dg_batch / dg_result objects until the matching *_close/_free.
+ * Threading: one dg_index is bound to one CUDA device and one internal stream; calls on one
+ * index must be serialised by the caller; different indexes (one per GPU) are independent.
+ * Every function returns DG_OK (0) or a negative dg_status; dg_last_error() gives the text.
+ */
+#ifndef DICEY_B200_H
+#define DICEY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dg_index dg_index;
+typedef struct dg_batch dg_batch;
+typedef struct dg_result dg_result;
+
+typedef enum {
+  DG_OK = 0,
+  DG_ERR_ARG = -1,         /* bad argument */
+  DG_ERR_IO = -2,          /* file cannot be read / written */
+  DG_ERR_FORMAT = -3,      /* not a csa_wt<> .fm9, or .fm9_check mismatch (SDSL io.hpp:917-936) */
+  DG_ERR_CUDA = -4,        /* no usable device, or a CUDA call failed (never falls back to CPU) */
+  DG_ERR_UNSUPPORTED = -5, /* outside the device path's limits (see DESIGN.md "Limits") */
+  DG_ERR_OVERFLOW = -6,    /* a bounded device buffer would overflow (too many occurrences) */
+  DG_ERR_NOMEM = -7
+} dg_status;
+
+/* Per-query status bits (dg_result_query_status). */
+enum {
+  DG_Q_TOO_SHORT = 1u << 0,       /* hunter.h:299-303: |seq| < 10 -> error, no search */
+  DG_Q_DIST_ADJUSTED = 1u << 1,   /* hunter.h:312-315: distance clamped to |seq|-1 */
+  DG_Q_HIT_CAP = 1u << 2,         /* hunter.h:434-437: hits >= max_locations */
+  DG_Q_NBR_CAP = 1u << 3,         /* hunter.h:342-345: neighbourhood size >= max_neighborhood */
+  DG_Q_NBR_UNVERIFIED = 1u << 4,  /* edit-mode set size not certified below max_neighborhood
+                                     (script count >= cap); searched untruncated */
+  DG_Q_SKIPPED = 1u << 5          /* silica.h:371: primer not longer than the seed k-mer */
+};
+
+/* hunter.h:37-50 (HunterConfig) / silica.h:38-67 (SilicaConfig), the fields the hot path reads. */
+typedef struct {
+  uint32_t distance;          /* -d; clamped per query to |seq|-1                      */
+  uint32_t max_neighborhood;  /* -x, default 10000                                     */
+  uint32_t max_locations;     /* -m, default 1000 (hunt) / 10000 (search)              */
+  uint8_t indel;              /* 1 = edit distance, 0 = Hamming (-n)                   */
+  uint8_t reverse;            /* 1 = also search the reverse complement (0 with -f)    */
+  uint8_t reserved[2];
+  uint32_t seed_len;          /* 0 = whole query (hunt); k (search, silica.h:449-451)  */
+} dg_params;
+
+/* One DnaHit (hunter.h:53-66) in the reference's push order.  refalign/queryalign are
+ * aln_len bytes each at pool + aln_off and pool + aln_off + aln_len.                   */
+typedef struct {
+  uint32_t query;     /* index of the query in the batch                               */
+  int32_t score;      /* -(edit or Hamming distance)                                   */
+  uint32_t chr;       /* refIndex                                                      */
+  uint32_t start;     /* DnaHit.start (1-based, after leading-gap stripping)           */
+  uint64_t text_pos;  /* occurrence position of the neighbour string in the text       */
+  uint64_t aln_off;   /* offset of refalign in the alignment pool                      */
+  uint32_t aln_len;   /* alignment columns                                             */
+  uint32_t alignpos;  /* search only: chrpos + leading gap columns (silica.h:522-532)  */
+  uint8_t strand;     /* '+' or '-'                                                    */
+  uint8_t pad[7];
+} dg_hit;
+
+typedef struct {
+  uint64_t n;             /* csa.size(): text length including the sentinel            */
+  uint32_t sigma;         /* alphabet size including the sentinel                      */
+  uint32_t kmer;          /* K of the K-mer -> SA interval table                       */
+  uint64_t n_exceptions;  /* BWT symbols outside ACGT                                  */
+  uint64_t device_bytes;  /* HBM held by this index                                    */
+  uint32_t sa_sample;     /* suffix-array sampling rate (csa_wt<>: 32)                 */
+  uint32_t nseq;          /* records set by dg_index_set_records                       */
+} dg_index_info;
+
+/* Stage timings of the last dg_batch_run with profiling enabled (CUDA events on the index
+ * stream), and the launch count claimed for bench.py's "gpu_launches".                */
+typedef struct {
+  float ms_prepare;   /* normalise + reverse-complement + script counting              */
+  float ms_search;    /* k_search: neighbour enumeration x backward search (dominant)  */
+  float ms_filter;    /* minimality filter, lexicographic sort, dedupe, cap scan       */
+  float ms_locate;    /* SA-interval expansion + per-neighbour position sort           */
+  float ms_verify;    /* chromosome lookup, context fetch, NW traceback                */
+  float ms_total;     /* first to last event                                           */
+  uint64_t launches;  /* kernels launched by the run (ours + CUB's)                    */
+  uint64_t scripts;   /* edit scripts evaluated by k_search                            */
+  uint64_t candidates;/* neighbour strings with a non-empty SA interval                */
+  uint64_t located;   /* text positions located                                        */
+  uint64_t hits;      /* hits emitted                                                  */
+} dg_profile;
+
+/* ---- index ------------------------------------------------------------------------ */
+
+/* load_from_checked_file(fm_index, file): hunter.h:253-260, silica.h:340-347,
+ * padlock.h:259-265 -> SDSL io.hpp:917-936 -> csa_wt::load csa_wt.hpp:381-388.
+ * Parses the .fm9 written by `dicey index` as-is (+ .fm9_check) and transcodes it to the
+ * device layout (DESIGN.md "Data layout in HBM").  device >= 0 selects the CUDA device.  */
+int dg_index_open(const char* fm9_path, int device, dg_index** out);
+
+/* index.h:96-123 (dump -> construct) for a text already in dump format (records upper-cased,
+ * joined by '\n', trailing '\n'; no sentinel): suffix array, BWT and device layout are built
+ * on the GPU.  Alphabet: at most 7 distinct byte values besides the sentinel.              */
+int dg_index_build_text(const uint8_t* text, uint64_t len, int device, dg_index** out);
+
+/* Same, for the seeded synthetic reference of SURVEY.md 8(d) generated on the device
+ * (dicey_b200/synth.py documents the generator).                                          */
+int dg_index_build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device,
+                             dg_index** out);
+
+/* store_to_checked_file (index.h:122): writes an SDSL-loadable csa_wt<> .fm9 + .fm9_check
+ * from the device index.  Select supports are written empty (arg_cnt = 0; count / locate /
+ * extract never use them), everything else follows csa_wt.hpp:362-373.                   */
+int dg_index_write_fm9(dg_index* idx, const char* fm9_path);
+
+void dg_index_close(dg_index* idx);
+
+/* fm_index.size(): hunter.h:368-369, silica.h:487-488. */
+uint64_t dg_index_size(const dg_index* idx);
+
+/* getSeqLenName (util.h:183-206): seqlen[i] = faidx length + 1, used for the text position
+ * -> (refIndex, chrpos) mapping of hunter.h:358-362 / silica.h:475-479.                   */
+int dg_index_set_records(dg_index* idx, const uint32_t* seqlen_plus1, uint32_t nseq);
+
+int dg_index_get_info(const dg_index* idx, dg_index_info* info);
+
+/* The CUDA stream (cudaStream_t) every kernel of this index is launched on. */
+void* dg_index_stream(const dg_index* idx);
+
+/* Copies of device-resident index arrays for tests (what = "text", "sa_samples", "occ",
+ * "kmer", "C"); returns the byte count through *bytes; buf may be NULL to query the size. */
+int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* bytes);
+
+/* ---- batched queries ---------------------------------------------------------------- */
+
+/* The per-query loop of `dicey hunt` (hunter.h:289-433): neighbors() on both strands
+ * (neighbors.h:86-92), sdsl::count / locate / extract per neighbour
+ * (suffix_array_algorithm.hpp:447-454, 521-535, 643-657), needle() / needleScore()
+ * (needle.h:59-138, hunter.h:79-88), DnaHit push.  Hits come back per query in the
+ * reference's push order (strand, neighbour lexicographic, position ascending), capped at
+ * max_locations; the caller applies hunter.h:440 std::sort and the JSON writer.
+ * seqs holds the nq raw query sequences back to back; offsets has nq+1 entries.
+ * With params->seed_len = k it is the FM / NW part of `dicey search` (silica.h:449-573):
+ * the last k bases are the seed, contexts are extended by |primer|-k on the 5' side, and
+ * each hit additionally carries alignpos; every candidate is returned (the thal Tm gate of
+ * silica.h:508-519 stays with the caller).                                               */
+int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq,
+                  const dg_params* params, dg_result** out);
+
+/* The same call split into its three phases, so a caller (bench.py) can keep inputs resident
+ * in HBM: stage = host -> device copy of the queries; run = every kernel, asynchronous on the
+ * index stream; fetch = device -> host copy of the hit records (synchronises).             */
+int dg_batch_stage(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq,
+                   const dg_params* params, dg_batch** out);
+int dg_batch_run(dg_batch* b);
+int dg_batch_fetch(dg_batch* b, dg_result** out);
+int dg_batch_summary(dg_batch* b, uint64_t* n_hits, uint64_t* n_candidates); /* synchronises */
+void dg_batch_free(dg_batch* b);
+
+/* sdsl::count over a neighbourhood: padlock.h:381-427 (exact count of each string when
+ * params->distance == 0, else the sum over neighbors() of both strands) and the prune of
+ * silica.h:365-394.  counts[i] receives the total for query i.                           */
+int dg_count_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq,
+                   const dg_params* params, uint64_t* counts);
+
+/* sdsl::backward_search for literal patterns (suffix_array_algorithm.hpp:207-226): the
+ * closed interval [l[i], r[i]] (r = l - 1 when empty), as SDSL reports it.              */
+int dg_backward_search_batch(dg_index* idx, const char* seqs, const uint64_t* offsets,
+                             uint32_t nq, uint64_t* l, uint64_t* r);
+
+/* ---- results ------------------------------------------------------------------------ */
+const dg_hit* dg_result_hits(const dg_result* r, uint64_t* n);
+const uint64_t* dg_result_query_offsets(const dg_result* r, uint32_t* nq); /* nq+1 entries */
+const uint32_t* dg_result_query_status(const dg_result* r);               /* nq entries   */
+const uint32_t* dg_result_query_distance(const dg_result* r);             /* clamped d    */
+const char* dg_result_pool(const dg_result* r, uint64_t* bytes);
+const char* dg_result_sequences(const dg_result* r, uint64_t* bytes);     /* normalised queries, same offsets as the input */
+void dg_result_free(dg_result* r);
+
+/* ---- multi-GPU ---------------------------------------------------------------------- */
+/* The hit all-gather is done by the host layer over torch.distributed /
+ * NCCL on flat byte buffers; these two calls give it the wire format.                    */
+int dg_result_pack(const dg_result* r, void* buf, uint64_t* bytes);   /* buf NULL -> size  */
+int dg_result_unpack(const void* buf, uint64_t bytes, dg_result** out);
+
+/* ---- diagnostics -------------------------------------------------------------------- */
+int dg_profile_enable(dg_index* idx, int on);
+int dg_profile_get(dg_index* idx, dg_profile* out);
+const char* dg_last_error(void);
+const char* dg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DICEY_B200_H */

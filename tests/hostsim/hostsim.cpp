@@ -1,0 +1,90 @@
+// tests/hostsim -- TEST INFRASTRUCTURE.  Compiles the per-item arithmetic of
+// dicey_b200/csrc/dg_core.cuh with g++ so that the script enumeration, the antichain rule and
+// the NW traceback can be checked against the reference on a box without a GPU.  Nothing here
+// is linked into the product library.
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <fstream>
+#include <set>
+#include <string>
+#include <vector>
+#include "../../dicey_b200/csrc/dg_core.cuh"
+
+using namespace dg;
+
+static void neighbors(const std::string& q, int d, bool indel, std::set<std::string>& out) {
+  int m = (int)q.size();
+  const uint8_t* base = (const uint8_t*)q.data();
+  int E = slots_per_pos(indel) * m;
+  std::set<std::string> all;
+  std::vector<uint8_t> buf(m + 8);
+  auto add = [&](const Script& sc) {
+    int L = script_ltr(base, m, sc, buf.data());
+    // cross-check the right-to-left emitter
+    std::string rt;
+    script_rtl(base, m, sc, [&](uint8_t x) { rt.push_back((char)x); return true; });
+    std::string lt((char*)buf.data(), L);
+    if (std::string(rt.rbegin(), rt.rend()) != lt || L != script_len(m, sc)) { fprintf(stderr, "rtl/ltr mismatch\n"); exit(3); }
+    all.insert(lt);
+  };
+  Script sc; sc.nev = 0; sc.pos[0] = sc.pos[1] = sc.k[0] = sc.k[1] = 0;
+  add(sc);
+  if (d >= 1)
+    for (int e1 = 0; e1 < E; ++e1) {
+      int p1, k1;
+      if (!decode_event(base, m, indel, e1, p1, k1)) continue;
+      sc.nev = 1; sc.pos[0] = p1; sc.k[0] = k1;
+      add(sc);
+      if (d >= 2)
+        for (int e2 = second_event_start(p1, k1, indel); e2 < E; ++e2) {
+          int p2, k2;
+          if (!decode_event(base, m, indel, e2, p2, k2)) continue;
+          if (!pair_ok(p1, k1, p2)) continue;
+          sc.nev = 2; sc.pos[1] = p2; sc.k[1] = k2;
+          add(sc);
+        }
+    }
+  if (!indel) { out = all; return; }
+  std::vector<uint8_t> s0(m + 8), s1(m + 8);
+  for (auto const& t : all)
+    if (is_minimal(base, m, d, (const uint8_t*)t.data(), (int)t.size(), s0.data(), s1.data())) out.insert(t);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  std::string cmd = argv[1];
+  if (cmd == "neighbors" && argc >= 5) {
+    std::ifstream f(argv[2]);
+    int d = atoi(argv[3]);
+    bool indel = atoi(argv[4]) != 0;
+    std::string q;
+    while (std::getline(f, q)) {
+      if (q.empty()) continue;
+      std::set<std::string> st;
+      neighbors(q, d, indel, st);
+      std::cout << "Q\t" << q << '\t' << st.size() << '\n';
+      for (auto const& s : st) std::cout << s << '\n';
+    }
+    return 0;
+  }
+  if (cmd == "needle" && argc >= 3) {
+    std::ifstream f(argv[2]);
+    std::string line;
+    while (std::getline(f, line)) {
+      size_t t = line.find('\t');
+      if (t == std::string::npos) continue;
+      std::string g = line.substr(0, t), s = line.substr(t + 1);
+      int mg = (int)g.size(), n = (int)s.size();
+      std::vector<uint8_t> trace(((mg + 1) * (n + 1) + 3) / 4 + 1), ops(mg + n + 1), ra(mg + n + 1), qa(mg + n + 1);
+      std::vector<int> srow(n + 1);
+      int lead = 0, score = 0;
+      int kept = needle_align((const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, trace.data(), srow.data(),
+                              ops.data(), ra.data(), qa.data(), &lead, &score);
+      std::cout << score << '\t' << lead << '\t' << std::string((char*)ra.data(), kept) << '\t'
+                << std::string((char*)qa.data(), kept) << '\n';
+    }
+    return 0;
+  }
+  return 2;
+}
