@@ -1,0 +1,739 @@
+// dg_build.cu -- builds the device-resident index (DESIGN.md "Data layout in HBM") either from a
+// `.fm9` written by `dicey index` (SDSL csa_wt<> serialization, parsed by fm9.hpp) or from a text
+// in dicey's dump format (reference src/index.h:96-123), entirely on the GPU.
+//
+//   .fm9 path : wavelet-tree bits -> BWT bytes (k_decode_bwt, the arithmetic of wt_pc::operator[]
+//               wt_pc.hpp:294-311 over rank_support_v blocks rank_support_v.hpp:104-115)
+//               -> occurrence blocks + exception lists -> K-mer interval table
+//               -> text rebuilt from the ISA samples by 64-step LF chains (the walk of
+//               suffix_array_algorithm.hpp:588-609, run for every sample at once).
+//   text path : suffix array by bucketed radix sort of 21-symbol prefixes with tie refinement
+//               (replaces divsufsort in construct_sa.hpp:96-120), BWT = T[SA-1]
+//               (construct_bwt.hpp:35-71), SA samples every 32 rows, ISA samples every 64 positions
+//               (csa_sampling_strategy.hpp:70-93, 669-706).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "dg_common.cuh"
+#include "fm9.hpp"
+
+namespace dg {
+
+namespace {
+
+struct Temp {  // growable CUB scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  ~Temp() { if (p) cudaFree(p); }
+  void* ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = bytes + (bytes >> 2) + 256;
+      DG_CUDA(cudaMalloc(&p, cap));
+    }
+    return p;
+  }
+};
+
+inline unsigned grid_for(uint64_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
+
+// ---------------------------------------------------------------- wavelet tree -> BWT bytes
+struct WtView {
+  const uint64_t* bv;
+  const uint64_t* bb;       // rank_support_v basic blocks
+  const uint64_t* bv_pos;   // per node
+  const uint64_t* bv_rank;  // per node (leaves: the symbol)
+  const uint16_t* child0;
+  const uint16_t* child1;
+};
+
+__device__ __forceinline__ uint64_t rank1_v(const WtView& w, uint64_t idx) {
+  // rank_support_v<1>::rank (rank_support_v.hpp:104-115)
+  const uint64_t* p = w.bb + ((idx >> 8) & 0xFFFFFFFFFFFFFFFEULL);
+  uint64_t r = p[0] + ((p[1] >> (63 - 9 * ((idx & 0x1FF) >> 6))) & 0x1FF);
+  if (idx & 0x3F) r += __popcll(w.bv[idx >> 6] & ((1ULL << (idx & 0x3F)) - 1));
+  return r;
+}
+
+__global__ void k_decode_bwt(WtView w, uint64_t n, uint8_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v = 0;
+  uint64_t pos = i;
+  while (w.child0[v] != 0xFFFF) {  // wt_pc::operator[] (wt_pc.hpp:294-311)
+    uint64_t at = w.bv_pos[v] + pos;
+    uint64_t r = rank1_v(w, at) - w.bv_rank[v];
+    if ((w.bv[at >> 6] >> (at & 63)) & 1) { pos = r; v = w.child1[v]; }
+    else { pos -= r; v = w.child0[v]; }
+  }
+  out[i] = (uint8_t)w.bv_rank[v];
+}
+
+// ---------------------------------------------------------------- BWT bytes -> occ blocks
+__global__ void k_pack_blocks(const uint8_t* __restrict__ bwt, uint64_t n, uint64_t nblocks, OccBlock* __restrict__ occ,
+                              uint32_t* __restrict__ ca, uint32_t* __restrict__ cc, uint32_t* __restrict__ cg,
+                              uint32_t* __restrict__ ct, unsigned long long* __restrict__ n_exc) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  uint64_t lo = 0, hi = 0;
+  uint32_t c[5] = {0, 0, 0, 0, 0};
+  uint64_t base = b << 6;
+  for (int o = 0; o < 64; ++o) {
+    uint64_t i = base + o;
+    if (i >= n) break;
+    int code = base_code(bwt[i]);
+    c[code]++;
+    if (code < 4) {
+      lo |= (uint64_t)(code & 1) << o;
+      hi |= (uint64_t)(code >> 1) << o;
+    }
+  }
+  occ[b].lo = lo;
+  occ[b].hi = hi;
+  ca[b] = c[0]; cc[b] = c[1]; cg[b] = c[2]; ct[b] = c[3];
+  if (c[4]) atomicAdd(n_exc, (unsigned long long)c[4]);
+}
+
+__global__ void k_fill_counts(uint64_t nblocks, OccBlock* __restrict__ occ, const uint32_t* __restrict__ ca,
+                              const uint32_t* __restrict__ cc, const uint32_t* __restrict__ cg,
+                              const uint32_t* __restrict__ ct) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  occ[b].cnt[0] = ca[b]; occ[b].cnt[1] = cc[b]; occ[b].cnt[2] = cg[b]; occ[b].cnt[3] = ct[b];
+}
+
+struct IsException {
+  const uint8_t* bwt;
+  __device__ bool operator()(uint32_t i) const { return base_code(bwt[i]) == 4; }
+};
+
+__global__ void k_exc_fill(const uint8_t* __restrict__ bwt, const uint32_t* __restrict__ pos, uint32_t n_exc,
+                           uint8_t* __restrict__ sym, uint32_t* __restrict__ flags, uint32_t* __restrict__ hist) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_exc) return;
+  uint32_t p = pos[k];
+  uint8_t s = bwt[p];
+  sym[k] = s;
+  uint32_t g = p >> kFlagShift;
+  atomicOr(&flags[g >> 5], 1u << (g & 31));
+  atomicAdd(&hist[s], 1u);
+}
+
+// ---------------------------------------------------------------- K-mer interval table
+// level k+1 from level k: the interval of c.S is one backward step from the interval of S.
+__global__ void k_kmer_level(IndexView ix, const uint2* __restrict__ prev, uint2* __restrict__ cur, uint32_t k) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t cnt = 1ULL << (2 * (k + 1));
+  if (t >= cnt) return;
+  uint32_t c = (uint32_t)(t >> (2 * k));
+  uint2 iv = prev[t & ((1ULL << (2 * k)) - 1)];
+  uint2 o = make_uint2(0, 0);
+  if (iv.x < iv.y) {
+    uint32_t l = iv.x, r = iv.y;
+    backward_step(ix, l, r, code_base((int)c));
+    if (l < r) o = make_uint2(l, r);
+  }
+  cur[t] = o;
+}
+
+// ---------------------------------------------------------------- text from ISA samples
+__global__ void k_rebuild_text(IndexView ix, const uint32_t* __restrict__ isa, uint64_t nchains, uint8_t* __restrict__ text) {
+  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchains) return;
+  uint64_t n = ix.n, first = c << 6, end = (c + 1) << 6;
+  uint32_t row;
+  int64_t p;
+  if (end <= n - 1) { row = isa[c + 1]; p = (int64_t)end - 1; }
+  else { text[n - 1] = 0; row = 0; p = (int64_t)n - 2; }  // suffix n-1 (the sentinel) is row 0
+  for (; p >= (int64_t)first; --p) {
+    uint8_t s;
+    row = lf_step(ix, row, &s);
+    text[p] = s;
+  }
+}
+
+// ---------------------------------------------------------------- synthetic text (dicey_b200/synth.py)
+__global__ void k_synth_text(uint64_t seed, uint64_t reclen, uint64_t n, uint8_t* __restrict__ text) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == n - 1) { text[i] = 0; return; }
+  uint64_t rec = i / (reclen + 1), o = i - rec * (reclen + 1);
+  if (o == reclen) { text[i] = '\n'; return; }
+  uint64_t z = seed + (rec * reclen + o) * 0x9E3779B97F4A7C15ULL;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  text[i] = (uint8_t)("ACGT"[z >> 62]);
+}
+
+// ---------------------------------------------------------------- suffix array on the GPU
+struct CodeMap { uint8_t code[256]; };
+
+__global__ void k_byte_hist(const uint8_t* __restrict__ t, uint64_t n, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&sh[t[i]], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+constexpr int kKeySyms = 21;  // 3-bit codes per 63-bit key
+
+__device__ __forceinline__ uint64_t suffix_key(const uint8_t* __restrict__ t, uint64_t n, uint64_t i, const CodeMap& cm) {
+  uint64_t key = 0;
+#pragma unroll
+  for (int j = 0; j < kKeySyms; ++j) {
+    uint64_t p = i + j;
+    uint64_t c = p < n ? cm.code[t[p]] : 0;
+    key = (key << 3) | c;
+  }
+  return key;
+}
+
+struct InBucket {
+  const uint8_t* t;
+  uint64_t n;
+  CodeMap cm;
+  uint32_t bucket;
+  __device__ bool operator()(uint32_t i) const {
+    uint32_t c0 = cm.code[t[i]];
+    uint32_t c1 = (uint64_t)i + 1 < n ? cm.code[t[(uint64_t)i + 1]] : 0;
+    return ((c0 << 3) | c1) == bucket;
+  }
+};
+
+__global__ void k_pair_hist(const uint8_t* __restrict__ t, uint64_t n, CodeMap cm, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[64];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t c0 = cm.code[t[i]];
+    uint32_t c1 = i + 1 < n ? cm.code[t[i + 1]] : 0;
+    atomicAdd(&sh[(c0 << 3) | c1], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+__global__ void k_make_keys(const uint8_t* __restrict__ t, uint64_t n, CodeMap cm, const uint32_t* __restrict__ suf,
+                            uint64_t cnt, uint64_t depth, uint64_t* __restrict__ keys) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cnt) return;
+  keys[j] = suffix_key(t, n, (uint64_t)suf[j] + depth, cm);
+}
+
+// tie flag of sorted position j: shares its key with a neighbour
+__global__ void k_tie_flags(const uint64_t* __restrict__ keys, uint64_t cnt, uint8_t* __restrict__ flag) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cnt) return;
+  uint64_t k = keys[j];
+  bool tie = (j > 0 && keys[j - 1] == k) || (j + 1 < cnt && keys[j + 1] == k);
+  flag[j] = tie ? 1 : 0;
+}
+// compacted tied element t at slot s: group id = compacted index of the first element of its run
+__global__ void k_group_heads(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slots, uint32_t nt,
+                              uint32_t* __restrict__ head) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  uint32_t s = slots[t];
+  bool is_head = (s == 0) || keys[s - 1] != keys[s];
+  head[t] = is_head ? t : 0;
+}
+__global__ void k_gather_suffix(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ slots, uint32_t nt,
+                                uint32_t* __restrict__ suf) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) suf[t] = sa[slots[t]];
+}
+__global__ void k_iota(uint32_t* __restrict__ a, uint32_t n) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) a[t] = t;
+}
+__global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n,
+                             uint32_t* __restrict__ dst) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = src[perm[t]];
+}
+__global__ void k_gather_u64(const uint64_t* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n,
+                             uint64_t* __restrict__ dst) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = src[perm[t]];
+}
+__global__ void k_scatter_sa(uint32_t* __restrict__ sa, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ suf,
+                             uint32_t nt) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) sa[slots[t]] = suf[t];
+}
+// after refinement: element t still tied iff (gid, key2) equals a neighbour's
+__global__ void k_retie(const uint32_t* __restrict__ gid, const uint64_t* __restrict__ key2, uint32_t nt,
+                        uint8_t* __restrict__ flag, uint32_t* __restrict__ head) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  bool same_prev = t > 0 && gid[t - 1] == gid[t] && key2[t - 1] == key2[t];
+  bool same_next = t + 1 < nt && gid[t + 1] == gid[t] && key2[t + 1] == key2[t];
+  flag[t] = (same_prev || same_next) ? 1 : 0;
+  head[t] = same_prev ? 0 : t;  // new group heads (meaningful for the tied ones)
+}
+// re-number group ids of the surviving tied elements after compaction: head index -> rank among survivors
+__global__ void k_renumber(const uint32_t* __restrict__ headscan, const uint32_t* __restrict__ keep_idx, uint32_t nk,
+                           uint32_t* __restrict__ gid_out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nk) gid_out[t] = headscan[keep_idx[t]];
+}
+
+__global__ void k_bwt_from_sa(const uint8_t* __restrict__ text, const uint32_t* __restrict__ sa, uint64_t n,
+                              uint8_t* __restrict__ bwt, uint32_t* __restrict__ sa_s, uint32_t* __restrict__ isa_s) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t p = sa[j];
+  bwt[j] = p ? text[p - 1] : text[n - 1];
+  if ((j & (kSaSample - 1)) == 0) sa_s[j / kSaSample] = p;
+  if ((p & 63) == 0) isa_s[p >> 6] = (uint32_t)j;
+}
+
+struct MaxOp {
+  __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+// Sorts the suffixes listed in suf[0..cnt) (all starting with the same 2 symbols) into sa_out.
+void sort_bucket(const uint8_t* text, uint64_t n, const CodeMap& cm, uint32_t* suf, uint64_t cnt, uint32_t* sa_out,
+                 uint64_t* keys_a, uint64_t* keys_b, uint32_t* suf_b, uint8_t* flag, Temp& tmp, cudaStream_t st) {
+  if (cnt == 0) return;
+  if (cnt >= (1ULL << 31)) { set_error("suffix bucket too large for the GPU builder"); throw CudaFail{DG_ERR_UNSUPPORTED}; }
+  const unsigned B = 256;
+  k_make_keys<<<grid_for(cnt, B), B, 0, st>>>(text, n, cm, suf, cnt, 0, keys_a);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a, keys_b, suf, suf_b, (int)cnt, 0, 57, st);
+  cub::DeviceRadixSort::SortPairs(tmp.ensure(tb), tb, keys_a, keys_b, suf, suf_b, (int)cnt, 0, 57, st);
+  DG_CUDA(cudaMemcpyAsync(sa_out, suf_b, cnt * 4, cudaMemcpyDeviceToDevice, st));
+  // ---- ties
+  k_tie_flags<<<grid_for(cnt, B), B, 0, st>>>(keys_b, cnt, flag);
+  DevBuf<uint32_t> slots, nsel;
+  nsel.alloc(1);
+  // upper bound for tied elements is cnt; allocate lazily after counting
+  {
+    size_t tb2 = 0;
+    thrust::counting_iterator<uint32_t> it(0);
+    // count first
+    DevBuf<uint32_t> dummy;
+    cub::DeviceReduce::Sum(nullptr, tb2, flag, nsel.p, (int)cnt, st);
+    cub::DeviceReduce::Sum(tmp.ensure(tb2), tb2, flag, nsel.p, (int)cnt, st);
+  }
+  uint32_t nt = 0;
+  DG_CUDA(cudaMemcpyAsync(&nt, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  if (nt == 0) return;
+  slots.alloc(nt);
+  {
+    size_t tb2 = 0;
+    thrust::counting_iterator<uint32_t> it(0);
+    cub::DeviceSelect::Flagged(nullptr, tb2, it, flag, slots.p, nsel.p, (int)cnt, st);
+    cub::DeviceSelect::Flagged(tmp.ensure(tb2), tb2, it, flag, slots.p, nsel.p, (int)cnt, st);
+  }
+  DevBuf<uint32_t> gid, gid2, sufc, sufc2, perm, perm2, head, keep;
+  DevBuf<uint64_t> key2, key2b;
+  DevBuf<uint8_t> tflag;
+  gid.alloc(nt); gid2.alloc(nt); sufc.alloc(nt); sufc2.alloc(nt); perm.alloc(nt); perm2.alloc(nt); head.alloc(nt);
+  keep.alloc(nt); key2.alloc(nt); key2b.alloc(nt); tflag.alloc(nt);
+  DevBuf<uint32_t> slots2;
+  slots2.alloc(nt);
+  // group ids = compacted index of the run head (inclusive max-scan of head markers)
+  k_group_heads<<<grid_for(nt, B), B, 0, st>>>(keys_b, slots.p, nt, head.p);
+  {
+    size_t tb2 = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, tb2, head.p, gid.p, MaxOp(), (int)nt, st);
+    cub::DeviceScan::InclusiveScan(tmp.ensure(tb2), tb2, head.p, gid.p, MaxOp(), (int)nt, st);
+  }
+  k_gather_suffix<<<grid_for(nt, B), B, 0, st>>>(sa_out, slots.p, nt, sufc.p);
+  uint64_t depth = kKeySyms;
+  uint32_t* cur_slots = slots.p;
+  uint32_t* alt_slots = slots2.p;
+  for (int round = 0; nt > 0; ++round) {
+    if (round > 100000) { set_error("text too repetitive for the GPU suffix sorter"); throw CudaFail{DG_ERR_UNSUPPORTED}; }
+    // key2 = next 21 symbols; order by (gid, key2): stable sort by key2, then stable sort by gid
+    k_make_keys<<<grid_for(nt, B), B, 0, st>>>(text, n, cm, sufc.p, nt, depth, key2.p);
+    k_iota<<<grid_for(nt, B), B, 0, st>>>(perm.p, nt);
+    size_t tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, key2.p, key2b.p, perm.p, perm2.p, (int)nt, 0, 63, st);
+    cub::DeviceRadixSort::SortPairs(tmp.ensure(tb2), tb2, key2.p, key2b.p, perm.p, perm2.p, (int)nt, 0, 63, st);
+    k_gather_u32<<<grid_for(nt, B), B, 0, st>>>(gid.p, perm2.p, nt, gid2.p);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, gid2.p, gid.p, perm2.p, perm.p, (int)nt, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(tmp.ensure(tb2), tb2, gid2.p, gid.p, perm2.p, perm.p, (int)nt, 0, 32, st);
+    // now gid.p = sorted gids (same sequence as before), perm.p = element order
+    k_gather_u32<<<grid_for(nt, B), B, 0, st>>>(sufc.p, perm.p, nt, sufc2.p);
+    k_gather_u64<<<grid_for(nt, B), B, 0, st>>>(key2.p, perm.p, nt, key2b.p);
+    k_scatter_sa<<<grid_for(nt, B), B, 0, st>>>(sa_out, cur_slots, sufc2.p, nt);
+    // which are still tied?
+    k_retie<<<grid_for(nt, B), B, 0, st>>>(gid.p, key2b.p, nt, tflag.p, head.p);
+    cub::DeviceScan::InclusiveScan(nullptr, tb2, head.p, gid2.p, MaxOp(), (int)nt, st);
+    cub::DeviceScan::InclusiveScan(tmp.ensure(tb2), tb2, head.p, gid2.p, MaxOp(), (int)nt, st);
+    thrust::counting_iterator<uint32_t> it(0);
+    cub::DeviceSelect::Flagged(nullptr, tb2, it, tflag.p, keep.p, nsel.p, (int)nt, st);
+    cub::DeviceSelect::Flagged(tmp.ensure(tb2), tb2, it, tflag.p, keep.p, nsel.p, (int)nt, st);
+    uint32_t nk = 0;
+    DG_CUDA(cudaMemcpyAsync(&nk, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    if (nk == 0) break;
+    // compact survivors: slots, suffixes, group ids (head index is unique per group; keep it as id)
+    k_gather_u32<<<grid_for(nk, B), B, 0, st>>>(cur_slots, keep.p, nk, alt_slots);
+    k_gather_u32<<<grid_for(nk, B), B, 0, st>>>(sufc2.p, keep.p, nk, sufc.p);
+    k_renumber<<<grid_for(nk, B), B, 0, st>>>(gid2.p, keep.p, nk, gid.p);
+    std::swap(cur_slots, alt_slots);
+    nt = nk;
+    depth += kKeySyms;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- shared tail of both paths
+static void finish_from_bwt(dg_index* ix, const uint8_t* d_bwt, const std::vector<uint32_t>& Cb,
+                            const std::vector<uint8_t>& present) {
+  cudaStream_t st = ix->stream;
+  const unsigned B = 256;
+  uint64_t n = ix->n;
+  uint64_t nblocks = (n >> 6) + 1;
+  Temp tmp;
+  ix->occ.alloc(nblocks);
+  {
+    DevBuf<uint32_t> ca, cc, cg, ct;
+    DevBuf<unsigned long long> nexc;
+    ca.alloc(nblocks); cc.alloc(nblocks); cg.alloc(nblocks); ct.alloc(nblocks); nexc.alloc(1);
+    DG_CUDA(cudaMemsetAsync(nexc.p, 0, 8, st));
+    k_pack_blocks<<<grid_for(nblocks, B), B, 0, st>>>(d_bwt, n, nblocks, ix->occ.p, ca.p, cc.p, cg.p, ct.p, nexc.p);
+    uint32_t* arrs[4] = {ca.p, cc.p, cg.p, ct.p};
+    for (int c = 0; c < 4; ++c) {
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, arrs[c], arrs[c], (int)nblocks, st);
+      cub::DeviceScan::ExclusiveSum(tmp.ensure(tb), tb, arrs[c], arrs[c], (int)nblocks, st);
+    }
+    k_fill_counts<<<grid_for(nblocks, B), B, 0, st>>>(nblocks, ix->occ.p, ca.p, cc.p, cg.p, ct.p);
+    unsigned long long ne = 0;
+    DG_CUDA(cudaMemcpyAsync(&ne, nexc.p, 8, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    if (ne >= (1ULL << 32)) { set_error("too many non-ACGT BWT symbols"); throw CudaFail{DG_ERR_UNSUPPORTED}; }
+    ix->n_exc = (uint32_t)ne;
+  }
+  // exception lists
+  uint64_t nflagw = (((n >> kFlagShift) + 1) + 31) / 32;
+  ix->excflag.alloc(nflagw);
+  DG_CUDA(cudaMemsetAsync(ix->excflag.p, 0, nflagw * 4, st));
+  ix->exc_pos.alloc(ix->n_exc ? ix->n_exc : 1);
+  ix->exc_sym.alloc(ix->n_exc ? ix->n_exc : 1);
+  ix->rare_pos.alloc(ix->n_exc ? ix->n_exc : 1);
+  ix->rare_off.alloc(257);
+  std::vector<uint32_t> h_off(257, 0);
+  if (ix->n_exc) {
+    DevBuf<uint32_t> nsel, hist;
+    nsel.alloc(1); hist.alloc(256);
+    DG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * 4, st));
+    IsException pred{d_bwt};
+    uint64_t done = 0;
+    for (uint64_t start = 0; start < n; start += (1ULL << 30)) {
+      uint64_t cnt = std::min<uint64_t>(1ULL << 30, n - start);
+      thrust::counting_iterator<uint32_t> it((uint32_t)start);
+      size_t tb = 0;
+      cub::DeviceSelect::If(nullptr, tb, it, ix->exc_pos.p + done, nsel.p, (int)cnt, pred, st);
+      cub::DeviceSelect::If(tmp.ensure(tb), tb, it, ix->exc_pos.p + done, nsel.p, (int)cnt, pred, st);
+      uint32_t got = 0;
+      DG_CUDA(cudaMemcpyAsync(&got, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      done += got;
+    }
+    if (done != ix->n_exc) { set_error("internal: exception count mismatch"); throw CudaFail{DG_ERR_CUDA}; }
+    k_exc_fill<<<grid_for(ix->n_exc, B), B, 0, st>>>(d_bwt, ix->exc_pos.p, ix->n_exc, ix->exc_sym.p, ix->excflag.p, hist.p);
+    // group by symbol (stable radix sort on the byte keeps rows ascending inside a group)
+    DevBuf<uint8_t> symo;
+    symo.alloc(ix->n_exc);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, ix->exc_sym.p, symo.p, ix->exc_pos.p, ix->rare_pos.p, (int)ix->n_exc, 0, 8, st);
+    cub::DeviceRadixSort::SortPairs(tmp.ensure(tb), tb, ix->exc_sym.p, symo.p, ix->exc_pos.p, ix->rare_pos.p, (int)ix->n_exc, 0, 8, st);
+    std::vector<uint32_t> h_hist(256);
+    DG_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, 256 * 4, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < 256; ++s) h_off[s + 1] = h_off[s] + h_hist[s];
+  }
+  DG_CUDA(cudaMemcpyAsync(ix->rare_off.p, h_off.data(), 257 * 4, cudaMemcpyHostToDevice, st));
+  ix->Cb.alloc(256);
+  ix->present.alloc(256);
+  ix->h_Cb = Cb;
+  ix->h_present = present;
+  DG_CUDA(cudaMemcpyAsync(ix->Cb.p, Cb.data(), 256 * 4, cudaMemcpyHostToDevice, st));
+  DG_CUDA(cudaMemcpyAsync(ix->present.p, present.data(), 256, cudaMemcpyHostToDevice, st));
+  ix->C4[0] = Cb['A']; ix->C4[1] = Cb['C']; ix->C4[2] = Cb['G']; ix->C4[3] = Cb['T'];
+  DG_CUDA(cudaStreamSynchronize(st));
+}
+
+static void build_kmer_table(dg_index* ix) {
+  cudaStream_t st = ix->stream;
+  uint32_t K = 0;
+  if (const char* e = getenv("DG_KMER")) K = (uint32_t)atoi(e);
+  if (K == 0) {
+    // about one text suffix per table cell, capped at 14 (2 GiB of uint2 at 3 Gb)
+    K = 1;
+    while (K < 14 && (1ULL << (2 * (K + 1))) <= ix->n) ++K;
+  }
+  if (K > 15) K = 15;
+  ix->K = K;
+  DevBuf<uint2> a, b;
+  ix->kmer.alloc(1ULL << (2 * K));
+  if (K >= 1) a.alloc(1ULL << (2 * (K - 1)));
+  if (K >= 2) b.alloc(1ULL << (2 * (K - 2)));
+  // levels alternate between a and b so that level K lands in ix->kmer
+  uint2 root = make_uint2(0, (uint32_t)ix->n);
+  std::vector<uint2*> lv(K + 1);
+  lv[K] = ix->kmer.p;
+  for (int k = (int)K - 1; k >= 0; --k) lv[k] = ((K - 1 - k) % 2 == 0) ? a.p : b.p;
+  DG_CUDA(cudaMemcpyAsync(lv[0], &root, sizeof(uint2), cudaMemcpyHostToDevice, st));
+  IndexView v = ix->view();
+  for (uint32_t k = 0; k < K; ++k) {
+    uint64_t cnt = 1ULL << (2 * (k + 1));
+    k_kmer_level<<<grid_for(cnt, 256), 256, 0, st>>>(v, lv[k], lv[k + 1], k);
+  }
+  DG_CUDA(cudaGetLastError());
+  DG_CUDA(cudaStreamSynchronize(st));
+}
+
+static dg_index* new_index(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (the dicey_b200 library has no CPU path)");
+    throw CudaFail{DG_ERR_CUDA};
+  }
+  if (device < 0 || device >= ndev) { set_error("bad device ordinal"); throw CudaFail{DG_ERR_ARG}; }
+  DG_CUDA(cudaSetDevice(device));
+  dg_index* ix = new dg_index();
+  ix->device = device;
+  DG_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  ix->cum.alloc(1);
+  DG_CUDA(cudaMemset(ix->cum.p, 0, 8));
+  return ix;
+}
+
+int build_from_fm9(const char* path, int device, dg_index** out) {
+  Fm9 f;
+  std::string err;
+  int rc = fm9_parse(path, f, err);
+  if (rc) { set_error(err); return rc; }
+  if (f.n >= (1ULL << 32) - 64) { set_error("text longer than 2^32 - 64 symbols is outside the device path"); return DG_ERR_UNSUPPORTED; }
+  if (f.n < 2 || f.nodes.empty()) { set_error("empty index"); return DG_ERR_FORMAT; }
+  dg_index* ix = nullptr;
+  try {
+    ix = new_index(device);
+    cudaStream_t st = ix->stream;
+    ix->n = f.n;
+    ix->sigma = f.sigma;
+    // alphabet: C per byte value (csa_alphabet_strategy.hpp: char2comp / C)
+    std::vector<uint32_t> Cb(256, 0);
+    std::vector<uint8_t> present(256, 0);
+    for (int s = 0; s < 256; ++s) {
+      uint8_t cc = f.char2comp[s];
+      if (cc != 0 || s == 0) { present[s] = 1; Cb[s] = (uint32_t)f.C[cc]; }
+    }
+    // wavelet tree -> BWT bytes
+    DevBuf<uint8_t> bwt;
+    {
+      size_t nn = f.nodes.size();
+      std::vector<uint64_t> bvp(nn), bvr(nn);
+      std::vector<uint16_t> c0(nn), c1(nn);
+      for (size_t i = 0; i < nn; ++i) {
+        bvp[i] = f.nodes[i].bv_pos; bvr[i] = f.nodes[i].bv_pos_rank;
+        c0[i] = f.nodes[i].child[0]; c1[i] = f.nodes[i].child[1];
+      }
+      DevBuf<uint64_t> d_bv, d_bb, d_bvp, d_bvr;
+      DevBuf<uint16_t> d_c0, d_c1;
+      d_bv.alloc(f.bv.size() + 1); d_bb.alloc(f.rank_bb.size()); d_bvp.alloc(nn); d_bvr.alloc(nn); d_c0.alloc(nn); d_c1.alloc(nn);
+      DG_CUDA(cudaMemcpyAsync(d_bv.p, f.bv.data(), f.bv.size() * 8, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemsetAsync(d_bv.p + f.bv.size(), 0, 8, st));
+      DG_CUDA(cudaMemcpyAsync(d_bb.p, f.rank_bb.data(), f.rank_bb.size() * 8, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(d_bvp.p, bvp.data(), nn * 8, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(d_bvr.p, bvr.data(), nn * 8, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(d_c0.p, c0.data(), nn * 2, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(d_c1.p, c1.data(), nn * 2, cudaMemcpyHostToDevice, st));
+      bwt.alloc(f.n);
+      WtView w{d_bv.p, d_bb.p, d_bvp.p, d_bvr.p, d_c0.p, d_c1.p};
+      k_decode_bwt<<<grid_for(f.n, 256), 256, 0, st>>>(w, f.n, bwt.p);
+      DG_CUDA(cudaGetLastError());
+      DG_CUDA(cudaStreamSynchronize(st));
+    }
+    f.bv.clear(); f.bv.shrink_to_fit();
+    f.rank_bb.clear(); f.rank_bb.shrink_to_fit();
+    finish_from_bwt(ix, bwt.p, Cb, present);
+    bwt.release();
+    // SA / ISA samples: unpack the int_vector<0> payloads to u32
+    {
+      std::vector<uint32_t> s(f.sa_count);
+      for (uint64_t i = 0; i < f.sa_count; ++i) s[i] = (uint32_t)fm9_get_int(f.sa_words, i, f.sa_width);
+      ix->sa_samples.alloc(f.sa_count);
+      DG_CUDA(cudaMemcpyAsync(ix->sa_samples.p, s.data(), f.sa_count * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      s.resize(f.isa_count + 1);
+      for (uint64_t i = 0; i < f.isa_count; ++i) s[i] = (uint32_t)fm9_get_int(f.isa_words, i, f.isa_width);
+      ix->isa_samples.alloc(f.isa_count + 1);
+      DG_CUDA(cudaMemcpyAsync(ix->isa_samples.p, s.data(), f.isa_count * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+    }
+    build_kmer_table(ix);
+    // text from the ISA samples
+    ix->text.alloc(f.n + 64);
+    DG_CUDA(cudaMemsetAsync(ix->text.p, 0, f.n + 64, st));
+    uint64_t nchains = (f.n - 1) / 64 + 1;
+    k_rebuild_text<<<grid_for(nchains, 128), 128, 0, st>>>(ix->view(), ix->isa_samples.p, nchains, ix->text.p);
+    DG_CUDA(cudaGetLastError());
+    DG_CUDA(cudaStreamSynchronize(st));
+    *out = ix;
+    return DG_OK;
+  } catch (CudaFail& e) {
+    if (ix) dg_index_close(ix);
+    return e.code;
+  } catch (std::bad_alloc&) {
+    if (ix) dg_index_close(ix);
+    set_error("out of host memory");
+    return DG_ERR_NOMEM;
+  }
+}
+
+// Builds everything from ix->text (n bytes incl. sentinel, already on the device).
+static void build_from_device_text(dg_index* ix) {
+  cudaStream_t st = ix->stream;
+  const unsigned B = 256;
+  uint64_t n = ix->n;
+  const uint8_t* text = ix->text.p;
+  Temp tmp;
+  // alphabet
+  DevBuf<unsigned long long> d_hist;
+  d_hist.alloc(256);
+  DG_CUDA(cudaMemsetAsync(d_hist.p, 0, 256 * 8, st));
+  k_byte_hist<<<148 * 8, 256, 0, st>>>(text, n, d_hist.p);
+  std::vector<unsigned long long> hist(256);
+  DG_CUDA(cudaMemcpyAsync(hist.data(), d_hist.p, 256 * 8, cudaMemcpyDeviceToHost, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  if (hist[0] != 1) { set_error("text must not contain NUL bytes"); throw CudaFail{DG_ERR_ARG}; }
+  CodeMap cm;
+  memset(cm.code, 0, sizeof(cm.code));
+  std::vector<uint32_t> Cb(256, 0);
+  std::vector<uint8_t> present(256, 0);
+  uint32_t sigma = 0;
+  uint64_t run = 0;
+  for (int s = 0; s < 256; ++s) {
+    Cb[s] = (uint32_t)run;
+    if (hist[s]) {
+      present[s] = 1;
+      if (sigma >= 8) { set_error("more than 7 distinct symbols: outside the GPU builder (use `dicey index`)"); throw CudaFail{DG_ERR_UNSUPPORTED}; }
+      cm.code[s] = (uint8_t)sigma++;
+      run += hist[s];
+    }
+  }
+  for (int s = 0; s < 256; ++s) if (!present[s]) Cb[s] = 0;
+  ix->sigma = sigma;
+  // bucket sizes by the first two symbols
+  DevBuf<unsigned long long> d_ph;
+  d_ph.alloc(64);
+  DG_CUDA(cudaMemsetAsync(d_ph.p, 0, 64 * 8, st));
+  k_pair_hist<<<148 * 8, 256, 0, st>>>(text, n, cm, d_ph.p);
+  std::vector<unsigned long long> ph(64);
+  DG_CUDA(cudaMemcpyAsync(ph.data(), d_ph.p, 64 * 8, cudaMemcpyDeviceToHost, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  uint64_t maxb = 0;
+  for (auto v : ph) maxb = std::max<uint64_t>(maxb, v);
+  DevBuf<uint32_t> sa, suf, suf_b, nsel;
+  DevBuf<uint64_t> keys_a, keys_b;
+  DevBuf<uint8_t> flag;
+  sa.alloc(n); suf.alloc(maxb); suf_b.alloc(maxb); keys_a.alloc(maxb); keys_b.alloc(maxb); flag.alloc(maxb); nsel.alloc(1);
+  uint64_t out_pos = 0;
+  for (uint32_t b = 0; b < 64; ++b) {
+    uint64_t cnt = ph[b];
+    if (!cnt) continue;
+    InBucket pred{text, n, cm, b};
+    uint64_t done = 0;
+    for (uint64_t start = 0; start < n; start += (1ULL << 30)) {
+      uint64_t c = std::min<uint64_t>(1ULL << 30, n - start);
+      thrust::counting_iterator<uint32_t> it((uint32_t)start);
+      size_t tb = 0;
+      cub::DeviceSelect::If(nullptr, tb, it, suf.p + done, nsel.p, (int)c, pred, st);
+      cub::DeviceSelect::If(tmp.ensure(tb), tb, it, suf.p + done, nsel.p, (int)c, pred, st);
+      uint32_t got = 0;
+      DG_CUDA(cudaMemcpyAsync(&got, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      done += got;
+    }
+    if (done != cnt) { set_error("internal: bucket count mismatch"); throw CudaFail{DG_ERR_CUDA}; }
+    sort_bucket(text, n, cm, suf.p, cnt, sa.p + out_pos, keys_a.p, keys_b.p, suf_b.p, flag.p, tmp, st);
+    out_pos += cnt;
+  }
+  if (out_pos != n) { set_error("internal: suffix count mismatch"); throw CudaFail{DG_ERR_CUDA}; }
+  suf.release(); suf_b.release(); keys_a.release(); keys_b.release(); flag.release();
+  // BWT, SA samples, ISA samples
+  DevBuf<uint8_t> bwt;
+  bwt.alloc(n);
+  uint64_t nsa = (n + kSaSample - 1) / kSaSample, nisa = (n - 1) / 64 + 1;
+  ix->sa_samples.alloc(nsa);
+  ix->isa_samples.alloc(nisa + 1);
+  k_bwt_from_sa<<<grid_for(n, B), B, 0, st>>>(text, sa.p, n, bwt.p, ix->sa_samples.p, ix->isa_samples.p);
+  DG_CUDA(cudaGetLastError());
+  DG_CUDA(cudaStreamSynchronize(st));
+  sa.release();
+  finish_from_bwt(ix, bwt.p, Cb, present);
+  bwt.release();
+  build_kmer_table(ix);
+}
+
+int build_from_text_host(const uint8_t* text, uint64_t len, int device, dg_index** out) {
+  if (!text || !out) { set_error("null argument"); return DG_ERR_ARG; }
+  if (len + 1 >= (1ULL << 32) - 64) { set_error("text longer than 2^32 - 64 symbols is outside the device path"); return DG_ERR_UNSUPPORTED; }
+  dg_index* ix = nullptr;
+  try {
+    ix = new_index(device);
+    ix->n = len + 1;
+    ix->text.alloc(ix->n + 64);
+    DG_CUDA(cudaMemsetAsync(ix->text.p, 0, ix->n + 64, ix->stream));
+    DG_CUDA(cudaMemcpyAsync(ix->text.p, text, len, cudaMemcpyHostToDevice, ix->stream));
+    DG_CUDA(cudaStreamSynchronize(ix->stream));
+    build_from_device_text(ix);
+    *out = ix;
+    return DG_OK;
+  } catch (CudaFail& e) {
+    if (ix) dg_index_close(ix);
+    return e.code;
+  }
+}
+
+int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, dg_index** out) {
+  if (!out || nrec == 0 || reclen == 0) { set_error("bad argument"); return DG_ERR_ARG; }
+  uint64_t n = (uint64_t)nrec * (reclen + 1) + 1;
+  if (n >= (1ULL << 32) - 64) { set_error("text longer than 2^32 - 64 symbols is outside the device path"); return DG_ERR_UNSUPPORTED; }
+  dg_index* ix = nullptr;
+  try {
+    ix = new_index(device);
+    ix->n = n;
+    ix->text.alloc(n + 64);
+    DG_CUDA(cudaMemsetAsync(ix->text.p, 0, n + 64, ix->stream));
+    k_synth_text<<<grid_for(n, 256), 256, 0, ix->stream>>>(seed, reclen, n, ix->text.p);
+    DG_CUDA(cudaGetLastError());
+    build_from_device_text(ix);
+    // records: nrec x (reclen + 1), as util.h:201 would report them
+    std::vector<uint32_t> sl(nrec, (uint32_t)(reclen + 1));
+    int rc = dg_index_set_records(ix, sl.data(), nrec);
+    if (rc) { dg_index_close(ix); return rc; }
+    *out = ix;
+    return DG_OK;
+  } catch (CudaFail& e) {
+    if (ix) dg_index_close(ix);
+    return e.code;
+  }
+}
+
+}  // namespace dg
+
+namespace dg {
+int write_fm9(dg_index*, const char*) {
+  set_error("dg_index_write_fm9: not built yet");
+  return DG_ERR_UNSUPPORTED;
+}
+}  // namespace dg

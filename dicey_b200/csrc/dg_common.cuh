@@ -1,0 +1,101 @@
+// dg_common.cuh -- host-side state of one device-resident index and small CUDA helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/dicey_b200.h"
+#include "dg_core.cuh"
+
+namespace dg {
+
+void set_error(const std::string& msg);
+std::string& last_error_ref();
+
+struct CudaFail { int code; };
+
+#define DG_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::dg::set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                      std::to_string(__LINE__) + " (" #expr ")");                              \
+      throw ::dg::CudaFail{DG_ERR_CUDA};                                                       \
+    }                                                                                          \
+  } while (0)
+
+// Device buffer owned by an Index / Batch (plain cudaMalloc: these live as long as the owner).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    count = n;
+    if (n) DG_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    count = 0;
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+struct ProfileState {
+  bool enabled = false;
+  cudaEvent_t ev[8] = {};
+  bool created = false;
+  dg_profile last = {};
+  uint64_t launches = 0;
+};
+
+}  // namespace dg
+
+// The opaque handle of include/dicey_b200.h.
+struct dg_index {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t n = 0;
+  uint32_t sigma = 0;
+  uint32_t K = 0;
+  dg::DevBuf<dg::OccBlock> occ;
+  dg::DevBuf<uint32_t> excflag, exc_pos, rare_pos, rare_off, Cb, sa_samples, isa_samples;
+  dg::DevBuf<uint8_t> exc_sym, present, text;
+  dg::DevBuf<uint2> kmer;
+  dg::DevBuf<uint64_t> cum;
+  uint32_t n_exc = 0;
+  uint32_t nseq = 0;
+  uint32_t C4[4] = {0, 0, 0, 0};
+  std::vector<uint32_t> h_Cb;      // host copies for the .fm9 writer / info
+  std::vector<uint8_t> h_present;
+  dg::ProfileState prof;
+
+  dg::IndexView view() const {
+    dg::IndexView v;
+    v.occ = occ.p; v.n = n; v.excflag = excflag.p; v.exc_pos = exc_pos.p; v.exc_sym = exc_sym.p;
+    v.n_exc = n_exc; v.rare_pos = rare_pos.p; v.rare_off = rare_off.p; v.Cb = Cb.p; v.present = present.p;
+    for (int i = 0; i < 4; ++i) v.C4[i] = C4[i];
+    v.kmer = kmer.p; v.K = K; v.sa_samples = sa_samples.p; v.text = text.p; v.cum = cum.p; v.nseq = nseq;
+    return v;
+  }
+  uint64_t device_bytes() const {
+    return occ.bytes() + excflag.bytes() + exc_pos.bytes() + rare_pos.bytes() + rare_off.bytes() + Cb.bytes() +
+           sa_samples.bytes() + isa_samples.bytes() + exc_sym.bytes() + present.bytes() + text.bytes() +
+           kmer.bytes() + cum.bytes();
+  }
+};
+
+namespace dg {
+// dg_build.cu
+int build_from_fm9(const char* path, int device, dg_index** out);
+int build_from_text_host(const uint8_t* text, uint64_t len, int device, dg_index** out);
+int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, dg_index** out);
+int write_fm9(dg_index* idx, const char* path);
+}  // namespace dg

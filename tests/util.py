@@ -1,0 +1,77 @@
+"""Helpers shared by the tests: readers of the golden files written by tests/golden/make_golden.py."""
+import os
+
+from dicey_b200.api import HuntParams
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def read_queries(path):
+    out = []
+    for line in open(path):
+        line = line.rstrip("\n")
+        if not line:
+            continue
+        if "\t" in line:
+            n, s = line.split("\t", 1)
+        else:
+            n, s = "", line
+        out.append((n, s))
+    return out
+
+
+def read_records(path):
+    """-> list of dict(seq, distance, msgs, push, sorted, work) per query."""
+    qs = []
+    for line in open(path):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "Q":
+            qs.append({"seq": f[2], "distance": int(f[3]), "msgs": [], "push": [], "sorted": [], "work": None})
+        elif f[0] == "M":
+            qs[-1]["msgs"].append(f[1])
+        elif f[0] in ("P", "S"):
+            rec = (int(f[1]), int(f[2]), int(f[3]), f[4], f[5], f[6])
+            qs[-1]["push" if f[0] == "P" else "sorted"].append(rec)
+        elif f[0] == "W":
+            qs[-1]["work"] = tuple(int(x) for x in f[1:])
+    return qs
+
+
+def read_rec_tsv(path):
+    names, lens = [], []
+    for line in open(path):
+        n, l = line.split()
+        names.append(n)
+        lens.append(int(l) + 1)  # util.h:201
+    return names, lens
+
+
+def params_from_flags(flags: str, search=False) -> HuntParams:
+    p = HuntParams()
+    if search:
+        p.maxmatches = 10000
+    t = flags.split()
+    i = 0
+    while i < len(t):
+        if t[i] == "-d":
+            p.distance = int(t[i + 1]); i += 2
+        elif t[i] == "-m":
+            p.maxmatches = int(t[i + 1]); i += 2
+        elif t[i] == "-x":
+            p.max_neighborhood = int(t[i + 1]); i += 2
+        elif t[i] == "-k":
+            p.seed_len = int(t[i + 1]); i += 2
+        elif t[i] == "-n":
+            p.hamming = True; i += 1
+        elif t[i] == "-f":
+            p.forward_only = True; i += 1
+        else:
+            i += 1
+    return p
+
+
+HUNT_CASES = [
+    ("cfg1_d0", "t1m"), ("t1m_e1", "t1m"), ("t1m_h1", "t1m"), ("t1m_h2", "t1m"), ("t1m_e2", "t1m"),
+    ("t1m_e1_fwd", "t1m"), ("t1m_e0", "t1m"), ("stress_e1", "stress"), ("stress_h1", "stress"),
+    ("stress_e1_m7", "stress"), ("stress_h2_m50", "stress"), ("stress_e2", "stress"),
+]
