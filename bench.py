@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- primers/s of the `dicey hunt` hot path on the synthetic 3 Gb reference.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+Workload (BASELINE.json metric: "primers/sec (3 Gb ref, edit-dist 1)"): 24 x 125 Mb iid-uniform
+ACGT records, 1,000,000 20-mers per GPU (half planted with <= 1 edit, half random),
+edit distance 1, both strands, dicey defaults (-m 1000 -x 10000).  One step = one pass of the whole
+hot path (prepare, neighbour search, antichain filter, locate, NW verify) over the batch.
+The index is replicated per GPU and the primer batch is sharded by rank (weak scaling: every rank
+runs 1 M primers); `value` counts the primers of all ranks.
+
+Keys beyond the base contract:
+  roofline      k_search (the dominant kernel): algorithmic bytes of SURVEY.md 8(d),
+                32 R + 32 L + 4 H + X per primer taken from the instrumented reference run on the
+                same index, x primers per launch / CUDA-event duration of that kernel
+  cpu_baseline  the reference (oracle/_ref/dicey_ref: verbatim SDSL / neighbors.h / needle.h) on the
+                host cores, on a bounded sample of the same primers over the same 3 Gb index
+  e2e           the same metric through the C ABI (dg_hunt_batch) with pinned host buffers:
+                H2D of the queries and D2H of every hit record inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")
+SEED = 42
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--primers", type=int, default=1_000_000, help="primers per GPU per step")
+    ap.add_argument("--length", type=int, default=20)
+    ap.add_argument("--distance", type=int, default=1)
+    ap.add_argument("--hamming", action="store_true")
+    ap.add_argument("--nrec", type=int, default=24)
+    ap.add_argument("--reclen", type=int, default=125_000_000)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: primers per step (0 = auto)")
+    ap.add_argument("--fm9-dir", default=None)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_primers(args, rank: int) -> np.ndarray:
+    from dicey_b200 import synth
+    return synth.primers_fast(SEED, args.nrec, args.reclen, args.primers, args.length, args.distance,
+                              not args.hamming, rng_seed=7 + rank)
+
+
+def write_sample(path: str, primers: np.ndarray):
+    with open(path, "wb") as f:
+        f.write(b"\n".join(bytes(row) for row in primers) + b"\n")
+
+
+def run_ref(fm9: str, rec: str, qfile: str, args, threads: int, counters: bool) -> dict:
+    cmd = [REF_BIN, "hunt", fm9, rec, qfile, "-d", str(args.distance), "--threads", str(threads)]
+    if args.hamming:
+        cmd.append("-n")
+    if counters:
+        cmd.append("--counters")
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def workload_name(args) -> str:
+    gb = args.nrec * args.reclen / 1e9
+    mode = "hamming" if args.hamming else "edit"
+    return (f"dicey hunt: {args.primers} {args.length}-mers per GPU, {mode}-distance {args.distance}, both strands, "
+            f"{gb:.3g} Gb synthetic reference ({args.nrec} x {args.reclen} bp)")
+
+
+def build_index(args, device: int):
+    from dicey_b200.api import Index
+    t0 = time.time()
+    ix = Index.build_synthetic(SEED, args.nrec, args.reclen, device)
+    return ix, time.time() - t0
+
+
+def ensure_fm9(ix, args) -> tuple[str, str, float]:
+    d = args.fm9_dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    fm9 = os.path.join(d, f"dicey_b200_bench_{args.nrec}x{args.reclen}.fm9")
+    rec = fm9 + ".rec.tsv"
+    t0 = time.time()
+    ix.write_fm9(fm9)
+    with open(rec, "w") as f:
+        for i in range(args.nrec):
+            f.write(f"chr{i + 1}\t{args.reclen}\n")
+    return fm9, rec, time.time() - t0
+
+
+def cpu_leg(fm9, rec, primers, args, cores, seconds):
+    """Reference on the host cores over a bounded sample; returns (primers/s, sample size, counters)."""
+    tmp = tempfile.mkdtemp(prefix="dicey_b200_cpu_")
+    probe_n = min(len(primers), 64 * cores)
+    qf = os.path.join(tmp, "probe.txt")
+    write_sample(qf, primers[:probe_n])
+    r = run_ref(fm9, rec, qf, args, cores, False)
+    rate = max(r["queries_per_s"], 1e-9)
+    n = int(min(len(primers), max(probe_n, rate * seconds)))
+    write_sample(qf, primers[:n])
+    r = run_ref(fm9, rec, qf, args, cores, True)
+    return r, n
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dicey_ref has not been built"}))
+        return 0
+    cores = os.cpu_count() or 1
+    ix, _ = build_index(args, int(os.environ.get("LOCAL_RANK", "0")))
+    fm9, rec, _ = ensure_fm9(ix, args)
+    ix.close()
+    primers = make_primers(args, 0)
+    tmp = tempfile.mkdtemp(prefix="dicey_b200_ref_")
+    sample = args.ref_sample
+    if not sample:
+        qf = os.path.join(tmp, "probe.txt")
+        write_sample(qf, primers[:32 * cores])
+        rate = max(run_ref(fm9, rec, qf, args, cores, False)["queries_per_s"], 1e-9)
+        sample = int(max(32 * cores, min(len(primers) // max(1, args.steps + args.warmup), rate * 8.0)))
+    loop_s, done = 0.0, 0
+    for step in range(args.warmup + args.steps):
+        lo = (step * sample) % max(1, len(primers) - sample)
+        qf = os.path.join(tmp, f"step{step}.txt")
+        write_sample(qf, primers[lo:lo + sample])
+        r = run_ref(fm9, rec, qf, args, cores, False)
+        if step >= args.warmup:
+            loop_s += r["loop_s"]
+            done += r["queries"]
+    value = done / loop_s if loop_s > 0 else 0.0
+    sample_desc = f"{sample} primers per step of the same primer set and 3 Gb index; per-primer loop only (index load excluded)"
+    line = {
+        "impl": "reference", "metric": "primers/sec (3 Gb ref, edit-dist 1)", "value": value, "unit": "primers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop_s / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "threads": cores},
+        "cpu_baseline": {"value": value, "unit": "primers/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "primers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from dicey_b200.api import HuntParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (dicey_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    ix, build_s = build_index(args, local)
+    info = ix.info()
+    params = HuntParams(distance=args.distance, hamming=args.hamming)
+    primers = make_primers(args, rank)
+    nq = primers.shape[0]
+    # pinned host copies of the inputs
+    pin = torch.empty(primers.size, dtype=torch.uint8, pin_memory=True)
+    pin.numpy()[:] = primers.reshape(-1)
+    off_pin = torch.empty(nq + 1, dtype=torch.int64, pin_memory=True)
+    off_pin.numpy()[:] = np.arange(nq + 1, dtype=np.int64) * args.length
+    seqs = (pin.numpy(), off_pin.numpy().view(np.uint64))
+
+    stream = torch.cuda.ExternalStream(ix.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: queries staged once, every kernel per step
+    batch = ix.stage(seqs, params)
+    for _ in range(args.warmup):
+        batch.run()
+        batch.summary()
+    ix.profile(True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    profs = []
+    for _ in range(args.steps):
+        batch.run()
+        batch.summary()          # synchronises the index stream; collects the stage timings
+        profs.append(ix.last_profile())
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    nhits, ncand = batch.summary()
+    ix.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * nq * args.steps / (ms / 1e3)
+    batch.free()
+
+    # ---------------- end-to-end arm: host buffers through dg_hunt_batch
+    for _ in range(min(args.warmup, 2)):
+        res = ix.hunt(seqs, params)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        res = ix.hunt(seqs, params)
+        d2h = res.hits.nbytes + res.pool.nbytes + res.qoff.nbytes + res.status.nbytes + res.dist.nbytes + res.seqs.nbytes
+        if world > 1:
+            # the hit all-gather of SURVEY.md 8(e): counts, then padded hit records, over NCCL
+            cnt = torch.tensor([len(res.hits)], dtype=torch.int64, device="cuda")
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt)
+            mx = int(max(int(c.item()) for c in cnts))
+            buf = torch.zeros(mx * res.hits.dtype.itemsize, dtype=torch.uint8, device="cuda")
+            mine = torch.from_numpy(res.hits.view(np.uint8).reshape(-1))
+            buf[:mine.numel()].copy_(mine, non_blocking=True)
+            allb = torch.empty(world * buf.numel(), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allb, buf)
+            if rank == 0:
+                _ = allb.cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * nq * args.steps / e2e_s
+    h2d = int(pin.numel() + off_pin.numel() * 8)
+
+    # ---------------- CPU reference beside it (rank 0, single GPU run only) + roofline numerator
+    cpu = None
+    work = None
+    if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(REF_BIN):
+        try:
+            fm9, rec, write_s = ensure_fm9(ix, args)
+            cores = os.cpu_count() or 1
+            r, n = cpu_leg(fm9, rec, primers, args, cores, args.cpu_seconds)
+            cpu = {"value": r["queries_per_s"], "unit": "primers/s", "cores": cores, "kind": "reference",
+                   "sample": f"first {n} primers of the batch on the same 3 Gb index ({r['loop_s']:.1f} s loop, index load excluded)"}
+            work = {k: r[k] / r["queries"] for k in ("R", "L", "H", "X", "strings", "steps")}
+            try:
+                os.remove(fm9); os.remove(fm9 + "_check")
+            except OSError:
+                pass
+        except Exception as e:  # the bench line must still be printed
+            cpu = {"value": None, "unit": "primers/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    if work is None:
+        # SURVEY.md 8(d) expectation for 20-mers at edit distance 1 on 3 Gb (used only when the
+        # reference could not be run, e.g. under torchrun N > 1; the N = 1 run measures it)
+        fallback = os.path.join(ROOT, "profiles", "work_counters.json")
+        try:
+            work = json.load(open(fallback))[f"{'h' if args.hamming else 'e'}{args.distance}"]
+        except Exception:
+            work = None
+
+    ms_search = float(np.mean([p["ms_search"] for p in profs])) if profs else None
+    roof = None
+    if work and ms_search:
+        alg = (32 * work["R"] + 32 * work["L"] + 4 * work["H"] + work["X"]) * nq
+        achieved = alg / (ms_search / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_primer": alg / nq, "kernel_ms": ms_search,
+                "kernel_share_of_step": ms_search / (ms / args.steps)}
+        tr = os.path.join(ROOT, "profiles", "k_search_traffic.json")
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    if rank == 0:
+        stage = {k: float(np.mean([p[k] for p in profs])) for k in ("ms_prepare", "ms_search", "ms_filter", "ms_locate", "ms_verify", "ms_total")}
+        line = {
+            "metric": "primers/sec (3 Gb ref, edit-dist 1)", "value": value, "unit": "primers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded",
+                       "global_primers_per_step": world * nq, "l2": "inputs larger than L2: 7 GB index, random access",
+                       "kmer_table_K": info["kmer"], "index_device_bytes": info["device_bytes"],
+                       "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "primers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(sum(p["launches"] for p in profs)),
+            "stages_ms": stage,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <deque>
+#include <queue>
 #include <thrust/iterator/counting_iterator.h>
 
 #include "dg_common.cuh"
@@ -731,9 +733,312 @@ int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, d
 
 }  // namespace dg
 
+// ================================================================================================
+// .fm9 writer: store_to_checked_file (index.h:122 -> io.hpp:814-828) of a csa_wt<> whose wavelet
+// tree, rank blocks, samples and alphabet are rebuilt from the device index.  The Huffman shape
+// follows _huff_shape::construct_tree (wt_huff.hpp:72-100) and _byte_tree's BFS numbering
+// (wt_helper.hpp:199-269) so that the written bytes equal SDSL's, except for the two
+// select_support_mcl sections, which are written empty (arg_cnt = 0, select_support_mcl.hpp:470-476)
+// because count / locate / extract never touch them.
 namespace dg {
-int write_fm9(dg_index*, const char*) {
-  set_error("dg_index_write_fm9: not built yet");
-  return DG_ERR_UNSUPPORTED;
+namespace {
+
+struct WtShape {            // device-side description of the tree for k_wt_bits
+  int n_internal;           // internal nodes, numbered 0..n_internal-1 in BFS order among internals
+  uint64_t bv_pos[8];       // start of each internal node's bit vector
+  uint8_t path_len[256];    // per byte symbol
+  uint8_t path_node[256][8];// internal node visited at depth d
+  uint8_t path_bit[256][8]; // branch taken at depth d
+  uint8_t member[8][8];     // member[v][k]: k-th symbol class (0..3 ACGT, 4.. rare list) lies under v
+  uint8_t rare_sym[4];      // byte values of the rare classes 4..7
+  int n_rare;
+};
+
+// one thread per occurrence block: appends the block's 64 symbols to every internal node on
+// their paths; bits are staged per node and flushed with one atomicOr per touched word
+__global__ void k_wt_bits(IndexView ix, WtShape sh, uint64_t nblocks, unsigned long long* __restrict__ bv) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  uint64_t base = b << 6;
+  if (base >= ix.n) return;
+  OccBlock blk = load_block(ix.occ + b);
+  // class counts before the block
+  uint64_t cls[8];
+  for (int c = 0; c < 4; ++c) cls[c] = blk.cnt[c];
+  for (int k = 0; k < sh.n_rare; ++k) {
+    uint8_t s = sh.rare_sym[k];
+    uint32_t a = ix.rare_off[s], e = ix.rare_off[s + 1];
+    cls[4 + k] = lower_bound_u32(ix.rare_pos, a, e, (uint32_t)base) - a;
+  }
+  uint64_t at[8];          // next bit position per internal node
+  unsigned long long acc[8];
+  for (int v = 0; v < sh.n_internal; ++v) {
+    uint64_t cnt = 0;
+    for (int k = 0; k < 4 + sh.n_rare; ++k) if (sh.member[v][k]) cnt += cls[k];
+    at[v] = sh.bv_pos[v] + cnt;
+    acc[v] = 0;
+  }
+  bool flagged = region_flag(ix, base);
+  uint32_t ek = flagged ? lower_bound_u32(ix.exc_pos, 0, ix.n_exc, (uint32_t)base) : 0;
+  for (int o = 0; o < 64; ++o) {
+    uint64_t i = base + o;
+    if (i >= ix.n) break;
+    uint8_t s = code_base((int)(((blk.hi >> o) & 1) << 1 | ((blk.lo >> o) & 1)));
+    if (flagged && ek < ix.n_exc && ix.exc_pos[ek] == (uint32_t)i) { s = ix.exc_sym[ek]; ++ek; }
+    int len = sh.path_len[s];
+    for (int d = 0; d < len; ++d) {
+      int v = sh.path_node[s][d];
+      uint64_t pos = at[v]++;
+      if (sh.path_bit[s][d]) acc[v] |= 1ULL << (pos & 63);
+      if ((pos & 63) == 63) {  // word complete: flush
+        if (acc[v]) atomicOr(&bv[pos >> 6], acc[v]);
+        acc[v] = 0;
+      }
+    }
+  }
+  for (int v = 0; v < sh.n_internal; ++v)
+    if (acc[v]) atomicOr(&bv[(at[v] - 1) >> 6], acc[v]);
+}
+
+// rank_support_v<1> (rank_support_v.hpp:57-96): per 512-bit superblock the absolute count and the
+// seven 9-bit relative counts
+__global__ void k_sb_popc(const unsigned long long* __restrict__ bv, uint64_t nwords, uint64_t nsb, uint64_t* __restrict__ sbsum) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nsb) return;
+  uint64_t s = 0;
+  for (int t = 0; t < 8; ++t) { uint64_t w = 8 * k + t; if (w < nwords) s += __popcll(bv[w]); }
+  sbsum[k] = s;
+}
+__global__ void k_rank_blocks(const unsigned long long* __restrict__ bv, uint64_t nwords, uint64_t nsb,
+                              const uint64_t* __restrict__ sbabs, uint64_t* __restrict__ bb) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nsb) return;
+  uint64_t rel = 0, s = 0;
+  for (int t = 1; t <= 7; ++t) {
+    uint64_t w = 8 * k + t - 1;
+    if (w < nwords) s += __popcll(bv[w]);
+    if (8 * k + t <= nwords) rel |= s << (63 - 9 * t);
+  }
+  bb[2 * k] = sbabs[k];
+  bb[2 * k + 1] = rel;
+}
+
+struct PcNode { uint64_t freq, sym; uint64_t parent, child[2]; };
+const uint64_t kUndef = 0xFFFFFFFFFFFFFFFFULL;
+
+bool put(FILE* f, const void* p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+bool put_u64(FILE* f, uint64_t v) { return put(f, &v, 8); }
+bool put_int_vector(FILE* f, const uint64_t* words, uint64_t bits, uint8_t width) {
+  return put_u64(f, ((uint64_t)width << 56) | bits) && put(f, words, ((bits + 63) >> 6) * 8);
+}
+void pack_ints(const std::vector<uint32_t>& v, uint8_t width, std::vector<uint64_t>& out) {
+  uint64_t bits = (uint64_t)v.size() * width;
+  out.assign((bits + 63) >> 6, 0);
+  for (uint64_t i = 0; i < v.size(); ++i) {
+    uint64_t bit = i * width, w = bit >> 6, o = bit & 63;
+    out[w] |= (uint64_t)v[i] << o;
+    if (o + width > 64) out[w + 1] |= (uint64_t)v[i] >> (64 - o);
+  }
+}
+
+}  // namespace
+
+int write_fm9(dg_index* ix, const char* path) {
+  try {
+    DG_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    uint64_t n = ix->n;
+    // ---- symbol frequencies from C
+    std::vector<int> syms;
+    for (int s = 0; s < 256; ++s) if (ix->h_present[s]) syms.push_back(s);
+    int sigma = (int)syms.size();
+    std::vector<uint64_t> C(sigma + 1, 0), freq(256, 0);
+    for (int i = 0; i < sigma; ++i) C[i] = ix->h_Cb[syms[i]];
+    C[sigma] = n;
+    for (int i = 0; i < sigma; ++i) freq[syms[i]] = C[i + 1] - C[i];
+    if (sigma < 2) { set_error("alphabet too small to write"); return DG_ERR_UNSUPPORTED; }
+    // ---- Huffman shape (wt_huff.hpp:72-100)
+    std::vector<PcNode> tmp;
+    typedef std::pair<uint64_t, uint64_t> P;
+    std::priority_queue<P, std::vector<P>, std::greater<P>> pq;
+    for (int s = 0; s < 256; ++s)
+      if (freq[s] > 0) { pq.push(P(freq[s], tmp.size())); tmp.push_back(PcNode{freq[s], (uint64_t)s, kUndef, {kUndef, kUndef}}); }
+    while (pq.size() > 1) {
+      P v1 = pq.top(); pq.pop();
+      P v2 = pq.top(); pq.pop();
+      tmp[v1.second].parent = tmp.size();
+      tmp[v2.second].parent = tmp.size();
+      pq.push(P(v1.first + v2.first, tmp.size()));
+      tmp.push_back(PcNode{v1.first + v2.first, 0, kUndef, {v1.second, v2.second}});
+    }
+    // ---- BFS numbering (wt_helper.hpp:199-236)
+    size_t nn = tmp.size();
+    std::vector<Fm9Node> nodes(nn);
+    std::vector<uint64_t> nfreq(nn);
+    std::vector<uint64_t> tchild0(nn), tchild1(nn);
+    auto setnode = [&](size_t dst, const PcNode& src, uint16_t parent) {
+      nfreq[dst] = src.freq;
+      nodes[dst].bv_pos = 0;
+      nodes[dst].bv_pos_rank = src.sym;
+      nodes[dst].parent = parent;
+      tchild0[dst] = src.child[0];
+      tchild1[dst] = src.child[1];
+      nodes[dst].child[0] = nodes[dst].child[1] = 0xFFFF;
+    };
+    setnode(0, tmp.back(), 0xFFFF);
+    uint64_t bv_size = 0;
+    size_t node_cnt = 1;
+    std::deque<size_t> q;
+    q.push_back(0);
+    while (!q.empty()) {
+      size_t idx = q.front();
+      q.pop_front();
+      nodes[idx].bv_pos = bv_size;
+      bool internal = tchild0[idx] != kUndef;
+      if (internal) {
+        bv_size += nfreq[idx];
+        uint64_t ch[2] = {tchild0[idx], tchild1[idx]};
+        for (int k = 0; k < 2; ++k) {
+          setnode(node_cnt, tmp[ch[k]], (uint16_t)idx);
+          q.push_back(node_cnt);
+          nodes[idx].child[k] = (uint16_t)node_cnt++;
+        }
+      }
+    }
+    uint16_t c_to_leaf[256];
+    uint64_t pathv[256];
+    for (int i = 0; i < 256; ++i) c_to_leaf[i] = 0xFFFF;
+    for (size_t v = 0; v < nn; ++v) if (nodes[v].child[0] == 0xFFFF) c_to_leaf[(uint8_t)nodes[v].bv_pos_rank] = (uint16_t)v;
+    for (uint32_t c = 0, prev_c = 0; c < 256; ++c) {
+      if (c_to_leaf[c] != 0xFFFF) {
+        uint16_t v = c_to_leaf[c];
+        uint64_t pw = 0, pl = 0;
+        while (v != 0) {
+          pw <<= 1;
+          if (nodes[nodes[v].parent].child[1] == v) pw |= 1ULL;
+          ++pl;
+          v = nodes[v].parent;
+        }
+        pathv[c] = pw | (pl << 56);
+        prev_c = c;
+      } else {
+        pathv[c] = prev_c;
+      }
+    }
+    // ---- device description of the paths
+    WtShape sh;
+    memset(&sh, 0, sizeof(sh));
+    std::vector<int> internal_id(nn, -1);
+    for (size_t v = 0; v < nn; ++v)
+      if (nodes[v].child[0] != 0xFFFF) {
+        if (sh.n_internal >= 8) { set_error("alphabet too large for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
+        sh.bv_pos[sh.n_internal] = nodes[v].bv_pos;
+        internal_id[v] = sh.n_internal++;
+      }
+    int cls_of[256];
+    for (int i = 0; i < 256; ++i) cls_of[i] = -1;
+    cls_of['A'] = 0; cls_of['C'] = 1; cls_of['G'] = 2; cls_of['T'] = 3;
+    for (int s : syms)
+      if (cls_of[s] < 0) {
+        if (sh.n_rare >= 4) { set_error("alphabet too large for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
+        sh.rare_sym[sh.n_rare] = (uint8_t)s;
+        cls_of[s] = 4 + sh.n_rare++;
+      }
+    for (int s : syms) {
+      uint64_t pw = pathv[s] & ((1ULL << 56) - 1), pl = pathv[s] >> 56;
+      sh.path_len[s] = (uint8_t)pl;
+      uint16_t v = 0;
+      for (uint64_t d = 0; d < pl; ++d) {
+        int bit = (int)((pw >> d) & 1);
+        sh.path_node[s][d] = (uint8_t)internal_id[v];
+        sh.path_bit[s][d] = (uint8_t)bit;
+        sh.member[internal_id[v]][cls_of[s]] = 1;
+        v = nodes[v].child[bit];
+      }
+    }
+    // ---- wavelet tree bits + rank blocks on the device
+    uint64_t nwords = (bv_size + 63) >> 6;
+    uint64_t nsb = ((bv_size + 63) >> 9) + 1;
+    DevBuf<unsigned long long> d_bv;
+    DevBuf<uint64_t> d_sbsum, d_sbabs, d_bb;
+    d_bv.alloc(nwords + 8);
+    d_sbsum.alloc(nsb); d_sbabs.alloc(nsb); d_bb.alloc(2 * nsb);
+    DG_CUDA(cudaMemsetAsync(d_bv.p, 0, (nwords + 8) * 8, st));
+    uint64_t nblocks = (n + 63) >> 6;
+    k_wt_bits<<<grid_for(nblocks, 128), 128, 0, st>>>(ix->view(), sh, nblocks, d_bv.p);
+    k_sb_popc<<<grid_for(nsb, 256), 256, 0, st>>>(d_bv.p, nwords, nsb, d_sbsum.p);
+    {
+      Temp tmpb;
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, d_sbsum.p, d_sbabs.p, (int)nsb, st);
+      cub::DeviceScan::ExclusiveSum(tmpb.ensure(tb), tb, d_sbsum.p, d_sbabs.p, (int)nsb, st);
+      k_rank_blocks<<<grid_for(nsb, 256), 256, 0, st>>>(d_bv.p, nwords, nsb, d_sbabs.p, d_bb.p);
+      DG_CUDA(cudaGetLastError());
+      DG_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<uint64_t> bv(nwords), bb(2 * nsb);
+    DG_CUDA(cudaMemcpy(bv.data(), d_bv.p, nwords * 8, cudaMemcpyDeviceToHost));
+    DG_CUDA(cudaMemcpy(bb.data(), d_bb.p, 2 * nsb * 8, cudaMemcpyDeviceToHost));
+    d_bv.release();
+    // bv_pos_rank of internal nodes (wt_helper.hpp:272-279): rank1(bv_pos)
+    auto rank1 = [&](uint64_t idx) -> uint64_t {
+      const uint64_t* p = bb.data() + ((idx >> 8) & 0xFFFFFFFFFFFFFFFEULL);
+      uint64_t r = p[0] + ((p[1] >> (63 - 9 * ((idx & 0x1FF) >> 6))) & 0x1FF);
+      if (idx & 0x3F) r += (uint64_t)__builtin_popcountll(bv[idx >> 6] & ((1ULL << (idx & 0x3F)) - 1));
+      return r;
+    };
+    for (size_t v = 0; v < nn; ++v) if (nodes[v].child[0] != 0xFFFF) nodes[v].bv_pos_rank = rank1(nodes[v].bv_pos);
+    // ---- samples
+    uint64_t nsa = (n + kSaSample - 1) / kSaSample, nisa = (n - 1) / 64 + 1;
+    std::vector<uint32_t> sa(nsa), isa(nisa);
+    DG_CUDA(cudaMemcpy(sa.data(), ix->sa_samples.p, nsa * 4, cudaMemcpyDeviceToHost));
+    DG_CUDA(cudaMemcpy(isa.data(), ix->isa_samples.p, nisa * 4, cudaMemcpyDeviceToHost));
+    uint8_t width = 1;
+    while ((n >> width) != 0) ++width;  // bits::hi(n) + 1
+    std::vector<uint64_t> saw, isaw;
+    pack_ints(sa, width, saw);
+    sa.clear(); sa.shrink_to_fit();
+    pack_ints(isa, width, isaw);
+    // ---- file
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error(std::string("cannot create ") + path); return DG_ERR_IO; }
+    bool ok = put_u64(f, n) && put_u64(f, (uint64_t)sigma);
+    ok = ok && put_int_vector(f, bv.data(), bv_size, 1);
+    ok = ok && put_int_vector(f, bb.data(), (uint64_t)bb.size() * 64, 64);
+    ok = ok && put_u64(f, 0) && put_u64(f, 0);  // select_support_mcl<1>, <0>: arg_cnt = 0
+    ok = ok && put_u64(f, (uint64_t)nn);
+    for (size_t v = 0; ok && v < nn; ++v) {
+      uint8_t rec[22];
+      memcpy(rec, &nodes[v].bv_pos, 8);
+      memcpy(rec + 8, &nodes[v].bv_pos_rank, 8);
+      memcpy(rec + 16, &nodes[v].parent, 2);
+      memcpy(rec + 18, &nodes[v].child[0], 2);
+      memcpy(rec + 20, &nodes[v].child[1], 2);
+      ok = put(f, rec, 22);
+    }
+    ok = ok && put(f, c_to_leaf, sizeof(c_to_leaf)) && put(f, pathv, sizeof(pathv));
+    ok = ok && put_int_vector(f, saw.data(), (uint64_t)nsa * width, width);
+    ok = ok && put_int_vector(f, isaw.data(), (uint64_t)nisa * width, width);
+    // byte_alphabet (csa_alphabet_strategy.hpp:233-244)
+    uint64_t c2c[32];
+    memset(c2c, 0, sizeof(c2c));
+    for (int i = 0; i < sigma; ++i) ((uint8_t*)c2c)[syms[i]] = (uint8_t)i;
+    ok = ok && put_int_vector(f, c2c, 256 * 8, 8);
+    std::vector<uint64_t> comp((sigma * 8 + 63) / 64, 0);
+    for (int i = 0; i < sigma; ++i) ((uint8_t*)comp.data())[i] = (uint8_t)syms[i];
+    ok = ok && put_int_vector(f, comp.data(), (uint64_t)sigma * 8, 8);
+    ok = ok && put_int_vector(f, C.data(), (uint64_t)(sigma + 1) * 64, 64);
+    uint16_t sg = (uint16_t)sigma;
+    ok = ok && put(f, &sg, 2);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { set_error(std::string("write failed: ") + path); return DG_ERR_IO; }
+    FILE* c = fopen((std::string(path) + "_check").c_str(), "wb");
+    uint64_t h = fm9_type_hash();
+    if (!c || fwrite(&h, 8, 1, c) != 1) { if (c) fclose(c); set_error("cannot write the _check sidecar"); return DG_ERR_IO; }
+    fclose(c);
+    return DG_OK;
+  } catch (CudaFail& e) {
+    return e.code;
+  }
 }
 }  // namespace dg

@@ -35,7 +35,7 @@ struct BatchDev {
   uint32_t nq;
   uint32_t* status;
   uint32_t* dist;
-  uint32_t seed_len, distance, max_loc;
+  uint32_t seed_len, distance, max_loc, max_nbr;
   uint8_t indel, reverse;
 };
 
@@ -52,6 +52,7 @@ struct UnitTabs {
   const uint32_t* tab;      // packed (row + 1) << 12 | first   (row 0 = "no first event")
   const uint32_t* tab_off;  // 256 entries
   const uint32_t* tab_cnt;  // 256 entries: units per strand for query length m
+  const uint32_t* script_ub; // 256 entries: scripts per strand if every slot were valid (saturating)
 };
 
 namespace {
@@ -113,9 +114,23 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
     st |= DG_Q_DIST_ADJUSTED;
   }
   if (d > (uint32_t)kMaxDist || (b.seed_len && d >= b.seed_len)) st |= DG_Q_UNSUPPORTED;
+  bool run = !(st & (DG_Q_SKIPPED | DG_Q_TOO_SHORT | DG_Q_UNSUPPORTED));
+  if (run && m <= kMaxQuery) {
+    // neighbors.h:50 stops the DFS once the set holds max_neighborhood strings.  The set never
+    // holds more strings than scripts were generated, so fewer scripts than the cap certifies an
+    // untruncated neighbourhood.  Hamming sets hold exactly one string per script.
+    if (b.indel) {
+      if (ut.script_ub[m] >= b.max_nbr) st |= DG_Q_NBR_UNVERIFIED;
+    } else {
+      uint64_t w = 0, w2 = 0;  // per-position substitution choices: 3, or 4 at an 'N'
+      const uint8_t* s0 = fwd + o + (L - m);
+      for (int i = 0; i < m; ++i) { uint64_t c = base_code(s0[i]) < 4 ? 3 : 4; w += c; w2 += c * c; }
+      uint64_t size = 1 + (d >= 1 ? w : 0) + (d >= 2 ? (w * w - w2) / 2 : 0);
+      if (size >= b.max_nbr) st |= DG_Q_NBR_CAP;
+    }
+  }
   b.status[q] = st;
   b.dist[q] = d;
-  bool run = !(st & (DG_Q_SKIPPED | DG_Q_TOO_SHORT | DG_Q_UNSUPPORTED));
   units[q] = run ? (uint64_t)ut.tab_cnt[m] * (b.reverse ? 2 : 1) : 0;
 }
 
@@ -526,7 +541,7 @@ struct dg_batch {
   // inputs
   ABuf<uint8_t> raw, fwd, rc;
   ABuf<uint64_t> off, units, unit_off;
-  ABuf<uint32_t> status, dist, tab, tab_off, tab_cnt;
+  ABuf<uint32_t> status, dist, tab, tab_off, tab_cnt, script_ub;
   uint64_t uniform_units = 0;
   int max_len = 0, min_len = 0;
   // outputs of run()
@@ -546,6 +561,7 @@ static BatchDev batch_dev(const dg_batch* b) {
   BatchDev d;
   d.fwd = b->fwd.p; d.rc = b->rc.p; d.off = b->off.p; d.nq = b->nq; d.status = b->status.p; d.dist = b->dist.p;
   d.seed_len = b->par.seed_len; d.distance = b->par.distance; d.max_loc = b->par.max_locations;
+  d.max_nbr = b->par.max_neighborhood ? b->par.max_neighborhood : 10000;
   d.indel = b->par.indel; d.reverse = b->par.reverse;
   return d;
 }
@@ -587,18 +603,27 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     if (nq == 0) { minL = maxL = 0; }
     b->min_len = minL;
     b->max_len = maxL;
-    std::vector<uint32_t> tab, tab_off(256, 0), tab_cnt(256, 0), one;
+    std::vector<uint32_t> tab, tab_off(256, 0), tab_cnt(256, 0), sub(256, 0), one;
     for (int m = 1; m < 256; ++m) {
       if (!have[m]) continue;
       int d = std::min<int>((int)par->distance, m - 1);
       build_unit_table(m, d, par->indel != 0, one);
       tab_off[m] = (uint32_t)tab.size();
       tab_cnt[m] = (uint32_t)one.size();
+      {
+        int sl = slots_per_pos(par->indel != 0), E = sl * m;
+        uint64_t ub = 1 + (d >= 1 ? (uint64_t)E : 0);
+        if (d >= 2)
+          for (int e1 = 0; e1 < E; ++e1) ub += (uint64_t)(E - second_event_start(e1 / sl, e1 % sl, par->indel != 0));
+        sub[m] = ub > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)ub;
+      }
       tab.insert(tab.end(), one.begin(), one.end());
     }
     b->tab.alloc(tab.size(), st);
     b->tab_off.alloc(256, st);
     b->tab_cnt.alloc(256, st);
+    b->script_ub.alloc(256, st);
+    DG_CUDA(cudaMemcpyAsync(b->script_ub.p, sub.data(), 256 * 4, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(b->tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(b->tab_off.p, tab_off.data(), 256 * 4, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(b->tab_cnt.p, tab_cnt.data(), 256 * 4, cudaMemcpyHostToDevice, st));
@@ -649,7 +674,7 @@ static int run_impl(dg_batch* b) {
     b->nhits = 0;
     b->ncand = 0;
     BatchDev bd = batch_dev(b);
-    UnitTabs ut{b->tab.p, b->tab_off.p, b->tab_cnt.p};
+    UnitTabs ut{b->tab.p, b->tab_off.p, b->tab_cnt.p, b->script_ub.p};
     IndexView v = ix->view();
     ABuf<uint8_t> tmp;
     size_t tmp_cap = 0;

@@ -75,3 +75,61 @@ HUNT_CASES = [
     ("t1m_e1_fwd", "t1m"), ("t1m_e0", "t1m"), ("stress_e1", "stress"), ("stress_h1", "stress"),
     ("stress_e1_m7", "stress"), ("stress_h2_m50", "stress"), ("stress_e2", "stress"),
 ]
+
+
+def fm9_sections(path):
+    """Byte ranges of a .fm9: dict name -> bytes."""
+    import struct
+    data = open(path, "rb").read()
+    pos = 0
+    out = {}
+
+    def int_vector():
+        nonlocal pos
+        (h,) = struct.unpack_from("<Q", data, pos)
+        bits = h & ((1 << 56) - 1)
+        n = 8 + ((bits + 63) >> 6) * 8
+        pos += n
+        return n
+
+    def select():
+        nonlocal pos
+        (cnt,) = struct.unpack_from("<Q", data, pos)
+        pos += 8
+        if cnt:
+            int_vector()
+            int_vector()
+            for _ in range((cnt + 4095) >> 12):
+                int_vector()
+
+    def take(name, fn):
+        nonlocal pos
+        a = pos
+        fn()
+        out[name] = data[a:pos]
+
+    def hdr():
+        nonlocal pos
+        pos += 16
+
+    def tree():
+        nonlocal pos
+        (nn,) = struct.unpack_from("<Q", data, pos)
+        pos += 8 + nn * 22 + 256 * 2 + 256 * 8
+
+    def alphabet():
+        nonlocal pos
+        int_vector(); int_vector(); int_vector()
+        pos += 2
+
+    take("header", hdr)
+    take("bv", int_vector)
+    take("rank", int_vector)
+    take("select1", select)
+    take("select0", select)
+    take("tree", tree)
+    take("sa", int_vector)
+    take("isa", int_vector)
+    take("alphabet", alphabet)
+    assert pos == len(data), (pos, len(data))
+    return out
