@@ -133,10 +133,11 @@ def _check(rc: int) -> None:
 
 
 def _from_ptr(ptr, nbytes: int, dtype) -> np.ndarray:
+    """Zero-copy view of library-owned memory (the owner must outlive the array)."""
     if not ptr or nbytes == 0:
         return np.zeros(0, dtype=dtype)
     buf = (C.c_uint8 * nbytes).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype).copy()
+    return np.frombuffer(buf, dtype=dtype)
 
 
 def pack_sequences(seqs) -> tuple[np.ndarray, np.ndarray]:
@@ -171,9 +172,25 @@ class HuntParams:
 class HuntResult:
     """Hits of one batch in the reference's push order (hunter.h:349-433)."""
 
-    def __init__(self, hits, qoff, status, dist, pool, seqs, seq_off):
+    def __init__(self, hits, qoff, status, dist, pool, seqs, seq_off, handle=None):
         self.hits, self.qoff, self.status, self.dist = hits, qoff, status, dist
         self.pool, self.seqs, self.seq_off = pool, seqs, seq_off
+        self._res = handle  # the arrays above are views into this dg_result
+
+    def close(self) -> None:
+        if self._res:
+            h, self._res = self._res, None
+            self.hits = self.hits.copy(); self.qoff = self.qoff.copy(); self.status = self.status.copy()
+            self.dist = self.dist.copy(); self.pool = self.pool.copy(); self.seqs = self.seqs.copy()
+            library().dg_result_free(h)
+
+    def __del__(self):
+        if getattr(self, "_res", None):
+            try:
+                library().dg_result_free(self._res)
+            except Exception:
+                pass
+            self._res = None
 
     @property
     def nq(self) -> int:
@@ -318,7 +335,7 @@ class Index:
         pool = _from_ptr(pp, nb.value, np.uint8)
         sp = lib.dg_result_sequences(res, C.byref(nb))
         seqs = _from_ptr(sp, nb.value, np.uint8)
-        return HuntResult(hits, qoff, status, dist, pool, seqs, seq_off)
+        return HuntResult(hits, qoff, status, dist, pool, seqs, seq_off, res)
 
     def hunt(self, seqs, params: HuntParams | None = None) -> HuntResult:
         """hunter.h:289-433 for every query of the batch (one library call, host buffers)."""
@@ -327,10 +344,7 @@ class Index:
         res = C.c_void_p()
         p = params.to_c()
         _check(library().dg_hunt_batch(self._h, buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(p), C.byref(res)))
-        try:
-            return self._collect(res, off)
-        finally:
-            library().dg_result_free(res)
+        return self._collect(res.value, off)
 
     def stage(self, seqs, params: HuntParams | None = None) -> "Batch":
         params = params or HuntParams()
@@ -376,10 +390,7 @@ class Batch:
     def fetch(self) -> HuntResult:
         res = C.c_void_p()
         _check(library().dg_batch_fetch(self._h, C.byref(res)))
-        try:
-            return self.index._collect(res, self.off)
-        finally:
-            library().dg_result_free(res)
+        return self.index._collect(res.value, self.off)
 
     def free(self) -> None:
         if self._h:

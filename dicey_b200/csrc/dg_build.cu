@@ -513,6 +513,14 @@ static dg_index* new_index(int device) {
   dg_index* ix = new dg_index();
   ix->device = device;
   DG_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  {
+    // batch temporaries come from the stream-ordered pool: keep freed memory in the pool instead
+    // of returning it to the driver at every synchronisation
+    cudaMemPool_t pool;
+    DG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ULL;
+    DG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
   ix->cum.alloc(1);
   DG_CUDA(cudaMemset(ix->cum.p, 0, 8));
   return ix;

@@ -240,11 +240,6 @@ DG_HD bool script_rtl(const uint8_t* base, int m, const Script& sc, F&& f) {
       if (!f(code_base(sc.k[ev] - 5))) return false;
       --ev;
     }
-    if (ev < 0 && p > 0) {
-      // no events left: the rest is the unedited prefix
-      for (int t = p - 1; t >= 0; --t) if (!f(base[t])) return false;
-      return true;
-    }
   }
   return true;
 }
@@ -331,31 +326,48 @@ DG_HD bool is_minimal(const uint8_t* q, int m, int d, const uint8_t* t, int L, u
 // ------------------------------------------------------------------------------------------
 // needle() for std::string x std::string, AlignConfig<false,true>, DnaScore(0,-1,-1,-1)
 // (needle.h:59-138, align.h:52-80): rows = genomic g (length mg), columns = query s (length n).
-// trace: caller scratch of >= ((mg+1)*(n+1)+3)/4 bytes (2 bits per cell: 1 = bit3, 2 = bit4);
+// tr: trace storage (TraceBytes: >= ((mg+1)*(n+1)+3)/4 bytes; TraceRows64: mg+1 words, n <= 31);
 // srow: >= n+1 ints; ops: >= mg+n bytes.  Outputs the alignment with leading / trailing
 // query-gap columns stripped (hunter.h:391-401), the number of stripped leading columns, and
 // the score.  Returns the number of kept columns.
-DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, uint8_t* trace, int* srow,
+// Trace storage: 2 bits per DP cell (1 = bit3 "left", 2 = bit4 "up", 0 = diagonal).
+struct TraceBytes {   // any size: (mg+1)*(n+1) cells packed 4 per byte in caller memory
+  uint8_t* t;
+  int mf;
+  DG_HD void set(int row, int col, int v) {
+    int cell = row * mf + col, sh = (cell & 3) * 2;
+    t[cell >> 2] = (uint8_t)((t[cell >> 2] & ~(3 << sh)) | (v << sh));
+  }
+  DG_HD int get(int row, int col) const {
+    int cell = row * mf + col;
+    return (t[cell >> 2] >> ((cell & 3) * 2)) & 3;
+  }
+};
+struct TraceRows64 {  // n <= 31: one 64-bit word per DP row (thread-local array)
+  uint64_t* w;
+  DG_HD void set(int row, int col, int v) {
+    w[row] = (w[row] & ~(3ULL << (2 * col))) | ((uint64_t)v << (2 * col));
+  }
+  DG_HD int get(int row, int col) const { return (int)((w[row] >> (2 * col)) & 3); }
+};
+
+template <typename Tr>
+DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, Tr tr, int* srow,
                        uint8_t* ops, uint8_t* refalign, uint8_t* queryalign, int* lead_out, int* score_out) {
-  const int mf = n + 1;
-  auto setbits = [&](int cell, int v) {
-    int sh = (cell & 3) * 2;
-    trace[cell >> 2] = (uint8_t)((trace[cell >> 2] & ~(3 << sh)) | (v << sh));
-  };
-  auto getbits = [&](int cell) { return (trace[cell >> 2] >> ((cell & 3) * 2)) & 3; };
+  auto setbits = [&](int row, int col, int v) { tr.set(row, col, v); };
+  auto getbits = [&](int row, int col) { return tr.get(row, col); };
   int prevsub = 0;
   for (int row = 0; row <= mg; ++row) {
     for (int col = 0; col <= n; ++col) {
-      int cell = row * mf + col;
       if (row == 0 && col == 0) {
-        srow[0] = 0; prevsub = 0; setbits(cell, 0);
+        srow[0] = 0; prevsub = 0; setbits(row, col, 0);
       } else if (row == 0) {
         srow[col] = -col;            // _horizontalGap(AlignConfig<false,*>) = col * ge
-        setbits(cell, 1);
+        setbits(row, col, 1);
       } else if (col == 0) {
         srow[0] = 0;                 // _verticalGap(AlignConfig<*,true>, 0, n, ..) = 0
         prevsub = 0;
-        setbits(cell, 2);
+        setbits(row, col, 2);
       } else {
         int prevprevsub = prevsub;
         prevsub = srow[col];
@@ -366,7 +378,7 @@ DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, uint8_
         int v = diag > up ? diag : up;
         if (left > v) v = left;
         srow[col] = v;
-        setbits(cell, v == left ? 1 : (v == up ? 2 : 0));
+        setbits(row, col, v == left ? 1 : (v == up ? 2 : 0));
       }
     }
   }
@@ -374,7 +386,7 @@ DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, uint8_
   // traceback (needle.h:114-131): bit3 -> 'h', bit4 -> 'v', else 's'
   int row = mg, col = n, nops = 0;
   while (row > 0 || col > 0) {
-    int b = getbits(row * mf + col);
+    int b = getbits(row, col);
     if (b == 1) { --col; ops[nops++] = 'h'; }
     else if (b == 2) { --row; ops[nops++] = 'v'; }
     else { --row; --col; ops[nops++] = 's'; }
@@ -403,6 +415,23 @@ DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, uint8_
   *lead_out = lead;
   return kept;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Packed fast path: an ACGT-only string of length <= 31 as 2-bit codes, LAST base in the low
+// bits (so the low 2K bits are the K-mer table index and base t from the right is bits 2t..2t+1).
+// apply_event_packed applies one canonical event (k < 4 substitute code k, 4 delete, 5.. insert
+// code k-5 before the base) at right-based index j of the base it refers to.  Two events are
+// applied left one first: an edit never moves anything to its right.
+DG_HD uint64_t apply_event_packed(uint64_t code, int j, int k) {
+  int sh = 2 * j;
+  if (k < 4) return (code & ~(3ULL << sh)) | ((uint64_t)k << sh);
+  uint64_t low_excl = code & ((1ULL << sh) - 1);          // bases right of j
+  if (k == 4) return (((code >> sh) >> 2) << sh) | low_excl;
+  uint64_t low_incl = code & ((1ULL << (sh + 2)) - 1);     // base j and everything right of it
+  return (((code >> sh) >> 2) << (sh + 4)) | ((uint64_t)(k - 5) << (sh + 2)) | low_incl;
+}
+constexpr int kMaxPacked = 31;  // longest edited string the packed path handles
 
 // hunter.h:358-362 / silica.h:475-479: text position -> (refIndex, chrpos).
 DG_HD void locate_record(const uint64_t* cum, uint32_t nseq, uint64_t pos, uint32_t& refIndex, uint32_t& chrpos) {

@@ -19,6 +19,8 @@
 #include <cstring>
 #include <cub/cub.cuh>
 #include <map>
+#include <mutex>
+#include <new>
 
 #include "dg_common.cuh"
 
@@ -37,6 +39,10 @@ struct BatchDev {
   uint32_t* dist;
   uint32_t seed_len, distance, max_loc, max_nbr;
   uint8_t indel, reverse;
+  uint64_t* qcode;          // 2 per query: packed forward / reverse-complement search string
+  uint8_t* qflag;           // bit0 = ACGT only ("clean"), bit1 = packed code valid
+  uint32_t* irregular;      // set when any query departs from the uniform batch shape
+  uint32_t uniform_len;     // common raw length of the batch (0 = mixed lengths)
 };
 
 DG_HD void query_geom(const BatchDev& b, uint32_t q, int strand, const uint8_t*& base, int& m, int& koff) {
@@ -47,12 +53,32 @@ DG_HD void query_geom(const BatchDev& b, uint32_t q, int strand, const uint8_t*&
   base = strand == 0 ? b.fwd + o + koff : b.rc + o;
 }
 
+// Script enumeration.  A "clean" (ACGT-only) query enumerates 3 substitutions per position (the
+// three other letters), a query holding 'N' enumerates 4 (neighbors.h:61-69 substitutes every
+// alphabet letter different from the base); edit mode adds 1 deletion + 4 insertions per position.
+DG_HD int enum_slots(bool indel, bool clean) { return indel ? (clean ? 8 : 9) : (clean ? 3 : 4); }
+DG_HD bool enum_is_ins(bool indel, bool clean, int kk) { return indel && kk >= (clean ? 4 : 5); }
+// enumeration slot kk at a position whose base has 2-bit code bc (4 = not ACGT) -> canonical k
+// (0..3 substitute that letter, 4 delete, 5..8 insert); false if the slot is not a real edit
+DG_HD bool enum_to_canonical(bool clean, int kk, int bc, int& k) {
+  if (clean) {
+    if (kk < 3) { k = (bc + 1 + kk) & 3; return true; }
+    k = kk + 1;  // 3 -> delete (4), 4..7 -> insert (5..8)
+    return true;
+  }
+  k = kk;
+  return !(kk < 4 && kk == bc);
+}
+
 // Per-length unit tables: a "unit" is a group of <= 32 consecutive scripts run by one warp.
+// Row 0 holds the single-event scripts (preceded by the unedited string unless edit mode with
+// d >= 1, where the query itself can never be substring-minimal); row e1 + 1 holds the pairs
+// whose first event is enumeration slot e1.
 struct UnitTabs {
-  const uint32_t* tab;      // packed (row + 1) << 12 | first   (row 0 = "no first event")
-  const uint32_t* tab_off;  // 256 entries
-  const uint32_t* tab_cnt;  // 256 entries: units per strand for query length m
-  const uint32_t* script_ub; // 256 entries: scripts per strand if every slot were valid (saturating)
+  const uint32_t* tab;       // packed (row << 12) | first index
+  const uint32_t* tab_off;   // [2][256]: variant 0 = clean, 1 = with 'N'
+  const uint32_t* tab_cnt;   // [2][256]: units per strand for search-string length m
+  const uint32_t* script_ub; // 256 entries: scripts per strand (9- / 4-slot count, saturating)
 };
 
 namespace {
@@ -115,23 +141,39 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   }
   if (d > (uint32_t)kMaxDist || (b.seed_len && d >= b.seed_len)) st |= DG_Q_UNSUPPORTED;
   bool run = !(st & (DG_Q_SKIPPED | DG_Q_TOO_SHORT | DG_Q_UNSUPPORTED));
-  if (run && m <= kMaxQuery) {
+  bool clean = true;
+  uint64_t cf = 0, cr = 0;
+  if (run) {
+    // search strings: forward = last m bases, reverse = first m bases of the reverse complement
+    const uint8_t* s0 = fwd + o + (L - m);
+    const uint8_t* s1 = rc + o;
+    uint64_t w = 0, w2 = 0;  // per-position substitution choices: 3, or 4 at an 'N'
+    for (int i = 0; i < m; ++i) {
+      int c0 = base_code(s0[i]), c1 = base_code(s1[i]);
+      if (c0 == 4) clean = false;
+      uint64_t c = c0 < 4 ? 3 : 4;
+      w += c; w2 += c * c;
+      if (m <= 32) { cf = (cf << 2) | (uint64_t)(c0 & 3); cr = (cr << 2) | (uint64_t)(c1 & 3); }
+    }
     // neighbors.h:50 stops the DFS once the set holds max_neighborhood strings.  The set never
     // holds more strings than scripts were generated, so fewer scripts than the cap certifies an
     // untruncated neighbourhood.  Hamming sets hold exactly one string per script.
     if (b.indel) {
       if (ut.script_ub[m] >= b.max_nbr) st |= DG_Q_NBR_UNVERIFIED;
     } else {
-      uint64_t w = 0, w2 = 0;  // per-position substitution choices: 3, or 4 at an 'N'
-      const uint8_t* s0 = fwd + o + (L - m);
-      for (int i = 0; i < m; ++i) { uint64_t c = base_code(s0[i]) < 4 ? 3 : 4; w += c; w2 += c * c; }
       uint64_t size = 1 + (d >= 1 ? w : 0) + (d >= 2 ? (w * w - w2) / 2 : 0);
       if (size >= b.max_nbr) st |= DG_Q_NBR_CAP;
     }
   }
+  bool packed = run && clean && (m + (int)d <= kMaxPacked);
+  b.qcode[2 * (uint64_t)q] = cf;
+  b.qcode[2 * (uint64_t)q + 1] = cr;
+  b.qflag[q] = (uint8_t)((clean ? 1 : 0) | (packed ? 2 : 0));
   b.status[q] = st;
   b.dist[q] = d;
-  units[q] = run ? (uint64_t)ut.tab_cnt[m] * (b.reverse ? 2 : 1) : 0;
+  int variant = clean ? 0 : 1;
+  units[q] = run ? (uint64_t)ut.tab_cnt[variant * 256 + m] * (b.reverse ? 2 : 1) : 0;
+  if (!run || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -144,6 +186,15 @@ struct SearchOut {
   unsigned long long* n_scripts;
 };
 
+__device__ __forceinline__ void step_acgt(const IndexView& ix, uint32_t& l, uint32_t& r, int c) {
+  OccBlock bl = load_block(ix.occ + (l >> 6));
+  uint32_t nl = ix.C4[c] + rank_in_block(ix, bl, l, c);
+  uint32_t nr;
+  if ((r >> 6) == (l >> 6)) nr = ix.C4[c] + rank_in_block(ix, bl, r, c);
+  else nr = ix.C4[c] + rank_acgt(ix, r, c);
+  l = nl; r = nr;
+}
+
 __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTabs ut, const uint64_t* __restrict__ unit_off,
                                                 uint64_t uniform_units, SearchOut out) {
   const uint32_t lane = threadIdx.x & 31;
@@ -151,13 +202,15 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t total = unit_off[b.nq];
   const bool indel = b.indel != 0;
-  const int nstrand = b.reverse ? 2 : 1;
+  const bool uniform = uniform_units != 0 && *b.irregular == 0;
+  const int K = (int)ix.K;
+  const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
   unsigned long long my_scripts = 0;
   for (uint64_t unit = warp; unit < total; unit += nwarps) {
     // unit -> (query, strand, local unit)
     uint32_t q;
     uint64_t local;
-    if (uniform_units) {
+    if (uniform) {
       q = (uint32_t)(unit / uniform_units);
       local = unit - (uint64_t)q * uniform_units;
     } else {
@@ -169,74 +222,107 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
       q = lo;
       local = unit - unit_off[q];
     }
+    const uint8_t flags = b.qflag[q];
+    const bool clean = flags & 1, packed = flags & 2;
     const uint8_t* base;
     int m, koff;
     query_geom(b, q, 0, base, m, koff);
-    uint32_t per_strand = ut.tab_cnt[m];
+    const int variant = clean ? 0 : 1;
+    uint32_t per_strand = ut.tab_cnt[variant * 256 + m];
     int strand = (int)(local / per_strand);
     uint32_t u = (uint32_t)(local - (uint64_t)strand * per_strand);
     if (strand) query_geom(b, q, 1, base, m, koff);
-    (void)nstrand;
-    uint32_t packed = ut.tab[ut.tab_off[m] + u];
-    int row = (int)(packed >> 12);          // 0 = no first event
-    int idx = (int)(packed & 0xFFF) + (int)lane;
+    uint32_t pk = ut.tab[ut.tab_off[variant * 256 + m] + u];
+    const int row = (int)(pk >> 12);          // 0 = singles (+ the unedited string)
+    int idx = (int)(pk & 0xFFF) + (int)lane;
     const int dq = (int)b.dist[q];
-    const int E = slots_per_pos(indel) * m;
+    const int S = enum_slots(indel, clean);
+    const int E = S * m;
+    const bool with_base = !(indel && dq >= 1);
+    uint64_t code = packed ? b.qcode[2 * (uint64_t)q + strand] : 0;
+    auto bcode = [&](int pos) -> int {
+      return packed ? (int)((code >> (2 * (m - 1 - pos))) & 3) : base_code(base[pos]);
+    };
     Script sc;
     sc.nev = 0; sc.pos[0] = sc.pos[1] = 0; sc.k[0] = sc.k[1] = 0;
     bool valid = true;
-    int e1 = 0, e2 = 0;
     if (row == 0) {
-      // index 0 = the unedited string, index s >= 1 = single event s-1
-      if (idx > 0) {
-        e1 = idx - 1;
-        valid = dq >= 1 && e1 < E && decode_event(base, m, indel, e1, sc.pos[0], sc.k[0]);
+      int e = with_base ? idx - 1 : idx;
+      if (e >= 0) {
+        valid = dq >= 1 && e < E;
+        if (valid) {
+          sc.pos[0] = e / S;
+          valid = enum_to_canonical(clean, e - sc.pos[0] * S, bcode(sc.pos[0]), sc.k[0]);
+        }
         sc.nev = 1;
       }
     } else {
-      e1 = row - 1;
-      e2 = idx;
-      valid = dq >= 2 && e2 < E && decode_event(base, m, indel, e1, sc.pos[0], sc.k[0]) &&
-              decode_event(base, m, indel, e2, sc.pos[1], sc.k[1]) && pair_ok(sc.pos[0], sc.k[0], sc.pos[1]);
+      int e1 = row - 1, e2 = idx;
+      valid = dq >= 2 && e2 < E;
+      if (valid) {
+        sc.pos[0] = e1 / S;
+        sc.pos[1] = e2 / S;
+        valid = enum_to_canonical(clean, e1 - sc.pos[0] * S, bcode(sc.pos[0]), sc.k[0]) &&
+                enum_to_canonical(clean, e2 - sc.pos[1] * S, bcode(sc.pos[1]), sc.k[1]) &&
+                pair_ok(sc.pos[0], sc.k[0], sc.pos[1]);
+      }
       sc.nev = 2;
     }
     if (!valid) continue;
     ++my_scripts;
     const int L = script_len(m, sc);
     if (L <= 0) continue;
-    const int K = (int)ix.K;
-    bool collecting = L >= K;
-    int cnt = 0;
-    uint32_t kc = 0;
     uint32_t l = 0, r = (uint32_t)ix.n;
-    bool alive = script_rtl(base, m, sc, [&](uint8_t x) -> bool {
-      if (collecting) {
-        int c = base_code(x);
-        if (c < 4) {
-          kc |= (uint32_t)c << (2 * cnt);
-          if (++cnt == K) {
-            uint2 iv = __ldg(&ix.kmer[kc]);
-            l = iv.x; r = iv.y;
-            collecting = false;
-            return l < r;
-          }
-          return true;
-        }
-        // a non-ACGT letter inside the last K: replay what was collected, then step normally
-        collecting = false;
-        for (int t = 0; t < cnt; ++t) {
-          backward_step(ix, l, r, code_base((int)((kc >> (2 * t)) & 3)));
-          if (l >= r) return false;
-        }
+    bool alive;
+    if (packed) {
+      // the edited string as one 64-bit code: table lookup on its low 2K bits, then one
+      // backward step per remaining base
+      for (int e = 0; e < sc.nev; ++e) code = apply_event_packed(code, m - 1 - sc.pos[e], sc.k[e]);
+      int t = 0;
+      if (L >= K) {
+        uint2 iv = __ldg(&ix.kmer[(uint32_t)code & kmask]);
+        l = iv.x; r = iv.y; t = K;
       }
-      backward_step(ix, l, r, x);
-      return l < r;
-    });
-    if (alive && l < r) {
+      while (l < r && t < L) {
+        step_acgt(ix, l, r, (int)((code >> (2 * t)) & 3));
+        ++t;
+      }
+      alive = l < r;
+    } else {
+      bool collecting = L >= K;
+      int cnt = 0;
+      uint32_t kc = 0;
+      alive = script_rtl(base, m, sc, [&](uint8_t x) -> bool {
+        if (collecting) {
+          int c = base_code(x);
+          if (c < 4) {
+            kc |= (uint32_t)c << (2 * cnt);
+            if (++cnt == K) {
+              uint2 iv = __ldg(&ix.kmer[kc]);
+              l = iv.x; r = iv.y;
+              collecting = false;
+              return l < r;
+            }
+            return true;
+          }
+          // a non-ACGT letter inside the last K: replay what was collected, then step normally
+          collecting = false;
+          for (int t = 0; t < cnt; ++t) {
+            backward_step(ix, l, r, code_base((int)((kc >> (2 * t)) & 3)));
+            if (l >= r) return false;
+          }
+        }
+        backward_step(ix, l, r, x);
+        return l < r;
+      }) && l < r;
+    }
+    if (alive) {
       unsigned int slot = atomicAdd(out.n_cand, 1u);
       if (slot < out.cap) {
+        const int cs = indel ? 9 : 4;  // canonical slot numbering carried by the candidate
         Cand c;
-        c.q = q; c.l = l; c.r = r; c.code = pack_script(strand, sc.nev, e1, e2);
+        c.q = q; c.l = l; c.r = r;
+        c.code = pack_script(strand, sc.nev, sc.pos[0] * cs + sc.k[0], sc.pos[1] * cs + sc.k[1]);
         out.cands[slot] = c;
       } else {
         atomicExch(out.overflow, 1u);
@@ -383,14 +469,17 @@ struct VerifyArgs {
   dg_hit* hits;
   uint8_t* pool;
   uint32_t pool_stride;      // bytes per hit in the pool
-  uint8_t* scratch;          // per-thread NW scratch
+  uint8_t* scratch;          // NW scratch for alignments too large for the thread-local path
   uint32_t scratch_stride;
   uint32_t trace_bytes, srow_ints;
   uint64_t first_hit;        // chunk start
   uint64_t chunk;            // hits in this launch
 };
 
-__global__ void k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
+constexpr int kLocalQ = 31;   // thread-local NW: query columns
+constexpr int kLocalG = 40;   // thread-local NW: genomic rows
+
+__global__ void __launch_bounds__(128) k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.chunk) return;
   uint64_t h = a.first_hit + t;
@@ -435,35 +524,41 @@ __global__ void k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
   out.strand = strand ? '-' : '+';
   out.aln_off = h * a.pool_stride;
   uint8_t* slot = a.pool + out.aln_off;
-  if (b.seed_len) {
-    // search: genomic context for the Tm gate + alignpos (silica.h:522-532)
-    uint8_t* scr = a.scratch + t * (uint64_t)a.scratch_stride;
-    int* srow = (int*)scr;
-    uint8_t* trace = scr + a.srow_ints * 4;
-    uint8_t* ops = trace + a.trace_bytes;
-    uint8_t* ra = ops + (mg + mq + 4);
-    uint8_t* qa = ra + (mg + mq + 4);
-    int lead = 0, score = 0;
-    needle_align(g, mg, base, mq, trace, srow, ops, ra, qa, &lead, &score);
-    for (int i = 0; i < mg; ++i) slot[i] = g[i];
-    out.aln_len = (uint32_t)mg;
+  if (b.seed_len || indel) {
+    int lead = 0, score = 0, kept = 0;
+    if (mq <= kLocalQ && mg <= kLocalG) {
+      // thread-local DP: one 64-bit trace word per row
+      uint64_t rows[kLocalG + 1];
+      int srow[kLocalQ + 1];
+      uint8_t ops[kLocalQ + kLocalG + 1], ra[kLocalQ + kLocalG + 1], qa[kLocalQ + kLocalG + 1];
+      uint8_t gl[kLocalG], ql[kLocalQ];
+      for (int i = 0; i < mg; ++i) gl[i] = g[i];
+      for (int i = 0; i < mq; ++i) ql[i] = base[i];
+      for (int i = 0; i <= mg; ++i) rows[i] = 0;
+      kept = needle_align(gl, mg, ql, mq, TraceRows64{rows}, srow, ops, ra, qa, &lead, &score);
+      if (!b.seed_len) for (int i = 0; i < kept; ++i) { slot[i] = ra[i]; slot[kept + i] = qa[i]; }
+    } else {
+      uint8_t* scr = a.scratch + t * (uint64_t)a.scratch_stride;
+      int* srow = (int*)scr;
+      uint8_t* trace = scr + a.srow_ints * 4;
+      uint8_t* ops = trace + a.trace_bytes;
+      uint8_t* ra = ops + (mg + mq + 4);
+      uint8_t* qa = ra + (mg + mq + 4);
+      kept = needle_align(g, mg, base, mq, TraceBytes{trace, mq + 1}, srow, ops, ra, qa, &lead, &score);
+      if (!b.seed_len) for (int i = 0; i < kept; ++i) { slot[i] = ra[i]; slot[kept + i] = qa[i]; }
+    }
     out.score = score;
-    out.start = chrpos;
-    out.alignpos = chrpos + (uint32_t)lead;
-  } else if (indel) {
-    uint8_t* scr = a.scratch + t * (uint64_t)a.scratch_stride;
-    int* srow = (int*)scr;
-    uint8_t* trace = scr + a.srow_ints * 4;
-    uint8_t* ops = trace + a.trace_bytes;
-    uint8_t* ra = ops + (mg + mq + 4);
-    uint8_t* qa = ra + (mg + mq + 4);
-    int lead = 0, score = 0;
-    int kept = needle_align(g, mg, base, mq, trace, srow, ops, ra, qa, &lead, &score);
-    for (int i = 0; i < kept; ++i) { slot[i] = ra[i]; slot[kept + i] = qa[i]; }
-    out.aln_len = (uint32_t)kept;
-    out.score = score;
-    out.start = chrpos + (uint32_t)lead + 1;  // hunter.h:399,402
-    out.alignpos = out.start;
+    if (b.seed_len) {
+      // search: genomic context for the Tm gate + alignpos (silica.h:522-532)
+      for (int i = 0; i < mg; ++i) slot[i] = g[i];
+      out.aln_len = (uint32_t)mg;
+      out.start = chrpos;
+      out.alignpos = chrpos + (uint32_t)lead;
+    } else {
+      out.aln_len = (uint32_t)kept;
+      out.start = chrpos + (uint32_t)lead + 1;  // hunter.h:399,402
+      out.alignpos = out.start;
+    }
   } else {
     // needleScore (hunter.h:79-88): mismatches over min(|genomic|, |query|)
     int score = 0;
@@ -479,6 +574,21 @@ __global__ void k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
     out.alignpos = out.start;
   }
   a.hits[h] = out;
+}
+
+// alignment pool compaction: strided slots -> back-to-back strings (fewer D2H bytes)
+__global__ void k_aln_bytes(const dg_hit* __restrict__ hits, uint64_t n, uint32_t per_hit_mult, uint64_t* __restrict__ len) {
+  uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < n) len[h] = (uint64_t)hits[h].aln_len * per_hit_mult;
+  if (h == n) len[h] = 0;
+}
+__global__ void k_compact_pool(dg_hit* __restrict__ hits, uint64_t n, const uint64_t* __restrict__ off,
+                               const uint8_t* __restrict__ src, uint8_t* __restrict__ dst) {
+  uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n) return;
+  uint64_t from = hits[h].aln_off, to = off[h], nb = off[h + 1] - off[h];
+  for (uint64_t i = 0; i < nb; ++i) dst[to + i] = src[from + i];
+  hits[h].aln_off = to;
 }
 
 __global__ void k_count(const Cand* __restrict__ cands, uint32_t n, unsigned long long* __restrict__ counts) {
@@ -501,17 +611,17 @@ __global__ void k_backward_search(IndexView ix, const uint8_t* __restrict__ seqs
   else { lout[q] = l; rout[q] = (uint64_t)l - 1; }  // SDSL reports an empty interval as r = l - 1 (r + 1 - l == 0)
 }
 
-// unit table of one query length (host)
-void build_unit_table(int m, int d, bool indel, std::vector<uint32_t>& tab) {
-  int E = slots_per_pos(indel) * m;
+// unit table of one search-string length (host)
+void build_unit_table(int m, int d, bool indel, bool clean, std::vector<uint32_t>& tab) {
+  int S = enum_slots(indel, clean), E = S * m;
+  bool with_base = !(indel && d >= 1);
   tab.clear();
-  int n0 = 1 + (d >= 1 ? E : 0);  // row 0: the unedited string + the single events
+  int n0 = (with_base ? 1 : 0) + (d >= 1 ? E : 0);  // row 0: (the unedited string +) the single events
   for (int s = 0; s < n0; s += 32) tab.push_back((0u << 12) | (uint32_t)s);
   if (d >= 2) {
-    int sl = slots_per_pos(indel);
     for (int e1 = 0; e1 < E; ++e1) {
-      int p1 = e1 / sl, k1 = e1 - p1 * sl;
-      int start = second_event_start(p1, k1, indel);
+      int p1 = e1 / S, kk = e1 - p1 * S;
+      int start = (enum_is_ins(indel, clean, kk) ? p1 : p1 + 1) * S;
       for (int s = start; s < E; s += 32) tab.push_back(((uint32_t)(e1 + 1) << 12) | (uint32_t)s);
     }
   }
@@ -524,12 +634,71 @@ void build_unit_table(int m, int d, bool indel, std::vector<uint32_t>& tab) {
 using namespace dg;
 
 // ============================================================================================
+// Host-side result storage.  Results fetched from the device land in page-locked memory (so the
+// D2H copies run at full PCIe rate); freed blocks are kept in a small process-wide cache because
+// cudaHostAlloc costs milliseconds.
+namespace {
+struct PinCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_blocks;
+  size_t cached = 0;
+  void* get(size_t need, size_t& cap) {
+    std::lock_guard<std::mutex> g(mu);
+    size_t best = free_blocks.size();
+    for (size_t i = 0; i < free_blocks.size(); ++i)
+      if (free_blocks[i].second >= need && (best == free_blocks.size() || free_blocks[i].second < free_blocks[best].second)) best = i;
+    if (best == free_blocks.size() || free_blocks[best].second > 4 * need + (1u << 20)) return nullptr;
+    void* p = free_blocks[best].first;
+    cap = free_blocks[best].second;
+    cached -= cap;
+    free_blocks.erase(free_blocks.begin() + best);
+    return p;
+  }
+  void put(void* p, size_t cap) {
+    std::lock_guard<std::mutex> g(mu);
+    if (cached + cap > (3ULL << 30) || free_blocks.size() >= 64) { cudaFreeHost(p); return; }
+    free_blocks.push_back({p, cap});
+    cached += cap;
+  }
+};
+PinCache g_pin;
+
+struct HostBuf {
+  void* p = nullptr;
+  size_t bytes = 0, cap = 0;
+  bool pinned = false;
+  HostBuf() = default;
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+  ~HostBuf() { release(); }
+  void alloc(size_t n, bool pin) {
+    release();
+    bytes = n;
+    if (!n) return;
+    if (pin) {
+      p = g_pin.get(n, cap);
+      if (!p) {
+        cap = n + (n >> 3) + 4096;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cudaGetLastError(); }
+      }
+      if (p) { pinned = true; return; }
+    }
+    p = malloc(n);
+    cap = n;
+    pinned = false;
+    if (!p) throw std::bad_alloc();
+  }
+  void release() {
+    if (p) { if (pinned) g_pin.put(p, cap); else free(p); }
+    p = nullptr; bytes = cap = 0; pinned = false;
+  }
+};
+}  // namespace
+
 struct dg_result {
-  std::vector<dg_hit> hits;
-  std::vector<uint64_t> qoff;
-  std::vector<uint32_t> status, dist;
-  std::vector<char> pool;
-  std::vector<char> seqs;
+  HostBuf hits, qoff, status, dist, pool, seqs;
+  uint64_t nhits = 0;
+  uint32_t nq = 0;
 };
 
 struct dg_batch {
@@ -541,7 +710,10 @@ struct dg_batch {
   // inputs
   ABuf<uint8_t> raw, fwd, rc;
   ABuf<uint64_t> off, units, unit_off;
-  ABuf<uint32_t> status, dist, tab, tab_off, tab_cnt, script_ub;
+  ABuf<uint32_t> status, dist, tab, tab_off, tab_cnt, script_ub, irregular;
+  ABuf<uint64_t> qcode;
+  ABuf<uint8_t> qflag;
+  uint32_t uniform_len = 0;
   uint64_t uniform_units = 0;
   int max_len = 0, min_len = 0;
   // outputs of run()
@@ -553,7 +725,9 @@ struct dg_batch {
   ABuf<uint64_t> qoff;
   ABuf<unsigned long long> counts;
   uint64_t nhits = 0;
+  uint64_t pool_bytes = 0;   // compacted alignment pool
   uint32_t pool_stride = 0;
+  ABuf<uint8_t> pool2;
   bool ran = false;
 };
 
@@ -562,6 +736,7 @@ static BatchDev batch_dev(const dg_batch* b) {
   d.fwd = b->fwd.p; d.rc = b->rc.p; d.off = b->off.p; d.nq = b->nq; d.status = b->status.p; d.dist = b->dist.p;
   d.seed_len = b->par.seed_len; d.distance = b->par.distance; d.max_loc = b->par.max_locations;
   d.max_nbr = b->par.max_neighborhood ? b->par.max_neighborhood : 10000;
+  d.qcode = b->qcode.p; d.qflag = b->qflag.p; d.irregular = b->irregular.p; d.uniform_len = b->uniform_len;
   d.indel = b->par.indel; d.reverse = b->par.reverse;
   return d;
 }
@@ -603,37 +778,45 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     if (nq == 0) { minL = maxL = 0; }
     b->min_len = minL;
     b->max_len = maxL;
-    std::vector<uint32_t> tab, tab_off(256, 0), tab_cnt(256, 0), sub(256, 0), one;
+    std::vector<uint32_t> tab, tab_off(512, 0), tab_cnt(512, 0), sub(256, 0), one;
+    const bool indel = par->indel != 0;
     for (int m = 1; m < 256; ++m) {
       if (!have[m]) continue;
       int d = std::min<int>((int)par->distance, m - 1);
-      build_unit_table(m, d, par->indel != 0, one);
-      tab_off[m] = (uint32_t)tab.size();
-      tab_cnt[m] = (uint32_t)one.size();
+      for (int variant = 0; variant < 2; ++variant) {
+        build_unit_table(m, d, indel, variant == 0, one);
+        tab_off[variant * 256 + m] = (uint32_t)tab.size();
+        tab_cnt[variant * 256 + m] = (uint32_t)one.size();
+        tab.insert(tab.end(), one.begin(), one.end());
+      }
       {
-        int sl = slots_per_pos(par->indel != 0), E = sl * m;
+        int sl = slots_per_pos(indel), E = sl * m;
         uint64_t ub = 1 + (d >= 1 ? (uint64_t)E : 0);
         if (d >= 2)
-          for (int e1 = 0; e1 < E; ++e1) ub += (uint64_t)(E - second_event_start(e1 / sl, e1 % sl, par->indel != 0));
+          for (int e1 = 0; e1 < E; ++e1) ub += (uint64_t)(E - second_event_start(e1 / sl, e1 % sl, indel));
         sub[m] = ub > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)ub;
       }
-      tab.insert(tab.end(), one.begin(), one.end());
     }
     b->tab.alloc(tab.size(), st);
-    b->tab_off.alloc(256, st);
-    b->tab_cnt.alloc(256, st);
+    b->tab_off.alloc(512, st);
+    b->tab_cnt.alloc(512, st);
     b->script_ub.alloc(256, st);
+    b->irregular.alloc(1, st);
     DG_CUDA(cudaMemcpyAsync(b->script_ub.p, sub.data(), 256 * 4, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(b->tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaMemcpyAsync(b->tab_off.p, tab_off.data(), 256 * 4, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaMemcpyAsync(b->tab_cnt.p, tab_cnt.data(), 256 * 4, cudaMemcpyHostToDevice, st));
-    // uniform batches map unit -> query by a division instead of a binary search
+    DG_CUDA(cudaMemcpyAsync(b->tab_off.p, tab_off.data(), 512 * 4, cudaMemcpyHostToDevice, st));
+    DG_CUDA(cudaMemcpyAsync(b->tab_cnt.p, tab_cnt.data(), 512 * 4, cudaMemcpyHostToDevice, st));
+    // uniform batches (one length, all ACGT, nothing skipped) map unit -> query by a division
+    // instead of a binary search; k_prepare clears the shortcut if any query is irregular
     bool uniform = nq > 0 && minL == maxL && maxL <= kMaxQuery &&
                    (par->seed_len ? (maxL > (int)par->seed_len) : (maxL >= 10)) && par->distance < (uint32_t)maxL;
     if (uniform) {
       int m = par->seed_len ? (int)par->seed_len : maxL;
       b->uniform_units = (uint64_t)tab_cnt[m] * (par->reverse ? 2 : 1);
+      b->uniform_len = (uint32_t)maxL;
     }
+    b->qcode.alloc(2 * (size_t)nq + 2, st);
+    b->qflag.alloc((size_t)nq + 1, st);
     b->raw.alloc(b->nbytes + 1, st);
     b->fwd.alloc(b->nbytes + 1, st);
     b->rc.alloc(b->nbytes + 1, st);
@@ -685,6 +868,7 @@ static int run_impl(dg_batch* b) {
     prof_mark(ix, 0);
     // ---- prepare
     DG_CUDA(cudaMemsetAsync(b->units.p, 0, ((size_t)nq + 1) * 8, st));
+    DG_CUDA(cudaMemsetAsync(b->irregular.p, 0, 4, st));
     if (nq) { k_prepare<<<grid_for(nq, B), B, 0, st>>>(b->raw.p, bd, b->fwd.p, b->rc.p, ut, b->units.p); ++launches; }
     {
       size_t tb = 0;
@@ -708,7 +892,10 @@ static int run_impl(dg_batch* b) {
     SearchOut so{b->cands.p, (uint32_t)cap64, ctr.p, ctr.p + 1, nscripts.p};
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ix->device);
-    if (nq) { k_search<<<nsm * 8, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so); ++launches; }
+    int per_sm = 0;
+    DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (nq) { k_search<<<nsm * per_sm, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so); ++launches; }
     prof_mark(ix, 2);
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
@@ -855,7 +1042,7 @@ static int run_impl(dg_batch* b) {
       a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
       a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);
       a.scratch_stride = (a.scratch_stride + 15) & ~15u;
-      bool need_scratch = b->par.indel || b->par.seed_len;
+      bool need_scratch = (b->par.indel || b->par.seed_len) && (maxq > kLocalQ || maxg > kLocalG);
       uint64_t chunk = nhits;
       if (need_scratch) {
         uint64_t budget = 1ULL << 30;
@@ -870,6 +1057,22 @@ static int run_impl(dg_batch* b) {
         k_verify<<<grid_for(a.chunk, 128), 128, 0, st>>>(v, bd, a);
         ++launches;
       }
+    }
+    b->pool_bytes = 0;
+    if (nhits) {
+      ABuf<uint64_t> alen, aoff;
+      alen.alloc(nhits + 1, st);
+      aoff.alloc(nhits + 1, st);
+      uint32_t mult = b->par.seed_len ? 1u : 2u;
+      k_aln_bytes<<<grid_for(nhits + 1, B), B, 0, st>>>(b->hits.p, nhits, mult, alen.p);
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, alen.p, aoff.p, (int)(nhits + 1), st);
+      cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, alen.p, aoff.p, (int)(nhits + 1), st);
+      DG_CUDA(cudaMemcpyAsync(&b->pool_bytes, aoff.p + nhits, 8, cudaMemcpyDeviceToHost, st));
+      b->pool2.alloc(nhits * (uint64_t)b->pool_stride, st);  // upper bound; only pool_bytes are fetched
+      k_compact_pool<<<grid_for(nhits, B), B, 0, st>>>(b->hits.p, nhits, aoff.p, b->pool.p, b->pool2.p);
+      launches += 4;
+      DG_CUDA(cudaStreamSynchronize(st));
     }
     prof_mark(ix, 5);
     DG_CUDA(cudaGetLastError());
@@ -902,33 +1105,41 @@ static void prof_collect(dg_index* ix) {
 static int fetch_impl(dg_batch* b, dg_result** out) {
   if (!b->ran) { set_error("dg_batch_fetch before dg_batch_run"); return DG_ERR_ARG; }
   dg_index* ix = b->ix;
+  dg_result* r = nullptr;
   try {
     DG_CUDA(cudaSetDevice(ix->device));
     cudaStream_t st = ix->stream;
-    dg_result* r = new dg_result();
+    r = new dg_result();
     uint32_t nq = b->nq;
-    r->hits.resize(b->nhits);
-    r->qoff.resize((size_t)nq + 1);
-    r->status.resize(nq);
-    r->dist.resize(nq);
-    r->pool.resize(b->nhits * b->pool_stride);
-    r->seqs.resize(b->nbytes);
+    r->nq = nq;
+    r->nhits = b->nhits;
+    r->hits.alloc(b->nhits * sizeof(dg_hit), true);
+    r->qoff.alloc(((size_t)nq + 1) * 8, true);
+    r->status.alloc((size_t)nq * 4, true);
+    r->dist.alloc((size_t)nq * 4, true);
+    r->pool.alloc(b->pool_bytes, true);
+    r->seqs.alloc(b->nbytes, true);
     if (b->nhits) {
-      DG_CUDA(cudaMemcpyAsync(r->hits.data(), b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaMemcpyAsync(r->pool.data(), b->pool.p, b->nhits * b->pool_stride, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaMemcpyAsync(r->hits.p, b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, st));
+      if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync(r->pool.p, b->pool2.p, b->pool_bytes, cudaMemcpyDeviceToHost, st));
     }
-    DG_CUDA(cudaMemcpyAsync(r->qoff.data(), b->qoff.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaMemcpyAsync(r->qoff.p, b->qoff.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (nq) {
-      DG_CUDA(cudaMemcpyAsync(r->status.data(), b->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaMemcpyAsync(r->dist.data(), b->dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaMemcpyAsync(r->status.p, b->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaMemcpyAsync(r->dist.p, b->dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     }
-    if (b->nbytes) DG_CUDA(cudaMemcpyAsync(r->seqs.data(), b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
+    if (b->nbytes) DG_CUDA(cudaMemcpyAsync(r->seqs.p, b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
     prof_collect(ix);
     *out = r;
     return DG_OK;
   } catch (CudaFail& e) {
+    delete r;
     return e.code;
+  } catch (std::bad_alloc&) {
+    delete r;
+    set_error("out of host memory");
+    return DG_ERR_NOMEM;
   }
 }
 
@@ -1014,22 +1225,22 @@ int dg_backward_search_batch(dg_index* idx, const char* seqs, const uint64_t* of
 }
 
 const dg_hit* dg_result_hits(const dg_result* r, uint64_t* n) {
-  if (n) *n = r ? r->hits.size() : 0;
-  return r && !r->hits.empty() ? r->hits.data() : nullptr;
+  if (n) *n = r ? r->nhits : 0;
+  return r ? (const dg_hit*)r->hits.p : nullptr;
 }
 const uint64_t* dg_result_query_offsets(const dg_result* r, uint32_t* nq) {
-  if (nq) *nq = r ? (uint32_t)(r->qoff.size() - 1) : 0;
-  return r ? r->qoff.data() : nullptr;
+  if (nq) *nq = r ? r->nq : 0;
+  return r ? (const uint64_t*)r->qoff.p : nullptr;
 }
-const uint32_t* dg_result_query_status(const dg_result* r) { return r ? r->status.data() : nullptr; }
-const uint32_t* dg_result_query_distance(const dg_result* r) { return r ? r->dist.data() : nullptr; }
+const uint32_t* dg_result_query_status(const dg_result* r) { return r ? (const uint32_t*)r->status.p : nullptr; }
+const uint32_t* dg_result_query_distance(const dg_result* r) { return r ? (const uint32_t*)r->dist.p : nullptr; }
 const char* dg_result_pool(const dg_result* r, uint64_t* bytes) {
-  if (bytes) *bytes = r ? r->pool.size() : 0;
-  return r ? r->pool.data() : nullptr;
+  if (bytes) *bytes = r ? r->pool.bytes : 0;
+  return r ? (const char*)r->pool.p : nullptr;
 }
 const char* dg_result_sequences(const dg_result* r, uint64_t* bytes) {
-  if (bytes) *bytes = r ? r->seqs.size() : 0;
-  return r ? r->seqs.data() : nullptr;
+  if (bytes) *bytes = r ? r->seqs.bytes : 0;
+  return r ? (const char*)r->seqs.p : nullptr;
 }
 void dg_result_free(dg_result* r) { delete r; }
 
@@ -1037,19 +1248,20 @@ void dg_result_free(dg_result* r) { delete r; }
 // qoff[nq+1], status[nq], dist[nq], hits[nhits], pool, seqs
 int dg_result_pack(const dg_result* r, void* buf, uint64_t* bytes) {
   if (!r || !bytes) { set_error("null argument"); return DG_ERR_ARG; }
-  uint64_t nq = r->qoff.size() - 1, nh = r->hits.size(), np = r->pool.size(), ns = r->seqs.size();
+  uint64_t nq = r->nq, nh = r->nhits, np = r->pool.bytes, ns = r->seqs.bytes;
   uint64_t need = 32 + (nq + 1) * 8 + nq * 8 + nh * sizeof(dg_hit) + np + ns;
   if (!buf) { *bytes = need; return DG_OK; }
   if (*bytes < need) { set_error("buffer too small"); return DG_ERR_ARG; }
   uint8_t* p = (uint8_t*)buf;
   uint64_t hdr[4] = {nq, nh, np, ns};
-  memcpy(p, hdr, 32); p += 32;
-  memcpy(p, r->qoff.data(), (nq + 1) * 8); p += (nq + 1) * 8;
-  memcpy(p, r->status.data(), nq * 4); p += nq * 4;
-  memcpy(p, r->dist.data(), nq * 4); p += nq * 4;
-  memcpy(p, r->hits.data(), nh * sizeof(dg_hit)); p += nh * sizeof(dg_hit);
-  memcpy(p, r->pool.data(), np); p += np;
-  memcpy(p, r->seqs.data(), ns);
+  auto put = [&](const void* src, uint64_t n) { if (n) memcpy(p, src, n); p += n; };
+  put(hdr, 32);
+  put(r->qoff.p, (nq + 1) * 8);
+  put(r->status.p, nq * 4);
+  put(r->dist.p, nq * 4);
+  put(r->hits.p, nh * sizeof(dg_hit));
+  put(r->pool.p, np);
+  put(r->seqs.p, ns);
   *bytes = need;
   return DG_OK;
 }
@@ -1062,13 +1274,21 @@ int dg_result_unpack(const void* buf, uint64_t bytes, dg_result** out) {
   uint64_t need = 32 + (nq + 1) * 8 + nq * 8 + nh * sizeof(dg_hit) + np + ns;
   if (bytes < need) { set_error("truncated buffer"); return DG_ERR_ARG; }
   dg_result* r = new dg_result();
-  r->qoff.resize(nq + 1); r->status.resize(nq); r->dist.resize(nq); r->hits.resize(nh); r->pool.resize(np); r->seqs.resize(ns);
-  memcpy(r->qoff.data(), p, (nq + 1) * 8); p += (nq + 1) * 8;
-  memcpy(r->status.data(), p, nq * 4); p += nq * 4;
-  memcpy(r->dist.data(), p, nq * 4); p += nq * 4;
-  memcpy(r->hits.data(), p, nh * sizeof(dg_hit)); p += nh * sizeof(dg_hit);
-  memcpy(r->pool.data(), p, np); p += np;
-  memcpy(r->seqs.data(), p, ns);
+  try {
+    r->nq = (uint32_t)nq;
+    r->nhits = nh;
+    auto get = [&](HostBuf& hb, uint64_t n) { hb.alloc(n, false); if (n) memcpy(hb.p, p, n); p += n; };
+    get(r->qoff, (nq + 1) * 8);
+    get(r->status, nq * 4);
+    get(r->dist, nq * 4);
+    get(r->hits, nh * sizeof(dg_hit));
+    get(r->pool, np);
+    get(r->seqs, ns);
+  } catch (std::bad_alloc&) {
+    delete r;
+    set_error("out of host memory");
+    return DG_ERR_NOMEM;
+  }
   *out = r;
   return DG_OK;
 }

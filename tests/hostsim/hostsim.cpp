@@ -26,6 +26,17 @@ static void neighbors(const std::string& q, int d, bool indel, std::set<std::str
     script_rtl(base, m, sc, [&](uint8_t x) { rt.push_back((char)x); return true; });
     std::string lt((char*)buf.data(), L);
     if (std::string(rt.rbegin(), rt.rend()) != lt || L != script_len(m, sc)) { fprintf(stderr, "rtl/ltr mismatch\n"); exit(3); }
+    // cross-check the packed fast path (ACGT-only, short strings)
+    bool clean = true;
+    for (char ch : q) if (base_code((uint8_t)ch) == 4) clean = false;
+    if (clean && m + sc.nev <= kMaxPacked) {
+      uint64_t code = 0;
+      for (int i = 0; i < m; ++i) code = (code << 2) | (uint64_t)base_code(base[i]);
+      for (int e = 0; e < sc.nev; ++e) code = apply_event_packed(code, m - 1 - sc.pos[e], sc.k[e]);
+      std::string pk;
+      for (int t = L - 1; t >= 0; --t) pk.push_back((char)code_base((int)((code >> (2 * t)) & 3)));
+      if (pk != lt || (L < 32 && (code >> (2 * L)) != 0)) { fprintf(stderr, "packed mismatch %s vs %s\n", pk.c_str(), lt.c_str()); exit(3); }
+    }
     all.insert(lt);
   };
   Script sc; sc.nev = 0; sc.pos[0] = sc.pos[1] = sc.k[0] = sc.k[1] = 0;
@@ -79,8 +90,21 @@ int main(int argc, char** argv) {
       std::vector<uint8_t> trace(((mg + 1) * (n + 1) + 3) / 4 + 1), ops(mg + n + 1), ra(mg + n + 1), qa(mg + n + 1);
       std::vector<int> srow(n + 1);
       int lead = 0, score = 0;
-      int kept = needle_align((const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, trace.data(), srow.data(),
+      TraceBytes tb{trace.data(), n + 1};
+      int kept = needle_align((const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, tb, srow.data(),
                               ops.data(), ra.data(), qa.data(), &lead, &score);
+      if (n <= 31) {  // the thread-local trace layout of k_verify must agree with the byte layout
+        std::vector<uint64_t> rows(mg + 1, 0);
+        std::vector<uint8_t> ra2(mg + n + 1), qa2(mg + n + 1);
+        int lead2 = 0, score2 = 0;
+        TraceRows64 tr{rows.data()};
+        int kept2 = needle_align((const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, tr, srow.data(), ops.data(),
+                                 ra2.data(), qa2.data(), &lead2, &score2);
+        if (kept2 != kept || lead2 != lead || score2 != score || memcmp(ra.data(), ra2.data(), kept) || memcmp(qa.data(), qa2.data(), kept)) {
+          fprintf(stderr, "TraceRows64 / TraceBytes mismatch\n");
+          return 3;
+        }
+      }
       std::cout << score << '\t' << lead << '\t' << std::string((char*)ra.data(), kept) << '\t'
                 << std::string((char*)qa.data(), kept) << '\n';
     }
