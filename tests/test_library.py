@@ -1,0 +1,101 @@
+"""CPU tests of the boundary: the C ABI library loads, exports every symbol the header declares,
+fails loudly without a GPU, and its host-only entry points work."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dicey_b200.api as api
+from dicey_b200 import shard, synth
+from util import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "dicey_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.library()
+    syms = header_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert missing == []
+    assert sorted(api.EXPORTS) == syms
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.DiceyB200Error) as e:
+        api.Index.open(os.path.join(GOLDEN, "t1m.fm9"), 0)
+    assert e.value.code == -4 and "no CPU path" in str(e.value)
+    with pytest.raises(api.DiceyB200Error):
+        api.Index.build_synthetic(42, 2, 1000, 0)
+
+
+def test_open_rejects_bad_files(tmp_path):
+    bad = tmp_path / "x.fm9"
+    bad.write_bytes(b"\0" * 100)
+    with pytest.raises(api.DiceyB200Error) as e:
+        api.Index.open(str(bad), 0)
+    assert e.value.code == -2          # no _check sidecar (load_from_checked_file refuses)
+    (tmp_path / "x.fm9_check").write_bytes(b"\1" * 8)
+    with pytest.raises(api.DiceyB200Error) as e:
+        api.Index.open(str(bad), 0)
+    assert e.value.code == -3          # wrong type hash
+
+
+def test_hits_sort_matches_dnahit_order():
+    h = np.zeros(5, dtype=api.HIT_DTYPE)
+    h["score"] = [-1, 0, -1, 0, -2]
+    h["chr"] = [2, 1, 1, 0, 0]
+    h["start"] = [5, 9, 7, 3, 1]
+    api.library().dg_hits_sort(h.ctypes.data, len(h))
+    assert [(int(x["score"]), int(x["chr"]), int(x["start"])) for x in h] == [(0, 0, 3), (0, 1, 9), (-1, 1, 7), (-1, 2, 5), (-2, 0, 1)]
+
+
+def fake_result(nq, hits_per_q, tag):
+    """A packed dg_result built by hand (wire format of dg_result_pack)."""
+    nh = nq * hits_per_q
+    hits = np.zeros(nh, dtype=api.HIT_DTYPE)
+    hits["query"] = np.repeat(np.arange(nq), hits_per_q)
+    hits["score"] = -1
+    hits["chr"] = tag
+    hits["start"] = np.arange(nh) + 1
+    hits["aln_len"] = 4
+    hits["aln_off"] = np.arange(nh) * 8
+    hits["strand"] = ord("+")
+    pool = np.frombuffer((b"ACGT" + b"ACGA") * nh, dtype=np.uint8)
+    qoff = (np.arange(nq + 1) * hits_per_q).astype(np.uint64)
+    seqs = np.frombuffer(b"ACGTACGTAC" * nq, dtype=np.uint8)
+    hdr = np.array([nq, nh, pool.size, seqs.size], dtype=np.uint64)
+    return np.concatenate([hdr.view(np.uint8), qoff.view(np.uint8), np.zeros(nq, np.uint32).view(np.uint8),
+                           np.ones(nq, np.uint32).view(np.uint8), hits.view(np.uint8), pool, seqs])
+
+
+def test_pack_unpack_merge_roundtrip():
+    a = shard.unpack_result(fake_result(3, 2, 7))
+    b = shard.unpack_result(fake_result(2, 1, 9))
+    assert a.nq == 3 and len(a.hits) == 6 and a.push_hits(1)[0][4:] == ("ACGT", "ACGA")
+    assert np.array_equal(shard.pack_result(a), fake_result(3, 2, 7))
+    so = [np.arange(4, dtype=np.uint64) * 10, np.arange(3, dtype=np.uint64) * 10 + 30]
+    m = shard.merge_results([a, b], so)
+    assert m.nq == 5 and len(m.hits) == 8
+    assert [int(x) for x in m.qoff] == [0, 2, 4, 6, 7, 8]
+    assert m.push_hits(4) == [(-1, 9, 2, "+", "ACGT", "ACGA")]
+    assert m.sequence(3) == b"ACGTACGTAC"
+    assert shard.shard_bounds(10, 4) == [0, 2, 5, 7, 10]
+
+
+def test_synth_generator_is_windowable():
+    t = synth.text(42, 3, 1000)
+    assert t.size == 3 * 1001 and t[1000] == 10
+    assert np.array_equal(synth.bases(42, 1000 + 17, 50), t[1001 + 17:1001 + 67])
+    p = synth.primers_fast(42, 3, 1000, 8, 20, 1, True)
+    assert p.shape == (8, 20) and set(np.unique(p)) <= set(b"ACGT")

@@ -1,0 +1,86 @@
+"""CPU tests: the oracle restatement (oracle/dicey_oracle) and the host-compiled per-item
+arithmetic of the CUDA kernels (tests/hostsim) against the golden outputs of the reference."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+from util import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle", "dicey_oracle")
+HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "hostsim")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostsim")], check=True, capture_output=True)
+
+
+def run(binary, args):
+    return subprocess.run([binary] + args, check=True, capture_output=True, text=True, cwd=GOLDEN).stdout
+
+
+FAST_HUNT = ["cfg1_d0", "t1m_e1", "t1m_h1", "t1m_e0", "t1m_e1_fwd", "stress_e1", "stress_h1", "stress_e1_m7", "stress_h2_m50", "t1m_h2"]
+
+
+@pytest.mark.parametrize("case", FAST_HUNT)
+def test_oracle_hunt_matches_reference(case, tmp_path):
+    index = "t1m" if case.startswith(("t1m", "cfg1")) else "stress"
+    flags = open(os.path.join(GOLDEN, case + ".flags.txt")).read().split()
+    out = str(tmp_path / "rec.tsv")
+    run(ORACLE, ["hunt", index + ".fm9", index + ".rec.tsv", case + ".queries.txt", "--records", out] + flags)
+    want = "".join(l for l in open(os.path.join(GOLDEN, case + ".records.tsv")) if not l.startswith("W\t"))
+    assert open(out).read() == want
+
+
+def test_oracle_count_locate_seed_padcount():
+    assert run(ORACLE, ["count", "stress.fm9", "stress.patterns.txt"]) == open(os.path.join(GOLDEN, "stress.count.tsv")).read()
+    assert run(ORACLE, ["locate", "stress.fm9", "stress.patterns.txt"]) == open(os.path.join(GOLDEN, "stress.locate.tsv")).read()
+    assert run(ORACLE, ["seed", "t1m.fm9", "t1m.rec.tsv", "t1m_seed.queries.txt", "-k", "15", "-d", "1"]) == \
+        open(os.path.join(GOLDEN, "t1m_seed_k15_e1.seed.tsv")).read()
+    assert run(ORACLE, ["seed", "t1m.fm9", "t1m.rec.tsv", "t1m_seed.queries.txt", "-k", "12", "-d", "1", "-n"]) == \
+        open(os.path.join(GOLDEN, "t1m_seed_k12_h1.seed.tsv")).read()
+    assert run(ORACLE, ["seed", "stress.fm9", "stress.rec.tsv", "stress_seed.queries.txt", "-k", "15", "-d", "1", "-m", "300"]) == \
+        open(os.path.join(GOLDEN, "stress_seed_k15_e1.seed.tsv")).read()
+    assert run(ORACLE, ["padcount", "stress.fm9", "arms.txt", "-d", "1"]) == open(os.path.join(GOLDEN, "stress_arms_e1.padcount.tsv")).read()
+    assert run(ORACLE, ["padcount", "stress.fm9", "arms.txt", "-d", "1", "-n"]) == open(os.path.join(GOLDEN, "stress_arms_h1.padcount.tsv")).read()
+
+
+def test_oracle_needle_and_neighbors():
+    assert run(ORACLE, ["needle", "needle.pairs.tsv"]) == open(os.path.join(GOLDEN, "needle.out.tsv")).read()
+    for tag, args in (("e1", ["-d", "1"]), ("h1", ["-d", "1", "-n"]), ("h2", ["-d", "2", "-n"])):
+        want = gzip.open(os.path.join(GOLDEN, f"neighbors_{tag}.txt.gz"), "rt").read()
+        assert run(ORACLE, ["neighbors", "neighbors.queries.txt", "-x", "1000000"] + args) == want
+
+
+@pytest.mark.parametrize("tag,d,indel", [("e1", 1, 1), ("h1", 1, 0), ("h2", 2, 0), ("e2", 2, 1)])
+def test_kernel_scripts_reproduce_neighbor_sets(tag, d, indel):
+    """Edit scripts + the antichain rule of dg_core.cuh == std::set contents of neighbors();
+    the packed 2-bit fast path is cross-checked against the byte path inside hostsim."""
+    want = gzip.open(os.path.join(GOLDEN, f"neighbors_{tag}.txt.gz"), "rt").read()
+    assert run(HOSTSIM, ["neighbors", "neighbors.queries.txt", str(d), str(indel)]) == want
+
+
+def test_kernel_needle_reproduces_alignments():
+    """needle_align of dg_core.cuh (both trace layouts) == needle() + the gap stripping of hunter.h:391-401."""
+    got = run(HOSTSIM, ["needle", "needle.pairs.tsv"]).strip().split("\n")
+    ref = open(os.path.join(GOLDEN, "needle.out.tsv")).read().strip().split("\n")
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        sc, r0, r1 = r.split("\t")
+        last = len(r1) - 1
+        for j, ch in enumerate(r1):
+            if ch != "-":
+                last = j
+        lead, ra, qa, nlead = True, "", "", 0
+        for j in range(last + 1):
+            if r1[j] != "-":
+                lead = False
+            if not lead:
+                ra += r0[j]; qa += r1[j]
+            else:
+                nlead += 1
+        assert g == f"{sc}\t{nlead}\t{ra}\t{qa}"
