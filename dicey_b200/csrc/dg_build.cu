@@ -477,11 +477,12 @@ static void build_kmer_table(dg_index* ix) {
   uint32_t K = 0;
   if (const char* e = getenv("DG_KMER")) K = (uint32_t)atoi(e);
   if (K == 0) {
-    // about one text suffix per table cell, capped at 14 (2 GiB of uint2 at 3 Gb)
+    // about one text suffix per table cell, capped at 15 (8 GiB of uint2 at 3 Gb: HBM capacity
+    // traded for one fewer dependent DRAM access per neighbour string)
     K = 1;
-    while (K < 14 && (1ULL << (2 * (K + 1))) <= ix->n) ++K;
+    while (K < 15 && (1ULL << (2 * (K + 1))) <= ix->n) ++K;
   }
-  if (K > 15) K = 15;
+  if (K > 16) K = 16;
   ix->K = K;
   DevBuf<uint2> a, b;
   ix->kmer.alloc(1ULL << (2 * K));

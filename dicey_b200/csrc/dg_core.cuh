@@ -285,25 +285,38 @@ DG_HD void unpack_script(uint32_t code, bool indel, int& strand, Script& sc) {
 DG_HD int restricted_distance(const uint8_t* q, int m, const uint8_t* u, int ulen, int cap,
                               uint8_t* prev, uint8_t* row) {
   const int INF = 100;
-  for (int j = 0; j <= ulen; ++j) {
-    // D[0][j]: j insertions before q[0] (needs m > 0 and ACGT letters)
-    int v = (j == 0) ? 0 : ((m > 0 && prev[j - 1] < INF && base_code(u[j - 1]) < 4) ? prev[j - 1] + 1 : INF);
-    prev[j] = (uint8_t)(v > INF ? INF : v);
+  int dl = m - ulen;
+  if (dl > cap || -dl > cap) return cap + 1;  // every insertion / deletion changes the length by one
+  // only the diagonal band |i - j| <= cap can hold values <= cap; cells just outside it are INF
+  {
+    int jhi = cap < ulen ? cap : ulen;
+    prev[0] = 0;
+    for (int j = 1; j <= jhi; ++j)  // D[0][j]: j insertions before q[0] (ACGT letters only)
+      prev[j] = (uint8_t)((m > 0 && prev[j - 1] < INF && base_code(u[j - 1]) < 4) ? prev[j - 1] + 1 : INF);
+    if (jhi + 1 <= ulen) prev[jhi + 1] = (uint8_t)INF;
   }
   for (int i = 1; i <= m; ++i) {
-    row[0] = (uint8_t)(i > INF ? INF : i);
-    int best = row[0];
-    for (int j = 1; j <= ulen; ++j) {
-      int sub = prev[j - 1];
-      if (q[i - 1] != u[j - 1]) sub = (base_code(u[j - 1]) < 4) ? sub + 1 : INF;
-      int del = prev[j] + 1;
-      int ins = (i < m && base_code(u[j - 1]) < 4) ? row[j - 1] + 1 : INF;
-      int v = sub < del ? sub : del;
-      if (ins < v) v = ins;
+    int jlo = i - cap > 0 ? i - cap : 0;
+    int jhi = i + cap < ulen ? i + cap : ulen;
+    int best = INF;
+    for (int j = jlo; j <= jhi; ++j) {
+      int v;
+      if (j == 0) {
+        v = i;  // i deletions
+      } else {
+        int uc = base_code(u[j - 1]);
+        int sub = prev[j - 1];
+        if (q[i - 1] != u[j - 1]) sub = (uc < 4) ? sub + 1 : INF;
+        int del = prev[j] + 1;
+        int ins = (j > jlo && i < m && uc < 4) ? row[j - 1] + 1 : INF;
+        v = sub < del ? sub : del;
+        if (ins < v) v = ins;
+      }
       if (v > INF) v = INF;
       row[j] = (uint8_t)v;
       if (v < best) best = v;
     }
+    if (jhi + 1 <= ulen) row[jhi + 1] = (uint8_t)INF;
     if (best > cap) return cap + 1;
     uint8_t* t = prev; prev = row; row = t;
   }
