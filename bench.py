@@ -279,8 +279,11 @@ def main_b200(args):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    step_ms = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         res = ix.hunt(seqs, params)
+        step_ms.append(round(1e3 * (time.perf_counter() - ts), 3))
         d2h = res.hits.nbytes + res.pool.nbytes + res.qoff.nbytes + res.status.nbytes + res.dist.nbytes + res.seqs.nbytes
         if world > 1:
             # the hit all-gather of SURVEY.md 8(e): counts, then padded hit records, over NCCL
@@ -303,6 +306,15 @@ def main_b200(args):
     e2e_s = float(t.item())
     e2e_value = world * nq * args.steps / e2e_s
     h2d = int(pin.numel() + off_pin.numel() * 8)
+    # where the end-to-end time goes (untimed extra passes through the split form of the same call)
+    phases = []
+    for _ in range(3):
+        t0 = time.perf_counter(); bt = ix.stage(seqs, params)
+        t1 = time.perf_counter(); bt.run()
+        t2 = time.perf_counter(); r2 = bt.fetch()
+        t3 = time.perf_counter(); bt.free(); del r2
+        t4 = time.perf_counter()
+        phases.append([round(1e3 * (b - a), 3) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])
 
     # ---------------- CPU reference beside it (rank 0, single GPU run only) + roofline numerator
     cpu = None
@@ -367,7 +379,7 @@ def main_b200(args):
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "primers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "phases_ms_stage_run_fetch_free": phases, "hunt_call_ms": step_ms},
             "gpu_launches": int(sum(p["launches"] for p in profs)),
             "stages_ms": stage,
             "roofline": roof,

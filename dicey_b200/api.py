@@ -37,7 +37,8 @@ class _Params(C.Structure):
 
 class _Info(C.Structure):
     _fields_ = [("n", C.c_uint64), ("sigma", C.c_uint32), ("kmer", C.c_uint32), ("n_exceptions", C.c_uint64),
-                ("device_bytes", C.c_uint64), ("sa_sample", C.c_uint32), ("nseq", C.c_uint32)]
+                ("device_bytes", C.c_uint64), ("sa_sample", C.c_uint32), ("nseq", C.c_uint32), ("bitmap_k", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class _Profile(C.Structure):

@@ -68,6 +68,8 @@ int dg_index_get_info(const dg_index* idx, dg_index_info* info) {
   info->device_bytes = idx->device_bytes();
   info->sa_sample = kSaSample;
   info->nseq = idx->nseq;
+  info->bitmap_k = idx->KB;
+  info->reserved = 0;
   return DG_OK;
 }
 
@@ -86,6 +88,7 @@ int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* by
   else if (w == "C") { src = idx->Cb.p; nb = 256 * 4; }
   else if (w == "exc_pos") { src = idx->exc_pos.p; nb = (uint64_t)idx->n_exc * 4; }
   else if (w == "exc_sym") { src = idx->exc_sym.p; nb = idx->n_exc; }
+  else if (w == "present_kb") { src = idx->present_kb.p; nb = idx->present_kb.bytes(); }
   else { set_error("unknown array name"); return DG_ERR_ARG; }
   if (!buf) { *bytes = nb; return DG_OK; }
   if (*bytes < nb) { set_error("buffer too small"); return DG_ERR_ARG; }

@@ -142,6 +142,27 @@ __global__ void k_kmer_level(IndexView ix, const uint2* __restrict__ prev, uint2
   cur[t] = o;
 }
 
+// ---------------------------------------------------------------- KB-mer presence bitmap
+// bit (packed code of T[i, i+KB), last base in the low bits) is set for every ACGT-only window of
+// the text: a neighbour string whose last KB bases have a clear bit has an empty SA interval, so
+// k_search_packed drops it after ONE DRAM access instead of a table lookup + backward steps.
+constexpr int kPresenceChunk = 256;
+__global__ void k_presence(const uint8_t* __restrict__ text, uint64_t n, uint32_t KB, uint32_t* __restrict__ bits) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t first = t * kPresenceChunk;
+  if (first >= n) return;
+  uint64_t end = first + kPresenceChunk;  // windows starting in [first, end)
+  uint64_t last = end + KB - 1 < n ? end + KB - 1 : n;
+  const uint64_t mask = (KB >= 32) ? ~0ULL : ((1ULL << (2 * KB)) - 1);
+  uint64_t code = 0;
+  uint32_t valid = 0;
+  for (uint64_t j = first; j < last; ++j) {
+    int c = base_code(text[j]);
+    if (c < 4) { code = ((code << 2) | (uint64_t)c) & mask; ++valid; } else { code = 0; valid = 0; }
+    if (valid >= KB) atomicOr(&bits[code >> 5], 1u << (code & 31));
+  }
+}
+
 // ---------------------------------------------------------------- text from ISA samples
 __global__ void k_rebuild_text(IndexView ix, const uint32_t* __restrict__ isa, uint64_t nchains, uint8_t* __restrict__ text) {
   uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -503,6 +524,30 @@ static void build_kmer_table(dg_index* ix) {
   DG_CUDA(cudaStreamSynchronize(st));
 }
 
+// needs ix->text
+static void build_presence_bitmap(dg_index* ix) {
+  cudaStream_t st = ix->stream;
+  uint32_t KB = 0;
+  if (const char* e = getenv("DG_BITMAP_K")) {
+    KB = (uint32_t)atoi(e);  // 0 switches the filter off
+  } else {
+    // about 1 set bit in 16 at most, capped at 18 (8 GiB of bits at 3 Gb)
+    KB = 8;
+    while (KB < 18 && (1ULL << (2 * KB)) < 16 * ix->n) ++KB;
+  }
+  if (KB > 19) KB = 19;
+  if (KB && KB < 3) KB = 3;
+  ix->KB = KB;
+  if (!KB) return;
+  uint64_t words = (1ULL << (2 * KB)) >> 5;
+  ix->present_kb.alloc(words);
+  DG_CUDA(cudaMemsetAsync(ix->present_kb.p, 0, words * 4, st));
+  uint64_t nthreads = (ix->n + kPresenceChunk - 1) / kPresenceChunk;
+  k_presence<<<grid_for(nthreads, 128), 128, 0, st>>>(ix->text.p, ix->n, KB, ix->present_kb.p);
+  DG_CUDA(cudaGetLastError());
+  DG_CUDA(cudaStreamSynchronize(st));
+}
+
 static dg_index* new_index(int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -521,6 +566,13 @@ static dg_index* new_index(int device) {
     DG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = ~0ULL;
     DG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  // every hot access is a random 32-byte sector: ask L2 not to widen DRAM fetches beyond that
+  {
+    size_t gran = 32;
+    if (const char* e = getenv("DG_L2_FETCH")) gran = (size_t)atoi(e);
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
   }
   ix->cum.alloc(1);
   DG_CUDA(cudaMemset(ix->cum.p, 0, 8));
@@ -598,6 +650,7 @@ int build_from_fm9(const char* path, int device, dg_index** out) {
     k_rebuild_text<<<grid_for(nchains, 128), 128, 0, st>>>(ix->view(), ix->isa_samples.p, nchains, ix->text.p);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaStreamSynchronize(st));
+    build_presence_bitmap(ix);
     *out = ix;
     return DG_OK;
   } catch (CudaFail& e) {
@@ -693,6 +746,7 @@ static void build_from_device_text(dg_index* ix) {
   finish_from_bwt(ix, bwt.p, Cb, present);
   bwt.release();
   build_kmer_table(ix);
+  build_presence_bitmap(ix);
 }
 
 int build_from_text_host(const uint8_t* text, uint64_t len, int device, dg_index** out) {

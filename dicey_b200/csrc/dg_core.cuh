@@ -60,6 +60,8 @@ struct IndexView {
   const uint8_t* text;        // the n text bytes (sentinel included)
   const uint64_t* cum;        // nseq + 1 cumulative seqlen (util.h:201 lengths)
   uint32_t nseq;
+  const uint32_t* present_kb; // 4^KB bits: the ACGT KB-mer with this packed code occurs in the text
+  uint32_t KB;                // 0 = no presence bitmap
 };
 
 DG_HD int popc64(uint64_t x) {

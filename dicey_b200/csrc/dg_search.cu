@@ -15,6 +15,7 @@
 //   k_verify    hunter.h:358-432: record lookup, context with '\n' trimming, needle() /
 //               needleScore(), gap stripping, DnaHit
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
@@ -172,7 +173,8 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   b.status[q] = st;
   b.dist[q] = d;
   int variant = clean ? 0 : 1;
-  units[q] = run ? (uint64_t)ut.tab_cnt[variant * 256 + m] * (b.reverse ? 2 : 1) : 0;
+  // packed queries are searched by k_search_packed; k_search takes the rest
+  units[q] = (run && !packed) ? (uint64_t)ut.tab_cnt[variant * 256 + m] * (b.reverse ? 2 : 1) : 0;
   if (!run || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
 }
 
@@ -186,13 +188,39 @@ struct SearchOut {
   unsigned long long* n_scripts;
 };
 
+// One backward-search step for an ACGT code.  Only the count of code c and the two bit planes of
+// the 32-byte block are loaded (no dynamically indexed register array -> no local memory).
+__device__ __forceinline__ uint32_t rank_planes(const IndexView& ix, uint64_t lo, uint64_t hi, uint32_t i, int c) {
+  const uint32_t o = i & 63;
+  const uint64_t mask = o ? (~0ULL >> (64 - o)) : 0ULL;
+  const uint64_t m = ((c & 1) ? lo : ~lo) & ((c & 2) ? hi : ~hi) & mask;
+  uint32_t r = (uint32_t)__popcll(m);
+  if (c == 0 && o && region_flag(ix, (uint64_t)i - 1)) {
+    // non-ACGT symbols are stored as code 0: take those inside [64*blk, i) back out
+    const uint32_t base = i & ~63u;
+    const uint32_t a = lower_bound_u32(ix.exc_pos, 0, ix.n_exc, base);
+    const uint32_t e = lower_bound_u32(ix.exc_pos, a, ix.n_exc, i);
+    r -= (e - a);
+  }
+  return r;
+}
 __device__ __forceinline__ void step_acgt(const IndexView& ix, uint32_t& l, uint32_t& r, int c) {
-  OccBlock bl = load_block(ix.occ + (l >> 6));
-  uint32_t nl = ix.C4[c] + rank_in_block(ix, bl, l, c);
+  const OccBlock* pl = ix.occ + (l >> 6);
+  const uint32_t cl = __ldg(&pl->cnt[c]);
+  const uint4 wl = __ldg(reinterpret_cast<const uint4*>(pl) + 1);
+  const uint64_t llo = ((uint64_t)wl.y << 32) | wl.x, lhi = ((uint64_t)wl.w << 32) | wl.z;
+  const uint32_t c4 = ix.C4[c];
   uint32_t nr;
-  if ((r >> 6) == (l >> 6)) nr = ix.C4[c] + rank_in_block(ix, bl, r, c);
-  else nr = ix.C4[c] + rank_acgt(ix, r, c);
-  l = nl; r = nr;
+  if ((r >> 6) == (l >> 6)) {
+    nr = c4 + cl + rank_planes(ix, llo, lhi, r, c);
+  } else {
+    const OccBlock* pr = ix.occ + (r >> 6);
+    const uint32_t cr = __ldg(&pr->cnt[c]);
+    const uint4 wr = __ldg(reinterpret_cast<const uint4*>(pr) + 1);
+    nr = c4 + cr + rank_planes(ix, ((uint64_t)wr.y << 32) | wr.x, ((uint64_t)wr.w << 32) | wr.z, r, c);
+  }
+  l = c4 + cl + rank_planes(ix, llo, lhi, l, c);
+  r = nr;
 }
 
 __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTabs ut, const uint64_t* __restrict__ unit_off,
@@ -331,6 +359,153 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
   }
   // one statistics update per warp
   for (int o = 16; o; o >>= 1) my_scripts += __shfl_down_sync(0xFFFFFFFFu, my_scripts, o);
+  if (lane == 0 && my_scripts) atomicAdd(out.n_scripts, my_scripts);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_search_packed: the fast path for ACGT-only queries whose edited strings fit one 64-bit code
+// (qflag bit 1).  One warp owns one (query, strand) and walks its edit scripts 32 at a time:
+//   1. every lane builds its edited string as a packed code (a few shifts) and probes the KB-mer
+//      presence bitmap with the last KB bases: one DRAM access that empties ~95 % of the lanes
+//      on a 3 Gb text (the string cannot occur if its suffix does not);
+//   2. the survivors are compacted with a warp ballot into a per-warp shared-memory queue, and
+//      each time 32 of them are queued they run the slow path together with full lanes:
+//      K-mer table lookup on the last K bases + one backward-search step per remaining base.
+// The strings enumerated are exactly those of k_search for a clean query (neighbors.h:47-83).
+template <bool INDEL>
+__global__ void __launch_bounds__(256) k_search_packed(IndexView ix, BatchDev b, SearchOut out) {
+  constexpr int S = INDEL ? 8 : 3;    // enumeration slots per position of a clean query
+  constexpr int CS = INDEL ? 9 : 4;   // canonical slot numbering carried by the candidate
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  __shared__ uint64_t q_code[8][64];
+  __shared__ uint2 q_meta[8][64];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t npairs = b.reverse ? 2ULL * b.nq : (uint64_t)b.nq;
+  const int K = (int)ix.K;
+  const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
+  const int KB = (int)ix.KB;
+  const uint64_t kbmask = (1ULL << (2 * KB)) - 1ULL;
+  uint32_t queued = 0;
+  unsigned long long my_scripts = 0;
+
+  // slow path of one queued string (all 32 lanes call; `have` marks the real ones)
+  auto resolve = [&](bool have, uint64_t code, uint2 meta) {
+    bool alive = false;
+    uint32_t l = 0, r = (uint32_t)ix.n;
+    if (have) {
+      const int L = (int)(meta.y >> 27);
+      int t = 0;
+      if (L >= K) {
+        uint2 iv = __ldg(&ix.kmer[(uint32_t)code & kmask]);
+        l = iv.x; r = iv.y; t = K;
+      }
+      while (l < r && t < L) {
+        step_acgt(ix, l, r, (int)((code >> (2 * t)) & 3));
+        ++t;
+      }
+      alive = l < r;
+    }
+    unsigned am = __ballot_sync(FULL, alive);
+    if (am) {
+      unsigned int first = 0;
+      if (lane == (uint32_t)(__ffs(am) - 1)) first = atomicAdd(out.n_cand, (unsigned int)__popc(am));
+      first = __shfl_sync(FULL, first, __ffs(am) - 1);
+      if (alive) {
+        unsigned int slot = first + (unsigned int)__popc(am & lt);
+        if (slot < out.cap) {
+          Cand c;
+          c.q = meta.x; c.l = l; c.r = r; c.code = meta.y & 0x07FFFFFFu;
+          out.cands[slot] = c;
+        } else {
+          atomicExch(out.overflow, 1u);
+        }
+      }
+    }
+  };
+
+  for (uint64_t pair = warp; pair < npairs; pair += nwarps) {
+    const uint32_t q = b.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+    const int strand = b.reverse ? (int)(pair & 1) : 0;
+    if (!(b.qflag[q] & 2)) continue;
+    const int m = b.seed_len ? (int)b.seed_len : (int)(b.off[q + 1] - b.off[q]);
+    const uint64_t code0 = b.qcode[2 * (uint64_t)q + strand];
+    const int dq = (int)b.dist[q];
+    const int E = S * m;
+    const bool with_base = !(INDEL && dq >= 1);
+    const int nrows = dq >= 2 ? E : 0;
+    auto canon = [&](int kk, int pos) -> int {   // enumeration slot -> canonical event (enum_to_canonical, clean)
+      if (kk < 3) return (int)(((code0 >> (2 * (m - 1 - pos))) & 3) + 1 + kk) & 3;
+      return kk + 1;
+    };
+    for (int row = -1; row < nrows; ++row) {
+      uint64_t code1 = code0;
+      int p1 = 0, k1 = 0, start, end, L1 = m;
+      if (row < 0) {
+        start = with_base ? -1 : 0;
+        end = dq >= 1 ? E : 0;
+      } else {
+        p1 = row / S;
+        k1 = canon(row - p1 * S, p1);
+        code1 = apply_event_packed(code0, m - 1 - p1, k1);
+        L1 = m + (k1 == 4 ? -1 : (k1 >= 5 ? 1 : 0));
+        start = (k1 >= 5 ? p1 : p1 + 1) * S;
+        end = E;
+      }
+      for (int s = start; s < end; s += 32) {
+        const int e = s + (int)lane;
+        const bool have = e < end;
+        uint64_t code = code1;
+        uint32_t scode = 0;
+        int L = L1;
+        bool pass = false;
+        if (have) {
+          ++my_scripts;
+          if (e < 0) {
+            scode = pack_script(strand, 0, 0, 0);
+          } else {
+            const int p2 = e / S;
+            const int k2 = canon(e - p2 * S, p2);
+            code = apply_event_packed(code1, m - 1 - p2, k2);
+            L += (k2 == 4 ? -1 : (k2 >= 5 ? 1 : 0));
+            scode = row < 0 ? pack_script(strand, 1, p2 * CS + k2, 0)
+                            : pack_script(strand, 2, p1 * CS + k1, p2 * CS + k2);
+          }
+          pass = L > 0;
+          if (pass && KB && L >= KB) {
+            const uint64_t bit = code & kbmask;
+            pass = (__ldg(&ix.present_kb[bit >> 5]) >> (uint32_t)(bit & 31)) & 1u;
+          }
+        }
+        const unsigned pm = __ballot_sync(FULL, pass);
+        if (pm) {
+          if (pass) {
+            const uint32_t slot = queued + (uint32_t)__popc(pm & lt);
+            q_code[wib][slot] = code;
+            q_meta[wib][slot] = make_uint2(q, scode | ((uint32_t)L << 27));
+          }
+          queued += (uint32_t)__popc(pm);
+          __syncwarp();
+          if (queued >= 32) {
+            queued -= 32;
+            const uint64_t c = q_code[wib][queued + lane];
+            const uint2 mt = q_meta[wib][queued + lane];
+            __syncwarp();
+            resolve(true, c, mt);
+          }
+        }
+      }
+    }
+  }
+  if (queued) {
+    const bool have = lane < queued;
+    const uint64_t c = have ? q_code[wib][lane] : 0;
+    const uint2 mt = have ? q_meta[wib][lane] : make_uint2(0, 0);
+    resolve(have, c, mt);
+  }
+  for (int o = 16; o; o >>= 1) my_scripts += __shfl_down_sync(FULL, my_scripts, o);
   if (lane == 0 && my_scripts) atomicAdd(out.n_scripts, my_scripts);
 }
 
@@ -638,31 +813,41 @@ using namespace dg;
 // D2H copies run at full PCIe rate); freed blocks are kept in a small process-wide cache because
 // cudaHostAlloc costs milliseconds.
 namespace {
+struct HostBlock { void* p; size_t cap; bool pinned; };
 struct PinCache {
   std::mutex mu;
-  std::vector<std::pair<void*, size_t>> free_blocks;
+  std::vector<HostBlock> free_blocks;
   size_t cached = 0;
-  void* get(size_t need, size_t& cap) {
+  bool get(size_t need, HostBlock& out) {
     std::lock_guard<std::mutex> g(mu);
     size_t best = free_blocks.size();
-    for (size_t i = 0; i < free_blocks.size(); ++i)
-      if (free_blocks[i].second >= need && (best == free_blocks.size() || free_blocks[i].second < free_blocks[best].second)) best = i;
-    if (best == free_blocks.size() || free_blocks[best].second > 4 * need + (1u << 20)) return nullptr;
-    void* p = free_blocks[best].first;
-    cap = free_blocks[best].second;
-    cached -= cap;
+    for (size_t i = 0; i < free_blocks.size(); ++i) {
+      const HostBlock& f = free_blocks[i];
+      if (f.cap < need || f.cap > 4 * need + (1u << 20)) continue;
+      if (best == free_blocks.size() || (f.pinned && !free_blocks[best].pinned) ||
+          (f.pinned == free_blocks[best].pinned && f.cap < free_blocks[best].cap)) best = i;
+    }
+    if (best == free_blocks.size()) return false;
+    out = free_blocks[best];
+    cached -= out.cap;
     free_blocks.erase(free_blocks.begin() + best);
-    return p;
+    return true;
   }
-  void put(void* p, size_t cap) {
+  void put(const HostBlock& b) {
     std::lock_guard<std::mutex> g(mu);
-    if (cached + cap > (3ULL << 30) || free_blocks.size() >= 64) { cudaFreeHost(p); return; }
-    free_blocks.push_back({p, cap});
-    cached += cap;
+    if (cached + b.cap > (3ULL << 30) || free_blocks.size() >= 64) {
+      if (b.pinned) cudaFreeHost(b.p); else free(b.p);
+      return;
+    }
+    free_blocks.push_back(b);
+    cached += b.cap;
   }
 };
 PinCache g_pin;
 
+// Result storage on the host.  Page-locked when the driver grants it; when it does not (locked-
+// memory limits of the container) the block is ordinary memory, still recycled through the cache
+// so that a steady stream of batches neither re-pins nor re-faults its result buffers.
 struct HostBuf {
   void* p = nullptr;
   size_t bytes = 0, cap = 0;
@@ -675,21 +860,22 @@ struct HostBuf {
     release();
     bytes = n;
     if (!n) return;
+    HostBlock b;
+    if (g_pin.get(n, b)) { p = b.p; cap = b.cap; pinned = b.pinned; return; }
+    cap = n + (n >> 3) + 4096;
     if (pin) {
-      p = g_pin.get(n, cap);
-      if (!p) {
-        cap = n + (n >> 3) + 4096;
-        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cudaGetLastError(); }
-      }
-      if (p) { pinned = true; return; }
+      if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return; }
+      p = nullptr;
+      cudaGetLastError();
+      static bool warned = false;
+      if (!warned && getenv("DG_TRACE")) { warned = true; fprintf(stderr, "[dicey_b200] cudaHostAlloc(%zu) failed: results land in pageable memory\n", cap); }
     }
-    p = malloc(n);
-    cap = n;
+    p = malloc(cap);
     pinned = false;
     if (!p) throw std::bad_alloc();
   }
   void release() {
-    if (p) { if (pinned) g_pin.put(p, cap); else free(p); }
+    if (p) g_pin.put(HostBlock{p, cap, pinned});
     p = nullptr; bytes = cap = 0; pinned = false;
   }
 };
@@ -892,10 +1078,21 @@ static int run_impl(dg_batch* b) {
     SearchOut so{b->cands.p, (uint32_t)cap64, ctr.p, ctr.p + 1, nscripts.p};
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ix->device);
-    int per_sm = 0;
-    DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (nq) { k_search<<<nsm * per_sm, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so); ++launches; }
+    if (nq) {
+      // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
+      int per_sm = 0;
+      if (b->par.indel) {
+        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_packed<true>, 256, 0));
+        k_search_packed<true><<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, so);
+      } else {
+        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_packed<false>, 256, 0));
+        k_search_packed<false><<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, so);
+      }
+      // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
+      DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
+      k_search<<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
+      launches += 2;
+    }
     prof_mark(ix, 2);
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
@@ -1174,12 +1371,19 @@ void dg_batch_free(dg_batch* b) {
 
 int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* params,
                   dg_result** out) {
+  static const bool trace = getenv("DG_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
   dg_batch* b = nullptr;
   int rc = stage_impl(idx, seqs, offsets, nq, params, &b);
   if (rc) return rc;
+  double t1 = now();
   rc = run_impl(b);
+  double t2 = now();
   if (!rc) rc = fetch_impl(b, out);
+  double t3 = now();
   dg_batch_free(b);
+  if (trace) fprintf(stderr, "[dg_hunt_batch] nq=%u stage %.3f ms, run %.3f ms, fetch %.3f ms, free %.3f ms\n", nq, t1 - t0, t2 - t1, t3 - t2, now() - t3);
   return rc;
 }
 

@@ -82,6 +82,8 @@ typedef struct {
   uint64_t device_bytes;  /* HBM held by this index                                    */
   uint32_t sa_sample;     /* suffix-array sampling rate (csa_wt<>: 32)                 */
   uint32_t nseq;          /* records set by dg_index_set_records                       */
+  uint32_t bitmap_k;      /* KB of the KB-mer presence bitmap (0 = none)               */
+  uint32_t reserved;
 } dg_index_info;
 
 /* Stage timings of the last dg_batch_run with profiling enabled (CUDA events on the index
@@ -138,7 +140,7 @@ int dg_index_get_info(const dg_index* idx, dg_index_info* info);
 void* dg_index_stream(const dg_index* idx);
 
 /* Copies of device-resident index arrays for tests (what = "text", "sa_samples", "occ",
- * "kmer", "C"); returns the byte count through *bytes; buf may be NULL to query the size. */
+ * "kmer", "C", "present_kb"); returns the byte count through *bytes; buf may be NULL to query the size. */
 int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* bytes);
 
 /* ---- batched queries ---------------------------------------------------------------- */

@@ -1,0 +1,139 @@
+"""The C++ host program (dicey_b200/dicey-b200): dicey's `hunt` command line and JSON output over
+the C ABI.  CPU tests cover argument handling and the error records that need no index; the GPU
+tests compare its stdout / gzipped output byte for byte with the reference's golden JSON lines."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from util import GOLDEN, HUNT_CASES, read_queries
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "dicey_b200", "dicey-b200")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "dicey_b200", "host")], check=True, capture_output=True)
+
+
+def run(args, cwd=None):
+    return subprocess.run([BIN] + args, capture_output=True, text=True, cwd=cwd)
+
+
+def make_genome_dir(tmp_path, index):
+    """<dir>/genome.fa.gz (+ .fai) and <dir>/genome.fa.fm9 (+ _check): the layout hunter.h:248-256 expects."""
+    d = str(tmp_path)
+    with gzip.open(os.path.join(d, "genome.fa.gz"), "wb") as f:
+        f.write(b">placeholder\nACGT\n")  # hunt only checks that the genome exists; names come from the .fai
+    with open(os.path.join(d, "genome.fa.gz.fai"), "w") as fai:
+        for line in open(os.path.join(GOLDEN, index + ".rec.tsv")):
+            n, l = line.split()
+            fai.write(f"{n}\t{l}\t0\t60\t61\n")
+    shutil.copy(os.path.join(GOLDEN, index + ".fm9"), os.path.join(d, "genome.fa.fm9"))
+    shutil.copy(os.path.join(GOLDEN, index + ".fm9_check"), os.path.join(d, "genome.fa.fm9_check"))
+    return d
+
+
+def test_usage_and_unknown_command():
+    r = run([])
+    assert r.returncode == 0 and "Usage: dicey <command> <arguments>" in r.stdout
+    r = run(["hunt"])
+    assert r.returncode == 255 and r.stdout.startswith("Usage: dicey hunt [OPTIONS] -g Danio_rerio.fa.gz CATTACTAACATCAGT")
+    r = run(["frobnicate"])
+    assert r.returncode == 1 and "Unrecognized command frobnicate" in r.stderr
+    r = run(["hunt", "--bogus", "x"])
+    assert r.returncode == 1 and "unrecognised option" in r.stderr
+    assert run(["version"]).stdout.startswith("Dicey version: v0.5.1")
+
+
+def test_missing_genome_is_an_error_record(tmp_path):
+    r = run(["hunt", "-g", str(tmp_path / "nope.fa.gz"), "ACGTACGTACGT"])
+    assert r.returncode == 1
+    assert r.stdout == '{"errors": [{"title":"Error: Genome does not exist!","type":"error"}]}\n'
+    # -o: the same record as one gzip member of the (truncated) output file
+    out = tmp_path / "o.json.gz"
+    out.write_bytes(b"stale")
+    r = run(["hunt", "--genome=" + str(tmp_path / "nope.fa.gz"), "-o", str(out), "ACGTACGTACGT"])
+    assert r.returncode == 1 and r.stdout == ""
+    assert gzip.open(out, "rt").read() == '{"errors": [{"title":"Error: Genome does not exist!","type":"error"}]}\n'
+
+
+def test_no_gpu_means_index_error_not_a_cpu_search(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = make_genome_dir(tmp_path, "t1m")
+    r = run(["hunt", "-g", "genome.fa.gz", "GAATACACCTAAAAACAC"], cwd=d)
+    assert r.returncode == 1
+    assert r.stdout == '{"errors": [{"title":"Error: FM-Index cannot be loaded!","type":"error"}]}\n'
+    assert "no CPU path" in r.stderr
+
+
+def fasta_of(case, path):
+    qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
+    with open(path, "w") as f:
+        for n, s in qs:
+            f.write(f">{n}\n{s}\n")
+    return qs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,index", HUNT_CASES)
+def test_hunt_cli_matches_reference_json(tmp_path, case, index):
+    d = make_genome_dir(tmp_path, index)
+    qs = fasta_of(case, os.path.join(d, "q.fa"))
+    flags = open(os.path.join(GOLDEN, case + ".flags.txt")).read().split()
+    want = [l for l in open(os.path.join(GOLDEN, case + ".jsonl"))]
+    r = run(["hunt", "-g", "genome.fa.gz"] + flags + ["q.fa"], cwd=d)
+    assert r.returncode == 0, r.stderr
+    got = r.stdout.splitlines(keepends=True)
+    assert len(got) == len(want) == len(qs)
+    for q, (g, w) in enumerate(zip(got, want)):
+        if "Neighborhood size exceeds" in w:
+            continue  # the reference truncated its neighbourhood (Limits)
+        assert g == w, (case, q)
+
+
+@pytest.mark.gpu
+def test_hunt_cli_single_sequence_and_outfile(tmp_path):
+    d = make_genome_dir(tmp_path, "t1m")
+    name, seq = read_queries(os.path.join(GOLDEN, "cfg1_d0.queries.txt"))[0]
+    want = open(os.path.join(GOLDEN, "cfg1_d0.jsonl")).read()
+    r = run(["hunt", "-g", "genome.fa.gz", "-d", "0", seq], cwd=d)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want.replace(f'"name":"{name}",', "")  # a literal sequence has no name (hunter.h:286)
+    r = run(["hunt", "-g", "genome.fa.gz", "-d0", "-o", "out.json.gz", seq], cwd=d)
+    assert r.returncode == 0 and r.stdout == ""
+    got = gzip.open(os.path.join(d, "out.json.gz"), "rt").read()
+    assert got == want.replace(f'"name":"{name}",', "").replace('"outfile":""', '"outfile":"out.json.gz"')
+    # a too-short sequence is an error record, the run still succeeds (hunter.h:299-303)
+    r = run(["hunt", "-g", "genome.fa.gz", "ACGTACG"], cwd=d)
+    assert r.returncode == 0
+    assert r.stdout == '{"errors": [{"title":"Error: Input sequence is shorter than 10 nucleotides!","type":"error"}]}\n'
+
+
+@pytest.mark.gpu
+def test_index_cli_writes_a_loadable_fm9(tmp_path):
+    """`dicey-b200 index genome.fa.gz` then `hunt` on the result reproduces the golden records."""
+    import numpy as np
+    from dicey_b200 import synth
+    d = str(tmp_path)
+    txt = synth.text(42, 8, 125000).tobytes().decode().split("\n")
+    with gzip.open(os.path.join(d, "genome.fa.gz"), "wt") as f:
+        for i, rec in enumerate(r for r in txt if r):
+            f.write(f">chr{i + 1} synthetic\n")
+            for o in range(0, len(rec), 60):
+                f.write(rec[o:o + 60].lower() if i == 3 else rec[o:o + 60])
+                f.write("\n")
+    r = run(["index", "genome.fa.gz"], cwd=d)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(os.path.join(d, "genome.fa.fm9")) and os.path.exists(os.path.join(d, "genome.fa.fm9_check"))
+    fasta_of("t1m_e1", os.path.join(d, "q.fa"))
+    r = run(["hunt", "-g", "genome.fa.gz", "q.fa"], cwd=d)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(GOLDEN, "t1m_e1.jsonl")).read()
+    fai = open(os.path.join(d, "genome.fa.gz.fai")).read().splitlines()
+    assert fai[0].split("\t")[:2] == ["chr1", "125000"] and len(fai) == 8
