@@ -88,6 +88,7 @@ int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* by
   else if (w == "C") { src = idx->Cb.p; nb = 256 * 4; }
   else if (w == "exc_pos") { src = idx->exc_pos.p; nb = (uint64_t)idx->n_exc * 4; }
   else if (w == "exc_sym") { src = idx->exc_sym.p; nb = idx->n_exc; }
+  else if (w == "sa_full") { src = idx->sa_full.p; nb = idx->sa_full.bytes(); }
   else if (w == "present_kb") { src = idx->present_kb.p; nb = idx->present_kb.bytes(); }
   else { set_error("unknown array name"); return DG_ERR_ARG; }
   if (!buf) { *bytes = nb; return DG_OK; }

@@ -164,18 +164,21 @@ __global__ void k_presence(const uint8_t* __restrict__ text, uint64_t n, uint32_
 }
 
 // ---------------------------------------------------------------- text from ISA samples
-__global__ void k_rebuild_text(IndexView ix, const uint32_t* __restrict__ isa, uint64_t nchains, uint8_t* __restrict__ text) {
+// The same walk visits ISA[p] for every p, so it also fills the full suffix array (sa != null).
+__global__ void k_rebuild_text(IndexView ix, const uint32_t* __restrict__ isa, uint64_t nchains, uint8_t* __restrict__ text,
+                               uint32_t* __restrict__ sa) {
   uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchains) return;
   uint64_t n = ix.n, first = c << 6, end = (c + 1) << 6;
   uint32_t row;
   int64_t p;
   if (end <= n - 1) { row = isa[c + 1]; p = (int64_t)end - 1; }
-  else { text[n - 1] = 0; row = 0; p = (int64_t)n - 2; }  // suffix n-1 (the sentinel) is row 0
+  else { text[n - 1] = 0; row = 0; p = (int64_t)n - 2; if (sa) sa[0] = (uint32_t)(n - 1); }  // suffix n-1 (the sentinel) is row 0
   for (; p >= (int64_t)first; --p) {
     uint8_t s;
     row = lf_step(ix, row, &s);
     text[p] = s;
+    if (sa) sa[row] = (uint32_t)p;
   }
 }
 
@@ -524,6 +527,12 @@ static void build_kmer_table(dg_index* ix) {
   DG_CUDA(cudaStreamSynchronize(st));
 }
 
+// HBM capacity traded for locate latency: the whole suffix array (4 n bytes) unless DG_FULL_SA=0
+static bool want_full_sa() {
+  const char* e = getenv("DG_FULL_SA");
+  return !(e && atoi(e) == 0);
+}
+
 // needs ix->text
 static void build_presence_bitmap(dg_index* ix) {
   cudaStream_t st = ix->stream;
@@ -647,7 +656,10 @@ int build_from_fm9(const char* path, int device, dg_index** out) {
     ix->text.alloc(f.n + 64);
     DG_CUDA(cudaMemsetAsync(ix->text.p, 0, f.n + 64, st));
     uint64_t nchains = (f.n - 1) / 64 + 1;
-    k_rebuild_text<<<grid_for(nchains, 128), 128, 0, st>>>(ix->view(), ix->isa_samples.p, nchains, ix->text.p);
+    if (want_full_sa()) ix->sa_full.alloc(f.n);
+    IndexView wv = ix->view();
+    wv.sa_full = nullptr;  // the walk itself must use the samples
+    k_rebuild_text<<<grid_for(nchains, 128), 128, 0, st>>>(wv, ix->isa_samples.p, nchains, ix->text.p, ix->sa_full.p);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaStreamSynchronize(st));
     build_presence_bitmap(ix);
@@ -742,7 +754,8 @@ static void build_from_device_text(dg_index* ix) {
   k_bwt_from_sa<<<grid_for(n, B), B, 0, st>>>(text, sa.p, n, bwt.p, ix->sa_samples.p, ix->isa_samples.p);
   DG_CUDA(cudaGetLastError());
   DG_CUDA(cudaStreamSynchronize(st));
-  sa.release();
+  if (want_full_sa()) { ix->sa_full.p = sa.p; ix->sa_full.count = sa.count; sa.p = nullptr; sa.count = 0; }
+  else sa.release();
   finish_from_bwt(ix, bwt.p, Cb, present);
   bwt.release();
   build_kmer_table(ix);

@@ -57,6 +57,7 @@ struct IndexView {
   const uint2* kmer;          // 4^K half-open SA intervals [x, y) of the ACGT K-mers
   uint32_t K;
   const uint32_t* sa_samples; // SA[32 k]
+  const uint32_t* sa_full;    // SA[row] for every row, or null (then sa_samples + LF walks)
   const uint8_t* text;        // the n text bytes (sentinel included)
   const uint64_t* cum;        // nseq + 1 cumulative seqlen (util.h:201 lengths)
   uint32_t nseq;
@@ -185,6 +186,7 @@ DG_HD uint32_t lf_step(const IndexView& ix, uint32_t row, uint8_t* sym) {
 
 // SA[row]: csa_wt::operator[] (csa_wt.hpp:340-354) with sa_order_sa_sampling, t_dens = 32.
 DG_HD uint32_t sa_value(const IndexView& ix, uint32_t row) {
+  if (ix.sa_full) return ix.sa_full[row];
   uint32_t off = 0;
   while (row & (kSaSample - 1)) { row = lf_step(ix, row, nullptr); ++off; }
   uint64_t v = (uint64_t)ix.sa_samples[row / kSaSample] + off;

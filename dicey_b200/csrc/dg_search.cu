@@ -104,6 +104,7 @@ struct ABuf {  // stream-ordered allocation (cudaMallocAsync pool; reuse across 
     p = nullptr;
     count = 0;
   }
+  void swap(ABuf& o) { std::swap(p, o.p); std::swap(count, o.count); std::swap(st, o.st); }
 };
 
 inline unsigned grid_for(uint64_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
@@ -590,6 +591,65 @@ __global__ void k_unique(BatchDev b, const Cand* __restrict__ cands, uint32_t n,
     if (a.q == c.q && ((a.code ^ c.code) & 1) == 0 && cand_string_cmp(b, a, c) == 0) first = false;
   }
   keep[i] = first ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Radix-sortable image of a candidate: (query, strand) then the neighbour string as 3-bit codes
+// (end = 0 < A < C < G < N < T, the byte order of std::string's operator<), 21 characters per
+// word.  Strings of up to 42 characters are ordered and de-duplicated by the key alone; batches
+// with longer strings take the comparison sort below instead.
+struct CandKey {
+  uint64_t hi, lo;
+  uint32_t qs;    // (query << 1) | strand, or the sentinel (dropped by the antichain rule)
+  uint32_t idx;   // position in the unsorted candidate array
+};
+struct CandKeyDecomposer {
+  __host__ __device__ ::cuda::std::tuple<uint32_t&, uint64_t&, uint64_t&> operator()(CandKey& k) const {
+    return {k.qs, k.hi, k.lo};
+  }
+};
+constexpr int kKeyChars = 42;
+
+__global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t n, uint32_t sentinel, CandKey* __restrict__ keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Cand c = cands[i];
+  const bool indel = b.indel != 0;
+  int strand;
+  Script sc;
+  unpack_script(c.code, indel, strand, sc);
+  const uint8_t* base;
+  int m, koff;
+  query_geom(b, c.q, strand, base, m, koff);
+  uint8_t t[kMaxQuery + 8], s0[kMaxQuery + 8], s1[kMaxQuery + 8];
+  int L = script_ltr(base, m, sc, t);
+  bool keep = !indel || is_minimal(base, m, (int)b.dist[c.q], t, L, s0, s1);
+  CandKey k;
+  k.hi = k.lo = 0;
+  int lim = L < kKeyChars ? L : kKeyChars;
+  for (int j = 0; j < lim; ++j) {
+    uint8_t ch = t[j];
+    uint64_t v = ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 5 : 4;
+    if (j < 21) k.hi |= v << (60 - 3 * j); else k.lo |= v << (60 - 3 * (j - 21));
+  }
+  k.qs = keep ? ((c.q << 1) | (uint32_t)strand) : sentinel;
+  k.idx = i;
+  keys[i] = k;
+}
+__global__ void k_unique_keys(const CandKey* __restrict__ keys, uint32_t n, uint32_t sentinel, uint8_t* __restrict__ keep) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CandKey c = keys[i];
+  bool first = c.qs != sentinel;
+  if (first && i > 0) {
+    CandKey a = keys[i - 1];
+    if (a.qs == c.qs && a.hi == c.hi && a.lo == c.lo) first = false;
+  }
+  keep[i] = first ? 1 : 0;
+}
+__global__ void k_gather_cands(const Cand* __restrict__ cands, const CandKey* __restrict__ keys, uint32_t n, Cand* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cands[keys[i].idx];
 }
 
 // hit budget: take[i] = min(occ, max_loc) per candidate
@@ -1112,46 +1172,78 @@ static int run_impl(dg_batch* b) {
     nsel.alloc(1, st);
     Cand* cur = b->cands.p;
     // ---- antichain rule (edit mode), lexicographic order, de-duplication
-    if (n && b->par.indel) {
+    const int maxq_str = b->par.seed_len ? (int)b->par.seed_len : std::min(b->max_len, kMaxQuery);
+    const bool key_sort = maxq_str + (int)b->par.distance <= kKeyChars && !getenv("DG_MERGE_SORT");
+    if (n && key_sort) {
+      // every string fits the 126-bit key: one kernel (antichain flag + key), one radix sort,
+      // one adjacent-duplicate pass, one gather
+      ABuf<CandKey> ka, kb;
+      ka.alloc(n, st);
+      kb.alloc(n, st);
       keep.alloc(n, st);
-      c2.alloc(n, st);
-      k_minimal<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, keep.p);
+      const uint32_t sentinel = nq >= 0x7FFFFFFFu ? 0xFFFFFFFFu : 2u * nq;
+      int qbits = 1;
+      while (qbits < 32 && (1ULL << qbits) <= (uint64_t)sentinel) ++qbits;
+      k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p);
+      const int begin_bit = (maxq_str + (int)b->par.distance <= 21) ? 64 : 0;
       size_t tb = 0;
-      cub::DeviceSelect::Flagged(nullptr, tb, cur, keep.p, c2.p, nsel.p, (int)n, st);
-      cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, cur, keep.p, c2.p, nsel.p, (int)n, st);
-      launches += 3;
-      uint32_t n2 = 0;
-      DG_CUDA(cudaMemcpyAsync(&n2, nsel.p, 4, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaStreamSynchronize(st));
-      // result now in c2; keep b->cands as the other buffer
-      cur = c2.p;
-      n = n2;
-    }
-    if (n) {
-      size_t tb = 0;
-      CandLess less{bd};
-      cub::DeviceMergeSort::SortKeys(nullptr, tb, cur, (int)n, less, st);
-      cub::DeviceMergeSort::SortKeys(ensure_tmp(tb), tb, cur, (int)n, less, st);
-      launches += 3;
-      if (!keep.p || keep.count < n) keep.alloc(n, st);
-      Cand* other = (cur == c2.p) ? b->cands.p : nullptr;
-      ABuf<Cand> c3;
-      if (!other) { c3.alloc(n, st); other = c3.p; }
-      k_unique<<<grid_for(n, B), B, 0, st>>>(bd, cur, n, keep.p);
-      cub::DeviceSelect::Flagged(nullptr, tb, cur, keep.p, other, nsel.p, (int)n, st);
-      cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, cur, keep.p, other, nsel.p, (int)n, st);
-      launches += 3;
+      cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
+      cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
+      k_unique_keys<<<grid_for(n, B), B, 0, st>>>(kb.p, n, sentinel, keep.p);
+      cub::DeviceSelect::Flagged(nullptr, tb, kb.p, keep.p, ka.p, nsel.p, (int)n, st);
+      cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, kb.p, keep.p, ka.p, nsel.p, (int)n, st);
       uint32_t n3 = 0;
       DG_CUDA(cudaMemcpyAsync(&n3, nsel.p, 4, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaStreamSynchronize(st));
-      if (other == c3.p) {
-        // final list must outlive this scope: move it into b->cands
-        DG_CUDA(cudaMemcpyAsync(b->cands.p, c3.p, (size_t)n3 * sizeof(Cand), cudaMemcpyDeviceToDevice, st));
-        cur = b->cands.p;
-      } else {
-        cur = other;  // == b->cands.p
-      }
+      ABuf<Cand> sorted;
+      sorted.alloc(n3 ? n3 : 1, st);
+      if (n3) k_gather_cands<<<grid_for(n3, B), B, 0, st>>>(cur, ka.p, n3, sorted.p);
+      b->cands.swap(sorted);  // the unsorted buffer is released with `sorted`
+      cur = b->cands.p;
       n = n3;
+      launches += 12;
+    } else {
+      if (n && b->par.indel) {
+        keep.alloc(n, st);
+        c2.alloc(n, st);
+        k_minimal<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, keep.p);
+        size_t tb = 0;
+        cub::DeviceSelect::Flagged(nullptr, tb, cur, keep.p, c2.p, nsel.p, (int)n, st);
+        cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, cur, keep.p, c2.p, nsel.p, (int)n, st);
+        launches += 3;
+        uint32_t n2 = 0;
+        DG_CUDA(cudaMemcpyAsync(&n2, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaStreamSynchronize(st));
+        // result now in c2; keep b->cands as the other buffer
+        cur = c2.p;
+        n = n2;
+      }
+      if (n) {
+        size_t tb = 0;
+        CandLess less{bd};
+        cub::DeviceMergeSort::SortKeys(nullptr, tb, cur, (int)n, less, st);
+        cub::DeviceMergeSort::SortKeys(ensure_tmp(tb), tb, cur, (int)n, less, st);
+        launches += 3;
+        if (!keep.p || keep.count < n) keep.alloc(n, st);
+        Cand* other = (cur == c2.p) ? b->cands.p : nullptr;
+        ABuf<Cand> c3;
+        if (!other) { c3.alloc(n, st); other = c3.p; }
+        k_unique<<<grid_for(n, B), B, 0, st>>>(bd, cur, n, keep.p);
+        cub::DeviceSelect::Flagged(nullptr, tb, cur, keep.p, other, nsel.p, (int)n, st);
+        cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, cur, keep.p, other, nsel.p, (int)n, st);
+        launches += 3;
+        uint32_t n3 = 0;
+        DG_CUDA(cudaMemcpyAsync(&n3, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaStreamSynchronize(st));
+        if (other == c3.p) {
+          // final list must outlive this scope: move it into b->cands
+          DG_CUDA(cudaMemcpyAsync(b->cands.p, c3.p, (size_t)n3 * sizeof(Cand), cudaMemcpyDeviceToDevice, st));
+          cur = b->cands.p;
+        } else {
+          cur = other;  // == b->cands.p
+        }
+        n = n3;
+      }
     }
     b->ncand = n;
     prof_mark(ix, 3);

@@ -52,6 +52,20 @@ def test_index_arrays_stress(indexes):
     assert bytes(got[:-1]) == raw and got[-1] == 0
     sa = np.array(naive_sa(raw), dtype=np.uint32)
     assert np.array_equal(ix.debug_array("sa_samples", np.uint32), sa[::32])
+    assert np.array_equal(ix.debug_array("sa_full", np.uint32), sa)   # rebuilt beside the text by the LF chains
+    # KB-mer presence bitmap: exactly the ACGT-only windows of the text
+    kb = ix.info()["bitmap_k"]
+    bits = ix.debug_array("present_kb", np.uint32)
+    want = np.zeros_like(bits)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    for i in range(len(raw) - kb + 1):
+        w = raw[i:i + kb]
+        if all(ch in code for ch in w):
+            v = 0
+            for ch in w:
+                v = (v << 2) | code[ch]
+            want[v >> 5] |= np.uint32(1 << (v & 31))
+    assert np.array_equal(bits, want)
     # occ blocks: cumulative ACGT counts + bit planes of the BWT
     t = np.frombuffer(raw + b"\0", dtype=np.uint8)
     bwt = t[(sa.astype(np.int64) - 1) % t.size]
@@ -122,7 +136,8 @@ def test_build_text_equals_fm9(indexes, name):
     with Index.build_text(text, 0) as ix:
         assert ix.info()["n"] == ref.info()["n"]
         for what, dt in (("text", np.uint8), ("sa_samples", np.uint32), ("isa_samples", np.uint32), ("occ", np.uint32),
-                         ("C", np.uint32), ("exc_pos", np.uint32), ("exc_sym", np.uint8), ("kmer", np.uint32)):
+                         ("C", np.uint32), ("exc_pos", np.uint32), ("exc_sym", np.uint8), ("kmer", np.uint32),
+                         ("sa_full", np.uint32), ("present_kb", np.uint32)):
             assert np.array_equal(ix.debug_array(what, dt), ref.debug_array(what, dt)), what
 
 
