@@ -59,47 +59,64 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md).  Sampled in-process
+    through NVML every 10 ms (an nvidia-smi child polling the driver perturbs kernel launches);
+    falls back to one nvidia-smi query at the end if NVML is unavailable."""
 
     def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.stop_flag, self.t = device, [], False, None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain list of ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = device
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[device])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.h is None:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        if self.h is None:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i",
+                                      str(self.device)], capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": ["nvml unavailable: one nvidia-smi sample after the run"]}
             except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=1)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.rows))
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max, "samples": len(sm), "reasons": reasons}
 
 
 def make_primers(args, rank: int) -> np.ndarray:
@@ -113,8 +130,10 @@ def write_sample(path: str, primers: np.ndarray):
         f.write(b"\n".join(bytes(row) for row in primers) + b"\n")
 
 
-def run_ref(fm9: str, rec: str, qfile: str, args, threads: int, counters: bool) -> dict:
+def run_ref(fm9: str, rec: str, qfile: str, args, threads: int, counters: bool, records: str | None = None) -> dict:
     cmd = [REF_BIN, "hunt", fm9, rec, qfile, "-d", str(args.distance), "--threads", str(threads)]
+    if records:
+        cmd += ["--records", records]
     if args.hamming:
         cmd.append("-n")
     if counters:
@@ -159,8 +178,24 @@ def cpu_leg(fm9, rec, primers, args, cores, seconds):
     rate = max(r["queries_per_s"], 1e-9)
     n = int(min(len(primers), max(probe_n, rate * seconds)))
     write_sample(qf, primers[:n])
-    r = run_ref(fm9, rec, qf, args, cores, True)
-    return r, n
+    rec_out = os.path.join(tmp, "ref.records.tsv")
+    r = run_ref(fm9, rec, qf, args, cores, True, rec_out)
+    return r, n, rec_out
+
+
+def parity_check(ix, params, primers, n, ref_records: str) -> dict:
+    """canonical dump of the hit records (push order and sorted order, alignment
+    strings included) of the CPU sample, reference vs CUDA path on the same 3 Gb index; SHA-256 of both."""
+    import hashlib
+    res = ix.hunt(primers[:n], params)
+    mine = res.records_tsv(params, primers[:n])
+    ref = "".join(l for l in open(ref_records) if not l.startswith("W\t"))
+    a, b = hashlib.sha256(mine.encode()).hexdigest(), hashlib.sha256(ref.encode()).hexdigest()
+    out = {"primers": int(n), "hits": int(len(res.hits)), "sha256_gpu": a, "sha256_reference": b, "equal": a == b}
+    if a != b:
+        ml, rl = mine.splitlines(), ref.splitlines()
+        out["first_difference"] = next(((i, x, y) for i, (x, y) in enumerate(zip(ml, rl)) if x != y), (min(len(ml), len(rl)), "", ""))
+    return out
 
 
 def main_reference(args):
@@ -319,11 +354,13 @@ def main_b200(args):
     # ---------------- CPU reference beside it (rank 0, single GPU run only) + roofline numerator
     cpu = None
     work = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(REF_BIN):
         try:
             fm9, rec, write_s = ensure_fm9(ix, args)
             cores = os.cpu_count() or 1
-            r, n = cpu_leg(fm9, rec, primers, args, cores, args.cpu_seconds)
+            r, n, ref_records = cpu_leg(fm9, rec, primers, args, cores, args.cpu_seconds)
+            parity = parity_check(ix, params, primers, n, ref_records)
             cpu = {"value": r["queries_per_s"], "unit": "primers/s", "cores": cores, "kind": "reference",
                    "sample": f"first {n} primers of the batch on the same 3 Gb index ({r['loop_s']:.1f} s loop, index load excluded)"}
             work = {k: r[k] / r["queries"] for k in ("R", "L", "H", "X", "strings", "steps")}
@@ -349,20 +386,22 @@ def main_b200(args):
         # term 32 R (L, H, X belong to k_locate / k_verify and are reported beside it)
         alg = 32 * work["R"] * nq
         achieved = alg / (ms_search / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k_search_packed", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_primer": alg / nq,
                 "algorithmic_bytes_per_primer_all_kernels": 32 * work["R"] + 32 * work["L"] + 4 * work["H"] + work["X"],
                 "kernel_ms": ms_search, "kernel_share_of_step": ms_search / (ms / args.steps),
                 "note": "algorithmic bytes = 32 B x the reference's rank queries (one per backward-search step of every "
-                        "neighbour string, counted by the instrumented reference); the K-mer interval table answers the "
-                        "first K steps of each string with one lookup, so frac > 1 is expected; traffic / frac_dram "
-                        "are the measured DRAM bytes of the same kernel (ncu)"}
+                        "neighbour string, counted by the instrumented reference in this run); the presence bitmap and the "
+                        "K-mer interval table answer most of them without DRAM, so frac > 1 is expected; traffic = DRAM "
+                        "bytes per launch of the same kernel from ncu --set full (profiles/), frac_dram = traffic / "
+                        "kernel time / peak; kernel_ms is the CUDA-event time of the search stage (k_search_packed plus "
+                        "the general k_search, which has no work on an ACGT-only batch)"}
         tr = os.path.join(ROOT, "profiles", "k_search_traffic.json")
         if os.path.exists(tr):
             try:
                 t_ = json.load(open(tr))
-                if t_.get("kmer") == info["kmer"] and t_.get("primers") == nq:
+                if t_.get("kmer") == info["kmer"] and t_.get("bitmap_k") == info["bitmap_k"] and t_.get("primers") == nq:
                     roof["traffic"] = t_.get("dram_bytes_per_launch")
                     roof["frac_dram"] = roof["traffic"] / (ms_search / 1e3) / 1e9 / peak_gbs
             except Exception:
@@ -374,16 +413,17 @@ def main_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded",
-                       "global_primers_per_step": world * nq, "l2": "inputs larger than L2: 7 GB index, random access",
-                       "kmer_table_K": info["kmer"], "index_device_bytes": info["device_bytes"],
+                       "global_primers_per_step": world * nq, "l2": "inputs larger than L2: random access into a 34 GB index",
+                       "kmer_table_K": info["kmer"], "presence_bitmap_K": info["bitmap_k"], "index_device_bytes": info["device_bytes"],
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "primers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "phases_ms_stage_run_fetch_free": phases, "hunt_call_ms": step_ms},
             "gpu_launches": int(sum(p["launches"] for p in profs)),
-            "stages_ms": stage,
+            "stages_ms": stage, "step_ms_total": [round(p["ms_total"], 3) for p in profs],
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity,
         }
         print(json.dumps(line))
     ix.close()

@@ -223,6 +223,26 @@ class HuntResult:
         """search: (refIndex, chrpos, alignpos, strand, genomicseq) per candidate, push order."""
         return [self._rec(h, True) for h in self.hits[int(self.qoff[q]):int(self.qoff[q + 1])]]
 
+    def records_tsv(self, params: HuntParams, raws=None, q_lo: int = 0, q_hi: int | None = None) -> str:
+        """Canonical dump of queries [q_lo, q_hi): per query one Q line (index, normalised sequence,
+        clamped distance, #messages, #hits), its messages (M), the hits in push order (P) and after
+        std::sort (S) -- the format of `dicey_ref hunt --records` (oracle/ref_driver.cpp), used for
+        whole-batch parity checks (bench.py, tests)."""
+        q_hi = self.nq if q_hi is None else q_hi
+        out = []
+        for q in range(q_lo, q_hi):
+            raw = None if raws is None else bytes(raws[q])
+            msgs = self.messages(q, params, raw)
+            if msgs and msgs[0].startswith("Error"):
+                seq, dist, push, srt = ("" if raw is None else raw.decode()), params.distance, [], []
+            else:
+                seq, dist, push, srt = self.sequence(q).decode(), int(self.dist[q]), self.push_hits(q), self.sorted_hits(q)
+            out.append(f"Q\t{q - q_lo}\t{seq}\t{dist}\t{len(msgs)}\t{len(push)}\n")
+            out.extend(f"M\t{m}\n" for m in msgs)
+            out.extend("P\t%d\t%d\t%d\t%s\t%s\t%s\n" % h for h in push)
+            out.extend("S\t%d\t%d\t%d\t%s\t%s\t%s\n" % h for h in srt)
+        return "".join(out)
+
     def messages(self, q: int, params: HuntParams, raw: bytes | None = None):
         """The msg vector of hunter.h for query q, in the reference's order."""
         msg = []

@@ -37,9 +37,13 @@ void dg_index_close(dg_index* idx) {
   cudaSetDevice(idx->device);
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   if (idx->prof.created) for (auto& e : idx->prof.ev) cudaEventDestroy(e);
-  cudaStream_t st = idx->stream;
+  cudaStream_t st = idx->stream, cs = idx->copy_stream, s2 = idx->stream2;
+  if (s2) cudaStreamSynchronize(s2);
+  if (cs) cudaStreamSynchronize(cs);
   delete idx;
   if (st) cudaStreamDestroy(st);
+  if (s2) cudaStreamDestroy(s2);
+  if (cs) cudaStreamDestroy(cs);
 }
 
 uint64_t dg_index_size(const dg_index* idx) { return idx ? idx->n : 0; }

@@ -435,6 +435,122 @@ DG_HD int needle_align(const uint8_t* g, int mg, const uint8_t* s, int n, Tr tr,
 
 
 // ------------------------------------------------------------------------------------------
+// Banded form of needle_align for the hunt loop.  In `hunt` the genomic context always contains
+// the matched neighbour string, so the optimal score is >= -dmax (dmax = the query's distance).
+// Every cell on an optimal full path then satisfies  -dmax <= row - col <= (mg - n) + dmax:
+//   * 0 < col < n, score >= -dmax  =>  col - (row - j) <= dmax for some free start j >= 0;
+//   * the rest of the path aligns s[col, n) with at most mg - row genomic symbols (trailing ones
+//     are free), so (n - col) - (mg - row) <= dmax.
+// Cells outside the band are treated as -inf.  Banded values never exceed the true ones and are
+// equal on every optimal full path (its cells' optimal predecessors are again such cells), so a
+// candidate that loses or ties in the full matrix (needle.h:87-101: horizontal, then vertical, then
+// diagonal) loses or ties identically here: score, traceback and alignment are those of needle().
+// Band width W = mg - n + 2 dmax + 1 <= kBandMax; trace = 2 bits x W per row in one 32-bit word.
+constexpr int kBandMax = 11;   // distance 2: mg - n <= 3 d, W <= 5 d + 1
+constexpr int kBandNeg = -1000;
+
+// 4-bit symbol classes for the register-resident query window: equal bytes <=> equal classes for
+// everything a normalised query can hold (A C G T N); any other text byte gets a class of its own.
+DG_HD uint32_t sym_class(uint8_t b) {
+  return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 3u : b == 'T' ? 4u : b == 'N' ? 5u : 6u;
+}
+
+// DP + trace.  tr: mg + 1 words.  Returns the score (srow[n] of needle()).
+DG_HD int needle_banded_fill(const uint8_t* g, int mg, const uint8_t* s, int n, int dmax, uint32_t* tr) {
+  const int hi = mg - n + dmax;            // largest row - col in the band
+  const int W = hi + dmax + 1;
+  // query as 4-bit classes, 16 per word (n <= 31)
+  uint64_t sq0 = 0, sq1 = 0;
+  for (int i = 0; i < n; ++i) {
+    uint64_t c = sym_class(s[i]);
+    if (i < 16) sq0 |= c << (4 * i); else sq1 |= c << (4 * (i - 16));
+  }
+  auto qclass = [&](int i) -> uint32_t {  // class of s[i], 0 outside the query
+    if (i < 0 || i >= n) return 0u;
+    return (uint32_t)(((i < 16 ? sq0 : sq1) >> (4 * (i & 15))) & 15u);
+  };
+  int v[kBandMax];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kBandMax; ++k) v[k] = kBandNeg;
+  // win holds the classes of s[col - 1] for the W columns of the current row: col = row - hi + k
+  uint64_t win = 0;
+  for (int k = 0; k < W; ++k) win |= (uint64_t)qclass(0 - hi + k - 1) << (4 * k);
+  int score = 0;
+  for (int row = 0; row <= mg; ++row) {
+    const uint32_t gc = row ? sym_class(g[row - 1]) : 0u;
+    uint32_t bits = 0;
+    const int c0 = row - hi;   // column of k = 0
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < kBandMax; ++k) {
+      if (k < W) {
+        const int col = c0 + k;
+        int val = kBandNeg, t = 0;
+        if (col >= 0 && col <= n) {
+          if (row == 0) {
+            val = -col; t = col ? 1 : 0;
+          } else if (col == 0) {
+            val = 0; t = 2;
+          } else {
+            const uint32_t qc = (uint32_t)((win >> (4 * k)) & 15u);
+            const int diag = v[k] + (gc == qc ? 0 : -1);
+            const int up = (k + 1 < W ? v[k + 1] : kBandNeg) + (col == n ? 0 : -1);
+            const int left = (k ? v[k - 1] : kBandNeg) - 1;
+            val = diag > up ? diag : up;
+            if (left > val) val = left;
+            t = val == left ? 1 : (val == up ? 2 : 0);
+          }
+          if (col == n) score = val;
+        }
+        v[k] = val;
+        bits |= (uint32_t)t << (2 * k);
+      }
+    }
+    tr[row] = bits;
+    // next row: every column index grows by one
+    win = (win >> 4) | ((uint64_t)qclass(c0 + W - 1) << (4 * (W - 1)));
+  }
+  return score;
+}
+
+// Traceback, first pass: number of alignment columns, leading and trailing columns whose query
+// row is a gap (hunter.h:69-77, 393-400).
+DG_HD void needle_banded_shape(const uint32_t* tr, int mg, int n, int dmax, int* nops_out, int* lead_out, int* trail_out) {
+  const int hi = mg - n + dmax;
+  int row = mg, col = n, nops = 0, trail = 0, run_v = 0;
+  bool seen_query = false;
+  while (row > 0 || col > 0) {
+    const int t = (int)((tr[row] >> (2 * (col - (row - hi)))) & 3u);
+    if (t == 1) { --col; seen_query = true; run_v = 0; }
+    else if (t == 2) { --row; if (!seen_query) ++trail; ++run_v; }
+    else { --row; --col; seen_query = true; run_v = 0; }
+    ++nops;
+  }
+  *nops_out = nops;
+  *trail_out = trail;
+  *lead_out = seen_query ? run_v : 0;   // the vertical moves made last are the leftmost columns
+}
+
+// Traceback, second pass: writes the kept columns (left to right) of both alignment rows.
+DG_HD void needle_banded_emit(const uint32_t* tr, const uint8_t* g, int mg, const uint8_t* s, int n, int dmax, int nops,
+                              int lead, int trail, uint8_t* refalign, uint8_t* queryalign) {
+  const int hi = mg - n + dmax;
+  int row = mg, col = n;
+  for (int step = 0; step < nops; ++step) {
+    const int t = (int)((tr[row] >> (2 * (col - (row - hi)))) & 3u);
+    uint8_t a0, a1;
+    if (t == 1) { --col; a0 = '-'; a1 = s[col]; }
+    else if (t == 2) { --row; a0 = g[row]; a1 = '-'; }
+    else { --row; --col; a0 = g[row]; a1 = s[col]; }
+    const int j = nops - 1 - step;           // column index from the left
+    if (j >= lead && j < nops - trail) { refalign[j - lead] = a0; queryalign[j - lead] = a1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Packed fast path: an ACGT-only string of length <= 31 as 2-bit codes, LAST base in the low
 // bits (so the low 2K bits are the K-mer table index and base t from the right is bits 2t..2t+1).
 // apply_event_packed applies one canonical event (k < 4 substitute code k, 4 delete, 5.. insert

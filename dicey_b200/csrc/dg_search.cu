@@ -20,7 +20,10 @@
 #include <cstring>
 #include <cub/cub.cuh>
 #include <map>
+#include <condition_variable>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <new>
 
 #include "dg_common.cuh"
@@ -702,9 +705,9 @@ struct VerifyArgs {
   const uint64_t* keys;      // sorted (candidate << 32 | position)
   uint64_t nhits;
   dg_hit* hits;
-  uint8_t* pool;
-  uint32_t pool_stride;      // bytes per hit in the pool
-  uint8_t* scratch;          // NW scratch for alignments too large for the thread-local path
+  uint8_t* pool;             // alignment pool: strings back to back, claimed block by block
+  unsigned long long* pool_cursor;
+  uint8_t* scratch;          // NW scratch for alignments too large for the thread-local paths
   uint32_t scratch_stride;
   uint32_t trace_bytes, srow_ints;
   uint64_t first_hit;        // chunk start
@@ -713,75 +716,138 @@ struct VerifyArgs {
 
 constexpr int kLocalQ = 31;   // thread-local NW: query columns
 constexpr int kLocalG = 40;   // thread-local NW: genomic rows
+constexpr int kVerifyBlock = 128;
 
-__global__ void __launch_bounds__(128) k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.chunk) return;
-  uint64_t h = a.first_hit + t;
-  uint32_t lo = 0, hi = a.ncand;
-  while (hi - lo > 1) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (a.hit_off[mid] <= h) lo = mid; else hi = mid;
-  }
-  Cand c = a.cands[lo];
-  uint64_t j = h - a.hit_off[lo];
-  uint64_t pos = a.keys[a.loc_off[lo] + j] & 0xFFFFFFFFULL;
+// One thread per hit (hunter.h:358-432 / silica.h:475-573).  Three alignment paths:
+//   banded   hunt, edit mode, query <= 31, band <= kBandMax: register-resident banded DP, one trace
+//            word per row, alignment written straight to the pool (needle_banded_* in dg_core.cuh)
+//   local    anything else that fits 31 x 40: the full matrix in thread-local memory
+//   scratch  larger alignments: the full matrix in a global scratch slab
+// The pool has no per-hit stride: each block sums the bytes its hits need (one block scan) and
+// claims that many with one atomicAdd, so only the bytes that travel to the host are written.
+__global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
+  __shared__ unsigned long long s_warp[kVerifyBlock / 32];
+  __shared__ unsigned long long s_base;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < a.chunk;
   const bool indel = b.indel != 0;
-  int strand;
-  Script sc;
-  unpack_script(c.code, indel, strand, sc);
-  const uint8_t* base;
-  int mq, koff;
-  query_geom(b, c.q, strand, base, mq, koff);
-  const int m = script_len(mq, sc);             // neighbour length
-  const int d = (int)b.dist[c.q];
-  // hunter.h:358-362
-  uint32_t refIndex, chrpos;
-  locate_record(ix.cum, ix.nseq, pos, refIndex, chrpos);
-  // context (hunter.h:318-323,363-378; silica.h:480-497)
-  uint64_t pre_extract = indel ? d : 0, post_extract = indel ? d : 0;
-  if (b.seed_len) { if (strand) post_extract += koff; else pre_extract += koff; }
-  if (pre_extract > pos) pre_extract = pos;
-  if (pos + m + post_extract > ix.n) post_extract = ix.n - pos - m;
-  const uint8_t* T = ix.text;
-  uint64_t pre = 0;
-  while (pre < pre_extract && T[pos - 1 - pre] != '\n') ++pre;   // keep what follows the last '\n'
-  uint64_t post = 0;
-  while (post < post_extract && T[pos + m + post] != '\n') ++post;
-  const uint8_t* g = T + pos - pre;
-  const int mg = (int)(pre + m + post);
-  if (b.seed_len ? (pre <= chrpos) : (pre < chrpos)) chrpos -= (uint32_t)pre;  // silica.h:501 / hunter.h:382
   dg_hit out;
   memset(&out, 0, sizeof(out));
-  out.query = c.q;
-  out.chr = refIndex;
-  out.text_pos = pos;
-  out.strand = strand ? '-' : '+';
-  out.aln_off = h * a.pool_stride;
-  uint8_t* slot = a.pool + out.aln_off;
-  if (b.seed_len || indel) {
-    int lead = 0, score = 0, kept = 0;
-    if (mq <= kLocalQ && mg <= kLocalG) {
-      // thread-local DP: one 64-bit trace word per row
-      uint64_t rows[kLocalG + 1];
-      int srow[kLocalQ + 1];
-      uint8_t ops[kLocalQ + kLocalG + 1], ra[kLocalQ + kLocalG + 1], qa[kLocalQ + kLocalG + 1];
-      uint8_t gl[kLocalG], ql[kLocalQ];
-      for (int i = 0; i < mg; ++i) gl[i] = g[i];
-      for (int i = 0; i < mq; ++i) ql[i] = base[i];
-      for (int i = 0; i <= mg; ++i) rows[i] = 0;
-      kept = needle_align(gl, mg, ql, mq, TraceRows64{rows}, srow, ops, ra, qa, &lead, &score);
-      if (!b.seed_len) for (int i = 0; i < kept; ++i) { slot[i] = ra[i]; slot[kept + i] = qa[i]; }
-    } else {
-      uint8_t* scr = a.scratch + t * (uint64_t)a.scratch_stride;
-      int* srow = (int*)scr;
-      uint8_t* trace = scr + a.srow_ints * 4;
-      uint8_t* ops = trace + a.trace_bytes;
-      uint8_t* ra = ops + (mg + mq + 4);
-      uint8_t* qa = ra + (mg + mq + 4);
-      kept = needle_align(g, mg, base, mq, TraceBytes{trace, mq + 1}, srow, ops, ra, qa, &lead, &score);
-      if (!b.seed_len) for (int i = 0; i < kept; ++i) { slot[i] = ra[i]; slot[kept + i] = qa[i]; }
+  uint32_t tr[kLocalG + 1];
+  uint64_t rows[kLocalG + 1];
+  const uint8_t* g = nullptr;
+  const uint8_t* base = nullptr;
+  int mq = 0, mg = 0, d = 0, mode = 0;  // 1 banded, 2 local, 3 scratch, 4 Hamming
+  int nops = 0, lead = 0, trail = 0, kept = 0, score = 0;
+  uint32_t chrpos = 0, bytes = 0;
+  uint64_t h = 0;
+  if (valid) {
+    h = a.first_hit + t;
+    uint32_t lo = 0, hi = a.ncand;
+    while (hi - lo > 1) {
+      uint32_t mid = lo + ((hi - lo) >> 1);
+      if (a.hit_off[mid] <= h) lo = mid; else hi = mid;
     }
+    Cand c = a.cands[lo];
+    uint64_t j = h - a.hit_off[lo];
+    uint64_t pos = a.keys[a.loc_off[lo] + j] & 0xFFFFFFFFULL;
+    int strand, koff;
+    Script sc;
+    unpack_script(c.code, indel, strand, sc);
+    query_geom(b, c.q, strand, base, mq, koff);
+    const int m = script_len(mq, sc);             // neighbour length
+    d = (int)b.dist[c.q];
+    // hunter.h:358-362
+    uint32_t refIndex;
+    locate_record(ix.cum, ix.nseq, pos, refIndex, chrpos);
+    // context (hunter.h:318-323,363-378; silica.h:480-497)
+    uint64_t pre_extract = indel ? d : 0, post_extract = indel ? d : 0;
+    if (b.seed_len) { if (strand) post_extract += koff; else pre_extract += koff; }
+    if (pre_extract > pos) pre_extract = pos;
+    if (pos + m + post_extract > ix.n) post_extract = ix.n - pos - m;
+    const uint8_t* T = ix.text;
+    uint64_t pre = 0;
+    while (pre < pre_extract && T[pos - 1 - pre] != '\n') ++pre;   // keep what follows the last '\n'
+    uint64_t post = 0;
+    while (post < post_extract && T[pos + m + post] != '\n') ++post;
+    g = T + pos - pre;
+    mg = (int)(pre + m + post);
+    if (b.seed_len ? (pre <= chrpos) : (pre < chrpos)) chrpos -= (uint32_t)pre;  // silica.h:501 / hunter.h:382
+    out.query = c.q;
+    out.chr = refIndex;
+    out.text_pos = pos;
+    out.strand = strand ? '-' : '+';
+    if (b.seed_len || indel) {
+      const int band_hi = mg - mq + d;
+      if (!b.seed_len && mq <= kLocalQ && mg <= kLocalG && band_hi >= 0 && band_hi + d + 1 <= kBandMax) {
+        mode = 1;
+        score = needle_banded_fill(g, mg, base, mq, d, tr);
+        needle_banded_shape(tr, mg, mq, d, &nops, &lead, &trail);
+        kept = nops - lead - trail;
+      } else if (mq <= kLocalQ && mg <= kLocalG) {
+        mode = 2;
+      } else {
+        mode = 3;
+      }
+      bytes = b.seed_len ? (uint32_t)mg : 0u;  // modes 2 / 3 (hunt) learn their size below
+    } else {
+      mode = 4;
+      bytes = (uint32_t)(mg + mq);
+    }
+  }
+  // modes 2 and 3 run the full-matrix DP before the pool offset is known: keep the alignment in
+  // thread-local / scratch memory and copy it afterwards
+  uint8_t ra[kLocalQ + kLocalG + 1], qa[kLocalQ + kLocalG + 1];
+  uint8_t *ra_p = ra, *qa_p = qa;
+  if (mode == 2) {
+    int srow[kLocalQ + 1];
+    uint8_t ops[kLocalQ + kLocalG + 1];
+    for (int i = 0; i <= mg; ++i) rows[i] = 0;
+    kept = needle_align(g, mg, base, mq, TraceRows64{rows}, srow, ops, ra, qa, &lead, &score);
+    if (!b.seed_len) bytes = 2u * (uint32_t)kept;
+  } else if (mode == 3) {
+    uint8_t* scr = a.scratch + t * (uint64_t)a.scratch_stride;
+    int* srow = (int*)scr;
+    uint8_t* trace = scr + a.srow_ints * 4;
+    uint8_t* ops = trace + a.trace_bytes;
+    ra_p = ops + (mg + mq + 4);
+    qa_p = ra_p + (mg + mq + 4);
+    kept = needle_align(g, mg, base, mq, TraceBytes{trace, mq + 1}, srow, ops, ra_p, qa_p, &lead, &score);
+    if (!b.seed_len) bytes = 2u * (uint32_t)kept;
+  } else if (mode == 1) {
+    bytes = 2u * (uint32_t)kept;
+  }
+  // block-wide exclusive scan of `bytes`, one atomicAdd per block
+  unsigned long long incl = bytes;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += up;
+  }
+  if (lane == 31) s_warp[wib] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < kVerifyBlock / 32; ++w) { unsigned long long x = s_warp[w]; s_warp[w] = tot; tot += x; }
+    s_base = tot ? atomicAdd(a.pool_cursor, tot) : 0ULL;
+  }
+  __syncthreads();
+  if (!valid) return;
+  out.aln_off = s_base + s_warp[wib] + (incl - bytes);
+  uint8_t* slot = a.pool + out.aln_off;
+  if (mode == 4) {
+    // needleScore (hunter.h:79-88): mismatches over min(|genomic|, |query|); the record carries
+    // refalign = genomicseq and queryalign = the query
+    int sc2 = 0;
+    int lim = mg < mq ? mg : mq;
+    for (int i = 0; i < lim; ++i) if (g[i] != base[i]) --sc2;
+    for (int i = 0; i < mg; ++i) slot[i] = g[i];
+    for (int i = 0; i < mq; ++i) slot[mg + i] = base[i];
+    out.aln_len = (uint32_t)mg;
+    out.score = sc2;
+    out.start = chrpos + 1;
+    out.alignpos = out.start;
+  } else {
     out.score = score;
     if (b.seed_len) {
       // search: genomic context for the Tm gate + alignpos (silica.h:522-532)
@@ -790,40 +856,14 @@ __global__ void __launch_bounds__(128) k_verify(IndexView ix, BatchDev b, Verify
       out.start = chrpos;
       out.alignpos = chrpos + (uint32_t)lead;
     } else {
+      if (mode == 1) needle_banded_emit(tr, g, mg, base, mq, d, nops, lead, trail, slot, slot + kept);
+      else for (int i = 0; i < kept; ++i) { slot[i] = ra_p[i]; slot[kept + i] = qa_p[i]; }
       out.aln_len = (uint32_t)kept;
       out.start = chrpos + (uint32_t)lead + 1;  // hunter.h:399,402
       out.alignpos = out.start;
     }
-  } else {
-    // needleScore (hunter.h:79-88): mismatches over min(|genomic|, |query|)
-    int score = 0;
-    int lim = mg < mq ? mg : mq;
-    for (int i = 0; i < lim; ++i) if (g[i] != base[i]) --score;
-    for (int i = 0; i < mg; ++i) slot[i] = g[i];
-    // Hamming records carry refalign = genomicseq and queryalign = the query; both have length
-    // mq here (no context in Hamming mode, neighbour length = query length)
-    for (int i = 0; i < mq; ++i) slot[mg + i] = base[i];
-    out.aln_len = (uint32_t)mg;
-    out.score = score;
-    out.start = chrpos + 1;
-    out.alignpos = out.start;
   }
   a.hits[h] = out;
-}
-
-// alignment pool compaction: strided slots -> back-to-back strings (fewer D2H bytes)
-__global__ void k_aln_bytes(const dg_hit* __restrict__ hits, uint64_t n, uint32_t per_hit_mult, uint64_t* __restrict__ len) {
-  uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < n) len[h] = (uint64_t)hits[h].aln_len * per_hit_mult;
-  if (h == n) len[h] = 0;
-}
-__global__ void k_compact_pool(dg_hit* __restrict__ hits, uint64_t n, const uint64_t* __restrict__ off,
-                               const uint8_t* __restrict__ src, uint8_t* __restrict__ dst) {
-  uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= n) return;
-  uint64_t from = hits[h].aln_off, to = off[h], nb = off[h + 1] - off[h];
-  for (uint64_t i = 0; i < nb; ++i) dst[to + i] = src[from + i];
-  hits[h].aln_off = to;
 }
 
 __global__ void k_count(const Cand* __restrict__ cands, uint32_t n, unsigned long long* __restrict__ counts) {
@@ -831,6 +871,14 @@ __global__ void k_count(const Cand* __restrict__ cands, uint32_t n, unsigned lon
   if (i >= n) return;
   Cand c = cands[i];
   atomicAdd(&counts[c.q], (unsigned long long)(c.r - c.l));
+}
+
+// chunked dg_hunt_batch: chunk-local query ids, pool offsets and hit offsets -> batch-global
+__global__ void k_rebase(dg_hit* __restrict__ hits, uint64_t nhits, uint64_t* __restrict__ qoff, uint32_t nq1,
+                         uint32_t q0, uint64_t pool_base, uint64_t hit_base) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nhits) { hits[i].query += q0; hits[i].aln_off += pool_base; }
+  if (i < nq1) qoff[i] += hit_base;
 }
 
 // exact backward search of literal patterns (one thread per pattern)
@@ -938,6 +986,15 @@ struct HostBuf {
     if (p) g_pin.put(HostBlock{p, cap, pinned});
     p = nullptr; bytes = cap = 0; pinned = false;
   }
+  // capacity >= need, keeping the first `used` bytes (the caller has drained copies into p)
+  void reserve(size_t need, size_t used, bool pin) {
+    if (need <= cap) return;
+    HostBuf nb;
+    nb.alloc(need + (need >> 2), pin);
+    if (used) memcpy(nb.p, p, used);
+    std::swap(p, nb.p); std::swap(cap, nb.cap); std::swap(pinned, nb.pinned);
+    nb.bytes = 0;
+  }
 };
 }  // namespace
 
@@ -949,6 +1006,7 @@ struct dg_result {
 
 struct dg_batch {
   dg_index* ix = nullptr;
+  cudaStream_t st = nullptr;   // every kernel, allocation and copy of this batch
   dg_params par;
   uint32_t nq = 0;
   uint64_t nbytes = 0;
@@ -973,7 +1031,6 @@ struct dg_batch {
   uint64_t nhits = 0;
   uint64_t pool_bytes = 0;   // compacted alignment pool
   uint32_t pool_stride = 0;
-  ABuf<uint8_t> pool2;
   bool ran = false;
 };
 
@@ -988,7 +1045,7 @@ static BatchDev batch_dev(const dg_batch* b) {
 }
 
 static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* par,
-                      dg_batch** out) {
+                      dg_batch** out, cudaStream_t on_stream = nullptr) {
   if (!ix || !offsets || !par || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
   if (par->distance > (uint32_t)kMaxDist) {
     set_error("distance > 2 is outside the device path (DESIGN.md, Limits)");
@@ -1000,10 +1057,14 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
   }
   if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return DG_ERR_ARG; }
   dg_batch* b = new dg_batch();
+  static const bool trace = getenv("DG_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double ts0 = now();
   try {
     DG_CUDA(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = on_stream ? on_stream : ix->stream;
     b->ix = ix;
+    b->st = st;
     b->par = *par;
     if (b->par.max_locations == 0) b->par.max_locations = 1;
     b->nq = nq;
@@ -1012,7 +1073,19 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     bool have[256];
     memset(have, 0, sizeof(have));
     int minL = 1 << 30, maxL = 0;
-    for (uint32_t q = 0; q < nq; ++q) {
+    // equal-length batches (the common case) are recognised by one branch-free pass
+    bool equal_len = nq > 0;
+    if (nq) {
+      const uint64_t L0 = offsets[1];
+      uint64_t bad = 0;
+      for (uint32_t q = 0; q <= nq; ++q) bad |= offsets[q] ^ ((uint64_t)q * L0);
+      equal_len = bad == 0;
+      if (equal_len) {
+        minL = maxL = L0 > 100000 ? 100000 : (int)L0;
+        if (!par->seed_len && L0 <= (uint64_t)kMaxQuery) have[L0] = true;
+      }
+    }
+    for (uint32_t q = 0; q < nq && !equal_len; ++q) {
       if (offsets[q + 1] < offsets[q]) { set_error("offsets must be non-decreasing"); delete b; return DG_ERR_ARG; }
       uint64_t L = offsets[q + 1] - offsets[q];
       int Li = L > 100000 ? 100000 : (int)L;
@@ -1043,6 +1116,7 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
         sub[m] = ub > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)ub;
       }
     }
+    const double ts1 = now();
     b->tab.alloc(tab.size(), st);
     b->tab_off.alloc(512, st);
     b->tab_cnt.alloc(512, st);
@@ -1071,10 +1145,12 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     b->unit_off.alloc((size_t)nq + 1, st);
     b->status.alloc(nq, st);
     b->dist.alloc(nq, st);
+    const double ts2 = now();
     DG_CUDA(cudaMemcpyAsync(b->raw.p, seqs, b->nbytes, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(b->off.p, offsets, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
     // the copies above read caller memory: finish them before returning ownership
     DG_CUDA(cudaStreamSynchronize(st));
+    if (trace) fprintf(stderr, "[dg_batch_stage] scan+tables %.3f ms, allocs %.3f ms, copies %.3f ms\n", ts1 - ts0, ts2 - ts1, now() - ts2);
     *out = b;
     return DG_OK;
   } catch (CudaFail& e) {
@@ -1083,8 +1159,12 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
   }
 }
 
-static void prof_mark(dg_index* ix, int i) {
-  if (!ix->prof.enabled) return;
+static thread_local double g_host_mark[8];
+static void prof_mark(dg_index* ix, int i, cudaStream_t st = nullptr) {
+  if (st && st != ix->stream) return;   // chunk-pipeline batches on the second stream are not profiled
+  static const bool trace = getenv("DG_TRACE") != nullptr;
+  if (trace) g_host_mark[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (!ix->prof.enabled) return;   // (stage timings are taken on the index stream only)
   if (!ix->prof.created) {
     for (auto& e : ix->prof.ev) cudaEventCreate(&e);
     ix->prof.created = true;
@@ -1096,7 +1176,7 @@ static int run_impl(dg_batch* b) {
   dg_index* ix = b->ix;
   try {
     DG_CUDA(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = b->st;
     const unsigned B = 256;
     const uint32_t nq = b->nq;
     uint64_t launches = 0;
@@ -1111,7 +1191,7 @@ static int run_impl(dg_batch* b) {
       if (bytes > tmp_cap) { tmp.alloc(bytes + (bytes >> 3) + 256, st); tmp_cap = tmp.count; }
       return tmp.p;
     };
-    prof_mark(ix, 0);
+    prof_mark(ix, 0, st);
     // ---- prepare
     DG_CUDA(cudaMemsetAsync(b->units.p, 0, ((size_t)nq + 1) * 8, st));
     DG_CUDA(cudaMemsetAsync(b->irregular.p, 0, 4, st));
@@ -1122,7 +1202,7 @@ static int run_impl(dg_batch* b) {
       cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, b->units.p, b->unit_off.p, (int)(nq + 1), st);
       launches += 2;
     }
-    prof_mark(ix, 1);
+    prof_mark(ix, 1, st);
     // ---- search
     uint64_t cap64 = 32ULL * nq + (1ULL << 20);
     if (b->par.distance >= 2) cap64 = 256ULL * nq + (1ULL << 20);
@@ -1153,7 +1233,7 @@ static int run_impl(dg_batch* b) {
       k_search<<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
       launches += 2;
     }
-    prof_mark(ix, 2);
+    prof_mark(ix, 2, st);
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
     DG_CUDA(cudaMemcpyAsync(hc, ctr.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1246,18 +1326,20 @@ static int run_impl(dg_batch* b) {
       }
     }
     b->ncand = n;
-    prof_mark(ix, 3);
+    prof_mark(ix, 3, st);
     // ---- count-only mode (padlock.h:381-427, silica.h:365-394)
     if (b->counts_only) {
       b->counts.alloc(nq ? nq : 1, st);
       DG_CUDA(cudaMemsetAsync(b->counts.p, 0, (size_t)(nq ? nq : 1) * 8, st));
       if (n) { k_count<<<grid_for(n, B), B, 0, st>>>(cur, n, b->counts.p); ++launches; }
-      prof_mark(ix, 4);
-      prof_mark(ix, 5);
+      prof_mark(ix, 4, st);
+      prof_mark(ix, 5, st);
       b->ran = true;
-      ix->prof.launches = launches;
-      ix->prof.last.scripts = h_scripts;
-      ix->prof.last.candidates = n_candidates;
+      if (st == ix->stream) {
+        ix->prof.launches = launches;
+        ix->prof.last.scripts = h_scripts;
+        ix->prof.last.candidates = n_candidates;
+      }
       return DG_OK;
     }
     // ---- hit budget
@@ -1313,7 +1395,7 @@ static int run_impl(dg_batch* b) {
       launches += 4;
       sorted_keys = keys2.p;
     }
-    prof_mark(ix, 4);
+    prof_mark(ix, 4, st);
     // ---- verify
     b->nhits = nhits;
     int maxq = b->par.seed_len ? (int)b->par.seed_len : std::min(b->max_len, kMaxQuery);
@@ -1322,11 +1404,15 @@ static int run_impl(dg_batch* b) {
     uint32_t aln_max = (uint32_t)(maxg + maxq);
     b->pool_stride = b->par.seed_len ? (uint32_t)maxg : (b->par.indel ? 2 * aln_max : (uint32_t)(maxg + maxq));
     b->hits.alloc(nhits ? nhits : 1, st);
-    b->pool.alloc(nhits ? nhits * b->pool_stride : 1, st);
+    b->pool.alloc(nhits ? nhits * b->pool_stride : 1, st);   // upper bound; pool_bytes of it are used
+    b->pool_bytes = 0;
     if (nhits) {
+      ABuf<unsigned long long> cursor;
+      cursor.alloc(1, st);
+      DG_CUDA(cudaMemsetAsync(cursor.p, 0, 8, st));
       VerifyArgs a;
       a.cands = cur; a.ncand = n; a.hit_off = hit_off.p; a.loc_off = loc_off.p; a.keys = sorted_keys; a.nhits = nhits;
-      a.hits = b->hits.p; a.pool = b->pool.p; a.pool_stride = b->pool_stride;
+      a.hits = b->hits.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
       a.srow_ints = (uint32_t)(maxq + 2);
       a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
       a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);
@@ -1343,34 +1429,28 @@ static int run_impl(dg_batch* b) {
       for (uint64_t first = 0; first < nhits; first += chunk) {
         a.first_hit = first;
         a.chunk = std::min<uint64_t>(chunk, nhits - first);
-        k_verify<<<grid_for(a.chunk, 128), 128, 0, st>>>(v, bd, a);
+        k_verify<<<grid_for(a.chunk, kVerifyBlock), kVerifyBlock, 0, st>>>(v, bd, a);
         ++launches;
       }
-    }
-    b->pool_bytes = 0;
-    if (nhits) {
-      ABuf<uint64_t> alen, aoff;
-      alen.alloc(nhits + 1, st);
-      aoff.alloc(nhits + 1, st);
-      uint32_t mult = b->par.seed_len ? 1u : 2u;
-      k_aln_bytes<<<grid_for(nhits + 1, B), B, 0, st>>>(b->hits.p, nhits, mult, alen.p);
-      size_t tb = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, tb, alen.p, aoff.p, (int)(nhits + 1), st);
-      cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, alen.p, aoff.p, (int)(nhits + 1), st);
-      DG_CUDA(cudaMemcpyAsync(&b->pool_bytes, aoff.p + nhits, 8, cudaMemcpyDeviceToHost, st));
-      b->pool2.alloc(nhits * (uint64_t)b->pool_stride, st);  // upper bound; only pool_bytes are fetched
-      k_compact_pool<<<grid_for(nhits, B), B, 0, st>>>(b->hits.p, nhits, aoff.p, b->pool.p, b->pool2.p);
-      launches += 4;
+      unsigned long long used = 0;
+      DG_CUDA(cudaMemcpyAsync(&used, cursor.p, 8, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaStreamSynchronize(st));
+      b->pool_bytes = used;
     }
-    prof_mark(ix, 5);
+    prof_mark(ix, 5, st);
+    if (getenv("DG_TRACE"))
+      fprintf(stderr, "[dg_batch_run] host ms: prepare %.3f search %.3f filter %.3f locate %.3f verify %.3f (nq %u, cands %u, hits %llu)\n",
+              g_host_mark[1] - g_host_mark[0], g_host_mark[2] - g_host_mark[1], g_host_mark[3] - g_host_mark[2],
+              g_host_mark[4] - g_host_mark[3], g_host_mark[5] - g_host_mark[4], nq, n, (unsigned long long)nhits);
     DG_CUDA(cudaGetLastError());
     b->ran = true;
-    ix->prof.launches = launches;
-    ix->prof.last.scripts = h_scripts;
-    ix->prof.last.candidates = n_candidates;
-    ix->prof.last.located = nlocate;
-    ix->prof.last.hits = nhits;
+    if (st == ix->stream) {
+      ix->prof.launches = launches;
+      ix->prof.last.scripts = h_scripts;
+      ix->prof.last.candidates = n_candidates;
+      ix->prof.last.located = nlocate;
+      ix->prof.last.hits = nhits;
+    }
     return DG_OK;
   } catch (CudaFail& e) {
     return e.code;
@@ -1397,7 +1477,7 @@ static int fetch_impl(dg_batch* b, dg_result** out) {
   dg_result* r = nullptr;
   try {
     DG_CUDA(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = b->st;
     r = new dg_result();
     uint32_t nq = b->nq;
     r->nq = nq;
@@ -1410,7 +1490,7 @@ static int fetch_impl(dg_batch* b, dg_result** out) {
     r->seqs.alloc(b->nbytes, true);
     if (b->nhits) {
       DG_CUDA(cudaMemcpyAsync(r->hits.p, b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, st));
-      if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync(r->pool.p, b->pool2.p, b->pool_bytes, cudaMemcpyDeviceToHost, st));
+      if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync(r->pool.p, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, st));
     }
     DG_CUDA(cudaMemcpyAsync(r->qoff.p, b->qoff.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (nq) {
@@ -1449,7 +1529,7 @@ int dg_batch_fetch(dg_batch* b, dg_result** out) {
 }
 int dg_batch_summary(dg_batch* b, uint64_t* n_hits, uint64_t* n_candidates) {
   if (!b || !b->ran) { set_error("batch has not run"); return DG_ERR_ARG; }
-  cudaStreamSynchronize(b->ix->stream);
+  cudaStreamSynchronize(b->st);
   prof_collect(b->ix);
   if (n_hits) *n_hits = b->nhits;
   if (n_candidates) *n_candidates = b->ncand;
@@ -1461,10 +1541,167 @@ void dg_batch_free(dg_batch* b) {
   delete b;
 }
 
+// Large batches are cut into chunks that flow through a pipeline: two host workers, each with its
+// own compute stream, alternate over the chunks (stage -> search -> verify), so the host-side gaps
+// of one chunk (size read-backs, allocations, launches) are filled by the other chunk's kernels;
+// finished chunks are committed in query order: ids and offsets are rebased on the device and the
+// records travel to the host on the copy stream, straight into their final place in the result,
+// while later chunks are still being searched.
+namespace {
+struct ChunkPipe {
+  dg_index* idx;
+  const char* seqs;
+  const uint64_t* offsets;
+  uint32_t nq, nchunks;
+  const dg_params* params;
+  dg_result* r;
+  std::mutex mu;
+  std::condition_variable cv;
+  uint32_t next_commit = 0;      // chunks are committed (final offsets assigned) in order
+  uint64_t hit_base = 0, pool_base = 0;
+  int rc = DG_OK;
+  std::string err;
+  double t_begin = 0;
+  bool trace = false;
+
+  void fail(int code, const std::string& msg) {
+    std::lock_guard<std::mutex> g(mu);
+    if (rc == DG_OK) { rc = code; err = msg; }
+    cv.notify_all();
+  }
+
+  void worker(int w) {
+    struct Live { dg_batch* b; cudaEvent_t copied; };
+    std::vector<Live> live;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    try {
+      DG_CUDA(cudaSetDevice(idx->device));
+      cudaStream_t st = w == 0 ? idx->stream : idx->stream2, cs = idx->copy_stream;
+      std::vector<uint64_t> so;
+      for (uint32_t c = (uint32_t)w; c < nchunks; c += 2) {
+        { std::lock_guard<std::mutex> g(mu); if (rc != DG_OK) break; }
+        // release chunks whose records have reached the host (keeps at most 2 per worker alive)
+        while (!live.empty() && (live.size() >= 2 || cudaEventQuery(live.front().copied) == cudaSuccess)) {
+          DG_CUDA(cudaEventSynchronize(live.front().copied));
+          cudaEventDestroy(live.front().copied);
+          dg_batch_free(live.front().b);
+          live.erase(live.begin());
+        }
+        const uint32_t q0 = (uint32_t)(((uint64_t)nq * c) / nchunks), q1 = (uint32_t)(((uint64_t)nq * (c + 1)) / nchunks);
+        const uint32_t cn = q1 - q0;
+        if (offsets[q1] < offsets[q0]) { fail(DG_ERR_ARG, "offsets must be non-decreasing"); break; }
+        so.resize((size_t)cn + 1);
+        for (uint32_t k = 0; k <= cn; ++k) so[k] = offsets[q0 + k] - offsets[q0];
+        dg_batch* b = nullptr;
+        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st);
+        if (rc1) { fail(rc1, last_error_ref()); break; }
+        cudaEvent_t copied;
+        DG_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+        live.push_back(Live{b, copied});
+        rc1 = run_impl(b);
+        if (rc1) { fail(rc1, last_error_ref()); break; }
+        // commit in query order
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return next_commit == c || rc != DG_OK; });
+        if (rc != DG_OK) break;
+        const uint64_t need_hits = (hit_base + b->nhits) * sizeof(dg_hit), need_pool = pool_base + b->pool_bytes;
+        if (need_hits > r->hits.cap || need_pool > r->pool.cap) {
+          // first call with this volume (later calls get right-sized blocks from the cache): size for
+          // the whole batch from what the chunks so far produced
+          DG_CUDA(cudaStreamSynchronize(cs));
+          const double scale = 1.15 * (double)nq / (double)q1;
+          r->hits.reserve(std::max<size_t>(need_hits, (size_t)(scale * need_hits)), hit_base * sizeof(dg_hit), true);
+          r->pool.reserve(std::max<size_t>(need_pool, (size_t)(scale * need_pool)), pool_base, true);
+        }
+        k_rebase<<<grid_for(std::max<uint64_t>(b->nhits, (uint64_t)cn + 1), 256), 256, 0, st>>>(
+            b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base);
+        cudaEvent_t ev;
+        DG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        DG_CUDA(cudaEventRecord(ev, st));
+        DG_CUDA(cudaStreamWaitEvent(cs, ev, 0));
+        cudaEventDestroy(ev);   // released once the wait has been satisfied
+        if (b->nhits) {
+          DG_CUDA(cudaMemcpyAsync((uint8_t*)r->hits.p + hit_base * sizeof(dg_hit), b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, cs));
+          if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->pool.p + pool_base, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, cs));
+        }
+        DG_CUDA(cudaMemcpyAsync((uint64_t*)r->qoff.p + q0, b->qoff.p, ((size_t)cn + (c + 1 == nchunks ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, cs));
+        if (cn) {
+          DG_CUDA(cudaMemcpyAsync((uint32_t*)r->status.p + q0, b->status.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
+          DG_CUDA(cudaMemcpyAsync((uint32_t*)r->dist.p + q0, b->dist.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
+          if (b->nbytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
+        }
+        DG_CUDA(cudaEventRecord(copied, cs));
+        hit_base += b->nhits;
+        pool_base += b->pool_bytes;
+        ++next_commit;
+        if (trace) fprintf(stderr, "[dg_hunt_batch] worker %d committed chunk %u/%u: %u queries, %llu hits, t = %.3f ms\n", w, c + 1,
+                           nchunks, cn, (unsigned long long)b->nhits, now() - t_begin);
+        lk.unlock();
+        cv.notify_all();
+      }
+    } catch (CudaFail& e) {
+      fail(e.code, last_error_ref());
+    } catch (std::bad_alloc&) {
+      fail(DG_ERR_NOMEM, "out of host memory");
+    }
+    if (idx->copy_stream) cudaStreamSynchronize(idx->copy_stream);
+    for (auto& l : live) { cudaEventDestroy(l.copied); dg_batch_free(l.b); }
+  }
+};
+}  // namespace
+
+static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* params,
+                        uint32_t nchunks, dg_result** out) {
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  ChunkPipe p;
+  p.idx = idx; p.seqs = seqs; p.offsets = offsets; p.nq = nq; p.nchunks = nchunks; p.params = params;
+  p.trace = getenv("DG_TRACE") != nullptr;
+  p.t_begin = now();
+  dg_result* r = nullptr;
+  try {
+    DG_CUDA(cudaSetDevice(idx->device));
+    if (!idx->copy_stream) DG_CUDA(cudaStreamCreateWithFlags(&idx->copy_stream, cudaStreamNonBlocking));
+    if (!idx->stream2) DG_CUDA(cudaStreamCreateWithFlags(&idx->stream2, cudaStreamNonBlocking));
+    r = new dg_result();
+    r->nq = nq;
+    r->qoff.alloc(((size_t)nq + 1) * 8, true);
+    r->status.alloc((size_t)nq * 4, true);
+    r->dist.alloc((size_t)nq * 4, true);
+    r->seqs.alloc(offsets[nq], true);
+    p.r = r;
+    std::thread second([&p] { p.worker(1); });
+    p.worker(0);
+    second.join();
+    if (p.rc == DG_OK) {
+      DG_CUDA(cudaStreamSynchronize(idx->copy_stream));
+      r->nhits = p.hit_base;
+      r->hits.bytes = p.hit_base * sizeof(dg_hit);
+      r->pool.bytes = p.pool_base;
+    }
+  } catch (CudaFail& e) {
+    p.rc = e.code;
+    p.err = last_error_ref();
+  } catch (std::bad_alloc&) {
+    p.rc = DG_ERR_NOMEM;
+    p.err = "out of host memory";
+  }
+  if (p.rc != DG_OK) { delete r; set_error(p.err); return p.rc; }
+  if (p.trace) fprintf(stderr, "[dg_hunt_batch] nq=%u in %u chunks: %.3f ms\n", nq, nchunks, now() - p.t_begin);
+  *out = r;
+  return DG_OK;
+}
+
 int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* params,
                   dg_result** out) {
   static const bool trace = getenv("DG_TRACE") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  if (!idx || !offsets || !params || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
+  uint32_t chunk = 262144;
+  if (const char* e = getenv("DG_CHUNK")) chunk = (uint32_t)std::max<long long>(1024, atoll(e));
+  if (nq > chunk + chunk / 2 && offsets[0] == 0) {
+    const uint32_t nchunks = (uint32_t)(((uint64_t)nq + chunk - 1) / chunk);
+    return hunt_chunked(idx, seqs, offsets, nq, params, nchunks, out);
+  }
   double t0 = now();
   dg_batch* b = nullptr;
   int rc = stage_impl(idx, seqs, offsets, nq, params, &b);

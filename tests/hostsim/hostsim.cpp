@@ -82,6 +82,7 @@ int main(int argc, char** argv) {
   if (cmd == "needle" && argc >= 3) {
     std::ifstream f(argv[2]);
     std::string line;
+    int banded_checked = 0;
     while (std::getline(f, line)) {
       size_t t = line.find('\t');
       if (t == std::string::npos) continue;
@@ -105,10 +106,29 @@ int main(int argc, char** argv) {
           return 3;
         }
       }
+      // the banded register form used by k_verify in hunt mode: exact whenever score >= -dmax
+      for (int dmax = -score; dmax <= -score + 1; ++dmax) {
+        int hi = mg - n + dmax, W = hi + dmax + 1;
+        if (n > 31 || hi < 0 || W > kBandMax || dmax < 0) continue;
+        std::vector<uint32_t> tr(mg + 1, 0);
+        std::vector<uint8_t> ra3(mg + n + 1), qa3(mg + n + 1);
+        int score3 = needle_banded_fill((const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, dmax, tr.data());
+        int nops = 0, lead3 = 0, trail3 = 0;
+        needle_banded_shape(tr.data(), mg, n, dmax, &nops, &lead3, &trail3);
+        int kept3 = nops - lead3 - trail3;
+        needle_banded_emit(tr.data(), (const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, dmax, nops, lead3, trail3,
+                           ra3.data(), qa3.data());
+        ++banded_checked;
+        if (score3 != score || kept3 != kept || lead3 != lead || memcmp(ra.data(), ra3.data(), kept) || memcmp(qa.data(), qa3.data(), kept)) {
+          fprintf(stderr, "banded / full needle mismatch on %s %s (dmax %d)\n", g.c_str(), s.c_str(), dmax);
+          return 3;
+        }
+      }
       std::cout << score << '\t' << lead << '\t' << std::string((char*)ra.data(), kept) << '\t'
                 << std::string((char*)qa.data(), kept) << '\n';
     }
-    return 0;
+    fprintf(stderr, "banded needle checked on %d (pair, dmax) cases\n", banded_checked);
+    return banded_checked >= 100 ? 0 : 4;
   }
   return 2;
 }

@@ -212,3 +212,37 @@ def test_write_fm9(indexes, name, tmp_path, ref_bin):
         subprocess.run([ref_bin, "hunt", dst, os.path.join(GOLDEN, name + ".rec.tsv"), os.path.join(GOLDEN, case + ".queries.txt"),
                         "--records", out, "--counters"] + flags, check=True, capture_output=True)
         assert open(out).read() == open(os.path.join(GOLDEN, case + ".records.tsv")).read()
+
+
+def test_chunked_pipeline_equals_single_batch(indexes, monkeypatch):
+    """dg_hunt_batch cuts large batches into chunks whose hit records travel to the host while the
+    next chunk is searched; ids and offsets are rebased on the device.  Same records either way."""
+    ix = indexes["t1m"]
+    pr = synth.primers_fast(42, 8, 125000, 6000, 20, 1, True, rng_seed=3)
+    qs = [bytes(r) for r in pr]
+    qs[17] = b"ACGTAC"            # too short
+    qs[1500] = qs[1500][:12]      # ragged lengths
+    qs[4100] = b"ACGTNACGTACGTTGCAAGT"
+    monkeypatch.setenv("DG_CHUNK", "100000000")
+    one = ix.hunt(qs, HuntParams(distance=1))
+    monkeypatch.setenv("DG_CHUNK", "1024")
+    many = ix.hunt(qs, HuntParams(distance=1))
+    assert one.nq == many.nq == len(qs)
+    assert np.array_equal(one.qoff, many.qoff) and np.array_equal(one.status, many.status) and np.array_equal(one.dist, many.dist)
+    assert bytes(one.seqs) == bytes(many.seqs)
+    for f in ("query", "score", "chr", "start", "text_pos", "aln_len", "alignpos", "strand"):
+        assert np.array_equal(one.hits[f], many.hits[f]), f
+    assert len(one.hits) > 3000
+    for q in list(range(0, len(qs), 97)) + [17, 1500, 4100]:
+        assert one.push_hits(q) == many.push_hits(q)
+
+
+@pytest.mark.parametrize("case,index", [("t1m_e1", "t1m"), ("stress_h1", "stress"), ("t1m_e0", "t1m")])
+def test_records_dump_equals_reference_dump(indexes, case, index):
+    """The canonical whole-batch dump bench.py hashes against `dicey_ref hunt --records`."""
+    ix = indexes[index]
+    qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
+    par = params_from_flags(open(os.path.join(GOLDEN, case + ".flags.txt")).read())
+    want = "".join(l for l in open(os.path.join(GOLDEN, case + ".records.tsv")) if not l.startswith("W\t"))
+    res = ix.hunt([s for _, s in qs], par)
+    assert res.records_tsv(par, [s.encode() for _, s in qs]) == want
