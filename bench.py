@@ -279,11 +279,21 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm: queries staged once, every kernel per step
+    # ---------------- device-resident arm: queries staged once, every kernel per step; with more than
+    # one rank each step ends with the path's one exchange step, the NCCL all-gather of the hit
+    # records, straight from device memory
+    from dicey_b200 import shard
+
+    def resident_step(batch):
+        batch.run()
+        batch.summary()          # synchronises the index stream; collects the stage timings
+        if world > 1:
+            shard.allgather_hits_device(batch)
+            torch.cuda.current_stream().synchronize()
+
     batch = ix.stage(seqs, params)
     for _ in range(args.warmup):
-        batch.run()
-        batch.summary()
+        resident_step(batch)
     ix.profile(True)
     sampler = ClockSampler(local)
     barrier()
@@ -292,8 +302,7 @@ def main_b200(args):
     e0.record(stream)
     profs = []
     for _ in range(args.steps):
-        batch.run()
-        batch.summary()          # synchronises the index stream; collects the stage timings
+        resident_step(batch)
         profs.append(ix.last_profile())
     e1.record(stream)
     barrier()
@@ -308,31 +317,41 @@ def main_b200(args):
     value = world * nq * args.steps / (ms / 1e3)
     batch.free()
 
-    # ---------------- end-to-end arm: host buffers through dg_hunt_batch
+    # ---------------- end-to-end arm: host buffers through the C ABI.  One rank: dg_hunt_batch (H2D of
+    # the queries, every kernel, D2H of every hit record).  Several ranks: the same work as stage /
+    # run / fetch with the device-side all-gather in between, and rank 0 also reads the gathered
+    # records of all ranks back to its host.
+    gathered_pin = None
+
+    def e2e_step():
+        nonlocal gathered_pin
+        if world == 1:
+            return ix.hunt(seqs, params), 0
+        bt = ix.stage(seqs, params)
+        bt.run()
+        allb, _ = shard.allgather_hits_device(bt)
+        res = bt.fetch()
+        extra = 0
+        if rank == 0:
+            if gathered_pin is None or gathered_pin.numel() < allb.numel():
+                gathered_pin = torch.empty(int(allb.numel() * 1.1), dtype=torch.uint8, pin_memory=True)
+            gathered_pin[:allb.numel()].copy_(allb.view(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            extra = allb.numel()
+        bt.free()
+        return res, extra
+
     for _ in range(min(args.warmup, 2)):
-        res = ix.hunt(seqs, params)
+        res, _ = e2e_step()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     step_ms = []
     for _ in range(args.steps):
         ts = time.perf_counter()
-        res = ix.hunt(seqs, params)
+        res, extra = e2e_step()
         step_ms.append(round(1e3 * (time.perf_counter() - ts), 3))
-        d2h = res.hits.nbytes + res.pool.nbytes + res.qoff.nbytes + res.status.nbytes + res.dist.nbytes + res.seqs.nbytes
-        if world > 1:
-            # the hit all-gather of SURVEY.md 8(e): counts, then padded hit records, over NCCL
-            cnt = torch.tensor([len(res.hits)], dtype=torch.int64, device="cuda")
-            cnts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            mx = int(max(int(c.item()) for c in cnts))
-            buf = torch.zeros(mx * res.hits.dtype.itemsize, dtype=torch.uint8, device="cuda")
-            mine = torch.from_numpy(res.hits.view(np.uint8).reshape(-1))
-            buf[:mine.numel()].copy_(mine, non_blocking=True)
-            allb = torch.empty(world * buf.numel(), dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(allb, buf)
-            if rank == 0:
-                _ = allb.cpu()
+        d2h = res.hits.nbytes + res.pool.nbytes + res.qoff.nbytes + res.status.nbytes + res.dist.nbytes + res.seqs.nbytes + extra
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -412,7 +431,7 @@ def main_b200(args):
             "metric": "primers/sec (3 Gb ref, edit-dist 1)", "value": value, "unit": "primers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded",
+            "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded by rank" + (", NCCL all-gather of the hit records every step" if world > 1 else ""),
                        "global_primers_per_step": world * nq, "l2": "inputs larger than L2: random access into a 34 GB index",
                        "kmer_table_K": info["kmer"], "presence_bitmap_K": info["bitmap_k"], "index_device_bytes": info["device_bytes"],
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},

@@ -1535,6 +1535,13 @@ int dg_batch_summary(dg_batch* b, uint64_t* n_hits, uint64_t* n_candidates) {
   if (n_candidates) *n_candidates = b->ncand;
   return DG_OK;
 }
+int dg_batch_device_hits(dg_batch* b, const void** device_ptr, uint64_t* n_hits) {
+  if (!b || !b->ran || !device_ptr || !n_hits) { set_error("batch has not run"); return DG_ERR_ARG; }
+  cudaStreamSynchronize(b->st);
+  *device_ptr = b->nhits ? (const void*)b->hits.p : nullptr;
+  *n_hits = b->nhits;
+  return DG_OK;
+}
 void dg_batch_free(dg_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ix->device);

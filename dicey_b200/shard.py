@@ -101,6 +101,35 @@ def allgather_bytes(buf: np.ndarray, device=None) -> list[np.ndarray]:
     return [host[r, :sizes[r]].copy() for r in range(world)]
 
 
+class _DeviceBytes:
+    """A raw device address dressed up for torch.as_tensor (zero-copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def allgather_hits_device(batch):
+    """The exchange step of the path on device memory: the dg_hit records of a batch
+    that has run are all-gathered over NCCL / NVLink straight from HBM -- counts first, then the
+    records padded to the largest count.  Returns (uint8 tensor [world, max_count * 48] on the
+    device, int64 counts [world] on the device)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    ptr, n = batch.device_hits()
+    isz = HIT_DTYPE.itemsize
+    cnt = torch.tensor([n], dtype=torch.int64, device="cuda")
+    counts = torch.empty(world, dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(counts, cnt)
+    mx = max(int(counts.max().item()), 1)
+    mine = torch.zeros(mx * isz, dtype=torch.uint8, device="cuda")
+    if n:
+        mine[:n * isz].copy_(torch.as_tensor(_DeviceBytes(ptr, n * isz), device="cuda"))
+    out = torch.empty(world * mx * isz, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(out, mine)
+    return out.view(world, mx * isz), counts
+
+
 def hunt_sharded(index, seqs, params, rank: int | None = None, world: int | None = None) -> HuntResult:
     """The whole multi-GPU call: this rank hunts its shard on its own GPU, then the packed hit
     records are all-gathered and merged; every rank returns the global result."""

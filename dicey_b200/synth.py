@@ -101,7 +101,7 @@ def primers(seed: int, nrec: int, reclen: int, count: int, length: int, distance
 
 
 def primers_fast(seed: int, nrec: int, reclen: int, count: int, length: int, distance: int,
-                 indel: bool, rng_seed: int = 7) -> np.ndarray:
+                 indel: bool, rng_seed: int = 7, return_truth: bool = False):
     """Vectorised fixed-length variant for the large bench batches: returns a (count, length)
     uint8 array.  Even rows are planted loci with k in 0..distance substitutions (and, in
     edit mode, optionally one 1-base shift emulating an indel at the 5' end), odd rows are
@@ -130,4 +130,12 @@ def primers_fast(seed: int, nrec: int, reclen: int, count: int, length: int, dis
     rc = rng.random(npl) < 0.5
     planted[rc] = _COMP[planted[rc]][:, ::-1]
     out[0::2] = planted
-    return np.ascontiguousarray(out)
+    out = np.ascontiguousarray(out)
+    if return_truth:
+        # row 2 i was copied from record rec[i], 0-based offset off[i]; rc[i]: reverse-complemented;
+        # shifted[i]: the 5' base was dropped (an indel), so the locus starts one base later
+        shifted = np.zeros(npl, dtype=bool)
+        if indel:
+            shifted[sel] = True
+        return out, {"rec": rec.astype(np.int64), "off": off.astype(np.int64), "rc": rc, "shifted": shifted, "edits": k}
+    return out

@@ -167,6 +167,10 @@ int dg_batch_stage(dg_index* idx, const char* seqs, const uint64_t* offsets, uin
 int dg_batch_run(dg_batch* b);
 int dg_batch_fetch(dg_batch* b, dg_result** out);
 int dg_batch_summary(dg_batch* b, uint64_t* n_hits, uint64_t* n_candidates); /* synchronises */
+/* Device address of the hit records of a batch that has run (n_hits dg_hit structs in HBM, valid
+ * until dg_batch_free / the next dg_batch_run): lets the multi-GPU layer all-gather the records
+ * over NVLink straight from device memory, without a round trip through the host. */
+int dg_batch_device_hits(dg_batch* b, const void** device_ptr, uint64_t* n_hits);
 void dg_batch_free(dg_batch* b);
 
 /* sdsl::count over a neighbourhood: padlock.h:381-427 (exact count of each string when

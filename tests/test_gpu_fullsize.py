@@ -1,0 +1,269 @@
+"""BASELINE.json's configurations at FULL size (3 Gb synthetic reference, 24 x 125 Mb) on the GPU.
+
+Bit-exact comparison with the reference is only affordable on samples at this size (the reference
+needs ~1 ms per primer at edit distance 1 and ~2 s at edit distance 2), so each configuration is
+checked twice:
+  * size-independent properties over the whole batch: every reported alignment is re-derived from
+    the seeded text generator (dicey_b200/synth.py, no index involved), its score is recounted
+    from the alignment columns, every planted primer is found at its locus, and for a handful of
+    primers the hits equal a brute-force scan of all 3 G text windows;
+  * a sample of the same queries through oracle/_ref/dicey_ref (the reference's own SDSL /
+    neighbors.h / needle.h) on the same index, written as .fm9 by dg_index_write_fm9 -- records
+    compared bit for bit.  Skipped when the reference binary has not been built.
+"""
+import os
+import subprocess
+import tempfile
+import time
+
+import numpy as np
+import pytest
+
+from dicey_b200 import synth
+from dicey_b200.api import HuntParams, Index
+
+pytestmark = pytest.mark.gpu
+
+SEED, NREC, RECLEN = 42, 24, 125_000_000
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")
+COMP = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+
+@pytest.fixture(scope="module")
+def big():
+    t0 = time.time()
+    ix = Index.build_synthetic(SEED, NREC, RECLEN, 0)
+    print(f"[fullsize] 3 Gb index built on the GPU in {time.time() - t0:.1f} s, {ix.info()['device_bytes'] / 1e9:.1f} GB")
+    yield ix
+    ix.close()
+
+
+@pytest.fixture(scope="module")
+def fm9(big):
+    """The same index as an SDSL-loadable .fm9 for the reference binary (None without the binary)."""
+    if not os.path.exists(REF_BIN):
+        yield None
+        return
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(d, f"dicey_b200_test_{os.getpid()}.fm9")
+    t0 = time.time()
+    big.write_fm9(path)
+    rec = path + ".rec.tsv"
+    with open(rec, "w") as f:
+        for i in range(NREC):
+            f.write(f"chr{i + 1}\t{RECLEN}\n")
+    print(f"[fullsize] .fm9 written in {time.time() - t0:.1f} s ({os.path.getsize(path) / 1e9:.2f} GB)")
+    yield path, rec
+    for p in (path, path + "_check", rec):
+        try:
+            os.remove(p)
+        except OSError:
+            pass
+
+
+def revcomp(b: bytes) -> bytes:
+    return b.translate(COMP)[::-1]
+
+
+def window(chrom: int, start1: int, length: int) -> bytes:
+    """Bases [start1, start1 + length) (1-based) of record `chrom`, from the seeded generator."""
+    return synth.bases(SEED, chrom * RECLEN + start1 - 1, length).tobytes()
+
+
+def check_alignment(rec, query: bytes, dmax: int, indel: bool):
+    score, chrom, start, strand, ra, qa = rec
+    ra, qa = ra.encode(), qa.encode()
+    q = query if strand == "+" else revcomp(query)
+    assert len(ra) == len(qa)
+    g = ra.replace(b"-", b"")
+    assert qa.replace(b"-", b"") == q                       # the query row is the (strand of the) query
+    assert window(chrom, start, len(g)) == g                # the reference row is the genome at (chr, start)
+    cost = sum(1 for a, b in zip(ra, qa) if a != b)         # mismatches + gap columns
+    assert cost == -score and cost <= dmax
+    if not indel:
+        assert b"-" not in ra + qa
+    assert not (ra[:1] == b"-" and qa[:1] == b"-")
+
+
+def planted_found(res, truth, n_rows, length):
+    missing = 0
+    for i in range(0, n_rows, 2):
+        t = i // 2
+        want_chr = int(truth["rec"][t])
+        lo = int(truth["off"][t]) + 1
+        strand = "-" if truth["rc"][t] else "+"
+        ok = False
+        for (score, chrom, start, st, ra, qa) in res.push_hits(i):
+            if chrom == want_chr and st == strand and abs(start - lo) <= 2:
+                ok = True
+        missing += 0 if ok else 1
+    return missing
+
+
+def run_ref(args):
+    return subprocess.run([REF_BIN] + args, check=True, capture_output=True, text=True).stdout
+
+
+def write_queries(path, rows):
+    with open(path, "wb") as f:
+        f.write(b"\n".join(bytes(r) for r in rows) + b"\n")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_config2_hamming1_10k(big, fm9, tmp_path):
+    """dicey hunt: 10k random 20-mers, hamming-distance 1, 3 Gb reference, 1 x B200."""
+    n = 10_000
+    pr, truth = synth.primers_fast(SEED, NREC, RECLEN, n, 20, 1, False, rng_seed=11, return_truth=True)
+    par = HuntParams(distance=1, hamming=True)
+    res = big.hunt(pr, par)
+    assert res.nq == n and (res.status == 0).all()
+    for q in range(n):
+        hits = res.push_hits(q)
+        assert len(set(h[1:4] for h in hits)) == len(hits)   # one record per (chr, start, strand)
+        for h in hits:
+            check_alignment(h, bytes(pr[q]), 1, False)
+    assert planted_found(res, truth, n, 20) == 0
+    # brute force over all 3 G windows for a few primers (planted and random): no index involved
+    import torch
+    text = torch.from_numpy(big.debug_array("text")).cuda()
+    nl = (text == 10) | (text == 0)
+    bad = torch.zeros(text.numel() - 19, dtype=torch.uint8, device="cuda")
+    for j in range(20):
+        bad |= nl[j:j + bad.numel()].to(torch.uint8)
+    for q in (0, 1, 2, 3, 4, 5):
+        want = set()
+        for strand, s in (("+", bytes(pr[q])), ("-", revcomp(bytes(pr[q])))):
+            mism = bad * 2
+            for j in range(20):
+                mism += (text[j:j + bad.numel()] != s[j]).to(torch.uint8)
+            pos = torch.nonzero(mism <= 1).flatten().cpu().numpy()
+            for p in pos:
+                want.add((int(p) // (RECLEN + 1), int(p) % (RECLEN + 1) + 1, strand))
+        got = set((h[1], h[2], h[3]) for h in res.push_hits(q))
+        assert got == want, q
+    del text, nl, bad
+    torch.cuda.empty_cache()
+    if fm9:
+        path, rec = fm9
+        m = 2000
+        qf = str(tmp_path / "q.txt")
+        out = str(tmp_path / "rec.tsv")
+        write_queries(qf, pr[:m])
+        run_ref(["hunt", path, rec, qf, "-d", "1", "-n", "--threads", str(os.cpu_count() or 1), "--records", out])
+        sub = big.hunt(pr[:m], par)
+        assert sub.records_tsv(par, pr[:m]) == open(out).read()
+
+
+def test_config4_edit2_sample(big, fm9, tmp_path):
+    """dicey hunt: 20-mers at edit-distance 2 on the 3 Gb reference (the 1 M x 8-GPU config, one shard's worth of logic)."""
+    n = 20_000
+    pr, truth = synth.primers_fast(SEED, NREC, RECLEN, n, 20, 2, True, rng_seed=13, return_truth=True)
+    par = HuntParams(distance=2)
+    t0 = time.time()
+    res = big.hunt(pr, par)
+    dt = time.time() - t0
+    print(f"[fullsize] edit-2: {n} primers in {dt * 1e3:.0f} ms ({n / dt / 1e3:.0f} k primers/s), {len(res.hits)} hits")
+    for q in range(0, n, 7):
+        for h in res.push_hits(q):
+            check_alignment(h, bytes(pr[q]), 2, True)
+    assert planted_found(res, truth, n, 20) == 0
+    if fm9:
+        path, rec = fm9
+        m = 32
+        qf = str(tmp_path / "q.txt")
+        out = str(tmp_path / "rec.tsv")
+        write_queries(qf, pr[:m])
+        run_ref(["hunt", path, rec, qf, "-d", "2", "--threads", str(os.cpu_count() or 1), "--records", out])
+        sub = big.hunt(pr[:m], par)
+        assert sub.records_tsv(par, pr[:m]) == open(out).read()
+
+
+def test_config3_search_seeds(big, fm9, tmp_path):
+    """dicey search (FM / NW part): 1k primer pairs, 15-mer seeds at edit-distance 1, 3 Gb reference."""
+    rng = np.random.default_rng(5)
+    n = 2000
+    rows = []
+    for i in range(n):
+        L = int(rng.integers(18, 26))
+        chrom, off = int(rng.integers(0, NREC)), int(rng.integers(0, RECLEN - 3000))
+        s = bytearray(window(chrom, off + 1, L))
+        if i % 3 == 0:                      # one substitution inside the 3' seed
+            j = L - 1 - int(rng.integers(0, 15))
+            s[j] = ord("ACGT"[("ACGT".index(chr(s[j])) + 1 + int(rng.integers(0, 3))) % 4])
+        rows.append(bytes(s) if i % 2 == 0 else revcomp(bytes(s)))
+    par = HuntParams(distance=1, seed_len=15, maxmatches=10000)
+    res = big.hunt(rows, par)
+    assert res.nq == n
+    nfound = 0
+    for q in range(n):
+        for (chrom, chrpos, alignpos, strand, ctx) in res.seed_hits(q):
+            assert window(chrom, chrpos + 1, len(ctx)).decode() == ctx   # the context handed to the Tm gate
+            assert chrpos <= alignpos <= chrpos + len(ctx)
+            nfound += 1
+    assert nfound >= n
+    if fm9:
+        path, rec = fm9
+        m = 300
+        qf = str(tmp_path / "p.txt")
+        with open(qf, "w") as f:
+            for i, r in enumerate(rows[:m]):
+                f.write(f"p{i}\t{r.decode()}\n")
+        want, cur = [], None
+        for line in run_ref(["seed", path, rec, qf, "-k", "15", "-d", "1"]).splitlines():
+            f = line.split("\t")
+            if f[0] == "Q":
+                cur = []
+                want.append(cur)
+            else:
+                cur.append((int(f[2]), int(f[3]), int(f[4]), "-" if f[1] == "1" else "+", f[5]))
+        for q in range(m):
+            assert res.seed_hits(q) == want[q], q
+
+
+def test_config5_padlock_arm_counts(big, fm9, tmp_path):
+    """dicey padlock (count-only use of the path): 20-mer arms of 100 synthetic regions, exact and edit-1 neighbourhood counts."""
+    rng = np.random.default_rng(9)
+    arms = []
+    for i in range(100):
+        chrom, off = int(rng.integers(0, NREC)), int(rng.integers(0, RECLEN - 3000))
+        region = window(chrom, off + 1, 2000)
+        for j in range(4):
+            o = int(rng.integers(0, 1960))
+            arms.append(region[o:o + 20])
+    exact = big.count(arms, HuntParams(distance=0))
+    total = big.count(arms, HuntParams(distance=1))
+    assert (exact >= 1).all() and (total >= exact).all()
+    if fm9:
+        path, rec = fm9
+        qf = str(tmp_path / "arms.txt")
+        write_queries(qf, arms)
+        lines = run_ref(["padcount", path, qf, "-d", "1"]).splitlines()
+        assert len(lines) == len(arms)
+        for i, line in enumerate(lines):
+            f = line.split("\t")
+            assert (int(exact[i]), int(total[i])) == (int(f[1]), int(f[2])), i
+
+
+def test_config_headline_edit1_properties(big):
+    """The bench workload itself (1 M 20-mers, edit distance 1): whole-batch invariants."""
+    n = 1_000_000
+    pr, truth = synth.primers_fast(SEED, NREC, RECLEN, n, 20, 1, True, rng_seed=7, return_truth=True)
+    par = HuntParams(distance=1)
+    res = big.hunt(pr, par)
+    assert res.nq == n and int(res.qoff[-1]) == len(res.hits)
+    h = res.hits
+    assert (np.diff(h["query"].astype(np.int64)) >= 0).all()            # hits grouped by query, in query order
+    assert ((h["score"] <= 0) & (h["score"] >= -1)).all()
+    assert (h["chr"] < NREC).all() and (h["start"] >= 1).all() and (h["start"] <= RECLEN).all()
+    # the planted half is found (sampled: re-deriving 1 M alignments in Python would take minutes)
+    sub = np.arange(0, 40_000, 2)
+    for i in sub:
+        t = i // 2
+        hits = res.push_hits(int(i))
+        assert any(c == int(truth["rec"][t]) and abs(s - int(truth["off"][t]) - 1) <= 2 for (_, c, s, _, _, _) in hits), i
+        for rec in hits:
+            check_alignment(rec, bytes(pr[i]), 1, True)
+    # text_pos <-> (chr, start) consistency over the whole batch, vectorised
+    lead = h["start"].astype(np.int64) - 1 + h["chr"].astype(np.int64) * (RECLEN + 1) - h["text_pos"].astype(np.int64)
+    assert (np.abs(lead) <= 2).all()
