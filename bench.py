@@ -59,13 +59,16 @@ def parse_args():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons during the timed region (B200_PROFILING.md).  Sampled in-process
-    through NVML every 10 ms (an nvidia-smi child polling the driver perturbs kernel launches);
-    falls back to one nvidia-smi query at the end if NVML is unavailable."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), read through NVML
+    by the timing thread itself right after each step's synchronisation.  A concurrent poller (an
+    nvidia-smi child, or an NVML thread) takes driver locks while kernels are being launched and
+    was measured to stretch individual steps by 2-180 ms on this box; two NVML reads between steps
+    cost ~0.05 ms.  Falls back to one nvidia-smi query after the run if NVML is unavailable."""
 
     def __init__(self, device: int):
-        self.device, self.rows, self.stop_flag, self.t = device, [], False, None
-        self.h = None
+        self.device, self.rows, self.h = device, [], None
+        if os.environ.get("BENCH_CLOCK", "") == "off":
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -77,26 +80,23 @@ class ClockSampler:
                 idx = int(vis.split(",")[device])
             self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            for _ in range(3):   # the first NVML reads are slow: take them before the timed region
+                self.sample()
+            self.rows = []
         except Exception:
             self.h = None
 
-    def _loop(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.rows.append((sm, rs))
-            except Exception:
-                pass
-            time.sleep(0.01)
-
-    def start(self):
+    def sample(self):
         if self.h is None:
             return
-        self.t = threading.Thread(target=self._loop, daemon=True)
-        self.t.start()
+        try:
+            self.rows.append((float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)), int(self.reasons_fn(self.h))))
+        except Exception:
+            pass
+
+    def start(self):
+        self.rows = []
 
     def stop(self) -> dict:
         if self.h is None:
@@ -106,9 +106,6 @@ class ClockSampler:
                 return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": ["nvml unavailable: one nvidia-smi sample after the run"]}
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
-        self.stop_flag = True
-        if self.t:
-            self.t.join(timeout=1)
         nv = self.nv
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
@@ -294,6 +291,11 @@ def main_b200(args):
     batch = ix.stage(seqs, params)
     for _ in range(args.warmup):
         resident_step(batch)
+    # the GPU idles while the primers are generated on the host and needs a few hundred ms of load
+    # to come back to its boost clock: keep warming (untimed) for 0.4 s beyond the W requested steps
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < 0.4:
+        resident_step(batch)
     ix.profile(True)
     sampler = ClockSampler(local)
     barrier()
@@ -304,6 +306,7 @@ def main_b200(args):
     for _ in range(args.steps):
         resident_step(batch)
         profs.append(ix.last_profile())
+        sampler.sample()         # right after the step's synchronisation: the clock it ran at
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -342,6 +345,9 @@ def main_b200(args):
         return res, extra
 
     for _ in range(min(args.warmup, 2)):
+        res, _ = e2e_step()
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < 0.3:
         res, _ = e2e_step()
     barrier()
     t0 = time.perf_counter()

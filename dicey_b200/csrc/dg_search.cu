@@ -1560,6 +1560,7 @@ struct ChunkPipe {
   const char* seqs;
   const uint64_t* offsets;
   uint32_t nq, nchunks;
+  std::vector<uint32_t> bounds;   // chunk c = queries [bounds[c], bounds[c + 1])
   const dg_params* params;
   dg_result* r;
   std::mutex mu;
@@ -1594,7 +1595,7 @@ struct ChunkPipe {
           dg_batch_free(live.front().b);
           live.erase(live.begin());
         }
-        const uint32_t q0 = (uint32_t)(((uint64_t)nq * c) / nchunks), q1 = (uint32_t)(((uint64_t)nq * (c + 1)) / nchunks);
+        const uint32_t q0 = bounds[c], q1 = bounds[c + 1];
         const uint32_t cn = q1 - q0;
         if (offsets[q1] < offsets[q0]) { fail(DG_ERR_ARG, "offsets must be non-decreasing"); break; }
         so.resize((size_t)cn + 1);
@@ -1616,7 +1617,7 @@ struct ChunkPipe {
           // first call with this volume (later calls get right-sized blocks from the cache): size for
           // the whole batch from what the chunks so far produced
           DG_CUDA(cudaStreamSynchronize(cs));
-          const double scale = 1.15 * (double)nq / (double)q1;
+          const double scale = 1.15 * (double)nq / (double)q1;  // q1 = queries committed so far
           r->hits.reserve(std::max<size_t>(need_hits, (size_t)(scale * need_hits)), hit_base * sizeof(dg_hit), true);
           r->pool.reserve(std::max<size_t>(need_pool, (size_t)(scale * need_pool)), pool_base, true);
         }
@@ -1658,9 +1659,16 @@ struct ChunkPipe {
 }  // namespace
 
 static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* params,
-                        uint32_t nchunks, dg_result** out) {
+                        uint32_t chunk, dg_result** out) {
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   ChunkPipe p;
+  // the first chunk is half-sized so that the two workers run out of phase: one worker's host gaps
+  // (size read-backs between kernels) then fall into the other worker's long kernels
+  p.bounds.push_back(0);
+  for (uint64_t q = chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
+  if (p.bounds.size() > 1 && nq - p.bounds.back() < chunk / 4) p.bounds.pop_back();  // no tiny tail chunk
+  p.bounds.push_back(nq);
+  const uint32_t nchunks = (uint32_t)p.bounds.size() - 1;
   p.idx = idx; p.seqs = seqs; p.offsets = offsets; p.nq = nq; p.nchunks = nchunks; p.params = params;
   p.trace = getenv("DG_TRACE") != nullptr;
   p.t_begin = now();
@@ -1705,10 +1713,7 @@ int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint
   if (!idx || !offsets || !params || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
   uint32_t chunk = 262144;
   if (const char* e = getenv("DG_CHUNK")) chunk = (uint32_t)std::max<long long>(1024, atoll(e));
-  if (nq > chunk + chunk / 2 && offsets[0] == 0) {
-    const uint32_t nchunks = (uint32_t)(((uint64_t)nq + chunk - 1) / chunk);
-    return hunt_chunked(idx, seqs, offsets, nq, params, nchunks, out);
-  }
+  if (nq > chunk + chunk / 2 && offsets[0] == 0) return hunt_chunked(idx, seqs, offsets, nq, params, chunk, out);
   double t0 = now();
   dg_batch* b = nullptr;
   int rc = stage_impl(idx, seqs, offsets, nq, params, &b);
