@@ -159,7 +159,7 @@ __global__ void k_presence(const uint8_t* __restrict__ text, uint64_t n, uint32_
   for (uint64_t j = first; j < last; ++j) {
     int c = base_code(text[j]);
     if (c < 4) { code = ((code << 2) | (uint64_t)c) & mask; ++valid; } else { code = 0; valid = 0; }
-    if (valid >= KB) atomicOr(&bits[code >> 5], 1u << (code & 31));
+    if (valid >= KB) { const uint64_t bit = presence_bit(code, (int)KB); atomicOr(&bits[bit >> 5], 1u << (bit & 31)); }
   }
 }
 
@@ -545,7 +545,7 @@ static void build_presence_bitmap(dg_index* ix) {
     while (KB < 18 && (1ULL << (2 * KB)) < 16 * ix->n) ++KB;
   }
   if (KB > 19) KB = 19;
-  if (KB && KB < 3) KB = 3;
+  if (KB && KB < 6) KB = 6;
   ix->KB = KB;
   if (!KB) return;
   uint64_t words = (1ULL << (2 * KB)) >> 5;

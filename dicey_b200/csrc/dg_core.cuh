@@ -340,6 +340,90 @@ DG_HD bool is_minimal(const uint8_t* q, int m, int d, const uint8_t* t, int L, u
   return true;
 }
 
+// Register-resident form of restricted_distance / is_minimal for m + d <= 31: both strings as 4-bit
+// symbol classes (A C G T = 1..4, N = 5), 16 per 64-bit word, the DP as a band of 2 cap + 1 cells
+// (k = j - i + cap) held in scalars.  Same recurrence, same result (tests/hostsim cross-checks the
+// two on every generated string).
+struct Packed4 {
+  uint64_t w0, w1;
+  DG_HD uint32_t at(int i) const { return (uint32_t)(((i < 16 ? w0 : w1) >> (4 * (i & 15))) & 15u); }
+};
+DG_HD Packed4 pack4(const uint8_t* s, int n) {
+  Packed4 p;
+  p.w0 = p.w1 = 0;
+  for (int i = 0; i < n; ++i) {
+    uint8_t b = s[i];
+    uint64_t c = b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 3u : b == 'T' ? 4u : 5u;
+    if (i < 16) p.w0 |= c << (4 * i); else p.w1 |= c << (4 * (i - 16));
+  }
+  return p;
+}
+constexpr int kSmallBand = 2 * kMaxDist + 1;
+
+// min(cost, cap + 1) of turning q (length m) into t[a, a + ulen) under the DFS rules
+DG_HD int restricted_distance_small(const Packed4& q, int m, const Packed4& t, int a, int ulen, int cap) {
+  const int INF = 100;
+  const int dl = m - ulen;
+  if (dl > cap || -dl > cap) return cap + 1;
+  const int W = 2 * cap + 1;
+  int v[kSmallBand];
+  // row 0: D[0][j] = j insertions before q[0] (ACGT letters only); k = j + cap
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kSmallBand; ++k) {
+    int j = k - cap, val = INF;
+    if (k < W && j >= 0 && j <= ulen) {
+      val = j;
+      for (int x = 0; x < j; ++x) if (t.at(a + x) > 4u || m == 0) val = INF;
+    }
+    v[k] = val;
+  }
+  for (int i = 1; i <= m; ++i) {
+    const uint32_t qc = q.at(i - 1);
+    int best = INF;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < kSmallBand; ++k) {
+      if (k < W) {
+        const int j = i + k - cap;
+        int val = INF;
+        if (j == 0) {
+          val = i;
+        } else if (j > 0 && j <= ulen) {
+          const uint32_t uc = t.at(a + j - 1);
+          int sub = v[k];                                        // D[i-1][j-1]
+          if (qc != uc) sub = uc <= 4u ? sub + 1 : INF;
+          const int del = (k + 1 < W ? v[k + 1] : INF) + 1;      // D[i-1][j] + 1
+          const int ins = (k > 0 && i < m && uc <= 4u) ? v[k - 1] + 1 : INF;   // D[i][j-1] + 1 (v[k-1] already holds row i)
+          val = sub < del ? sub : del;
+          if (ins < val) val = ins;
+          if (val > INF) val = INF;
+        }
+        v[k] = val;
+        if (val < best) best = val;
+      }
+    }
+    if (best > cap) return cap + 1;
+  }
+  const int kf = ulen - m + cap;   // j = ulen at i = m
+  int r = INF;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kSmallBand; ++k) if (k == kf) r = v[k];
+  return r > cap ? cap + 1 : r;
+}
+DG_HD bool is_minimal_small(const Packed4& q, int m, int d, const Packed4& t, int L) {
+  int minlen = m - d;
+  if (minlen < 1) minlen = 1;
+  for (int len = minlen; len < L; ++len)
+    for (int a = 0; a + len <= L; ++a)
+      if (restricted_distance_small(q, m, t, a, len, d) <= d) return false;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // needle() for std::string x std::string, AlignConfig<false,true>, DnaScore(0,-1,-1,-1)
 // (needle.h:59-138, align.h:52-80): rows = genomic g (length mg), columns = query s (length n).
@@ -565,6 +649,16 @@ DG_HD uint64_t apply_event_packed(uint64_t code, int j, int k) {
   return (((code >> sh) >> 2) << (sh + 4)) | ((uint64_t)(k - 5) << (sh + 2)) | low_incl;
 }
 constexpr int kMaxPacked = 31;  // longest edited string the packed path handles
+
+// Bit address of a KB-mer window (packed, last base in the low bits) in the presence bitmap.
+// A random access moves a whole 128-byte line (1024 bits) of DRAM, so the line is selected by the
+// LAST KB - 5 bases and the bit inside it by the 5 bases before them: every neighbour string whose
+// edit lies left of its last KB - 5 bases (right-anchored, so indels there shift nothing) probes
+// the same line as its siblings -- one DRAM access for ~7 x 8 of the 160 strings of a 20-mer.
+DG_HD uint64_t presence_bit(uint64_t window, int KB) {
+  const int lo = 2 * (KB - 5);
+  return ((window & ((1ULL << lo) - 1ULL)) << 10) | (window >> lo);
+}
 
 // hunter.h:358-362 / silica.h:475-479: text position -> (refIndex, chrpos).
 DG_HD void locate_record(const uint64_t* cum, uint32_t nseq, uint64_t pos, uint32_t& refIndex, uint32_t& chrpos) {

@@ -376,8 +376,11 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
 //      each time 32 of them are queued they run the slow path together with full lanes:
 //      K-mer table lookup on the last K bases + one backward-search step per remaining base.
 // The strings enumerated are exactly those of k_search for a clean query (neighbors.h:47-83).
+#ifndef DG_PACKED_MIN_BLOCKS
+#define DG_PACKED_MIN_BLOCKS 6
+#endif
 template <bool INDEL>
-__global__ void __launch_bounds__(256) k_search_packed(IndexView ix, BatchDev b, SearchOut out) {
+__global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(IndexView ix, BatchDev b, SearchOut out) {
   constexpr int S = INDEL ? 8 : 3;    // enumeration slots per position of a clean query
   constexpr int CS = INDEL ? 9 : 4;   // canonical slot numbering carried by the candidate
   constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -479,8 +482,11 @@ __global__ void __launch_bounds__(256) k_search_packed(IndexView ix, BatchDev b,
           }
           pass = L > 0;
           if (pass && KB && L >= KB) {
-            const uint64_t bit = code & kbmask;
-            pass = (__ldg(&ix.present_kb[bit >> 5]) >> (uint32_t)(bit & 31)) & 1u;
+            const uint64_t bit = presence_bit(code & kbmask, KB);
+            // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
+            uint32_t word;
+            asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(ix.present_kb + (bit >> 5)));
+            pass = (word >> (uint32_t)(bit & 31)) & 1u;
           }
         }
         const unsigned pm = __ballot_sync(FULL, pass);
@@ -624,16 +630,44 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
   const uint8_t* base;
   int m, koff;
   query_geom(b, c.q, strand, base, m, koff);
-  uint8_t t[kMaxQuery + 8], s0[kMaxQuery + 8], s1[kMaxQuery + 8];
-  int L = script_ltr(base, m, sc, t);
-  bool keep = !indel || is_minimal(base, m, (int)b.dist[c.q], t, L, s0, s1);
+  const int d = (int)b.dist[c.q];
   CandKey k;
   k.hi = k.lo = 0;
-  int lim = L < kKeyChars ? L : kKeyChars;
-  for (int j = 0; j < lim; ++j) {
-    uint8_t ch = t[j];
-    uint64_t v = ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 5 : 4;
-    if (j < 21) k.hi |= v << (60 - 3 * j); else k.lo |= v << (60 - 3 * (j - 21));
+  bool keep;
+  if (m + d <= 31) {
+    // register path: the edited string is generated straight into 4-bit classes and key codes
+    const Packed4 q4 = pack4(base, m);
+    Packed4 t4;
+    t4.w0 = t4.w1 = 0;
+    int L = 0;
+    auto emit = [&](uint32_t cls) {   // cls: A C G T N = 1..5
+      if (L < 16) t4.w0 |= (uint64_t)cls << (4 * L); else t4.w1 |= (uint64_t)cls << (4 * (L - 16));
+      const uint64_t v = cls == 4u ? 5u : (cls == 5u ? 4u : cls);   // key order: A < C < G < N < T
+      if (L < 21) k.hi |= v << (60 - 3 * L); else k.lo |= v << (60 - 3 * (L - 21));
+      ++L;
+    };
+    int ev = 0;
+    for (int p = 0; p < m; ++p) {
+      while (ev < sc.nev && sc.pos[ev] == p && sc.k[ev] >= 5) { emit((uint32_t)(sc.k[ev] - 5) + 1u); ++ev; }
+      uint32_t cls = q4.at(p);
+      bool out = true;
+      if (ev < sc.nev && sc.pos[ev] == p) {
+        if (sc.k[ev] == 4) out = false; else cls = (uint32_t)sc.k[ev] + 1u;
+        ++ev;
+      }
+      if (out) emit(cls);
+    }
+    keep = !indel || is_minimal_small(q4, m, d, t4, L);
+  } else {
+    uint8_t t[kMaxQuery + 8], s0[kMaxQuery + 8], s1[kMaxQuery + 8];
+    int L = script_ltr(base, m, sc, t);
+    keep = !indel || is_minimal(base, m, d, t, L, s0, s1);
+    int lim = L < kKeyChars ? L : kKeyChars;
+    for (int j = 0; j < lim; ++j) {
+      uint8_t ch = t[j];
+      uint64_t v = ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 5 : 4;
+      if (j < 21) k.hi |= v << (60 - 3 * j); else k.lo |= v << (60 - 3 * (j - 21));
+    }
   }
   k.qs = keep ? ((c.q << 1) | (uint32_t)strand) : sentinel;
   k.idx = i;
@@ -649,6 +683,27 @@ __global__ void k_unique_keys(const CandKey* __restrict__ keys, uint32_t n, uint
     if (a.qs == c.qs && a.hi == c.hi && a.lo == c.lo) first = false;
   }
   keep[i] = first ? 1 : 0;
+}
+// After a radix sort on (query, strand) alone: orders every small group by its string key with a
+// rank count (groups hold ~1-40 candidates); a group larger than kGroupMax raises `big` and the
+// host falls back to the full-key radix sort.
+constexpr int kGroupMax = 256;
+__global__ void k_group_order(const CandKey* __restrict__ in, uint32_t n, uint32_t sentinel, CandKey* __restrict__ out,
+                              unsigned int* __restrict__ big) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const CandKey me = in[i];
+  if (me.qs == sentinel) { out[i] = me; return; }
+  uint32_t s = i, e = i + 1;
+  while (s > 0 && i - s < (uint32_t)kGroupMax && in[s - 1].qs == me.qs) --s;
+  while (e < n && e - i < (uint32_t)kGroupMax && in[e].qs == me.qs) ++e;
+  if (i - s >= (uint32_t)kGroupMax || e - i >= (uint32_t)kGroupMax) { atomicExch(big, 1u); out[i] = me; return; }
+  uint32_t rank = 0;
+  for (uint32_t j = s; j < e; ++j) {
+    const CandKey o = in[j];
+    if (o.hi < me.hi || (o.hi == me.hi && (o.lo < me.lo || (o.lo == me.lo && o.idx < me.idx)))) ++rank;
+  }
+  out[s + rank] = me;
 }
 __global__ void k_gather_cands(const Cand* __restrict__ cands, const CandKey* __restrict__ keys, uint32_t n, Cand* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1221,11 +1276,14 @@ static int run_impl(dg_batch* b) {
     if (nq) {
       // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
       int per_sm = 0;
+      static const int cap_blocks = getenv("DG_SEARCH_BLOCKS") ? atoi(getenv("DG_SEARCH_BLOCKS")) : 0;
       if (b->par.indel) {
         DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_packed<true>, 256, 0));
+        if (cap_blocks > 0) per_sm = std::min(per_sm, cap_blocks);
         k_search_packed<true><<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, so);
       } else {
         DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_packed<false>, 256, 0));
+        if (cap_blocks > 0) per_sm = std::min(per_sm, cap_blocks);
         k_search_packed<false><<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, so);
       }
       // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
@@ -1264,24 +1322,44 @@ static int run_impl(dg_batch* b) {
       const uint32_t sentinel = nq >= 0x7FFFFFFFu ? 0xFFFFFFFFu : 2u * nq;
       int qbits = 1;
       while (qbits < 32 && (1ULL << qbits) <= (uint64_t)sentinel) ++qbits;
-      k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p);
+      ABuf<unsigned int> big;
+      big.alloc(1, st);
+      DG_CUDA(cudaMemsetAsync(big.p, 0, 4, st));
       const int begin_bit = (maxq_str + (int)b->par.distance <= 21) ? 64 : 0;
-      size_t tb = 0;
-      cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
-      cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
-      k_unique_keys<<<grid_for(n, B), B, 0, st>>>(kb.p, n, sentinel, keep.p);
-      cub::DeviceSelect::Flagged(nullptr, tb, kb.p, keep.p, ka.p, nsel.p, (int)n, st);
-      cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, kb.p, keep.p, ka.p, nsel.p, (int)n, st);
+      const bool full_sort_always = getenv("DG_FULL_KEY_SORT") != nullptr;
       uint32_t n3 = 0;
-      DG_CUDA(cudaMemcpyAsync(&n3, nsel.p, 4, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaStreamSynchronize(st));
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool by_group = attempt == 0 && !full_sort_always;
+        k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p);
+        size_t tb = 0;
+        if (by_group) {
+          // 3 radix passes on (query, strand), then a rank count inside each small group
+          ABuf<CandKey> kc;
+          kc.alloc(n, st);
+          cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.p, kc.p, (int)n, CandKeyDecomposer{}, 128, 128 + qbits, st);
+          cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, ka.p, kc.p, (int)n, CandKeyDecomposer{}, 128, 128 + qbits, st);
+          k_group_order<<<grid_for(n, B), B, 0, st>>>(kc.p, n, sentinel, kb.p, big.p);
+        } else {
+          cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
+          cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
+        }
+        k_unique_keys<<<grid_for(n, B), B, 0, st>>>(kb.p, n, sentinel, keep.p);
+        cub::DeviceSelect::Flagged(nullptr, tb, kb.p, keep.p, ka.p, nsel.p, (int)n, st);
+        cub::DeviceSelect::Flagged(ensure_tmp(tb), tb, kb.p, keep.p, ka.p, nsel.p, (int)n, st);
+        unsigned int h_big = 0;
+        DG_CUDA(cudaMemcpyAsync(&n3, nsel.p, 4, cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaMemcpyAsync(&h_big, big.p, 4, cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaStreamSynchronize(st));
+        launches += 9;
+        if (!(by_group && h_big)) break;   // a group beyond kGroupMax: once more with the full key
+      }
       ABuf<Cand> sorted;
       sorted.alloc(n3 ? n3 : 1, st);
       if (n3) k_gather_cands<<<grid_for(n3, B), B, 0, st>>>(cur, ka.p, n3, sorted.p);
       b->cands.swap(sorted);  // the unsorted buffer is released with `sorted`
       cur = b->cands.p;
       n = n3;
-      launches += 12;
+      launches += 1;
     } else {
       if (n && b->par.indel) {
         keep.alloc(n, st);

@@ -58,8 +58,14 @@ static void neighbors(const std::string& q, int d, bool indel, std::set<std::str
     }
   if (!indel) { out = all; return; }
   std::vector<uint8_t> s0(m + 8), s1(m + 8);
-  for (auto const& t : all)
-    if (is_minimal(base, m, d, (const uint8_t*)t.data(), (int)t.size(), s0.data(), s1.data())) out.insert(t);
+  for (auto const& t : all) {
+    bool keep = is_minimal(base, m, d, (const uint8_t*)t.data(), (int)t.size(), s0.data(), s1.data());
+    if (m + d <= 31) {  // the register-resident form used by k_cand_keys must agree on every string
+      bool keep2 = is_minimal_small(pack4(base, m), m, d, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
+      if (keep2 != keep) { fprintf(stderr, "is_minimal_small mismatch on %s / %s\n", q.c_str(), t.c_str()); exit(3); }
+    }
+    if (keep) out.insert(t);
+  }
 }
 
 int main(int argc, char** argv) {
