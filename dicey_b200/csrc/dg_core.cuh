@@ -424,6 +424,58 @@ DG_HD bool is_minimal_small(const Packed4& q, int m, int d, const Packed4& t, in
   return true;
 }
 
+// Distance 1 needs no DP at all: a string of G_1(q) of length m - 1 / m / m + 1 is q with one
+// deletion / substitution / insertion, so "some proper substring of t (length >= m - 1) is
+// generated" reduces to two predicates on packed strings, each a handful of shifts and XORs:
+//   one_deletion(q, u)  |u| = m - 1 and u is q with one base removed (any position)
+//   hamming_le1(q, u)   |u| = m and u differs from q in at most one place, the new letter in ACGT
+DG_HD Packed4 shr4(const Packed4& p, int a) {   // drop the first a symbols
+  Packed4 r;
+  if (a >= 16) { r.w0 = a >= 32 ? 0 : p.w1 >> (4 * (a - 16)); r.w1 = 0; }
+  else if (a == 0) { r = p; }
+  else { r.w0 = (p.w0 >> (4 * a)) | (p.w1 << (64 - 4 * a)); r.w1 = p.w1 >> (4 * a); }
+  return r;
+}
+DG_HD Packed4 keep4(const Packed4& p, int len) {   // first len symbols, the rest cleared
+  Packed4 r;
+  r.w0 = len >= 16 ? p.w0 : (len <= 0 ? 0 : p.w0 & ((1ULL << (4 * len)) - 1ULL));
+  r.w1 = len >= 32 ? p.w1 : (len <= 16 ? 0 : p.w1 & ((1ULL << (4 * (len - 16))) - 1ULL));
+  return r;
+}
+DG_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+// index of the first symbol where x and y differ among the first len, or len
+DG_HD int first_diff4(const Packed4& x, const Packed4& y, int len) {
+  const Packed4 a = keep4(x, len), b = keep4(y, len);
+  const uint64_t d0 = a.w0 ^ b.w0, d1 = a.w1 ^ b.w1;
+  if (d0) return ctz64(d0) >> 2;
+  if (d1) return 16 + (ctz64(d1) >> 2);
+  return len;
+}
+DG_HD bool one_deletion4(const Packed4& q, int m, const Packed4& u) {   // |u| = m - 1
+  const int f = first_diff4(q, u, m - 1);
+  if (f >= m - 1) return true;                       // u = q without its last base
+  return first_diff4(shr4(q, f + 1), shr4(u, f), m - 1 - f) >= m - 1 - f;
+}
+DG_HD bool hamming_le1_4(const Packed4& q, int m, const Packed4& u) {   // |u| = m
+  const int f = first_diff4(q, u, m);
+  if (f >= m) return true;                           // u = q
+  if (u.at(f) > 4u) return false;                    // only ACGT can be written
+  return first_diff4(shr4(q, f + 1), shr4(u, f + 1), m - 1 - f) >= m - 1 - f;
+}
+DG_HD bool is_minimal_d1(const Packed4& q, int m, const Packed4& t, int L) {
+  if (L < m) return true;                            // nothing of length >= m - 1 fits inside
+  if (L == m) return !(one_deletion4(q, m, t) || one_deletion4(q, m, shr4(t, 1)));
+  // L == m + 1
+  if (hamming_le1_4(q, m, t) || hamming_le1_4(q, m, shr4(t, 1))) return false;
+  return !(one_deletion4(q, m, t) || one_deletion4(q, m, shr4(t, 1)) || one_deletion4(q, m, shr4(t, 2)));
+}
+
 // ------------------------------------------------------------------------------------------
 // needle() for std::string x std::string, AlignConfig<false,true>, DnaScore(0,-1,-1,-1)
 // (needle.h:59-138, align.h:52-80): rows = genomic g (length mg), columns = query s (length n).

@@ -657,7 +657,7 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
       }
       if (out) emit(cls);
     }
-    keep = !indel || is_minimal_small(q4, m, d, t4, L);
+    keep = !indel || (d == 1 && m >= 2 ? is_minimal_d1(q4, m, t4, L) : is_minimal_small(q4, m, d, t4, L));
   } else {
     uint8_t t[kMaxQuery + 8], s0[kMaxQuery + 8], s1[kMaxQuery + 8];
     int L = script_ltr(base, m, sc, t);
@@ -723,7 +723,8 @@ __global__ void k_take_in(const Cand* __restrict__ cands, uint32_t n, uint32_t m
 // before[i] = sum of take over earlier candidates of the same query -> hits taken / rows located
 __global__ void k_take_out(const Cand* __restrict__ cands, uint32_t n, uint32_t max_loc, const uint64_t* __restrict__ before,
                            const uint64_t* __restrict__ take, uint64_t* __restrict__ ntake, uint64_t* __restrict__ nloc,
-                           unsigned long long* __restrict__ qhits, uint32_t* __restrict__ status) {
+                           unsigned long long* __restrict__ qhits, uint32_t* __restrict__ status,
+                           unsigned long long* __restrict__ max_rows) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Cand c = cands[i];
@@ -731,6 +732,7 @@ __global__ void k_take_out(const Cand* __restrict__ cands, uint32_t n, uint32_t 
   uint64_t nt = bf < max_loc ? (tk < max_loc - bf ? tk : max_loc - bf) : 0;
   ntake[i] = nt;
   nloc[i] = nt ? (uint64_t)(c.r - c.l) : 0;
+  if (nt && c.r - c.l > 1) atomicMax(max_rows, (unsigned long long)(c.r - c.l));
   if (nt) atomicAdd(&qhits[c.q], (unsigned long long)nt);
   if (bf + tk >= max_loc) atomicOr(&status[c.q], (uint32_t)DG_Q_HIT_CAP);  // hunter.h:434-437
 }
@@ -750,6 +752,24 @@ __global__ void k_locate(IndexView ix, const Cand* __restrict__ cands, uint32_t 
   uint32_t row = c.l + (uint32_t)(t - loc_off[lo]);
   uint32_t pos = sa_value(ix, row);
   keys[t] = ((uint64_t)lo << 32) | pos;
+}
+
+// Ascending text positions inside each candidate's segment of located rows (hunter.h:356) by a
+// rank count; used when no candidate holds more than kGroupMax rows (else: radix sort).
+__global__ void k_locate_order(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ loc_off, uint64_t total,
+                               uint64_t* __restrict__ out) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint64_t me = keys[t];
+  const uint32_t c = (uint32_t)(me >> 32);
+  const uint64_t s = loc_off[c], e = loc_off[c + 1];
+  uint64_t rank = 0;
+  if (e - s > 1)
+    for (uint64_t j = s; j < e; ++j) {
+      const uint64_t o = keys[j];
+      if (o < me || (o == me && j < t)) ++rank;
+    }
+  out[s + rank] = me;
 }
 
 struct VerifyArgs {
@@ -1427,6 +1447,8 @@ static int run_impl(dg_batch* b) {
     ABuf<uint64_t> take, before, ntake, nloc, hit_off, loc_off, keys, keys2;
     ABuf<uint32_t> qkey;
     uint64_t nhits = 0, nlocate = 0;
+    unsigned long long h_max_rows = 0;
+    ABuf<unsigned long long> max_rows;
     if (n) {
       take.alloc(n, st); before.alloc(n, st); ntake.alloc((size_t)n + 1, st); nloc.alloc((size_t)n + 1, st);
       hit_off.alloc((size_t)n + 1, st); loc_off.alloc((size_t)n + 1, st); qkey.alloc(n, st);
@@ -1436,8 +1458,10 @@ static int run_impl(dg_batch* b) {
       size_t tb = 0;
       cub::DeviceScan::ExclusiveSumByKey(nullptr, tb, qkey.p, take.p, before.p, (int)n, cub::Equality(), st);
       cub::DeviceScan::ExclusiveSumByKey(ensure_tmp(tb), tb, qkey.p, take.p, before.p, (int)n, cub::Equality(), st);
+      max_rows.alloc(1, st);
+      DG_CUDA(cudaMemsetAsync(max_rows.p, 0, 8, st));
       k_take_out<<<grid_for(n, B), B, 0, st>>>(cur, n, b->par.max_locations, before.p, take.p, ntake.p, nloc.p, b->qhits.p,
-                                              b->status.p);
+                                              b->status.p, max_rows.p);
       cub::DeviceScan::ExclusiveSum(nullptr, tb, ntake.p, hit_off.p, (int)(n + 1), st);
       cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, ntake.p, hit_off.p, (int)(n + 1), st);
       cub::DeviceScan::ExclusiveSum(nullptr, tb, nloc.p, loc_off.p, (int)(n + 1), st);
@@ -1445,6 +1469,7 @@ static int run_impl(dg_batch* b) {
       launches += 8;
       DG_CUDA(cudaMemcpyAsync(&nhits, hit_off.p + n, 8, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaMemcpyAsync(&nlocate, loc_off.p + n, 8, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaMemcpyAsync(&h_max_rows, max_rows.p, 8, cudaMemcpyDeviceToHost, st));
     }
     {
       size_t tb = 0;
@@ -1465,12 +1490,17 @@ static int run_impl(dg_batch* b) {
       keys.alloc(nlocate, st);
       keys2.alloc(nlocate, st);
       k_locate<<<grid_for(nlocate, 128), 128, 0, st>>>(v, cur, n, loc_off.p, nlocate, keys.p);
-      int cbits = 1;
-      while ((1ULL << cbits) < (uint64_t)n + 1 && cbits < 32) ++cbits;
-      size_t tb = 0;
-      cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, (int)nlocate, 0, 32 + cbits, st);
-      cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, keys.p, keys2.p, (int)nlocate, 0, 32 + cbits, st);
-      launches += 4;
+      if (h_max_rows <= (unsigned long long)kGroupMax && !getenv("DG_LOCATE_RADIX")) {
+        k_locate_order<<<grid_for(nlocate, 256), 256, 0, st>>>(keys.p, loc_off.p, nlocate, keys2.p);
+        launches += 2;
+      } else {
+        int cbits = 1;
+        while ((1ULL << cbits) < (uint64_t)n + 1 && cbits < 32) ++cbits;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, (int)nlocate, 0, 32 + cbits, st);
+        cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, keys.p, keys2.p, (int)nlocate, 0, 32 + cbits, st);
+        launches += 4;
+      }
       sorted_keys = keys2.p;
     }
     prof_mark(ix, 4, st);

@@ -63,6 +63,10 @@ static void neighbors(const std::string& q, int d, bool indel, std::set<std::str
     if (m + d <= 31) {  // the register-resident form used by k_cand_keys must agree on every string
       bool keep2 = is_minimal_small(pack4(base, m), m, d, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
       if (keep2 != keep) { fprintf(stderr, "is_minimal_small mismatch on %s / %s\n", q.c_str(), t.c_str()); exit(3); }
+      if (d == 1 && m >= 2) {
+        bool keep3 = is_minimal_d1(pack4(base, m), m, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
+        if (keep3 != keep) { fprintf(stderr, "is_minimal_d1 mismatch on %s / %s\n", q.c_str(), t.c_str()); exit(3); }
+      }
     }
     if (keep) out.insert(t);
   }

@@ -250,7 +250,7 @@ def test_records_dump_equals_reference_dump(indexes, case, index):
     assert res.records_tsv(par, [s.encode() for _, s in qs]) == want
 
 
-@pytest.mark.parametrize("knob", ["DG_FULL_KEY_SORT", "DG_MERGE_SORT"])
+@pytest.mark.parametrize("knob", ["DG_FULL_KEY_SORT", "DG_MERGE_SORT", "DG_LOCATE_RADIX"])
 @pytest.mark.parametrize("case,index", [("stress_e2", "stress"), ("t1m_e1", "t1m"), ("stress_h2_m50", "stress")])
 def test_alternative_candidate_orderings(indexes, monkeypatch, knob, case, index):
     """The three ways of putting candidates into std::set order (group rank count, full-key radix
