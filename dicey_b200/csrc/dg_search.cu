@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
 #define DG_PACKED_MIN_BLOCKS 6
 #endif
 template <bool INDEL>
-__global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(IndexView ix, BatchDev b, SearchOut out) {
+__global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(IndexView ix, BatchDev b, SearchOut out, uint32_t pairs_per_warp) {
   constexpr int S = INDEL ? 8 : 3;    // enumeration slots per position of a clean query
   constexpr int CS = INDEL ? 9 : 4;   // canonical slot numbering carried by the candidate
   constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -389,8 +389,11 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t npairs = b.reverse ? 2ULL * b.nq : (uint64_t)b.nq;
+  // every warp owns a short run of consecutive pairs: blocks are short-lived, so the small kernels
+  // of another chunk of the pipeline (other stream) get SM slots while this search is running
+  const uint64_t pair_lo = warp * pairs_per_warp;
+  const uint64_t pair_hi = pair_lo + pairs_per_warp < npairs ? pair_lo + pairs_per_warp : npairs;
   const int K = (int)ix.K;
   const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
   const int KB = (int)ix.KB;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
     }
   };
 
-  for (uint64_t pair = warp; pair < npairs; pair += nwarps) {
+  for (uint64_t pair = pair_lo; pair < pair_hi; ++pair) {
     const uint32_t q = b.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
     const int strand = b.reverse ? (int)(pair & 1) : 0;
     if (!(b.qflag[q] & 2)) continue;
@@ -1296,16 +1299,15 @@ static int run_impl(dg_batch* b) {
     if (nq) {
       // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
       int per_sm = 0;
-      static const int cap_blocks = getenv("DG_SEARCH_BLOCKS") ? atoi(getenv("DG_SEARCH_BLOCKS")) : 0;
-      if (b->par.indel) {
-        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_packed<true>, 256, 0));
-        if (cap_blocks > 0) per_sm = std::min(per_sm, cap_blocks);
-        k_search_packed<true><<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, so);
-      } else {
-        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_packed<false>, 256, 0));
-        if (cap_blocks > 0) per_sm = std::min(per_sm, cap_blocks);
-        k_search_packed<false><<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, so);
-      }
+      const uint64_t npairs = b->par.reverse ? 2ULL * nq : (uint64_t)nq;
+      static const int ppw_env = getenv("DG_PAIRS_PER_WARP") ? atoi(getenv("DG_PAIRS_PER_WARP")) : 0;
+      uint32_t ppw = ppw_env > 0 ? (uint32_t)ppw_env : 4u;
+      // small batches: fewer pairs per warp so that the grid still covers every SM
+      while (ppw > 1 && npairs / (8ull * ppw) < (uint64_t)nsm * 6) ppw >>= 1;
+      const unsigned blocks = (unsigned)((npairs + 8ull * ppw - 1) / (8ull * ppw));
+      (void)per_sm;
+      if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
+      else k_search_packed<false><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
       // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
       DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
       k_search<<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
