@@ -37,12 +37,13 @@ void dg_index_close(dg_index* idx) {
   cudaSetDevice(idx->device);
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   if (idx->prof.created) for (auto& e : idx->prof.ev) cudaEventDestroy(e);
-  cudaStream_t st = idx->stream, cs = idx->copy_stream, s2 = idx->stream2;
-  if (s2) cudaStreamSynchronize(s2);
+  cudaStream_t st = idx->stream, cs = idx->copy_stream;
+  cudaStream_t xs[3] = {idx->xstream[0], idx->xstream[1], idx->xstream[2]};
+  for (auto s2 : xs) if (s2) cudaStreamSynchronize(s2);
   if (cs) cudaStreamSynchronize(cs);
   delete idx;
   if (st) cudaStreamDestroy(st);
-  if (s2) cudaStreamDestroy(s2);
+  for (auto s2 : xs) if (s2) cudaStreamDestroy(s2);
   if (cs) cudaStreamDestroy(cs);
 }
 

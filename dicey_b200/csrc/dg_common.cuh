@@ -62,7 +62,7 @@ struct ProfileState {
 struct dg_index {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;       // second compute stream of the chunk pipeline (dg_hunt_batch)
+  cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};   // extra compute streams of the chunk pipeline (dg_hunt_batch)
   cudaStream_t copy_stream = nullptr;   // device -> host copies of finished chunks
   uint64_t n = 0;
   uint32_t sigma = 0;

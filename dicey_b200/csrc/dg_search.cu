@@ -1658,8 +1658,8 @@ void dg_batch_free(dg_batch* b) {
   delete b;
 }
 
-// Large batches are cut into chunks that flow through a pipeline: two host workers, each with its
-// own compute stream, alternate over the chunks (stage -> search -> verify), so the host-side gaps
+// Large batches are cut into chunks that flow through a pipeline: three host workers, each with its
+// own compute stream, take the chunks in turn (stage -> search -> verify), so the host-side gaps
 // of one chunk (size read-backs, allocations, launches) are filled by the other chunk's kernels;
 // finished chunks are committed in query order: ids and offsets are rebased on the device and the
 // records travel to the host on the copy stream, straight into their final place in the result,
@@ -1675,6 +1675,7 @@ struct ChunkPipe {
   dg_result* r;
   std::mutex mu;
   std::condition_variable cv;
+  int nworkers = 2;
   uint32_t next_commit = 0;      // chunks are committed (final offsets assigned) in order
   uint64_t hit_base = 0, pool_base = 0;
   int rc = DG_OK;
@@ -1694,9 +1695,9 @@ struct ChunkPipe {
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     try {
       DG_CUDA(cudaSetDevice(idx->device));
-      cudaStream_t st = w == 0 ? idx->stream : idx->stream2, cs = idx->copy_stream;
+      cudaStream_t st = w == 0 ? idx->stream : idx->xstream[w - 1], cs = idx->copy_stream;
       std::vector<uint64_t> so;
-      for (uint32_t c = (uint32_t)w; c < nchunks; c += 2) {
+      for (uint32_t c = (uint32_t)w; c < nchunks; c += (uint32_t)nworkers) {
         { std::lock_guard<std::mutex> g(mu); if (rc != DG_OK) break; }
         // release chunks whose records have reached the host (keeps at most 2 per worker alive)
         while (!live.empty() && (live.size() >= 2 || cudaEventQuery(live.front().copied) == cudaSuccess)) {
@@ -1775,7 +1776,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
   // the first chunk is half-sized so that the two workers run out of phase: one worker's host gaps
   // (size read-backs between kernels) then fall into the other worker's long kernels
   p.bounds.push_back(0);
-  for (uint64_t q = chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
+  for (uint64_t q = getenv("DG_NO_STAGGER") ? chunk : chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
   if (p.bounds.size() > 1 && nq - p.bounds.back() < chunk / 4) p.bounds.pop_back();  // no tiny tail chunk
   p.bounds.push_back(nq);
   const uint32_t nchunks = (uint32_t)p.bounds.size() - 1;
@@ -1786,7 +1787,11 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
   try {
     DG_CUDA(cudaSetDevice(idx->device));
     if (!idx->copy_stream) DG_CUDA(cudaStreamCreateWithFlags(&idx->copy_stream, cudaStreamNonBlocking));
-    if (!idx->stream2) DG_CUDA(cudaStreamCreateWithFlags(&idx->stream2, cudaStreamNonBlocking));
+    p.nworkers = 3;
+    if (const char* e = getenv("DG_WORKERS")) p.nworkers = std::min(4, std::max(1, atoi(e)));
+    p.nworkers = (int)std::min<uint32_t>((uint32_t)p.nworkers, nchunks);
+    for (int w = 1; w < p.nworkers; ++w)
+      if (!idx->xstream[w - 1]) DG_CUDA(cudaStreamCreateWithFlags(&idx->xstream[w - 1], cudaStreamNonBlocking));
     r = new dg_result();
     r->nq = nq;
     r->qoff.alloc(((size_t)nq + 1) * 8, true);
@@ -1794,9 +1799,10 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     r->dist.alloc((size_t)nq * 4, true);
     r->seqs.alloc(offsets[nq], true);
     p.r = r;
-    std::thread second([&p] { p.worker(1); });
+    std::vector<std::thread> others;
+    for (int w = 1; w < p.nworkers; ++w) others.emplace_back([&p, w] { p.worker(w); });
     p.worker(0);
-    second.join();
+    for (auto& t : others) t.join();
     if (p.rc == DG_OK) {
       DG_CUDA(cudaStreamSynchronize(idx->copy_stream));
       r->nhits = p.hit_base;
