@@ -126,10 +126,26 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   if (q >= b.nq) return;
   uint64_t o = b.off[q];
   int L = (int)(b.off[q + 1] - o);
-  for (int i = 0; i < L; ++i) {
-    uint8_t ch = norm_base(raw[o + i]);
-    fwd[o + i] = ch;
-    rc[o + L - 1 - i] = comp_base(ch);
+  if (((o | (uint64_t)L) & 3) == 0) {
+    // word path (offsets and length multiples of 4, e.g. batches of 20-mers): 4 bases per access
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + o);
+    uint32_t* fw = reinterpret_cast<uint32_t*>(fwd + o);
+    uint32_t* cw = reinterpret_cast<uint32_t*>(rc + o);
+    const int nw = L >> 2;
+    for (int j = 0; j < nw; ++j) {
+      const uint32_t w = rw[j];
+      const uint8_t c0 = norm_base((uint8_t)w), c1 = norm_base((uint8_t)(w >> 8)), c2 = norm_base((uint8_t)(w >> 16)),
+                    c3 = norm_base((uint8_t)(w >> 24));
+      fw[j] = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16) | ((uint32_t)c3 << 24);
+      cw[nw - 1 - j] = (uint32_t)comp_base(c3) | ((uint32_t)comp_base(c2) << 8) | ((uint32_t)comp_base(c1) << 16) |
+                       ((uint32_t)comp_base(c0) << 24);
+    }
+  } else {
+    for (int i = 0; i < L; ++i) {
+      uint8_t ch = norm_base(raw[o + i]);
+      fwd[o + i] = ch;
+      rc[o + L - 1 - i] = comp_base(ch);
+    }
   }
   uint32_t st = 0;
   int m = b.seed_len ? (int)b.seed_len : L;
@@ -740,17 +756,45 @@ __global__ void k_take_out(const Cand* __restrict__ cands, uint32_t n, uint32_t 
   if (bf + tk >= max_loc) atomicOr(&status[c.q], (uint32_t)DG_Q_HIT_CAP);  // hunter.h:434-437
 }
 
+// Largest i in [0, n) with off[i] <= x (off ascending, off[0] <= x).  Segments are mostly one
+// element long, so i is close to x: gallop out from that guess, then bisect the bracket --
+// two or three dependent loads instead of log2(n).
+__device__ __forceinline__ uint32_t find_segment(const uint64_t* __restrict__ off, uint32_t n, uint64_t x) {
+  uint32_t g = x < (uint64_t)n ? (uint32_t)x : n - 1;
+  uint32_t lo, hi;   // invariant: off[lo] <= x, (hi == n or off[hi] > x)
+  if (off[g] <= x) {
+    lo = g;
+    uint32_t step = 1;
+    hi = n;
+    while (lo + step < n) {
+      if (off[lo + step] > x) { hi = lo + step; break; }
+      lo += step;
+      step <<= 1;
+    }
+  } else {
+    hi = g;
+    uint32_t step = 1;
+    lo = 0;
+    while (hi > step) {
+      if (off[hi - step] <= x) { lo = hi - step; break; }
+      hi -= step;
+      step <<= 1;
+    }
+  }
+  while (hi - lo > 1) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (off[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void k_locate(IndexView ix, const Cand* __restrict__ cands, uint32_t n, const uint64_t* __restrict__ loc_off,
                          uint64_t total, uint64_t* __restrict__ keys) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  // candidate i with loc_off[i] <= t < loc_off[i+1]
-  uint32_t lo = 0, hi = n;
-  while (hi - lo > 1) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (loc_off[mid] <= t) lo = mid; else hi = mid;
-  }
-  // skip candidates with zero rows that share the offset
+  // candidate with loc_off[i] <= t < loc_off[i+1] (the last one of a run sharing the offset:
+  // candidates without rows are skipped)
+  const uint32_t lo = find_segment(loc_off, n, t);
   Cand c = cands[lo];
   uint32_t row = c.l + (uint32_t)(t - loc_off[lo]);
   uint32_t pos = sa_value(ix, row);
@@ -821,11 +865,7 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
   uint64_t h = 0;
   if (valid) {
     h = a.first_hit + t;
-    uint32_t lo = 0, hi = a.ncand;
-    while (hi - lo > 1) {
-      uint32_t mid = lo + ((hi - lo) >> 1);
-      if (a.hit_off[mid] <= h) lo = mid; else hi = mid;
-    }
+    const uint32_t lo = find_segment(a.hit_off, a.ncand, h);
     Cand c = a.cands[lo];
     uint64_t j = h - a.hit_off[lo];
     uint64_t pos = a.keys[a.loc_off[lo] + j] & 0xFFFFFFFFULL;
