@@ -591,8 +591,10 @@ DG_HD uint32_t sym_class(uint8_t b) {
   return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 3u : b == 'T' ? 4u : b == 'N' ? 5u : 6u;
 }
 
-// DP + trace.  tr: mg + 1 words.  Returns the score (srow[n] of needle()).
-DG_HD int needle_banded_fill(const uint8_t* g, int mg, const uint8_t* s, int n, int dmax, uint32_t* tr) {
+// DP + trace.  tr: mg + 1 words.  Returns the score (srow[n] of needle()).  BAND is the compile-time
+// capacity of the register band (W <= BAND): 6 covers distance 1, kBandMax distance 2.
+template <int BAND>
+DG_HD int needle_banded_fill_t(const uint8_t* g, int mg, const uint8_t* s, int n, int dmax, uint32_t* tr) {
   const int hi = mg - n + dmax;            // largest row - col in the band
   const int W = hi + dmax + 1;
   // query as 4-bit classes, 16 per word (n <= 31)
@@ -605,11 +607,11 @@ DG_HD int needle_banded_fill(const uint8_t* g, int mg, const uint8_t* s, int n, 
     if (i < 0 || i >= n) return 0u;
     return (uint32_t)(((i < 16 ? sq0 : sq1) >> (4 * (i & 15))) & 15u);
   };
-  int v[kBandMax];
+  int v[BAND];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int k = 0; k < kBandMax; ++k) v[k] = kBandNeg;
+  for (int k = 0; k < BAND; ++k) v[k] = kBandNeg;
   // win holds the classes of s[col - 1] for the W columns of the current row: col = row - hi + k
   uint64_t win = 0;
   for (int k = 0; k < W; ++k) win |= (uint64_t)qclass(0 - hi + k - 1) << (4 * k);
@@ -621,7 +623,7 @@ DG_HD int needle_banded_fill(const uint8_t* g, int mg, const uint8_t* s, int n, 
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < kBandMax; ++k) {
+    for (int k = 0; k < BAND; ++k) {
       if (k < W) {
         const int col = c0 + k;
         int val = kBandNeg, t = 0;
@@ -650,6 +652,12 @@ DG_HD int needle_banded_fill(const uint8_t* g, int mg, const uint8_t* s, int n, 
     win = (win >> 4) | ((uint64_t)qclass(c0 + W - 1) << (4 * (W - 1)));
   }
   return score;
+}
+
+DG_HD int needle_banded_fill(const uint8_t* g, int mg, const uint8_t* s, int n, int dmax, uint32_t* tr) {
+  const int W = mg - n + 2 * dmax + 1;
+  if (W <= 6) return needle_banded_fill_t<6>(g, mg, s, n, dmax, tr);
+  return needle_banded_fill_t<kBandMax>(g, mg, s, n, dmax, tr);
 }
 
 // Traceback, first pass: number of alignment columns, leading and trailing columns whose query
