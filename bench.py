@@ -320,28 +320,26 @@ def main_b200(args):
     value = world * nq * args.steps / (ms / 1e3)
     batch.free()
 
-    # ---------------- end-to-end arm: host buffers through the C ABI.  One rank: dg_hunt_batch (H2D of
-    # the queries, every kernel, D2H of every hit record).  Several ranks: the same work as stage /
-    # run / fetch with the device-side all-gather in between, and rank 0 also reads the gathered
+    # ---------------- end-to-end arm: host buffers through the C ABI: dg_hunt_batch (H2D of the queries,
+    # every kernel, D2H of every hit record and alignment).  With several ranks the hit records are then
+    # all-gathered (16-byte wire records: coordinates, strand, distance) and rank 0 reads the gathered
     # records of all ranks back to its host.
     gathered_pin = None
 
     def e2e_step():
         nonlocal gathered_pin
+        res = ix.hunt(seqs, params)          # H2D, every kernel, D2H of every record (chunk-pipelined)
         if world == 1:
-            return ix.hunt(seqs, params), 0
-        bt = ix.stage(seqs, params)
-        bt.run()
-        allb, _ = shard.allgather_hits_device(bt)
-        res = bt.fetch()
+            return res, 0
+        allb, _ = shard.allgather_hits_index(ix)
         extra = 0
         if rank == 0:
-            if gathered_pin is None or gathered_pin.numel() < allb.numel():
-                gathered_pin = torch.empty(int(allb.numel() * 1.1), dtype=torch.uint8, pin_memory=True)
-            gathered_pin[:allb.numel()].copy_(allb.view(-1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            extra = allb.numel()
-        bt.free()
+            nb = allb.numel() * 4
+            if gathered_pin is None or gathered_pin.numel() < nb:
+                gathered_pin = torch.empty(int(nb * 1.1), dtype=torch.uint8, pin_memory=True)
+            gathered_pin[:nb].copy_(allb.view(torch.uint8).view(-1), non_blocking=True)
+            extra = nb
+        torch.cuda.current_stream().synchronize()
         return res, extra
 
     for _ in range(min(args.warmup, 2)):

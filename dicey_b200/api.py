@@ -62,7 +62,7 @@ EXPORTS = [
     "dg_index_open", "dg_index_build_text", "dg_index_build_synthetic", "dg_index_write_fm9", "dg_index_close",
     "dg_index_size", "dg_index_set_records", "dg_index_get_info", "dg_index_stream", "dg_index_debug_copy",
     "dg_hunt_batch", "dg_batch_stage", "dg_batch_run", "dg_batch_fetch", "dg_batch_summary", "dg_batch_device_hits",
-    "dg_batch_free",
+    "dg_batch_free", "dg_index_wire_records",
     "dg_count_batch", "dg_backward_search_batch", "dg_result_hits", "dg_result_query_offsets",
     "dg_result_query_status", "dg_result_query_distance", "dg_result_pool", "dg_result_sequences",
     "dg_result_free", "dg_hits_sort", "dg_result_pack", "dg_result_unpack", "dg_profile_enable",
@@ -102,6 +102,7 @@ def library() -> C.CDLL:
     lib.dg_batch_fetch.argtypes = [vp, C.POINTER(vp)]
     lib.dg_batch_summary.argtypes = [vp, u64p, u64p]
     lib.dg_batch_device_hits.argtypes = [vp, C.POINTER(vp), u64p]
+    lib.dg_index_wire_records.argtypes = [vp, C.POINTER(vp), u64p]
     lib.dg_batch_free.argtypes = [vp]
     lib.dg_batch_free.restype = None
     lib.dg_count_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(_Params), vp]
@@ -323,6 +324,12 @@ class Index:
 
     def stream(self) -> int:
         return int(library().dg_index_stream(self._h) or 0)
+
+    def wire_records(self) -> tuple[int, int]:
+        """(device address, count) of the 16-byte wire records of the last hunt() on this index."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(library().dg_index_wire_records(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
 
     def debug_array(self, what: str, dtype=np.uint8) -> np.ndarray:
         nb = C.c_uint64(0)

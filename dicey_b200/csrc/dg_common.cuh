@@ -72,6 +72,8 @@ struct dg_index {
   uint32_t KB = 0;
   dg::DevBuf<uint8_t> exc_sym, present, text;
   dg::DevBuf<uint2> kmer;
+  dg::DevBuf<int4> wire;        // 16-byte wire records of the last dg_hunt_batch (dg_index_wire_records)
+  uint64_t wire_n = 0;
   dg::DevBuf<uint64_t> cum;
   uint32_t n_exc = 0;
   uint32_t nseq = 0;

@@ -992,10 +992,18 @@ __global__ void k_count(const Cand* __restrict__ cands, uint32_t n, unsigned lon
 }
 
 // chunked dg_hunt_batch: chunk-local query ids, pool offsets and hit offsets -> batch-global
+// ... and the 16-byte wire record of every hit (dg_index_wire_records)
 __global__ void k_rebase(dg_hit* __restrict__ hits, uint64_t nhits, uint64_t* __restrict__ qoff, uint32_t nq1,
-                         uint32_t q0, uint64_t pool_base, uint64_t hit_base) {
+                         uint32_t q0, uint64_t pool_base, uint64_t hit_base, int4* __restrict__ wire) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nhits) { hits[i].query += q0; hits[i].aln_off += pool_base; }
+  if (i < nhits) {
+    dg_hit h = hits[i];
+    h.query += q0;
+    h.aln_off += pool_base;
+    hits[i].query = h.query;
+    hits[i].aln_off = h.aln_off;
+    if (wire) wire[i] = make_int4((int)h.query, (int)h.chr, (int)h.start, (int)(((uint32_t)h.score & 0xFFFFu) | ((uint32_t)h.strand << 16)));
+  }
   if (i < nq1) qoff[i] += hit_base;
 }
 
@@ -1685,6 +1693,15 @@ int dg_batch_summary(dg_batch* b, uint64_t* n_hits, uint64_t* n_candidates) {
   if (n_candidates) *n_candidates = b->ncand;
   return DG_OK;
 }
+int dg_index_wire_records(dg_index* idx, const void** device_ptr, uint64_t* n) {
+  if (!idx || !device_ptr || !n) { set_error("null argument"); return DG_ERR_ARG; }
+  cudaSetDevice(idx->device);
+  cudaStreamSynchronize(idx->stream);
+  for (auto s2 : idx->xstream) if (s2) cudaStreamSynchronize(s2);
+  *device_ptr = idx->wire_n ? (const void*)idx->wire.p : nullptr;
+  *n = idx->wire_n;
+  return DG_OK;
+}
 int dg_batch_device_hits(dg_batch* b, const void** device_ptr, uint64_t* n_hits) {
   if (!b || !b->ran || !device_ptr || !n_hits) { set_error("batch has not run"); return DG_ERR_ARG; }
   cudaStreamSynchronize(b->st);
@@ -1772,8 +1789,17 @@ struct ChunkPipe {
           r->hits.reserve(std::max<size_t>(need_hits, (size_t)(scale * need_hits)), hit_base * sizeof(dg_hit), true);
           r->pool.reserve(std::max<size_t>(need_pool, (size_t)(scale * need_pool)), pool_base, true);
         }
+        if (hit_base + b->nhits > idx->wire.count) {
+          // grow (first call with this volume): keep what earlier chunks wrote
+          for (cudaStream_t s2 : {idx->stream, idx->xstream[0], idx->xstream[1], idx->xstream[2]}) if (s2) DG_CUDA(cudaStreamSynchronize(s2));
+          DevBuf<int4> bigger;
+          bigger.alloc((size_t)(1.15 * (double)nq / (double)q1 * (double)(hit_base + b->nhits)) + 1024);
+          if (hit_base) DG_CUDA(cudaMemcpy(bigger.p, idx->wire.p, hit_base * sizeof(int4), cudaMemcpyDeviceToDevice));
+          std::swap(idx->wire.p, bigger.p);
+          std::swap(idx->wire.count, bigger.count);
+        }
         k_rebase<<<grid_for(std::max<uint64_t>(b->nhits, (uint64_t)cn + 1), 256), 256, 0, st>>>(
-            b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base);
+            b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base, idx->wire.p + hit_base);
         cudaEvent_t ev;
         DG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         DG_CUDA(cudaEventRecord(ev, st));
@@ -1850,6 +1876,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
       r->nhits = p.hit_base;
       r->hits.bytes = p.hit_base * sizeof(dg_hit);
       r->pool.bytes = p.pool_base;
+      idx->wire_n = p.hit_base;
     }
   } catch (CudaFail& e) {
     p.rc = e.code;
@@ -1878,6 +1905,14 @@ int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint
   if (rc) return rc;
   double t1 = now();
   rc = run_impl(b);
+  if (!rc) {
+    try {
+      if (b->nhits > idx->wire.count) idx->wire.alloc(b->nhits + (b->nhits >> 3) + 1024);
+      if (b->nhits)
+        k_rebase<<<grid_for(b->nhits, 256), 256, 0, b->st>>>(b->hits.p, b->nhits, b->qoff.p, 0, 0, 0, 0, idx->wire.p);
+      idx->wire_n = b->nhits;
+    } catch (CudaFail& e) { rc = e.code; }
+  }
   double t2 = now();
   if (!rc) rc = fetch_impl(b, out);
   double t3 = now();

@@ -108,26 +108,82 @@ class _DeviceBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def allgather_hits_device(batch):
-    """The exchange step of the path on device memory: the dg_hit records of a batch
-    that has run are all-gathered over NCCL / NVLink straight from HBM -- counts first, then the
-    records padded to the largest count.  Returns (uint8 tensor [world, max_count * 48] on the
-    device, int64 counts [world] on the device)."""
+WIRE_INTS = 4  # int32 words per hit on the wire: query, chr, start, score (low 16 bits) | strand (bits 16-23)
+
+
+def _wire_records(raw_u8):
+    """dg_hit records (uint8 tensor, 48 bytes each) -> the 16-byte wire record the ranks exchange:
+    hit coordinates, strand and edit distance.  Alignment strings stay with the owning rank."""
+    import torch
+    w = raw_u8.view(torch.int32).view(-1, HIT_DTYPE.itemsize // 4)
+    query, score, chrom, start = w[:, 0], w[:, 1], w[:, 2], w[:, 3]
+    strand = w[:, 10] & 0xFF                      # byte 40 of dg_hit
+    return torch.stack((query, chrom, start, (score & 0xFFFF) | (strand << 16)), dim=1).contiguous()
+
+
+def unwire_records(wire: np.ndarray) -> np.ndarray:
+    """The inverse for the host: structured array (query, chr, start, score, strand)."""
+    wire = np.ascontiguousarray(wire, dtype=np.int32).reshape(-1, WIRE_INTS)
+    out = np.zeros(len(wire), dtype=[("query", "<u4"), ("chr", "<u4"), ("start", "<u4"), ("score", "<i4"), ("strand", "u1")])
+    out["query"], out["chr"], out["start"] = wire[:, 0].view(np.uint32), wire[:, 1].view(np.uint32), wire[:, 2].view(np.uint32)
+    out["score"] = (wire[:, 3] & 0xFFFF).astype(np.int16).astype(np.int32)
+    out["strand"] = ((wire[:, 3] >> 16) & 0xFF).astype(np.uint8)
+    return out
+
+
+def _allgather_wire(mine):
+    """counts first, then the wire records padded to the largest count (one NCCL all-gather each)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
-    ptr, n = batch.device_hits()
-    isz = HIT_DTYPE.itemsize
-    cnt = torch.tensor([n], dtype=torch.int64, device="cuda")
-    counts = torch.empty(world, dtype=torch.int64, device="cuda")
+    n = mine.shape[0]
+    cnt = torch.tensor([n], dtype=torch.int64, device=mine.device)
+    counts = torch.empty(world, dtype=torch.int64, device=mine.device)
     dist.all_gather_into_tensor(counts, cnt)
     mx = max(int(counts.max().item()), 1)
-    mine = torch.zeros(mx * isz, dtype=torch.uint8, device="cuda")
+    padded = torch.zeros((mx, WIRE_INTS), dtype=torch.int32, device=mine.device)
+    padded[:n] = mine
+    out = torch.empty((world * mx, WIRE_INTS), dtype=torch.int32, device=mine.device)
+    dist.all_gather_into_tensor(out, padded)
+    return out.view(world, mx, WIRE_INTS), counts
+
+
+def allgather_hits_device(batch):
+    """The exchange step of the path on device memory: the hit records of a batch
+    that has run are turned into 16-byte wire records and all-gathered over NCCL / NVLink straight
+    from HBM.  Returns (int32 tensor [world, max_count, 4] on the device, int64 counts [world])."""
+    import torch
+    ptr, n = batch.device_hits()
+    isz = HIT_DTYPE.itemsize
     if n:
-        mine[:n * isz].copy_(torch.as_tensor(_DeviceBytes(ptr, n * isz), device="cuda"))
-    out = torch.empty(world * mx * isz, dtype=torch.uint8, device="cuda")
-    dist.all_gather_into_tensor(out, mine)
-    return out.view(world, mx * isz), counts
+        mine = _wire_records(torch.as_tensor(_DeviceBytes(ptr, n * isz), device="cuda"))
+    else:
+        mine = torch.zeros((0, WIRE_INTS), dtype=torch.int32, device="cuda")
+    return _allgather_wire(mine)
+
+
+def allgather_hits_index(index):
+    """The exchange after Index.hunt(): the library keeps the wire records of the last call in HBM
+    (dg_index_wire_records), so nothing is uploaded again."""
+    import torch
+    ptr, n = index.wire_records()
+    if n:
+        mine = torch.as_tensor(_DeviceBytes(ptr, n * 4 * WIRE_INTS), device="cuda").view(torch.int32).view(-1, WIRE_INTS)
+    else:
+        mine = torch.zeros((0, WIRE_INTS), dtype=torch.int32, device="cuda")
+    return _allgather_wire(mine)
+
+
+def allgather_hits_host(res: HuntResult):
+    """The same exchange starting from a host-resident result (dg_hunt_batch): the records go back
+    to the device as wire records (16 of their 48 bytes) and are all-gathered there."""
+    import torch
+    if len(res.hits):
+        raw = torch.from_numpy(res.hits.view(np.uint8).reshape(-1)).cuda(non_blocking=True)
+        mine = _wire_records(raw)
+    else:
+        mine = torch.zeros((0, WIRE_INTS), dtype=torch.int32, device="cuda")
+    return _allgather_wire(mine)
 
 
 def hunt_sharded(index, seqs, params, rank: int | None = None, world: int | None = None) -> HuntResult:

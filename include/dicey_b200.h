@@ -184,6 +184,12 @@ int dg_count_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uin
 int dg_backward_search_batch(dg_index* idx, const char* seqs, const uint64_t* offsets,
                              uint32_t nq, uint64_t* l, uint64_t* r);
 
+/* The hit records of the last dg_hunt_batch on this index as 16-byte wire records in HBM
+ * (int32 x 4: query, chr, start, (score & 0xFFFF) | strand << 16 -- coordinates, strand and
+ * distance; alignments stay in the dg_result), valid until the next dg_hunt_batch / close.  The
+ * multi-GPU layer all-gathers them over NVLink from device memory.              */
+int dg_index_wire_records(dg_index* idx, const void** device_ptr, uint64_t* n);
+
 /* ---- results ------------------------------------------------------------------------ */
 const dg_hit* dg_result_hits(const dg_result* r, uint64_t* n);
 const uint64_t* dg_result_query_offsets(const dg_result* r, uint32_t* nq); /* nq+1 entries */

@@ -25,8 +25,15 @@ def _worker(rank, world, port, q):
     parts = [shard.unpack_result(g) for g in gathered]
     offs = [np.arange(b[r], b[r + 1] + 1, dtype=np.uint64) * 10 for r in range(world)]
     m = shard.merge_results(parts, offs)
+    # the 16-byte wire records of the device-side exchange (counts, then padded records)
+    import torch
+    wire = shard._wire_records(torch.from_numpy(mine.hits.view(np.uint8).reshape(-1).copy()))
+    allw, counts = shard._allgather_wire(wire)
+    got = [shard.unwire_records(allw[r, :int(counts[r])].numpy()) for r in range(world)]
+    wire_ok = all(len(got[r]) == (b[r + 1] - b[r]) * (r + 1) and (got[r]["chr"] == 10 + r).all() and (got[r]["score"] == -1).all()
+                  and (got[r]["strand"] == ord("+")).all() for r in range(world))
     q.put((rank, m.nq, len(m.hits), [int(x) for x in m.qoff], [int(x) for x in m.hits["chr"]],
-           [int(x) for x in m.hits["query"]]))
+           [int(x) for x in m.hits["query"]], wire_ok))
     dist.destroy_process_group()
 
 
@@ -43,7 +50,8 @@ def test_gloo_allgather_of_hit_records():
         p.join(timeout=60)
         assert p.exitcode == 0
     # rank 0 owns queries 0..2 (1 hit each), rank 1 owns 3..6 (2 hits each); both ranks see the same merge
-    for rank, nq, nh, qoff, chrs, qs in out:
+    for rank, nq, nh, qoff, chrs, qs, wire_ok in out:
+        assert wire_ok
         assert nq == 7 and nh == 3 * 1 + 4 * 2
         assert qoff == [0, 1, 2, 3, 5, 7, 9, 11]
         assert chrs == [10] * 3 + [11] * 8

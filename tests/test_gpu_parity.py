@@ -264,3 +264,20 @@ def test_alternative_candidate_orderings(indexes, monkeypatch, knob, case, index
     alt = ix.hunt(seqs, par)
     raws = [s.encode() for s in seqs]
     assert alt.records_tsv(par, raws) == base.records_tsv(par, raws)
+
+
+@pytest.mark.parametrize("chunk", ["100000000", "1500"])
+def test_wire_records_in_hbm(indexes, monkeypatch, chunk):
+    """dg_index_wire_records: the 16-byte records the multi-GPU exchange all-gathers from device memory."""
+    import torch
+    from dicey_b200 import shard
+    ix = indexes["t1m"]
+    monkeypatch.setenv("DG_CHUNK", chunk)
+    pr = synth.primers_fast(42, 8, 125000, 5000, 20, 1, True, rng_seed=5)
+    res = ix.hunt(pr, HuntParams(distance=1))
+    ptr, n = ix.wire_records()
+    assert n == len(res.hits) > 2000
+    wire = torch.as_tensor(shard._DeviceBytes(ptr, n * 16), device="cuda").view(torch.int32).view(-1, 4).cpu().numpy()
+    got = shard.unwire_records(wire)
+    for f in ("query", "chr", "start", "score", "strand"):
+        assert np.array_equal(got[f], res.hits[f]), f
