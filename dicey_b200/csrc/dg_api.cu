@@ -95,6 +95,8 @@ int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* by
   else if (w == "exc_sym") { src = idx->exc_sym.p; nb = idx->n_exc; }
   else if (w == "sa_full") { src = idx->sa_full.p; nb = idx->sa_full.bytes(); }
   else if (w == "present_kb") { src = idx->present_kb.p; nb = idx->present_kb.bytes(); }
+  else if (w == "present_hi") { src = idx->present_hi.p; nb = idx->present_hi.bytes(); }
+  else if (w == "present_lo") { src = idx->present_lo.p; nb = idx->present_lo.bytes(); }
   else { set_error("unknown array name"); return DG_ERR_ARG; }
   if (!buf) { *bytes = nb; return DG_OK; }
   if (*bytes < nb) { set_error("buffer too small"); return DG_ERR_ARG; }

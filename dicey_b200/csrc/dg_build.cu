@@ -545,15 +545,28 @@ static void build_presence_bitmap(dg_index* ix) {
     while (KB < 18 && (1ULL << (2 * KB)) < 16 * ix->n) ++KB;
   }
   if (KB > 19) KB = 19;
-  if (KB && KB < 6) KB = 6;
+  if (KB && KB < 7) KB = 7;
   ix->KB = KB;
   if (!KB) return;
-  uint64_t words = (1ULL << (2 * KB)) >> 5;
-  ix->present_kb.alloc(words);
-  DG_CUDA(cudaMemsetAsync(ix->present_kb.p, 0, words * 4, st));
   uint64_t nthreads = (ix->n + kPresenceChunk - 1) / kPresenceChunk;
-  k_presence<<<grid_for(nthreads, 128), 128, 0, st>>>(ix->text.p, ix->n, KB, ix->present_kb.p);
-  DG_CUDA(cudaGetLastError());
+  auto build = [&](DevBuf<uint32_t>& buf, uint32_t kb) {
+    uint64_t words = (1ULL << (2 * kb)) >> 5;
+    buf.alloc(words);
+    DG_CUDA(cudaMemsetAsync(buf.p, 0, words * 4, st));
+    k_presence<<<grid_for(nthreads, 128), 128, 0, st>>>(ix->text.p, ix->n, kb, buf.p);
+    DG_CUDA(cudaGetLastError());
+  };
+  build(ix->present_kb, KB);
+  // neighbours: KB - 1 always (a quarter of the size); KB + 1 (four times the size) when it fits
+  // comfortably in what is left of the HBM (DG_BITMAP_EXTRA=0 switches both off)
+  const char* ex = getenv("DG_BITMAP_EXTRA");
+  if (!(ex && atoi(ex) == 0)) {
+    build(ix->present_lo, KB - 1);
+    size_t free_b = 0, total_b = 0;
+    DG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t hi_bytes = (1ULL << (2 * (KB + 1))) >> 3;
+    if (KB + 1 <= 19 && hi_bytes * 3 < free_b) build(ix->present_hi, KB + 1);
+  }
   DG_CUDA(cudaStreamSynchronize(st));
 }
 

@@ -63,6 +63,10 @@ struct IndexView {
   uint32_t nseq;
   const uint32_t* present_kb; // 4^KB bits: the ACGT KB-mer with this packed code occurs in the text
   uint32_t KB;                // 0 = no presence bitmap
+  // the same for KB + 1 (strings at least that long are tested there: 4 x fewer false survivors)
+  // and KB - 1 (strings one base too short for the primary bitmap); null = not built
+  const uint32_t* present_hi;
+  const uint32_t* present_lo;
 };
 
 DG_HD int popc64(uint64_t x) {

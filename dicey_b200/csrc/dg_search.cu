@@ -413,7 +413,6 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
   const int K = (int)ix.K;
   const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
   const int KB = (int)ix.KB;
-  const uint64_t kbmask = (1ULL << (2 * KB)) - 1ULL;
   uint32_t queued = 0;
   unsigned long long my_scripts = 0;
 
@@ -500,12 +499,20 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
                             : pack_script(strand, 2, p1 * CS + k1, p2 * CS + k2);
           }
           pass = L > 0;
-          if (pass && KB && L >= KB) {
-            const uint64_t bit = presence_bit(code & kbmask, KB);
-            // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
-            uint32_t word;
-            asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(ix.present_kb + (bit >> 5)));
-            pass = (word >> (uint32_t)(bit & 31)) & 1u;
+          if (pass && KB) {
+            // the longest window the string covers: KB + 1, KB or KB - 1 bases
+            const uint32_t* bm = nullptr;
+            int kb = 0;
+            if (L > KB && ix.present_hi) { bm = ix.present_hi; kb = KB + 1; }
+            else if (L >= KB) { bm = ix.present_kb; kb = KB; }
+            else if (L == KB - 1 && ix.present_lo) { bm = ix.present_lo; kb = KB - 1; }
+            if (bm) {
+              const uint64_t bit = presence_bit(code & ((1ULL << (2 * kb)) - 1ULL), kb);
+              // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
+              uint32_t word;
+              asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(bm + (bit >> 5)));
+              pass = (word >> (uint32_t)(bit & 31)) & 1u;
+            }
           }
         }
         const unsigned pm = __ballot_sync(FULL, pass);

@@ -53,21 +53,23 @@ def test_index_arrays_stress(indexes):
     sa = np.array(naive_sa(raw), dtype=np.uint32)
     assert np.array_equal(ix.debug_array("sa_samples", np.uint32), sa[::32])
     assert np.array_equal(ix.debug_array("sa_full", np.uint32), sa)   # rebuilt beside the text by the LF chains
-    # KB-mer presence bitmap: exactly the ACGT-only windows of the text
-    kb = ix.info()["bitmap_k"]
-    bits = ix.debug_array("present_kb", np.uint32)
-    want = np.zeros_like(bits)
+    # KB-mer presence bitmaps (KB - 1, KB, KB + 1): exactly the ACGT-only windows of the text
     code = {65: 0, 67: 1, 71: 2, 84: 3}
-    for i in range(len(raw) - kb + 1):
-        w = raw[i:i + kb]
-        if all(ch in code for ch in w):
-            v = 0
-            for ch in w:
-                v = (v << 2) | code[ch]
-            lo = 2 * (kb - 5)   # presence_bit(): line = last kb - 5 bases, bit = the 5 bases before them
-            v = ((v & ((1 << lo) - 1)) << 10) | (v >> lo)
-            want[v >> 5] |= np.uint32(1 << (v & 31))
-    assert np.array_equal(bits, want)
+    kb0 = ix.info()["bitmap_k"]
+    for name, kb in (("present_lo", kb0 - 1), ("present_kb", kb0), ("present_hi", kb0 + 1)):
+        bits = ix.debug_array(name, np.uint32)
+        assert bits.size == (4 ** kb) // 32, name
+        want = np.zeros_like(bits)
+        for i in range(len(raw) - kb + 1):
+            w = raw[i:i + kb]
+            if all(ch in code for ch in w):
+                v = 0
+                for ch in w:
+                    v = (v << 2) | code[ch]
+                lo = 2 * (kb - 5)   # presence_bit(): line = last kb - 5 bases, bit = the 5 bases before them
+                v = ((v & ((1 << lo) - 1)) << 10) | (v >> lo)
+                want[v >> 5] |= np.uint32(1 << (v & 31))
+        assert np.array_equal(bits, want), name
     # occ blocks: cumulative ACGT counts + bit planes of the BWT
     t = np.frombuffer(raw + b"\0", dtype=np.uint8)
     bwt = t[(sa.astype(np.int64) - 1) % t.size]
@@ -139,7 +141,8 @@ def test_build_text_equals_fm9(indexes, name):
         assert ix.info()["n"] == ref.info()["n"]
         for what, dt in (("text", np.uint8), ("sa_samples", np.uint32), ("isa_samples", np.uint32), ("occ", np.uint32),
                          ("C", np.uint32), ("exc_pos", np.uint32), ("exc_sym", np.uint8), ("kmer", np.uint32),
-                         ("sa_full", np.uint32), ("present_kb", np.uint32)):
+                         ("sa_full", np.uint32), ("present_kb", np.uint32), ("present_hi", np.uint32),
+                         ("present_lo", np.uint32)):
             assert np.array_equal(ix.debug_array(what, dt), ref.debug_array(what, dt)), what
 
 
