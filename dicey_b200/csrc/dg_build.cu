@@ -21,6 +21,7 @@
 
 #include "dg_common.cuh"
 #include "fm9.hpp"
+#include "fm9_select.hpp"
 
 namespace dg {
 
@@ -826,9 +827,8 @@ int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, d
 // .fm9 writer: store_to_checked_file (index.h:122 -> io.hpp:814-828) of a csa_wt<> whose wavelet
 // tree, rank blocks, samples and alphabet are rebuilt from the device index.  The Huffman shape
 // follows _huff_shape::construct_tree (wt_huff.hpp:72-100) and _byte_tree's BFS numbering
-// (wt_helper.hpp:199-269) so that the written bytes equal SDSL's, except for the two
-// select_support_mcl sections, which are written empty (arg_cnt = 0, select_support_mcl.hpp:470-476)
-// because count / locate / extract never touch them.
+// (wt_helper.hpp:199-269), and the two select_support_mcl sections are rebuilt by fm9_select.hpp,
+// so that the written bytes equal SDSL's.
 namespace dg {
 namespace {
 
@@ -1094,7 +1094,18 @@ int write_fm9(dg_index* ix, const char* path) {
     bool ok = put_u64(f, n) && put_u64(f, (uint64_t)sigma);
     ok = ok && put_int_vector(f, bv.data(), bv_size, 1);
     ok = ok && put_int_vector(f, bb.data(), (uint64_t)bb.size() * 64, 64);
-    ok = ok && put_u64(f, 0) && put_u64(f, 0);  // select_support_mcl<1>, <0>: arg_cnt = 0
+    {
+      // select_support_mcl<1>, <0> over m_bv (never read by count / locate / extract, written so that
+      // the file equals SDSL's byte for byte); DG_FM9_NO_SELECT=1 writes them empty (arg_cnt = 0)
+      if (getenv("DG_FM9_NO_SELECT")) {
+        ok = ok && put_u64(f, 0) && put_u64(f, 0);
+      } else {
+        for (int one = 1; one >= 0 && ok; --one) {
+          SelectMclWriter sel(bv.data(), bv_size, one == 1);
+          ok = put(f, sel.bytes().data(), sel.bytes().size());
+        }
+      }
+    }
     ok = ok && put_u64(f, (uint64_t)nn);
     for (size_t v = 0; ok && v < nn; ++v) {
       uint8_t rec[22];

@@ -120,9 +120,9 @@ int dg_index_build_text(const uint8_t* text, uint64_t len, int device, dg_index*
 int dg_index_build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device,
                              dg_index** out);
 
-/* store_to_checked_file (index.h:122): writes an SDSL-loadable csa_wt<> .fm9 + .fm9_check
- * from the device index.  Select supports are written empty (arg_cnt = 0; count / locate /
- * extract never use them), everything else follows csa_wt.hpp:362-373.                   */
+/* store_to_checked_file (index.h:122): writes the csa_wt<> .fm9 + .fm9_check from the device
+ * index, byte for byte what SDSL writes for the same text (csa_wt.hpp:362-373: Huffman-shaped
+ * wavelet tree, rank_support_v, both select_support_mcl, SA / ISA samples, byte_alphabet).      */
 int dg_index_write_fm9(dg_index* idx, const char* fm9_path);
 
 void dg_index_close(dg_index* idx);

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include "../../dicey_b200/csrc/dg_core.cuh"
+#include "../../dicey_b200/csrc/fm9.hpp"
+#include "../../dicey_b200/csrc/fm9_select.hpp"
 
 using namespace dg;
 
@@ -139,6 +141,32 @@ int main(int argc, char** argv) {
     }
     fprintf(stderr, "banded needle checked on %d (pair, dmax) cases\n", banded_checked);
     return banded_checked >= 100 ? 0 : 4;
+  }
+  if (cmd == "select" && argc >= 3) {
+    // the select_support_mcl sections rebuilt from m_bv must equal the bytes SDSL wrote into the file
+    FILE* f = fopen(argv[2], "rb");
+    if (!f) return 2;
+    Fm9Reader rd(f);
+    uint64_t n, sigma, bits, rbits;
+    uint8_t w;
+    std::vector<uint64_t> bv;
+    if (!rd.u64(n) || !rd.u64(sigma) || !rd.int_vector(&bv, bits, w) || !rd.int_vector(nullptr, rbits, w)) return 2;
+    for (int one = 1; one >= 0; --one) {
+      long a = ftell(f);
+      if (!fm9_skip_select(rd)) return 2;
+      long b = ftell(f);
+      std::vector<uint8_t> want((size_t)(b - a));
+      fseek(f, a, SEEK_SET);
+      if (fread(want.data(), 1, want.size(), f) != want.size()) return 2;
+      SelectMclWriter sel(bv.data(), bits, one == 1);
+      if (sel.bytes() != want) {
+        fprintf(stderr, "select_support_mcl<%d> differs: %zu bytes built, %zu in the file\n", one, sel.bytes().size(), want.size());
+        return 3;
+      }
+      std::cout << "select_support_mcl<" << one << "> " << want.size() << " bytes identical\n";
+    }
+    fclose(f);
+    return 0;
   }
   return 2;
 }

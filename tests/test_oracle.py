@@ -84,3 +84,11 @@ def test_kernel_needle_reproduces_alignments():
             else:
                 nlead += 1
         assert g == f"{sc}\t{nlead}\t{ra}\t{qa}"
+
+
+@pytest.mark.parametrize("name", ["t1m", "stress"])
+def test_select_supports_rebuilt_byte_for_byte(name):
+    """fm9_select.hpp (used by dg_index_write_fm9) against the select_support_mcl sections SDSL wrote
+    into the golden indexes: t1m takes SDSL's init_fast path, stress (< 100000 bits) init_slow."""
+    out = run(HOSTSIM, ["select", name + ".fm9"])
+    assert out.count("bytes identical") == 2
