@@ -796,27 +796,28 @@ __device__ __forceinline__ uint32_t find_segment(const uint64_t* __restrict__ of
 }
 
 __global__ void k_locate(IndexView ix, const Cand* __restrict__ cands, uint32_t n, const uint64_t* __restrict__ loc_off,
-                         uint64_t total, uint64_t* __restrict__ keys) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
+                         uint64_t first_row, uint64_t nrows, uint64_t* __restrict__ keys) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrows) return;
+  const uint64_t t = first_row + k;   // row number over the whole batch; keys holds this slice
   // candidate with loc_off[i] <= t < loc_off[i+1] (the last one of a run sharing the offset:
   // candidates without rows are skipped)
   const uint32_t lo = find_segment(loc_off, n, t);
   Cand c = cands[lo];
   uint32_t row = c.l + (uint32_t)(t - loc_off[lo]);
   uint32_t pos = sa_value(ix, row);
-  keys[t] = ((uint64_t)lo << 32) | pos;
+  keys[k] = ((uint64_t)lo << 32) | pos;
 }
 
 // Ascending text positions inside each candidate's segment of located rows (hunter.h:356) by a
 // rank count; used when no candidate holds more than kGroupMax rows (else: radix sort).
-__global__ void k_locate_order(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ loc_off, uint64_t total,
-                               uint64_t* __restrict__ out) {
+__global__ void k_locate_order(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ loc_off, uint64_t first_row,
+                               uint64_t nrows, uint64_t* __restrict__ out) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
+  if (t >= nrows) return;
   const uint64_t me = keys[t];
   const uint32_t c = (uint32_t)(me >> 32);
-  const uint64_t s = loc_off[c], e = loc_off[c + 1];
+  const uint64_t s = loc_off[c] - first_row, e = loc_off[c + 1] - first_row;
   uint64_t rank = 0;
   if (e - s > 1)
     for (uint64_t j = s; j < e; ++j) {
@@ -831,7 +832,8 @@ struct VerifyArgs {
   uint32_t ncand;
   const uint64_t* hit_off;   // per candidate (exclusive scan of ntake), ncand + 1 entries
   const uint64_t* loc_off;   // per candidate, ncand + 1 entries
-  const uint64_t* keys;      // sorted (candidate << 32 | position)
+  const uint64_t* keys;      // sorted (candidate << 32 | position) of the rows [key_base, ...)
+  uint64_t key_base;
   uint64_t nhits;
   dg_hit* hits;
   uint8_t* pool;             // alignment pool: strings back to back, claimed block by block
@@ -875,7 +877,7 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     const uint32_t lo = find_segment(a.hit_off, a.ncand, h);
     Cand c = a.cands[lo];
     uint64_t j = h - a.hit_off[lo];
-    uint64_t pos = a.keys[a.loc_off[lo] + j] & 0xFFFFFFFFULL;
+    uint64_t pos = a.keys[a.loc_off[lo] - a.key_base + j] & 0xFFFFFFFFULL;
     int strand, koff;
     Script sc;
     unpack_script(c.code, indel, strand, sc);
@@ -1341,43 +1343,48 @@ static int run_impl(dg_batch* b) {
     if (b->par.distance >= 2) cap64 = 256ULL * nq + (1ULL << 20);
     if (const char* e = getenv("DG_CAND_CAP")) cap64 = strtoull(e, nullptr, 10);
     if (cap64 > (1ULL << 30)) cap64 = 1ULL << 30;
-    b->cands.alloc(cap64, st);
     ABuf<unsigned int> ctr;     // [0] n_cand, [1] overflow
     ABuf<unsigned long long> nscripts;
     ctr.alloc(2, st);
     nscripts.alloc(1, st);
-    DG_CUDA(cudaMemsetAsync(ctr.p, 0, 8, st));
-    DG_CUDA(cudaMemsetAsync(nscripts.p, 0, 8, st));
-    SearchOut so{b->cands.p, (uint32_t)cap64, ctr.p, ctr.p + 1, nscripts.p};
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ix->device);
-    if (nq) {
-      // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
-      int per_sm = 0;
-      const uint64_t npairs = b->par.reverse ? 2ULL * nq : (uint64_t)nq;
-      static const int ppw_env = getenv("DG_PAIRS_PER_WARP") ? atoi(getenv("DG_PAIRS_PER_WARP")) : 0;
-      uint32_t ppw = ppw_env > 0 ? (uint32_t)ppw_env : 4u;
-      // small batches: fewer pairs per warp so that the grid still covers every SM
-      while (ppw > 1 && npairs / (8ull * ppw) < (uint64_t)nsm * 6) ppw >>= 1;
-      const unsigned blocks = (unsigned)((npairs + 8ull * ppw - 1) / (8ull * ppw));
-      (void)per_sm;
-      if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
-      else k_search_packed<false><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
-      // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
-      DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
-      k_search<<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
-      launches += 2;
-    }
-    prof_mark(ix, 2, st);
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
-    DG_CUDA(cudaMemcpyAsync(hc, ctr.p, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(&h_scripts, nscripts.p, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
-    DG_CUDA(cudaGetLastError());
-    if (hc[1]) {
-      set_error("candidate buffer overflow (" + std::to_string(hc[0]) + " neighbour strings matched; raise DG_CAND_CAP)");
-      return DG_ERR_OVERFLOW;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      b->cands.alloc(cap64, st);
+      DG_CUDA(cudaMemsetAsync(ctr.p, 0, 8, st));
+      DG_CUDA(cudaMemsetAsync(nscripts.p, 0, 8, st));
+      SearchOut so{b->cands.p, (uint32_t)cap64, ctr.p, ctr.p + 1, nscripts.p};
+      if (nq) {
+        // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
+        int per_sm = 0;
+        const uint64_t npairs = b->par.reverse ? 2ULL * nq : (uint64_t)nq;
+        static const int ppw_env = getenv("DG_PAIRS_PER_WARP") ? atoi(getenv("DG_PAIRS_PER_WARP")) : 0;
+        uint32_t ppw = ppw_env > 0 ? (uint32_t)ppw_env : 4u;
+        // small batches: fewer pairs per warp so that the grid still covers every SM
+        while (ppw > 1 && npairs / (8ull * ppw) < (uint64_t)nsm * 6) ppw >>= 1;
+        const unsigned blocks = (unsigned)((npairs + 8ull * ppw - 1) / (8ull * ppw));
+        if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
+        else k_search_packed<false><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
+        // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
+        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
+        k_search<<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
+        launches += 2;
+      }
+      if (attempt == 0) prof_mark(ix, 2, st);
+      DG_CUDA(cudaMemcpyAsync(hc, ctr.p, 8, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaMemcpyAsync(&h_scripts, nscripts.p, 8, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      DG_CUDA(cudaGetLastError());
+      if (!hc[1]) break;
+      // more neighbour strings matched than the buffer holds (repeat-rich queries): the counter
+      // kept counting, so the second attempt is sized exactly
+      if (attempt == 1 || hc[0] >= 0x7FFFFFF0u) {
+        set_error("candidate buffer overflow (" + std::to_string(hc[0]) + " neighbour strings matched); split the batch");
+        return DG_ERR_OVERFLOW;
+      }
+      cap64 = (uint64_t)hc[0] + 1024;
     }
     uint32_t n = hc[0];
     uint64_t n_candidates = n;
@@ -1535,33 +1542,35 @@ static int run_impl(dg_batch* b) {
       launches += 2;
     }
     DG_CUDA(cudaStreamSynchronize(st));
-    uint64_t loc_cap = 1ULL << 28;
-    if (const char* e = getenv("DG_LOCATE_CAP")) loc_cap = strtoull(e, nullptr, 10);
-    if (nlocate > loc_cap || nlocate >= (1ULL << 31)) {
-      set_error("too many occurrences to locate in one batch (" + std::to_string(nlocate) + "; raise DG_LOCATE_CAP or split the batch)");
-      return DG_ERR_OVERFLOW;
-    }
-    // ---- locate + per-candidate ascending order
-    const uint64_t* sorted_keys = nullptr;
-    if (nlocate) {
-      keys.alloc(nlocate, st);
-      keys2.alloc(nlocate, st);
-      k_locate<<<grid_for(nlocate, 128), 128, 0, st>>>(v, cur, n, loc_off.p, nlocate, keys.p);
-      if (h_max_rows <= (unsigned long long)kGroupMax && !getenv("DG_LOCATE_RADIX")) {
-        k_locate_order<<<grid_for(nlocate, 256), 256, 0, st>>>(keys.p, loc_off.p, nlocate, keys2.p);
-        launches += 2;
-      } else {
-        int cbits = 1;
-        while ((1ULL << cbits) < (uint64_t)n + 1 && cbits < 32) ++cbits;
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, (int)nlocate, 0, 32 + cbits, st);
-        cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, keys.p, keys2.p, (int)nlocate, 0, 32 + cbits, st);
-        launches += 4;
+    uint64_t loc_cap = 1ULL << 28;   // located rows held at once (8-byte keys, two buffers)
+    if (const char* e = getenv("DG_LOCATE_CAP")) loc_cap = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    // Batches whose candidates hold more rows than that (repeat-rich queries: the reference locates
+    // every occurrence before it keeps the first max_locations) are located and verified in slices
+    // of consecutive candidates.
+    std::vector<uint64_t> h_loc, h_hit;
+    std::vector<uint32_t> slice_end;    // candidate index one past each slice
+    if (nlocate > loc_cap) {
+      h_loc.resize((size_t)n + 1);
+      h_hit.resize((size_t)n + 1);
+      DG_CUDA(cudaMemcpyAsync(h_loc.data(), loc_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaMemcpyAsync(h_hit.data(), hit_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      uint32_t c0 = 0;
+      while (c0 < n) {
+        uint32_t c1 = c0 + 1;
+        while (c1 < n && h_loc[c1 + 1] - h_loc[c0] <= loc_cap) ++c1;
+        if (h_loc[c1] - h_loc[c0] >= (1ULL << 31)) {
+          set_error("a single neighbour string occurs " + std::to_string(h_loc[c1] - h_loc[c0]) + " times: too many to locate");
+          return DG_ERR_OVERFLOW;
+        }
+        slice_end.push_back(c1);
+        c0 = c1;
       }
-      sorted_keys = keys2.p;
+    } else {
+      slice_end.push_back(n);
     }
-    prof_mark(ix, 4, st);
-    // ---- verify
+    prof_mark(ix, 4, st);   // (locate and verify alternate per slice: both are reported under "verify" when sliced)
+    // ---- locate + per-candidate ascending order + verify, slice by slice
     b->nhits = nhits;
     int maxq = b->par.seed_len ? (int)b->par.seed_len : std::min(b->max_len, kMaxQuery);
     int maxg = std::min(b->max_len, kMaxQuery) + 2 * (int)b->par.distance;
@@ -1571,32 +1580,61 @@ static int run_impl(dg_batch* b) {
     b->hits.alloc(nhits ? nhits : 1, st);
     b->pool.alloc(nhits ? nhits * b->pool_stride : 1, st);   // upper bound; pool_bytes of it are used
     b->pool_bytes = 0;
-    if (nhits) {
-      ABuf<unsigned long long> cursor;
-      cursor.alloc(1, st);
-      DG_CUDA(cudaMemsetAsync(cursor.p, 0, 8, st));
-      VerifyArgs a;
-      a.cands = cur; a.ncand = n; a.hit_off = hit_off.p; a.loc_off = loc_off.p; a.keys = sorted_keys; a.nhits = nhits;
-      a.hits = b->hits.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
-      a.srow_ints = (uint32_t)(maxq + 2);
-      a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
-      a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);
-      a.scratch_stride = (a.scratch_stride + 15) & ~15u;
-      bool need_scratch = (b->par.indel || b->par.seed_len) && (maxq > kLocalQ || maxg > kLocalG);
-      uint64_t chunk = nhits;
-      if (need_scratch) {
-        uint64_t budget = 1ULL << 30;
-        chunk = std::max<uint64_t>(1, std::min<uint64_t>(nhits, budget / a.scratch_stride));
+    ABuf<unsigned long long> cursor;
+    cursor.alloc(1, st);
+    DG_CUDA(cudaMemsetAsync(cursor.p, 0, 8, st));
+    uint32_t c0 = 0;
+    for (size_t sl = 0; sl < slice_end.size() && nlocate; ++sl) {
+      const uint32_t c1 = slice_end[sl];
+      const bool whole = slice_end.size() == 1;
+      const uint64_t row0 = whole ? 0 : h_loc[c0], row1 = whole ? nlocate : h_loc[c1];
+      const uint64_t hit0 = whole ? 0 : h_hit[c0], hit1 = whole ? nhits : h_hit[c1];
+      const uint64_t nrows = row1 - row0;
+      if (nrows) {
+        keys.alloc(nrows, st);
+        keys2.alloc(nrows, st);
+        k_locate<<<grid_for(nrows, 128), 128, 0, st>>>(v, cur, n, loc_off.p, row0, nrows, keys.p);
+        if (h_max_rows <= (unsigned long long)kGroupMax && !getenv("DG_LOCATE_RADIX")) {
+          k_locate_order<<<grid_for(nrows, 256), 256, 0, st>>>(keys.p, loc_off.p, row0, nrows, keys2.p);
+          launches += 2;
+        } else {
+          int cbits = 1;
+          while ((1ULL << cbits) < (uint64_t)n + 1 && cbits < 32) ++cbits;
+          size_t tb = 0;
+          cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, (int)nrows, 0, 32 + cbits, st);
+          cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, keys.p, keys2.p, (int)nrows, 0, 32 + cbits, st);
+          launches += 4;
+        }
       }
-      ABuf<uint8_t> scratch;
-      scratch.alloc(need_scratch ? chunk * a.scratch_stride : 1, st);
-      a.scratch = scratch.p;
-      for (uint64_t first = 0; first < nhits; first += chunk) {
-        a.first_hit = first;
-        a.chunk = std::min<uint64_t>(chunk, nhits - first);
-        k_verify<<<grid_for(a.chunk, kVerifyBlock), kVerifyBlock, 0, st>>>(v, bd, a);
-        ++launches;
+      if (whole) prof_mark(ix, 4, st);
+      if (hit1 > hit0) {
+        VerifyArgs a;
+        a.cands = cur; a.ncand = n; a.hit_off = hit_off.p; a.loc_off = loc_off.p; a.keys = keys2.p; a.key_base = row0; a.nhits = nhits;
+        a.hits = b->hits.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
+        a.srow_ints = (uint32_t)(maxq + 2);
+        a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
+        a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);
+        a.scratch_stride = (a.scratch_stride + 15) & ~15u;
+        bool need_scratch = (b->par.indel || b->par.seed_len) && (maxq > kLocalQ || maxg > kLocalG);
+        const uint64_t span = hit1 - hit0;
+        uint64_t chunk = span;
+        if (need_scratch) {
+          uint64_t budget = 1ULL << 30;
+          chunk = std::max<uint64_t>(1, std::min<uint64_t>(span, budget / a.scratch_stride));
+        }
+        ABuf<uint8_t> scratch;
+        scratch.alloc(need_scratch ? chunk * a.scratch_stride : 1, st);
+        a.scratch = scratch.p;
+        for (uint64_t first = hit0; first < hit1; first += chunk) {
+          a.first_hit = first;
+          a.chunk = std::min<uint64_t>(chunk, hit1 - first);
+          k_verify<<<grid_for(a.chunk, kVerifyBlock), kVerifyBlock, 0, st>>>(v, bd, a);
+          ++launches;
+        }
       }
+      c0 = c1;
+    }
+    {
       unsigned long long used = 0;
       DG_CUDA(cudaMemcpyAsync(&used, cursor.p, 8, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaStreamSynchronize(st));
