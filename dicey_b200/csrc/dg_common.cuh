@@ -105,4 +105,6 @@ int build_from_fm9(const char* path, int device, dg_index** out);
 int build_from_text_host(const uint8_t* text, uint64_t len, int device, dg_index** out);
 int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, dg_index** out);
 int write_fm9(dg_index* idx, const char* path);
+// dg_search.cu
+void release_stream_pools(const cudaStream_t* streams, int n);
 }  // namespace dg

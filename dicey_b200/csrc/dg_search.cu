@@ -87,10 +87,50 @@ struct UnitTabs {
 
 namespace {
 
+// Per-stream cache of device blocks.  One batch makes ~40 short-lived allocations; with three
+// pipeline workers the CUDA API calls behind them serialise on the context lock and were the
+// largest part of the per-chunk fixed cost.  A freed block goes back to the cache of ITS stream
+// and is only ever handed out again for work on the same stream, so stream order keeps reuse
+// safe without events; misses fall through to cudaMallocAsync.
+struct StreamPool {
+  std::multimap<size_t, void*> free_blocks;   // capacity -> block
+  size_t cached = 0;
+  static size_t round_up(size_t bytes) {       // (8 + k) * 2^e classes: at most 12.5 % slack
+    if (bytes < 4096) return 4096;
+    int e = 63 - __builtin_clzll((unsigned long long)bytes);
+    size_t step = (size_t)1 << (e - 3);
+    return (bytes + step - 1) & ~(step - 1);
+  }
+  void* get(size_t cap) {
+    auto it = free_blocks.find(cap);
+    if (it == free_blocks.end()) return nullptr;
+    void* p = it->second;
+    free_blocks.erase(it);
+    cached -= cap;
+    return p;
+  }
+  bool put(void* p, size_t cap) {
+    if (cached + cap > (24ULL << 30)) return false;
+    free_blocks.emplace(cap, p);
+    cached += cap;
+    return true;
+  }
+};
+std::mutex g_pools_mu;
+std::map<cudaStream_t, StreamPool*> g_pools;
+StreamPool* pool_of(cudaStream_t st) {
+  std::lock_guard<std::mutex> g(g_pools_mu);
+  auto it = g_pools.find(st);
+  if (it != g_pools.end()) return it->second;
+  StreamPool* p = new StreamPool();
+  g_pools[st] = p;
+  return p;
+}
+
 template <typename T>
-struct ABuf {  // stream-ordered allocation (cudaMallocAsync pool; reuse across batches is cheap)
+struct ABuf {  // stream-ordered allocation through the stream's block cache
   T* p = nullptr;
-  size_t count = 0;
+  size_t count = 0, cap = 0;
   cudaStream_t st = nullptr;
   ABuf() = default;
   ABuf(const ABuf&) = delete;
@@ -100,14 +140,16 @@ struct ABuf {  // stream-ordered allocation (cudaMallocAsync pool; reuse across 
     release();
     st = s;
     count = n;
-    DG_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), s));
+    cap = StreamPool::round_up((n ? n : 1) * sizeof(T));
+    p = (T*)pool_of(s)->get(cap);
+    if (!p) DG_CUDA(cudaMallocAsync((void**)&p, cap, s));
   }
   void release() {
-    if (p) cudaFreeAsync(p, st);
+    if (p && !pool_of(st)->put(p, cap)) cudaFreeAsync(p, st);
     p = nullptr;
-    count = 0;
+    count = cap = 0;
   }
-  void swap(ABuf& o) { std::swap(p, o.p); std::swap(count, o.count); std::swap(st, o.st); }
+  void swap(ABuf& o) { std::swap(p, o.p); std::swap(count, o.count); std::swap(cap, o.cap); std::swap(st, o.st); }
 };
 
 inline unsigned grid_for(uint64_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
@@ -1047,6 +1089,23 @@ void build_unit_table(int m, int d, bool indel, bool clean, std::vector<uint32_t
 
 }  // namespace
 
+// called by dg_index_close before the streams are destroyed
+void release_stream_pools(const cudaStream_t* streams, int n) {
+  for (int i = 0; i < n; ++i) {
+    if (!streams[i]) continue;
+    StreamPool* p = nullptr;
+    {
+      std::lock_guard<std::mutex> g(g_pools_mu);
+      auto it = g_pools.find(streams[i]);
+      if (it != g_pools.end()) { p = it->second; g_pools.erase(it); }
+    }
+    if (!p) continue;
+    cudaStreamSynchronize(streams[i]);
+    for (auto& kv : p->free_blocks) cudaFree(kv.second);
+    delete p;
+  }
+}
+
 }  // namespace dg
 
 using namespace dg;
@@ -1347,8 +1406,14 @@ static int run_impl(dg_batch* b) {
     ABuf<unsigned long long> nscripts;
     ctr.alloc(2, st);
     nscripts.alloc(1, st);
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ix->device);
+    static int nsm = 0, general_per_sm = 0;   // (every device of the box is the same part)
+    if (!nsm) {
+      int v1 = 148, v2 = 1;
+      cudaDeviceGetAttribute(&v1, cudaDevAttrMultiProcessorCount, ix->device);
+      DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v2, k_search, 256, 0));
+      general_per_sm = std::max(v2, 1);
+      nsm = v1;
+    }
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1358,7 +1423,6 @@ static int run_impl(dg_batch* b) {
       SearchOut so{b->cands.p, (uint32_t)cap64, ctr.p, ctr.p + 1, nscripts.p};
       if (nq) {
         // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
-        int per_sm = 0;
         const uint64_t npairs = b->par.reverse ? 2ULL * nq : (uint64_t)nq;
         static const int ppw_env = getenv("DG_PAIRS_PER_WARP") ? atoi(getenv("DG_PAIRS_PER_WARP")) : 0;
         uint32_t ppw = ppw_env > 0 ? (uint32_t)ppw_env : 4u;
@@ -1368,8 +1432,7 @@ static int run_impl(dg_batch* b) {
         if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
         else k_search_packed<false><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
         // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
-        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, 256, 0));
-        k_search<<<nsm * std::max(per_sm, 1), 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
+        k_search<<<nsm * general_per_sm, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
         launches += 2;
       }
       if (attempt == 0) prof_mark(ix, 2, st);
