@@ -424,7 +424,8 @@ def main_b200(args):
         if os.path.exists(tr):
             try:
                 t_ = json.load(open(tr))
-                if t_.get("kmer") == info["kmer"] and t_.get("bitmap_k") == info["bitmap_k"] and t_.get("primers") == nq:
+                if (t_.get("kmer") == info["kmer"] and t_.get("bitmap_k") == info["bitmap_k"] and t_.get("primers") == nq
+                        and t_.get("index_device_bytes") == info["device_bytes"] and not args.hamming and args.distance == 1):
                     roof["traffic"] = t_.get("dram_bytes_per_launch")
                     roof["frac_dram"] = roof["traffic"] / (ms_search / 1e3) / 1e9 / peak_gbs
             except Exception:
