@@ -53,7 +53,8 @@ class SelectMclWriter {
     put_u64(o, ((uint64_t)width << 56) | bits);
     size_t at = o.size();
     o.resize(at + nw * 8, 0);
-    std::vector<uint64_t> tmp(nw, 0);
+    std::vector<uint64_t>& tmp = scratch_;
+    tmp.assign(nw, 0);
     for (uint64_t i = 0; i < nvals; ++i) {
       const uint64_t b = i * width, wd = b >> 6, off = b & 63;
       const uint64_t v = width == 64 ? vals[i] : (vals[i] & ((1ULL << width) - 1ULL));
@@ -171,6 +172,7 @@ class SelectMclWriter {
   std::vector<uint64_t> super_;
   std::vector<uint8_t> is_mini_;
   std::vector<uint8_t> blocks_, out_;
+  std::vector<uint64_t> scratch_;
 };
 
 }  // namespace dg

@@ -267,3 +267,36 @@ def test_config_headline_edit1_properties(big):
     # text_pos <-> (chr, start) consistency over the whole batch, vectorised
     lead = h["start"].astype(np.int64) - 1 + h["chr"].astype(np.int64) * (RECLEN + 1) - h["text_pos"].astype(np.int64)
     assert (np.abs(lead) <= 2).all()
+
+
+def test_fm9_loaded_as_is_at_full_size(big, fm9):
+    """The 1.6 GB .fm9 (byte-identical to what `dicey index` writes for this text) is parsed and
+    transcoded to the device layout; the result must equal the index built from the text on the GPU."""
+    if not fm9:
+        pytest.skip("needs the .fm9 written for the reference binary")
+    path, _ = fm9
+    t0 = time.time()
+    ix = Index.open(path, 0)
+    print(f"[fullsize] dg_index_open of the 3 Gb .fm9: {time.time() - t0:.1f} s")
+    try:
+        ix.set_records([f"chr{i + 1}" for i in range(NREC)], [RECLEN + 1] * NREC)
+        a, b = ix.info(), big.info()
+        for k in ("n", "sigma", "kmer", "bitmap_k", "n_exceptions"):  # (device_bytes differs: with two replicas on one GPU the second skips the optional KB + 1 bitmap)
+            assert a[k] == b[k], k
+        for what, dt in (("C", np.uint32), ("sa_samples", np.uint32), ("isa_samples", np.uint32), ("exc_pos", np.uint32)):
+            assert np.array_equal(ix.debug_array(what, dt), big.debug_array(what, dt)), what
+        for what in ("text", "occ"):
+            x = ix.debug_array(what)
+            y = big.debug_array(what)
+            assert x.size == y.size and np.array_equal(x, y), what
+            del x, y
+        pr = synth.primers_fast(SEED, NREC, RECLEN, 20_000, 20, 1, True, rng_seed=21)
+        par = HuntParams(distance=1)
+        r1, r2 = ix.hunt(pr, par), big.hunt(pr, par)
+        assert np.array_equal(r1.qoff, r2.qoff)
+        for f in ("query", "score", "chr", "start", "text_pos", "aln_len", "strand"):
+            assert np.array_equal(r1.hits[f], r2.hits[f]), f
+        for q in range(0, 20_000, 211):
+            assert r1.push_hits(q) == r2.push_hits(q)
+    finally:
+        ix.close()
