@@ -35,7 +35,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")      # the reference's own code ("kind": "reference")
+PORT_BIN = os.path.join(ROOT, "oracle", "dicey_oracle")          # the plain C++ restatement ("kind": "port")
+
+
+def cpu_binary():
+    """(path, kind) of the CPU comparator: the reference compiled from its own sources when it was
+    built (oracle/_ref), otherwise the oracle port; (None, None) if neither exists."""
+    if os.path.exists(REF_BIN):
+        return REF_BIN, "reference"
+    if os.path.exists(PORT_BIN):
+        return PORT_BIN, "port"
+    return None, None
 SEED = 42
 
 
@@ -128,7 +139,7 @@ def write_sample(path: str, primers: np.ndarray):
 
 
 def run_ref(fm9: str, rec: str, qfile: str, args, threads: int, counters: bool, records: str | None = None) -> dict:
-    cmd = [REF_BIN, "hunt", fm9, rec, qfile, "-d", str(args.distance), "--threads", str(threads)]
+    cmd = [cpu_binary()[0], "hunt", fm9, rec, qfile, "-d", str(args.distance), "--threads", str(threads)]
     if records:
         cmd += ["--records", records]
     if args.hamming:
@@ -199,8 +210,9 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    if not os.path.exists(REF_BIN):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dicey_ref has not been built"}))
+    ref_bin, ref_kind = cpu_binary()
+    if ref_bin is None:
+        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/dicey_ref nor oracle/dicey_oracle has been built"}))
         return 0
     cores = os.cpu_count() or 1
     ix, _ = build_index(args, int(os.environ.get("LOCAL_RANK", "0")))
@@ -230,7 +242,7 @@ def main_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop_s / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args), "threads": cores},
-        "cpu_baseline": {"value": value, "unit": "primers/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "primers/s", "cores": cores, "kind": ref_kind, "sample": sample_desc},
         "e2e": {"value": value, "unit": "primers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -378,21 +390,21 @@ def main_b200(args):
     cpu = None
     work = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(REF_BIN):
+    if rank == 0 and world == 1 and not args.no_cpu and cpu_binary()[0]:
         try:
             fm9, rec, write_s = ensure_fm9(ix, args)
             cores = os.cpu_count() or 1
             r, n, ref_records = cpu_leg(fm9, rec, primers, args, cores, args.cpu_seconds)
             parity = parity_check(ix, params, primers, n, ref_records)
-            cpu = {"value": r["queries_per_s"], "unit": "primers/s", "cores": cores, "kind": "reference",
+            cpu = {"value": r["queries_per_s"], "unit": "primers/s", "cores": cores, "kind": cpu_binary()[1],
                    "sample": f"first {n} primers of the batch on the same 3 Gb index ({r['loop_s']:.1f} s loop, index load excluded)"}
-            work = {k: r[k] / r["queries"] for k in ("R", "L", "H", "X", "strings", "steps")}
+            work = {k: r[k] / r["queries"] for k in ("R", "L", "H", "X", "strings", "steps")} if "R" in r else None
             try:
                 os.remove(fm9); os.remove(fm9 + "_check")
             except OSError:
                 pass
         except Exception as e:  # the bench line must still be printed
-            cpu = {"value": None, "unit": "primers/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+            cpu = {"value": None, "unit": "primers/s", "cores": os.cpu_count(), "kind": cpu_binary()[1], "sample": f"failed: {e}"}
     if work is None:
         # SURVEY.md 8(d) expectation for 20-mers at edit distance 1 on 3 Gb (used only when the
         # reference could not be run, e.g. under torchrun N > 1; the N = 1 run measures it)

@@ -1406,14 +1406,15 @@ static int run_impl(dg_batch* b) {
     ABuf<unsigned long long> nscripts;
     ctr.alloc(2, st);
     nscripts.alloc(1, st);
-    static int nsm = 0, general_per_sm = 0;   // (every device of the box is the same part)
-    if (!nsm) {
-      int v1 = 148, v2 = 1;
-      cudaDeviceGetAttribute(&v1, cudaDevAttrMultiProcessorCount, ix->device);
-      DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v2, k_search, 256, 0));
-      general_per_sm = std::max(v2, 1);
-      nsm = v1;
-    }
+    struct Geometry { int nsm, general_per_sm; };
+    static const Geometry geo = [&] {   // (every device of the box is the same part; magic statics are thread-safe)
+      Geometry g{148, 1};
+      cudaDeviceGetAttribute(&g.nsm, cudaDevAttrMultiProcessorCount, ix->device);
+      int v2 = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v2, k_search, 256, 0) == cudaSuccess) g.general_per_sm = std::max(v2, 1);
+      return g;
+    }();
+    const int nsm = geo.nsm, general_per_sm = geo.general_per_sm;
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {

@@ -36,6 +36,8 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
+#include <chrono>
 #include <vector>
 
 namespace orc {
@@ -449,6 +451,7 @@ struct Args {
   uint32_t d = 1, x = 10000, k = 15;
   size_t m = 1000; bool mset = false, hamming = false, forward = false;
   std::string records;
+  unsigned threads = 1;
 };
 
 }  // namespace orc
@@ -468,6 +471,8 @@ int main(int argc, char** argv) {
     else if (s == "-n") a.hamming = true;
     else if (s == "-f") a.forward = true;
     else if (s == "--records") a.records = val();
+    else if (s == "--threads") a.threads = (unsigned)atoi(val());
+    else if (s == "--counters") { /* accepted for command-line compatibility with dicey_ref; the port counts no work */ }
     else a.pos.push_back(s);
   }
   if (cmd == "neighbors") {
@@ -542,17 +547,38 @@ int main(int argc, char** argv) {
   if (cmd == "hunt") {
     Params p;
     p.indel = !a.hamming; p.reverse = !a.forward; p.distance = a.d; p.maxnbr = a.x; p.maxloc = a.mset ? a.m : 1000;
-    std::ofstream os(a.records.c_str());
-    for (size_t i = 0; i < ql.size(); ++i) {
-      std::string name, seq;
-      split_query(ql[i], name, seq);
-      QRes r;
-      run_hunt(fm, seqlen, seq, p, r);
-      os << "Q\t" << i << '\t' << r.seq << '\t' << r.distance << '\t' << r.msg.size() << '\t' << r.push.size() << '\n';
-      for (auto& m : r.msg) os << "M\t" << m << '\n';
-      for (auto& h : r.push) os << "P\t" << h.score << '\t' << h.chr << '\t' << h.start << '\t' << h.strand << '\t' << h.ra << '\t' << h.qa << '\n';
-      for (auto& h : r.sorted) os << "S\t" << h.score << '\t' << h.chr << '\t' << h.start << '\t' << h.strand << '\t' << h.ra << '\t' << h.qa << '\n';
+    // queries are independent: P threads take them in an interleaved fashion (bench.py's CPU baseline
+    // when oracle/_ref/dicey_ref is not available); the timing line mirrors dicey_ref's
+    std::vector<QRes> res(ql.size());
+    unsigned P = a.threads ? a.threads : 1;
+    auto t0 = std::chrono::steady_clock::now();
+    {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < P; ++t)
+        th.emplace_back([&, t] {
+          for (size_t i = t; i < ql.size(); i += P) {
+            std::string name, seq;
+            split_query(ql[i], name, seq);
+            run_hunt(fm, seqlen, seq, p, res[i]);
+          }
+        });
+      for (auto& t : th) t.join();
     }
+    double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t nhits = 0;
+    for (auto& r : res) nhits += r.push.size();
+    if (!a.records.empty()) {
+      std::ofstream os(a.records.c_str());
+      for (size_t i = 0; i < ql.size(); ++i) {
+        const QRes& r = res[i];
+        os << "Q\t" << i << '\t' << r.seq << '\t' << r.distance << '\t' << r.msg.size() << '\t' << r.push.size() << '\n';
+        for (auto& m : r.msg) os << "M\t" << m << '\n';
+        for (auto& h : r.push) os << "P\t" << h.score << '\t' << h.chr << '\t' << h.start << '\t' << h.strand << '\t' << h.ra << '\t' << h.qa << '\n';
+        for (auto& h : r.sorted) os << "S\t" << h.score << '\t' << h.chr << '\t' << h.start << '\t' << h.strand << '\t' << h.ra << '\t' << h.qa << '\n';
+      }
+    }
+    std::cout << "{\"queries\": " << ql.size() << ", \"threads\": " << P << ", \"loop_s\": " << loop_s << ", \"queries_per_s\": "
+              << (loop_s > 0 ? ql.size() / loop_s : 0.0) << ", \"hits\": " << nhits << ", \"n\": " << fm.size() << "}" << std::endl;
     return 0;
   }
   if (cmd == "seed") {  // silica.h:449-573 without the thal gate
