@@ -1,0 +1,306 @@
+// dg_thal.cuh -- the melting-temperature gate of `dicey search` (reference src/silica.h:508-519):
+// primer3's nearest-neighbour thermodynamic alignment of a primer against a genomic site, duplex
+// mode thal_end1, temperature only (reference src/thal.h: thal() :2408-2655 with initMatrix :821-835,
+// LSH :854-960, RSH :963-1076, Ss/Hs :1078-1122, maxTM :1123-1161, calc_bulge_internal :1200-1334,
+// fillMatrix :1504-1551, traceback :2134-2179, the Tm line of drawDimer :2196-2204).
+//
+// SURVEY.md 8(f) rank 1.  Restated as one inline function over plain arrays so that the same source
+// runs per thread on the GPU (dg_thal.cu) and on the host (tests/hostsim); results are compared
+// bit for bit with the reference's own thal() through oracle/_ref/dicey_ref.  Exactness rests on
+// evaluating every sum, product and quotient in the reference's order in IEEE double without
+// fused multiply-add (the device translation unit is built with -fmad=false); the only
+// transcendental terms (salt correction, R ln(c)) depend on the run's conditions alone and are
+// computed once on the host.
+#pragma once
+#include <stdint.h>
+
+#include "dg_core.cuh"
+
+namespace dg {
+
+constexpr double kThalInf = 999999.0;            // _INFINITY
+constexpr double kThalMinEntropyCutoff = -2500.0;
+constexpr double kThalMinEntropy = -3224.0;
+constexpr double kThalTempK = 310.15;            // TEMP_KELVIN
+constexpr double kThalAbsZero = 273.15;
+constexpr double kThalInitH = 200.0, kThalInitS = -5.7;   // duplex initiation
+constexpr double kThalIlas = (-300 / 310.15);    // internal-loop asymmetry (entropy); the enthalpy term is 0
+constexpr int kThalMaxLen = 60;                  // THAL_MAX_ALIGN: the shorter sequence; both sides are capped for the DP tables
+constexpr int kThalMaxLoop = 30;
+
+// Nearest-neighbour tables exactly as the reference holds them after get_thermodynamic_values()
+// (5 x 5 x ... over A C G T N), plus the two condition-dependent constants.
+struct ThalParams {
+  double stackS[625], stackH[625];
+  double int2S[625], int2H[625];
+  double dangS3[125], dangH3[125], dangS5[125], dangH5[125];
+  double intlS[30], bulgeS[30], intlH[30], bulgeH[30];
+  double tstackS[625], tstackH[625];
+  double tstack2S[625], tstack2H[625];
+  double atpS[25], atpH[25];
+  double salt;        // saltCorrectS(mv, dv, dntp)
+  double rc[2];       // R ln(c / 1e9) for two self-complementary oligos, R ln(c / 4e9) otherwise
+};
+
+DG_HD bool thal_fin(double x) { return x < kThalInf / 2; }
+DG_HD int thal_i4(int a, int b, int c, int d) { return ((a * 5 + b) * 5 + c) * 5 + d; }
+DG_HD int thal_i3(int a, int b, int c) { return (a * 5 + b) * 5 + c; }
+DG_HD int thal_bp(int a, int b) { return (a < 4 && b < 4 && a + b == 3) ? 1 : 0; }   // A-T, C-G
+DG_HD int thal_code(uint8_t c) {
+  if (c >= 'a' && c <= 'z') c -= 32;
+  return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+}
+
+struct ThalWork {
+  const ThalParams* p;
+  const uint8_t* n1;   // 0 .. len1 + 1, sentinels 4
+  const uint8_t* n2;   // the second sequence reversed, same framing
+  int len1, len2;
+  double* ds;          // entropy DP table, len1 x len2
+  double* dh;          // enthalpy DP table
+  double rc;
+  long stride;         // distance between consecutive table cells (1 on the host; on the device the
+                       // tables of the threads of a launch are interleaved so that a warp working on
+                       // the same cell touches consecutive addresses)
+  DG_HD double& S(int i, int j) const { return ds[(long)((j) + (i - 1) * len2 - 1) * stride]; }
+  DG_HD double& H(int i, int j) const { return dh[(long)((j) + (i - 1) * len2 - 1) * stride]; }
+};
+
+// The terminal stack / dangling-end term on one side of the pair (x .. z): LSH looks left
+// (x = n2[j], y = n2[j-1], z = n1[i], w = n1[i-1]), RSH right (x = n1[i], y = n1[i+1], z = n2[j],
+// w = n2[j+1]); both pick, among terminal mismatch and dangling ends, the variant with the highest
+// melting temperature.  as / ah: AT penalty of the pair.  Returns through (os, oh).
+DG_HD void thal_end_term(const ThalWork& w, int x, int y, int z, int ww, double as, double ah, bool open, double& os, double& oh) {
+  const ThalParams& p = *w.p;
+  double S1, H1, T1, G1, S2, H2, T2, G2;
+  T1 = -kThalInf;
+  S1 = as + p.tstack2S[thal_i4(x, y, z, ww)];
+  H1 = ah + p.tstack2H[thal_i4(x, y, z, ww)];
+  G1 = H1 - kThalTempK * S1;
+  if (!thal_fin(H1) || G1 > 0) { H1 = kThalInf; S1 = -1.0; G1 = 1.0; }
+  const double d3h = p.dangH3[thal_i3(x, y, z)], d5h = p.dangH5[thal_i3(x, z, ww)];
+  int variant = 0;
+  if (open && thal_fin(d3h) && thal_fin(d5h)) variant = 3;
+  else if (open && thal_fin(d3h)) variant = 1;
+  else if (open && thal_fin(d5h)) variant = 2;
+  if (variant) {
+    if (variant == 3) {
+      S2 = as + p.dangS3[thal_i3(x, y, z)] + p.dangS5[thal_i3(x, z, ww)];
+      H2 = ah + d3h + d5h;
+    } else if (variant == 1) {
+      S2 = as + p.dangS3[thal_i3(x, y, z)];
+      H2 = ah + d3h;
+    } else {
+      S2 = as + p.dangS5[thal_i3(x, z, ww)];
+      H2 = ah + d5h;
+    }
+    G2 = H2 - kThalTempK * S2;
+    if (!thal_fin(H2) || G2 > 0) { H2 = kThalInf; S2 = -1.0; G2 = 1.0; }
+    T2 = (H2 + kThalInitH) / (S2 + kThalInitS + w.rc);
+    if (thal_fin(H1) && G1 < 0) {
+      T1 = (H1 + kThalInitH) / (S1 + kThalInitS + w.rc);
+      if (T1 < T2 && G2 < 0) { S1 = S2; H1 = H2; T1 = T2; }
+    } else if (G2 < 0) {
+      S1 = S2; H1 = H2; T1 = T2;
+    }
+  }
+  S2 = as;
+  H2 = ah;
+  T2 = (H2 + kThalInitH) / (S2 + kThalInitS + w.rc);
+  if (thal_fin(H1) && !(T1 < T2)) { os = S1; oh = H1; }
+  else { os = S2; oh = H2; }
+}
+
+// RSH(i, j): (-1, inf) when the bases do not pair.
+DG_HD void thal_right(const ThalWork& w, int i, int j, double& os, double& oh) {
+  const int a = w.n1[i], b = w.n2[j];
+  if (!thal_bp(a, b)) { os = -1.0; oh = kThalInf; return; }
+  const int a2 = w.n1[i + 1], b2 = w.n2[j + 1];
+  thal_end_term(w, a, a2, b, b2, w.p->atpS[a * 5 + b], w.p->atpH[a * 5 + b], thal_bp(a2, b2) == 0, os, oh);
+}
+// LSH(i, j): a non-pair resets the cell and leaves (os, oh) as the caller set them.
+DG_HD void thal_left(const ThalWork& w, int i, int j, double& os, double& oh) {
+  const int a = w.n1[i], b = w.n2[j];
+  if (!thal_bp(a, b)) { w.S(i, j) = -1.0; w.H(i, j) = kThalInf; return; }
+  const int a2 = w.n1[i - 1], b2 = w.n2[j - 1];
+  thal_end_term(w, b, b2, a, a2, w.p->atpS[a * 5 + b], w.p->atpH[a * 5 + b], thal_bp(a2, b2) != 1, os, oh);
+}
+
+// calc_bulge_internal(i, j, ii, jj): the loop closed by (i, j) on the left and (ii, jj) on the right.
+DG_HD void thal_loop(const ThalWork& w, int i, int j, int ii, int jj, bool traceback, double& os, double& oh) {
+  const ThalParams& p = *w.p;
+  const uint8_t *n1 = w.n1, *n2 = w.n2;
+  const int l1 = ii - i - 1, l2 = jj - j - 1, ls = l1 + l2 - 1;
+  double S = -1.0, H = kThalInf;
+  if ((l1 == 0 && l2 > 0) || (l2 == 0 && l1 > 0)) {
+    if (l2 == 1 || l1 == 1) {      // a bulge of one base keeps the stack across it
+      H = p.bulgeH[ls] + p.stackH[thal_i4(n1[i], n1[ii], n2[j], n2[jj])];
+      S = p.bulgeS[ls] + p.stackS[thal_i4(n1[i], n1[ii], n2[j], n2[jj])];
+      if (H > 0 || S > 0) { H = kThalInf; S = -1.0; }
+      H += w.H(i, j);
+      S += w.S(i, j);
+      if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+    } else {
+      H = p.bulgeH[ls] + p.atpH[n1[i] * 5 + n2[j]] + p.atpH[n1[ii] * 5 + n2[jj]];
+      H += w.H(i, j);
+      S = p.bulgeS[ls] + p.atpS[n1[i] * 5 + n2[j]] + p.atpS[n1[ii] * 5 + n2[jj]];
+      S += w.S(i, j);
+      if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+      if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
+    }
+  } else if (l1 == 1 && l2 == 1) {
+    S = p.int2S[thal_i4(n1[i], n1[i + 1], n2[j], n2[j + 1])] + p.int2S[thal_i4(n2[jj], n2[jj - 1], n1[ii], n1[ii - 1])];
+    S += w.S(i, j);
+    H = p.int2H[thal_i4(n1[i], n1[i + 1], n2[j], n2[j + 1])] + p.int2H[thal_i4(n2[jj], n2[jj - 1], n1[ii], n1[ii - 1])];
+    H += w.H(i, j);
+    if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+    if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
+  } else {
+    const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+    H = p.intlH[ls] + p.tstackH[thal_i4(n1[i], n1[i + 1], n2[j], n2[j + 1])] +
+        p.tstackH[thal_i4(n2[jj], n2[jj - 1], n1[ii], n1[ii - 1])] + (0.0 * asym);
+    H += w.H(i, j);
+    S = p.intlS[ls] + p.tstackS[thal_i4(n1[i], n1[i + 1], n2[j], n2[j + 1])] +
+        p.tstackS[thal_i4(n2[jj], n2[jj - 1], n1[ii], n1[ii - 1])] + (kThalIlas * asym);
+    S += w.S(i, j);
+    if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+    if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
+  }
+  double rs, rh;
+  thal_right(w, ii, jj, rs, rh);
+  const double G1 = H + rh - kThalTempK * (S + rs);
+  const double G2 = w.H(ii, jj) + rh - kThalTempK * (w.S(ii, jj) + rs);
+  if (G1 < G2 || traceback) { os = S; oh = H; }
+}
+
+// maxTM(i, j): keep the cell, or extend the stack from (i-1, j-1), whichever melts higher.
+DG_HD void thal_stack(const ThalWork& w, int i, int j) {
+  const ThalParams& p = *w.p;
+  double S0 = w.S(i, j), H0 = w.H(i, j), S1, H1, T1;
+  double rs, rh;
+  thal_right(w, i, j, rs, rh);
+  const double T0 = (H0 + kThalInitH + rh) / (S0 + kThalInitS + rs + w.rc);
+  const int k = thal_i4(w.n1[i - 1], w.n1[i], w.n2[j - 1], w.n2[j]);
+  if (thal_fin(w.H(i - 1, j - 1)) && thal_fin(p.stackH[k])) {
+    S1 = (w.S(i - 1, j - 1) + p.stackS[k]);
+    H1 = (w.H(i - 1, j - 1) + p.stackH[k]);
+    T1 = (H1 + kThalInitH + rh) / (S1 + kThalInitS + rs + w.rc);
+  } else {
+    S1 = -1.0;
+    H1 = kThalInf;
+    T1 = (H1 + kThalInitH) / (S1 + kThalInitS + w.rc);
+  }
+  if (S1 < kThalMinEntropyCutoff) { S1 = kThalMinEntropy; H1 = 0.0; }
+  if (S0 < kThalMinEntropyCutoff) { S0 = kThalMinEntropy; H0 = 0.0; }
+  if (T1 > T0) { w.S(i, j) = S1; w.H(i, j) = H1; }
+  else if (T0 >= T1) { w.S(i, j) = S0; w.H(i, j) = H0; }
+}
+
+DG_HD bool thal_symmetric(const uint8_t* s, int len) {   // symmetry_thermo
+  if (len % 2 == 1) return false;
+  for (int i = 0; i < len / 2; ++i) {
+    const int a = thal_code(s[i]), b = thal_code(s[len - 1 - i]);
+    if ((a < 4 || b < 4) && a + b != 3) return false;   // any A/C/G/T on either side must face its complement
+  }
+  return true;
+}
+
+// thal(oligo1, oligo2, thal_end1, temponly): returns false where the reference returns false
+// (a sequence longer than the DP tables); *tm is o->temp.  num1 / num2: len + 2 bytes each,
+// ds / dh: len1 * len2 cells each, `stride` doubles apart.
+DG_HD bool thal_end1_tm(const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
+                        uint8_t* num2, double* ds, double* dh, double* tm, long stride = 1) {
+  *tm = -kThalInf;   // THAL_ERROR_SCORE
+  if (len1 <= 0 || len2 <= 0) { *tm = 0.0; return false; }
+  if (len1 > kThalMaxLen || len2 > kThalMaxLen) return false;
+  ThalWork w;
+  w.p = p; w.n1 = num1; w.n2 = num2; w.len1 = len1; w.len2 = len2; w.ds = ds; w.dh = dh; w.stride = stride;
+  w.rc = (thal_symmetric(o1, len1) && thal_symmetric(o2, len2)) ? p->rc[0] : p->rc[1];
+  for (int i = 1; i <= len1; ++i) num1[i] = (uint8_t)thal_code(o1[i - 1]);
+  for (int j = 1; j <= len2; ++j) num2[j] = (uint8_t)thal_code(o2[len2 - j]);   // 3' -> 5'
+  num1[0] = num1[len1 + 1] = num2[0] = num2[len2 + 1] = 4;
+  // initMatrix
+  for (int i = 1; i <= len1; ++i)
+    for (int j = 1; j <= len2; ++j) {
+      const bool pair = thal_bp(num1[i], num2[j]) != 0;
+      w.H(i, j) = pair ? 0.0 : kThalInf;
+      w.S(i, j) = pair ? kThalMinEntropy : -1.0;
+    }
+  // fillMatrix
+  for (int i = 1; i <= len1; ++i)
+    for (int j = 1; j <= len2; ++j) {
+      if (!thal_fin(w.H(i, j))) continue;
+      double s = -1.0, h = kThalInf;
+      thal_left(w, i, j, s, h);
+      if (thal_fin(h)) { w.S(i, j) = s; w.H(i, j) = h; }
+      if (i > 1 && j > 1) {
+        thal_stack(w, i, j);
+        for (int d = 3; d <= kThalMaxLoop + 2; ++d) {
+          int ii = i - 1;
+          int jj = -ii - d + (j + i);
+          if (jj < 1) { ii -= (1 - jj); jj = 1; }
+          for (; ii > 0 && jj < j; --ii, ++jj) {
+            if (!thal_fin(w.H(ii, jj))) continue;
+            s = -1.0; h = kThalInf;
+            thal_loop(w, ii, jj, i, j, false, s, h);
+            if (s < kThalMinEntropyCutoff) { s = kThalMinEntropy; h = 0.0; }
+            if (thal_fin(h)) { w.H(i, j) = h; w.S(i, j) = s; }
+          }
+        }
+      }
+    }
+  // the most stable structure ending at the 3' end of the first sequence (thal_end1)
+  int bestI = len1, bestJ = 0;
+  double bestG = kThalInf;
+  for (int j = 1; j <= len2; ++j) {
+    double s, h;
+    thal_right(w, len1, j, s, h);
+    s = s + 0.000001;
+    h = h + 0.000001;
+    const double G1 = (w.H(len1, j) + h + kThalInitH) - kThalTempK * (w.S(len1, j) + s + kThalInitS);
+    if (G1 < bestG) { bestG = G1; bestJ = j; }
+  }
+  if (!thal_fin(bestG)) bestI = bestJ = 1;
+  double rs, rh;
+  thal_right(w, bestI, bestJ, rs, rh);
+  const double dH = w.H(bestI, bestJ) + rh + kThalInitH;
+  const double dS = (w.S(bestI, bestJ) + rs + kThalInitS);
+  if (!thal_fin(w.H(bestI, bestJ))) { *tm = 0.0; return true; }
+  // traceback: only the number of paired bases enters the temperature
+  int paired = 2, i = bestI, j = bestJ;   // ps1[i-1] and ps2[j-1]
+  for (int guard = 0; guard < 4 * (len1 + len2); ++guard) {
+    double s = -1.0, h = kThalInf;
+    thal_left(w, i, j, s, h);
+    if (w.S(i, j) == s && w.H(i, j) == h) break;
+    bool done = false;
+    if (i > 1 && j > 1) {
+      const int k = thal_i4(num1[i - 1], num1[i], num2[j - 1], num2[j]);
+      if (w.S(i, j) == p->stackS[k] + w.S(i - 1, j - 1) && w.H(i, j) == p->stackH[k] + w.H(i - 1, j - 1)) {
+        --i; --j;
+        paired += 2;
+        done = true;
+      }
+    }
+    for (int d = 3; !done && d <= kThalMaxLoop + 2; ++d) {
+      int ii = i - 1;
+      int jj = -ii - d + (j + i);
+      if (jj < 1) { ii -= (1 - jj); jj = 1; }
+      for (; !done && ii > 0 && jj < j; --ii, ++jj) {
+        s = -1.0; h = kThalInf;
+        thal_loop(w, ii, jj, i, j, true, s, h);
+        if (w.S(i, j) == s && w.H(i, j) == h) {
+          i = ii; j = jj;
+          paired += 2;
+          done = true;
+          break;
+        }
+      }
+    }
+    if (!done) break;   // (the reference would spin here; never observed)
+  }
+  const int N = (paired / 2) - 1;
+  *tm = ((dH) / (dS + (N * p->salt) + w.rc)) - kThalAbsZero;
+  return true;
+}
+
+}  // namespace dg

@@ -41,6 +41,7 @@
 #include "neighbors.h"  // verbatim reference (src/neighbors.h)
 #include "needle.h"     // verbatim reference (src/needle.h, src/align.h)
 #include "version.h"    // verbatim reference (src/version.h)
+#include "thal.h"       // verbatim reference (src/thal.h: primer3 thal, the Tm gate of silica.h:508-519)
 
 using namespace sdsl;
 
@@ -787,6 +788,76 @@ static int cmd_padcount(Args const& a) {
   return 0;
 }
 
+// thal <primer3_config_dir/> <pairs.tsv> [params_out.tsv]: the Tm gate of `dicey search`
+// (silica.h:316-329, 508-512): thal_end1, dicey's default conditions (37 C, 50 mM monovalent,
+// 1.5 mM divalent, 0.6 mM dNTP, 50 nM oligo).  One line per pair: success flag, Tm as %.17g and as
+// the raw 64-bit pattern.  With a third argument the thermodynamic tables the reference loaded
+// from its parameter files are dumped (bit patterns), for tests that cannot read /root/reference.
+static void dump_table(std::ostream& os, const char* name, const double* p, size_t n) {
+  os << name << '\t' << n;
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t u;
+    memcpy(&u, p + i, 8);
+    os << '\t' << std::hex << u << std::dec;
+  }
+  os << '\n';
+}
+static int cmd_thal(Args const& a) {
+  if (a.pos.size() < 2) return usage();
+  std::string cfg = a.pos[0];
+  if (cfg.empty() || cfg.back() != '/') cfg += '/';
+  primer3thal::thal_args ta;
+  primer3thal::set_thal_default_args(&ta);
+  ta.temponly = 1;
+  ta.type = primer3thal::thal_end1;
+  primer3thal::get_thermodynamic_values(cfg.c_str());
+  ta.temp = 37.0; ta.mv = 50.0; ta.dv = 1.5; ta.dna_conc = 50.0; ta.dntp = 0.6;   // silica.h:242-246
+  ta.temp += primer3thal::ABSOLUTE_ZERO;
+  std::vector<std::string> lines;
+  if (!read_lines(a.pos[1], lines)) return 1;
+  for (auto const& line : lines) {
+    size_t t = line.find('\t');
+    if (t == std::string::npos) continue;
+    std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+    primer3thal::thal_results o;
+    bool ok = primer3thal::thal((const unsigned char*)o1.c_str(), (const unsigned char*)o2.c_str(), &ta, &o);
+    uint64_t u;
+    double tm = o.temp;
+    memcpy(&u, &tm, 8);
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.17g", tm);
+    std::cout << (ok ? 1 : 0) << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
+  }
+  if (a.pos.size() >= 3) {
+    using namespace primer3thal;
+    std::ofstream os(a.pos[2].c_str());
+    dump_table(os, "stackEntropies", &stackEntropies[0][0][0][0], 625);
+    dump_table(os, "stackEnthalpies", &stackEnthalpies[0][0][0][0], 625);
+    dump_table(os, "stackint2Entropies", &stackint2Entropies[0][0][0][0], 625);
+    dump_table(os, "stackint2Enthalpies", &stackint2Enthalpies[0][0][0][0], 625);
+    dump_table(os, "dangleEntropies3", &dangleEntropies3[0][0][0], 125);
+    dump_table(os, "dangleEnthalpies3", &dangleEnthalpies3[0][0][0], 125);
+    dump_table(os, "dangleEntropies5", &dangleEntropies5[0][0][0], 125);
+    dump_table(os, "dangleEnthalpies5", &dangleEnthalpies5[0][0][0], 125);
+    dump_table(os, "interiorLoopEntropies", interiorLoopEntropies, 30);
+    dump_table(os, "bulgeLoopEntropies", bulgeLoopEntropies, 30);
+    dump_table(os, "interiorLoopEnthalpies", interiorLoopEnthalpies, 30);
+    dump_table(os, "bulgeLoopEnthalpies", bulgeLoopEnthalpies, 30);
+    dump_table(os, "tstackEntropies", &tstackEntropies[0][0][0][0], 625);
+    dump_table(os, "tstackEnthalpies", &tstackEnthalpies[0][0][0][0], 625);
+    dump_table(os, "tstack2Entropies", &tstack2Entropies[0][0][0][0], 625);
+    dump_table(os, "tstack2Enthalpies", &tstack2Enthalpies[0][0][0][0], 625);
+    dump_table(os, "atpS", &atpS[0][0], 25);
+    dump_table(os, "atpH", &atpH[0][0], 25);
+    double sc = saltCorrectS(ta.mv, ta.dv, ta.dntp);
+    double rc[2] = {R * log(ta.dna_conc / 1000000000.0), R * log(ta.dna_conc / 4000000000.0)};
+    dump_table(os, "saltCorrection", &sc, 1);
+    dump_table(os, "RC_symmetric_asymmetric", rc, 2);
+  }
+  primer3thal::destroy_thal_structures();
+  return 0;
+}
+
 static int cmd_dump(Args const& a) {
   if (a.pos.size() < 1) return usage();
   TIndex fm;
@@ -825,5 +896,6 @@ int main(int argc, char** argv) {
   if (cmd == "extract") return cmd_extract(a);
   if (cmd == "padcount") return cmd_padcount(a);
   if (cmd == "dump") return cmd_dump(a);
+  if (cmd == "thal") return cmd_thal(a);
   return usage();
 }

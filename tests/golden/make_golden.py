@@ -203,6 +203,53 @@ def main():
     pfn = os.path.join(HERE, "needle.pairs.tsv")
     open(pfn, "w").write("".join(f"{g}\t{q}\n" for g, q in pairs))
     open(os.path.join(HERE, "needle.out.tsv"), "w").write(run(["needle", pfn, "-"]))
+    make_thal()
+
+
+def make_thal():
+    """The Tm gate of `dicey search` (primer3 thal, thal_end1): pairs (primer, genomic site as
+    silica.h:508-511 passes them), the reference's results as 64-bit patterns, and the nearest-neighbour
+    tables the reference held after reading its primer3_config directory (the GPU box has no
+    /root/reference to read them from)."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    pairs = []
+    for i in range(700):
+        L = int(rng.integers(15, 31))
+        primer = bytes(acgt[rng.integers(0, 4, L)])
+        site = bytearray(primer.translate(comp)[::-1])
+        kind = i % 7
+        if kind in (1, 2, 3):
+            for _ in range(kind):
+                p = int(rng.integers(0, len(site)))
+                site[p] = acgt[rng.integers(0, 4)]
+        elif kind == 4:
+            p = int(rng.integers(1, len(site) - 1))
+            del site[p]
+        elif kind == 5:
+            p = int(rng.integers(1, len(site) - 1))
+            site.insert(p, int(acgt[rng.integers(0, 4)]))
+        elif kind == 6:
+            site = bytearray(acgt[rng.integers(0, 4, int(rng.integers(15, 34)))])
+        fl, fr = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        site = bytes(acgt[rng.integers(0, 4, fl)]) + bytes(site) + bytes(acgt[rng.integers(0, 4, fr)])
+        if i % 53 == 0:
+            site = site[:3] + b"N" + site[4:]
+        if i % 97 == 0:
+            primer = primer.lower()
+        pairs.append((primer, site))
+    pairs += [(b"ACGTACGTACGTACGTACGT", b"ACGTACGTACGTACGTACGT"), (b"GAATTCGAATTC", b"GAATTCGAATTC"),
+              (b"GGGGGGGGGGCCCCCCCCCC", b"GGGGGGGGGGCCCCCCCCCC"), (b"AAAAAAAAAAAAAAAAAAAA", b"TTTTTTTTTTTTTTTTTTTT"),
+              (b"AAAAAAAAAAAAAAAAAAAA", b"CCCCCCCCCCCCCCCCCCCC"), (b"ACG", b"CGT"), (b"A", b"T"),
+              (b"GCGCGCGCGCGCGCGCGCGC", b"GCGCGCGCGCGCGCGCGCGC"), (b"ATATATATATATATATATAT", b"ATATATATATATATATATAT")]
+    pfn = os.path.join(HERE, "thal.pairs.tsv")
+    with open(pfn, "wb") as f:
+        for a, b in pairs:
+            f.write(a + b"\t" + b + b"\n")
+    out = run(["thal", "/root/reference/src/primer3_config/", pfn, os.path.join(HERE, "thal.params.tsv")])
+    open(os.path.join(HERE, "thal.out.tsv"), "w").write(out)
 
 
 if __name__ == "__main__":

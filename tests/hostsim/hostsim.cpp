@@ -12,6 +12,8 @@
 #include "../../dicey_b200/csrc/dg_core.cuh"
 #include "../../dicey_b200/csrc/fm9.hpp"
 #include "../../dicey_b200/csrc/fm9_select.hpp"
+#include "../../dicey_b200/csrc/dg_thal.cuh"
+#include "../../dicey_b200/csrc/thal_params.hpp"
 
 using namespace dg;
 
@@ -141,6 +143,46 @@ int main(int argc, char** argv) {
     }
     fprintf(stderr, "banded needle checked on %d (pair, dmax) cases\n", banded_checked);
     return banded_checked >= 100 ? 0 : 4;
+  }
+  if (cmd == "thal" && argc >= 4) {
+    // dg_thal.cuh on the host: <params.tsv> <pairs.tsv> -> the lines `dicey_ref thal` prints
+    ThalParams tp;
+    std::string err;
+    if (!thal_params_from_dump(argv[2], tp, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    std::ifstream f(argv[3]);
+    std::string line;
+    while (std::getline(f, line)) {
+      size_t t = line.find('\t');
+      if (t == std::string::npos) continue;
+      std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2);
+      std::vector<double> ds(o1.size() * o2.size() + 1), dh(o1.size() * o2.size() + 1);
+      double tm = 0;
+      bool ok = thal_end1_tm(&tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(), n1.data(),
+                             n2.data(), ds.data(), dh.data(), &tm);
+      uint64_t u;
+      memcpy(&u, &tm, 8);
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%.17g", tm);
+      std::cout << (ok ? 1 : 0) << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
+    }
+    return 0;
+  }
+  if (cmd == "thalcfg" && argc >= 4) {
+    // the primer3_config loader must reproduce the tables the reference holds: <config dir> <params.tsv>
+    ThalParams a, b;
+    std::string err;
+    if (!thal_params_from_config(argv[2], 50.0, 1.5, 0.6, 50.0, a, err) || !thal_params_from_dump(argv[3], b, err)) {
+      fprintf(stderr, "%s\n", err.c_str());
+      return 2;
+    }
+    if (memcmp(&a, &b, sizeof(a)) != 0) {
+      const double* x = (const double*)&a; const double* y = (const double*)&b;
+      for (size_t i = 0; i < sizeof(a) / 8; ++i) if (memcmp(x + i, y + i, 8)) { fprintf(stderr, "first difference at double %zu: %.17g vs %.17g\n", i, x[i], y[i]); break; }
+      return 3;
+    }
+    std::cout << "tables identical (" << sizeof(a) / 8 << " doubles)\n";
+    return 0;
   }
   if (cmd == "select" && argc >= 3) {
     // the select_support_mcl sections rebuilt from m_bv must equal the bytes SDSL wrote into the file

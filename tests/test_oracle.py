@@ -92,3 +92,23 @@ def test_select_supports_rebuilt_byte_for_byte(name):
     into the golden indexes: t1m takes SDSL's init_fast path, stress (< 100000 bits) init_slow."""
     out = run(HOSTSIM, ["select", name + ".fm9"])
     assert out.count("bytes identical") == 2
+
+
+def test_thal_restatement_is_bit_exact():
+    """dg_thal.cuh (the Tm gate of `dicey search`, primer3 thal in thal_end1 mode) compiled for the
+    host: 709 (primer, site) pairs -- perfect sites, 1-3 mismatches, bulges, unrelated sequence,
+    self-complementary oligos, N, lower case -- must give the 64-bit patterns the reference's own
+    thal() produced (tests/golden/thal.out.tsv, written by `dicey_ref thal`)."""
+    got = run(HOSTSIM, ["thal", "thal.params.tsv", "thal.pairs.tsv"])
+    want = open(os.path.join(GOLDEN, "thal.out.tsv")).read()
+    assert got == want
+    temps = [float(l.split("\t")[1]) for l in want.splitlines()]
+    assert len(temps) == 709 and sum(t > 45.0 for t in temps) > 300
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/primer3_config"), reason="needs the reference's primer3_config directory")
+def test_thal_config_loader_reproduces_the_reference_tables():
+    """thal_params_from_config (what the product reads: dicey's -i directory) against the tables the
+    reference held after get_thermodynamic_values() (the committed dump)."""
+    out = run(HOSTSIM, ["thalcfg", "/root/reference/src/primer3_config/", "thal.params.tsv"])
+    assert "tables identical" in out
