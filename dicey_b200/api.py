@@ -62,7 +62,7 @@ EXPORTS = [
     "dg_index_open", "dg_index_build_text", "dg_index_build_synthetic", "dg_index_write_fm9", "dg_index_close",
     "dg_index_size", "dg_index_set_records", "dg_index_get_info", "dg_index_stream", "dg_index_debug_copy",
     "dg_hunt_batch", "dg_batch_stage", "dg_batch_run", "dg_batch_fetch", "dg_batch_summary", "dg_batch_device_hits",
-    "dg_batch_free", "dg_index_wire_records",
+    "dg_batch_free", "dg_index_wire_records", "dg_thal_open", "dg_thal_open_tables", "dg_thal_batch", "dg_thal_close",
     "dg_count_batch", "dg_backward_search_batch", "dg_result_hits", "dg_result_query_offsets",
     "dg_result_query_status", "dg_result_query_distance", "dg_result_pool", "dg_result_sequences",
     "dg_result_free", "dg_hits_sort", "dg_result_pack", "dg_result_unpack", "dg_profile_enable",
@@ -103,6 +103,11 @@ def library() -> C.CDLL:
     lib.dg_batch_summary.argtypes = [vp, u64p, u64p]
     lib.dg_batch_device_hits.argtypes = [vp, C.POINTER(vp), u64p]
     lib.dg_index_wire_records.argtypes = [vp, C.POINTER(vp), u64p]
+    lib.dg_thal_open.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)]
+    lib.dg_thal_open_tables.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.dg_thal_batch.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]
+    lib.dg_thal_close.argtypes = [vp]
+    lib.dg_thal_close.restype = None
     lib.dg_batch_free.argtypes = [vp]
     lib.dg_batch_free.restype = None
     lib.dg_count_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(_Params), vp]
@@ -431,6 +436,43 @@ class Batch:
     def free(self) -> None:
         if self._h:
             library().dg_batch_free(self._h)
+            self._h = None
+
+
+class Thal:
+    """Batched melting temperatures (primer3 thal, thal_end1) on the GPU: the gate of silica.h:508-519."""
+
+    def __init__(self, handle: int):
+        self._h = handle
+
+    @classmethod
+    def open(cls, primer3_config_dir: str, mv: float = 50.0, dv: float = 1.5, dntp: float = 0.6, dna_conc: float = 50.0,
+             device: int = 0) -> "Thal":
+        h = C.c_void_p()
+        _check(library().dg_thal_open(os.fsencode(primer3_config_dir), mv, dv, dntp, dna_conc, device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def open_tables(cls, dump_path: str, device: int = 0) -> "Thal":
+        h = C.c_void_p()
+        _check(library().dg_thal_open_tables(os.fsencode(dump_path), device, C.byref(h)))
+        return cls(h.value)
+
+    def tm(self, oligos1, oligos2) -> tuple[np.ndarray, np.ndarray]:
+        """(Tm in Celsius as float64, ok flags) for the pairs (oligos1[i], oligos2[i])."""
+        b1, o1 = pack_sequences(oligos1)
+        b2, o2 = pack_sequences(oligos2)
+        n = len(o1) - 1
+        assert n == len(o2) - 1
+        tm = np.zeros(n, dtype=np.float64)
+        ok = np.zeros(n, dtype=np.uint8)
+        _check(library().dg_thal_batch(self._h, b1.ctypes.data, o1.ctypes.data, b2.ctypes.data, o2.ctypes.data, n, tm.ctypes.data,
+                                       ok.ctypes.data))
+        return tm, ok
+
+    def close(self) -> None:
+        if self._h:
+            library().dg_thal_close(self._h)
             self._h = None
 
 

@@ -210,6 +210,21 @@ void dg_hits_sort(dg_hit* hits, uint64_t n);
 int dg_result_pack(const dg_result* r, void* buf, uint64_t* bytes);   /* buf NULL -> size  */
 int dg_result_unpack(const void* buf, uint64_t bytes, dg_result** out);
 
+/* ---- melting temperatures (the Tm gate of `dicey search`) ---------------------------- */
+/* primer3thal::thal(oligo1, oligo2, &a, &o) with a.type = thal_end1 and a.temponly = 1 as
+ * silica.h:316-329,508-519 and padlock.h call it, for n pairs at once on the GPU, bit for bit
+ * (o.temp as a double; ok[i] = the bool thal() returns).  dg_thal_open reads the primer3_config
+ * directory a dicey installation ships (-i, silica.h:216) as get_thermodynamic_values does
+ * (thal.h:2368-2393); mv / dv / dntp in mM, dna_conc in nM (silica.h:243-246).
+ * dg_thal_open_tables reads the table dump `oracle/_ref/dicey_ref thal` writes (tests).
+ * Limits: both sequences at most 60 bases (the reference allows one side longer).            */
+typedef struct dg_thal dg_thal;
+int dg_thal_open(const char* primer3_config_dir, double mv, double dv, double dntp, double dna_conc, int device, dg_thal** out);
+int dg_thal_open_tables(const char* table_dump_path, int device, dg_thal** out);
+int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint32_t n,
+                  double* tm, uint8_t* ok);
+void dg_thal_close(dg_thal* t);
+
 /* ---- diagnostics -------------------------------------------------------------------- */
 int dg_profile_enable(dg_index* idx, int on);
 int dg_profile_get(dg_index* idx, dg_profile* out);

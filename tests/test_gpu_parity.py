@@ -286,3 +286,23 @@ def test_wire_records_in_hbm(indexes, monkeypatch, chunk):
     got = shard.unwire_records(wire)
     for f in ("query", "chr", "start", "score", "strand"):
         assert np.array_equal(got[f], res.hits[f]), f
+
+
+def test_thal_gpu_is_bit_exact():
+    """dg_thal_batch (one pair per thread, interleaved DP tables, -fmad=false) against the 64-bit
+    patterns of the reference's own thal() for the 709 golden pairs, then the same pairs many
+    times over in one batch (several launches' worth of scratch)."""
+    from dicey_b200.api import Thal
+    pairs = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLDEN, "thal.pairs.tsv"))]
+    want = [l.split("\t") for l in open(os.path.join(GOLDEN, "thal.out.tsv")).read().splitlines()]
+    th = Thal.open_tables(os.path.join(GOLDEN, "thal.params.tsv"), 0)
+    try:
+        tm, ok = th.tm([p[0] for p in pairs], [p[1] for p in pairs])
+        bits = tm.view(np.uint64)
+        for i, w in enumerate(want):
+            assert int(ok[i]) == int(w[0]) and int(bits[i]) == int(w[2], 16), (i, pairs[i], float(tm[i]), w[1])
+        reps = 150
+        tm2, ok2 = th.tm([p[0] for p in pairs] * reps, [p[1] for p in pairs] * reps)
+        assert np.array_equal(tm2.view(np.uint64).reshape(reps, -1), np.tile(bits, (reps, 1))) and ok2.all()
+    finally:
+        th.close()
