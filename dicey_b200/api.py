@@ -62,7 +62,7 @@ EXPORTS = [
     "dg_index_open", "dg_index_build_text", "dg_index_build_synthetic", "dg_index_write_fm9", "dg_index_close",
     "dg_index_size", "dg_index_set_records", "dg_index_get_info", "dg_index_stream", "dg_index_debug_copy",
     "dg_hunt_batch", "dg_batch_stage", "dg_batch_run", "dg_batch_fetch", "dg_batch_summary", "dg_batch_device_hits",
-    "dg_batch_free", "dg_index_wire_records", "dg_thal_open", "dg_thal_open_tables", "dg_thal_batch", "dg_thal_close",
+    "dg_batch_free", "dg_index_wire_records", "dg_index_fetch_text", "dg_thal_open", "dg_thal_open_tables", "dg_thal_batch", "dg_thal_close",
     "dg_count_batch", "dg_backward_search_batch", "dg_result_hits", "dg_result_query_offsets",
     "dg_result_query_status", "dg_result_query_distance", "dg_result_pool", "dg_result_sequences",
     "dg_result_free", "dg_hits_sort", "dg_result_pack", "dg_result_unpack", "dg_profile_enable",
@@ -103,6 +103,7 @@ def library() -> C.CDLL:
     lib.dg_batch_summary.argtypes = [vp, u64p, u64p]
     lib.dg_batch_device_hits.argtypes = [vp, C.POINTER(vp), u64p]
     lib.dg_index_wire_records.argtypes = [vp, C.POINTER(vp), u64p]
+    lib.dg_index_fetch_text.argtypes = [vp, vp, vp, C.c_uint32, vp]
     lib.dg_thal_open.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)]
     lib.dg_thal_open_tables.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     lib.dg_thal_batch.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]

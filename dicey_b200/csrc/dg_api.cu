@@ -82,6 +82,23 @@ int dg_index_get_info(const dg_index* idx, dg_index_info* info) {
   return DG_OK;
 }
 
+int dg_index_fetch_text(dg_index* idx, const uint64_t* pos, const uint64_t* len, uint32_t n, char* buf) {
+  if (!idx || (n && (!pos || !len || !buf))) { set_error("null argument"); return DG_ERR_ARG; }
+  try {
+    DG_CUDA(cudaSetDevice(idx->device));
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (pos[i] > idx->n || len[i] > idx->n - pos[i]) { set_error("text range out of bounds"); return DG_ERR_ARG; }
+      if (len[i]) DG_CUDA(cudaMemcpyAsync(buf + at, idx->text.p + pos[i], len[i], cudaMemcpyDeviceToHost, idx->stream));
+      at += len[i];
+    }
+    DG_CUDA(cudaStreamSynchronize(idx->stream));
+    return DG_OK;
+  } catch (CudaFail& e) {
+    return e.code;
+  }
+}
+
 void* dg_index_stream(const dg_index* idx) { return idx ? (void*)idx->stream : nullptr; }
 
 int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* bytes) {

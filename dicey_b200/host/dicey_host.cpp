@@ -10,9 +10,9 @@
 // all queries of a FASTA input are searched in ONE dg_hunt_batch call instead of one by one, and
 // queries outside the device path's limits (DESIGN.md "Limits") get an error record instead of
 // a CPU search -- there is no CPU search path in this program.
-// `search` and `padlock` need primer3's thal() Tm model on top of the FM / NW path (SURVEY.md 8f
-// rank 1) and are not part of this round; the library entry points they would call
-// (dg_hunt_batch with seed_len, dg_count_batch) exist and are tested.
+//   dicey-b200 search [OPTIONS] -g genome.fa.gz -i primer3_config/ primers.fasta             reference src/silica.h:208-660
+// `padlock` (probe design over GTF regions) is not part of this round; the library entry points it
+// would call (dg_count_batch, dg_thal_batch) exist and are tested.
 #include <algorithm>
 #include <cstdlib>
 #include <ctime>
@@ -20,6 +20,9 @@
 
 #include "../../include/dicey_b200.h"
 #include "hostutil.hpp"
+#include "jsonnum.hpp"
+#include <set>
+#include <cmath>
 
 using namespace dhost;
 
@@ -292,6 +295,489 @@ int hunter(int argc, char** argv) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// `dicey search`: in-silico PCR (reference src/silica.h:208-660).  The FM-index / NW part of every
+// primer runs as one dg_hunt_batch call in seed mode, the melting temperatures of every candidate
+// site as one dg_thal_batch call (primer3 thal on the GPU, bit-identical); the Tm gate, the
+// (refIndex, alignpos) de-duplication, amplicon pairing, penalties and the JSON are host code that
+// follows silica.h line by line.
+struct SilicaConfig {  // silica.h:38-67
+  bool indel = true, pruneprimer = false, hasOutfile = false;
+  uint32_t kmer = 15, distance = 1, maxNeighborhood = 10000, maxProdSize = 15000, maxPruneCount = 0;
+  uint64_t max_locations = 10000;
+  double cutTemp = 45.0, cutofPen = -1.0, penDiff = 0.6, penMis = 0.4, penLen = 0.001;
+  double temp = 37.0, mv = 50.0, dv = 1.5, dna_conc = 50.0, dntp = 0.6;
+  std::string outfile, infile, genome, primer3Config = "./src/primer3_config/";
+  int device = 0;
+};
+struct PrimerBind {  // silica.h:69-82
+  uint32_t refIndex, pos, primerId;
+  bool onFor;
+  double temp, perfTemp;
+  std::string genome;
+  bool operator<(const PrimerBind& b) const { return (temp > b.temp); }
+};
+struct PcrProduct {  // silica.h:84-98
+  uint32_t refIndex, leng, forPos, revPos, forId, revId;
+  double forTemp, revTemp, penalty;
+  bool operator<(const PcrProduct& b) const { return (penalty < b.penalty); }
+};
+
+std::string revcomp_upper(const std::string& in) {  // util.h:54-114 on an upper-cased sequence
+  std::string s(in.rbegin(), in.rend());
+  for (char& ch : s) {
+    switch (ch) {
+      case 'A': ch = 'T'; break; case 'C': ch = 'G'; break; case 'G': ch = 'C'; break; case 'T': ch = 'A'; break;
+      case 'U': ch = 'A'; break; case 'R': ch = 'Y'; break; case 'Y': ch = 'R'; break; case 'K': ch = 'M'; break;
+      case 'M': ch = 'K'; break; case 'B': ch = 'V'; break; case 'V': ch = 'B'; break; case 'D': ch = 'H'; break;
+      case 'H': ch = 'D'; break; case 'S': case 'W': case 'N': break;
+      default: ch = 'N';
+    }
+  }
+  return s;
+}
+
+struct JsonRaw : JsonObject {
+  void set_double(const std::string& k, double v) { set_raw(k, json_double(v)); }
+};
+
+// writeJsonPrimerOut (silica.h:100-187)
+std::string search_json(const SilicaConfig& c, uint32_t distance, const std::vector<std::string>& qn, const std::vector<PrimerBind>& allp,
+                        const std::vector<PcrProduct>& pcrColl, const std::vector<std::string>& pName,
+                        const std::vector<std::string>& pSeq, const std::vector<std::string>& msg,
+                        const std::vector<std::string>& ampSeq) {
+  std::string o = "{\"errors\": [";
+  bool errors = false;
+  for (size_t i = 0; i < msg.size(); ++i) {
+    std::string type = "warning";
+    if (msg[i].compare(0, 5, "Error") == 0) { errors = true; type = "error"; }
+    JsonObject e;
+    e.set_string("type", type);
+    e.set_string("title", msg[i]);
+    if (i) o += ',';
+    o += e.dump();
+  }
+  o += "]";
+  if (!errors) {
+    JsonObject meta;
+    meta.set_string("version", kDiceyVersion);
+    meta.set_string("subcommand", "search");
+    meta.set_uint("distance", distance);
+    meta.set_string("genome", c.genome);
+    meta.set_string("outfile", c.outfile);
+    meta.set_uint("maxmatches", c.max_locations);
+    meta.set_bool("hamming", !c.indel);
+    o += ",\"meta\":" + meta.dump() + ",\"data\":{\"primers\":[";
+    for (size_t i = 0; i < allp.size(); ++i) {
+      if (i) o += ',';
+      JsonRaw j;
+      j.set_string("Chrom", qn[allp[i].refIndex]);
+      j.set_uint("Id", i);
+      j.set_double("Tm", allp[i].temp);
+      j.set_uint("Pos", (uint32_t)(allp[i].pos + 1));
+      j.set_uint("End", (uint64_t)allp[i].pos + pSeq[allp[i].primerId].size());
+      j.set_string("Ori", allp[i].onFor ? "forward" : "reverse");
+      j.set_string("Name", pName[allp[i].primerId]);
+      j.set_double("MatchTm", allp[i].perfTemp);
+      j.set_string("Seq", pSeq[allp[i].primerId]);
+      j.set_string("Genome", allp[i].genome);
+      o += j.dump();
+    }
+    o += "],\"amplicons\":[";
+    for (size_t i = 0; i < pcrColl.size(); ++i) {
+      if (i) o += ',';
+      const PcrProduct& p = pcrColl[i];
+      JsonRaw j;
+      j.set_string("Chrom", qn[p.refIndex]);
+      j.set_uint("Id", i);
+      j.set_uint("Length", p.leng);
+      j.set_double("Penalty", p.penalty);
+      j.set_uint("ForPos", (uint32_t)(p.forPos + 1));
+      j.set_uint("ForEnd", (uint64_t)p.forPos + pSeq[p.forId].size());
+      j.set_double("ForTm", p.forTemp);
+      j.set_string("ForName", pName[p.forId]);
+      j.set_string("ForSeq", pSeq[p.forId]);
+      j.set_uint("RevPos", (uint32_t)(p.revPos + 1));
+      j.set_uint("RevEnd", (uint64_t)p.revPos + pSeq[p.revId].size());
+      j.set_double("RevTm", p.revTemp);
+      j.set_string("RevName", pName[p.revId]);
+      j.set_string("RevSeq", pSeq[p.revId]);
+      j.set_string("Seq", ampSeq[i]);
+      o += j.dump();
+    }
+    o += "]}";
+  }
+  o += "}\n";
+  return o;
+}
+
+void search_usage(const char* argv0) {
+  std::cout << "Usage: dicey " << argv0 << " [OPTIONS] -g <ref.fa.gz> sequences.fasta" << std::endl;
+  std::cout << "Generic options:\n"
+               "  -? [ --help ]                         show help message\n"
+               "  -g [ --genome ] arg                   genome file\n"
+               "  -i [ --config ] arg (=./src/primer3_config/)\n"
+               "                                        primer3 config directory\n"
+               "  -o [ --outfile ] arg                  output file\n"
+               "\nApproximate Search Options:\n"
+               "  -k [ --kmer ] arg (=15)               k-mer size\n"
+               "  -m [ --maxmatches ] arg (=10000)      max. number of matches per k-mer\n"
+               "  -x [ --maxNeighborhood ] arg (=10000) max. neighborhood size\n"
+               "  -d [ --distance ] arg (=1)            neighborhood distance\n"
+               "  -q [ --pruneprimer ] arg              prune primer threshold\n"
+               "  -n [ --hamming ]                      use hamming neighborhood instead of edit \n"
+               "                                        distance\n"
+               "\nParameters for Scoring and Penalty Calculation:\n"
+               "  -c [ --cutTemp ] arg (=45)            min. primer melting temperature\n"
+               "  -l [ --maxProdSize ] arg (=15000)     max. PCR Product size\n"
+               "  --cutoffPenalty arg (=-1)             max. penalty for products (-1 = keep all)\n"
+               "  --penaltyTmDiff arg (=0.6)            multiplication factor for deviation of \n"
+               "                                        primer Tm penalty\n"
+               "  --penaltyTmMismatch arg (=0.4)        multiplication factor for Tm pair \n"
+               "                                        difference penalty\n"
+               "  --penaltyLength arg (=0.001)          multiplication factor for amplicon length \n"
+               "                                        penalty\n"
+               "\nParameters for Tm Calculation:\n"
+               "  --enttemp arg (=37)                   temperature for entropie and entalpie \n"
+               "                                        calculation in Celsius\n"
+               "  --monovalent arg (=50)                concentration of monovalent ions in mMol\n"
+               "  --divalent arg (=1.5)                 concentration of divalent ions in mMol\n"
+               "  --dna arg (=50)                       concentration of annealing(!) Oligos in nMol\n"
+               "  --dntp arg (=0.6)                     the sum  of all dNTPs in mMol\n"
+               "\n";
+}
+
+int silica(int argc, char** argv) {
+  SilicaConfig c;
+  Options opt({{"help", '?', false}, {"genome", 'g', true}, {"config", 'i', true}, {"outfile", 'o', true}, {"kmer", 'k', true},
+               {"maxmatches", 'm', true}, {"maxNeighborhood", 'x', true}, {"distance", 'd', true}, {"pruneprimer", 'q', true},
+               {"hamming", 'n', false}, {"cutTemp", 'c', true}, {"maxProdSize", 'l', true}, {"cutoffPenalty", 0, true},
+               {"penaltyTmDiff", 0, true}, {"penaltyTmMismatch", 0, true}, {"penaltyLength", 0, true}, {"enttemp", 0, true},
+               {"monovalent", 0, true}, {"divalent", 0, true}, {"dna", 0, true}, {"dntp", 0, true}, {"input-file", 0, true},
+               {"device", 0, true}});
+  try {
+    opt.parse(argc, argv);
+    c.kmer = (uint32_t)opt.get_u64("kmer", 15);
+    c.max_locations = opt.get_u64("maxmatches", 10000);
+    c.maxNeighborhood = (uint32_t)opt.get_u64("maxNeighborhood", 10000);
+    c.distance = (uint32_t)opt.get_u64("distance", 1);
+    c.maxPruneCount = (uint32_t)opt.get_u64("pruneprimer", 0);
+    c.maxProdSize = (uint32_t)opt.get_u64("maxProdSize", 15000);
+    c.cutTemp = opt.get_double("cutTemp", 45.0);
+    c.cutofPen = opt.get_double("cutoffPenalty", -1.0);
+    c.penDiff = opt.get_double("penaltyTmDiff", 0.6);
+    c.penMis = opt.get_double("penaltyTmMismatch", 0.4);
+    c.penLen = opt.get_double("penaltyLength", 0.001);
+    c.temp = opt.get_double("enttemp", 37.0);
+    c.mv = opt.get_double("monovalent", 50.0);
+    c.dv = opt.get_double("divalent", 1.5);
+    c.dna_conc = opt.get_double("dna", 50.0);
+    c.dntp = opt.get_double("dntp", 0.6);
+    c.device = (int)opt.get_u64("device", getenv("DICEY_B200_DEVICE") ? strtoull(getenv("DICEY_B200_DEVICE"), nullptr, 10) : 0);
+  } catch (std::exception& e) {
+    std::cerr << "dicey " << argv[0] << ": " << e.what() << std::endl;
+    return 1;
+  }
+  if (opt.has("input-file")) opt.positional.insert(opt.positional.begin(), opt.get("input-file"));
+  if (opt.has("help") || opt.positional.empty() || !opt.has("genome")) {
+    search_usage(argv[0]);
+    return -1;
+  }
+  c.infile = opt.positional.back();
+  c.genome = opt.get("genome");
+  c.outfile = opt.get("outfile");
+  if (opt.has("config")) c.primer3Config = opt.get("config");
+  c.indel = !opt.has("hamming");
+  c.hasOutfile = opt.has("outfile");
+  c.pruneprimer = opt.has("pruneprimer");
+
+  std::vector<PrimerBind> allp;
+  std::vector<PcrProduct> pcrColl;
+  std::vector<std::string> msg, seqname, pName, pSeq, ampSeq;
+  uint32_t distance = c.distance;
+  dg_index* ix = nullptr;
+  dg_thal* th = nullptr;
+  auto out = [&]() {   // jsonPrimerOut (silica.h:190-205): one gzip stream, truncating
+    const std::string json = search_json(c, distance, seqname, allp, pcrColl, pName, pSeq, msg, ampSeq);
+    if (c.hasOutfile) {
+      FILE* t = fopen(c.outfile.c_str(), "wb");
+      if (t) fclose(t);
+      if (!gz_append(c.outfile, json)) std::cerr << "Error: cannot write " << c.outfile << std::endl;
+    } else {
+      std::cout << json << std::flush;
+    }
+  };
+  auto fail = [&](const std::string& m) {
+    msg.push_back(m);
+    out();
+    if (th) dg_thal_close(th);
+    if (ix) dg_index_close(ix);
+    return 1;
+  };
+  if (!nonempty_regular_file(c.genome)) return fail("Error: Genome does not exist!");
+  // primer3 config directory (silica.h:300-315)
+  {
+    struct stat stc;
+    if (stat(c.primer3Config.c_str(), &stc) != 0 || !S_ISDIR(stc.st_mode)) return fail("Error: Cannot find primer3 config directory!");
+    while (c.primer3Config.size() > 1 && c.primer3Config.back() == '/') c.primer3Config.pop_back();
+    c.primer3Config += '/';
+    struct stat stf;
+    if (stat((c.primer3Config + "tetraloop.dh").c_str(), &stf) != 0) return fail("Error: Config directory path appears to be incorrect!");
+  }
+  std::vector<uint64_t> lens;
+  if (!read_fai(c.genome, seqname, lens)) {
+    std::cerr << "Fail to open genome fai index for " << c.genome << std::endl;
+    return fail("Error: Could not retrieve sequence lengths!");
+  }
+  const uint32_t nseq = (uint32_t)lens.size();
+  std::vector<uint32_t> seqlen(nseq);
+  std::vector<uint64_t> cum(nseq + 1, 0);
+  for (uint32_t i = 0; i < nseq; ++i) { seqlen[i] = (uint32_t)(lens[i] + 1); cum[i + 1] = cum[i] + seqlen[i]; }
+  std::string index_file = path_join(path_parent(c.genome), path_stem(c.genome)) + ".fm9";
+  if (dg_index_open(index_file.c_str(), c.device, &ix) != DG_OK) {
+    std::cerr << "dicey-b200: " << dg_last_error() << std::endl;
+    ix = nullptr;
+    return fail("Error: FM-Index cannot be loaded!");
+  }
+  dg_index_set_records(ix, seqlen.data(), nseq);
+  if (dg_thal_open(c.primer3Config.c_str(), c.mv, c.dv, c.dntp, c.dna_conc, c.device, &th) != DG_OK) {
+    std::cerr << "dicey-b200: " << dg_last_error() << std::endl;
+    th = nullptr;
+    return fail("Error: Config directory path appears to be incorrect!");
+  }
+  // input FASTA (silica.h:349-408)
+  {
+    struct stat sti;
+    if (stat(c.infile.c_str(), &sti) != 0 || S_ISDIR(sti.st_mode)) return fail("Error: Input fasta file is missing!");
+  }
+  struct Rec { std::string name, seq; };
+  std::vector<Rec> recs;   // records that reach the count / length tests, in file order
+  {
+    std::ifstream fafile(c.infile.c_str());
+    std::string fan, tmpfasta, line;
+    while (std::getline(fafile, line)) {
+      if (line.empty()) continue;
+      if (line[0] == '>') {
+        if (!fan.empty() && !tmpfasta.empty() && tmpfasta.size() > c.kmer) {
+          recs.push_back({fan, tmpfasta});
+          tmpfasta.clear();   // (a sequence not longer than k stays and is prepended to the next record, as in the reference)
+        }
+        fan = line.substr(1);
+      } else {
+        for (char& ch : line) ch = (char)toupper((unsigned char)ch);
+        tmpfasta += line;
+      }
+    }
+    if (!fan.empty() && !tmpfasta.empty() && tmpfasta.size() > c.kmer) recs.push_back({fan, tmpfasta});
+  }
+  // prune counts of the 3' k-mer and its reverse complement (silica.h:364-367): exact, forward strand
+  std::vector<uint64_t> cnt_f(recs.size(), 0), cnt_r(recs.size(), 0);
+  if (c.pruneprimer && !recs.empty()) {
+    std::string cat_f, cat_r;
+    std::vector<uint64_t> off(1, 0);
+    for (const auto& r : recs) {
+      std::string qr = r.seq.substr(r.seq.size() - c.kmer);
+      cat_f += qr;
+      cat_r += revcomp_upper(qr);
+      off.push_back(cat_f.size());
+    }
+    dg_params pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.distance = 0; pc.max_neighborhood = c.maxNeighborhood; pc.max_locations = 1; pc.indel = 1; pc.reverse = 0;
+    if (dg_count_batch(ix, cat_f.data(), off.data(), (uint32_t)recs.size(), &pc, cnt_f.data()) != DG_OK ||
+        dg_count_batch(ix, cat_r.data(), off.data(), (uint32_t)recs.size(), &pc, cnt_r.data()) != DG_OK)
+      return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
+  }
+  for (size_t i = 0; i < recs.size(); ++i) {
+    if (c.pruneprimer && (cnt_f[i] > c.maxPruneCount || cnt_r[i] > c.maxPruneCount)) continue;
+    std::string inseq;
+    for (char ch : recs[i].seq) {   // replaceNonDna (util.h:208-219)
+      if (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T') inseq += ch;
+      else { msg.push_back("Warning: Non-DNA character in nucleotide sequence detected and replaced by 'N'!"); inseq += 'N'; }
+    }
+    if (inseq.size() < 10 || inseq.size() < c.kmer)
+      return fail("Error: Input sequence is shorter than 10 nucleotides or shorter than the selected k-mer length!");
+    if (distance >= inseq.size()) {
+      distance = (uint32_t)inseq.size() - 1;
+      msg.push_back("Warning: Distance was adjusted to sequence length!");
+    }
+    pName.push_back(recs[i].name);
+    pSeq.push_back(inseq);
+  }
+  const uint32_t np = (uint32_t)pSeq.size();
+  // perfect-match temperatures: thal(primer, reverse complement) (silica.h:430-443)
+  std::vector<std::string> revQ(np);
+  std::vector<double> matchTemp(np, 0.0);
+  if (np) {
+    std::string c1, c2;
+    std::vector<uint64_t> o1(1, 0), o2(1, 0);
+    for (uint32_t i = 0; i < np; ++i) {
+      revQ[i] = revcomp_upper(pSeq[i]);
+      c1 += pSeq[i]; o1.push_back(c1.size());
+      c2 += revQ[i]; o2.push_back(c2.size());
+    }
+    std::vector<uint8_t> ok(np);
+    if (dg_thal_batch(th, c1.data(), o1.data(), c2.data(), o2.data(), np, matchTemp.data(), ok.data()) != DG_OK)
+      return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
+    for (uint32_t i = 0; i < np; ++i)
+      if (!ok[i] || matchTemp[i] == -999999.0) return fail("Error: Thermodynamical calculation failed!");
+  }
+  // seeds: every candidate site of every primer (silica.h:446-500, 521-532)
+  dg_result* res = nullptr;
+  if (np) {
+    std::string cat;
+    std::vector<uint64_t> off(1, 0);
+    for (const auto& s2 : pSeq) { cat += s2; off.push_back(cat.size()); }
+    dg_params par;
+    memset(&par, 0, sizeof(par));
+    par.distance = distance;
+    par.max_neighborhood = c.maxNeighborhood;
+    par.max_locations = c.max_locations > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)c.max_locations;
+    par.indel = c.indel ? 1 : 0;
+    par.reverse = 1;
+    par.seed_len = c.kmer;
+    if (dg_hunt_batch(ix, cat.data(), off.data(), np, &par, &res) != DG_OK)
+      return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
+  }
+  uint64_t nh = 0, pool_bytes = 0;
+  uint32_t nq = 0;
+  const dg_hit* hits = res ? dg_result_hits(res, &nh) : nullptr;
+  const uint64_t* qoff = res ? dg_result_query_offsets(res, &nq) : nullptr;
+  const uint32_t* status = res ? dg_result_query_status(res) : nullptr;
+  const char* pool = res ? dg_result_pool(res, &pool_bytes) : nullptr;
+  // melting temperature of every candidate (silica.h:502-512)
+  std::vector<double> tm(nh, 0.0);
+  std::vector<uint8_t> tok(nh, 1);
+  if (nh) {
+    std::string c1, c2;
+    std::vector<uint64_t> o1(1, 0), o2(1, 0);
+    c1.reserve(nh * 24); c2.reserve(nh * 32);
+    for (uint64_t h = 0; h < nh; ++h) {
+      const std::string& primer = hits[h].strand == '-' ? pSeq[hits[h].query] : revQ[hits[h].query];
+      c1 += primer; o1.push_back(c1.size());
+      c2.append(pool + hits[h].aln_off, hits[h].aln_len); o2.push_back(c2.size());
+    }
+    if (nh > 0xFFFFFFFFULL || dg_thal_batch(th, c1.data(), o1.data(), c2.data(), o2.data(), (uint32_t)nh, tm.data(), tok.data()) != DG_OK) {
+      if (res) dg_result_free(res);
+      return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
+    }
+  }
+  std::vector<std::vector<PrimerBind>> forBind(nseq), revBind(nseq);
+  for (uint32_t primerId = 0; primerId < np; ++primerId) {
+    const uint32_t koffset = (uint32_t)pSeq[primerId].size() - c.kmer;
+    if (status[primerId] & DG_Q_NBR_CAP) {
+      std::string x = std::to_string(c.maxNeighborhood);
+      msg.push_back("Warning: Neighborhood size exceeds " + x + " candidates. Only first " + x +
+                    " neighbors are searched, results are likely incomplete!");
+    }
+    for (int fwrvidx = 0; fwrvidx < 2; ++fwrvidx) {
+      std::set<std::pair<uint32_t, uint32_t>> uphit;
+      for (uint64_t h = qoff[primerId]; h < qoff[primerId + 1]; ++h) {
+        if ((hits[h].strand == '-') != (fwrvidx == 1)) continue;
+        if (!tok[h] || tm[h] == -999999.0) {
+          if (res) dg_result_free(res);
+          return fail("Error: Thermodynamical calculation failed!");
+        }
+        if (!(tm[h] > c.cutTemp)) continue;
+        uint32_t refIndex = hits[h].chr, chrpos = hits[h].start, alignpos = hits[h].alignpos;
+        if (!uphit.insert(std::make_pair(refIndex, alignpos)).second) continue;
+        const std::string& primer = fwrvidx ? pSeq[primerId] : revQ[primerId];
+        std::string genomicseq(pool + hits[h].aln_off, hits[h].aln_len);
+        if (fwrvidx) {
+          uint32_t alignshift = alignpos - chrpos;
+          chrpos = alignpos;
+          genomicseq = alignshift <= genomicseq.size() ? genomicseq.substr(alignshift, primer.size()) : std::string();
+        } else {
+          uint32_t alignshift = alignpos - chrpos;
+          chrpos = alignpos - koffset;
+          if (alignshift >= koffset) {
+            alignshift -= koffset;
+            genomicseq = alignshift <= genomicseq.size() ? genomicseq.substr(alignshift, primer.size()) : std::string();
+          }
+        }
+        PrimerBind prim;
+        prim.refIndex = refIndex; prim.temp = tm[h]; prim.perfTemp = matchTemp[primerId]; prim.primerId = primerId;
+        prim.genome = genomicseq; prim.onFor = !fwrvidx; prim.pos = chrpos;
+        (fwrvidx ? revBind : forBind)[refIndex].push_back(prim);
+      }
+    }
+    if (status[primerId] & DG_Q_HIT_CAP) {
+      std::string x = std::to_string(c.max_locations);
+      msg.push_back("Warning: More than " + x + " matches found. Only first " + x + " matches are reported, results are likely incomplete!");
+    }
+  }
+  if (res) dg_result_free(res);
+  for (uint32_t refIndex = 0; refIndex < nseq; ++refIndex) {   // silica.h:580-587
+    allp.insert(allp.end(), forBind[refIndex].begin(), forBind[refIndex].end());
+    allp.insert(allp.end(), revBind[refIndex].begin(), revBind[refIndex].end());
+  }
+  std::sort(allp.begin(), allp.end());
+  if (!c.pruneprimer) {
+    for (uint32_t refIndex = 0; refIndex < nseq; ++refIndex) {   // silica.h:591-634
+      std::vector<std::pair<uint32_t, uint32_t>> rvByPos;
+      rvByPos.reserve(revBind[refIndex].size());
+      for (uint32_t k = 0; k < revBind[refIndex].size(); ++k) rvByPos.push_back(std::make_pair(revBind[refIndex][k].pos, k));
+      std::sort(rvByPos.begin(), rvByPos.end());
+      std::vector<uint32_t> rvPos(rvByPos.size());
+      for (uint32_t k = 0; k < rvByPos.size(); ++k) rvPos[k] = rvByPos[k].first;
+      std::vector<uint32_t> cand;
+      for (auto fw = forBind[refIndex].begin(); fw != forBind[refIndex].end(); ++fw) {
+        auto loIt = std::upper_bound(rvPos.begin(), rvPos.end(), fw->pos);
+        std::vector<uint32_t>::iterator hiIt;
+        uint64_t hiBound = (uint64_t)fw->pos + (uint64_t)c.maxProdSize;
+        if (hiBound >= ((uint64_t)1 << 32)) hiIt = rvPos.end();
+        else hiIt = std::upper_bound(rvPos.begin(), rvPos.end(), (uint32_t)hiBound);
+        cand.clear();
+        for (auto pit = loIt; pit != hiIt; ++pit) cand.push_back(rvByPos[pit - rvPos.begin()].second);
+        std::sort(cand.begin(), cand.end());
+        for (auto cit = cand.begin(); cit != cand.end(); ++cit) {
+          auto rv = revBind[refIndex].begin() + (*cit);
+          if ((rv->pos > fw->pos) && (rv->pos + pSeq[rv->primerId].size() - fw->pos <= c.maxProdSize)) {
+            PcrProduct pp;
+            pp.refIndex = refIndex; pp.forPos = fw->pos; pp.forTemp = fw->temp; pp.forId = fw->primerId;
+            pp.revPos = rv->pos; pp.revTemp = rv->temp; pp.revId = rv->primerId;
+            pp.leng = (uint32_t)((rv->pos + pSeq[pp.revId].size()) - fw->pos);
+            double pen = (fw->perfTemp - fw->temp) * c.penDiff;
+            if (pen < 0) pen = 0;
+            double bpen = (rv->perfTemp - rv->temp) * c.penDiff;
+            if (bpen > 0) pen += bpen;
+            pen += std::abs(fw->temp - rv->temp) * c.penMis;
+            pen += pp.leng * c.penLen;
+            pp.penalty = pen;
+            if ((c.cutofPen < 0) || (pen < c.cutofPen)) pcrColl.push_back(pp);
+          }
+        }
+      }
+    }
+    std::sort(pcrColl.begin(), pcrColl.end());
+    // amplicon sequences: faidx_fetch_seq(chrom, forPos, revPos + |rev| - 1), clipped to the record
+    if (!pcrColl.empty()) {
+      std::vector<uint64_t> pos(pcrColl.size()), len(pcrColl.size());
+      uint64_t total = 0;
+      for (size_t i = 0; i < pcrColl.size(); ++i) {
+        const PcrProduct& p = pcrColl[i];
+        uint64_t lo = p.forPos, hi = (uint64_t)p.revPos + pSeq[p.revId].size();   // [lo, hi) inside the record
+        if (hi > lens[p.refIndex]) hi = lens[p.refIndex];
+        if (lo > hi) lo = hi;
+        pos[i] = cum[p.refIndex] + lo;
+        len[i] = hi - lo;
+        total += len[i];
+      }
+      std::string buf(total, '\0');
+      if (dg_index_fetch_text(ix, pos.data(), len.data(), (uint32_t)pcrColl.size(), &buf[0]) != DG_OK)
+        return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
+      ampSeq.resize(pcrColl.size());
+      uint64_t at = 0;
+      for (size_t i = 0; i < pcrColl.size(); ++i) { ampSeq[i] = buf.substr(at, len[i]); at += len[i]; }
+    }
+  }
+  out();
+  dg_thal_close(th);
+  dg_index_close(ix);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 std::string now_string() {  // boost::posix_time::to_simple_string(second_clock::local_time())
   time_t t = time(nullptr);
@@ -378,8 +864,9 @@ void display_usage() {
   std::cout << "Commands:" << std::endl << std::endl;
   std::cout << "    index        index FASTA reference file" << std::endl;
   std::cout << "    hunt         search DNA sequences" << std::endl;
+  std::cout << "    search       in-silico PCR" << std::endl;
   std::cout << std::endl;
-  std::cout << "(search and padlock are not part of dicey-b200 yet: DESIGN.md, scope)" << std::endl << std::endl;
+  std::cout << "(padlock is not part of dicey-b200 yet: DESIGN.md, scope)" << std::endl << std::endl;
 }
 
 }  // namespace
@@ -395,8 +882,9 @@ int main(int argc, char** argv) {
   if (cmd == "help" || cmd == "--help" || cmd == "-h" || cmd == "-?") { display_usage(); return 0; }
   if (cmd == "index") return index_cmd(argc - 1, argv + 1);
   if (cmd == "hunt") return hunter(argc - 1, argv + 1);
-  if (cmd == "search" || cmd == "padlock") {
-    std::cerr << "dicey-b200: '" << cmd << "' is not available in this build (needs the thal Tm model; DESIGN.md, scope)" << std::endl;
+  if (cmd == "search") return silica(argc - 1, argv + 1);
+  if (cmd == "padlock") {
+    std::cerr << "dicey-b200: 'padlock' is not part of this build yet (DESIGN.md, scope)" << std::endl;
     return 1;
   }
   std::cerr << "Unrecognized command " << cmd << std::endl;

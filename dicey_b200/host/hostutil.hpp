@@ -89,6 +89,15 @@ class Options {
       throw std::runtime_error("the argument ('" + v + "') for option '--" + n + "' is invalid");
     return x;
   }
+  double get_double(const std::string& n, double dflt) const {
+    if (!has(n)) return dflt;
+    const std::string v = get(n);
+    size_t pos = 0;
+    double x = 0;
+    try { x = std::stod(v, &pos); } catch (...) { pos = 0; }
+    if (pos != v.size() || v.empty()) throw std::runtime_error("the argument ('" + v + "') for option '--" + n + "' is invalid");
+    return x;
+  }
   std::vector<std::string> positional;
   std::map<std::string, std::string> values;
 
@@ -179,6 +188,7 @@ class JsonObject {
   void set_uint(const std::string& k, uint64_t v) { kv_[k] = std::to_string(v); }
   void set_int(const std::string& k, int64_t v) { kv_[k] = std::to_string(v); }
   void set_bool(const std::string& k, bool v) { kv_[k] = v ? "true" : "false"; }
+  void set_raw(const std::string& k, const std::string& serialised) { kv_[k] = serialised; }
   std::string dump() const {
     std::string o = "{";
     bool first = true;

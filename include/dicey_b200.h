@@ -136,6 +136,12 @@ int dg_index_set_records(dg_index* idx, const uint32_t* seqlen_plus1, uint32_t n
 
 int dg_index_get_info(const dg_index* idx, dg_index_info* info);
 
+/* Text substrings from the device-resident text (what `dicey search` reads back from the FASTA
+ * with faidx_fetch_seq for its amplicon sequences, silica.h:170-173; the index text is the
+ * upper-cased FASTA): n ranges [pos[i], pos[i] + len[i]) of text positions, written back to back
+ * into buf (sum of len bytes).                                                                */
+int dg_index_fetch_text(dg_index* idx, const uint64_t* pos, const uint64_t* len, uint32_t n, char* buf);
+
 /* The CUDA stream (cudaStream_t) every kernel of this index is launched on. */
 void* dg_index_stream(const dg_index* idx);
 

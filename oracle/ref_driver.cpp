@@ -519,6 +519,10 @@ struct Args {
   bool hamming = false, forward = false, counters = false;
   std::string records, json, genome = "genome.fa.gz", outfile = "";
   std::size_t limit = 0;
+  double cutTemp = 45.0;       // silica.h:232
+  uint32_t maxProd = 15000;    // silica.h:233
+  bool prune = false;          // silica.h:226 (-q)
+  uint32_t pruneCount = 0;
 };
 static bool parse(int argc, char** argv, Args& a) {
   for (int i = 2; i < argc; ++i) {
@@ -532,6 +536,9 @@ static bool parse(int argc, char** argv, Args& a) {
     else if (s == "-k") a.k = std::strtoul(need("-k"), 0, 10);
     else if (s == "-m") { a.m = std::strtoull(need("-m"), 0, 10); a.mset = true; }
     else if (s == "-n") a.hamming = true;
+    else if (s == "-c") a.cutTemp = std::strtod(need("-c"), 0);
+    else if (s == "-l") a.maxProd = std::strtoul(need("-l"), 0, 10);
+    else if (s == "-q") { a.prune = true; a.pruneCount = std::strtoul(need("-q"), 0, 10); }
     else if (s == "-f") a.forward = true;
     else if (s == "--counters") a.counters = true;
     else if (s == "--threads") a.threads = std::strtoul(need("--threads"), 0, 10);
@@ -858,6 +865,292 @@ static int cmd_thal(Args const& a) {
   return 0;
 }
 
+// search <in.fm9> <records.tsv> <primers.fa> <primer3_config/> [-k K] [-d D] [-n] [-m MAXLOC] [-x MAXNBR]
+//        [-c CUTTEMP] [-l MAXPRODSIZE] [-q PRUNE]: restates silica() (silica.h:340-641) and
+// writeJsonPrimerOut (silica.h:100-187) around the verbatim SDSL / neighbors.h / needle.h / thal.h /
+// nlohmann code; the FM / NW part is run_seed above.  Amplicon sequences come from the index text
+// (the reference reads them back from the FASTA with faidx_fetch_seq and upper-cases them).
+struct PrimerBind {  // silica.h:69-82
+  uint32_t refIndex, pos, primerId;
+  bool onFor;
+  double temp, perfTemp;
+  std::string genome;
+  bool operator<(const PrimerBind& b) const { return (temp > b.temp); }
+};
+struct PcrProduct {  // silica.h:84-98
+  uint32_t refIndex, leng, forPos, revPos, forId, revId;
+  double forTemp, revTemp, penalty;
+  bool operator<(const PcrProduct& b) const { return (penalty < b.penalty); }
+};
+static int cmd_search(Args const& a) {
+  if (a.pos.size() < 4) return usage();
+  TIndex fm_index;
+  if (!load_index(a.pos[0], fm_index)) return 1;
+  std::vector<std::string> seqname;
+  std::vector<uint32_t> seqlen;
+  if (!read_records(a.pos[1], seqname, seqlen)) return 1;
+  uint32_t nseq = seqlen.size();
+  std::string cfg = a.pos[3];
+  if (cfg.empty() || cfg.back() != '/') cfg += '/';
+  uint32_t kmer = a.k, distance = a.d;
+  bool indel = !a.hamming;
+  std::size_t max_locations = a.mset ? a.m : 10000;
+  double cutTemp = a.cutTemp, penDiff = 0.6, penMis = 0.4, penLen = 0.001, cutofPen = -1.0;
+  uint32_t maxProdSize = a.maxProd;
+  primer3thal::thal_args ta;
+  primer3thal::set_thal_default_args(&ta);
+  ta.temponly = 1;
+  ta.type = primer3thal::thal_end1;
+  primer3thal::get_thermodynamic_values(cfg.c_str());
+  ta.temp = 37.0; ta.mv = 50.0; ta.dv = 1.5; ta.dna_conc = 50.0; ta.dntp = 0.6;
+  ta.temp += primer3thal::ABSOLUTE_ZERO;
+  std::vector<std::string> msg, pName, pSeq;
+  std::vector<PrimerBind> allp;
+  std::vector<PcrProduct> pcrColl;
+  bool fatal = false;
+  // primers (silica.h:355-408)
+  {
+    std::ifstream fafile(a.pos[2].c_str());
+    std::string fan, tmpfasta, line;
+    auto flush = [&]() {
+      if ((!fan.empty()) && (!tmpfasta.empty()) && (tmpfasta.size() > kmer)) {
+        std::string qr = tmpfasta.substr(tmpfasta.size() - kmer);
+        if ((!a.prune) || (sdsl::count(fm_index, qr.begin(), qr.end()) <= a.pruneCount)) {
+          reverseComplement(qr);
+          if ((!a.prune) || (sdsl::count(fm_index, qr.begin(), qr.end()) <= a.pruneCount)) {
+            std::string inseq = replaceNonDna(tmpfasta, msg);
+            if ((inseq.size() < 10) || (inseq.size() < kmer)) {
+              msg.push_back("Error: Input sequence is shorter than 10 nucleotides or shorter than the selected k-mer length!");
+              fatal = true;
+              return;
+            }
+            if (distance >= inseq.size()) {
+              distance = inseq.size() - 1;
+              msg.push_back("Warning: Distance was adjusted to sequence length!");
+            }
+            pName.push_back(fan);
+            pSeq.push_back(inseq);
+          }
+        }
+      }
+    };
+    while (!fatal && std::getline(fafile, line)) {
+      if (line.empty()) continue;
+      if (line[0] == '>') {
+        if ((!fan.empty()) && (!tmpfasta.empty()) && (tmpfasta.size() > kmer)) { flush(); tmpfasta = ""; }
+        fan = line.substr(1);
+      } else {
+        std::string up = line;
+        for (auto& ch : up) ch = (char)std::toupper((unsigned char)ch);
+        tmpfasta += up;
+      }
+    }
+    if (!fatal) flush();
+  }
+  std::vector<std::vector<PrimerBind>> forBind(nseq), revBind(nseq);
+  for (uint32_t primerId = 0; !fatal && primerId < pSeq.size(); ++primerId) {
+    std::string forQuery = pSeq[primerId], revQuery = pSeq[primerId];
+    reverseComplement(revQuery);
+    primer3thal::thal_results oi;
+    bool ok1 = primer3thal::thal((const unsigned char*)forQuery.c_str(), (const unsigned char*)revQuery.c_str(), &ta, &oi);
+    if ((!ok1) || (oi.temp == primer3thal::THAL_ERROR_SCORE)) { msg.push_back("Error: Thermodynamical calculation failed!"); fatal = true; break; }
+    double matchTemp = oi.temp;
+    uint32_t koffset = pSeq[primerId].size() - kmer;
+    // neighbourhood cap warning (silica.h:456-459)
+    {
+      typedef std::set<char> TAlphabet;
+      char tmp[] = {'A', 'C', 'G', 'T'};
+      TAlphabet alphabet(tmp, tmp + 4);
+      std::string sequence = pSeq[primerId].substr(pSeq[primerId].size() - kmer), rev = sequence;
+      reverseComplement(rev);
+      std::set<std::string> f0, f1;
+      dicey::neighbors(sequence, alphabet, distance, indel, a.x, f0);
+      dicey::neighbors(rev, alphabet, distance, indel, a.x, f1);
+      if ((f0.size() >= a.x) || (f1.size() >= a.x))
+        msg.push_back("Warning: Neighborhood size exceeds " + std::to_string(a.x) + " candidates. Only first " + std::to_string(a.x) +
+                      " neighbors are searched, results are likely incomplete!");
+    }
+    std::vector<SeedCand> cands;
+    uint32_t hits = 0;
+    run_seed(fm_index, seqlen, pSeq[primerId], kmer, distance, indel, a.x, max_locations, cands, hits);
+    for (uint32_t fwrvidx = 0; !fatal && fwrvidx < 2; ++fwrvidx) {
+      std::set<std::pair<uint32_t, uint32_t>> uphit;
+      for (auto const& cd : cands) {
+        if (cd.strand != fwrvidx) continue;
+        std::string primer = fwrvidx ? forQuery : revQuery;
+        std::string genomicseq = cd.genomicseq;
+        primer3thal::thal_results o;
+        bool ok = primer3thal::thal((const unsigned char*)primer.c_str(), (const unsigned char*)genomicseq.c_str(), &ta, &o);
+        if ((!ok) || (o.temp == primer3thal::THAL_ERROR_SCORE)) { msg.push_back("Error: Thermodynamical calculation failed!"); fatal = true; break; }
+        if (o.temp > cutTemp) {
+          uint32_t chrpos = cd.chrpos, alignpos = cd.alignpos, refIndex = cd.refIndex;
+          if (uphit.find(std::make_pair(refIndex, alignpos)) == uphit.end()) {
+            uphit.insert(std::make_pair(refIndex, alignpos));
+            if (fwrvidx) {
+              uint32_t alignshift = alignpos - chrpos;
+              chrpos = alignpos;
+              genomicseq = genomicseq.substr(alignshift, primer.size());
+            } else {
+              uint32_t alignshift = alignpos - chrpos;
+              chrpos = alignpos - koffset;
+              if (alignshift >= koffset) {
+                alignshift -= koffset;
+                genomicseq = genomicseq.substr(alignshift, primer.size());
+              }
+            }
+            PrimerBind prim;
+            prim.refIndex = refIndex; prim.temp = o.temp; prim.perfTemp = matchTemp; prim.primerId = primerId; prim.genome = genomicseq;
+            prim.onFor = !fwrvidx;
+            prim.pos = chrpos;
+            (fwrvidx ? revBind : forBind)[refIndex].push_back(prim);
+          }
+        }
+      }
+    }
+    if (hits >= max_locations)
+      msg.push_back("Warning: More than " + std::to_string(max_locations) + " matches found. Only first " + std::to_string(max_locations) +
+                    " matches are reported, results are likely incomplete!");
+  }
+  if (!fatal) {
+    for (uint32_t refIndex = 0; refIndex < nseq; ++refIndex) {
+      allp.insert(allp.end(), forBind[refIndex].begin(), forBind[refIndex].end());
+      allp.insert(allp.end(), revBind[refIndex].begin(), revBind[refIndex].end());
+    }
+    std::sort(allp.begin(), allp.end());
+    if (!a.prune) {
+      for (uint32_t refIndex = 0; refIndex < nseq; ++refIndex) {   // silica.h:591-634
+        std::vector<std::pair<uint32_t, uint32_t>> rvByPos;
+        for (uint32_t k = 0; k < revBind[refIndex].size(); ++k) rvByPos.push_back(std::make_pair(revBind[refIndex][k].pos, k));
+        std::sort(rvByPos.begin(), rvByPos.end());
+        std::vector<uint32_t> rvPos(rvByPos.size());
+        for (uint32_t k = 0; k < rvByPos.size(); ++k) rvPos[k] = rvByPos[k].first;
+        std::vector<uint32_t> cand;
+        for (auto fw = forBind[refIndex].begin(); fw != forBind[refIndex].end(); ++fw) {
+          auto loIt = std::upper_bound(rvPos.begin(), rvPos.end(), fw->pos);
+          std::vector<uint32_t>::iterator hiIt;
+          uint64_t hiBound = (uint64_t)fw->pos + (uint64_t)maxProdSize;
+          if (hiBound >= ((uint64_t)1 << 32)) hiIt = rvPos.end();
+          else hiIt = std::upper_bound(rvPos.begin(), rvPos.end(), (uint32_t)hiBound);
+          cand.clear();
+          for (auto pit = loIt; pit != hiIt; ++pit) cand.push_back(rvByPos[pit - rvPos.begin()].second);
+          std::sort(cand.begin(), cand.end());
+          for (auto cit = cand.begin(); cit != cand.end(); ++cit) {
+            auto rv = revBind[refIndex].begin() + (*cit);
+            if ((rv->pos > fw->pos) && (rv->pos + pSeq[rv->primerId].size() - fw->pos <= maxProdSize)) {
+              PcrProduct pp;
+              pp.refIndex = refIndex; pp.forPos = fw->pos; pp.forTemp = fw->temp; pp.forId = fw->primerId;
+              pp.revPos = rv->pos; pp.revTemp = rv->temp; pp.revId = rv->primerId;
+              pp.leng = (rv->pos + pSeq[pp.revId].size()) - fw->pos;
+              double pen = (fw->perfTemp - fw->temp) * penDiff;
+              if (pen < 0) pen = 0;
+              double bpen = (rv->perfTemp - rv->temp) * penDiff;
+              if (bpen > 0) pen += bpen;
+              pen += std::abs(fw->temp - rv->temp) * penMis;
+              pen += pp.leng * penLen;
+              pp.penalty = pen;
+              if ((cutofPen < 0) || (pen < cutofPen)) pcrColl.push_back(pp);
+            }
+          }
+        }
+      }
+      std::sort(pcrColl.begin(), pcrColl.end());
+    }
+  }
+  // writeJsonPrimerOut (silica.h:100-187)
+  std::ostream& rcfile = std::cout;
+  bool errors = false;
+  rcfile << "{\"errors\": [";
+  for (uint32_t i = 0; i < msg.size(); ++i) {
+    std::string msgtype = "warning";
+    if (msg[i].compare(0, 5, "Error") == 0) { errors = true; msgtype = "error"; }
+    nlohmann::json err;
+    err["type"] = msgtype;
+    err["title"] = msg[i];
+    if (i > 0) rcfile << ',';
+    rcfile << err.dump();
+  }
+  rcfile << "]";
+  if (!errors) {
+    std::vector<uint64_t> cum(nseq + 1, 0);
+    for (uint32_t i = 0; i < nseq; ++i) cum[i + 1] = cum[i] + seqlen[i];
+    rcfile << ",\"meta\":";
+    nlohmann::json meta;
+    meta["version"] = dicey::diceyVersionNumber;
+    meta["subcommand"] = "search";
+    meta["distance"] = distance;
+    meta["genome"] = a.genome;
+    meta["outfile"] = a.outfile;
+    meta["maxmatches"] = max_locations;
+    meta["hamming"] = (!indel);
+    rcfile << meta.dump() << ',';
+    rcfile << "\"data\":{\"primers\":[";
+    for (uint32_t i = 0; i < allp.size(); ++i) {
+      if (i > 0) rcfile << ',';
+      nlohmann::json j;
+      j["Chrom"] = seqname[allp[i].refIndex];
+      j["Id"] = i;
+      j["Tm"] = allp[i].temp;
+      j["Pos"] = allp[i].pos + 1;
+      j["End"] = allp[i].pos + pSeq[allp[i].primerId].size();
+      if (allp[i].onFor) j["Ori"] = "forward";
+      else j["Ori"] = "reverse";
+      j["Name"] = pName[allp[i].primerId];
+      j["MatchTm"] = allp[i].perfTemp;
+      j["Seq"] = pSeq[allp[i].primerId];
+      j["Genome"] = allp[i].genome;
+      rcfile << j.dump();
+    }
+    rcfile << "],\"amplicons\":[";
+    for (uint32_t i = 0; i < pcrColl.size(); ++i) {
+      if (i > 0) rcfile << ',';
+      nlohmann::json j;
+      j["Chrom"] = seqname[pcrColl[i].refIndex];
+      j["Id"] = i;
+      j["Length"] = pcrColl[i].leng;
+      j["Penalty"] = pcrColl[i].penalty;
+      j["ForPos"] = pcrColl[i].forPos + 1;
+      j["ForEnd"] = pcrColl[i].forPos + pSeq[pcrColl[i].forId].size();
+      j["ForTm"] = pcrColl[i].forTemp;
+      j["ForName"] = pName[pcrColl[i].forId];
+      j["ForSeq"] = pSeq[pcrColl[i].forId];
+      j["RevPos"] = pcrColl[i].revPos + 1;
+      j["RevEnd"] = pcrColl[i].revPos + pSeq[pcrColl[i].revId].size();
+      j["RevTm"] = pcrColl[i].revTemp;
+      j["RevName"] = pName[pcrColl[i].revId];
+      j["RevSeq"] = pSeq[pcrColl[i].revId];
+      // faidx_fetch_seq(fai, chrom, forPos, revPos + |rev| - 1): the same bases from the index text
+      uint64_t lo = cum[pcrColl[i].refIndex] + pcrColl[i].forPos;
+      uint64_t hi = cum[pcrColl[i].refIndex] + pcrColl[i].revPos + pSeq[pcrColl[i].revId].size() - 1;
+      uint64_t last = cum[pcrColl[i].refIndex] + seqlen[pcrColl[i].refIndex] - 2;   // faidx clips at the end of the record
+      if (hi > last) hi = last;
+      std::string seqstr;
+      if (lo <= hi) { auto sx = extract(fm_index, lo, hi); seqstr.assign(sx.begin(), sx.end()); }
+      j["Seq"] = seqstr;
+      rcfile << j.dump();
+    }
+    rcfile << "]}";
+  }
+  rcfile << '}' << std::endl;
+  primer3thal::destroy_thal_structures();
+  return fatal ? 1 : 0;
+}
+
+// jsonfloat <file of 64-bit hex patterns>: nlohmann::json(double).dump() per line (the number
+// format of the Tm / Penalty fields of the search JSON)
+static int cmd_jsonfloat(Args const& a) {
+  if (a.pos.size() < 1) return usage();
+  std::vector<std::string> lines;
+  if (!read_lines(a.pos[0], lines)) return 1;
+  for (auto const& l : lines) {
+    uint64_t u = std::strtoull(l.c_str(), nullptr, 16);
+    double d;
+    memcpy(&d, &u, 8);
+    nlohmann::json j = d;
+    std::cout << j.dump() << '\n';
+  }
+  return 0;
+}
+
 static int cmd_dump(Args const& a) {
   if (a.pos.size() < 1) return usage();
   TIndex fm;
@@ -897,5 +1190,7 @@ int main(int argc, char** argv) {
   if (cmd == "padcount") return cmd_padcount(a);
   if (cmd == "dump") return cmd_dump(a);
   if (cmd == "thal") return cmd_thal(a);
+  if (cmd == "search") return cmd_search(a);
+  if (cmd == "jsonfloat") return cmd_jsonfloat(a);
   return usage();
 }

@@ -14,6 +14,7 @@
 #include "../../dicey_b200/csrc/fm9_select.hpp"
 #include "../../dicey_b200/csrc/dg_thal.cuh"
 #include "../../dicey_b200/csrc/thal_params.hpp"
+#include "../../dicey_b200/host/jsonnum.hpp"
 
 using namespace dg;
 
@@ -182,6 +183,18 @@ int main(int argc, char** argv) {
       return 3;
     }
     std::cout << "tables identical (" << sizeof(a) / 8 << " doubles)\n";
+    return 0;
+  }
+  if (cmd == "jsonfloat" && argc >= 3) {
+    // jsonnum.hpp: one 64-bit pattern per line -> what nlohmann::json(double).dump() prints
+    std::ifstream f(argv[2]);
+    std::string line;
+    while (std::getline(f, line)) {
+      uint64_t u = strtoull(line.c_str(), nullptr, 16);
+      double d;
+      memcpy(&d, &u, 8);
+      std::cout << dhost::json_double(d) << '\n';
+    }
     return 0;
   }
   if (cmd == "select" && argc >= 3) {

@@ -137,3 +137,47 @@ def test_index_cli_writes_a_loadable_fm9(tmp_path):
     assert r.stdout == open(os.path.join(GOLDEN, "t1m_e1.jsonl")).read()
     fai = open(os.path.join(d, "genome.fa.gz.fai")).read().splitlines()
     assert fai[0].split("\t")[:2] == ["chr1", "125000"] and len(fai) == 8
+
+
+SEARCH_CASES = [("search_t1m_default", "t1m", "search_t1m"), ("search_t1m_h1_k12", "t1m", "search_t1m"),
+                ("search_t1m_c55_l1000", "t1m", "search_t1m"), ("search_t1m_d0", "t1m", "search_t1m"),
+                ("search_t1m_prune", "t1m", "search_t1m"), ("search_stress_l400", "stress", "search_stress"),
+                ("search_stress_big", "stress", "search_stress")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,index,primers", SEARCH_CASES)
+def test_search_cli_matches_reference_json(tmp_path, case, index, primers):
+    """`dicey-b200 search` (seeds + NW on the GPU, primer3 thal on the GPU, Tm gate, de-duplication,
+    amplicon pairing, penalties, JSON with nlohmann's number format) against the output of the
+    reference driver built around the reference's own SDSL / neighbors.h / needle.h / thal.h / json."""
+    import hashlib
+    from util import write_primer3_config
+    d = make_genome_dir(tmp_path, index)
+    cfg = write_primer3_config(os.path.join(d, "p3cfg"))
+    shutil.copy(os.path.join(GOLDEN, primers + ".primers.fa"), os.path.join(d, "primers.fa"))
+    flags = open(os.path.join(GOLDEN, case + ".flags.txt")).read().split()
+    r = run(["search", "-g", "genome.fa.gz", "-i", cfg] + flags + ["primers.fa"], cwd=d)
+    assert r.returncode == 0, r.stderr
+    want_file = os.path.join(GOLDEN, case + ".json")
+    if os.path.exists(want_file):
+        assert r.stdout == open(want_file).read()
+    else:   # large outputs are pinned by their SHA-256
+        want = open(want_file + ".sha256").read().split()[0]
+        assert hashlib.sha256(r.stdout.encode()).hexdigest() == want
+
+
+@pytest.mark.gpu
+def test_search_cli_errors_and_outfile(tmp_path):
+    from util import write_primer3_config
+    d = make_genome_dir(tmp_path, "t1m")
+    cfg = write_primer3_config(os.path.join(d, "p3cfg"))
+    shutil.copy(os.path.join(GOLDEN, "search_t1m.primers.fa"), os.path.join(d, "primers.fa"))
+    r = run(["search", "-g", "genome.fa.gz", "-i", os.path.join(d, "nope"), "primers.fa"], cwd=d)
+    assert r.returncode == 1 and r.stdout == '{"errors": [{"title":"Error: Cannot find primer3 config directory!","type":"error"}]}\n'
+    r = run(["search", "-g", "genome.fa.gz", "-i", cfg, "missing.fa"], cwd=d)
+    assert r.returncode == 1 and "Error: Input fasta file is missing!" in r.stdout
+    r = run(["search", "-g", "genome.fa.gz", "-i", cfg, "-o", "out.json.gz", "-c", "55", "-l", "1000", "primers.fa"], cwd=d)
+    assert r.returncode == 0 and r.stdout == ""
+    want = open(os.path.join(GOLDEN, "search_t1m_c55_l1000.json")).read().replace('"outfile":""', '"outfile":"out.json.gz"')
+    assert gzip.open(os.path.join(d, "out.json.gz"), "rt").read() == want

@@ -112,3 +112,18 @@ def test_thal_config_loader_reproduces_the_reference_tables():
     reference held after get_thermodynamic_values() (the committed dump)."""
     out = run(HOSTSIM, ["thalcfg", "/root/reference/src/primer3_config/", "thal.params.tsv"])
     assert "tables identical" in out
+
+
+def test_json_double_format_matches_nlohmann():
+    """dicey_b200/host/jsonnum.hpp (Grisu2 + nlohmann's formatting rules) on 31 k doubles: the Tm /
+    penalty values of the golden search outputs, random values over 60 orders of magnitude, random
+    bit patterns, edge cases -- against nlohmann::json(double).dump() (tests/golden/jsonfloat.out.txt)."""
+    assert run(HOSTSIM, ["jsonfloat", "jsonfloat.hex.txt"]) == open(os.path.join(GOLDEN, "jsonfloat.out.txt")).read()
+
+
+def test_primer3_config_rebuilt_from_the_dump_loads_identically(tmp_path):
+    """tests/util.write_primer3_config (the -i directory the search tests hand to dicey-b200 on the GPU
+    box) -> thal_params_from_config -> the same tables, bit for bit."""
+    from util import write_primer3_config
+    d = write_primer3_config(str(tmp_path / "p3"))
+    assert "tables identical" in run(HOSTSIM, ["thalcfg", d + "/", "thal.params.tsv"])

@@ -133,3 +133,50 @@ def fm9_sections(path):
     take("alphabet", alphabet)
     assert pos == len(data), (pos, len(data))
     return out
+
+
+def write_primer3_config(dirpath, dump_path=None):
+    """A primer3_config directory (what `dicey search -i` reads) rebuilt from the committed dump of
+    the tables the reference held (tests/golden/thal.params.tsv): the GPU box has no /root/reference.
+    Values are written with repr(), which strtod reads back to the same double."""
+    import struct
+    dump_path = dump_path or os.path.join(GOLDEN, "thal.params.tsv")
+    tabs = {}
+    for line in open(dump_path):
+        f = line.split()
+        tabs[f[0]] = [struct.unpack("<d", struct.pack("<Q", int(x, 16)))[0] for x in f[2:]]
+    os.makedirs(dirpath, exist_ok=True)
+
+    def num(x):
+        return "inf" if x >= 999999.0 / 2 else repr(x)
+
+    def four(name, key):
+        t = tabs[key]
+        with open(os.path.join(dirpath, name), "w") as fh:
+            for i in range(4):
+                for ii in range(4):
+                    for j in range(4):
+                        for jj in range(4):
+                            fh.write(num(t[((i * 5 + ii) * 5 + j) * 5 + jj]) + "\n")
+
+    four("stack.ds", "stackEntropies"); four("stack.dh", "stackEnthalpies")
+    four("stackmm.ds", "stackint2Entropies"); four("stackmm.dh", "stackint2Enthalpies")
+    four("tstack_tm_inf.ds", "tstackEntropies"); four("tstack.dh", "tstackEnthalpies")
+    four("tstack2.ds", "tstack2Entropies"); four("tstack2.dh", "tstack2Enthalpies")
+    for ext, k3, k5 in ((".ds", "dangleEntropies3", "dangleEntropies5"), (".dh", "dangleEnthalpies3", "dangleEnthalpies5")):
+        with open(os.path.join(dirpath, "dangle" + ext), "w") as fh:
+            for i in range(4):
+                for j in range(4):
+                    for k in range(4):
+                        fh.write(num(tabs[k3][(i * 5 + k) * 5 + j]) + "\n")      # dangle3[i][k][j]
+            for i in range(4):
+                for j in range(4):
+                    for k in range(4):
+                        fh.write(num(tabs[k5][(i * 5 + j) * 5 + k]) + "\n")      # dangle5[i][j][k]
+    for ext, ki, kb in ((".ds", "interiorLoopEntropies", "bulgeLoopEntropies"), (".dh", "interiorLoopEnthalpies", "bulgeLoopEnthalpies")):
+        with open(os.path.join(dirpath, "loops" + ext), "w") as fh:
+            for k in range(30):
+                fh.write(f"{k + 1}\t{num(tabs[ki][k])}\t{num(tabs[kb][k])}\t0\n")
+    for name in ("tetraloop.ds", "tetraloop.dh", "triloop.ds", "triloop.dh"):
+        open(os.path.join(dirpath, name), "w").close()
+    return dirpath
