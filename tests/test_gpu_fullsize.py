@@ -300,3 +300,49 @@ def test_fm9_loaded_as_is_at_full_size(big, fm9):
             assert r1.push_hits(q) == r2.push_hits(q)
     finally:
         ix.close()
+
+
+def test_config3_search_end_to_end(big, fm9, tmp_path):
+    """dicey search at full size: `dicey-b200 search` on the 3 Gb .fm9 (loaded as-is) against the
+    reference driver (SDSL + neighbors.h + needle.h + thal.h + nlohmann) for planted primer pairs:
+    binding sites, melting temperatures, amplicons, penalties -- the JSON must be the same bytes."""
+    if not fm9:
+        pytest.skip("needs oracle/_ref/dicey_ref")
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import write_primer3_config
+    path, rec = fm9
+    d = str(tmp_path)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "dicey_b200", "host")], check=True, capture_output=True)
+    os.symlink(path, os.path.join(d, "genome.fa.fm9"))
+    os.symlink(path + "_check", os.path.join(d, "genome.fa.fm9_check"))
+    with open(os.path.join(d, "genome.fa.gz"), "wb") as f:
+        f.write(b"placeholder: search only needs the .fai and the index")
+    with open(os.path.join(d, "genome.fa.gz.fai"), "w") as f:
+        for i in range(NREC):
+            f.write(f"chr{i + 1}\t{RECLEN}\t0\t60\t61\n")
+    cfg = write_primer3_config(os.path.join(d, "p3cfg"))
+    rng = np.random.default_rng(17)
+    with open(os.path.join(d, "primers.fa"), "w") as f:
+        for i in range(24):
+            chrom, off, alen = int(rng.integers(0, NREC)), int(rng.integers(0, RECLEN - 5000)), int(rng.integers(150, 3000))
+            L1, L2 = int(rng.integers(18, 25)), int(rng.integers(18, 25))
+            fw = bytearray(window(chrom, off + 1, L1))
+            rv = bytearray(revcomp(window(chrom, off + alen - L2 + 1, L2)))
+            if i % 3 == 1:
+                fw[1] = ord("ACGT"[("ACGT".index(chr(fw[1])) + 1) % 4])
+            f.write(f">amp{i}_F\n{fw.decode()}\n>amp{i}_R\n{rv.decode()}\n")
+    t0 = time.time()
+    want = subprocess.run([REF_BIN, "search", path, rec, os.path.join(d, "primers.fa"), cfg], check=True, capture_output=True, text=True).stdout
+    t1 = time.time()
+    got = subprocess.run([os.path.join(ROOT, "dicey_b200", "dicey-b200"), "search", "-g", "genome.fa.gz", "-i", cfg, "primers.fa"],
+                         cwd=d, capture_output=True, text=True)
+    t2 = time.time()
+    assert got.returncode == 0, got.stderr
+    import json
+    j = json.loads(want)
+    print(f"[fullsize] search, 48 primers: reference {t1 - t0:.1f} s, dicey-b200 {t2 - t1:.1f} s (index load included); "
+          f"{len(j['data']['primers'])} binding sites, {len(j['data']['amplicons'])} amplicons")
+    assert len(j["data"]["amplicons"]) >= 20
+    assert got.stdout == want
