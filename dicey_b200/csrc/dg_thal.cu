@@ -1,10 +1,14 @@
 // dg_thal.cu -- batched melting temperatures on the GPU: the thal() gate of `dicey search`
 // (reference src/silica.h:508-519; the arithmetic is dg_thal.cuh) for every candidate site at once.
 //
-// k_thal runs one pair per thread.  The two DP tables of a thread (|primer| x |site| doubles each)
-// live in a scratch slab in which the tables of the threads of a launch are interleaved cell by
-// cell, so the lanes of a warp -- which walk the same (i, j) order -- read and write consecutive
-// addresses.  Built with -fmad=false: results equal the reference's bit for bit.
+// k_thal_warp (the product path) gives every pair to one warp: the DP table, the list of paired
+// cells and one row of end terms live in shared memory, the lanes evaluate the loop partners of a
+// cell side by side and an arg-min shuffle picks the one the reference's sequential scan would
+// have kept (thal_end1_tm_lanes in dg_thal.cuh has the argument).  k_thal is the sequential form,
+// one pair per thread with the tables of a launch interleaved in a global scratch slab; it serves
+// the pairs the warp form declines (none within primer3's length limit, but the condition is
+// checked) and DG_THAL_SEQ=1 routes everything through it.
+// Built with -fmad=false: results equal the reference's bit for bit.
 #include <algorithm>
 #include <cstring>
 #include <new>
@@ -26,13 +30,71 @@ struct dg_thal {
 
 namespace {
 
+struct ThalWarp {   // the Warp concept of dg_thal.cuh on 32 lanes
+  static constexpr int n = 32;
+  int lane;
+  __device__ void sync() const { __syncwarp(); }
+  __device__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ unsigned lanemask_lt() const { return (1u << lane) - 1u; }
+  __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
+  __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ void argmin(double& g, uint32_t& o, double& S, double& H) const {
+    int who = lane;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, g, off);
+      const uint32_t oo = __shfl_xor_sync(0xffffffffu, o, off);
+      const int ow = __shfl_xor_sync(0xffffffffu, who, off);
+      if (og < g || (og == g && (oo < o || (oo == o && ow < who)))) { g = og; o = oo; who = ow; }
+    }
+    S = __shfl_sync(0xffffffffu, S, who);
+    H = __shfl_sync(0xffffffffu, H, who);
+  }
+};
+
+// shared memory of one warp: table (S, H interleaved), one row of RSH terms, the paired-cell list,
+// the row starts, the two encoded sequences
+__host__ __device__ inline size_t thal_warp_bytes(uint64_t cells) {
+  return (size_t)cells * 16 + 2 * 64 * 8 + (((size_t)cells * 2 + 15) & ~(size_t)15) + 64 * 2 + 64 + 64;
+}
+
+__global__ void __launch_bounds__(128) k_thal_warp(const ThalParams* __restrict__ p, const uint8_t* __restrict__ s1,
+                                                   const uint64_t* __restrict__ off1, const uint8_t* __restrict__ s2,
+                                                   const uint64_t* __restrict__ off2, const uint32_t* __restrict__ ids, uint32_t count,
+                                                   uint64_t cells, double* __restrict__ tm, uint8_t* __restrict__ ok) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * wpb + warp;
+  if (t >= count) return;
+  const uint32_t q = ids[t];
+  unsigned char* base = smem + (size_t)warp * thal_warp_bytes(cells);
+  double* tab = (double*)base;
+  double* rrow = tab + 2 * cells;
+  uint16_t* plist = (uint16_t*)(rrow + 2 * 64);
+  uint16_t* rstart = (uint16_t*)((unsigned char*)plist + (((size_t)cells * 2 + 15) & ~(size_t)15));
+  uint8_t* n1 = (uint8_t*)(rstart + 64);
+  uint8_t* n2 = n1 + 64;
+  const int len1 = (int)(off1[q + 1] - off1[q]), len2 = (int)(off2[q + 1] - off2[q]);
+  ThalWarp wp;
+  wp.lane = threadIdx.x & 31;
+  double out = -kThalInf;
+  int rc = 0;
+  if (len1 <= kThalMaxLen && len2 <= kThalMaxLen && (uint64_t)(len1 > 0 ? len1 : 0) * (uint64_t)(len2 > 0 ? len2 : 0) <= cells)
+    rc = thal_end1_tm_lanes(wp, p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, rrow, plist, rstart, &out);
+  if (wp.lane == 0) {
+    tm[q] = out;
+    ok[q] = (uint8_t)rc;   // 2: the sequential kernel recomputes this pair
+  }
+}
+
 __global__ void __launch_bounds__(128) k_thal(const ThalParams* __restrict__ p, const uint8_t* __restrict__ s1,
                                               const uint64_t* __restrict__ off1, const uint8_t* __restrict__ s2,
-                                              const uint64_t* __restrict__ off2, uint32_t first, uint32_t count, double* __restrict__ scratch,
-                                              uint64_t cells, double* __restrict__ tm, uint8_t* __restrict__ ok) {
+                                              const uint64_t* __restrict__ off2, const uint32_t* __restrict__ ids, uint32_t first,
+                                              uint32_t count, double* __restrict__ scratch, uint64_t cells, double* __restrict__ tm,
+                                              uint8_t* __restrict__ ok) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
-  const uint32_t q = first + t;
+  const uint32_t q = ids ? ids[first + t] : first + t;
   const int len1 = (int)(off1[q + 1] - off1[q]), len2 = (int)(off2[q + 1] - off2[q]);
   uint8_t n1[kThalMaxLen + 2], n2[kThalMaxLen + 2];
   double out = -kThalInf;
@@ -120,19 +182,66 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
     DevBuf<uint8_t> d_s1, d_s2, d_ok;
     DevBuf<uint64_t> d_o1, d_o2;
     DevBuf<double> d_tm, scratch;
+    DevBuf<uint32_t> d_ids;
     d_s1.alloc(nb1 + 1); d_s2.alloc(nb2 + 1); d_o1.alloc((size_t)n + 1); d_o2.alloc((size_t)n + 1); d_tm.alloc(n); d_ok.alloc(n);
     DG_CUDA(cudaMemcpyAsync(d_s1.p, seq1, nb1, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(d_s2.p, seq2, nb2, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(d_o1.p, off1, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(d_o2.p, off2, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
-    // pairs per launch: two tables of `cells` doubles each, at most ~2 GiB of scratch
-    uint64_t per = std::max<uint64_t>(1024, std::min<uint64_t>(n, (2ULL << 30) / (16 * cells)));
-    per = std::min<uint64_t>(per, 1u << 20);
-    scratch.alloc(2 * cells * per);
-    for (uint64_t first = 0; first < n; first += per) {
-      const uint32_t count = (uint32_t)std::min<uint64_t>(per, n - first);
-      k_thal<<<(count + 127) / 128, 128, 0, st>>>(t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p, (uint32_t)first, count, scratch.p, cells,
-                                                   d_tm.p, d_ok.p);
+    // the sequential kernel over `ids` (null: all pairs), at most ~2 GiB of scratch per launch
+    auto sequential = [&](const uint32_t* ids, uint64_t m) {
+      uint64_t per = std::max<uint64_t>(1024, std::min<uint64_t>(m, (2ULL << 30) / (16 * cells)));
+      per = std::min<uint64_t>(per, 1u << 20);
+      scratch.alloc(2 * cells * per);
+      for (uint64_t first = 0; first < m; first += per) {
+        const uint32_t count = (uint32_t)std::min<uint64_t>(per, m - first);
+        k_thal<<<(count + 127) / 128, 128, 0, st>>>(t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p, ids, (uint32_t)first, count, scratch.p,
+                                                     cells, d_tm.p, d_ok.p);
+      }
+      DG_CUDA(cudaGetLastError());
+    };
+    const char* seq_env = getenv("DG_THAL_SEQ");
+    if (seq_env && atoi(seq_env) == 1) {
+      sequential(nullptr, n);
+    } else {
+      // two size classes so that one long pair does not take the shared memory of all the others
+      constexpr uint64_t kSmall = 768;
+      std::vector<uint32_t> order(n);
+      uint64_t n_small = 0, cells_small = 1;
+      {
+        std::vector<uint32_t> large;
+        for (uint32_t q = 0; q < n; ++q) {
+          const uint64_t a = off1[q + 1] - off1[q], b = off2[q + 1] - off2[q];
+          const bool valid = a <= (uint64_t)kThalMaxLen && b <= (uint64_t)kThalMaxLen;
+          if (valid && a * b > kSmall) large.push_back(q);
+          else { order[n_small++] = q; if (valid) cells_small = std::max(cells_small, a * b); }
+        }
+        std::copy(large.begin(), large.end(), order.begin() + n_small);
+      }
+      d_ids.alloc(n);
+      DG_CUDA(cudaMemcpyAsync(d_ids.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaFuncSetAttribute(k_thal_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      auto launch = [&](uint64_t first, uint64_t m, uint64_t cap) {
+        if (!m) return;
+        const size_t per_warp = thal_warp_bytes(cap);
+        const uint32_t wpb = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / per_warp));
+        k_thal_warp<<<(unsigned)((m + wpb - 1) / wpb), wpb * 32, wpb * per_warp, st>>>(t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p,
+                                                                                         d_ids.p + first, (uint32_t)m, cap, d_tm.p, d_ok.p);
+      };
+      launch(0, n_small, cells_small);
+      launch(n_small, n - n_small, cells);
+      DG_CUDA(cudaGetLastError());
+      const bool force_redo = seq_env && atoi(seq_env) == 2;   // test hook: treat every pair as declined
+      std::vector<uint8_t> flags(n);
+      DG_CUDA(cudaMemcpyAsync(flags.data(), d_ok.p, n, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      std::vector<uint32_t> redo;
+      for (uint32_t q = 0; q < n; ++q)
+        if (flags[q] == 2 || force_redo) redo.push_back(q);
+      if (!redo.empty()) {
+        DG_CUDA(cudaMemcpyAsync(d_ids.p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+        sequential(d_ids.p, redo.size());
+      }
     }
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(tm, d_tm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));

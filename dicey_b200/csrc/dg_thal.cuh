@@ -126,12 +126,14 @@ DG_HD void thal_left(const ThalWork& w, int i, int j, double& os, double& oh) {
   thal_end_term(w, b, b2, a, a2, w.p->atpS[a * 5 + b], w.p->atpH[a * 5 + b], thal_bp(a2, b2) != 1, os, oh);
 }
 
-// calc_bulge_internal(i, j, ii, jj): the loop closed by (i, j) on the left and (ii, jj) on the right.
-DG_HD void thal_loop(const ThalWork& w, int i, int j, int ii, int jj, bool traceback, double& os, double& oh) {
+// calc_bulge_internal(i, j, ii, jj), first half: entropy / enthalpy of the structure that reaches
+// (ii, jj) through the loop closed by (i, j) on the left and (ii, jj) on the right.
+DG_HD void thal_loop_value(const ThalWork& w, int i, int j, int ii, int jj, double& S, double& H) {
   const ThalParams& p = *w.p;
   const uint8_t *n1 = w.n1, *n2 = w.n2;
   const int l1 = ii - i - 1, l2 = jj - j - 1, ls = l1 + l2 - 1;
-  double S = -1.0, H = kThalInf;
+  S = -1.0;
+  H = kThalInf;
   if ((l1 == 0 && l2 > 0) || (l2 == 0 && l1 > 0)) {
     if (l2 == 1 || l1 == 1) {      // a bulge of one base keeps the stack across it
       H = p.bulgeH[ls] + p.stackH[thal_i4(n1[i], n1[ii], n2[j], n2[jj])];
@@ -166,19 +168,27 @@ DG_HD void thal_loop(const ThalWork& w, int i, int j, int ii, int jj, bool trace
     if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
     if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
   }
-  double rs, rh;
+}
+
+// The free energy calc_bulge_internal compares structures by; (rs, rh) = RSH of the right end.
+DG_HD double thal_loop_energy(double S, double H, double rs, double rh) { return H + rh - kThalTempK * (S + rs); }
+
+// calc_bulge_internal as the reference calls it: the candidate replaces (os, oh) when it is more
+// stable than the cell's current value (always, during traceback).
+DG_HD void thal_loop(const ThalWork& w, int i, int j, int ii, int jj, bool traceback, double& os, double& oh) {
+  double S, H, rs, rh;
+  thal_loop_value(w, i, j, ii, jj, S, H);
   thal_right(w, ii, jj, rs, rh);
-  const double G1 = H + rh - kThalTempK * (S + rs);
-  const double G2 = w.H(ii, jj) + rh - kThalTempK * (w.S(ii, jj) + rs);
+  const double G1 = thal_loop_energy(S, H, rs, rh);
+  const double G2 = thal_loop_energy(w.S(ii, jj), w.H(ii, jj), rs, rh);
   if (G1 < G2 || traceback) { os = S; oh = H; }
 }
 
 // maxTM(i, j): keep the cell, or extend the stack from (i-1, j-1), whichever melts higher.
-DG_HD void thal_stack(const ThalWork& w, int i, int j) {
+// (rs, rh) = RSH(i, j).
+DG_HD void thal_stack_rs(const ThalWork& w, int i, int j, double rs, double rh) {
   const ThalParams& p = *w.p;
   double S0 = w.S(i, j), H0 = w.H(i, j), S1, H1, T1;
-  double rs, rh;
-  thal_right(w, i, j, rs, rh);
   const double T0 = (H0 + kThalInitH + rh) / (S0 + kThalInitS + rs + w.rc);
   const int k = thal_i4(w.n1[i - 1], w.n1[i], w.n2[j - 1], w.n2[j]);
   if (thal_fin(w.H(i - 1, j - 1)) && thal_fin(p.stackH[k])) {
@@ -194,6 +204,11 @@ DG_HD void thal_stack(const ThalWork& w, int i, int j) {
   if (S0 < kThalMinEntropyCutoff) { S0 = kThalMinEntropy; H0 = 0.0; }
   if (T1 > T0) { w.S(i, j) = S1; w.H(i, j) = H1; }
   else if (T0 >= T1) { w.S(i, j) = S0; w.H(i, j) = H0; }
+}
+DG_HD void thal_stack(const ThalWork& w, int i, int j) {
+  double rs, rh;
+  thal_right(w, i, j, rs, rh);
+  thal_stack_rs(w, i, j, rs, rh);
 }
 
 DG_HD bool thal_symmetric(const uint8_t* s, int len) {   // symmetry_thermo
@@ -301,6 +316,210 @@ DG_HD bool thal_end1_tm(const ThalParams* p, const uint8_t* o1, int len1, const 
   const int N = (paired / 2) - 1;
   *tm = ((dH) / (dS + (N * p->salt) + w.rc)) - kThalAbsZero;
   return true;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// The same computation arranged for a group of cooperating lanes (a warp on the device, one lane
+// in the host build that the CPU tests run):
+//   * only cells whose bases pair are ever finite, so the fill walks a row-major list of paired
+//     cells instead of the whole table;
+//   * LSH (thal_left) and RSH (thal_right) depend on the sequences alone: LSH seeds the table for
+//     all paired cells at once, RSH is evaluated once per row;
+//   * for one cell the reference scans its loop partners (ii, jj) in a fixed order and keeps a
+//     candidate when its free energy is strictly below that of the cell's current value, which
+//     then becomes the candidate -- a running strict minimum.  Its outcome is the first partner
+//     in scan order that attains the overall minimum, if that is below the starting value; the
+//     lanes evaluate partners independently and an arg-min over (energy, scan rank) picks it.
+//     Two things would break that equivalence and make the function return 2 ("use the
+//     sequential form"): a candidate entropy below the -2500 cutoff (the reference then stores
+//     a substitute value), which no pair of sequences within the length limit produces;
+//   * the traceback looks for the first partner in scan order whose value reproduces the cell:
+//     the same arg-min with a constant energy.
+// Warp concept: static n (lanes), lane, sync(), ballot(p), lanemask_lt(), all(p), any(p),
+// argmin(g, order, S, H) -- after it every lane holds the (g, order) minimum (ties: lower order)
+// and that lane's S, H.
+struct ThalOneLane {
+  static constexpr int n = 1;
+  int lane = 0;
+  DG_HD void sync() const {}
+  DG_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  DG_HD unsigned lanemask_lt() const { return 0u; }
+  DG_HD bool all(bool p) const { return p; }
+  DG_HD bool any(bool p) const { return p; }
+  DG_HD void argmin(double&, uint32_t&, double&, double&) const {}
+};
+
+constexpr uint32_t kThalNone = 0xFFFFFFFFu;
+DG_HD int thal_popc(unsigned x) {
+#ifdef __CUDA_ARCH__
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+// Work areas: num1 / num2 len + 2 bytes; tab 2 * len1 * len2 doubles (S, H interleaved);
+// rrow 2 * (len2 + 1) doubles; plist len1 * len2 entries; rstart len1 + 2 entries.
+// Returns 0 where the reference's thal() fails, 1 with *tm set, 2 for "use thal_end1_tm".
+template <class Warp>
+DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
+                             uint8_t* num2, double* tab, double* rrow, uint16_t* plist, uint16_t* rstart, double* tm) {
+  constexpr int n = Warp::n;
+  const int lane = wp.lane;
+  *tm = -kThalInf;
+  if (len1 <= 0 || len2 <= 0) { *tm = 0.0; return 0; }
+  if (len1 > kThalMaxLen || len2 > kThalMaxLen) return 0;
+  for (int i = 1 + lane; i <= len1; i += n) num1[i] = (uint8_t)thal_code(o1[i - 1]);
+  for (int j = 1 + lane; j <= len2; j += n) num2[j] = (uint8_t)thal_code(o2[len2 - j]);
+  if (lane == 0) num1[0] = num1[len1 + 1] = num2[0] = num2[len2 + 1] = 4;
+  wp.sync();
+  bool sym = (len1 % 2 == 0) && (len2 % 2 == 0);
+  if (sym) {
+    bool mine = true;
+    for (int t = lane; t < len1 / 2; t += n) {
+      const int a = num1[1 + t], b = num1[len1 - t];
+      if ((a < 4 || b < 4) && a + b != 3) mine = false;
+    }
+    for (int t = lane; t < len2 / 2; t += n) {
+      const int a = num2[1 + t], b = num2[len2 - t];
+      if ((a < 4 || b < 4) && a + b != 3) mine = false;
+    }
+    sym = wp.all(mine);
+  }
+  ThalWork w;
+  w.p = p; w.n1 = num1; w.n2 = num2; w.len1 = len1; w.len2 = len2; w.ds = tab; w.dh = tab + 1; w.stride = 2;
+  w.rc = sym ? p->rc[0] : p->rc[1];
+  // initMatrix + the list of paired cells, row-major
+  int np = 0;
+  for (int i = 1; i <= len1; ++i) {
+    if (lane == 0) rstart[i] = (uint16_t)np;
+    for (int jb = 1; jb <= len2; jb += n) {
+      const int j = jb + lane;
+      const bool in = j <= len2;
+      const bool pr = in && thal_bp(num1[i], num2[j]) != 0;
+      if (in) { w.H(i, j) = pr ? 0.0 : kThalInf; w.S(i, j) = pr ? kThalMinEntropy : -1.0; }
+      const unsigned m = wp.ballot(pr);
+      if (pr) plist[np + thal_popc(m & wp.lanemask_lt())] = (uint16_t)((i << 8) | j);
+      np += thal_popc(m);
+    }
+  }
+  if (lane == 0) rstart[len1 + 1] = (uint16_t)np;
+  wp.sync();
+  for (int e = lane; e < np; e += n) {   // LSH of every paired cell
+    const int i = plist[e] >> 8, j = plist[e] & 0xff;
+    double s = -1.0, h = kThalInf;
+    thal_left(w, i, j, s, h);
+    if (thal_fin(h)) { w.S(i, j) = s; w.H(i, j) = h; }
+  }
+  wp.sync();
+  // fillMatrix over the paired cells
+  bool odd = false;
+  int row = 0;
+  for (int m = 0; m < np; ++m) {
+    const int i = plist[m] >> 8, j = plist[m] & 0xff;
+    if (i != row) {   // RSH of this row
+      row = i;
+      wp.sync();
+      for (int e = rstart[i] + lane; e < rstart[i + 1]; e += n) {
+        const int jj = plist[e] & 0xff;
+        double rs, rh;
+        thal_right(w, i, jj, rs, rh);
+        rrow[2 * jj] = rs;
+        rrow[2 * jj + 1] = rh;
+      }
+      wp.sync();
+    }
+    if (i == 1 || j == 1) continue;
+    if (!thal_fin(w.H(i, j))) continue;
+    const double rs = rrow[2 * j], rh = rrow[2 * j + 1];
+    wp.sync();
+    thal_stack_rs(w, i, j, rs, rh);   // every lane stores the same value
+    wp.sync();
+    const double G2 = thal_loop_energy(w.S(i, j), w.H(i, j), rs, rh);
+    double bestG = 0.0, bS = -1.0, bH = kThalInf;
+    uint32_t bestO = kThalNone;
+    const int lo = rstart[i > kThalMaxLoop + 1 ? i - (kThalMaxLoop + 1) : 1], hi = rstart[i];
+    for (int e = lo + lane; e < hi; e += n) {
+      const int ii = plist[e] >> 8, jj = plist[e] & 0xff;
+      const int d = (i - ii) + (j - jj);
+      if (jj >= j || d < 3 || d > kThalMaxLoop + 2) continue;
+      if (!thal_fin(w.H(ii, jj))) continue;
+      double S, H;
+      thal_loop_value(w, ii, jj, i, j, S, H);
+      if (!thal_fin(H)) continue;                    // never stored by the reference
+      if (S < kThalMinEntropyCutoff) odd = true;
+      const double G1 = thal_loop_energy(S, H, rs, rh);
+      const uint32_t order = ((uint32_t)d << 6) | (uint32_t)(i - 1 - ii);
+      if (bestO == kThalNone || G1 < bestG || (G1 == bestG && order < bestO)) { bestG = G1; bestO = order; bS = S; bH = H; }
+    }
+    if (bestO == kThalNone) bestG = 1e300;
+    wp.argmin(bestG, bestO, bS, bH);
+    if (bestO != kThalNone && bestG < G2) { w.S(i, j) = bS; w.H(i, j) = bH; }
+    // (wp.sync() at the top of the next iteration orders this store)
+  }
+  wp.sync();
+  if (wp.any(odd)) return 2;
+  // the most stable structure ending at the 3' end of the first sequence
+  int bestI = len1, bestJ = 0;
+  {
+    double bestG = 1e300, dS_ = 0.0, dH_ = 0.0;
+    uint32_t bestO = kThalNone;
+    for (int j = 1 + lane; j <= len2; j += n) {
+      const bool pr = thal_bp(num1[len1], num2[j]) != 0;
+      double s = pr ? rrow[2 * j] : -1.0, h = pr ? rrow[2 * j + 1] : kThalInf;
+      s = s + 0.000001;
+      h = h + 0.000001;
+      const double G1 = (w.H(len1, j) + h + kThalInitH) - kThalTempK * (w.S(len1, j) + s + kThalInitS);
+      if (G1 < kThalInf && (bestO == kThalNone || G1 < bestG)) { bestG = G1; bestO = (uint32_t)j; }
+    }
+    wp.argmin(bestG, bestO, dS_, dH_);
+    if (bestO != kThalNone && thal_fin(bestG)) bestJ = (int)bestO;
+    else bestI = bestJ = 1;
+  }
+  double rs, rh;
+  thal_right(w, bestI, bestJ, rs, rh);
+  const double dH = w.H(bestI, bestJ) + rh + kThalInitH;
+  const double dS = (w.S(bestI, bestJ) + rs + kThalInitS);
+  if (!thal_fin(w.H(bestI, bestJ))) { *tm = 0.0; return 1; }
+  // traceback: only the number of paired bases enters the temperature
+  int paired = 2, i = bestI, j = bestJ;
+  for (int guard = 0; guard < 4 * (len1 + len2); ++guard) {
+    double s = -1.0, h = kThalInf;
+    wp.sync();
+    if (thal_bp(num1[i], num2[j])) thal_left(w, i, j, s, h);   // (a finite cell always pairs)
+    const double cs = w.S(i, j), ch = w.H(i, j);
+    if (cs == s && ch == h) break;
+    if (i > 1 && j > 1) {
+      const int k = thal_i4(num1[i - 1], num1[i], num2[j - 1], num2[j]);
+      if (cs == p->stackS[k] + w.S(i - 1, j - 1) && ch == p->stackH[k] + w.H(i - 1, j - 1)) {
+        --i; --j;
+        paired += 2;
+        continue;
+      }
+    }
+    double g = 0.0, dS_ = 0.0, dH_ = 0.0;
+    uint32_t bestO = kThalNone;
+    const int lo = rstart[i > kThalMaxLoop + 1 ? i - (kThalMaxLoop + 1) : 1], hi = rstart[i];
+    for (int e = lo + lane; e < hi; e += n) {
+      const int ii = plist[e] >> 8, jj = plist[e] & 0xff;
+      const int d = (i - ii) + (j - jj);
+      if (jj >= j || d < 3 || d > kThalMaxLoop + 2) continue;
+      double S, H;
+      thal_loop_value(w, ii, jj, i, j, S, H);
+      const uint32_t order = ((uint32_t)d << 6) | (uint32_t)(i - 1 - ii);
+      if (cs == S && ch == H && order < bestO) bestO = order;
+    }
+    wp.argmin(g, bestO, dS_, dH_);
+    if (bestO == kThalNone) break;   // (the reference would spin here; never observed)
+    const int d = (int)(bestO >> 6), ii = i - 1 - (int)(bestO & 63);
+    j = j - (d - (i - ii));
+    i = ii;
+    paired += 2;
+  }
+  const int N = (paired / 2) - 1;
+  *tm = ((dH) / (dS + (N * p->salt) + w.rc)) - kThalAbsZero;
+  return 1;
 }
 
 }  // namespace dg

@@ -14,6 +14,7 @@
 // `padlock` (probe design over GTF regions) is not part of this round; the library entry points it
 // would call (dg_count_batch, dg_thal_batch) exist and are tested.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <ctime>
 #include <iostream>
@@ -496,6 +497,16 @@ int silica(int argc, char** argv) {
   std::vector<PcrProduct> pcrColl;
   std::vector<std::string> msg, seqname, pName, pSeq, ampSeq;
   uint32_t distance = c.distance;
+  // DICEY_B200_TRACE=1: wall time of every stage on stderr
+  const bool trace = getenv("DICEY_B200_TRACE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char* what, uint64_t items) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[search] %-28s %9.1f ms  (%llu)\n", what, std::chrono::duration<double, std::milli>(t - t_last).count(),
+            (unsigned long long)items);
+    t_last = t;
+  };
   dg_index* ix = nullptr;
   dg_thal* th = nullptr;
   auto out = [&]() {   // jsonPrimerOut (silica.h:190-205): one gzip stream, truncating
@@ -541,6 +552,7 @@ int silica(int argc, char** argv) {
     return fail("Error: FM-Index cannot be loaded!");
   }
   dg_index_set_records(ix, seqlen.data(), nseq);
+  stage("index load", dg_index_size(ix));
   if (dg_thal_open(c.primer3Config.c_str(), c.mv, c.dv, c.dntp, c.dna_conc, c.device, &th) != DG_OK) {
     std::cerr << "dicey-b200: " << dg_last_error() << std::endl;
     th = nullptr;
@@ -606,6 +618,7 @@ int silica(int argc, char** argv) {
     pSeq.push_back(inseq);
   }
   const uint32_t np = (uint32_t)pSeq.size();
+  stage("primers read / pruned", np);
   // perfect-match temperatures: thal(primer, reverse complement) (silica.h:430-443)
   std::vector<std::string> revQ(np);
   std::vector<double> matchTemp(np, 0.0);
@@ -623,6 +636,7 @@ int silica(int argc, char** argv) {
     for (uint32_t i = 0; i < np; ++i)
       if (!ok[i] || matchTemp[i] == -999999.0) return fail("Error: Thermodynamical calculation failed!");
   }
+  stage("perfect-match Tm", np);
   // seeds: every candidate site of every primer (silica.h:446-500, 521-532)
   dg_result* res = nullptr;
   if (np) {
@@ -646,6 +660,7 @@ int silica(int argc, char** argv) {
   const uint64_t* qoff = res ? dg_result_query_offsets(res, &nq) : nullptr;
   const uint32_t* status = res ? dg_result_query_status(res) : nullptr;
   const char* pool = res ? dg_result_pool(res, &pool_bytes) : nullptr;
+  stage("seeds: FM search + NW", nh);
   // melting temperature of every candidate (silica.h:502-512)
   std::vector<double> tm(nh, 0.0);
   std::vector<uint8_t> tok(nh, 1);
@@ -663,6 +678,7 @@ int silica(int argc, char** argv) {
       return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
     }
   }
+  stage("candidate Tm (thal)", nh);
   std::vector<std::vector<PrimerBind>> forBind(nseq), revBind(nseq);
   for (uint32_t primerId = 0; primerId < np; ++primerId) {
     const uint32_t koffset = (uint32_t)pSeq[primerId].size() - c.kmer;
@@ -713,6 +729,7 @@ int silica(int argc, char** argv) {
     allp.insert(allp.end(), revBind[refIndex].begin(), revBind[refIndex].end());
   }
   std::sort(allp.begin(), allp.end());
+  stage("Tm gate, de-duplication", allp.size());
   if (!c.pruneprimer) {
     for (uint32_t refIndex = 0; refIndex < nseq; ++refIndex) {   // silica.h:591-634
       std::vector<std::pair<uint32_t, uint32_t>> rvByPos;
@@ -772,7 +789,9 @@ int silica(int argc, char** argv) {
       for (size_t i = 0; i < pcrColl.size(); ++i) { ampSeq[i] = buf.substr(at, len[i]); at += len[i]; }
     }
   }
+  stage("amplicons", pcrColl.size());
   out();
+  stage("JSON", allp.size());
   dg_thal_close(th);
   dg_index_close(ix);
   return 0;

@@ -204,6 +204,7 @@ def main():
     open(pfn, "w").write("".join(f"{g}\t{q}\n" for g, q in pairs))
     open(os.path.join(HERE, "needle.out.tsv"), "w").write(run(["needle", pfn, "-"]))
     make_thal()
+    make_thal_long()
 
 
 def make_thal():
@@ -250,6 +251,49 @@ def make_thal():
             f.write(a + b"\t" + b + b"\n")
     out = run(["thal", "/root/reference/src/primer3_config/", pfn, os.path.join(HERE, "thal.params.tsv")])
     open(os.path.join(HERE, "thal.out.tsv"), "w").write(out)
+
+
+def make_thal_long():
+    """A second thal set at the limits of the DP: both sequences 8..60 bases, several mismatches,
+    multi-base deletions / insertions (bulges and internal loops up to the 30-base loop limit),
+    replaced middles, low-complexity oligos.  Results only (the tables are thal.params.tsv)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    pairs = []
+    for i in range(1500):
+        L = int(rng.integers(8, 61))
+        kind = i % 9
+        if kind == 7:
+            unit = bytes(acgt[rng.integers(0, 4, int(rng.integers(1, 4)))])
+            primer = (unit * 60)[:L]
+        else:
+            primer = bytes(acgt[rng.integers(0, 4, L)])
+        site = bytearray(primer.translate(comp)[::-1])
+        if kind in (1, 2, 3):
+            for _ in range(kind * 2):
+                site[int(rng.integers(0, len(site)))] = acgt[rng.integers(0, 4)]
+        elif kind == 4:
+            for _ in range(int(rng.integers(1, 4))):
+                if len(site) > 3:
+                    del site[int(rng.integers(1, len(site) - 1))]
+        elif kind == 5:
+            for _ in range(int(rng.integers(1, 6))):
+                site.insert(int(rng.integers(1, len(site) - 1)), int(acgt[rng.integers(0, 4)]))
+        elif kind == 6:
+            site = bytearray(acgt[rng.integers(0, 4, int(rng.integers(8, 61)))])
+        elif kind == 8:
+            a = int(rng.integers(2, max(3, L // 2)))
+            site[a:a + int(rng.integers(0, 10))] = bytes(acgt[rng.integers(0, 4, int(rng.integers(1, 20)))])
+        site = bytes(site)[:60] or b"A"
+        pairs.append((primer, site))
+    pfn = os.path.join(HERE, "thal_long.pairs.tsv")
+    with open(pfn, "wb") as f:
+        for a, b in pairs:
+            f.write(a + b"\t" + b + b"\n")
+    out = run(["thal", "/root/reference/src/primer3_config/", pfn, "/dev/null"])
+    open(os.path.join(HERE, "thal_long.out.tsv"), "w").write(out)
 
 
 if __name__ == "__main__":

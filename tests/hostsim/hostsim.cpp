@@ -145,6 +145,34 @@ int main(int argc, char** argv) {
     fprintf(stderr, "banded needle checked on %d (pair, dmax) cases\n", banded_checked);
     return banded_checked >= 100 ? 0 : 4;
   }
+  if (cmd == "thal2" && argc >= 4) {
+    // the lane-cooperative arrangement of dg_thal.cuh (what the GPU kernel runs) with one lane
+    ThalParams tp;
+    std::string err;
+    if (!thal_params_from_dump(argv[2], tp, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    std::ifstream f(argv[3]);
+    std::string line;
+    while (std::getline(f, line)) {
+      size_t t = line.find('\t');
+      if (t == std::string::npos) continue;
+      std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+      const size_t cells = o1.size() * o2.size();
+      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2);
+      std::vector<double> tab(2 * cells + 2), rrow(2 * o2.size() + 2);
+      std::vector<uint16_t> plist(cells + 1), rstart(o1.size() + 2);
+      double tm = 0;
+      ThalOneLane wp;
+      int rc = thal_end1_tm_lanes(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(), n1.data(),
+                                  n2.data(), tab.data(), rrow.data(), plist.data(), rstart.data(), &tm);
+      if (rc == 2) { fprintf(stderr, "sequential form requested\n"); return 3; }
+      uint64_t u;
+      memcpy(&u, &tm, 8);
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%.17g", tm);
+      std::cout << rc << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
+    }
+    return 0;
+  }
   if (cmd == "thal" && argc >= 4) {
     // dg_thal.cuh on the host: <params.tsv> <pairs.tsv> -> the lines `dicey_ref thal` prints
     ThalParams tp;

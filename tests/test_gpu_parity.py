@@ -288,21 +288,27 @@ def test_wire_records_in_hbm(indexes, monkeypatch, chunk):
         assert np.array_equal(got[f], res.hits[f]), f
 
 
-def test_thal_gpu_is_bit_exact():
-    """dg_thal_batch (one pair per thread, interleaved DP tables, -fmad=false) against the 64-bit
-    patterns of the reference's own thal() for the 709 golden pairs, then the same pairs many
-    times over in one batch (several launches' worth of scratch)."""
+def test_thal_gpu_is_bit_exact(monkeypatch):
+    """dg_thal_batch (-fmad=false) against the 64-bit patterns of the reference's own thal() for the
+    golden pairs (709 primer-like, 1500 at the limits of the DP): the warp-per-pair kernel, the
+    sequential kernel alone (DG_THAL_SEQ=1), and the warp kernel with every pair handed on to the
+    sequential one (DG_THAL_SEQ=2, the path of a declined pair); then the same pairs many times
+    over in one batch."""
     from dicey_b200.api import Thal
-    pairs = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLDEN, "thal.pairs.tsv"))]
-    want = [l.split("\t") for l in open(os.path.join(GOLDEN, "thal.out.tsv")).read().splitlines()]
     th = Thal.open_tables(os.path.join(GOLDEN, "thal.params.tsv"), 0)
     try:
-        tm, ok = th.tm([p[0] for p in pairs], [p[1] for p in pairs])
-        bits = tm.view(np.uint64)
-        for i, w in enumerate(want):
-            assert int(ok[i]) == int(w[0]) and int(bits[i]) == int(w[2], 16), (i, pairs[i], float(tm[i]), w[1])
-        reps = 150
-        tm2, ok2 = th.tm([p[0] for p in pairs] * reps, [p[1] for p in pairs] * reps)
-        assert np.array_equal(tm2.view(np.uint64).reshape(reps, -1), np.tile(bits, (reps, 1))) and ok2.all()
+        for name in ("thal", "thal_long"):
+            pairs = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLDEN, name + ".pairs.tsv"))]
+            want = [l.split("\t") for l in open(os.path.join(GOLDEN, name + ".out.tsv")).read().splitlines()]
+            for mode in ("0", "1", "2"):
+                monkeypatch.setenv("DG_THAL_SEQ", mode)
+                tm, ok = th.tm([p[0] for p in pairs], [p[1] for p in pairs])
+                bits = tm.view(np.uint64)
+                for i, w in enumerate(want):
+                    assert int(ok[i]) == int(w[0]) and int(bits[i]) == int(w[2], 16), (name, mode, i, pairs[i], float(tm[i]), w[1])
+            monkeypatch.setenv("DG_THAL_SEQ", "0")
+            reps = 150 if name == "thal" else 20
+            tm2, ok2 = th.tm([p[0] for p in pairs] * reps, [p[1] for p in pairs] * reps)
+            assert np.array_equal(tm2.view(np.uint64).reshape(reps, -1), np.tile(bits, (reps, 1))) and ok2.all()
     finally:
         th.close()

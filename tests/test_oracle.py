@@ -104,6 +104,17 @@ def test_thal_restatement_is_bit_exact():
     assert got == want
     temps = [float(l.split("\t")[1]) for l in want.splitlines()]
     assert len(temps) == 709 and sum(t > 45.0 for t in temps) > 300
+    # the limits of the DP: both sides up to 60 bases, long bulges and internal loops
+    assert run(HOSTSIM, ["thal", "thal.params.tsv", "thal_long.pairs.tsv"]) == open(os.path.join(GOLDEN, "thal_long.out.tsv")).read()
+
+
+def test_thal_lane_cooperative_form_is_bit_exact():
+    """thal_end1_tm_lanes -- the arrangement the GPU kernel runs (paired-cell list, LSH / RSH hoisted
+    out of the fill, arg-min over loop partners instead of the sequential scan) -- with one lane on
+    the host, against the reference's results for both golden sets (2209 pairs)."""
+    for name in ("thal", "thal_long"):
+        got = run(HOSTSIM, ["thal2", "thal.params.tsv", name + ".pairs.tsv"])
+        assert got == open(os.path.join(GOLDEN, name + ".out.tsv")).read(), name
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/primer3_config"), reason="needs the reference's primer3_config directory")
