@@ -10,6 +10,9 @@
 // checked) and DG_THAL_SEQ=1 routes everything through it.
 // Built with -fmad=false: results equal the reference's bit for bit.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -38,24 +41,35 @@ struct ThalWarp {   // the Warp concept of dg_thal.cuh on 32 lanes
   __device__ unsigned lanemask_lt() const { return (1u << lane) - 1u; }
   __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
   __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
-  __device__ void argmin(double& g, uint32_t& o, double& S, double& H) const {
-    int who = lane;
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      const double og = __shfl_xor_sync(0xffffffffu, g, off);
-      const uint32_t oo = __shfl_xor_sync(0xffffffffu, o, off);
-      const int ow = __shfl_xor_sync(0xffffffffu, who, off);
-      if (og < g || (og == g && (oo < o || (oo == o && ow < who)))) { g = og; o = oo; who = ow; }
-    }
-    S = __shfl_sync(0xffffffffu, S, who);
-    H = __shfl_sync(0xffffffffu, H, who);
+  __device__ unsigned group_mask(int first_lane, int lanes, bool member) const {
+    if (!member) return 1u << lane;
+    return lanes >= 32 ? 0xffffffffu : (((1u << lanes) - 1u) << first_lane);
+  }
+  // arg-min over the lanes of `mask` by (g, o): three integer min-reductions on an order-preserving
+  // image of the double (callers pass g + 0.0, so there is one zero), then the winner's payload
+  __device__ void argmin(unsigned mask, double& g, uint32_t& o, double& S, double& H) const {
+    const long long b = __double_as_longlong(g);
+    const unsigned long long key = b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ULL);
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mhi = __reduce_min_sync(mask, hi);
+    bool in = hi == mhi;
+    const uint32_t mlo = __reduce_min_sync(mask, in ? lo : 0xffffffffu);
+    in = in && lo == mlo;
+    const uint32_t mo = __reduce_min_sync(mask, in ? o : 0xffffffffu);
+    in = in && o == mo;
+    const unsigned winners = __ballot_sync(mask, in);   // never empty: the lanes holding (mhi, mlo) include one with o == mo
+    const int who = __ffs(winners) - 1;
+    g = __shfl_sync(mask, g, who);
+    o = mo;
+    S = __shfl_sync(mask, S, who);
+    H = __shfl_sync(mask, H, who);
   }
 };
 
-// shared memory of one warp: table (S, H interleaved), one row of RSH terms, the paired-cell list,
-// the row starts, the two encoded sequences
+// shared memory of one warp: table (S, H interleaved), the paired-cell list, the row starts, the
+// two encoded sequences
 __host__ __device__ inline size_t thal_warp_bytes(uint64_t cells) {
-  return (size_t)cells * 16 + 2 * 64 * 8 + (((size_t)cells * 2 + 15) & ~(size_t)15) + 64 * 2 + 64 + 64;
+  return (size_t)cells * 16 + (((size_t)cells * 2 + 15) & ~(size_t)15) + 64 * 2 + 64 + 64;
 }
 
 __global__ void __launch_bounds__(128) k_thal_warp(const ThalParams* __restrict__ p, const uint8_t* __restrict__ s1,
@@ -69,8 +83,7 @@ __global__ void __launch_bounds__(128) k_thal_warp(const ThalParams* __restrict_
   const uint32_t q = ids[t];
   unsigned char* base = smem + (size_t)warp * thal_warp_bytes(cells);
   double* tab = (double*)base;
-  double* rrow = tab + 2 * cells;
-  uint16_t* plist = (uint16_t*)(rrow + 2 * 64);
+  uint16_t* plist = (uint16_t*)(tab + 2 * cells);
   uint16_t* rstart = (uint16_t*)((unsigned char*)plist + (((size_t)cells * 2 + 15) & ~(size_t)15));
   uint8_t* n1 = (uint8_t*)(rstart + 64);
   uint8_t* n2 = n1 + 64;
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(128) k_thal_warp(const ThalParams* __restrict_
   double out = -kThalInf;
   int rc = 0;
   if (len1 <= kThalMaxLen && len2 <= kThalMaxLen && (uint64_t)(len1 > 0 ? len1 : 0) * (uint64_t)(len2 > 0 ? len2 : 0) <= cells)
-    rc = thal_end1_tm_lanes(wp, p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, rrow, plist, rstart, &out);
+    rc = thal_end1_tm_lanes(wp, p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, plist, rstart, &out);
   if (wp.lane == 0) {
     tm[q] = out;
     ok[q] = (uint8_t)rc;   // 2: the sequential kernel recomputes this pair
@@ -172,6 +185,15 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
   try {
     DG_CUDA(cudaSetDevice(t->device));
     cudaStream_t st = t->st;
+    const bool trace = getenv("DG_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) {   // DG_TRACE=1: host wall time per stage (synchronises the stream)
+      if (!trace) return;
+      cudaStreamSynchronize(st);
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[thal] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
     const uint64_t nb1 = off1[n], nb2 = off2[n];
     uint64_t cells = 1;
     for (uint32_t q = 0; q < n; ++q) {
@@ -188,6 +210,7 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
     DG_CUDA(cudaMemcpyAsync(d_s2.p, seq2, nb2, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(d_o1.p, off1, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaMemcpyAsync(d_o2.p, off2, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+    stage("alloc + H2D");
     // the sequential kernel over `ids` (null: all pairs), at most ~2 GiB of scratch per launch
     auto sequential = [&](const uint32_t* ids, uint64_t m) {
       uint64_t per = std::max<uint64_t>(1024, std::min<uint64_t>(m, (2ULL << 30) / (16 * cells)));
@@ -204,33 +227,41 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
     if (seq_env && atoi(seq_env) == 1) {
       sequential(nullptr, n);
     } else {
-      // two size classes so that one long pair does not take the shared memory of all the others
-      constexpr uint64_t kSmall = 768;
-      std::vector<uint32_t> order(n);
-      uint64_t n_small = 0, cells_small = 1;
+      // size classes (by table cells), so that long pairs do not take the shared memory -- and with it
+      // the resident warps -- of all the others
+      static const uint64_t kClass[] = {400, 480, 576, 704, 896, 1280, 2048, 3600};
+      constexpr int kClasses = (int)(sizeof(kClass) / sizeof(kClass[0]));
+      std::vector<uint32_t> order(n), cls(n);
+      uint64_t count[kClasses] = {0}, cap[kClasses] = {0}, start[kClasses + 1] = {0};
+      for (uint32_t q = 0; q < n; ++q) {
+        const uint64_t a = off1[q + 1] - off1[q], b = off2[q + 1] - off2[q];
+        const bool valid = a <= (uint64_t)kThalMaxLen && b <= (uint64_t)kThalMaxLen;
+        int c = 0;
+        while (valid && c + 1 < kClasses && a * b > kClass[c]) ++c;
+        cls[q] = (uint32_t)c;
+        ++count[c];
+        if (valid) cap[c] = std::max(cap[c], a * b);
+      }
+      for (int c = 0; c < kClasses; ++c) start[c + 1] = start[c] + count[c];
       {
-        std::vector<uint32_t> large;
-        for (uint32_t q = 0; q < n; ++q) {
-          const uint64_t a = off1[q + 1] - off1[q], b = off2[q + 1] - off2[q];
-          const bool valid = a <= (uint64_t)kThalMaxLen && b <= (uint64_t)kThalMaxLen;
-          if (valid && a * b > kSmall) large.push_back(q);
-          else { order[n_small++] = q; if (valid) cells_small = std::max(cells_small, a * b); }
-        }
-        std::copy(large.begin(), large.end(), order.begin() + n_small);
+        uint64_t at[kClasses];
+        for (int c = 0; c < kClasses; ++c) at[c] = start[c];
+        for (uint32_t q = 0; q < n; ++q) order[at[cls[q]]++] = q;
       }
       d_ids.alloc(n);
       DG_CUDA(cudaMemcpyAsync(d_ids.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      stage("size classes");
       DG_CUDA(cudaFuncSetAttribute(k_thal_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      auto launch = [&](uint64_t first, uint64_t m, uint64_t cap) {
-        if (!m) return;
-        const size_t per_warp = thal_warp_bytes(cap);
+      for (int c = 0; c < kClasses; ++c) {
+        if (!count[c]) continue;
+        const uint64_t cells_c = std::max<uint64_t>(cap[c], 1);
+        const size_t per_warp = thal_warp_bytes(cells_c);
         const uint32_t wpb = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / per_warp));
-        k_thal_warp<<<(unsigned)((m + wpb - 1) / wpb), wpb * 32, wpb * per_warp, st>>>(t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p,
-                                                                                         d_ids.p + first, (uint32_t)m, cap, d_tm.p, d_ok.p);
-      };
-      launch(0, n_small, cells_small);
-      launch(n_small, n - n_small, cells);
+        k_thal_warp<<<(unsigned)((count[c] + wpb - 1) / wpb), wpb * 32, wpb * per_warp, st>>>(
+            t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p, d_ids.p + start[c], (uint32_t)count[c], cells_c, d_tm.p, d_ok.p);
+      }
       DG_CUDA(cudaGetLastError());
+      stage("k_thal_warp");
       const bool force_redo = seq_env && atoi(seq_env) == 2;   // test hook: treat every pair as declined
       std::vector<uint8_t> flags(n);
       DG_CUDA(cudaMemcpyAsync(flags.data(), d_ok.p, n, cudaMemcpyDeviceToHost, st));
@@ -247,6 +278,7 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
     DG_CUDA(cudaMemcpyAsync(tm, d_tm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(ok, d_ok.p, n, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
+    stage("D2H");
     return DG_OK;
   } catch (CudaFail& e) {
     return e.code;

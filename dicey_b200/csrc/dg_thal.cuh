@@ -185,10 +185,12 @@ DG_HD void thal_loop(const ThalWork& w, int i, int j, int ii, int jj, bool trace
 }
 
 // maxTM(i, j): keep the cell, or extend the stack from (i-1, j-1), whichever melts higher.
-// (rs, rh) = RSH(i, j).
-DG_HD void thal_stack_rs(const ThalWork& w, int i, int j, double rs, double rh) {
+// (rs, rh) = RSH(i, j).  Returns the cell's new value.
+DG_HD void thal_stack_value(const ThalWork& w, int i, int j, double rs, double rh, double& oS, double& oH) {
   const ThalParams& p = *w.p;
   double S0 = w.S(i, j), H0 = w.H(i, j), S1, H1, T1;
+  oS = S0;
+  oH = H0;
   const double T0 = (H0 + kThalInitH + rh) / (S0 + kThalInitS + rs + w.rc);
   const int k = thal_i4(w.n1[i - 1], w.n1[i], w.n2[j - 1], w.n2[j]);
   if (thal_fin(w.H(i - 1, j - 1)) && thal_fin(p.stackH[k])) {
@@ -202,8 +204,14 @@ DG_HD void thal_stack_rs(const ThalWork& w, int i, int j, double rs, double rh) 
   }
   if (S1 < kThalMinEntropyCutoff) { S1 = kThalMinEntropy; H1 = 0.0; }
   if (S0 < kThalMinEntropyCutoff) { S0 = kThalMinEntropy; H0 = 0.0; }
-  if (T1 > T0) { w.S(i, j) = S1; w.H(i, j) = H1; }
-  else if (T0 >= T1) { w.S(i, j) = S0; w.H(i, j) = H0; }
+  if (T1 > T0) { oS = S1; oH = H1; }
+  else if (T0 >= T1) { oS = S0; oH = H0; }
+}
+DG_HD void thal_stack_rs(const ThalWork& w, int i, int j, double rs, double rh) {
+  double S, H;
+  thal_stack_value(w, i, j, rs, rh, S, H);
+  w.S(i, j) = S;
+  w.H(i, j) = H;
 }
 DG_HD void thal_stack(const ThalWork& w, int i, int j) {
   double rs, rh;
@@ -325,20 +333,22 @@ DG_HD bool thal_end1_tm(const ThalParams* p, const uint8_t* o1, int len1, const 
 //   * only cells whose bases pair are ever finite, so the fill walks a row-major list of paired
 //     cells instead of the whole table;
 //   * LSH (thal_left) and RSH (thal_right) depend on the sequences alone: LSH seeds the table for
-//     all paired cells at once, RSH is evaluated once per row;
+//     all paired cells at once, RSH is evaluated once per cell;
+//   * a cell reads only cells above and to the left of it, so the cells of one row are independent:
+//     the lanes split into one group per paired cell of the row and the groups work side by side;
 //   * for one cell the reference scans its loop partners (ii, jj) in a fixed order and keeps a
 //     candidate when its free energy is strictly below that of the cell's current value, which
 //     then becomes the candidate -- a running strict minimum.  Its outcome is the first partner
 //     in scan order that attains the overall minimum, if that is below the starting value; the
-//     lanes evaluate partners independently and an arg-min over (energy, scan rank) picks it.
-//     Two things would break that equivalence and make the function return 2 ("use the
-//     sequential form"): a candidate entropy below the -2500 cutoff (the reference then stores
-//     a substitute value), which no pair of sequences within the length limit produces;
+//     lanes of a group evaluate partners independently and an arg-min over (energy, scan rank)
+//     picks it.  One thing would break that equivalence and makes the function return 2 ("use
+//     the sequential form"): a candidate entropy below the -2500 cutoff (the reference then
+//     stores a substitute value), which no pair of sequences within the length limit produces;
 //   * the traceback looks for the first partner in scan order whose value reproduces the cell:
 //     the same arg-min with a constant energy.
 // Warp concept: static n (lanes), lane, sync(), ballot(p), lanemask_lt(), all(p), any(p),
-// argmin(g, order, S, H) -- after it every lane holds the (g, order) minimum (ties: lower order)
-// and that lane's S, H.
+// group_mask(first_lane, lanes, member), argmin(mask, g, order, S, H) -- after it every lane of
+// the group `mask` holds the group's (g, order) minimum (ties: lower order) and that lane's S, H.
 struct ThalOneLane {
   static constexpr int n = 1;
   int lane = 0;
@@ -347,7 +357,8 @@ struct ThalOneLane {
   DG_HD unsigned lanemask_lt() const { return 0u; }
   DG_HD bool all(bool p) const { return p; }
   DG_HD bool any(bool p) const { return p; }
-  DG_HD void argmin(double&, uint32_t&, double&, double&) const {}
+  DG_HD unsigned group_mask(int, int, bool) const { return 1u; }
+  DG_HD void argmin(unsigned, double&, uint32_t&, double&, double&) const {}
 };
 
 constexpr uint32_t kThalNone = 0xFFFFFFFFu;
@@ -360,13 +371,14 @@ DG_HD int thal_popc(unsigned x) {
 }
 
 // Work areas: num1 / num2 len + 2 bytes; tab 2 * len1 * len2 doubles (S, H interleaved);
-// rrow 2 * (len2 + 1) doubles; plist len1 * len2 entries; rstart len1 + 2 entries.
+// plist len1 * len2 entries; rstart len1 + 2 entries.
 // Returns 0 where the reference's thal() fails, 1 with *tm set, 2 for "use thal_end1_tm".
 template <class Warp>
 DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
-                             uint8_t* num2, double* tab, double* rrow, uint16_t* plist, uint16_t* rstart, double* tm) {
+                             uint8_t* num2, double* tab, uint16_t* plist, uint16_t* rstart, double* tm) {
   constexpr int n = Warp::n;
   const int lane = wp.lane;
+  const unsigned everyone = wp.group_mask(0, n, true);
   *tm = -kThalInf;
   if (len1 <= 0 || len2 <= 0) { *tm = 0.0; return 0; }
   if (len1 > kThalMaxLen || len2 > kThalMaxLen) return 0;
@@ -413,52 +425,49 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
     if (thal_fin(h)) { w.S(i, j) = s; w.H(i, j) = h; }
   }
   wp.sync();
-  // fillMatrix over the paired cells
+  // fillMatrix, one row of paired cells at a time
   bool odd = false;
-  int row = 0;
-  for (int m = 0; m < np; ++m) {
-    const int i = plist[m] >> 8, j = plist[m] & 0xff;
-    if (i != row) {   // RSH of this row
-      row = i;
+  for (int i = 2; i <= len1; ++i) {
+    const int r0 = rstart[i], r1 = rstart[i + 1];
+    const int lo = rstart[i > kThalMaxLoop + 1 ? i - (kThalMaxLoop + 1) : 1], hi = r0;
+    for (int c0 = r0; c0 < r1; c0 += n) {
+      const int cells = r1 - c0 < n ? r1 - c0 : n;
+      const int gsize = n / cells, g = lane / gsize, gl = lane - g * gsize;
+      const bool member = g < cells;
+      const unsigned gmask = wp.group_mask(g * gsize, gsize, member);
+      const int j = member ? (plist[c0 + g] & 0xff) : 0;
+      const bool live = member && j > 1 && thal_fin(w.H(i, j));
+      double cs = -1.0, ch = kThalInf, rs = -1.0, rh = kThalInf, G2 = 0.0;
+      double bestG = 1e300, bS = -1.0, bH = kThalInf;
+      uint32_t bestO = kThalNone;
+      if (live) {
+        thal_right(w, i, j, rs, rh);
+        thal_stack_value(w, i, j, rs, rh, cs, ch);
+        G2 = thal_loop_energy(cs, ch, rs, rh);
+        for (int e = lo + gl; e < hi; e += gsize) {
+          const int ii = plist[e] >> 8, jj = plist[e] & 0xff;
+          const int d = (i - ii) + (j - jj);
+          if (jj >= j || d < 3 || d > kThalMaxLoop + 2) continue;
+          if (!thal_fin(w.H(ii, jj))) continue;
+          double S, H;
+          thal_loop_value(w, ii, jj, i, j, S, H);
+          if (!thal_fin(H)) continue;                    // never stored by the reference
+          if (S < kThalMinEntropyCutoff) odd = true;
+          const double G1 = thal_loop_energy(S, H, rs, rh) + 0.0;   // (+ 0.0: one zero for the bitwise arg-min)
+          const uint32_t order = ((uint32_t)d << 6) | (uint32_t)(i - 1 - ii);
+          if (bestO == kThalNone || G1 < bestG || (G1 == bestG && order < bestO)) { bestG = G1; bestO = order; bS = S; bH = H; }
+        }
+      }
       wp.sync();
-      for (int e = rstart[i] + lane; e < rstart[i + 1]; e += n) {
-        const int jj = plist[e] & 0xff;
-        double rs, rh;
-        thal_right(w, i, jj, rs, rh);
-        rrow[2 * jj] = rs;
-        rrow[2 * jj + 1] = rh;
+      wp.argmin(gmask, bestG, bestO, bS, bH);
+      if (live && gl == 0) {
+        const bool take = bestO != kThalNone && bestG < G2;
+        w.S(i, j) = take ? bS : cs;
+        w.H(i, j) = take ? bH : ch;
       }
       wp.sync();
     }
-    if (i == 1 || j == 1) continue;
-    if (!thal_fin(w.H(i, j))) continue;
-    const double rs = rrow[2 * j], rh = rrow[2 * j + 1];
-    wp.sync();
-    thal_stack_rs(w, i, j, rs, rh);   // every lane stores the same value
-    wp.sync();
-    const double G2 = thal_loop_energy(w.S(i, j), w.H(i, j), rs, rh);
-    double bestG = 0.0, bS = -1.0, bH = kThalInf;
-    uint32_t bestO = kThalNone;
-    const int lo = rstart[i > kThalMaxLoop + 1 ? i - (kThalMaxLoop + 1) : 1], hi = rstart[i];
-    for (int e = lo + lane; e < hi; e += n) {
-      const int ii = plist[e] >> 8, jj = plist[e] & 0xff;
-      const int d = (i - ii) + (j - jj);
-      if (jj >= j || d < 3 || d > kThalMaxLoop + 2) continue;
-      if (!thal_fin(w.H(ii, jj))) continue;
-      double S, H;
-      thal_loop_value(w, ii, jj, i, j, S, H);
-      if (!thal_fin(H)) continue;                    // never stored by the reference
-      if (S < kThalMinEntropyCutoff) odd = true;
-      const double G1 = thal_loop_energy(S, H, rs, rh);
-      const uint32_t order = ((uint32_t)d << 6) | (uint32_t)(i - 1 - ii);
-      if (bestO == kThalNone || G1 < bestG || (G1 == bestG && order < bestO)) { bestG = G1; bestO = order; bS = S; bH = H; }
-    }
-    if (bestO == kThalNone) bestG = 1e300;
-    wp.argmin(bestG, bestO, bS, bH);
-    if (bestO != kThalNone && bestG < G2) { w.S(i, j) = bS; w.H(i, j) = bH; }
-    // (wp.sync() at the top of the next iteration orders this store)
   }
-  wp.sync();
   if (wp.any(odd)) return 2;
   // the most stable structure ending at the 3' end of the first sequence
   int bestI = len1, bestJ = 0;
@@ -466,14 +475,15 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
     double bestG = 1e300, dS_ = 0.0, dH_ = 0.0;
     uint32_t bestO = kThalNone;
     for (int j = 1 + lane; j <= len2; j += n) {
-      const bool pr = thal_bp(num1[len1], num2[j]) != 0;
-      double s = pr ? rrow[2 * j] : -1.0, h = pr ? rrow[2 * j + 1] : kThalInf;
+      double s, h;
+      thal_right(w, len1, j, s, h);
       s = s + 0.000001;
       h = h + 0.000001;
-      const double G1 = (w.H(len1, j) + h + kThalInitH) - kThalTempK * (w.S(len1, j) + s + kThalInitS);
+      const double G1 = ((w.H(len1, j) + h + kThalInitH) - kThalTempK * (w.S(len1, j) + s + kThalInitS)) + 0.0;
       if (G1 < kThalInf && (bestO == kThalNone || G1 < bestG)) { bestG = G1; bestO = (uint32_t)j; }
     }
-    wp.argmin(bestG, bestO, dS_, dH_);
+    wp.sync();
+    wp.argmin(everyone, bestG, bestO, dS_, dH_);
     if (bestO != kThalNone && thal_fin(bestG)) bestJ = (int)bestO;
     else bestI = bestJ = 1;
   }
@@ -486,7 +496,6 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
   int paired = 2, i = bestI, j = bestJ;
   for (int guard = 0; guard < 4 * (len1 + len2); ++guard) {
     double s = -1.0, h = kThalInf;
-    wp.sync();
     if (thal_bp(num1[i], num2[j])) thal_left(w, i, j, s, h);   // (a finite cell always pairs)
     const double cs = w.S(i, j), ch = w.H(i, j);
     if (cs == s && ch == h) break;
@@ -510,7 +519,8 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
       const uint32_t order = ((uint32_t)d << 6) | (uint32_t)(i - 1 - ii);
       if (cs == S && ch == H && order < bestO) bestO = order;
     }
-    wp.argmin(g, bestO, dS_, dH_);
+    wp.sync();
+    wp.argmin(everyone, g, bestO, dS_, dH_);
     if (bestO == kThalNone) break;   // (the reference would spin here; never observed)
     const int d = (int)(bestO >> 6), ii = i - 1 - (int)(bestO & 63);
     j = j - (d - (i - ii));

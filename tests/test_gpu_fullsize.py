@@ -325,7 +325,8 @@ def test_config3_search_end_to_end(big, fm9, tmp_path):
     cfg = write_primer3_config(os.path.join(d, "p3cfg"))
     rng = np.random.default_rng(17)
     with open(os.path.join(d, "primers.fa"), "w") as f:
-        for i in range(24):
+        npairs = int(os.environ.get("DG_SEARCH_PAIRS", "24"))   # BASELINE config 3 is 1000 (the reference then needs minutes)
+        for i in range(npairs):
             chrom, off, alen = int(rng.integers(0, NREC)), int(rng.integers(0, RECLEN - 5000)), int(rng.integers(150, 3000))
             L1, L2 = int(rng.integers(18, 25)), int(rng.integers(18, 25))
             fw = bytearray(window(chrom, off + 1, L1))
@@ -337,12 +338,13 @@ def test_config3_search_end_to_end(big, fm9, tmp_path):
     want = subprocess.run([REF_BIN, "search", path, rec, os.path.join(d, "primers.fa"), cfg], check=True, capture_output=True, text=True).stdout
     t1 = time.time()
     got = subprocess.run([os.path.join(ROOT, "dicey_b200", "dicey-b200"), "search", "-g", "genome.fa.gz", "-i", cfg, "primers.fa"],
-                         cwd=d, capture_output=True, text=True)
+                         cwd=d, capture_output=True, text=True, env=dict(os.environ, DICEY_B200_TRACE="1"))
     t2 = time.time()
     assert got.returncode == 0, got.stderr
     import json
     j = json.loads(want)
-    print(f"[fullsize] search, 48 primers: reference {t1 - t0:.1f} s, dicey-b200 {t2 - t1:.1f} s (index load included); "
+    print(f"[fullsize] search, {2 * npairs} primers: reference {t1 - t0:.1f} s, dicey-b200 {t2 - t1:.1f} s (index load included); "
           f"{len(j['data']['primers'])} binding sites, {len(j['data']['amplicons'])} amplicons")
-    assert len(j["data"]["amplicons"]) >= 20
+    print(got.stderr)
+    assert len(j["data"]["amplicons"]) >= npairs * 5 // 6
     assert got.stdout == want
