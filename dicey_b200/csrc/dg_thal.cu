@@ -29,6 +29,7 @@ struct dg_thal {
   cudaStream_t st = nullptr;
   ThalParams* d_params = nullptr;
   ThalParams h_params;
+  int sms = 148;
 };
 
 namespace {
@@ -69,7 +70,7 @@ struct ThalWarp {   // the Warp concept of dg_thal.cuh on 32 lanes
 // shared memory of one warp: table (S, H interleaved), the paired-cell list, the row starts, the
 // two encoded sequences
 __host__ __device__ inline size_t thal_warp_bytes(uint64_t cells) {
-  return (size_t)cells * 16 + (((size_t)cells * 2 + 15) & ~(size_t)15) + 64 * 2 + 64 + 64;
+  return (size_t)cells * 16 + (((size_t)cells * 2 + 15) & ~(size_t)15) + 64 * 2 + 64 + 64 + 256;
 }
 
 __global__ void __launch_bounds__(128) k_thal_warp(const ThalParams* __restrict__ p, const uint8_t* __restrict__ s1,
@@ -78,25 +79,30 @@ __global__ void __launch_bounds__(128) k_thal_warp(const ThalParams* __restrict_
                                                    uint64_t cells, double* __restrict__ tm, uint8_t* __restrict__ ok) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  const uint32_t t = blockIdx.x * wpb + warp;
-  if (t >= count) return;
-  const uint32_t q = ids[t];
   unsigned char* base = smem + (size_t)warp * thal_warp_bytes(cells);
   double* tab = (double*)base;
   uint16_t* plist = (uint16_t*)(tab + 2 * cells);
   uint16_t* rstart = (uint16_t*)((unsigned char*)plist + (((size_t)cells * 2 + 15) & ~(size_t)15));
   uint8_t* n1 = (uint8_t*)(rstart + 64);
   uint8_t* n2 = n1 + 64;
-  const int len1 = (int)(off1[q + 1] - off1[q]), len2 = (int)(off2[q + 1] - off2[q]);
+  uint8_t* codes = n2 + 64;
   ThalWarp wp;
   wp.lane = threadIdx.x & 31;
-  double out = -kThalInf;
-  int rc = 0;
-  if (len1 <= kThalMaxLen && len2 <= kThalMaxLen && (uint64_t)(len1 > 0 ? len1 : 0) * (uint64_t)(len2 > 0 ? len2 : 0) <= cells)
-    rc = thal_end1_tm_lanes(wp, p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, plist, rstart, &out);
-  if (wp.lane == 0) {
-    tm[q] = out;
-    ok[q] = (uint8_t)rc;   // 2: the sequential kernel recomputes this pair
+  // the warps of the grid share the pairs round-robin (the grid is sized to what is resident at once)
+  for (uint32_t t = blockIdx.x * wpb + warp; t < count; t += gridDim.x * wpb) {
+    const uint32_t q = ids[t];
+    const int len1 = (int)(off1[q + 1] - off1[q]), len2 = (int)(off2[q + 1] - off2[q]);
+    double out = -kThalInf;
+    int rc = 0;
+    __syncwarp();
+    if (len1 <= kThalMaxLen && len2 <= kThalMaxLen && (uint64_t)(len1 > 0 ? len1 : 0) * (uint64_t)(len2 > 0 ? len2 : 0) <= cells)
+      rc = thal_end1_tm_lanes(wp, p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, plist, rstart, codes, &out);
+    else if (len1 <= 0 || len2 <= 0)
+      out = 0.0;
+    if (wp.lane == 0) {
+      tm[q] = out;
+      ok[q] = (uint8_t)rc;   // 2: the sequential kernel recomputes this pair
+    }
   }
 }
 
@@ -132,6 +138,7 @@ int finish_open(dg_thal* t, int device, dg_thal** out) {
     DG_CUDA(cudaSetDevice(device));
     t->device = device;
     DG_CUDA(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+    DG_CUDA(cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, device));
     DG_CUDA(cudaMalloc((void**)&t->d_params, sizeof(ThalParams)));
     DG_CUDA(cudaMemcpy(t->d_params, &t->h_params, sizeof(ThalParams), cudaMemcpyHostToDevice));
   } catch (CudaFail& e) {
@@ -257,7 +264,10 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
         const uint64_t cells_c = std::max<uint64_t>(cap[c], 1);
         const size_t per_warp = thal_warp_bytes(cells_c);
         const uint32_t wpb = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / per_warp));
-        k_thal_warp<<<(unsigned)((count[c] + wpb - 1) / wpb), wpb * 32, wpb * per_warp, st>>>(
+        int resident = 1;
+        DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_thal_warp, (int)(wpb * 32), wpb * per_warp));
+        const uint64_t grid = std::min<uint64_t>((count[c] + wpb - 1) / wpb, (uint64_t)std::max(resident, 1) * (uint64_t)t->sms);
+        k_thal_warp<<<(unsigned)grid, wpb * 32, wpb * per_warp, st>>>(
             t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p, d_ids.p + start[c], (uint32_t)count[c], cells_c, d_tm.p, d_ok.p);
       }
       DG_CUDA(cudaGetLastError());

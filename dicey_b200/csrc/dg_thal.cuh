@@ -327,6 +327,67 @@ DG_HD bool thal_end1_tm(const ThalParams* p, const uint8_t* o1, int len1, const 
 }
 
 
+// thal_loop_value with everything that depends on the right-hand cell (ii, jj) alone looked up
+// once (the lanes form evaluates many left-hand partners (i, j) against one right-hand cell), and
+// the 4-base table indices composed from per-position base-pair codes:
+//   a1[i] = n1[i] * 5 + n1[i + 1]   ra[i] = n1[i] * 5 + n1[i - 1]
+//   b[j]  = n2[j] * 5 + n2[j + 1]   rb[j] = n2[j] * 5 + n2[j - 1]
+// Same additions in the same order as thal_loop_value.
+struct ThalRight {
+  double tsS, tsH, i2S, i2H, atS, atH;   // tstack / int2 at (n2[jj], n2[jj-1], n1[ii], n1[ii-1]); AT penalty of (ii, jj)
+  int mix;                               // n1[ii] * 25 + n2[jj]
+};
+DG_HD void thal_right_consts(const ThalWork& w, const uint8_t* ra, const uint8_t* rb, int ii, int jj, ThalRight& c) {
+  const ThalParams& p = *w.p;
+  const int k = rb[jj] * 25 + ra[ii];
+  c.tsS = p.tstackS[k]; c.tsH = p.tstackH[k];
+  c.i2S = p.int2S[k]; c.i2H = p.int2H[k];
+  c.atS = p.atpS[w.n1[ii] * 5 + w.n2[jj]]; c.atH = p.atpH[w.n1[ii] * 5 + w.n2[jj]];
+  c.mix = w.n1[ii] * 25 + w.n2[jj];
+}
+DG_HD void thal_loop_value_right(const ThalWork& w, const uint8_t* a1, const uint8_t* b, const ThalRight& c, int i, int j, int ii, int jj,
+                                 double& S, double& H) {
+  const ThalParams& p = *w.p;
+  const int l1 = ii - i - 1, l2 = jj - j - 1, ls = l1 + l2 - 1;
+  const double cS = w.S(i, j), cH = w.H(i, j);
+  if (l1 == 0 || l2 == 0) {        // (not both: the caller's d >= 3)
+    if (l2 == 1 || l1 == 1) {
+      const int k = w.n1[i] * 125 + w.n2[j] * 5 + c.mix;
+      H = p.bulgeH[ls] + p.stackH[k];
+      S = p.bulgeS[ls] + p.stackS[k];
+      if (H > 0 || S > 0) { H = kThalInf; S = -1.0; }
+      H += cH;
+      S += cS;
+      if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+    } else {
+      const int k = w.n1[i] * 5 + w.n2[j];
+      H = p.bulgeH[ls] + p.atpH[k] + c.atH;
+      H += cH;
+      S = p.bulgeS[ls] + p.atpS[k] + c.atS;
+      S += cS;
+      if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+      if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
+    }
+  } else if (l1 == 1 && l2 == 1) {
+    const int k = a1[i] * 25 + b[j];
+    S = p.int2S[k] + c.i2S;
+    S += cS;
+    H = p.int2H[k] + c.i2H;
+    H += cH;
+    if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+    if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
+  } else {
+    const int k = a1[i] * 25 + b[j];
+    const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+    H = p.intlH[ls] + p.tstackH[k] + c.tsH + (0.0 * asym);
+    H += cH;
+    S = p.intlS[ls] + p.tstackS[k] + c.tsS + (kThalIlas * asym);
+    S += cS;
+    if (!thal_fin(H)) { H = kThalInf; S = -1.0; }
+    if (H > 0 && S > 0) { H = kThalInf; S = -1.0; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // The same computation arranged for a group of cooperating lanes (a warp on the device, one lane
 // in the host build that the CPU tests run):
@@ -371,11 +432,11 @@ DG_HD int thal_popc(unsigned x) {
 }
 
 // Work areas: num1 / num2 len + 2 bytes; tab 2 * len1 * len2 doubles (S, H interleaved);
-// plist len1 * len2 entries; rstart len1 + 2 entries.
+// plist len1 * len2 entries; rstart len1 + 2 entries; codes 4 * 64 bytes.
 // Returns 0 where the reference's thal() fails, 1 with *tm set, 2 for "use thal_end1_tm".
 template <class Warp>
 DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
-                             uint8_t* num2, double* tab, uint16_t* plist, uint16_t* rstart, double* tm) {
+                             uint8_t* num2, double* tab, uint16_t* plist, uint16_t* rstart, uint8_t* codes, double* tm) {
   constexpr int n = Warp::n;
   const int lane = wp.lane;
   const unsigned everyone = wp.group_mask(0, n, true);
@@ -386,6 +447,15 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
   for (int j = 1 + lane; j <= len2; j += n) num2[j] = (uint8_t)thal_code(o2[len2 - j]);
   if (lane == 0) num1[0] = num1[len1 + 1] = num2[0] = num2[len2 + 1] = 4;
   wp.sync();
+  uint8_t *a1 = codes, *ra = codes + 64, *b = codes + 128, *rb = codes + 192;
+  for (int i = 1 + lane; i <= len1; i += n) {
+    a1[i] = (uint8_t)(num1[i] * 5 + num1[i + 1]);
+    ra[i] = (uint8_t)(num1[i] * 5 + num1[i - 1]);
+  }
+  for (int j = 1 + lane; j <= len2; j += n) {
+    b[j] = (uint8_t)(num2[j] * 5 + num2[j + 1]);
+    rb[j] = (uint8_t)(num2[j] * 5 + num2[j - 1]);
+  }
   bool sym = (len1 % 2 == 0) && (len2 % 2 == 0);
   if (sym) {
     bool mine = true;
@@ -444,13 +514,15 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
         thal_right(w, i, j, rs, rh);
         thal_stack_value(w, i, j, rs, rh, cs, ch);
         G2 = thal_loop_energy(cs, ch, rs, rh);
+        ThalRight rc;
+        thal_right_consts(w, ra, rb, i, j, rc);
         for (int e = lo + gl; e < hi; e += gsize) {
           const int ii = plist[e] >> 8, jj = plist[e] & 0xff;
           const int d = (i - ii) + (j - jj);
           if (jj >= j || d < 3 || d > kThalMaxLoop + 2) continue;
           if (!thal_fin(w.H(ii, jj))) continue;
           double S, H;
-          thal_loop_value(w, ii, jj, i, j, S, H);
+          thal_loop_value_right(w, a1, b, rc, ii, jj, i, j, S, H);
           if (!thal_fin(H)) continue;                    // never stored by the reference
           if (S < kThalMinEntropyCutoff) odd = true;
           const double G1 = thal_loop_energy(S, H, rs, rh) + 0.0;   // (+ 0.0: one zero for the bitwise arg-min)
@@ -510,12 +582,14 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
     double g = 0.0, dS_ = 0.0, dH_ = 0.0;
     uint32_t bestO = kThalNone;
     const int lo = rstart[i > kThalMaxLoop + 1 ? i - (kThalMaxLoop + 1) : 1], hi = rstart[i];
+    ThalRight rc;
+    thal_right_consts(w, ra, rb, i, j, rc);
     for (int e = lo + lane; e < hi; e += n) {
       const int ii = plist[e] >> 8, jj = plist[e] & 0xff;
       const int d = (i - ii) + (j - jj);
       if (jj >= j || d < 3 || d > kThalMaxLoop + 2) continue;
       double S, H;
-      thal_loop_value(w, ii, jj, i, j, S, H);
+      thal_loop_value_right(w, a1, b, rc, ii, jj, i, j, S, H);
       const uint32_t order = ((uint32_t)d << 6) | (uint32_t)(i - 1 - ii);
       if (cs == S && ch == H && order < bestO) bestO = order;
     }

@@ -157,13 +157,13 @@ int main(int argc, char** argv) {
       if (t == std::string::npos) continue;
       std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
       const size_t cells = o1.size() * o2.size();
-      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2);
+      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2), codes(256);
       std::vector<double> tab(2 * cells + 2);
       std::vector<uint16_t> plist(cells + 1), rstart(o1.size() + 2);
       double tm = 0;
       ThalOneLane wp;
       int rc = thal_end1_tm_lanes(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(), n1.data(),
-                                  n2.data(), tab.data(), plist.data(), rstart.data(), &tm);
+                                  n2.data(), tab.data(), plist.data(), rstart.data(), codes.data(), &tm);
       if (rc == 2) { fprintf(stderr, "sequential form requested\n"); return 3; }
       uint64_t u;
       memcpy(&u, &tm, 8);
