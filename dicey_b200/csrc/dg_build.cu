@@ -12,6 +12,7 @@
 //               (construct_bwt.hpp:35-71), SA samples every 32 rows, ISA samples every 64 positions
 //               (csa_sampling_strategy.hpp:70-93, 669-706).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
@@ -60,6 +61,19 @@ __device__ __forceinline__ uint64_t rank1_v(const WtView& w, uint64_t idx) {
   uint64_t r = p[0] + ((p[1] >> (63 - 9 * ((idx & 0x1FF) >> 6))) & 0x1FF);
   if (idx & 0x3F) r += __popcll(w.bv[idx >> 6] & ((1ULL << (idx & 0x3F)) - 1));
   return r;
+}
+
+// int_vector<0> -> u32: entry i occupies bits [i * width, (i + 1) * width) of the word stream
+// (int_vector.hpp:813-842; one zero word follows the payload)
+__global__ void k_unpack_ints(const uint64_t* __restrict__ words, uint64_t count, uint32_t width, uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t bit = i * width, word = bit >> 6;
+  const uint32_t off = (uint32_t)(bit & 63);
+  uint64_t v = words[word] >> off;
+  if (off + width > 64) v |= words[word + 1] << (64 - off);
+  if (width < 64) v &= (1ULL << width) - 1;
+  out[i] = (uint32_t)v;
 }
 
 __global__ void k_decode_bwt(WtView w, uint64_t n, uint8_t* __restrict__ out) {
@@ -603,9 +617,18 @@ static dg_index* new_index(int device) {
 }
 
 int build_from_fm9(const char* path, int device, dg_index** out) {
+  const bool trace = getenv("DG_TRACE") != nullptr;   // wall time of every load stage on stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char* what) {
+    if (!trace) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[load] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   Fm9 f;
   std::string err;
   int rc = fm9_parse(path, f, err);
+  stage("read + parse .fm9");
   if (rc) { set_error(err); return rc; }
   if (f.n >= (1ULL << 32) - 64) { set_error("text longer than 2^32 - 64 symbols is outside the device path"); return DG_ERR_UNSUPPORTED; }
   if (f.n < 2 || f.nodes.empty()) { set_error("empty index"); return DG_ERR_FORMAT; }
@@ -634,10 +657,10 @@ int build_from_fm9(const char* path, int device, dg_index** out) {
       }
       DevBuf<uint64_t> d_bv, d_bb, d_bvp, d_bvr;
       DevBuf<uint16_t> d_c0, d_c1;
-      d_bv.alloc(f.bv.size() + 1); d_bb.alloc(f.rank_bb.size()); d_bvp.alloc(nn); d_bvr.alloc(nn); d_c0.alloc(nn); d_c1.alloc(nn);
-      DG_CUDA(cudaMemcpyAsync(d_bv.p, f.bv.data(), f.bv.size() * 8, cudaMemcpyHostToDevice, st));
-      DG_CUDA(cudaMemsetAsync(d_bv.p + f.bv.size(), 0, 8, st));
-      DG_CUDA(cudaMemcpyAsync(d_bb.p, f.rank_bb.data(), f.rank_bb.size() * 8, cudaMemcpyHostToDevice, st));
+      d_bv.alloc(f.bv.words + 1); d_bb.alloc(f.rank_bb.words ? f.rank_bb.words : 1); d_bvp.alloc(nn); d_bvr.alloc(nn); d_c0.alloc(nn); d_c1.alloc(nn);
+      if (f.bv.words) DG_CUDA(cudaMemcpyAsync(d_bv.p, f.bv.p, f.bv.bytes(), cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemsetAsync(d_bv.p + f.bv.words, 0, 8, st));
+      if (f.rank_bb.words) DG_CUDA(cudaMemcpyAsync(d_bb.p, f.rank_bb.p, f.rank_bb.bytes(), cudaMemcpyHostToDevice, st));
       DG_CUDA(cudaMemcpyAsync(d_bvp.p, bvp.data(), nn * 8, cudaMemcpyHostToDevice, st));
       DG_CUDA(cudaMemcpyAsync(d_bvr.p, bvr.data(), nn * 8, cudaMemcpyHostToDevice, st));
       DG_CUDA(cudaMemcpyAsync(d_c0.p, c0.data(), nn * 2, cudaMemcpyHostToDevice, st));
@@ -648,24 +671,31 @@ int build_from_fm9(const char* path, int device, dg_index** out) {
       DG_CUDA(cudaGetLastError());
       DG_CUDA(cudaStreamSynchronize(st));
     }
-    f.bv.clear(); f.bv.shrink_to_fit();
-    f.rank_bb.clear(); f.rank_bb.shrink_to_fit();
+    stage("context, wavelet tree -> BWT");
     finish_from_bwt(ix, bwt.p, Cb, present);
     bwt.release();
-    // SA / ISA samples: unpack the int_vector<0> payloads to u32
+    stage("occ blocks, exceptions");
+    // SA / ISA samples: the packed int_vector<0> payloads go up as they are and are widened to u32 there
     {
-      std::vector<uint32_t> s(f.sa_count);
-      for (uint64_t i = 0; i < f.sa_count; ++i) s[i] = (uint32_t)fm9_get_int(f.sa_words, i, f.sa_width);
+      DevBuf<uint64_t> packed;
+      packed.alloc(std::max(f.sa_words.words, f.isa_words.words) + 1);
+      auto unpack = [&](const Fm9Span& sp, uint64_t count, uint8_t width, uint32_t* dst) {
+        if (sp.words) DG_CUDA(cudaMemcpyAsync(packed.p, sp.p, sp.bytes(), cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemsetAsync(packed.p + sp.words, 0, 8, st));
+        k_unpack_ints<<<grid_for(count, 256), 256, 0, st>>>(packed.p, count, width, dst);
+        DG_CUDA(cudaGetLastError());
+      };
       ix->sa_samples.alloc(f.sa_count);
-      DG_CUDA(cudaMemcpyAsync(ix->sa_samples.p, s.data(), f.sa_count * 4, cudaMemcpyHostToDevice, st));
-      DG_CUDA(cudaStreamSynchronize(st));
-      s.resize(f.isa_count + 1);
-      for (uint64_t i = 0; i < f.isa_count; ++i) s[i] = (uint32_t)fm9_get_int(f.isa_words, i, f.isa_width);
+      unpack(f.sa_words, f.sa_count, f.sa_width, ix->sa_samples.p);
       ix->isa_samples.alloc(f.isa_count + 1);
-      DG_CUDA(cudaMemcpyAsync(ix->isa_samples.p, s.data(), f.isa_count * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemsetAsync(ix->isa_samples.p + f.isa_count, 0, 4, st));
+      unpack(f.isa_words, f.isa_count, f.isa_width, ix->isa_samples.p);
       DG_CUDA(cudaStreamSynchronize(st));
     }
+    f.unmap();
+    stage("SA / ISA samples");
     build_kmer_table(ix);
+    stage("k-mer interval table");
     // text from the ISA samples
     ix->text.alloc(f.n + 64);
     DG_CUDA(cudaMemsetAsync(ix->text.p, 0, f.n + 64, st));
@@ -676,7 +706,9 @@ int build_from_fm9(const char* path, int device, dg_index** out) {
     k_rebuild_text<<<grid_for(nchains, 128), 128, 0, st>>>(wv, ix->isa_samples.p, nchains, ix->text.p, ix->sa_full.p);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaStreamSynchronize(st));
+    stage("text + full suffix array");
     build_presence_bitmap(ix);
+    stage("presence bitmaps");
     *out = ix;
     return DG_OK;
   } catch (CudaFail& e) {

@@ -9,6 +9,11 @@
 // csa_alphabet_strategy.hpp:233-244, int_vector.hpp:813-842,1812-1838).  Nothing of SDSL is
 // included or linked; this is a byte-level parser of the layout written down in SURVEY.md 5.9.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -25,22 +30,43 @@ struct Fm9Node {  // wt_helper.hpp:121-125 (_node<byte_tree>), 22 bytes on disk
   uint16_t child[2];
 };
 
+// The large payloads stay where the kernel's page cache has them: the file is mapped read-only
+// and the spans below point into the mapping (they may be unaligned: copy, do not dereference).
+struct Fm9Span {
+  const uint8_t* p = nullptr;
+  uint64_t words = 0;   // 64-bit words
+  uint64_t bytes() const { return words * 8; }
+};
+
 struct Fm9 {
   uint64_t n = 0;         // wt.m_size == csa.size() (text length incl. sentinel)
   uint64_t wt_sigma = 0;  // wt.m_sigma
   uint64_t bv_bits = 0;
-  std::vector<uint64_t> bv;        // m_bv words
-  std::vector<uint64_t> rank_bb;   // rank_support_v basic blocks
+  Fm9Span bv;                      // m_bv words
+  Fm9Span rank_bb;                 // rank_support_v basic blocks
   std::vector<Fm9Node> nodes;      // byte_tree nodes (BFS order, root = 0)
   uint16_t c_to_leaf[256];
   uint64_t path[256];
   uint8_t sa_width = 0, isa_width = 0;
   uint64_t sa_count = 0, isa_count = 0;
-  std::vector<uint64_t> sa_words, isa_words;  // packed int_vector<0> payloads
+  Fm9Span sa_words, isa_words;     // packed int_vector<0> payloads
   uint8_t char2comp[256];
   std::vector<uint8_t> comp2char;
   std::vector<uint64_t> C;  // sigma + 1 entries
   uint16_t sigma = 0;
+
+  Fm9() = default;
+  Fm9(const Fm9&) = delete;
+  Fm9& operator=(const Fm9&) = delete;
+  ~Fm9() { unmap(); }
+  void unmap() {
+    if (map_) munmap(map_, map_bytes_);
+    map_ = nullptr;
+    map_bytes_ = 0;
+    bv = rank_bb = sa_words = isa_words = Fm9Span();
+  }
+  void* map_ = nullptr;
+  size_t map_bytes_ = 0;
 };
 
 // The type name SDSL hashes into `.fm9_check`: util::demangle2 of the csa_wt<> type
@@ -100,6 +126,57 @@ inline bool fm9_skip_select(Fm9Reader& rd) {
   return true;
 }
 
+// Cursor over the mapped file.
+class Fm9Cursor {
+ public:
+  Fm9Cursor(const uint8_t* p, uint64_t bytes) : p_(p), end_(p + bytes) {}
+  bool raw(void* out, uint64_t bytes) {
+    if ((uint64_t)(end_ - p_) < bytes) return false;
+    memcpy(out, p_, bytes);
+    p_ += bytes;
+    return true;
+  }
+  bool u64(uint64_t& v) { return raw(&v, 8); }
+  bool u16(uint16_t& v) { return raw(&v, 2); }
+  // int_vector<*>: header (width << 56 | bits), then ceil(bits/64) words
+  bool int_vector(Fm9Span* span, uint64_t& bits, uint8_t& width) {
+    uint64_t h;
+    if (!u64(h)) return false;
+    bits = h & ((1ULL << 56) - 1);
+    width = (uint8_t)(h >> 56);
+    const uint64_t nw = (bits + 63) >> 6;
+    if ((uint64_t)(end_ - p_) / 8 < nw) return false;
+    if (span) { span->p = p_; span->words = nw; }
+    p_ += nw * 8;
+    return true;
+  }
+  bool int_vector_copy(std::vector<uint64_t>& words, uint64_t& bits, uint8_t& width) {
+    Fm9Span sp;
+    if (!int_vector(&sp, bits, width)) return false;
+    words.resize(sp.words);
+    if (sp.words) memcpy(words.data(), sp.p, sp.bytes());
+    return true;
+  }
+  // select_support_mcl<b>::load (select_support_mcl.hpp:470-499): framing only
+  bool skip_select() {
+    uint64_t arg_cnt, bits;
+    uint8_t w;
+    if (!u64(arg_cnt)) return false;
+    if (!arg_cnt) return true;
+    const uint64_t sb = (arg_cnt + 4095) >> 12;
+    if (!int_vector(nullptr, bits, w)) return false;   // superblock
+    if (!int_vector(nullptr, bits, w)) return false;   // mini_or_long
+    for (uint64_t i = 0; i < sb; ++i)
+      if (!int_vector(nullptr, bits, w)) return false; // long or mini block: same framing
+    return true;
+  }
+  bool at_end() const { return p_ == end_; }
+
+ private:
+  const uint8_t* p_;
+  const uint8_t* end_;
+};
+
 // Returns 0 on success; -2 I/O, -3 format (codes of include/dicey_b200.h).
 inline int fm9_parse(const std::string& path, Fm9& o, std::string& err, bool check_sidecar = true) {
   if (check_sidecar) {
@@ -117,15 +194,33 @@ inline int fm9_parse(const std::string& path, Fm9& o, std::string& err, bool che
       return -3;
     }
   }
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) {
-    err = "cannot open " + path;
-    return -2;
+  o.unmap();
+  {
+    int fd = open(path.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+      if (fd >= 0) close(fd);
+      err = "cannot open " + path;
+      return -2;
+    }
+    if (st.st_size == 0) {
+      close(fd);
+      err = "malformed .fm9 (wt header): " + path;
+      return -3;
+    }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+      err = "cannot map " + path;
+      return -2;
+    }
+    o.map_ = m;
+    o.map_bytes_ = (size_t)st.st_size;
   }
-  Fm9Reader rd(f);
+  Fm9Cursor rd((const uint8_t*)o.map_, o.map_bytes_);
   auto fail = [&](const char* what) {
     err = std::string("malformed .fm9 (") + what + "): " + path;
-    fclose(f);
+    o.unmap();
     return -3;
   };
   uint8_t w;
@@ -134,9 +229,9 @@ inline int fm9_parse(const std::string& path, Fm9& o, std::string& err, bool che
   if (!rd.u64(o.n) || !rd.u64(o.wt_sigma)) return fail("wt header");
   if (!rd.int_vector(&o.bv, o.bv_bits, w) || w != 1) return fail("m_bv");
   if (!rd.int_vector(&o.rank_bb, bits, w) || w != 64) return fail("rank_support_v");
-  if (o.rank_bb.size() != 2 * (((o.bv_bits + 63) >> 9) + 1) && !(o.bv_bits == 0 && o.rank_bb.size() == 2))
+  if (o.rank_bb.words != 2 * (((o.bv_bits + 63) >> 9) + 1) && !(o.bv_bits == 0 && o.rank_bb.words == 2))
     return fail("rank_support_v size");
-  if (!fm9_skip_select(rd) || !fm9_skip_select(rd)) return fail("select_support_mcl");
+  if (!rd.skip_select() || !rd.skip_select()) return fail("select_support_mcl");
   uint64_t nn;
   if (!rd.u64(nn) || nn > 511) return fail("byte_tree size");
   o.nodes.resize(nn);
@@ -157,17 +252,15 @@ inline int fm9_parse(const std::string& path, Fm9& o, std::string& err, bool che
   o.isa_count = bits / o.isa_width;
   // 4. byte_alphabet
   std::vector<uint64_t> tmp;
-  if (!rd.int_vector(&tmp, bits, w) || w != 8 || bits != 256 * 8) return fail("char2comp");
+  if (!rd.int_vector_copy(tmp, bits, w) || w != 8 || bits != 256 * 8) return fail("char2comp");
   memcpy(o.char2comp, tmp.data(), 256);
-  if (!rd.int_vector(&tmp, bits, w) || w != 8) return fail("comp2char");
+  if (!rd.int_vector_copy(tmp, bits, w) || w != 8) return fail("comp2char");
   o.comp2char.assign((uint8_t*)tmp.data(), (uint8_t*)tmp.data() + bits / 8);
-  if (!rd.int_vector(&o.C, bits, w) || w != 64) return fail("C");
+  if (!rd.int_vector_copy(o.C, bits, w) || w != 64) return fail("C");
   if (!rd.u16(o.sigma)) return fail("sigma");
   if (o.C.size() != (size_t)o.sigma + 1 || o.comp2char.size() != o.sigma) return fail("alphabet sizes");
   if (o.sa_count != (o.n + 31) / 32 || o.isa_count != (o.n ? (o.n - 1) / 64 + 1 : 0)) return fail("sample counts");
-  uint8_t extra;
-  if (fread(&extra, 1, 1, f) != 0) return fail("trailing bytes");
-  fclose(f);
+  if (!rd.at_end()) return fail("trailing bytes");
   return 0;
 }
 
