@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <ctime>
 #include <iostream>
+#include <thread>
 
 #include "../../include/dicey_b200.h"
 #include "hostutil.hpp"
@@ -39,17 +40,34 @@ struct HunterConfig {  // hunter.h:37-50
   int device = 0;
 };
 
-struct DnaHitView {  // one DnaHit (hunter.h:53-66) read out of a dg_result
+struct DnaHitView {  // one DnaHit (hunter.h:53-66) read out of a dg_result (the alignment rows stay in its pool)
   int32_t score;
   uint32_t chr, start;
   char strand;
-  std::string refalign, queryalign;
+  const char* refalign;
+  const char* queryalign;
+  uint32_t aln_len;
 };
 
-uint32_t nucleotide_length(const std::string& s) {  // hunter.h:90-97
+uint32_t nucleotide_length(const char* s, uint32_t len) {  // hunter.h:90-97
   uint32_t n = 0;
-  for (char c : s) if (c != '-') ++n;
+  for (uint32_t i = 0; i < len; ++i) if (s[i] != '-') ++n;
   return n;
+}
+
+// nlohmann's string escaping appended in place (hostutil.hpp json_escape without the temporary)
+void append_escaped(std::string& o, const char* s, size_t len) {
+  for (size_t i = 0; i < len; ++i) {
+    const unsigned char ch = (unsigned char)s[i];
+    if (ch >= 0x20 && ch != '"' && ch != '\\') { o += (char)ch; continue; }
+    o += json_escape(std::string(1, (char)ch));
+  }
+}
+void append_uint(std::string& o, uint64_t v) {
+  char buf[24];
+  int n = 0;
+  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) o += buf[--n];
 }
 
 // writeJsonDnaHitOut (hunter.h:99-160)
@@ -87,15 +105,22 @@ std::string hunt_json(const HunterConfig& c, uint32_t distance, const std::strin
       if (oldchr != h.chr || oldstart != h.start) {
         if (!first) o += ',';
         first = false;
-        JsonObject j;
-        j.set_int("distance", std::abs(h.score));
-        j.set_string("chr", h.chr < qn.size() ? qn[h.chr] : std::string());
-        j.set_uint("start", h.start);
-        j.set_uint("end", h.start + nucleotide_length(h.refalign) - 1);
-        j.set_string("strand", std::string(1, h.strand));
-        j.set_string("refalign", h.refalign);
-        j.set_string("queryalign", h.queryalign);
-        o += j.dump();
+        // nlohmann::json::dump() of the record: keys in std::map order
+        o += "{\"chr\":\"";
+        if (h.chr < qn.size()) append_escaped(o, qn[h.chr].data(), qn[h.chr].size());
+        o += "\",\"distance\":";
+        append_uint(o, (uint64_t)std::abs(h.score));
+        o += ",\"end\":";
+        append_uint(o, (uint32_t)(h.start + nucleotide_length(h.refalign, h.aln_len) - 1));
+        o += ",\"queryalign\":\"";
+        append_escaped(o, h.queryalign, h.aln_len);
+        o += "\",\"refalign\":\"";
+        append_escaped(o, h.refalign, h.aln_len);
+        o += "\",\"start\":";
+        append_uint(o, h.start);
+        o += ",\"strand\":\"";
+        append_escaped(o, &h.strand, 1);
+        o += "\"}";
       }
       oldchr = h.chr;
       oldstart = h.start;
@@ -161,6 +186,15 @@ int hunter(int argc, char** argv) {
 
   std::vector<DnaHitView> none;
   std::vector<std::string> msg, seqname;
+  const bool trace = getenv("DICEY_B200_TRACE") != nullptr;   // wall time of every stage on stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char* what, uint64_t items) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hunt] %-28s %9.1f ms  (%llu)\n", what, std::chrono::duration<double, std::milli>(t - t_last).count(),
+            (unsigned long long)items);
+    t_last = t;
+  };
   if (c.hasOutfile) {  // truncate (hunter.h:226-230)
     FILE* t = fopen(c.outfile.c_str(), "wb");
     if (t) fclose(t);
@@ -187,6 +221,7 @@ int hunter(int argc, char** argv) {
     return fail("Error: FM-Index cannot be loaded!");
   }
   dg_index_set_records(ix, seqlen.data(), (uint32_t)seqlen.size());
+  stage("index load", dg_index_size(ix));
 
   // queries (hunter.h:262-288)
   std::vector<std::pair<std::string, std::string>> queries;
@@ -209,6 +244,7 @@ int hunter(int argc, char** argv) {
     queries.push_back({std::string(), c.sequence});
   }
 
+  stage("queries read", queries.size());
   // one batched call for every query (hunter.h:289-433 per query)
   std::string cat;
   std::vector<uint64_t> off(1, 0);
@@ -245,21 +281,25 @@ int hunter(int argc, char** argv) {
   const uint32_t* qdist = res ? dg_result_query_distance(res) : nullptr;
   const char* pool = res ? dg_result_pool(res, &pool_bytes) : nullptr;
   const char* norm = res ? dg_result_sequences(res, &seq_bytes) : nullptr;
+  stage("search (dg_hunt_batch)", nh);
 
-  for (size_t qi = 0; qi < queries.size(); ++qi) {
+  // one JSON line per query (hunter.h:289-444), formatted by several threads over blocks of queries
+  // and written in query order, one write (one gzip member) per block instead of per query: the
+  // bytes a reader sees are the same
+  auto format_query = [&](size_t qi, std::string& out) {
     std::vector<std::string> m;
     std::vector<DnaHitView> ht;
     const std::string& raw = queries[qi].second;
     if (raw.size() < 10) {  // hunter.h:299-303
       m.push_back("Error: Input sequence is shorter than 10 nucleotides!");
-      emit(c, hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m));
-      continue;
+      out += hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m);
+      return;
     }
     uint32_t st = all_unsupported ? (uint32_t)DG_Q_UNSUPPORTED : status[qi];
     if (st & DG_Q_UNSUPPORTED) {
       m.push_back("Error: Query is outside the limits of the GPU search path (length <= 255, distance <= 2)!");
-      emit(c, hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m));
-      continue;
+      out += hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m);
+      return;
     }
     // replaceNonDna warnings (util.h:208-219), one per replaced character
     for (char ch : raw) {
@@ -284,13 +324,44 @@ int hunter(int argc, char** argv) {
     for (const auto& h : mine) {
       DnaHitView v;
       v.score = h.score; v.chr = h.chr; v.start = h.start; v.strand = (char)h.strand;
-      v.refalign.assign(pool + h.aln_off, h.aln_len);
-      v.queryalign.assign(pool + h.aln_off + h.aln_len, h.aln_len);
-      ht.push_back(std::move(v));
+      v.refalign = pool + h.aln_off;
+      v.queryalign = pool + h.aln_off + h.aln_len;
+      v.aln_len = h.aln_len;
+      ht.push_back(v);
     }
     std::string sequence(norm + off[qi], norm + off[qi + 1]);
-    emit(c, hunt_json(c, qdist[qi], sequence, queries[qi].first, seqname, ht, m));
+    out += hunt_json(c, qdist[qi], sequence, queries[qi].first, seqname, ht, m);
+  };
+  {
+    const size_t nq_all = queries.size(), block = 1u << 16;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = getenv("DICEY_B200_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 32));
+    for (size_t b0 = 0; b0 < nq_all; b0 += block) {
+      const size_t b1 = std::min(nq_all, b0 + block), n = b1 - b0;
+      const size_t nt = std::max<size_t>(1, std::min(nthreads, n / 64));   // a handful of queries: no threads
+      std::vector<std::string> part(nt);
+      auto work = [&](size_t t) {
+        const size_t lo = b0 + n * t / nt, hi = b0 + n * (t + 1) / nt;
+        for (size_t qi = lo; qi < hi; ++qi) format_query(qi, part[t]);
+      };
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+      work(0);
+      for (auto& x : th) x.join();
+      if (nt == 1) {
+        emit(c, part[0]);
+      } else {
+        std::string all;
+        size_t total = 0;
+        for (const auto& x : part) total += x.size();
+        all.reserve(total);
+        for (const auto& x : part) all += x;
+        emit(c, all);
+      }
+    }
   }
+  stage("sort + JSON + write", nh);
   if (res) dg_result_free(res);
   dg_index_close(ix);
   return 0;

@@ -348,3 +348,40 @@ def test_config3_search_end_to_end(big, fm9, tmp_path):
     print(got.stderr)
     assert len(j["data"]["amplicons"]) >= npairs * 5 // 6
     assert got.stdout == want
+
+
+def test_hunt_cli_at_full_size(big, fm9, tmp_path):
+    """`dicey-b200 hunt` with a FASTA of 200 000 primers on the 3 Gb .fm9 (loaded as-is): every line
+    in input order; a sample of lines equals the Python mirror of writeJsonDnaHitOut built from the
+    library's records for the same primers (those records are pinned to the reference elsewhere)."""
+    if not fm9:
+        pytest.skip("needs the .fm9 written for the reference binary")
+    from dicey_b200.api import hunt_json
+    path, _ = fm9
+    d = str(tmp_path)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "dicey_b200", "host")], check=True, capture_output=True)
+    os.symlink(path, os.path.join(d, "genome.fa.fm9"))
+    os.symlink(path + "_check", os.path.join(d, "genome.fa.fm9_check"))
+    with open(os.path.join(d, "genome.fa.gz"), "wb") as f:
+        f.write(b"placeholder: hunt only needs the .fai and the index")
+    names = [f"chr{i + 1}" for i in range(NREC)]
+    with open(os.path.join(d, "genome.fa.gz.fai"), "w") as f:
+        for n in names:
+            f.write(f"{n}\t{RECLEN}\t0\t60\t61\n")
+    nq = 200_000
+    pr = synth.primers_fast(SEED, NREC, RECLEN, nq, 20, 1, True, rng_seed=33)
+    with open(os.path.join(d, "q.fa"), "w") as f:
+        f.write("".join(f">p{q}\n{pr[q].tobytes().decode()}\n" for q in range(nq)))
+    t0 = time.time()
+    r = subprocess.run([os.path.join(ROOT, "dicey_b200", "dicey-b200"), "hunt", "-g", "genome.fa.gz", "q.fa"], cwd=d,
+                       capture_output=True, text=True, env=dict(os.environ, DICEY_B200_TRACE="1"))
+    dt = time.time() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    print(f"[fullsize] dicey-b200 hunt, {nq} primers from a FASTA: {dt:.1f} s wall, {len(r.stdout) / 1e6:.0f} MB of JSON")
+    print(r.stderr)
+    assert len(lines) == nq
+    par = HuntParams(distance=1)
+    res = big.hunt(pr, par)
+    for q in list(range(0, nq, 997)) + [nq - 1]:
+        assert lines[q] == hunt_json(res, q, par, names, "genome.fa.gz", qname=f"p{q}").rstrip("\n"), q

@@ -98,6 +98,41 @@ def test_hunt_cli_matches_reference_json(tmp_path, case, index):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case,index", [("t1m_e1", "t1m"), ("stress_e1_m7", "stress")])
+def test_hunt_cli_many_queries_threaded_output(tmp_path, case, index):
+    """A FASTA of several thousand queries takes the threaded JSON path (blocks of queries formatted
+    side by side, written in order, one gzip member per block): the lines must still be the
+    reference's golden lines in input order, on stdout and in the gzipped output file, and must
+    not depend on the number of threads."""
+    d = make_genome_dir(tmp_path, index)
+    qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
+    want1 = [l for l in open(os.path.join(GOLDEN, case + ".jsonl"))]
+    reps = 70000 // len(qs) + 1            # more than one 65536-query block
+    with open(os.path.join(d, "q.fa"), "w") as f:
+        for _ in range(reps):
+            for n, s in qs:
+                f.write(f">{n}\n{s}\n")
+    flags = open(os.path.join(GOLDEN, case + ".flags.txt")).read().split()
+    outs = []
+    for threads in ("1", "7"):
+        r = subprocess.run([BIN, "hunt", "-g", "genome.fa.gz"] + flags + ["q.fa"], capture_output=True, text=True, cwd=d,
+                           env=dict(os.environ, DICEY_B200_THREADS=threads))
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == outs[1]
+    got = outs[1].splitlines(keepends=True)
+    assert len(got) == reps * len(qs)
+    for q, g in enumerate(got):
+        w = want1[q % len(qs)]
+        if "Neighborhood size exceeds" in w:
+            continue
+        assert g == w, (case, q)
+    r = run(["hunt", "-g", "genome.fa.gz"] + flags + ["-o", "out.json.gz", "q.fa"], cwd=d)
+    assert r.returncode == 0 and r.stdout == ""
+    assert gzip.open(os.path.join(d, "out.json.gz"), "rt").read() == outs[1].replace('"outfile":""', '"outfile":"out.json.gz"')
+
+
+@pytest.mark.gpu
 def test_hunt_cli_single_sequence_and_outfile(tmp_path):
     d = make_genome_dir(tmp_path, "t1m")
     name, seq = read_queries(os.path.join(GOLDEN, "cfg1_d0.queries.txt"))[0]
