@@ -441,42 +441,53 @@ std::string search_json(const SilicaConfig& c, uint32_t distance, const std::vec
     meta.set_uint("maxmatches", c.max_locations);
     meta.set_bool("hamming", !c.indel);
     o += ",\"meta\":" + meta.dump() + ",\"data\":{\"primers\":[";
+    // nlohmann::json::dump() of every record, keys in std::map order, appended in place
+    auto str = [&](const char* key, const std::string& v) {
+      o += key;
+      append_escaped(o, v.data(), v.size());
+      o += '"';
+    };
+    auto num = [&](const char* key, uint64_t v) { o += key; append_uint(o, v); };
+    auto dbl = [&](const char* key, double v) { o += key; o += json_double(v); };
+    size_t bytes = 256;
+    for (const auto& b : allp) bytes += 160 + b.genome.size() + pName[b.primerId].size() + pSeq[b.primerId].size();
+    for (size_t i = 0; i < pcrColl.size(); ++i) bytes += 320 + ampSeq[i].size() + 2 * 64;
+    o.reserve(o.size() + bytes);
     for (size_t i = 0; i < allp.size(); ++i) {
       if (i) o += ',';
-      JsonRaw j;
-      j.set_string("Chrom", qn[allp[i].refIndex]);
-      j.set_uint("Id", i);
-      j.set_double("Tm", allp[i].temp);
-      j.set_uint("Pos", (uint32_t)(allp[i].pos + 1));
-      j.set_uint("End", (uint64_t)allp[i].pos + pSeq[allp[i].primerId].size());
-      j.set_string("Ori", allp[i].onFor ? "forward" : "reverse");
-      j.set_string("Name", pName[allp[i].primerId]);
-      j.set_double("MatchTm", allp[i].perfTemp);
-      j.set_string("Seq", pSeq[allp[i].primerId]);
-      j.set_string("Genome", allp[i].genome);
-      o += j.dump();
+      const PrimerBind& b = allp[i];
+      str("{\"Chrom\":\"", qn[b.refIndex]);
+      num(",\"End\":", (uint64_t)b.pos + pSeq[b.primerId].size());
+      str(",\"Genome\":\"", b.genome);
+      num(",\"Id\":", i);
+      dbl(",\"MatchTm\":", b.perfTemp);
+      str(",\"Name\":\"", pName[b.primerId]);
+      str(",\"Ori\":\"", b.onFor ? "forward" : "reverse");
+      num(",\"Pos\":", (uint32_t)(b.pos + 1));
+      str(",\"Seq\":\"", pSeq[b.primerId]);
+      dbl(",\"Tm\":", b.temp);
+      o += '}';
     }
     o += "],\"amplicons\":[";
     for (size_t i = 0; i < pcrColl.size(); ++i) {
       if (i) o += ',';
       const PcrProduct& p = pcrColl[i];
-      JsonRaw j;
-      j.set_string("Chrom", qn[p.refIndex]);
-      j.set_uint("Id", i);
-      j.set_uint("Length", p.leng);
-      j.set_double("Penalty", p.penalty);
-      j.set_uint("ForPos", (uint32_t)(p.forPos + 1));
-      j.set_uint("ForEnd", (uint64_t)p.forPos + pSeq[p.forId].size());
-      j.set_double("ForTm", p.forTemp);
-      j.set_string("ForName", pName[p.forId]);
-      j.set_string("ForSeq", pSeq[p.forId]);
-      j.set_uint("RevPos", (uint32_t)(p.revPos + 1));
-      j.set_uint("RevEnd", (uint64_t)p.revPos + pSeq[p.revId].size());
-      j.set_double("RevTm", p.revTemp);
-      j.set_string("RevName", pName[p.revId]);
-      j.set_string("RevSeq", pSeq[p.revId]);
-      j.set_string("Seq", ampSeq[i]);
-      o += j.dump();
+      str("{\"Chrom\":\"", qn[p.refIndex]);
+      num(",\"ForEnd\":", (uint64_t)p.forPos + pSeq[p.forId].size());
+      str(",\"ForName\":\"", pName[p.forId]);
+      num(",\"ForPos\":", (uint32_t)(p.forPos + 1));
+      str(",\"ForSeq\":\"", pSeq[p.forId]);
+      dbl(",\"ForTm\":", p.forTemp);
+      num(",\"Id\":", i);
+      num(",\"Length\":", p.leng);
+      dbl(",\"Penalty\":", p.penalty);
+      num(",\"RevEnd\":", (uint64_t)p.revPos + pSeq[p.revId].size());
+      str(",\"RevName\":\"", pName[p.revId]);
+      num(",\"RevPos\":", (uint32_t)(p.revPos + 1));
+      str(",\"RevSeq\":\"", pSeq[p.revId]);
+      dbl(",\"RevTm\":", p.revTemp);
+      str(",\"Seq\":\"", ampSeq[i]);
+      o += '}';
     }
     o += "]}";
   }
