@@ -118,6 +118,8 @@ int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* by
   else if (w == "present_kb") { src = idx->present_kb.p; nb = idx->present_kb.bytes(); }
   else if (w == "present_hi") { src = idx->present_hi.p; nb = idx->present_hi.bytes(); }
   else if (w == "present_lo") { src = idx->present_lo.p; nb = idx->present_lo.bytes(); }
+  else if (w == "present_kb_l") { src = idx->present_kb_l.p; nb = idx->present_kb_l.bytes(); }
+  else if (w == "present_hi_l") { src = idx->present_hi_l.p; nb = idx->present_hi_l.bytes(); }
   else { set_error("unknown array name"); return DG_ERR_ARG; }
   if (!buf) { *bytes = nb; return DG_OK; }
   if (*bytes < nb) { set_error("buffer too small"); return DG_ERR_ARG; }

@@ -162,7 +162,8 @@ __global__ void k_kmer_level(IndexView ix, const uint2* __restrict__ prev, uint2
 // the text: a neighbour string whose last KB bases have a clear bit has an empty SA interval, so
 // k_search_packed drops it after ONE DRAM access instead of a table lookup + backward steps.
 constexpr int kPresenceChunk = 256;
-__global__ void k_presence(const uint8_t* __restrict__ text, uint64_t n, uint32_t KB, uint32_t* __restrict__ bits) {
+__global__ void k_presence(const uint8_t* __restrict__ text, uint64_t n, uint32_t KB, uint32_t* __restrict__ bits,
+                           uint32_t* __restrict__ bits_left) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t first = t * kPresenceChunk;
   if (first >= n) return;
@@ -174,7 +175,14 @@ __global__ void k_presence(const uint8_t* __restrict__ text, uint64_t n, uint32_
   for (uint64_t j = first; j < last; ++j) {
     int c = base_code(text[j]);
     if (c < 4) { code = ((code << 2) | (uint64_t)c) & mask; ++valid; } else { code = 0; valid = 0; }
-    if (valid >= KB) { const uint64_t bit = presence_bit(code, (int)KB); atomicOr(&bits[bit >> 5], 1u << (bit & 31)); }
+    if (valid >= KB) {
+      const uint64_t bit = presence_bit(code, (int)KB);
+      atomicOr(&bits[bit >> 5], 1u << (bit & 31));
+      if (bits_left) {
+        const uint64_t bl = presence_bit_left(code, (int)KB);
+        atomicOr(&bits_left[bl >> 5], 1u << (bl & 31));
+      }
+    }
   }
 }
 
@@ -564,23 +572,36 @@ static void build_presence_bitmap(dg_index* ix) {
   ix->KB = KB;
   if (!KB) return;
   uint64_t nthreads = (ix->n + kPresenceChunk - 1) / kPresenceChunk;
-  auto build = [&](DevBuf<uint32_t>& buf, uint32_t kb) {
+  // the left-anchored twin of a bitmap (DG_BITMAP_LEFT=0: none) when it fits comfortably
+  const char* lf = getenv("DG_BITMAP_LEFT");
+  const bool want_left = !(lf && atoi(lf) == 0);
+  auto build = [&](DevBuf<uint32_t>& buf, uint32_t kb, DevBuf<uint32_t>* left) {
     uint64_t words = (1ULL << (2 * kb)) >> 5;
     buf.alloc(words);
     DG_CUDA(cudaMemsetAsync(buf.p, 0, words * 4, st));
-    k_presence<<<grid_for(nthreads, 128), 128, 0, st>>>(ix->text.p, ix->n, kb, buf.p);
+    if (left) {
+      size_t free_b = 0, total_b = 0;
+      DG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      if (want_left && words * 4 * 2 < free_b) {
+        left->alloc(words);
+        DG_CUDA(cudaMemsetAsync(left->p, 0, words * 4, st));
+      } else {
+        left = nullptr;
+      }
+    }
+    k_presence<<<grid_for(nthreads, 128), 128, 0, st>>>(ix->text.p, ix->n, kb, buf.p, left ? left->p : nullptr);
     DG_CUDA(cudaGetLastError());
   };
-  build(ix->present_kb, KB);
+  build(ix->present_kb, KB, &ix->present_kb_l);
   // neighbours: KB - 1 always (a quarter of the size); KB + 1 (four times the size) when it fits
   // comfortably in what is left of the HBM (DG_BITMAP_EXTRA=0 switches both off)
   const char* ex = getenv("DG_BITMAP_EXTRA");
   if (!(ex && atoi(ex) == 0)) {
-    build(ix->present_lo, KB - 1);
+    build(ix->present_lo, KB - 1, nullptr);
     size_t free_b = 0, total_b = 0;
     DG_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t hi_bytes = (1ULL << (2 * (KB + 1))) >> 3;
-    if (KB + 1 <= 19 && hi_bytes * 3 < free_b) build(ix->present_hi, KB + 1);
+    if (KB + 1 <= 19 && hi_bytes * 3 < free_b) build(ix->present_hi, KB + 1, &ix->present_hi_l);
   }
   DG_CUDA(cudaStreamSynchronize(st));
 }

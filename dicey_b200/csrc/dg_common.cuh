@@ -68,7 +68,7 @@ struct dg_index {
   uint32_t sigma = 0;
   uint32_t K = 0;
   dg::DevBuf<dg::OccBlock> occ;
-  dg::DevBuf<uint32_t> excflag, exc_pos, rare_pos, rare_off, Cb, sa_samples, isa_samples, present_kb, present_hi, present_lo, sa_full;
+  dg::DevBuf<uint32_t> excflag, exc_pos, rare_pos, rare_off, Cb, sa_samples, isa_samples, present_kb, present_hi, present_lo, present_kb_l, present_hi_l, sa_full;
   uint32_t KB = 0;
   dg::DevBuf<uint8_t> exc_sym, present, text;
   dg::DevBuf<uint2> kmer;
@@ -90,12 +90,13 @@ struct dg_index {
     v.kmer = kmer.p; v.K = K; v.sa_samples = sa_samples.p; v.text = text.p; v.cum = cum.p; v.nseq = nseq;
     v.present_kb = present_kb.p; v.KB = KB; v.sa_full = sa_full.p;
     v.present_hi = present_hi.p; v.present_lo = present_lo.p;
+    v.present_kb_l = present_kb_l.p; v.present_hi_l = present_hi_l.p;
     return v;
   }
   uint64_t device_bytes() const {
     return occ.bytes() + excflag.bytes() + exc_pos.bytes() + rare_pos.bytes() + rare_off.bytes() + Cb.bytes() +
            sa_samples.bytes() + isa_samples.bytes() + exc_sym.bytes() + present.bytes() + text.bytes() +
-           kmer.bytes() + cum.bytes() + present_kb.bytes() + present_hi.bytes() + present_lo.bytes() + sa_full.bytes();
+           kmer.bytes() + cum.bytes() + present_kb.bytes() + present_hi.bytes() + present_lo.bytes() + present_kb_l.bytes() + present_hi_l.bytes() + sa_full.bytes();
   }
 };
 

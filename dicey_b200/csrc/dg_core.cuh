@@ -67,6 +67,8 @@ struct IndexView {
   // and KB - 1 (strings one base too short for the primary bitmap); null = not built
   const uint32_t* present_hi;
   const uint32_t* present_lo;
+  const uint32_t* present_kb_l;   // the same sets addressed by presence_bit_left() (null: not built)
+  const uint32_t* present_hi_l;
 };
 
 DG_HD int popc64(uint64_t x) {
@@ -723,6 +725,13 @@ DG_HD uint64_t presence_bit(uint64_t window, int KB) {
   const int lo = 2 * (KB - 5);
   return ((window & ((1ULL << lo) - 1ULL)) << 10) | (window >> lo);
 }
+
+// The mirror-image addressing: the line is selected by the FIRST KB - 5 bases of the window and the
+// bit by the 5 bases after them (with the first base in the high bits that is the packed code
+// itself).  A string whose edits all lie right of its first KB - 5 bases probes, with its first
+// KB bases, the same line as its siblings; between the two layouts only edits in the middle of
+// the string still cost one DRAM access each.
+DG_HD uint64_t presence_bit_left(uint64_t window, int KB) { (void)KB; return window; }
 
 // hunter.h:358-362 / silica.h:475-479: text position -> (refIndex, chrpos).
 DG_HD void locate_record(const uint64_t* cum, uint32_t nseq, uint64_t pos, uint32_t& refIndex, uint32_t& chrpos) {

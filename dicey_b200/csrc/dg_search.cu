@@ -544,12 +544,24 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
           if (pass && KB) {
             // the longest window the string covers: KB + 1, KB or KB - 1 bases
             const uint32_t* bm = nullptr;
+            const uint32_t* bml = nullptr;
             int kb = 0;
-            if (L > KB && ix.present_hi) { bm = ix.present_hi; kb = KB + 1; }
-            else if (L >= KB) { bm = ix.present_kb; kb = KB; }
+            if (L > KB && ix.present_hi) { bm = ix.present_hi; bml = ix.present_hi_l; kb = KB + 1; }
+            else if (L >= KB) { bm = ix.present_kb; bml = ix.present_kb_l; kb = KB; }
             else if (L == KB - 1 && ix.present_lo) { bm = ix.present_lo; kb = KB - 1; }
             if (bm) {
-              const uint64_t bit = presence_bit(code & ((1ULL << (2 * kb)) - 1ULL), kb);
+              // leftmost edit at or right of base kb - 5 of the string: its first kb bases share their
+              // line of the left-anchored bitmap with every sibling of that kind; otherwise the
+              // last kb bases go to the right-anchored one (shared when all edits lie left of its
+              // last kb - 5 bases)
+              const int p_left = e < 0 ? 0 : (row < 0 ? e / S : p1);
+              uint64_t bit;
+              if (bml && p_left >= kb - 5) {
+                bm = bml;
+                bit = presence_bit_left((code >> (2 * (L - kb))) & ((1ULL << (2 * kb)) - 1ULL), kb);
+              } else {
+                bit = presence_bit(code & ((1ULL << (2 * kb)) - 1ULL), kb);
+              }
               // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
               uint32_t word;
               asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(bm + (bit >> 5)));

@@ -56,7 +56,8 @@ def test_index_arrays_stress(indexes):
     # KB-mer presence bitmaps (KB - 1, KB, KB + 1): exactly the ACGT-only windows of the text
     code = {65: 0, 67: 1, 71: 2, 84: 3}
     kb0 = ix.info()["bitmap_k"]
-    for name, kb in (("present_lo", kb0 - 1), ("present_kb", kb0), ("present_hi", kb0 + 1)):
+    for name, kb in (("present_lo", kb0 - 1), ("present_kb", kb0), ("present_hi", kb0 + 1),
+                     ("present_kb_l", kb0), ("present_hi_l", kb0 + 1)):
         bits = ix.debug_array(name, np.uint32)
         assert bits.size == (4 ** kb) // 32, name
         want = np.zeros_like(bits)
@@ -66,8 +67,10 @@ def test_index_arrays_stress(indexes):
                 v = 0
                 for ch in w:
                     v = (v << 2) | code[ch]
-                lo = 2 * (kb - 5)   # presence_bit(): line = last kb - 5 bases, bit = the 5 bases before them
-                v = ((v & ((1 << lo) - 1)) << 10) | (v >> lo)
+                if not name.endswith("_l"):
+                    lo = 2 * (kb - 5)   # presence_bit(): line = last kb - 5 bases, bit = the 5 bases before them
+                    v = ((v & ((1 << lo) - 1)) << 10) | (v >> lo)
+                # (presence_bit_left(): line = first kb - 5 bases, bit = the 5 bases after them: the code itself)
                 want[v >> 5] |= np.uint32(1 << (v & 31))
         assert np.array_equal(bits, want), name
     # occ blocks: cumulative ACGT counts + bit planes of the BWT
@@ -142,7 +145,7 @@ def test_build_text_equals_fm9(indexes, name):
         for what, dt in (("text", np.uint8), ("sa_samples", np.uint32), ("isa_samples", np.uint32), ("occ", np.uint32),
                          ("C", np.uint32), ("exc_pos", np.uint32), ("exc_sym", np.uint8), ("kmer", np.uint32),
                          ("sa_full", np.uint32), ("present_kb", np.uint32), ("present_hi", np.uint32),
-                         ("present_lo", np.uint32)):
+                         ("present_lo", np.uint32), ("present_kb_l", np.uint32), ("present_hi_l", np.uint32)):
             assert np.array_equal(ix.debug_array(what, dt), ref.debug_array(what, dt)), what
 
 
