@@ -21,7 +21,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libdicey_b200.so")
+    # DICEY_B200_LIB: another build of the same library (A/B runs of kernel variants)
+    return os.environ.get("DICEY_B200_LIB") or os.path.join(_HERE, "libdicey_b200.so")
 
 
 class DiceyB200Error(RuntimeError):

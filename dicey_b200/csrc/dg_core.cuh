@@ -717,20 +717,28 @@ DG_HD uint64_t apply_event_packed(uint64_t code, int j, int k) {
 constexpr int kMaxPacked = 31;  // longest edited string the packed path handles
 
 // Bit address of a KB-mer window (packed, last base in the low bits) in the presence bitmap.
-// A random access moves a whole 128-byte line (1024 bits) of DRAM, so the line is selected by the
-// LAST KB - 5 bases and the bit inside it by the 5 bases before them: every neighbour string whose
-// edit lies left of its last KB - 5 bases (right-anchored, so indels there shift nothing) probes
-// the same line as its siblings -- one DRAM access for ~7 x 8 of the 160 strings of a 20-mer.
+// Random probes are bounded by DRAM row activations, not bytes, so addresses are arranged for
+// siblings to land together: the region is selected by the LAST KB - 7 bases and the bit inside it
+// by the 7 bases before them (2 KB: 16 lines of one DRAM row; the 4 outermost bases stay within
+// one 32-byte sector).  Every neighbour string whose edits lie left of its last KB - 7 bases
+// (right-anchored, so indels there shift nothing) probes the same region as its siblings.
+// Measured on the headline workload (search stage, ms): 5 bases 3.20, 6: 3.08, 7: 2.92, 8: 3.02,
+// 10: 3.18, 12: 3.50.
+#ifndef DG_BP
+#define DG_BP 7
+#endif
+constexpr int kPresenceBitBases = DG_BP;   // bases that select the bit inside a region
+DG_HD int presence_bit_bases(int KB) { return KB - 2 < kPresenceBitBases ? KB - 2 : kPresenceBitBases; }
 DG_HD uint64_t presence_bit(uint64_t window, int KB) {
-  const int lo = 2 * (KB - 5);
-  return ((window & ((1ULL << lo) - 1ULL)) << 10) | (window >> lo);
+  const int bp = presence_bit_bases(KB), lo = 2 * (KB - bp);
+  return ((window & ((1ULL << lo) - 1ULL)) << (2 * bp)) | (window >> lo);
 }
 
-// The mirror-image addressing: the line is selected by the FIRST KB - 5 bases of the window and the
-// bit by the 5 bases after them (with the first base in the high bits that is the packed code
-// itself).  A string whose edits all lie right of its first KB - 5 bases probes, with its first
-// KB bases, the same line as its siblings; between the two layouts only edits in the middle of
-// the string still cost one DRAM access each.
+// The mirror-image addressing: the region is selected by the FIRST KB - 7 bases of the window and
+// the bit by the 7 bases after them (with the first base in the high bits that is the packed code
+// itself).  A string whose edits all lie right of its first KB - 7 bases probes, with its first
+// KB bases, the same region as its siblings; between the two layouts only edits in the middle of
+// the string (5 of the 19 window positions of a 20-mer) still open a DRAM row of their own.
 DG_HD uint64_t presence_bit_left(uint64_t window, int KB) { (void)KB; return window; }
 
 // hunter.h:358-362 / silica.h:475-479: text position -> (refIndex, chrpos).

@@ -550,13 +550,13 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
             else if (L >= KB) { bm = ix.present_kb; bml = ix.present_kb_l; kb = KB; }
             else if (L == KB - 1 && ix.present_lo) { bm = ix.present_lo; kb = KB - 1; }
             if (bm) {
-              // leftmost edit at or right of base kb - 5 of the string: its first kb bases share their
-              // line of the left-anchored bitmap with every sibling of that kind; otherwise the
+              // leftmost edit at or right of base kb - 7 of the string: its first kb bases share their
+              // region of the left-anchored bitmap with every sibling of that kind; otherwise the
               // last kb bases go to the right-anchored one (shared when all edits lie left of its
-              // last kb - 5 bases)
+              // last kb - 7 bases)
               const int p_left = e < 0 ? 0 : (row < 0 ? e / S : p1);
               uint64_t bit;
-              if (bml && p_left >= kb - 5) {
+              if (bml && p_left >= kb - presence_bit_bases(kb)) {
                 bm = bml;
                 bit = presence_bit_left((code >> (2 * (L - kb))) & ((1ULL << (2 * kb)) - 1ULL), kb);
               } else {

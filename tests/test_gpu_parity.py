@@ -68,9 +68,10 @@ def test_index_arrays_stress(indexes):
                 for ch in w:
                     v = (v << 2) | code[ch]
                 if not name.endswith("_l"):
-                    lo = 2 * (kb - 5)   # presence_bit(): line = last kb - 5 bases, bit = the 5 bases before them
-                    v = ((v & ((1 << lo) - 1)) << 10) | (v >> lo)
-                # (presence_bit_left(): line = first kb - 5 bases, bit = the 5 bases after them: the code itself)
+                    bp = min(7, kb - 2)
+                    lo = 2 * (kb - bp)   # presence_bit(): region = last kb - 7 bases, bit = the 7 bases before them
+                    v = ((v & ((1 << lo) - 1)) << (2 * bp)) | (v >> lo)
+                # (presence_bit_left(): region = first kb - 7 bases, bit = the 7 bases after them: the code itself)
                 want[v >> 5] |= np.uint32(1 << (v & 31))
         assert np.array_equal(bits, want), name
     # occ blocks: cumulative ACGT counts + bit planes of the BWT
