@@ -699,7 +699,34 @@ struct CandKeyDecomposer {
 };
 constexpr int kKeyChars = 42;
 
-__global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t n, uint32_t sentinel, CandKey* __restrict__ keys) {
+// 2-bit packed string (last base in the low bits, L <= 32 bases) -> 4-bit classes A C G T = 1..4,
+// first base in the low nibble (Packed4): reverse the base order, spread every 2-bit field into a
+// nibble, add one to the L valid nibbles.
+__device__ __forceinline__ uint64_t spread2to4(uint64_t v) {   // 16 bases in the low 32 bits
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFULL;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFULL;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+  v = (v | (v << 2)) & 0x3333333333333333ULL;
+  return v;
+}
+__device__ __forceinline__ Packed4 packed2_to_packed4(uint64_t code, int L) {
+  Packed4 p;
+  p.w0 = p.w1 = 0;
+  if (L <= 0) return p;
+  uint64_t r = __brevll(code);
+  r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);   // base j (from the left) ...
+  r >>= 2 * (32 - L);                                                             // ... now at bits 2j
+  const uint64_t ones = 0x1111111111111111ULL;
+  const uint64_t m0 = L >= 16 ? ~0ULL : ((1ULL << (4 * L)) - 1ULL);
+  const uint64_t m1 = L <= 16 ? 0ULL : (L >= 32 ? ~0ULL : ((1ULL << (4 * (L - 16))) - 1ULL));
+  p.w0 = spread2to4(r & 0xFFFFFFFFULL) + (ones & m0);
+  p.w1 = (spread2to4(r >> 32) + (ones & m1)) & m1;
+  p.w0 &= m0;
+  return p;
+}
+
+__global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t n, uint32_t sentinel, CandKey* __restrict__ keys,
+                            int slow_keys) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Cand c = cands[i];
@@ -714,8 +741,34 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
   CandKey k;
   k.hi = k.lo = 0;
   bool keep;
+  if ((b.qflag[c.q] & 2) && !slow_keys) {
+    // packed path (ACGT-only query, m + d <= 31): the string k_search_packed searched, rebuilt the
+    // way it built it, then widened by shifts and masks instead of a walk over the bases
+    const uint64_t code0 = b.qcode[2 * (uint64_t)c.q + strand];
+    uint64_t code = code0;
+    int L = m;
+    for (int ev = 0; ev < sc.nev; ++ev) {   // the left event first: an edit never moves anything to its right
+      const int kk = sc.k[ev];
+      code = apply_event_packed(code, m - 1 - sc.pos[ev], kk);
+      L += kk == 4 ? -1 : (kk >= 5 ? 1 : 0);
+    }
+    const uint64_t al = L > 0 ? code << (64 - 2 * L) : 0;   // base j at bits 62 - 2j
+#pragma unroll
+    for (int j = 0; j < kMaxPacked; ++j) {
+      uint64_t v = (al >> (62 - 2 * j)) & 3ULL;
+      v = v + 1ULL + (v == 3ULL ? 1ULL : 0ULL);               // key order: A < C < G < N < T
+      if (j >= L) v = 0;
+      if (j < 21) k.hi |= v << (60 - 3 * j); else k.lo |= v << (60 - 3 * (j - 21));
+    }
+    if (!indel) {
+      keep = true;
+    } else {
+      const Packed4 q4 = packed2_to_packed4(code0, m), t4 = packed2_to_packed4(code, L);
+      keep = (d == 1 && m >= 2) ? is_minimal_d1(q4, m, t4, L) : is_minimal_small(q4, m, d, t4, L);
+    }
+  } else
   if (m + d <= 31) {
-    // register path: the edited string is generated straight into 4-bit classes and key codes
+    // register path (a query holding N): the edited string is generated into 4-bit classes and key codes
     const Packed4 q4 = pack4(base, m);
     Packed4 t4;
     t4.w0 = t4.w1 = 0;
@@ -1490,7 +1543,8 @@ static int run_impl(dg_batch* b) {
       uint32_t n3 = 0;
       for (int attempt = 0; attempt < 2; ++attempt) {
         const bool by_group = attempt == 0 && !full_sort_always;
-        k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p);
+        const int slow_keys = getenv("DG_SLOW_KEYS") ? 1 : 0;   // test knob: the byte-wise key builder for every query
+        k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p, slow_keys);
         size_t tb = 0;
         if (by_group) {
           // 3 radix passes on (query, strand), then a rank count inside each small group

@@ -257,13 +257,15 @@ def test_records_dump_equals_reference_dump(indexes, case, index):
     assert res.records_tsv(par, [s.encode() for _, s in qs]) == want
 
 
-@pytest.mark.parametrize("knob", ["DG_FULL_KEY_SORT=1", "DG_MERGE_SORT=1", "DG_LOCATE_RADIX=1", "DG_CAND_CAP=48", "DG_LOCATE_CAP=150"])
+@pytest.mark.parametrize("knob", ["DG_FULL_KEY_SORT=1", "DG_MERGE_SORT=1", "DG_LOCATE_RADIX=1", "DG_CAND_CAP=48", "DG_LOCATE_CAP=150",
+                                  "DG_SLOW_KEYS=1"])
 @pytest.mark.parametrize("case,index", [("stress_e2", "stress"), ("t1m_e1", "t1m"), ("stress_h2_m50", "stress"), ("stress_e1", "stress")])
 def test_alternative_paths_give_the_same_records(indexes, monkeypatch, knob, case, index):
     """The alternative routes through the pipeline must give the same records as the default one:
     the three ways of putting candidates into std::set order (group rank count, full-key radix sort,
     comparison sort for strings beyond the key), radix-sorted locate segments, the second search
-    attempt after a candidate-buffer overflow, and locate / verify in slices of candidates."""
+    attempt after a candidate-buffer overflow, locate / verify in slices of candidates, and the byte-wise
+    builder of the string keys in place of the shift-and-mask one."""
     ix = indexes[index]
     qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
     par = params_from_flags(open(os.path.join(GOLDEN, case + ".flags.txt")).read())
