@@ -41,14 +41,18 @@ void dg_index_close(dg_index* idx) {
   cudaStream_t xs[3] = {idx->xstream[0], idx->xstream[1], idx->xstream[2]};
   for (auto s2 : xs) if (s2) cudaStreamSynchronize(s2);
   if (cs) cudaStreamSynchronize(cs);
+  cudaStream_t us = idx->up_stream;
+  if (us) cudaStreamSynchronize(us);
   {
     cudaStream_t all[4] = {st, xs[0], xs[1], xs[2]};
     release_stream_pools(all, 4);
   }
+  for (auto e : idx->ev_pool) cudaEventDestroy(e);
   delete idx;
   if (st) cudaStreamDestroy(st);
   for (auto s2 : xs) if (s2) cudaStreamDestroy(s2);
   if (cs) cudaStreamDestroy(cs);
+  if (us) cudaStreamDestroy(us);
 }
 
 uint64_t dg_index_size(const dg_index* idx) { return idx ? idx->n : 0; }

@@ -63,6 +63,10 @@ struct dg_index {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};   // extra compute streams of the chunk pipeline (dg_hunt_batch)
+  cudaStream_t up_stream = nullptr;                         // its upload stream and the device copy of the caller's sequences
+  dg::DevBuf<uint8_t> upload;
+  std::vector<cudaEvent_t> ev_pool;                         // events of the chunk pipeline, created once and reused (creating or
+                                                            // destroying one while copies are in flight can stall the caller)
   cudaStream_t copy_stream = nullptr;   // device -> host copies of finished chunks
   uint64_t n = 0;
   uint32_t sigma = 0;

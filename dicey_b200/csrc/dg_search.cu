@@ -1100,6 +1100,11 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
   a.hits[h] = out;
 }
 
+__global__ void k_fill_offsets(uint64_t* __restrict__ off, uint64_t n, uint64_t len) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] = i * len;
+}
+
 __global__ void k_count(const Cand* __restrict__ cands, uint32_t n, unsigned long long* __restrict__ counts) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1303,8 +1308,11 @@ static BatchDev batch_dev(const dg_batch* b) {
   return d;
 }
 
+// d_seqs / ready: the sequence bytes are already in device memory (uploaded by the chunk pipeline's
+// uploader; `ready` is recorded after that copy) -- the host pointer is then only scanned.
 static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* par,
-                      dg_batch** out, cudaStream_t on_stream = nullptr) {
+                      dg_batch** out, cudaStream_t on_stream = nullptr, const uint8_t* d_seqs = nullptr,
+                      cudaEvent_t ready = nullptr) {
   if (!ix || !offsets || !par || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
   if (par->distance > (uint32_t)kMaxDist) {
     set_error("distance > 2 is outside the device path (DESIGN.md, Limits)");
@@ -1405,10 +1413,20 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     b->status.alloc(nq, st);
     b->dist.alloc(nq, st);
     const double ts2 = now();
-    DG_CUDA(cudaMemcpyAsync(b->raw.p, seqs, b->nbytes, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaMemcpyAsync(b->off.p, offsets, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (d_seqs) {
+      if (ready) DG_CUDA(cudaStreamWaitEvent(st, ready, 0));
+      if (b->nbytes) DG_CUDA(cudaMemcpyAsync(b->raw.p, d_seqs, b->nbytes, cudaMemcpyDeviceToDevice, st));
+    } else if (b->nbytes) {
+      DG_CUDA(cudaMemcpyAsync(b->raw.p, seqs, b->nbytes, cudaMemcpyHostToDevice, st));
+    }
+    if (equal_len) {   // equal-length batches do not send their offsets: the device writes q * L
+      k_fill_offsets<<<grid_for((uint64_t)nq + 1, 256), 256, 0, st>>>(b->off.p, (uint64_t)nq + 1, offsets[1]);
+      DG_CUDA(cudaGetLastError());
+    } else {
+      DG_CUDA(cudaMemcpyAsync(b->off.p, offsets, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
     // the copies above read caller memory: finish them before returning ownership
-    DG_CUDA(cudaStreamSynchronize(st));
+    if (!d_seqs || !equal_len) DG_CUDA(cudaStreamSynchronize(st));
     if (trace) fprintf(stderr, "[dg_batch_stage] scan+tables %.3f ms, allocs %.3f ms, copies %.3f ms\n", ts1 - ts0, ts2 - ts1, now() - ts2);
     *out = b;
     return DG_OK;
@@ -1419,10 +1437,11 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
 }
 
 static thread_local double g_host_mark[8];
+static double g_pipe_t0 = 0;   // DG_TRACE: start of the current dg_hunt_batch call (host clock, ms)
 static void prof_mark(dg_index* ix, int i, cudaStream_t st = nullptr) {
-  if (st && st != ix->stream) return;   // chunk-pipeline batches on the second stream are not profiled
   static const bool trace = getenv("DG_TRACE") != nullptr;
   if (trace) g_host_mark[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (st && st != ix->stream) return;   // chunk-pipeline batches on the other streams are not profiled
   if (!ix->prof.enabled) return;   // (stage timings are taken on the index stream only)
   if (!ix->prof.created) {
     for (auto& e : ix->prof.ev) cudaEventCreate(&e);
@@ -1772,9 +1791,12 @@ static int run_impl(dg_batch* b) {
     }
     prof_mark(ix, 5, st);
     if (getenv("DG_TRACE"))
-      fprintf(stderr, "[dg_batch_run] host ms: prepare %.3f search %.3f filter %.3f locate %.3f verify %.3f (nq %u, cands %u, hits %llu)\n",
+      fprintf(stderr, "[dg_batch_run] host ms: prepare %.3f search %.3f filter %.3f locate %.3f verify %.3f (nq %u, cands %u, hits %llu); "
+              "marks at %.3f %.3f %.3f %.3f %.3f %.3f ms of the call\n",
               g_host_mark[1] - g_host_mark[0], g_host_mark[2] - g_host_mark[1], g_host_mark[3] - g_host_mark[2],
-              g_host_mark[4] - g_host_mark[3], g_host_mark[5] - g_host_mark[4], nq, n, (unsigned long long)nhits);
+              g_host_mark[4] - g_host_mark[3], g_host_mark[5] - g_host_mark[4], nq, n, (unsigned long long)nhits,
+              g_host_mark[0] - g_pipe_t0, g_host_mark[1] - g_pipe_t0, g_host_mark[2] - g_pipe_t0, g_host_mark[3] - g_pipe_t0,
+              g_host_mark[4] - g_pipe_t0, g_host_mark[5] - g_pipe_t0);
     DG_CUDA(cudaGetLastError());
     b->ran = true;
     if (st == ix->stream) {
@@ -1909,6 +1931,9 @@ struct ChunkPipe {
   std::condition_variable cv;
   int nworkers = 2;
   uint32_t next_commit = 0;      // chunks are committed (final offsets assigned) in order
+  const uint8_t* d_up = nullptr; // the caller's sequences in device memory, chunk c valid once uploaded > c
+  std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev;   // per chunk, from the index's event pool
+  uint32_t uploaded = 0;
   uint64_t hit_base = 0, pool_base = 0;
   int rc = DG_OK;
   std::string err;
@@ -1931,10 +1956,11 @@ struct ChunkPipe {
       std::vector<uint64_t> so;
       for (uint32_t c = (uint32_t)w; c < nchunks; c += (uint32_t)nworkers) {
         { std::lock_guard<std::mutex> g(mu); if (rc != DG_OK) break; }
+        double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        tm[0] = now() - t_begin;
         // release chunks whose records have reached the host (keeps at most 2 per worker alive)
         while (!live.empty() && (live.size() >= 2 || cudaEventQuery(live.front().copied) == cudaSuccess)) {
           DG_CUDA(cudaEventSynchronize(live.front().copied));
-          cudaEventDestroy(live.front().copied);
           dg_batch_free(live.front().b);
           live.erase(live.begin());
         }
@@ -1943,18 +1969,27 @@ struct ChunkPipe {
         if (offsets[q1] < offsets[q0]) { fail(DG_ERR_ARG, "offsets must be non-decreasing"); break; }
         so.resize((size_t)cn + 1);
         for (uint32_t k = 0; k <= cn; ++k) so[k] = offsets[q0 + k] - offsets[q0];
+        tm[1] = now() - t_begin;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return uploaded > c || rc != DG_OK; });
+          if (rc != DG_OK) break;
+        }
+        tm[2] = now() - t_begin;
         dg_batch* b = nullptr;
-        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st);
+        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st, d_up + offsets[q0], up_ev[c]);
         if (rc1) { fail(rc1, last_error_ref()); break; }
-        cudaEvent_t copied;
-        DG_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+        cudaEvent_t copied = copied_ev[c];
         live.push_back(Live{b, copied});
+        tm[3] = now() - t_begin;
         rc1 = run_impl(b);
         if (rc1) { fail(rc1, last_error_ref()); break; }
+        tm[4] = now() - t_begin;
         // commit in query order
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&] { return next_commit == c || rc != DG_OK; });
         if (rc != DG_OK) break;
+        tm[5] = now() - t_begin;
         const uint64_t need_hits = (hit_base + b->nhits) * sizeof(dg_hit), need_pool = pool_base + b->pool_bytes;
         if (need_hits > r->hits.cap || need_pool > r->pool.cap) {
           // first call with this volume (later calls get right-sized blocks from the cache): size for
@@ -1975,11 +2010,9 @@ struct ChunkPipe {
         }
         k_rebase<<<grid_for(std::max<uint64_t>(b->nhits, (uint64_t)cn + 1), 256), 256, 0, st>>>(
             b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base, idx->wire.p + hit_base);
-        cudaEvent_t ev;
-        DG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaEvent_t ev = rebased_ev[c];
         DG_CUDA(cudaEventRecord(ev, st));
         DG_CUDA(cudaStreamWaitEvent(cs, ev, 0));
-        cudaEventDestroy(ev);   // released once the wait has been satisfied
         if (b->nhits) {
           DG_CUDA(cudaMemcpyAsync((uint8_t*)r->hits.p + hit_base * sizeof(dg_hit), b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, cs));
           if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->pool.p + pool_base, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, cs));
@@ -1994,8 +2027,9 @@ struct ChunkPipe {
         hit_base += b->nhits;
         pool_base += b->pool_bytes;
         ++next_commit;
-        if (trace) fprintf(stderr, "[dg_hunt_batch] worker %d committed chunk %u/%u: %u queries, %llu hits, t = %.3f ms\n", w, c + 1,
-                           nchunks, cn, (unsigned long long)b->nhits, now() - t_begin);
+        if (trace) fprintf(stderr, "[dg_hunt_batch] worker %d committed chunk %u/%u: %u queries, %llu hits, t = %.3f ms "
+                           "(loop top %.3f, offsets %.3f, upload %.3f, staged %.3f, ran %.3f, turn %.3f)\n", w, c + 1,
+                           nchunks, cn, (unsigned long long)b->nhits, now() - t_begin, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
         lk.unlock();
         cv.notify_all();
       }
@@ -2004,9 +2038,15 @@ struct ChunkPipe {
     } catch (std::bad_alloc&) {
       fail(DG_ERR_NOMEM, "out of host memory");
     }
-    if (idx->copy_stream) cudaStreamSynchronize(idx->copy_stream);
-    for (auto& l : live) { cudaEventDestroy(l.copied); dg_batch_free(l.b); }
+    // batches whose records may still be travelling are handed to the caller of the pipeline, which
+    // frees them after its final wait on the copy stream (a worker waiting here would sit inside a
+    // blocking CUDA call while the other workers still launch: their calls stall behind it)
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (auto& l : live) leftover.push_back(std::make_pair(l.b, l.copied));
+    }
   }
+  std::vector<std::pair<dg_batch*, cudaEvent_t>> leftover;
 };
 }  // namespace
 
@@ -2026,6 +2066,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
   p.idx = idx; p.seqs = seqs; p.offsets = offsets; p.nq = nq; p.nchunks = nchunks; p.params = params;
   p.trace = getenv("DG_TRACE") != nullptr;
   p.t_begin = now();
+  g_pipe_t0 = p.t_begin;
   dg_result* r = nullptr;
   try {
     DG_CUDA(cudaSetDevice(idx->device));
@@ -2042,10 +2083,51 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     r->dist.alloc((size_t)nq * 4, true);
     r->seqs.alloc(offsets[nq], true);
     p.r = r;
+    // The calling thread uploads the sequences chunk by chunk, in order, on a stream of its own (a
+    // copy from the caller's ordinary memory occupies the issuing thread; done per chunk by the
+    // workers, those copies queue behind each other and behind the result copies); the workers
+    // pick a chunk up as soon as its upload has been issued.
+    if (!idx->up_stream) DG_CUDA(cudaStreamCreateWithFlags(&idx->up_stream, cudaStreamNonBlocking));
+    if (idx->upload.count < offsets[nq] + 1) idx->upload.alloc(offsets[nq] + (offsets[nq] >> 3) + 4096);
+    p.d_up = idx->upload.p;
+    while (idx->ev_pool.size() < 3 * (size_t)nchunks) {
+      cudaEvent_t e;
+      DG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      idx->ev_pool.push_back(e);
+    }
+    p.up_ev.assign(idx->ev_pool.begin(), idx->ev_pool.begin() + nchunks);
+    p.copied_ev.assign(idx->ev_pool.begin() + nchunks, idx->ev_pool.begin() + 2 * (size_t)nchunks);
+    p.rebased_ev.assign(idx->ev_pool.begin() + 2 * (size_t)nchunks, idx->ev_pool.begin() + 3 * (size_t)nchunks);
     std::vector<std::thread> others;
-    for (int w = 1; w < p.nworkers; ++w) others.emplace_back([&p, w] { p.worker(w); });
-    p.worker(0);
+    for (int w = 0; w < p.nworkers; ++w) others.emplace_back([&p, w] { p.worker(w); });
+    try {
+      // Page-locked caller memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): one
+      // asynchronous copy per chunk.  Ordinary memory: such a copy occupies its caller and, issued
+      // next to kernels and result copies, stalls for milliseconds (and the CUDA calls of the other
+      // threads with it), so it is done in two pieces only -- the first chunk alone, so that the
+      // GPU starts at once, then all the others while little else is in flight.
+      cudaPointerAttributes attr;
+      const bool pinned_in = cudaPointerGetAttributes(&attr, seqs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      for (uint32_t c0 = 0; c0 < nchunks;) {
+        const uint32_t c1 = (pinned_in || c0 == 0) ? c0 + 1 : nchunks;
+        const uint64_t b0 = offsets[p.bounds[c0]], b1 = offsets[p.bounds[c1]];
+        if (b1 < b0) { p.fail(DG_ERR_ARG, "offsets must be non-decreasing"); break; }
+        if (b1 > b0) DG_CUDA(cudaMemcpyAsync(idx->upload.p + b0, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, idx->up_stream));
+        for (uint32_t c = c0; c < c1; ++c) DG_CUDA(cudaEventRecord(p.up_ev[c], idx->up_stream));
+        { std::lock_guard<std::mutex> g(p.mu); p.uploaded = c1; }
+        p.cv.notify_all();
+        c0 = c1;
+      }
+    } catch (CudaFail& e) {
+      p.fail(e.code, last_error_ref());
+    }
     for (auto& t : others) t.join();
+    cudaStreamSynchronize(idx->copy_stream);
+    for (auto& l : p.leftover) dg_batch_free(l.first);
+    p.leftover.clear();
+    cudaStreamSynchronize(idx->up_stream);
+    p.up_ev.clear();
     if (p.rc == DG_OK) {
       DG_CUDA(cudaStreamSynchronize(idx->copy_stream));
       r->nhits = p.hit_base;

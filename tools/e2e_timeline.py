@@ -8,6 +8,11 @@ from dicey_b200 import synth
 from dicey_b200.api import Index, HuntParams
 ix = Index.build_synthetic(42, 24, 125_000_000, 0)
 pr = synth.primers_fast(42, 24, 125_000_000, 1_000_000, 20, 1, True, rng_seed=7)
+if os.environ.get("DG_PINNED_INPUT", "1") != "0":   # what bench.py's end-to-end arm passes: page-locked host buffers
+    import torch
+    pin = torch.from_numpy(pr.reshape(-1)).pin_memory()
+    off = torch.from_numpy((np.arange(pr.shape[0] + 1, dtype=np.uint64) * np.uint64(pr.shape[1])).view(np.int64)).pin_memory()
+    pr = (pin.numpy(), off.numpy().view(np.uint64))
 ms = []
 for rep in range(14):
     t = time.perf_counter(); r = ix.hunt(pr, HuntParams(distance=1)); dt = time.perf_counter() - t
