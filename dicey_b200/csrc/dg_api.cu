@@ -38,14 +38,15 @@ void dg_index_close(dg_index* idx) {
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   if (idx->prof.created) for (auto& e : idx->prof.ev) cudaEventDestroy(e);
   cudaStream_t st = idx->stream, cs = idx->copy_stream;
-  cudaStream_t xs[3] = {idx->xstream[0], idx->xstream[1], idx->xstream[2]};
+  cudaStream_t xs[dg_index::kXStreams];
+  for (int i = 0; i < dg_index::kXStreams; ++i) xs[i] = idx->xstream[i];
   for (auto s2 : xs) if (s2) cudaStreamSynchronize(s2);
   if (cs) cudaStreamSynchronize(cs);
   cudaStream_t us = idx->up_stream;
   if (us) cudaStreamSynchronize(us);
   {
-    cudaStream_t all[4] = {st, xs[0], xs[1], xs[2]};
-    release_stream_pools(all, 4);
+    release_stream_pools(&st, 1);
+    release_stream_pools(xs, dg_index::kXStreams);
   }
   for (auto e : idx->ev_pool) cudaEventDestroy(e);
   delete idx;

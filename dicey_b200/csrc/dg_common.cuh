@@ -62,7 +62,8 @@ struct ProfileState {
 struct dg_index {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};   // extra compute streams of the chunk pipeline (dg_hunt_batch)
+  static constexpr int kXStreams = 6;
+  cudaStream_t xstream[kXStreams] = {};                     // compute streams of the chunk pipeline (dg_hunt_batch), descending priority
   cudaStream_t up_stream = nullptr;                         // its upload stream and the device copy of the caller's sequences
   dg::DevBuf<uint8_t> upload;
   std::vector<cudaEvent_t> ev_pool;                         // events of the chunk pipeline, created once and reused (creating or

@@ -1952,12 +1952,16 @@ struct ChunkPipe {
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     try {
       DG_CUDA(cudaSetDevice(idx->device));
-      cudaStream_t st = w == 0 ? idx->stream : idx->xstream[w - 1], cs = idx->copy_stream;
+      cudaStream_t cs = idx->copy_stream;
       std::vector<uint64_t> so;
       for (uint32_t c = (uint32_t)w; c < nchunks; c += (uint32_t)nworkers) {
         { std::lock_guard<std::mutex> g(mu); if (rc != DG_OK) break; }
         double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         tm[0] = now() - t_begin;
+        // chunk c runs on a stream of higher priority than chunks c + 1 and c + 2, which are in flight
+        // next to it: its pending blocks are dispatched first, so chunks finish -- and their records
+        // start leaving -- one after another instead of all together
+        cudaStream_t st = idx->xstream[c % (uint32_t)dg_index::kXStreams];
         // release chunks whose records have reached the host (keeps at most 2 per worker alive)
         while (!live.empty() && (live.size() >= 2 || cudaEventQuery(live.front().copied) == cudaSuccess)) {
           DG_CUDA(cudaEventSynchronize(live.front().copied));
@@ -2001,7 +2005,7 @@ struct ChunkPipe {
         }
         if (hit_base + b->nhits > idx->wire.count) {
           // grow (first call with this volume): keep what earlier chunks wrote
-          for (cudaStream_t s2 : {idx->stream, idx->xstream[0], idx->xstream[1], idx->xstream[2]}) if (s2) DG_CUDA(cudaStreamSynchronize(s2));
+          for (cudaStream_t s2 : idx->xstream) if (s2) DG_CUDA(cudaStreamSynchronize(s2));
           DevBuf<int4> bigger;
           bigger.alloc((size_t)(1.15 * (double)nq / (double)q1 * (double)(hit_base + b->nhits)) + 1024);
           if (hit_base) DG_CUDA(cudaMemcpy(bigger.p, idx->wire.p, hit_base * sizeof(int4), cudaMemcpyDeviceToDevice));
@@ -2074,8 +2078,13 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     p.nworkers = 3;
     if (const char* e = getenv("DG_WORKERS")) p.nworkers = std::min(4, std::max(1, atoi(e)));
     p.nworkers = (int)std::min<uint32_t>((uint32_t)p.nworkers, nchunks);
-    for (int w = 1; w < p.nworkers; ++w)
-      if (!idx->xstream[w - 1]) DG_CUDA(cudaStreamCreateWithFlags(&idx->xstream[w - 1], cudaStreamNonBlocking));
+    if (!idx->xstream[0]) {
+      int least = 0, greatest = 0;
+      DG_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));   // numerically lower = higher priority
+      const bool flat = getenv("DG_NO_PRIORITY") != nullptr;
+      for (int i = 0; i < dg_index::kXStreams; ++i)
+        DG_CUDA(cudaStreamCreateWithPriority(&idx->xstream[i], cudaStreamNonBlocking, flat ? least : std::min(least, greatest + i)));
+    }
     r = new dg_result();
     r->nq = nq;
     r->qoff.alloc(((size_t)nq + 1) * 8, true);
