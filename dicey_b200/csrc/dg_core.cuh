@@ -622,34 +622,51 @@ DG_HD int needle_banded_fill_t(const uint8_t* g, int mg, const uint8_t* s, int n
   uint64_t win = 0;
   for (int k = 0; k < W; ++k) win |= (uint64_t)qclass(0 - hi + k - 1) << (4 * k);
   int score = 0;
-  for (int row = 0; row <= mg; ++row) {
-    const uint32_t gc = row ? sym_class(g[row - 1]) : 0u;
+  // Row 0 (no genomic symbol yet): -col with a horizontal trace.  The rows after it are written
+  // without data-dependent branches: every band slot computes the recurrence from its three
+  // neighbours (slots outside the matrix hold kBandNeg and stay there) and the special cells
+  // (column 0, the free last column) are selected afterwards.
+  {
+    uint32_t bits = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < BAND; ++k) {
+      if (k < W) {
+        const int col = k - hi;
+        const bool inr = (unsigned)col <= (unsigned)n;
+        v[k] = inr ? -col : kBandNeg;
+        bits |= (uint32_t)((inr && col) ? 1 : 0) << (2 * k);
+        if (col == n) score = -col;
+      }
+    }
+    tr[0] = bits;
+    win = (win >> 4) | ((uint64_t)qclass(-hi + W - 1) << (4 * (W - 1)));
+  }
+  for (int row = 1; row <= mg; ++row) {
+    const uint32_t gc = sym_class(g[row - 1]);
     uint32_t bits = 0;
     const int c0 = row - hi;   // column of k = 0
+    int left_new = kBandNeg;   // value of the slot to the left in this row
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int k = 0; k < BAND; ++k) {
       if (k < W) {
         const int col = c0 + k;
-        int val = kBandNeg, t = 0;
-        if (col >= 0 && col <= n) {
-          if (row == 0) {
-            val = -col; t = col ? 1 : 0;
-          } else if (col == 0) {
-            val = 0; t = 2;
-          } else {
-            const uint32_t qc = (uint32_t)((win >> (4 * k)) & 15u);
-            const int diag = v[k] + (gc == qc ? 0 : -1);
-            const int up = (k + 1 < W ? v[k + 1] : kBandNeg) + (col == n ? 0 : -1);
-            const int left = (k ? v[k - 1] : kBandNeg) - 1;
-            val = diag > up ? diag : up;
-            if (left > val) val = left;
-            t = val == left ? 1 : (val == up ? 2 : 0);
-          }
-          if (col == n) score = val;
-        }
+        const bool inr = (unsigned)col <= (unsigned)n;
+        const uint32_t qc = (uint32_t)((win >> (4 * k)) & 15u);
+        const int diag = v[k] + (gc == qc ? 0 : -1);
+        const int up = (k + 1 < W ? v[k + 1] : kBandNeg) + (col == n ? 0 : -1);
+        const int left = left_new - 1;
+        int val = diag > up ? diag : up;
+        if (left > val) val = left;
+        int t = val == left ? 1 : (val == up ? 2 : 0);
+        if (col == 0) { val = 0; t = 2; }
+        if (!inr) { val = kBandNeg; t = 0; }
+        if (col == n) score = val;
         v[k] = val;
+        left_new = val;
         bits |= (uint32_t)t << (2 * k);
       }
     }
