@@ -13,6 +13,8 @@
 //   dicey-b200 search [OPTIONS] -g genome.fa.gz -i primer3_config/ primers.fasta             reference src/silica.h:208-660
 // `padlock` (probe design over GTF regions) is not part of this round; the library entry points it
 // would call (dg_count_batch, dg_thal_batch) exist and are tested.
+// DICEY_B200_TRACE=1 prints the wall time of every stage on stderr; DICEY_B200_THREADS bounds the
+// JSON formatting threads of `hunt`.
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -409,10 +411,6 @@ std::string revcomp_upper(const std::string& in) {  // util.h:54-114 on an upper
   }
   return s;
 }
-
-struct JsonRaw : JsonObject {
-  void set_double(const std::string& k, double v) { set_raw(k, json_double(v)); }
-};
 
 // writeJsonPrimerOut (silica.h:100-187)
 std::string search_json(const SilicaConfig& c, uint32_t distance, const std::vector<std::string>& qn, const std::vector<PrimerBind>& allp,
