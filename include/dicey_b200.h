@@ -161,7 +161,12 @@ int dg_index_debug_copy(dg_index* idx, const char* what, void* buf, uint64_t* by
  * With params->seed_len = k it is the FM / NW part of `dicey search` (silica.h:449-573):
  * the last k bases are the seed, contexts are extended by |primer|-k on the 5' side, and
  * each hit additionally carries alignpos; every candidate is returned (the thal Tm gate of
- * silica.h:508-519 stays with the caller).                                               */
+ * silica.h:508-519 is dg_thal_batch).
+ * seqs / offsets may live in ordinary or page-locked host memory (cudaHostAlloc,
+ * cudaHostRegister, a pinned torch tensor): large batches are cut into chunks that are
+ * uploaded, searched and read back as a pipeline, and page-locked input uploads without
+ * occupying the calling thread.  The result's buffers are page-locked when the driver
+ * grants it.                                                                              */
 int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint32_t nq,
                   const dg_params* params, dg_result** out);
 
