@@ -451,7 +451,7 @@ def main_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded by rank" + (", NCCL all-gather of the hit records every step" if world > 1 else ""),
-                       "global_primers_per_step": world * nq, "l2": "inputs larger than L2: random access into a 34 GB index",
+                       "global_primers_per_step": world * nq, "l2": f"inputs larger than L2: random access into {info['device_bytes'] / 1e9:.0f} GB of index tables",
                        "kmer_table_K": info["kmer"], "presence_bitmap_K": info["bitmap_k"], "index_device_bytes": info["device_bytes"],
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
             "clocks": clocks,
