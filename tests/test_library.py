@@ -51,6 +51,34 @@ def test_open_rejects_bad_files(tmp_path):
     assert e.value.code == -3          # wrong type hash
 
 
+def test_open_checks_the_fm9_framing(tmp_path):
+    """The .fm9 parser walks a read-only mapping of the file: a truncated copy of a real index, a copy
+    with trailing bytes and an empty file are format errors; the intact copy gets past the parser and
+    fails only for want of a GPU (this suite runs without one)."""
+    import shutil
+    src = os.path.join(GOLDEN, "t1m.fm9")
+    data = open(src, "rb").read()
+    check = open(src + "_check", "rb").read()
+
+    def try_open(payload):
+        f = tmp_path / "g.fm9"
+        f.write_bytes(payload)
+        (tmp_path / "g.fm9_check").write_bytes(check)
+        with pytest.raises(api.DiceyB200Error) as e:
+            api.Index.open(str(f), 0)
+        return e.value.code, str(e.value)
+
+    for cut in (0, 7, 16, len(data) // 3, len(data) - 2000, len(data) - 1):
+        code, msg = try_open(data[:cut])
+        assert code == -3 and "malformed .fm9" in msg, (cut, msg)
+    code, msg = try_open(data + b"\0")
+    assert code == -3 and "trailing bytes" in msg
+    import torch
+    if not torch.cuda.is_available():
+        code, msg = try_open(data)
+        assert code == -4 and "no CPU path" in msg   # parsed; no device to put it on
+
+
 def test_hits_sort_matches_dnahit_order():
     h = np.zeros(5, dtype=api.HIT_DTYPE)
     h["score"] = [-1, 0, -1, 0, -2]
