@@ -9,6 +9,8 @@
 #include <set>
 #include <string>
 #include <vector>
+#include <pthread.h>
+#include <thread>
 #include "../../dicey_b200/csrc/dg_core.cuh"
 #include "../../dicey_b200/csrc/fm9.hpp"
 #include "../../dicey_b200/csrc/fm9_select.hpp"
@@ -77,6 +79,50 @@ static void neighbors(const std::string& q, int d, bool indel, std::set<std::str
   }
 }
 
+// Eight cooperating lanes as threads: the Warp concept of dg_thal.cuh with its collectives built on a
+// barrier, so that the group logic the GPU kernel relies on (ballot compaction, one lane group per
+// cell of a row, arg-min within a group) runs -- with real concurrency -- in the CPU suite.
+struct LaneShared {
+  pthread_barrier_t bar;
+  unsigned pred[8];
+  double g[8], S[8], H[8];
+  uint32_t o[8];
+};
+struct ThalThreadLanes {
+  static constexpr int n = 8;
+  int lane = 0;
+  LaneShared* sh = nullptr;
+  void sync() const { pthread_barrier_wait(&sh->bar); }
+  unsigned ballot(bool p) const {
+    sh->pred[lane] = p ? 1u : 0u;
+    sync();
+    unsigned m = 0;
+    for (int i = 0; i < n; ++i) m |= sh->pred[i] << i;
+    sync();
+    return m;
+  }
+  unsigned lanemask_lt() const { return (1u << lane) - 1u; }
+  bool all(bool p) const { return ballot(p) == (1u << n) - 1u; }
+  bool any(bool p) const { return ballot(p) != 0u; }
+  unsigned group_mask(int first_lane, int lanes, bool member) const {
+    if (!member) return 1u << lane;
+    return lanes >= n ? (1u << n) - 1u : (((1u << lanes) - 1u) << first_lane);
+  }
+  void argmin(unsigned mask, double& g, uint32_t& o, double& S, double& H) const {
+    sh->g[lane] = g; sh->o[lane] = o; sh->S[lane] = S; sh->H[lane] = H;
+    sync();
+    int best = -1;
+    for (int i = 0; i < n; ++i) {
+      if (!((mask >> i) & 1u)) continue;
+      if (best < 0 || sh->g[i] < sh->g[best] || (sh->g[i] == sh->g[best] && sh->o[i] < sh->o[best])) best = i;
+    }
+    const double bg = sh->g[best], bS = sh->S[best], bH = sh->H[best];
+    const uint32_t bo = sh->o[best];
+    sync();
+    g = bg; o = bo; S = bS; H = bH;
+  }
+};
+
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
   std::string cmd = argv[1];
@@ -144,6 +190,47 @@ int main(int argc, char** argv) {
     }
     fprintf(stderr, "banded needle checked on %d (pair, dmax) cases\n", banded_checked);
     return banded_checked >= 100 ? 0 : 4;
+  }
+  if (cmd == "thal8" && argc >= 4) {
+    // the lane-cooperative arrangement on eight concurrent lanes (threads)
+    ThalParams tp;
+    std::string err;
+    if (!thal_params_from_dump(argv[2], tp, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    std::ifstream f(argv[3]);
+    std::string line;
+    LaneShared sh;
+    pthread_barrier_init(&sh.bar, nullptr, ThalThreadLanes::n);
+    while (std::getline(f, line)) {
+      size_t t = line.find('\t');
+      if (t == std::string::npos) continue;
+      std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+      const size_t cells = o1.size() * o2.size();
+      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2), codes(256);
+      std::vector<double> tab(2 * cells + 2);
+      std::vector<uint16_t> plist(cells + 1), rstart(o1.size() + 2);
+      double tms[ThalThreadLanes::n];
+      int rcs[ThalThreadLanes::n];
+      std::vector<std::thread> lanes;
+      for (int l = 0; l < ThalThreadLanes::n; ++l)
+        lanes.emplace_back([&, l] {
+          ThalThreadLanes wp;
+          wp.lane = l;
+          wp.sh = &sh;
+          rcs[l] = thal_end1_tm_lanes(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(),
+                                      n1.data(), n2.data(), tab.data(), plist.data(), rstart.data(), codes.data(), &tms[l]);
+        });
+      for (auto& th : lanes) th.join();
+      for (int l = 1; l < ThalThreadLanes::n; ++l)
+        if (rcs[l] != rcs[0] || memcmp(&tms[l], &tms[0], 8) != 0) { fprintf(stderr, "lanes disagree\n"); return 3; }
+      if (rcs[0] == 2) { fprintf(stderr, "sequential form requested\n"); return 3; }
+      uint64_t u;
+      memcpy(&u, &tms[0], 8);
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%.17g", tms[0]);
+      std::cout << rcs[0] << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
+    }
+    pthread_barrier_destroy(&sh.bar);
+    return 0;
   }
   if (cmd == "thal2" && argc >= 4) {
     // the lane-cooperative arrangement of dg_thal.cuh (what the GPU kernel runs) with one lane

@@ -117,6 +117,24 @@ def test_thal_lane_cooperative_form_is_bit_exact():
         assert got == open(os.path.join(GOLDEN, name + ".out.tsv")).read(), name
 
 
+def test_thal_lane_groups_on_eight_concurrent_lanes():
+    """The same template on eight lanes that really run side by side (threads; ballot, lane groups
+    and the group arg-min built on a barrier): what the warp does on the GPU -- list compaction,
+    one lane group per paired cell of a row, first-minimum selection -- must reproduce the
+    reference's bits for the primer-like golden set and the first 300 pairs at the limits of the DP."""
+    got = run(HOSTSIM, ["thal8", "thal.params.tsv", "thal.pairs.tsv"])
+    assert got == open(os.path.join(GOLDEN, "thal.out.tsv")).read()
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".tsv", delete=False) as f:
+        f.write("".join(open(os.path.join(GOLDEN, "thal_long.pairs.tsv")).readlines()[:300]))
+        part = f.name
+    try:
+        got = run(HOSTSIM, ["thal8", "thal.params.tsv", part])
+        assert got.splitlines() == open(os.path.join(GOLDEN, "thal_long.out.tsv")).read().splitlines()[:300]
+    finally:
+        os.unlink(part)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/primer3_config"), reason="needs the reference's primer3_config directory")
 def test_thal_config_loader_reproduces_the_reference_tables():
     """thal_params_from_config (what the product reads: dicey's -i directory) against the tables the
