@@ -12,6 +12,13 @@
 //   run_seed    restates  src/silica.h:449-573   FM/NW part of `search` (thal gate left out:
 //                                                 every candidate is reported)
 //   cmd_padcount restates src/padlock.h:381-427  (exact + neighbourhood count totals)
+//   cmd_thal    calls     src/thal.h verbatim    (get_thermodynamic_values + thal(), thal_end1, temponly:
+//                                                 one temperature per (oligo, site) line; dumps the tables)
+//   cmd_search  restates  src/silica.h:208-660   (`search` end to end around the verbatim SDSL / neighbors.h /
+//                                                 needle.h / thal.h / nlohmann code: Tm gate, de-duplication,
+//                                                 amplicon pairing, penalties, writeJsonPrimerOut)
+//   cmd_jsonfloat prints  nlohmann::json(double).dump() for 64-bit patterns (the number format the
+//                                                 product's jsonnum.hpp must reproduce)
 //
 // Built by oracle/Makefile into oracle/_ref/ (git-ignored, travels to the GPU box).
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
