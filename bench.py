@@ -66,7 +66,39 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: primers per step (0 = auto)")
     ap.add_argument("--fm9-dir", default=None)
+    ap.add_argument("--ramp", type=int, default=60, help="extra untimed resident steps after the W warm-up steps (clock ramp); "
+                    "a fixed count, identical on every rank, because every step holds a collective")
+    ap.add_argument("--ramp-e2e", type=int, default=25, help="the same for the end-to-end arm")
+    ap.add_argument("--gather-to-host", action="store_true", help="N > 1: rank 0 also copies the gathered coordinate table "
+                    "of all ranks to its host inside every end-to-end step")
     return ap.parse_args()
+
+
+class Watchdog:
+    """A multi-rank run that stops making progress names itself instead of sitting in a collective
+    until torch's watchdog fires: every rank records its last milestone; if none is reached for
+    `limit` seconds the rank prints where it is and exits."""
+
+    def __init__(self, rank: int, limit: float = 150.0):
+        self.rank, self.limit, self.where, self.t = rank, limit, "start", time.time()
+        self._stop = threading.Event()
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def mark(self, where: str):
+        self.where, self.t = where, time.time()
+        if os.environ.get("BENCH_PROGRESS"):
+            print(f"[bench rank {self.rank}] {where}", file=sys.stderr, flush=True)
+
+    def _run(self):
+        while not self._stop.wait(2.0):
+            if time.time() - self.t > self.limit:
+                print(f"[bench rank {self.rank}] no progress for {self.limit:.0f} s after milestone '{self.where}': giving up",
+                      file=sys.stderr, flush=True)
+                os._exit(3)
+
+    def stop(self):
+        self._stop.set()
 
 
 class ClockSampler:
@@ -260,8 +292,11 @@ def main_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (dicey_b200 has no CPU path)")
     torch.cuda.set_device(local)
+    dog = Watchdog(rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
+    dog.mark("process group up")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -270,9 +305,11 @@ def main_b200(args):
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
     ix, build_s = build_index(args, local)
+    dog.mark("index built")
     info = ix.info()
     params = HuntParams(distance=args.distance, hamming=args.hamming)
     primers = make_primers(args, rank)
+    dog.mark("primers made")
     nq = primers.shape[0]
     # pinned host copies of the inputs
     pin = torch.empty(primers.size, dtype=torch.uint8, pin_memory=True)
@@ -289,25 +326,29 @@ def main_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm: queries staged once, every kernel per step; with more than
-    # one rank each step ends with the path's one exchange step, the NCCL all-gather of the hit
-    # records, straight from device memory
+    # one rank each step ends with the path's one exchange step: dg_allgather_hits, ONE ncclAllGather of
+    # the 16-byte hit records issued on the index stream behind the step's kernels (C ABI, dg_comm.cu)
     from dicey_b200 import shard
+    comm = shard.comm_from_process_group(ix) if world > 1 else None
+    dog.mark("communicator up")
+    qbase = rank * nq
+    gathered = [0]
 
     def resident_step(batch):
         batch.run()
+        if comm is not None:
+            _, _, counts = comm.allgather_hits(batch, qbase)   # synchronises the index stream
+            gathered[0] = int(counts.sum())
         batch.summary()          # synchronises the index stream; collects the stage timings
-        if world > 1:
-            shard.allgather_hits_device(batch)
-            torch.cuda.current_stream().synchronize()
 
     batch = ix.stage(seqs, params)
-    for _ in range(args.warmup):
+    # W warm-up steps, then a FIXED number of further untimed steps: the GPU idles while the primers are
+    # generated on the host and needs a few hundred ms of load to come back to its boost clock.  (A
+    # wall-clock bound here would let ranks run different numbers of steps -- and every step holds a
+    # collective.)
+    for i in range(args.warmup + args.ramp):
         resident_step(batch)
-    # the GPU idles while the primers are generated on the host and needs a few hundred ms of load
-    # to come back to its boost clock: keep warming (untimed) for 0.4 s beyond the W requested steps
-    t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 0.4:
-        resident_step(batch)
+    dog.mark("resident warm-up done")
     ix.profile(True)
     sampler = ClockSampler(local)
     barrier()
@@ -321,6 +362,7 @@ def main_b200(args):
         sampler.sample()         # right after the step's synchronisation: the clock it ran at
     e1.record(stream)
     barrier()
+    dog.mark("resident arm timed")
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     nhits, ncand = batch.summary()
@@ -333,32 +375,23 @@ def main_b200(args):
     batch.free()
 
     # ---------------- end-to-end arm: host buffers through the C ABI: dg_hunt_batch (H2D of the queries,
-    # every kernel, D2H of every hit record and alignment).  With several ranks the hit records are then
-    # all-gathered (16-byte wire records: coordinates, strand, distance) and rank 0 reads the gathered
-    # records of all ranks back to its host.
-    gathered_pin = None
-
+    # every kernel, D2H of every hit record and alignment of this rank's shard to this rank's host).
+    # With several ranks the 16-byte hit records (coordinates, strand, distance, global query id) are
+    # then all-gathered on the device (dg_allgather_hits), so every rank holds the coordinate table of
+    # the whole batch in HBM; with --gather-to-host rank 0 also copies that table to its host.
     def e2e_step():
-        nonlocal gathered_pin
         res = ix.hunt(seqs, params)          # H2D, every kernel, D2H of every record (chunk-pipelined)
-        if world == 1:
+        if comm is None:
             return res, 0
-        allb, _ = shard.allgather_hits_index(ix)
+        comm.allgather_hits(None, qbase)
         extra = 0
-        if rank == 0:
-            nb = allb.numel() * 4
-            if gathered_pin is None or gathered_pin.numel() < nb:
-                gathered_pin = torch.empty(int(nb * 1.1), dtype=torch.uint8, pin_memory=True)
-            gathered_pin[:nb].copy_(allb.view(torch.uint8).view(-1), non_blocking=True)
-            extra = nb
-        torch.cuda.current_stream().synchronize()
+        if args.gather_to_host and rank == 0:
+            extra = comm.fetch_table().nbytes
         return res, extra
 
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(min(args.warmup, 2) + args.ramp_e2e):
         res, _ = e2e_step()
-    t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 0.3:
-        res, _ = e2e_step()
+    dog.mark("e2e warm-up done")
     barrier()
     t0 = time.perf_counter()
     d2h = 0
@@ -370,6 +403,7 @@ def main_b200(args):
         d2h = res.hits.nbytes + res.pool.nbytes + res.qoff.nbytes + res.status.nbytes + res.dist.nbytes + res.seqs.nbytes + extra
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    dog.mark("e2e arm timed")
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,6 +427,8 @@ def main_b200(args):
     work = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu and cpu_binary()[0]:
+        dog.limit = 1200.0      # no collectives from here on: the CPU leg may take its time
+        dog.mark("cpu leg")
         try:
             fm9, rec, write_s = ensure_fm9(ix, args)
             cores = os.cpu_count() or 1
@@ -450,23 +486,29 @@ def main_b200(args):
             "metric": "primers/sec (3 Gb ref, edit-dist 1)", "value": value, "unit": "primers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded by rank" + (", NCCL all-gather of the hit records every step" if world > 1 else ""),
+            "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded by rank" + (", one ncclAllGather of the 16-byte hit records per step on the index stream (dg_allgather_hits)" if world > 1 else ""),
+                       "gathered_hits_per_step": gathered[0] if world > 1 else None,
+                       "e2e_gather_to_host": bool(args.gather_to_host) if world > 1 else None,
                        "global_primers_per_step": world * nq, "l2": f"inputs larger than L2: random access into {info['device_bytes'] / 1e9:.0f} GB of index tables",
                        "kmer_table_K": info["kmer"], "presence_bitmap_K": info["bitmap_k"], "index_device_bytes": info["device_bytes"],
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "primers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "phases_ms_stage_run_fetch_free": phases, "hunt_call_ms": step_ms},
-            "gpu_launches": int(sum(p["launches"] for p in profs)),
+            "gpu_launches": int(sum(p["launches"] for p in profs)) + (2 * args.steps if world > 1 else 0),
             "stages_ms": stage, "step_ms_total": [round(p["ms_total"], 3) for p in profs],
             "roofline": roof,
             "cpu_baseline": cpu,
             "parity": parity,
         }
         print(json.dumps(line))
+    dog.mark("line printed")
+    if comm is not None:
+        comm.close()
     ix.close()
     if world > 1:
         dist.destroy_process_group()
+    dog.stop()
     return 0
 
 

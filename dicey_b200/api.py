@@ -68,7 +68,13 @@ EXPORTS = [
     "dg_result_query_status", "dg_result_query_distance", "dg_result_pool", "dg_result_sequences",
     "dg_result_free", "dg_hits_sort", "dg_result_pack", "dg_result_unpack", "dg_profile_enable",
     "dg_profile_get", "dg_last_error", "dg_version",
+    "dg_comm_get_unique_id", "dg_comm_init", "dg_comm_init_host", "dg_comm_rank", "dg_comm_size", "dg_comm_destroy",
+    "dg_allgather_hits", "dg_comm_fetch_table", "dg_allgather_result",
 ]
+
+WIRE_DTYPE = np.dtype([("query", "<u4"), ("chr", "<u4"), ("start", "<u4"), ("score", "<i2"), ("strand", "u1"), ("reserved", "u1")])
+assert WIRE_DTYPE.itemsize == 16
+HOST_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 
 
 def library() -> C.CDLL:
@@ -134,6 +140,16 @@ def library() -> C.CDLL:
     lib.dg_result_unpack.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     lib.dg_profile_enable.argtypes = [vp, C.c_int]
     lib.dg_profile_get.argtypes = [vp, C.POINTER(_Profile)]
+    lib.dg_comm_get_unique_id.argtypes = [vp]
+    lib.dg_comm_init.argtypes = [C.c_int, C.c_int, vp, vp, C.POINTER(vp)]
+    lib.dg_comm_init_host.argtypes = [C.c_int, C.c_int, HOST_ALLGATHER_FN, vp, C.POINTER(vp)]
+    lib.dg_comm_rank.argtypes = [vp]
+    lib.dg_comm_size.argtypes = [vp]
+    lib.dg_comm_destroy.argtypes = [vp]
+    lib.dg_comm_destroy.restype = None
+    lib.dg_allgather_hits.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p, C.POINTER(vp)]
+    lib.dg_comm_fetch_table.argtypes = [vp, vp, C.c_uint64, u64p]
+    lib.dg_allgather_result.argtypes = [vp, vp, C.POINTER(vp)]
     _lib = lib
     return lib
 
@@ -276,6 +292,45 @@ class HuntResult:
         return msg
 
 
+def collect_result(res, seq_off) -> HuntResult:
+    """A HuntResult of views into a library-owned dg_result (freed with the HuntResult)."""
+    lib = library()
+    n = C.c_uint64(0)
+    hp = lib.dg_result_hits(res, C.byref(n))
+    hits = _from_ptr(hp, n.value * HIT_DTYPE.itemsize, HIT_DTYPE)
+    nq = C.c_uint32(0)
+    qp = lib.dg_result_query_offsets(res, C.byref(nq))
+    qoff = _from_ptr(qp, (nq.value + 1) * 8, np.uint64)
+    status = _from_ptr(lib.dg_result_query_status(res), nq.value * 4, np.uint32)
+    dist = _from_ptr(lib.dg_result_query_distance(res), nq.value * 4, np.uint32)
+    nb = C.c_uint64(0)
+    pp = lib.dg_result_pool(res, C.byref(nb))
+    pool = _from_ptr(pp, nb.value, np.uint8)
+    sp = lib.dg_result_sequences(res, C.byref(nb))
+    seqs = _from_ptr(sp, nb.value, np.uint8)
+    return HuntResult(hits, qoff, status, dist, pool, seqs, seq_off, res)
+
+
+def pack_result(res: HuntResult) -> np.ndarray:
+    """dg_result_pack: the flat wire format of one result (a uint8 array)."""
+    if res._res is None:
+        raise ValueError("result has been closed")
+    lib = library()
+    nb = C.c_uint64(0)
+    _check(lib.dg_result_pack(res._res, None, C.byref(nb)))
+    buf = np.empty(nb.value, dtype=np.uint8)
+    _check(lib.dg_result_pack(res._res, buf.ctypes.data, C.byref(nb)))
+    return buf
+
+
+def unpack_result(buf: np.ndarray, seq_off=None) -> HuntResult:
+    """dg_result_unpack: a HuntResult from the wire format."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    h = C.c_void_p()
+    _check(library().dg_result_unpack(buf.ctypes.data, buf.size, C.byref(h)))
+    return collect_result(h.value, seq_off)
+
+
 class Index:
     """The device-resident FM-index (one per GPU)."""
 
@@ -358,21 +413,7 @@ class Index:
 
     # -- queries -------------------------------------------------------------------------
     def _collect(self, res, seq_off) -> HuntResult:
-        lib = library()
-        n = C.c_uint64(0)
-        hp = lib.dg_result_hits(res, C.byref(n))
-        hits = _from_ptr(hp, n.value * HIT_DTYPE.itemsize, HIT_DTYPE)
-        nq = C.c_uint32(0)
-        qp = lib.dg_result_query_offsets(res, C.byref(nq))
-        qoff = _from_ptr(qp, (nq.value + 1) * 8, np.uint64)
-        status = _from_ptr(lib.dg_result_query_status(res), nq.value * 4, np.uint32)
-        dist = _from_ptr(lib.dg_result_query_distance(res), nq.value * 4, np.uint32)
-        nb = C.c_uint64(0)
-        pp = lib.dg_result_pool(res, C.byref(nb))
-        pool = _from_ptr(pp, nb.value, np.uint8)
-        sp = lib.dg_result_sequences(res, C.byref(nb))
-        seqs = _from_ptr(sp, nb.value, np.uint8)
-        return HuntResult(hits, qoff, status, dist, pool, seqs, seq_off, res)
+        return collect_result(res, seq_off)
 
     def hunt(self, seqs, params: HuntParams | None = None) -> HuntResult:
         """hunter.h:289-433 for every query of the batch (one library call, host buffers)."""
@@ -438,6 +479,79 @@ class Batch:
     def free(self) -> None:
         if self._h:
             library().dg_batch_free(self._h)
+            self._h = None
+
+
+class Comm:
+    """One rank of the multi-GPU exchange (include/dicey_b200.h, "multi-GPU"): NCCL over the index
+    stream (``Comm.init``) or a caller-supplied host all-gather (``Comm.init_host``, CPU tests)."""
+
+    ID_BYTES = 128
+
+    def __init__(self, handle: int, nranks: int, rank: int, keep=None):
+        self._h, self.nranks, self.rank, self._keep = handle, nranks, rank, keep
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * Comm.ID_BYTES)()
+        _check(library().dg_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def init(cls, nranks: int, rank: int, uid: bytes, index: "Index") -> "Comm":
+        h = C.c_void_p()
+        idb = (C.c_uint8 * Comm.ID_BYTES).from_buffer_copy(uid)
+        _check(library().dg_comm_init(nranks, rank, idb, index._h, C.byref(h)))
+        return cls(h.value, nranks, rank)
+
+    @classmethod
+    def init_host(cls, nranks: int, rank: int, allgather) -> "Comm":
+        """allgather(send: np.ndarray[uint8, n]) -> np.ndarray[uint8, nranks * n] in rank order."""
+        def _cb(ctx, send, recv, nbytes):
+            try:
+                a = np.frombuffer((C.c_uint8 * nbytes).from_address(send), dtype=np.uint8) if nbytes else np.zeros(0, np.uint8)
+                out = np.ascontiguousarray(allgather(a), dtype=np.uint8)
+                if out.size != nbytes * nranks:
+                    return 2
+                if out.size:
+                    C.memmove(recv, out.ctypes.data, out.size)
+                return 0
+            except Exception:
+                return 1
+        fn = HOST_ALLGATHER_FN(_cb)
+        h = C.c_void_p()
+        _check(library().dg_comm_init_host(nranks, rank, fn, None, C.byref(h)))
+        return cls(h.value, nranks, rank, keep=fn)
+
+    def allgather_hits(self, batch: "Batch | None" = None, query_base: int = 0):
+        """The exchange step on device memory: (device address of the slot table, records per slot,
+        per-rank hit counts).  Rank r's records start at table + (r * slot + 1) * 16 bytes."""
+        t, slot, cn = C.c_void_p(), C.c_uint64(0), C.c_void_p()
+        _check(library().dg_allgather_hits(self._h, batch._h if batch is not None else None, query_base, C.byref(t), C.byref(slot),
+                                           C.byref(cn)))
+        counts = _from_ptr(cn.value, 8 * self.nranks, np.uint64).copy()
+        return int(t.value or 0), int(slot.value), counts
+
+    def fetch_table(self) -> np.ndarray:
+        """The gathered wire records on the host, compacted in rank order."""
+        n = C.c_uint64(0)
+        _check(library().dg_comm_fetch_table(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=WIRE_DTYPE)
+        if n.value:
+            _check(library().dg_comm_fetch_table(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def allgather_result(self, res: "HuntResult", seq_off=None) -> "HuntResult":
+        """Complete results of every rank, merged in rank order (query ids and offsets rebased)."""
+        if res._res is None:
+            raise ValueError("result has been closed")
+        g = C.c_void_p()
+        _check(library().dg_allgather_result(self._h, res._res, C.byref(g)))
+        return collect_result(g.value, seq_off)
+
+    def close(self) -> None:
+        if self._h:
+            library().dg_comm_destroy(self._h)
             self._h = None
 
 

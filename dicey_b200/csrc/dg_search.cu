@@ -943,6 +943,7 @@ struct VerifyArgs {
   uint64_t key_base;
   uint64_t nhits;
   dg_hit* hits;
+  int4* wire;                // 16-byte wire record per hit (dg_wire): what the multi-GPU all-gather moves
   uint8_t* pool;             // alignment pool: strings back to back, claimed block by block
   unsigned long long* pool_cursor;
   uint8_t* scratch;          // NW scratch for alignments too large for the thread-local paths
@@ -1098,6 +1099,7 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     }
   }
   a.hits[h] = out;
+  a.wire[h] = make_int4((int)out.query, (int)out.chr, (int)out.start, (int)(((uint32_t)out.score & 0xFFFFu) | ((uint32_t)out.strand << 16)));
 }
 
 __global__ void k_fill_offsets(uint64_t* __restrict__ off, uint64_t n, uint64_t len) {
@@ -1179,6 +1181,11 @@ void release_stream_pools(const cudaStream_t* streams, int n) {
 }  // namespace dg
 
 using namespace dg;
+
+struct dg_batch;
+namespace dg {
+int batch_wire_view(dg_batch* b, const int4** wire, uint64_t* n, cudaStream_t* st, dg_index** ix);
+}
 
 // ============================================================================================
 // Host-side result storage.  Results fetched from the device land in page-locked memory (so the
@@ -1288,6 +1295,7 @@ struct dg_batch {
   ABuf<Cand> cands;
   uint32_t ncand = 0;
   ABuf<dg_hit> hits;
+  ABuf<int4> wire;
   ABuf<uint8_t> pool;
   ABuf<unsigned long long> qhits;
   ABuf<uint64_t> qoff;
@@ -1297,6 +1305,15 @@ struct dg_batch {
   uint32_t pool_stride = 0;
   bool ran = false;
 };
+
+int dg::batch_wire_view(dg_batch* b, const int4** wire, uint64_t* n, cudaStream_t* st, dg_index** ix) {
+  if (!b || !b->ran || b->counts_only) { set_error("batch has not run"); return DG_ERR_ARG; }
+  *wire = b->nhits ? b->wire.p : nullptr;
+  *n = b->nhits;
+  *st = b->st;
+  *ix = b->ix;
+  return DG_OK;
+}
 
 static BatchDev batch_dev(const dg_batch* b) {
   BatchDev d;
@@ -1727,6 +1744,7 @@ static int run_impl(dg_batch* b) {
     uint32_t aln_max = (uint32_t)(maxg + maxq);
     b->pool_stride = b->par.seed_len ? (uint32_t)maxg : (b->par.indel ? 2 * aln_max : (uint32_t)(maxg + maxq));
     b->hits.alloc(nhits ? nhits : 1, st);
+    b->wire.alloc(nhits ? nhits : 1, st);
     b->pool.alloc(nhits ? nhits * b->pool_stride : 1, st);   // upper bound; pool_bytes of it are used
     b->pool_bytes = 0;
     ABuf<unsigned long long> cursor;
@@ -1759,7 +1777,7 @@ static int run_impl(dg_batch* b) {
       if (hit1 > hit0) {
         VerifyArgs a;
         a.cands = cur; a.ncand = n; a.hit_off = hit_off.p; a.loc_off = loc_off.p; a.keys = keys2.p; a.key_base = row0; a.nhits = nhits;
-        a.hits = b->hits.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
+        a.hits = b->hits.p; a.wire = b->wire.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
         a.srow_ints = (uint32_t)(maxq + 2);
         a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
         a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);

@@ -216,8 +216,60 @@ void dg_result_free(dg_result* r);
 void dg_hits_sort(dg_hit* hits, uint64_t n);
 
 /* ---- multi-GPU ---------------------------------------------------------------------- */
-/* The hit all-gather is done by the host layer over torch.distributed /
- * NCCL on flat byte buffers; these two calls give it the wire format.                    */
+/* The path shards by independent queries (hunter.h:291, silica.h:429: every iteration of the
+ * per-query loop reads the index only): the index is replicated on every GPU, rank r of nranks
+ * (one process or one host thread per GPU) owns a contiguous shard of the query batch, and ONE
+ * exchange step collects the hit records -- an all-gather.
+ *
+ * dg_comm_init binds rank `rank` of `nranks` to the device and stream of `idx`; every rank passes
+ * the 128-byte id rank 0 got from dg_comm_get_unique_id (sent through whatever channel the
+ * launcher has: torch.distributed broadcast, MPI, a file).  The transport is NCCL (libnccl.so.2 is
+ * loaded at run time, so a process that already holds torch's copy shares it).
+ * dg_comm_init_host builds a communicator over a caller-supplied all-gather of HOST buffers
+ * (send: bytes_per_rank bytes, recv: nranks * bytes_per_rank, rank order) -- for fabrics other
+ * than NCCL and for the CPU tests (gloo); it supports dg_allgather_result only.            */
+typedef struct dg_comm dg_comm;
+#define DG_COMM_ID_BYTES 128
+typedef int (*dg_host_allgather_fn)(void* ctx, const void* send, void* recv, uint64_t bytes_per_rank);
+int dg_comm_get_unique_id(void* id);
+int dg_comm_init(int nranks, int rank, const void* id, dg_index* idx, dg_comm** out);
+int dg_comm_init_host(int nranks, int rank, dg_host_allgather_fn fn, void* ctx, dg_comm** out);
+int dg_comm_rank(const dg_comm* c);
+int dg_comm_size(const dg_comm* c);
+void dg_comm_destroy(dg_comm* c);
+
+/* One hit on the wire: coordinates, strand and distance (alignment strings stay with the rank
+ * that owns the query).  query is the GLOBAL query index (local index + query_base).        */
+typedef struct {
+  uint32_t query;
+  uint32_t chr;        /* refIndex                                                          */
+  uint32_t start;      /* DnaHit.start                                                      */
+  int16_t score;       /* -(edit or Hamming distance)                                       */
+  uint8_t strand;      /* '+' or '-'                                                        */
+  uint8_t reserved;
+} dg_wire;
+
+/* The exchange step on device memory: the hit records of `b` (a batch that has run; NULL = the
+ * last dg_hunt_batch on the communicator's index) are all-gathered straight from HBM with ONE
+ * ncclAllGather issued on the index stream behind the batch's kernels -- no host round trip
+ * between the kernels and the collective.  Every rank sends a fixed-size slot (a 16-byte header
+ * holding its hit count, then `slot_records - 1` record places); the slot size is agreed once per
+ * communicator and grows, on every rank alike, only when a rank's count no longer fits (the
+ * all-gather is then repeated once).  On return *table points at nranks slots in DEVICE memory
+ * (rank r's records start at table + r * slot_records + 1), counts[r] (HOST memory, owned by the
+ * communicator) is the number of hits of rank r; both stay valid until the next call.       */
+int dg_allgather_hits(dg_comm* c, dg_batch* b, uint64_t query_base, const dg_wire** table,
+                      uint64_t* slot_records, const uint64_t** counts);
+/* Device -> host copy of the gathered records, compacted in rank order (sum of counts entries). */
+int dg_comm_fetch_table(dg_comm* c, dg_wire* out, uint64_t capacity, uint64_t* n);
+
+/* The same exchange for complete results (records, alignment strings, per-query status and the
+ * normalised queries): every rank passes its local dg_result and receives the result of the whole
+ * batch, query ids / offsets rebased in rank order -- what rank 0 of a multi-process `hunt` needs to
+ * print the JSON of every query.  Works on either transport.                                  */
+int dg_allgather_result(dg_comm* c, const dg_result* local, dg_result** global);
+
+/* Flat wire format of one result (what dg_allgather_result moves).                          */
 int dg_result_pack(const dg_result* r, void* buf, uint64_t* bytes);   /* buf NULL -> size  */
 int dg_result_unpack(const void* buf, uint64_t bytes, dg_result** out);
 

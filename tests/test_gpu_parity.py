@@ -278,20 +278,36 @@ def test_alternative_paths_give_the_same_records(indexes, monkeypatch, knob, cas
 
 
 @pytest.mark.parametrize("chunk", ["100000000", "1500"])
-def test_wire_records_in_hbm(indexes, monkeypatch, chunk):
-    """dg_index_wire_records: the 16-byte records the multi-GPU exchange all-gathers from device memory."""
-    import torch
-    from dicey_b200 import shard
+def test_allgather_hits_nccl_world1(indexes, monkeypatch, chunk):
+    """dg_comm_init / dg_allgather_hits / dg_comm_fetch_table on one GPU (an NCCL communicator of one
+    rank): the 16-byte wire records of the last dg_hunt_batch and of a resident batch, with global
+    query ids, through slot growth (a 64-record slot to start with)."""
+    from dicey_b200.api import Comm
     ix = indexes["t1m"]
     monkeypatch.setenv("DG_CHUNK", chunk)
+    monkeypatch.setenv("DG_COMM_SLOT", "64")
     pr = synth.primers_fast(42, 8, 125000, 5000, 20, 1, True, rng_seed=5)
-    res = ix.hunt(pr, HuntParams(distance=1))
-    ptr, n = ix.wire_records()
-    assert n == len(res.hits) > 2000
-    wire = torch.as_tensor(shard._DeviceBytes(ptr, n * 16), device="cuda").view(torch.int32).view(-1, 4).cpu().numpy()
-    got = shard.unwire_records(wire)
-    for f in ("query", "chr", "start", "score", "strand"):
-        assert np.array_equal(got[f], res.hits[f]), f
+    par = HuntParams(distance=1)
+    comm = Comm.init(1, 0, Comm.unique_id(), ix)
+    try:
+        res = ix.hunt(pr, par)
+        table, slot, counts = comm.allgather_hits(None, query_base=1000)
+        assert int(counts[0]) == len(res.hits) > 2000 and slot > len(res.hits)
+        got = comm.fetch_table()
+        assert np.array_equal(got["query"], res.hits["query"] + 1000)
+        for f in ("chr", "start", "score", "strand"):
+            assert np.array_equal(got[f], res.hits[f]), f
+        # a resident batch (dg_batch_stage / run), smaller than the grown slot: one all-gather, same table
+        bt = ix.stage(pr[:700], par)
+        bt.run()
+        table2, slot2, counts2 = comm.allgather_hits(bt, query_base=7)
+        r2 = bt.fetch()
+        got2 = comm.fetch_table()
+        assert slot2 == slot and int(counts2[0]) == len(r2.hits) == len(got2)
+        assert np.array_equal(got2["query"], r2.hits["query"] + 7) and np.array_equal(got2["start"], r2.hits["start"])
+        bt.free()
+    finally:
+        comm.close()
 
 
 def test_thal_gpu_is_bit_exact(monkeypatch):

@@ -107,18 +107,59 @@ def fake_result(nq, hits_per_q, tag):
                            np.ones(nq, np.uint32).view(np.uint8), hits.view(np.uint8), pool, seqs])
 
 
-def test_pack_unpack_merge_roundtrip():
-    a = shard.unpack_result(fake_result(3, 2, 7))
-    b = shard.unpack_result(fake_result(2, 1, 9))
+def test_pack_unpack_roundtrip():
+    a = shard.unpack_result(fake_result(3, 2, 7), np.arange(4, dtype=np.uint64) * 10)
     assert a.nq == 3 and len(a.hits) == 6 and a.push_hits(1)[0][4:] == ("ACGT", "ACGA")
     assert np.array_equal(shard.pack_result(a), fake_result(3, 2, 7))
-    so = [np.arange(4, dtype=np.uint64) * 10, np.arange(3, dtype=np.uint64) * 10 + 30]
-    m = shard.merge_results([a, b], so)
-    assert m.nq == 5 and len(m.hits) == 8
-    assert [int(x) for x in m.qoff] == [0, 2, 4, 6, 7, 8]
-    assert m.push_hits(4) == [(-1, 9, 2, "+", "ACGT", "ACGA")]
-    assert m.sequence(3) == b"ACGTACGTAC"
+    assert a.sequence(2) == b"ACGTACGTAC"
     assert shard.shard_bounds(10, 4) == [0, 2, 5, 7, 10]
+
+
+def test_allgather_result_merges_in_rank_order():
+    """dg_allgather_result over the host transport (dg_comm_init_host), three ranks played by three
+    threads of this process that meet in a barrier-style all-gather."""
+    import threading
+    world = 3
+    lock, cond = threading.Lock(), threading.Condition()
+    state = {"round": 0, "parts": {}, "done": {}}
+
+    def make_allgather(rank):
+        def allgather(send):
+            with cond:
+                rnd = state["round"]
+                state["parts"][rank] = bytes(send)
+                if len(state["parts"]) == world:
+                    state["done"][rnd] = b"".join(state["parts"][r] for r in range(world))
+                    state["parts"] = {}
+                    state["round"] += 1
+                    cond.notify_all()
+                else:
+                    cond.wait_for(lambda: rnd in state["done"], timeout=30)
+                return np.frombuffer(state["done"][rnd], dtype=np.uint8)
+        return allgather
+
+    out = {}
+
+    def run(rank):
+        comm = api.Comm.init_host(world, rank, make_allgather(rank))
+        mine = shard.unpack_result(fake_result(rank + 1, rank + 1, 20 + rank))
+        out[rank] = comm.allgather_result(mine, np.arange(7, dtype=np.uint64) * 10)
+        assert (comm.rank, comm.nranks) == (rank, world)
+        comm.close()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    for r in range(world):
+        m = out[r]
+        assert m.nq == 6 and len(m.hits) == 1 + 4 + 9
+        assert [int(x) for x in m.qoff] == [0, 1, 3, 5, 8, 11, 14]
+        assert [int(x) for x in m.hits["chr"]] == [20] + [21] * 4 + [22] * 9
+        assert [int(x) for x in m.hits["query"]] == [0, 1, 1, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5]
+        assert m.push_hits(5)[2] == (-1, 22, 9, "+", "ACGT", "ACGA")
+        assert m.sequence(4) == b"ACGTACGTAC"
 
 
 def test_synth_generator_is_windowable():
