@@ -400,7 +400,8 @@ def main_b200(args):
         ts = time.perf_counter()
         res, extra = e2e_step()
         step_ms.append(round(1e3 * (time.perf_counter() - ts), 3))
-        d2h = res.hits.nbytes + res.pool.nbytes + res.qoff.nbytes + res.status.nbytes + res.dist.nbytes + res.seqs.nbytes + extra
+        d2h = res.transfer_bytes + extra      # counted by the library from the copies it issued
+        e2e_hits = len(res.records)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     dog.mark("e2e arm timed")
@@ -494,6 +495,7 @@ def main_b200(args):
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "primers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                    "records_per_step": int(e2e_hits), "record_bytes": 24,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "phases_ms_stage_run_fetch_free": phases, "hunt_call_ms": step_ms},
             "gpu_launches": int(sum(p["launches"] for p in profs)) + (2 * args.steps if world > 1 else 0),
             "stages_ms": stage, "step_ms_total": [round(p["ms_total"], 3) for p in profs],

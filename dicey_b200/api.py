@@ -62,7 +62,7 @@ _lib = None
 EXPORTS = [
     "dg_index_open", "dg_index_build_text", "dg_index_build_synthetic", "dg_index_write_fm9", "dg_index_close",
     "dg_index_size", "dg_index_set_records", "dg_index_get_info", "dg_index_stream", "dg_index_debug_copy",
-    "dg_hunt_batch", "dg_batch_stage", "dg_batch_run", "dg_batch_fetch", "dg_batch_summary", "dg_batch_device_hits",
+    "dg_hunt_batch", "dg_batch_stage", "dg_batch_run", "dg_batch_fetch", "dg_batch_summary",
     "dg_batch_free", "dg_index_wire_records", "dg_index_fetch_text", "dg_thal_open", "dg_thal_open_tables", "dg_thal_batch", "dg_thal_close",
     "dg_count_batch", "dg_backward_search_batch", "dg_result_hits", "dg_result_query_offsets",
     "dg_result_query_status", "dg_result_query_distance", "dg_result_pool", "dg_result_sequences",
@@ -70,8 +70,12 @@ EXPORTS = [
     "dg_profile_get", "dg_last_error", "dg_version",
     "dg_comm_get_unique_id", "dg_comm_init", "dg_comm_init_host", "dg_comm_rank", "dg_comm_size", "dg_comm_destroy",
     "dg_allgather_hits", "dg_comm_fetch_table", "dg_allgather_result",
+    "dg_result_records", "dg_result_alignment", "dg_rec_alignment", "dg_recs_sort", "dg_result_transfer_bytes",
 ]
 
+REC_DTYPE = np.dtype([("query", "<u4"), ("chr", "<u4"), ("start", "<u4"), ("score", "<i2"), ("strand", "u1"), ("nops", "u1"),
+                      ("ops", "<u8")])
+assert REC_DTYPE.itemsize == 24
 WIRE_DTYPE = np.dtype([("query", "<u4"), ("chr", "<u4"), ("start", "<u4"), ("score", "<i2"), ("strand", "u1"), ("reserved", "u1")])
 assert WIRE_DTYPE.itemsize == 16
 HOST_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
@@ -108,7 +112,6 @@ def library() -> C.CDLL:
     lib.dg_batch_run.argtypes = [vp]
     lib.dg_batch_fetch.argtypes = [vp, C.POINTER(vp)]
     lib.dg_batch_summary.argtypes = [vp, u64p, u64p]
-    lib.dg_batch_device_hits.argtypes = [vp, C.POINTER(vp), u64p]
     lib.dg_index_wire_records.argtypes = [vp, C.POINTER(vp), u64p]
     lib.dg_index_fetch_text.argtypes = [vp, vp, vp, C.c_uint32, vp]
     lib.dg_thal_open.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)]
@@ -122,6 +125,14 @@ def library() -> C.CDLL:
     lib.dg_backward_search_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp]
     lib.dg_result_hits.argtypes = [vp, u64p]
     lib.dg_result_hits.restype = vp
+    lib.dg_result_records.argtypes = [vp, u64p]
+    lib.dg_result_records.restype = vp
+    lib.dg_result_alignment.argtypes = [vp, C.c_uint64, vp, vp]
+    lib.dg_rec_alignment.argtypes = [vp, vp, C.c_uint32, vp, vp]
+    lib.dg_recs_sort.argtypes = [vp, C.c_uint64]
+    lib.dg_recs_sort.restype = None
+    lib.dg_result_transfer_bytes.argtypes = [vp]
+    lib.dg_result_transfer_bytes.restype = C.c_uint64
     lib.dg_result_query_offsets.argtypes = [vp, u32p]
     lib.dg_result_query_offsets.restype = vp
     lib.dg_result_query_status.argtypes = [vp]
@@ -197,22 +208,71 @@ class HuntParams:
 
 
 class HuntResult:
-    """Hits of one batch in the reference's push order (hunter.h:349-433)."""
+    """Hits of one batch in the reference's push order (hunter.h:349-433).
 
-    def __init__(self, hits, qoff, status, dist, pool, seqs, seq_off, handle=None):
-        self.hits, self.qoff, self.status, self.dist = hits, qoff, status, dist
-        self.pool, self.seqs, self.seq_off = pool, seqs, seq_off
-        self._res = handle  # the arrays above are views into this dg_result
+    `hunt` results come back from the device in compact form (``records``: REC_DTYPE, 24 bytes per
+    hit, alignments as edit operations); ``hits`` / ``pool`` / ``qoff`` / ``status`` / ``dist`` are the
+    expanded views the library derives on the host the first time one of them is read."""
+
+    _LAZY = ("hits", "qoff", "status", "dist", "pool", "seqs")
+
+    def __init__(self, hits=None, qoff=None, status=None, dist=None, pool=None, seqs=None, seq_off=None, handle=None):
+        if hits is not None:
+            self.hits, self.qoff, self.status, self.dist, self.pool, self.seqs = hits, qoff, status, dist, pool, seqs
+        self.seq_off = seq_off
+        self._res = handle  # the arrays are views into this dg_result
+
+    def __getattr__(self, name):
+        if name in HuntResult._LAZY and self.__dict__.get("_res"):
+            self._load()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _load(self) -> None:
+        lib, res = library(), self._res
+        n = C.c_uint64(0)
+        hp = lib.dg_result_hits(res, C.byref(n))
+        self.hits = _from_ptr(hp, n.value * HIT_DTYPE.itemsize, HIT_DTYPE)
+        nq = C.c_uint32(0)
+        qp = lib.dg_result_query_offsets(res, C.byref(nq))
+        self.qoff = _from_ptr(qp, (nq.value + 1) * 8, np.uint64)
+        self.status = _from_ptr(lib.dg_result_query_status(res), nq.value * 4, np.uint32)
+        self.dist = _from_ptr(lib.dg_result_query_distance(res), nq.value * 4, np.uint32)
+        nb = C.c_uint64(0)
+        pp = lib.dg_result_pool(res, C.byref(nb))
+        self.pool = _from_ptr(pp, nb.value, np.uint8)
+        sp = lib.dg_result_sequences(res, C.byref(nb))
+        self.seqs = _from_ptr(sp, nb.value, np.uint8)
+
+    @property
+    def records(self) -> np.ndarray:
+        """The compact records as they crossed PCIe (empty for a `search` result)."""
+        n = C.c_uint64(0)
+        p = library().dg_result_records(self._res, C.byref(n)) if self._res else None
+        return _from_ptr(p, n.value * REC_DTYPE.itemsize, REC_DTYPE)
+
+    def alignment(self, i: int) -> tuple[str, str]:
+        """(refalign, queryalign) of hit i, rebuilt from its compact record (dg_result_alignment)."""
+        ra, qa = C.create_string_buffer(300), C.create_string_buffer(300)
+        n = library().dg_result_alignment(self._res, i, ra, qa)
+        if n < 0:
+            _check(n)
+        return ra.raw[:n].decode(), qa.raw[:n].decode()
+
+    @property
+    def transfer_bytes(self) -> int:
+        return int(library().dg_result_transfer_bytes(self._res)) if self._res else 0
 
     def close(self) -> None:
         if self._res:
+            self._load()
             h, self._res = self._res, None
             self.hits = self.hits.copy(); self.qoff = self.qoff.copy(); self.status = self.status.copy()
             self.dist = self.dist.copy(); self.pool = self.pool.copy(); self.seqs = self.seqs.copy()
             library().dg_result_free(h)
 
     def __del__(self):
-        if getattr(self, "_res", None):
+        if self.__dict__.get("_res"):
             try:
                 library().dg_result_free(self._res)
             except Exception:
@@ -293,22 +353,9 @@ class HuntResult:
 
 
 def collect_result(res, seq_off) -> HuntResult:
-    """A HuntResult of views into a library-owned dg_result (freed with the HuntResult)."""
-    lib = library()
-    n = C.c_uint64(0)
-    hp = lib.dg_result_hits(res, C.byref(n))
-    hits = _from_ptr(hp, n.value * HIT_DTYPE.itemsize, HIT_DTYPE)
-    nq = C.c_uint32(0)
-    qp = lib.dg_result_query_offsets(res, C.byref(nq))
-    qoff = _from_ptr(qp, (nq.value + 1) * 8, np.uint64)
-    status = _from_ptr(lib.dg_result_query_status(res), nq.value * 4, np.uint32)
-    dist = _from_ptr(lib.dg_result_query_distance(res), nq.value * 4, np.uint32)
-    nb = C.c_uint64(0)
-    pp = lib.dg_result_pool(res, C.byref(nb))
-    pool = _from_ptr(pp, nb.value, np.uint8)
-    sp = lib.dg_result_sequences(res, C.byref(nb))
-    seqs = _from_ptr(sp, nb.value, np.uint8)
-    return HuntResult(hits, qoff, status, dist, pool, seqs, seq_off, res)
+    """A HuntResult over a library-owned dg_result (freed with the HuntResult); the expanded arrays
+    are fetched on first use."""
+    return HuntResult(seq_off=seq_off, handle=res)
 
 
 def pack_result(res: HuntResult) -> np.ndarray:
@@ -464,12 +511,6 @@ class Batch:
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(library().dg_batch_summary(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
-
-    def device_hits(self) -> tuple[int, int]:
-        """(device address, count) of the dg_hit records in HBM (48 bytes each)."""
-        p, n = C.c_void_p(), C.c_uint64(0)
-        _check(library().dg_batch_device_hits(self._h, C.byref(p), C.byref(n)))
-        return int(p.value or 0), int(n.value)
 
     def fetch(self) -> HuntResult:
         res = C.c_void_p()

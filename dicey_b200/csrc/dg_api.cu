@@ -67,6 +67,7 @@ int dg_index_set_records(dg_index* idx, const uint32_t* seqlen_plus1, uint32_t n
     idx->cum.alloc((size_t)nseq + 1);
     DG_CUDA(cudaMemcpy(idx->cum.p, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice));
     idx->nseq = nseq;
+    idx->h_cum = cum;
     return DG_OK;
   } catch (CudaFail& e) {
     return e.code;

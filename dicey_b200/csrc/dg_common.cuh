@@ -80,6 +80,7 @@ struct dg_index {
   dg::DevBuf<int4> wire;        // 16-byte wire records of the last dg_hunt_batch (dg_index_wire_records)
   uint64_t wire_n = 0;
   dg::DevBuf<uint64_t> cum;
+  std::vector<uint64_t> h_cum;     // host copy (record starts; a compact result rebuilds text_pos from it)
   uint32_t n_exc = 0;
   uint32_t nseq = 0;
   uint32_t C4[4] = {0, 0, 0, 0};

@@ -718,6 +718,82 @@ DG_HD void needle_banded_emit(const uint32_t* tr, const uint8_t* g, int mg, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// Compact alignments (dg_rec of include/dicey_b200.h).  The kept columns of a `hunt` alignment hold
+// every query base exactly once, and every column that is not "genomic base == query base" costs
+// one unit of the score (leading / trailing query-gap columns are free and stripped, hunter.h:391-401),
+// so with score >= -d there are at most d such columns.  A record therefore carries up to kRecOps
+// edit operations instead of two strings; both rows are rebuilt on the host from the query:
+//   op = column (10 bits) | type << 10 (1 mismatch, 2 gap in the reference row, 3 gap in the query
+//        row) | genomic byte << 12; ops ascending by column from bit 0, 20 bits each;
+//   bits 60-63: (start - 1) - (text position - record start) + 8, which gives text_pos back.
+constexpr int kRecOps = 3;
+constexpr int kRecOpBits = 20;
+DG_HD uint64_t rec_op(int col, int type, uint8_t ref) {
+  return (uint64_t)(col & 1023) | ((uint64_t)type << 10) | ((uint64_t)ref << 12);
+}
+
+// Second traceback pass of the banded form: the operations of the kept columns (replaces
+// needle_banded_emit when the record is compact).  Returns the packed ops; *nop_out may exceed
+// kRecOps (then the packing is meaningless and the caller must fall back).
+DG_HD uint64_t needle_banded_ops(const uint32_t* tr, const uint8_t* g, int mg, const uint8_t* s, int n, int dmax, int nops,
+                                 int lead, int trail, int* nop_out) {
+  const int hi = mg - n + dmax;
+  int row = mg, col = n, nop = 0;
+  uint64_t bits = 0;
+  for (int step = 0; step < nops; ++step) {
+    const int t = (int)((tr[row] >> (2 * (col - (row - hi)))) & 3u);
+    int type = 0;
+    uint8_t ref = 0;
+    if (t == 1) { --col; type = 2; }
+    else if (t == 2) { --row; type = 3; ref = g[row]; }
+    else { --row; --col; if (g[row] != s[col]) { type = 1; ref = g[row]; } }
+    const int j = nops - 1 - step;           // column index from the left
+    if (type && j >= lead && j < nops - trail) {
+      bits = (bits << kRecOpBits) | rec_op(j - lead, type, ref);   // found right to left: the leftmost ends in the low bits
+      ++nop;
+    }
+  }
+  *nop_out = nop;
+  return bits & 0x0FFFFFFFFFFFFFFFULL;
+}
+
+// The same from materialised rows (the full-matrix paths).
+DG_HD uint64_t rows_to_ops(const uint8_t* ra, const uint8_t* qa, int kept, int* nop_out) {
+  uint64_t bits = 0;
+  int nop = 0;
+  for (int j = kept - 1; j >= 0; --j) {
+    if (ra[j] == qa[j]) continue;
+    const int type = ra[j] == '-' ? 2 : (qa[j] == '-' ? 3 : 1);
+    bits = (bits << kRecOpBits) | rec_op(j, type, type == 2 ? 0 : ra[j]);
+    ++nop;
+  }
+  *nop_out = nop;
+  return bits & 0x0FFFFFFFFFFFFFFFULL;
+}
+
+// Both alignment rows from the query (the strand's search string, m bases) and the ops; returns the
+// number of columns (m + query-gap columns).  ra / qa need m + kRecOps bytes.
+DG_HD int rec_expand_rows(uint64_t ops, int nop, const uint8_t* s, int m, uint8_t* ra, uint8_t* qa) {
+  int c = 0, col = 0, k = 0;
+  while (c < m || k < nop) {
+    const uint64_t op = ops >> (kRecOpBits * k);
+    if (k < nop && (int)(op & 1023) == col) {
+      const int type = (int)((op >> 10) & 3);
+      const uint8_t ref = (uint8_t)((op >> 12) & 255);
+      if (type == 1) { ra[col] = ref; qa[col] = s[c++]; }
+      else if (type == 2) { ra[col] = '-'; qa[col] = s[c++]; }
+      else { ra[col] = ref; qa[col] = '-'; }
+      ++k;
+    } else {
+      if (c >= m) break;   // malformed ops: never loop forever
+      ra[col] = qa[col] = s[c++];
+    }
+    ++col;
+  }
+  return col;
+}
+
+// ------------------------------------------------------------------------------------------
 // Packed fast path: an ACGT-only string of length <= 31 as 2-bit codes, LAST base in the low
 // bits (so the low 2K bits are the K-mer table index and base t from the right is bits 2t..2t+1).
 // apply_event_packed applies one canonical event (k < 4 substitute code k, 4 delete, 5.. insert

@@ -943,6 +943,7 @@ struct VerifyArgs {
   uint64_t key_base;
   uint64_t nhits;
   dg_hit* hits;
+  dg_rec* recs;              // compact form (hunt): replaces hits + pool
   int4* wire;                // 16-byte wire record per hit (dg_wire): what the multi-GPU all-gather moves
   uint8_t* pool;             // alignment pool: strings back to back, claimed block by block
   unsigned long long* pool_cursor;
@@ -964,6 +965,7 @@ constexpr int kVerifyBlock = 128;
 //   scratch  larger alignments: the full matrix in a global scratch slab
 // The pool has no per-hit stride: each block sums the bytes its hits need (one block scan) and
 // claims that many with one atomicAdd, so only the bytes that travel to the host are written.
+template <bool COMPACT>
 __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev b, VerifyArgs a) {
   __shared__ unsigned long long s_warp[kVerifyBlock / 32];
   __shared__ unsigned long long s_base;
@@ -978,7 +980,7 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
   const uint8_t* base = nullptr;
   int mq = 0, mg = 0, d = 0, mode = 0;  // 1 banded, 2 local, 3 scratch, 4 Hamming
   int nops = 0, lead = 0, trail = 0, kept = 0, score = 0;
-  uint32_t chrpos = 0, bytes = 0;
+  uint32_t chrpos = 0, chrpos0 = 0, bytes = 0;
   uint64_t h = 0;
   if (valid) {
     h = a.first_hit + t;
@@ -995,6 +997,7 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     // hunter.h:358-362
     uint32_t refIndex;
     locate_record(ix.cum, ix.nseq, pos, refIndex, chrpos);
+    chrpos0 = chrpos;
     // context (hunter.h:318-323,363-378; silica.h:480-497)
     uint64_t pre_extract = indel ? d : 0, post_extract = indel ? d : 0;
     if (b.seed_len) { if (strand) post_extract += koff; else pre_extract += koff; }
@@ -1051,6 +1054,37 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     if (!b.seed_len) bytes = 2u * (uint32_t)kept;
   } else if (mode == 1) {
     bytes = 2u * (uint32_t)kept;
+  }
+  if (COMPACT) {
+    // hunt: the record carries the alignment as at most kRecOps edit operations (dg_core.cuh)
+    if (!valid) return;
+    uint64_t ops = 0;
+    int nop = 0;
+    uint32_t start;
+    if (mode == 4) {
+      int lim = mg < mq ? mg : mq;
+      for (int i = lim - 1; i >= 0; --i)
+        if (g[i] != base[i]) { ops = (ops << kRecOpBits) | rec_op(i, 1, g[i]); ++nop; }
+      ops &= 0x0FFFFFFFFFFFFFFFULL;
+      score = -nop;
+      start = chrpos + 1;
+    } else {
+      if (mode == 1) ops = needle_banded_ops(tr, g, mg, base, mq, d, nops, lead, trail, &nop);
+      else ops = rows_to_ops(ra_p, qa_p, kept, &nop);
+      start = chrpos + (uint32_t)lead + 1;   // hunter.h:399,402
+    }
+    const int delta = (int)(start - 1) - (int)chrpos0;   // in [-d, 2 d]
+    dg_rec rec;
+    rec.query = out.query;
+    rec.chr = out.chr;
+    rec.start = start;
+    rec.score = (int16_t)score;
+    rec.strand = out.strand;
+    rec.nops = (uint8_t)(nop > kRecOps ? 255 : nop);
+    rec.ops = ops | ((uint64_t)((delta + 8) & 15) << 60);
+    a.recs[h] = rec;
+    a.wire[h] = make_int4((int)rec.query, (int)rec.chr, (int)rec.start, (int)(((uint32_t)score & 0xFFFFu) | ((uint32_t)rec.strand << 16)));
+    return;
   }
   // block-wide exclusive scan of `bytes`, one atomicAdd per block
   unsigned long long incl = bytes;
@@ -1128,6 +1162,22 @@ __global__ void k_rebase(dg_hit* __restrict__ hits, uint64_t nhits, uint64_t* __
     if (wire) wire[i] = make_int4((int)h.query, (int)h.chr, (int)h.start, (int)(((uint32_t)h.score & 0xFFFFu) | ((uint32_t)h.strand << 16)));
   }
   if (i < nq1) qoff[i] += hit_base;
+}
+
+// the compact form of the same: query ids -> batch-global, wire record = the record's first 16 bytes
+__global__ void k_rebase_recs(dg_rec* __restrict__ recs, uint64_t nhits, uint32_t q0, int4* __restrict__ wire) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nhits) return;
+  const uint2* p = reinterpret_cast<const uint2*>(recs + i);   // (24-byte records: 8-byte aligned)
+  const uint2 a = p[0], c = p[1];   // query, chr | start, score | strand << 16 | nops << 24
+  const uint32_t q = a.x + q0;
+  if (q0) recs[i].query = q;
+  if (wire) wire[i] = make_int4((int)q, (int)a.y, (int)c.x, (int)(c.y & 0x00FFFFFFu));
+}
+__global__ void k_pack_qmeta(const uint32_t* __restrict__ status, const uint32_t* __restrict__ dist, uint32_t nq,
+                             uint16_t* __restrict__ out) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq) out[q] = (uint16_t)((status[q] & 0xFFu) | ((dist[q] & 0xFFu) << 8));
 }
 
 // exact backward search of literal patterns (one thread per pattern)
@@ -1269,11 +1319,128 @@ struct HostBuf {
 };
 }  // namespace
 
+// A result is either FULL (dg_hit records + alignment pool, per-query offsets / status / distance:
+// `search` results and unpacked ones) or COMPACT (`hunt`: dg_rec records + one 16-bit word per query
+// came from the device; everything the older accessors hand out is derived on the host on first use).
 struct dg_result {
   HostBuf hits, qoff, status, dist, pool, seqs;
+  HostBuf recs, qmeta;            // compact form: dg_rec[nhits], uint16 status | distance << 8 per query
+  bool compact = false;
   uint64_t nhits = 0;
   uint32_t nq = 0;
+  uint64_t transfer_bytes = 0;    // device -> host bytes of this result
+  uint64_t uniform_len = 0;       // > 0: every query has this length; else seq_off holds nq + 1 offsets
+  std::vector<uint64_t> seq_off;
+  std::vector<uint64_t> cum;      // record starts of the index (text_pos of an expanded dg_hit)
+  mutable std::mutex mu;
+  mutable bool have_qinfo = false, have_hits = false;
+  uint64_t qstart(uint32_t q) const { return uniform_len ? (uint64_t)q * uniform_len : seq_off[q]; }
+  uint32_t qlen(uint32_t q) const { return uniform_len ? (uint32_t)uniform_len : (uint32_t)(seq_off[q + 1] - seq_off[q]); }
 };
+
+namespace {
+// the strand's search string of query q: the normalised query, or its reverse complement
+inline void strand_query(const dg_result* r, uint32_t q, bool minus, std::vector<uint8_t>& out) {
+  const uint8_t* s = (const uint8_t*)r->seqs.p + r->qstart(q);
+  const uint32_t m = r->qlen(q);
+  out.resize(m);
+  if (!minus) { memcpy(out.data(), s, m); return; }
+  for (uint32_t i = 0; i < m; ++i) {
+    const uint8_t ch = s[m - 1 - i];
+    out[i] = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N';
+  }
+}
+
+// per-query offsets / status / distance of a compact result (records are in query order)
+void ensure_qinfo(const dg_result* cr) {
+  dg_result* r = const_cast<dg_result*>(cr);
+  if (!r->compact) return;
+  std::lock_guard<std::mutex> g(r->mu);
+  if (r->have_qinfo) return;
+  const uint32_t nq = r->nq;
+  r->qoff.alloc(((size_t)nq + 1) * 8, false);
+  r->status.alloc((size_t)nq * 4, false);
+  r->dist.alloc((size_t)nq * 4, false);
+  uint64_t* qoff = (uint64_t*)r->qoff.p;
+  const dg_rec* recs = (const dg_rec*)r->recs.p;
+  uint64_t i = 0;
+  for (uint32_t q = 0; q < nq; ++q) {
+    qoff[q] = i;
+    while (i < r->nhits && recs[i].query == q) ++i;
+  }
+  qoff[nq] = r->nhits;
+  const uint16_t* qm = (const uint16_t*)r->qmeta.p;
+  for (uint32_t q = 0; q < nq; ++q) {
+    ((uint32_t*)r->status.p)[q] = qm[q] & 0xFFu;
+    ((uint32_t*)r->dist.p)[q] = qm[q] >> 8;
+  }
+  r->have_qinfo = true;
+}
+
+// dg_hit + pool of a compact result
+void ensure_hits(const dg_result* cr) {
+  dg_result* r = const_cast<dg_result*>(cr);
+  if (!r->compact) return;
+  std::lock_guard<std::mutex> g(r->mu);
+  if (r->have_hits) return;
+  const uint64_t n = r->nhits;
+  const dg_rec* recs = (const dg_rec*)r->recs.p;
+  std::vector<uint64_t> off((size_t)n + 1, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t cols = r->qlen(recs[i].query);
+    for (int k = 0; k < recs[i].nops && k < kRecOps; ++k) cols += ((recs[i].ops >> (kRecOpBits * k + 10)) & 3) == 3;
+    off[i + 1] = off[i] + 2ull * cols;
+  }
+  r->hits.alloc(n * sizeof(dg_hit), false);
+  r->pool.alloc(off[n], false);
+  dg_hit* hits = (dg_hit*)r->hits.p;
+  uint8_t* pool = (uint8_t*)r->pool.p;
+  const unsigned nthreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(8, n / 65536));
+  auto work = [&](uint64_t lo, uint64_t hi) {
+    std::vector<uint8_t> sq, ra, qa;
+    for (uint64_t i = lo; i < hi; ++i) {
+      const dg_rec& c = recs[i];
+      strand_query(r, c.query, c.strand == '-', sq);
+      const int m = (int)sq.size();
+      ra.resize((size_t)m + kRecOps + 1);
+      qa.resize((size_t)m + kRecOps + 1);
+      const int cols = rec_expand_rows(c.ops, c.nops <= kRecOps ? c.nops : 0, sq.data(), m, ra.data(), qa.data());
+      dg_hit h;
+      memset(&h, 0, sizeof(h));
+      h.query = c.query; h.score = c.score; h.chr = c.chr; h.start = c.start; h.strand = c.strand;
+      h.alignpos = c.start;
+      h.aln_off = off[i];
+      h.aln_len = (uint32_t)cols;
+      const int delta = (int)((c.ops >> 60) & 15) - 8;
+      const uint64_t rec0 = c.chr < r->cum.size() ? r->cum[c.chr] : 0;
+      h.text_pos = rec0 + (uint64_t)((int64_t)c.start - 1 - delta);
+      hits[i] = h;
+      memcpy(pool + off[i], ra.data(), (size_t)cols);
+      memcpy(pool + off[i] + cols, qa.data(), (size_t)cols);
+    }
+  };
+  if (nthreads <= 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < nthreads; ++t) ts.emplace_back(work, n * t / nthreads, n * (t + 1) / nthreads);
+    for (auto& t : ts) t.join();
+  }
+  r->have_hits = true;
+}
+
+// query offsets of the caller -> the result (equal-length batches keep one number)
+void keep_offsets(dg_result* r, const uint64_t* offsets, uint32_t nq) {
+  r->uniform_len = 0;
+  r->seq_off.clear();
+  if (!nq) return;
+  const uint64_t L0 = offsets[1];
+  uint64_t bad = offsets[0];
+  for (uint32_t q = 0; q <= nq; ++q) bad |= offsets[q] ^ ((uint64_t)q * L0);
+  if (!bad && L0) { r->uniform_len = L0; return; }
+  r->seq_off.assign(offsets, offsets + nq + 1);
+}
+}  // namespace
 
 struct dg_batch {
   dg_index* ix = nullptr;
@@ -1291,10 +1458,15 @@ struct dg_batch {
   uint32_t uniform_len = 0;
   uint64_t uniform_units = 0;
   int max_len = 0, min_len = 0;
+  uint64_t uniform_host_len = 0;        // the caller's offsets, for the result: one length, or a copy
+  std::vector<uint64_t> host_off;
   // outputs of run()
   ABuf<Cand> cands;
   uint32_t ncand = 0;
   ABuf<dg_hit> hits;
+  ABuf<dg_rec> recs;           // compact form (hunt): instead of hits + pool
+  ABuf<uint16_t> qmeta;        // compact form: status | distance << 8 per query
+  bool compact = false;
   ABuf<int4> wire;
   ABuf<uint8_t> pool;
   ABuf<unsigned long long> qhits;
@@ -1329,7 +1501,7 @@ static BatchDev batch_dev(const dg_batch* b) {
 // uploader; `ready` is recorded after that copy) -- the host pointer is then only scanned.
 static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* par,
                       dg_batch** out, cudaStream_t on_stream = nullptr, const uint8_t* d_seqs = nullptr,
-                      cudaEvent_t ready = nullptr) {
+                      cudaEvent_t ready = nullptr, bool keep_host_offsets = true) {
   if (!ix || !offsets || !par || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
   if (par->distance > (uint32_t)kMaxDist) {
     set_error("distance > 2 is outside the device path (DESIGN.md, Limits)");
@@ -1379,6 +1551,8 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     }
     if (par->seed_len) have[par->seed_len] = true;
     if (nq == 0) { minL = maxL = 0; }
+    if (equal_len && offsets[1] > 0) b->uniform_host_len = offsets[1];
+    else if (keep_host_offsets) b->host_off.assign(offsets, offsets + nq + 1);
     b->min_len = minL;
     b->max_len = maxL;
     std::vector<uint32_t> tab, tab_off(512, 0), tab_cnt(512, 0), sub(256, 0), one;
@@ -1743,9 +1917,17 @@ static int run_impl(dg_batch* b) {
     if (!b->par.indel && !b->par.seed_len) maxg = maxq;
     uint32_t aln_max = (uint32_t)(maxg + maxq);
     b->pool_stride = b->par.seed_len ? (uint32_t)maxg : (b->par.indel ? 2 * aln_max : (uint32_t)(maxg + maxq));
-    b->hits.alloc(nhits ? nhits : 1, st);
+    // hunt results travel as compact records (dg_rec); search results keep dg_hit + genomic contexts
+    static const bool full_records = getenv("DG_FULL_RECORDS") != nullptr;
+    b->compact = !b->par.seed_len && !full_records;
     b->wire.alloc(nhits ? nhits : 1, st);
-    b->pool.alloc(nhits ? nhits * b->pool_stride : 1, st);   // upper bound; pool_bytes of it are used
+    if (b->compact) {
+      b->recs.alloc(nhits ? nhits : 1, st);
+      b->qmeta.alloc(nq ? nq : 1, st);
+    } else {
+      b->hits.alloc(nhits ? nhits : 1, st);
+      b->pool.alloc(nhits ? nhits * b->pool_stride : 1, st);   // upper bound; pool_bytes of it are used
+    }
     b->pool_bytes = 0;
     ABuf<unsigned long long> cursor;
     cursor.alloc(1, st);
@@ -1777,7 +1959,7 @@ static int run_impl(dg_batch* b) {
       if (hit1 > hit0) {
         VerifyArgs a;
         a.cands = cur; a.ncand = n; a.hit_off = hit_off.p; a.loc_off = loc_off.p; a.keys = keys2.p; a.key_base = row0; a.nhits = nhits;
-        a.hits = b->hits.p; a.wire = b->wire.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
+        a.hits = b->hits.p; a.recs = b->recs.p; a.wire = b->wire.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
         a.srow_ints = (uint32_t)(maxq + 2);
         a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
         a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);
@@ -1795,13 +1977,17 @@ static int run_impl(dg_batch* b) {
         for (uint64_t first = hit0; first < hit1; first += chunk) {
           a.first_hit = first;
           a.chunk = std::min<uint64_t>(chunk, hit1 - first);
-          k_verify<<<grid_for(a.chunk, kVerifyBlock), kVerifyBlock, 0, st>>>(v, bd, a);
+          if (b->compact) k_verify<true><<<grid_for(a.chunk, kVerifyBlock), kVerifyBlock, 0, st>>>(v, bd, a);
+          else k_verify<false><<<grid_for(a.chunk, kVerifyBlock), kVerifyBlock, 0, st>>>(v, bd, a);
           ++launches;
         }
       }
       c0 = c1;
     }
-    {
+    if (b->compact) {
+      // (no alignment pool, hence no size to read back: the run ends without a host round trip)
+      if (nq) { k_pack_qmeta<<<grid_for(nq, B), B, 0, st>>>(b->status.p, b->dist.p, nq, b->qmeta.p); ++launches; }
+    } else {
       unsigned long long used = 0;
       DG_CUDA(cudaMemcpyAsync(&used, cursor.p, 8, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaStreamSynchronize(st));
@@ -1855,23 +2041,36 @@ static int fetch_impl(dg_batch* b, dg_result** out) {
     uint32_t nq = b->nq;
     r->nq = nq;
     r->nhits = b->nhits;
-    r->hits.alloc(b->nhits * sizeof(dg_hit), true);
-    r->qoff.alloc(((size_t)nq + 1) * 8, true);
-    r->status.alloc((size_t)nq * 4, true);
-    r->dist.alloc((size_t)nq * 4, true);
-    r->pool.alloc(b->pool_bytes, true);
+    r->compact = b->compact;
+    r->cum = ix->h_cum;
     r->seqs.alloc(b->nbytes, true);
-    if (b->nhits) {
-      DG_CUDA(cudaMemcpyAsync(r->hits.p, b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, st));
-      if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync(r->pool.p, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, st));
-    }
-    DG_CUDA(cudaMemcpyAsync(r->qoff.p, b->qoff.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (nq) {
-      DG_CUDA(cudaMemcpyAsync(r->status.p, b->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaMemcpyAsync(r->dist.p, b->dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (b->compact) {
+      r->recs.alloc(b->nhits * sizeof(dg_rec), true);
+      r->qmeta.alloc((size_t)nq * 2, true);
+      if (b->nhits) DG_CUDA(cudaMemcpyAsync(r->recs.p, b->recs.p, b->nhits * sizeof(dg_rec), cudaMemcpyDeviceToHost, st));
+      if (nq) DG_CUDA(cudaMemcpyAsync(r->qmeta.p, b->qmeta.p, (size_t)nq * 2, cudaMemcpyDeviceToHost, st));
+      r->transfer_bytes = b->nhits * sizeof(dg_rec) + (size_t)nq * 2 + b->nbytes;
+    } else {
+      r->hits.alloc(b->nhits * sizeof(dg_hit), true);
+      r->qoff.alloc(((size_t)nq + 1) * 8, true);
+      r->status.alloc((size_t)nq * 4, true);
+      r->dist.alloc((size_t)nq * 4, true);
+      r->pool.alloc(b->pool_bytes, true);
+      if (b->nhits) {
+        DG_CUDA(cudaMemcpyAsync(r->hits.p, b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, st));
+        if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync(r->pool.p, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, st));
+      }
+      DG_CUDA(cudaMemcpyAsync(r->qoff.p, b->qoff.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+      if (nq) {
+        DG_CUDA(cudaMemcpyAsync(r->status.p, b->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaMemcpyAsync(r->dist.p, b->dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+      }
+      r->transfer_bytes = b->nhits * sizeof(dg_hit) + b->pool_bytes + ((size_t)nq + 1) * 8 + (size_t)nq * 8 + b->nbytes;
     }
     if (b->nbytes) DG_CUDA(cudaMemcpyAsync(r->seqs.p, b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
+    if (b->host_off.size() == (size_t)nq + 1) keep_offsets(r, b->host_off.data(), nq);
+    else if (b->uniform_host_len) r->uniform_len = b->uniform_host_len;
     prof_collect(ix);
     *out = r;
     return DG_OK;
@@ -1915,13 +2114,6 @@ int dg_index_wire_records(dg_index* idx, const void** device_ptr, uint64_t* n) {
   for (auto s2 : idx->xstream) if (s2) cudaStreamSynchronize(s2);
   *device_ptr = idx->wire_n ? (const void*)idx->wire.p : nullptr;
   *n = idx->wire_n;
-  return DG_OK;
-}
-int dg_batch_device_hits(dg_batch* b, const void** device_ptr, uint64_t* n_hits) {
-  if (!b || !b->ran || !device_ptr || !n_hits) { set_error("batch has not run"); return DG_ERR_ARG; }
-  cudaStreamSynchronize(b->st);
-  *device_ptr = b->nhits ? (const void*)b->hits.p : nullptr;
-  *n_hits = b->nhits;
   return DG_OK;
 }
 void dg_batch_free(dg_batch* b) {
@@ -1999,7 +2191,7 @@ struct ChunkPipe {
         }
         tm[2] = now() - t_begin;
         dg_batch* b = nullptr;
-        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st, d_up + offsets[q0], up_ev[c]);
+        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st, d_up + offsets[q0], up_ev[c], false);
         if (rc1) { fail(rc1, last_error_ref()); break; }
         cudaEvent_t copied = copied_ev[c];
         live.push_back(Live{b, copied});
@@ -2012,13 +2204,17 @@ struct ChunkPipe {
         cv.wait(lk, [&] { return next_commit == c || rc != DG_OK; });
         if (rc != DG_OK) break;
         tm[5] = now() - t_begin;
-        const uint64_t need_hits = (hit_base + b->nhits) * sizeof(dg_hit), need_pool = pool_base + b->pool_bytes;
-        if (need_hits > r->hits.cap || need_pool > r->pool.cap) {
+        const bool compact = b->compact;
+        r->compact = compact;
+        const size_t rec_size = compact ? sizeof(dg_rec) : sizeof(dg_hit);
+        HostBuf& rbuf = compact ? r->recs : r->hits;
+        const uint64_t need_hits = (hit_base + b->nhits) * rec_size, need_pool = pool_base + b->pool_bytes;
+        if (need_hits > rbuf.cap || need_pool > r->pool.cap) {
           // first call with this volume (later calls get right-sized blocks from the cache): size for
           // the whole batch from what the chunks so far produced
           DG_CUDA(cudaStreamSynchronize(cs));
           const double scale = 1.15 * (double)nq / (double)q1;  // q1 = queries committed so far
-          r->hits.reserve(std::max<size_t>(need_hits, (size_t)(scale * need_hits)), hit_base * sizeof(dg_hit), true);
+          rbuf.reserve(std::max<size_t>(need_hits, (size_t)(scale * need_hits)), hit_base * rec_size, true);
           r->pool.reserve(std::max<size_t>(need_pool, (size_t)(scale * need_pool)), pool_base, true);
         }
         if (hit_base + b->nhits > idx->wire.count) {
@@ -2030,21 +2226,33 @@ struct ChunkPipe {
           std::swap(idx->wire.p, bigger.p);
           std::swap(idx->wire.count, bigger.count);
         }
-        k_rebase<<<grid_for(std::max<uint64_t>(b->nhits, (uint64_t)cn + 1), 256), 256, 0, st>>>(
-            b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base, idx->wire.p + hit_base);
+        if (compact) {
+          if (b->nhits)
+            k_rebase_recs<<<grid_for(b->nhits, 256), 256, 0, st>>>(b->recs.p, b->nhits, q0, idx->wire.p + hit_base);
+        } else {
+          k_rebase<<<grid_for(std::max<uint64_t>(b->nhits, (uint64_t)cn + 1), 256), 256, 0, st>>>(
+              b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base, idx->wire.p + hit_base);
+        }
         cudaEvent_t ev = rebased_ev[c];
         DG_CUDA(cudaEventRecord(ev, st));
         DG_CUDA(cudaStreamWaitEvent(cs, ev, 0));
-        if (b->nhits) {
-          DG_CUDA(cudaMemcpyAsync((uint8_t*)r->hits.p + hit_base * sizeof(dg_hit), b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, cs));
-          if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->pool.p + pool_base, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, cs));
+        if (compact) {
+          if (b->nhits) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->recs.p + hit_base * sizeof(dg_rec), b->recs.p, b->nhits * sizeof(dg_rec), cudaMemcpyDeviceToHost, cs));
+          if (cn) DG_CUDA(cudaMemcpyAsync((uint16_t*)r->qmeta.p + q0, b->qmeta.p, (size_t)cn * 2, cudaMemcpyDeviceToHost, cs));
+          r->transfer_bytes += b->nhits * sizeof(dg_rec) + (size_t)cn * 2 + b->nbytes;
+        } else {
+          if (b->nhits) {
+            DG_CUDA(cudaMemcpyAsync((uint8_t*)r->hits.p + hit_base * sizeof(dg_hit), b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, cs));
+            if (b->pool_bytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->pool.p + pool_base, b->pool.p, b->pool_bytes, cudaMemcpyDeviceToHost, cs));
+          }
+          DG_CUDA(cudaMemcpyAsync((uint64_t*)r->qoff.p + q0, b->qoff.p, ((size_t)cn + (c + 1 == nchunks ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, cs));
+          if (cn) {
+            DG_CUDA(cudaMemcpyAsync((uint32_t*)r->status.p + q0, b->status.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
+            DG_CUDA(cudaMemcpyAsync((uint32_t*)r->dist.p + q0, b->dist.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
+          }
+          r->transfer_bytes += b->nhits * sizeof(dg_hit) + b->pool_bytes + (size_t)cn * 16 + b->nbytes;
         }
-        DG_CUDA(cudaMemcpyAsync((uint64_t*)r->qoff.p + q0, b->qoff.p, ((size_t)cn + (c + 1 == nchunks ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, cs));
-        if (cn) {
-          DG_CUDA(cudaMemcpyAsync((uint32_t*)r->status.p + q0, b->status.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
-          DG_CUDA(cudaMemcpyAsync((uint32_t*)r->dist.p + q0, b->dist.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
-          if (b->nbytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
-        }
+        if (cn && b->nbytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
         DG_CUDA(cudaEventRecord(copied, cs));
         hit_base += b->nhits;
         pool_base += b->pool_bytes;
@@ -2105,9 +2313,15 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     }
     r = new dg_result();
     r->nq = nq;
-    r->qoff.alloc(((size_t)nq + 1) * 8, true);
-    r->status.alloc((size_t)nq * 4, true);
-    r->dist.alloc((size_t)nq * 4, true);
+    r->cum = idx->h_cum;
+    static const bool full_records = getenv("DG_FULL_RECORDS") != nullptr;
+    if (!params->seed_len && !full_records) {
+      r->qmeta.alloc((size_t)nq * 2, true);
+    } else {
+      r->qoff.alloc(((size_t)nq + 1) * 8, true);
+      r->status.alloc((size_t)nq * 4, true);
+      r->dist.alloc((size_t)nq * 4, true);
+    }
     r->seqs.alloc(offsets[nq], true);
     p.r = r;
     // The calling thread uploads the sequences chunk by chunk, in order, on a stream of its own (a
@@ -2158,9 +2372,11 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     if (p.rc == DG_OK) {
       DG_CUDA(cudaStreamSynchronize(idx->copy_stream));
       r->nhits = p.hit_base;
-      r->hits.bytes = p.hit_base * sizeof(dg_hit);
+      if (r->compact) r->recs.bytes = p.hit_base * sizeof(dg_rec);
+      else r->hits.bytes = p.hit_base * sizeof(dg_hit);
       r->pool.bytes = p.pool_base;
       idx->wire_n = p.hit_base;
+      keep_offsets(r, offsets, nq);
     }
   } catch (CudaFail& e) {
     p.rc = e.code;
@@ -2192,7 +2408,9 @@ int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint
   if (!rc) {
     try {
       if (b->nhits > idx->wire.count) idx->wire.alloc(b->nhits + (b->nhits >> 3) + 1024);
-      if (b->nhits)
+      if (b->nhits && b->compact)
+        k_rebase_recs<<<grid_for(b->nhits, 256), 256, 0, b->st>>>(b->recs.p, b->nhits, 0, idx->wire.p);
+      else if (b->nhits)
         k_rebase<<<grid_for(b->nhits, 256), 256, 0, b->st>>>(b->hits.p, b->nhits, b->qoff.p, 0, 0, 0, 0, idx->wire.p);
       idx->wire_n = b->nhits;
     } catch (CudaFail& e) { rc = e.code; }
@@ -2246,17 +2464,58 @@ int dg_backward_search_batch(dg_index* idx, const char* seqs, const uint64_t* of
   }
 }
 
+const dg_rec* dg_result_records(const dg_result* r, uint64_t* n) {
+  const bool have = r && r->compact;
+  if (n) *n = have ? r->nhits : 0;
+  return have ? (const dg_rec*)r->recs.p : nullptr;
+}
+int dg_rec_alignment(const dg_rec* rec, const char* query, uint32_t qlen, char* refalign, char* queryalign) {
+  if (!rec || !query || !refalign || !queryalign) { set_error("null argument"); return DG_ERR_ARG; }
+  if (rec->nops > kRecOps) { set_error("record holds more edit operations than the compact form carries"); return DG_ERR_FORMAT; }
+  return rec_expand_rows(rec->ops, rec->nops, (const uint8_t*)query, (int)qlen, (uint8_t*)refalign, (uint8_t*)queryalign);
+}
+int dg_result_alignment(const dg_result* r, uint64_t i, char* refalign, char* queryalign) {
+  if (!r || !refalign || !queryalign || i >= r->nhits) { set_error("bad argument"); return DG_ERR_ARG; }
+  if (!r->compact) {
+    const dg_hit& h = ((const dg_hit*)r->hits.p)[i];
+    memcpy(refalign, (const char*)r->pool.p + h.aln_off, h.aln_len);
+    memcpy(queryalign, (const char*)r->pool.p + h.aln_off + h.aln_len, h.aln_len);
+    return (int)h.aln_len;
+  }
+  const dg_rec& c = ((const dg_rec*)r->recs.p)[i];
+  if (c.query >= r->nq) { set_error("record with a query index outside the batch"); return DG_ERR_FORMAT; }
+  std::vector<uint8_t> sq;
+  strand_query(r, c.query, c.strand == '-', sq);
+  return dg_rec_alignment(&c, (const char*)sq.data(), (uint32_t)sq.size(), refalign, queryalign);
+}
+void dg_recs_sort(dg_rec* recs, uint64_t n) {
+  if (!recs || n < 2) return;
+  std::sort(recs, recs + n, [](const dg_rec& a, const dg_rec& b) {  // DnaHit::operator< hunter.h:63-65
+    return (a.score > b.score) || ((a.score == b.score) && (a.chr < b.chr)) ||
+           ((a.score == b.score) && (a.chr == b.chr) && (a.start < b.start));
+  });
+}
+uint64_t dg_result_transfer_bytes(const dg_result* r) { return r ? r->transfer_bytes : 0; }
 const dg_hit* dg_result_hits(const dg_result* r, uint64_t* n) {
   if (n) *n = r ? r->nhits : 0;
+  if (r) ensure_hits(r);
   return r ? (const dg_hit*)r->hits.p : nullptr;
 }
 const uint64_t* dg_result_query_offsets(const dg_result* r, uint32_t* nq) {
   if (nq) *nq = r ? r->nq : 0;
+  if (r) ensure_qinfo(r);
   return r ? (const uint64_t*)r->qoff.p : nullptr;
 }
-const uint32_t* dg_result_query_status(const dg_result* r) { return r ? (const uint32_t*)r->status.p : nullptr; }
-const uint32_t* dg_result_query_distance(const dg_result* r) { return r ? (const uint32_t*)r->dist.p : nullptr; }
+const uint32_t* dg_result_query_status(const dg_result* r) {
+  if (r) ensure_qinfo(r);
+  return r ? (const uint32_t*)r->status.p : nullptr;
+}
+const uint32_t* dg_result_query_distance(const dg_result* r) {
+  if (r) ensure_qinfo(r);
+  return r ? (const uint32_t*)r->dist.p : nullptr;
+}
 const char* dg_result_pool(const dg_result* r, uint64_t* bytes) {
+  if (r) ensure_hits(r);
   if (bytes) *bytes = r ? r->pool.bytes : 0;
   return r ? (const char*)r->pool.p : nullptr;
 }
@@ -2270,6 +2529,8 @@ void dg_result_free(dg_result* r) { delete r; }
 // qoff[nq+1], status[nq], dist[nq], hits[nhits], pool, seqs
 int dg_result_pack(const dg_result* r, void* buf, uint64_t* bytes) {
   if (!r || !bytes) { set_error("null argument"); return DG_ERR_ARG; }
+  ensure_qinfo(r);   // the packed form is the full one: a compact result is expanded first
+  ensure_hits(r);
   uint64_t nq = r->nq, nh = r->nhits, np = r->pool.bytes, ns = r->seqs.bytes;
   uint64_t need = 32 + (nq + 1) * 8 + nq * 8 + nh * sizeof(dg_hit) + np + ns;
   if (!buf) { *bytes = need; return DG_OK; }

@@ -74,6 +74,24 @@ typedef struct {
   uint8_t pad[7];
 } dg_hit;
 
+/* The same DnaHit in the compact form `hunt` results travel in (24 bytes instead of 48 + two
+ * alignment strings): coordinates, score, strand, and the at most three columns in which the
+ * alignment differs from "the query copied into both rows" (every such column costs one unit of the
+ * score, so a hit of distance <= 3 never has more).  dg_rec_alignment rebuilds refalign / queryalign
+ * from the record and the query; dg_result_hits still hands out dg_hit + pool (expanded on the host
+ * on first use).  ops: three 20-bit fields from bit 0, ascending by column: column (10 bits) |
+ * type << 10 (1 mismatch, 2 '-' in refalign, 3 '-' in queryalign) | genomic byte << 12; bits 60-63:
+ * (start - 1) - (text_pos - start of the record) + 8.                                          */
+typedef struct {
+  uint32_t query;
+  uint32_t chr;       /* refIndex                                                      */
+  uint32_t start;     /* DnaHit.start (1-based, after leading-gap stripping)           */
+  int16_t score;      /* -(edit or Hamming distance)                                   */
+  uint8_t strand;     /* '+' or '-'                                                    */
+  uint8_t nops;       /* number of ops (0..3)                                          */
+  uint64_t ops;
+} dg_rec;
+
 typedef struct {
   uint64_t n;             /* csa.size(): text length including the sentinel            */
   uint32_t sigma;         /* alphabet size including the sentinel                      */
@@ -178,10 +196,6 @@ int dg_batch_stage(dg_index* idx, const char* seqs, const uint64_t* offsets, uin
 int dg_batch_run(dg_batch* b);
 int dg_batch_fetch(dg_batch* b, dg_result** out);
 int dg_batch_summary(dg_batch* b, uint64_t* n_hits, uint64_t* n_candidates); /* synchronises */
-/* Device address of the hit records of a batch that has run (n_hits dg_hit structs in HBM, valid
- * until dg_batch_free / the next dg_batch_run): lets the multi-GPU layer all-gather the records
- * over NVLink straight from device memory, without a round trip through the host. */
-int dg_batch_device_hits(dg_batch* b, const void** device_ptr, uint64_t* n_hits);
 void dg_batch_free(dg_batch* b);
 
 /* sdsl::count over a neighbourhood: padlock.h:381-427 (exact count of each string when
@@ -202,6 +216,19 @@ int dg_backward_search_batch(dg_index* idx, const char* seqs, const uint64_t* of
 int dg_index_wire_records(dg_index* idx, const void** device_ptr, uint64_t* n);
 
 /* ---- results ------------------------------------------------------------------------ */
+/* Compact records of a `hunt` result in push order (NULL with *n = 0 for a `search` result, whose
+ * hits carry genomic contexts: use dg_result_hits).                                           */
+const dg_rec* dg_result_records(const dg_result* r, uint64_t* n);
+/* refalign / queryalign of record i (each needs |query| + 3 bytes; not NUL-terminated); returns
+ * the number of alignment columns, or a negative dg_status.                                   */
+int dg_result_alignment(const dg_result* r, uint64_t i, char* refalign, char* queryalign);
+/* The same for a record on its own: query = the normalised sequence the hit's strand searched
+ * (the query for '+', its reverse complement for '-'), qlen its length.                       */
+int dg_rec_alignment(const dg_rec* rec, const char* query, uint32_t qlen, char* refalign, char* queryalign);
+/* hunter.h:440 std::sort for compact records (same order as dg_hits_sort).                    */
+void dg_recs_sort(dg_rec* recs, uint64_t n);
+/* Bytes that crossed PCIe for this result (device -> host), for bench.py's accounting.        */
+uint64_t dg_result_transfer_bytes(const dg_result* r);
 const dg_hit* dg_result_hits(const dg_result* r, uint64_t* n);
 const uint64_t* dg_result_query_offsets(const dg_result* r, uint32_t* nq); /* nq+1 entries */
 const uint32_t* dg_result_query_status(const dg_result* r);               /* nq entries   */

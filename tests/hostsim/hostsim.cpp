@@ -143,7 +143,7 @@ int main(int argc, char** argv) {
   if (cmd == "needle" && argc >= 3) {
     std::ifstream f(argv[2]);
     std::string line;
-    int banded_checked = 0;
+    int banded_checked = 0, ops_checked = 0;
     while (std::getline(f, line)) {
       size_t t = line.find('\t');
       if (t == std::string::npos) continue;
@@ -180,16 +180,44 @@ int main(int argc, char** argv) {
         needle_banded_emit(tr.data(), (const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, dmax, nops, lead3, trail3,
                            ra3.data(), qa3.data());
         ++banded_checked;
+        {  // the compact record form: ops from the trace, rows rebuilt from the query alone
+          int nop = 0;
+          uint64_t bits = needle_banded_ops(tr.data(), (const uint8_t*)g.data(), mg, (const uint8_t*)s.data(), n, dmax, nops, lead3,
+                                            trail3, &nop);
+          if (nop != -score) { fprintf(stderr, "ops count %d != -score %d on %s %s\n", nop, -score, g.c_str(), s.c_str()); return 3; }
+          if (nop <= kRecOps) {
+            std::vector<uint8_t> ra4(n + kRecOps + 1), qa4(n + kRecOps + 1);
+            int cols = rec_expand_rows(bits, nop, (const uint8_t*)s.data(), n, ra4.data(), qa4.data());
+            if (cols != kept || memcmp(ra.data(), ra4.data(), kept) || memcmp(qa.data(), qa4.data(), kept)) {
+              fprintf(stderr, "compact ops do not rebuild the alignment of %s %s\n", g.c_str(), s.c_str());
+              return 3;
+            }
+            ++ops_checked;
+          }
+        }
         if (score3 != score || kept3 != kept || lead3 != lead || memcmp(ra.data(), ra3.data(), kept) || memcmp(qa.data(), qa3.data(), kept)) {
           fprintf(stderr, "banded / full needle mismatch on %s %s (dmax %d)\n", g.c_str(), s.c_str(), dmax);
           return 3;
         }
       }
+      {  // the same from materialised rows (full-matrix paths of k_verify)
+        int nop = 0;
+        uint64_t bits = rows_to_ops(ra.data(), qa.data(), kept, &nop);
+        if (nop <= kRecOps) {
+          std::vector<uint8_t> ra4(n + kRecOps + 1), qa4(n + kRecOps + 1);
+          int cols = rec_expand_rows(bits, nop, (const uint8_t*)s.data(), n, ra4.data(), qa4.data());
+          if (cols != kept || memcmp(ra.data(), ra4.data(), kept) || memcmp(qa.data(), qa4.data(), kept)) {
+            fprintf(stderr, "rows_to_ops does not round-trip on %s %s\n", g.c_str(), s.c_str());
+            return 3;
+          }
+          ++ops_checked;
+        }
+      }
       std::cout << score << '\t' << lead << '\t' << std::string((char*)ra.data(), kept) << '\t'
                 << std::string((char*)qa.data(), kept) << '\n';
     }
-    fprintf(stderr, "banded needle checked on %d (pair, dmax) cases\n", banded_checked);
-    return banded_checked >= 100 ? 0 : 4;
+    fprintf(stderr, "banded needle checked on %d (pair, dmax) cases, compact ops on %d\n", banded_checked, ops_checked);
+    return banded_checked >= 100 && ops_checked >= 200 ? 0 : 4;
   }
   if (cmd == "thal8" && argc >= 4) {
     // the lane-cooperative arrangement on eight concurrent lanes (threads)
