@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,6 +51,13 @@ struct DevBuf {
   size_t bytes() const { return count * sizeof(T); }
 };
 
+// Unit tables of one (distance, mode, set of query lengths): built once per index and shared by
+// every batch of that shape (script_ub[256] | tab_off[512] | tab_cnt[512] | tab[...] in one block).
+struct TabEntry {
+  DevBuf<uint32_t> blob;
+  std::vector<uint32_t> tab_cnt;   // host copy of tab_cnt
+};
+
 struct ProfileState {
   bool enabled = false;
   cudaEvent_t ev[8] = {};
@@ -87,6 +97,8 @@ struct dg_index {
   std::vector<uint32_t> h_Cb;      // host copies for the .fm9 writer / info
   std::vector<uint8_t> h_present;
   dg::ProfileState prof;
+  std::mutex tab_mu;
+  std::map<std::string, std::shared_ptr<dg::TabEntry>> tab_cache;
 
   dg::IndexView view() const {
     dg::IndexView v;

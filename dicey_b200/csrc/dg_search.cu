@@ -1452,7 +1452,8 @@ struct dg_batch {
   // inputs
   ABuf<uint8_t> raw, fwd, rc;
   ABuf<uint64_t> off, units, unit_off;
-  ABuf<uint32_t> status, dist, tab, tab_off, tab_cnt, script_ub, irregular;
+  ABuf<uint32_t> status, dist, irregular;
+  std::shared_ptr<TabEntry> tabs;   // unit tables (cached in the index)
   ABuf<uint64_t> qcode;
   ABuf<uint8_t> qflag;
   uint32_t uniform_len = 0;
@@ -1460,6 +1461,10 @@ struct dg_batch {
   int max_len = 0, min_len = 0;
   uint64_t uniform_host_len = 0;        // the caller's offsets, for the result: one length, or a copy
   std::vector<uint64_t> host_off;
+  // chunk pipeline: the normalised sequences leave for the host as soon as k_prepare has written them
+  cudaEvent_t ev_prepared = nullptr;
+  cudaStream_t seq_stream = nullptr;
+  void* seq_dst = nullptr;
   // outputs of run()
   ABuf<Cand> cands;
   uint32_t ncand = 0;
@@ -1501,7 +1506,11 @@ static BatchDev batch_dev(const dg_batch* b) {
 // uploader; `ready` is recorded after that copy) -- the host pointer is then only scanned.
 static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, uint32_t nq, const dg_params* par,
                       dg_batch** out, cudaStream_t on_stream = nullptr, const uint8_t* d_seqs = nullptr,
-                      cudaEvent_t ready = nullptr, bool keep_host_offsets = true) {
+                      cudaEvent_t ready = nullptr, bool keep_host_offsets = true, uint64_t uniform_L = 0) {
+  // uniform_L > 0: the caller has checked that every query has this length; offsets is not read
+  uint64_t two_off[2] = {0, uniform_L};
+  const uint64_t total_bytes = uniform_L ? (uint64_t)nq * uniform_L : (offsets ? offsets[nq] : 0);
+  if (uniform_L) offsets = two_off;
   if (!ix || !offsets || !par || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
   if (par->distance > (uint32_t)kMaxDist) {
     set_error("distance > 2 is outside the device path (DESIGN.md, Limits)");
@@ -1524,7 +1533,7 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     b->par = *par;
     if (b->par.max_locations == 0) b->par.max_locations = 1;
     b->nq = nq;
-    b->nbytes = offsets[nq];
+    b->nbytes = total_bytes;
     // distinct search-string lengths -> unit tables
     bool have[256];
     memset(have, 0, sizeof(have));
@@ -1534,7 +1543,7 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     if (nq) {
       const uint64_t L0 = offsets[1];
       uint64_t bad = 0;
-      for (uint32_t q = 0; q <= nq; ++q) bad |= offsets[q] ^ ((uint64_t)q * L0);
+      if (!uniform_L) for (uint32_t q = 0; q <= nq; ++q) bad |= offsets[q] ^ ((uint64_t)q * L0);
       equal_len = bad == 0;
       if (equal_len) {
         minL = maxL = L0 > 100000 ? 100000 : (int)L0;
@@ -1555,35 +1564,52 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     else if (keep_host_offsets) b->host_off.assign(offsets, offsets + nq + 1);
     b->min_len = minL;
     b->max_len = maxL;
-    std::vector<uint32_t> tab, tab_off(512, 0), tab_cnt(512, 0), sub(256, 0), one;
     const bool indel = par->indel != 0;
-    for (int m = 1; m < 256; ++m) {
-      if (!have[m]) continue;
-      int d = std::min<int>((int)par->distance, m - 1);
-      for (int variant = 0; variant < 2; ++variant) {
-        build_unit_table(m, d, indel, variant == 0, one);
-        tab_off[variant * 256 + m] = (uint32_t)tab.size();
-        tab_cnt[variant * 256 + m] = (uint32_t)one.size();
-        tab.insert(tab.end(), one.begin(), one.end());
-      }
-      {
-        int sl = slots_per_pos(indel), E = sl * m;
-        uint64_t ub = 1 + (d >= 1 ? (uint64_t)E : 0);
-        if (d >= 2)
-          for (int e1 = 0; e1 < E; ++e1) ub += (uint64_t)(E - second_event_start(e1 / sl, e1 % sl, indel));
-        sub[m] = ub > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)ub;
+    {
+      std::string key((const char*)have, sizeof(have));
+      key.push_back((char)par->distance);
+      key.push_back((char)indel);
+      std::lock_guard<std::mutex> g(ix->tab_mu);
+      auto it = ix->tab_cache.find(key);
+      if (it != ix->tab_cache.end()) {
+        b->tabs = it->second;
+      } else {
+        std::vector<uint32_t> tab, tab_off(512, 0), tab_cnt(512, 0), sub(256, 0), one;
+        for (int m = 1; m < 256; ++m) {
+          if (!have[m]) continue;
+          int d = std::min<int>((int)par->distance, m - 1);
+          for (int variant = 0; variant < 2; ++variant) {
+            build_unit_table(m, d, indel, variant == 0, one);
+            tab_off[variant * 256 + m] = (uint32_t)tab.size();
+            tab_cnt[variant * 256 + m] = (uint32_t)one.size();
+            tab.insert(tab.end(), one.begin(), one.end());
+          }
+          {
+            int sl = slots_per_pos(indel), E = sl * m;
+            uint64_t ub = 1 + (d >= 1 ? (uint64_t)E : 0);
+            if (d >= 2)
+              for (int e1 = 0; e1 < E; ++e1) ub += (uint64_t)(E - second_event_start(e1 / sl, e1 % sl, indel));
+            sub[m] = ub > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)ub;
+          }
+        }
+        std::vector<uint32_t> blob;
+        blob.reserve(1280 + tab.size());
+        blob.insert(blob.end(), sub.begin(), sub.end());
+        blob.insert(blob.end(), tab_off.begin(), tab_off.end());
+        blob.insert(blob.end(), tab_cnt.begin(), tab_cnt.end());
+        blob.insert(blob.end(), tab.begin(), tab.end());
+        auto e = std::make_shared<TabEntry>();
+        e->blob.alloc(blob.size() + 1);
+        DG_CUDA(cudaMemcpy(e->blob.p, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+        e->tab_cnt = tab_cnt;
+        if (ix->tab_cache.size() >= 64) ix->tab_cache.clear();   // (batches in flight keep their entry alive)
+        ix->tab_cache[key] = e;
+        b->tabs = e;
       }
     }
+    const std::vector<uint32_t>& tab_cnt = b->tabs->tab_cnt;
     const double ts1 = now();
-    b->tab.alloc(tab.size(), st);
-    b->tab_off.alloc(512, st);
-    b->tab_cnt.alloc(512, st);
-    b->script_ub.alloc(256, st);
     b->irregular.alloc(1, st);
-    DG_CUDA(cudaMemcpyAsync(b->script_ub.p, sub.data(), 256 * 4, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaMemcpyAsync(b->tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaMemcpyAsync(b->tab_off.p, tab_off.data(), 512 * 4, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaMemcpyAsync(b->tab_cnt.p, tab_cnt.data(), 512 * 4, cudaMemcpyHostToDevice, st));
     // uniform batches (one length, all ACGT, nothing skipped) map unit -> query by a division
     // instead of a binary search; k_prepare clears the shortcut if any query is irregular
     bool uniform = nq > 0 && minL == maxL && maxL <= kMaxQuery &&
@@ -1652,7 +1678,8 @@ static int run_impl(dg_batch* b) {
     b->nhits = 0;
     b->ncand = 0;
     BatchDev bd = batch_dev(b);
-    UnitTabs ut{b->tab.p, b->tab_off.p, b->tab_cnt.p, b->script_ub.p};
+    const uint32_t* tb = b->tabs->blob.p;
+    UnitTabs ut{tb + 1280, tb + 256, tb + 768, tb};
     IndexView v = ix->view();
     ABuf<uint8_t> tmp;
     size_t tmp_cap = 0;
@@ -1665,6 +1692,11 @@ static int run_impl(dg_batch* b) {
     DG_CUDA(cudaMemsetAsync(b->units.p, 0, ((size_t)nq + 1) * 8, st));
     DG_CUDA(cudaMemsetAsync(b->irregular.p, 0, 4, st));
     if (nq) { k_prepare<<<grid_for(nq, B), B, 0, st>>>(b->raw.p, bd, b->fwd.p, b->rc.p, ut, b->units.p); ++launches; }
+    if (b->seq_dst && b->nbytes) {
+      DG_CUDA(cudaEventRecord(b->ev_prepared, st));
+      DG_CUDA(cudaStreamWaitEvent(b->seq_stream, b->ev_prepared, 0));
+      DG_CUDA(cudaMemcpyAsync(b->seq_dst, b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, b->seq_stream));
+    }
     {
       size_t tb = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tb, b->units.p, b->unit_off.p, (int)(nq + 1), st);
@@ -2142,8 +2174,9 @@ struct ChunkPipe {
   int nworkers = 2;
   uint32_t next_commit = 0;      // chunks are committed (final offsets assigned) in order
   const uint8_t* d_up = nullptr; // the caller's sequences in device memory, chunk c valid once uploaded > c
-  std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev;   // per chunk, from the index's event pool
+  std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev, prepared_ev;   // per chunk, from the index's event pool
   uint32_t uploaded = 0;
+  std::vector<uint64_t> chunk_len;   // per chunk: the common query length, or 0 (set before `uploaded` passes the chunk)
   uint64_t hit_base = 0, pool_base = 0;
   int rc = DG_OK;
   std::string err;
@@ -2181,18 +2214,25 @@ struct ChunkPipe {
         const uint32_t q0 = bounds[c], q1 = bounds[c + 1];
         const uint32_t cn = q1 - q0;
         if (offsets[q1] < offsets[q0]) { fail(DG_ERR_ARG, "offsets must be non-decreasing"); break; }
-        so.resize((size_t)cn + 1);
-        for (uint32_t k = 0; k <= cn; ++k) so[k] = offsets[q0 + k] - offsets[q0];
         tm[1] = now() - t_begin;
         {
           std::unique_lock<std::mutex> lk(mu);
           cv.wait(lk, [&] { return uploaded > c || rc != DG_OK; });
           if (rc != DG_OK) break;
         }
+        // equal-length chunks (the common case; checked by the uploader) need no chunk-local offsets
+        const uint64_t uniform_L = chunk_len[c];
+        if (!uniform_L) {
+          so.resize((size_t)cn + 1);
+          for (uint32_t k = 0; k <= cn; ++k) so[k] = offsets[q0 + k] - offsets[q0];
+        }
         tm[2] = now() - t_begin;
         dg_batch* b = nullptr;
-        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st, d_up + offsets[q0], up_ev[c], false);
+        int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st, d_up + offsets[q0], up_ev[c], false, uniform_L);
         if (rc1) { fail(rc1, last_error_ref()); break; }
+        b->ev_prepared = prepared_ev[c];
+        b->seq_stream = cs;
+        b->seq_dst = (uint8_t*)r->seqs.p + offsets[q0];
         cudaEvent_t copied = copied_ev[c];
         live.push_back(Live{b, copied});
         tm[3] = now() - t_begin;
@@ -2252,7 +2292,7 @@ struct ChunkPipe {
           }
           r->transfer_bytes += b->nhits * sizeof(dg_hit) + b->pool_bytes + (size_t)cn * 16 + b->nbytes;
         }
-        if (cn && b->nbytes) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
+        // (the normalised sequences left right after k_prepare: run_impl, seq_dst)
         DG_CUDA(cudaEventRecord(copied, cs));
         hit_base += b->nhits;
         pool_base += b->pool_bytes;
@@ -2289,8 +2329,23 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
   // (shrinking the last chunks to shorten the device -> host tail was measured and costs more in
   // per-chunk fixed overhead than it saves)
   p.bounds.push_back(0);
-  for (uint64_t q = getenv("DG_NO_STAGGER") ? chunk : chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
-  if (p.bounds.size() > 1 && nq - p.bounds.back() < chunk / 4) p.bounds.pop_back();  // no tiny tail chunk
+  if (const char* tp = getenv("DG_TAPER")) {
+    // experiment: full chunks, then a geometric taper so that the records of the last chunk -- whose
+    // copy to the host nothing can hide -- are few.  DG_TAPER = number of halvings.
+    const int halvings = std::max(1, atoi(tp));
+    uint64_t q = chunk / 2;
+    while (q < nq && nq - q > chunk + chunk / 2) { p.bounds.push_back((uint32_t)q); q += chunk; }
+    uint64_t rest = nq - q;
+    if (q < nq) p.bounds.push_back((uint32_t)q);
+    for (int h = 0; h < halvings && rest > 32768; ++h) {
+      q += rest / 2;
+      rest -= rest / 2;
+      p.bounds.push_back((uint32_t)q);
+    }
+  } else {
+    for (uint64_t q = getenv("DG_NO_STAGGER") ? chunk : chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
+    if (p.bounds.size() > 1 && nq - p.bounds.back() < chunk / 4) p.bounds.pop_back();  // no tiny tail chunk
+  }
   p.bounds.push_back(nq);
   const uint32_t nchunks = (uint32_t)p.bounds.size() - 1;
   p.idx = idx; p.seqs = seqs; p.offsets = offsets; p.nq = nq; p.nchunks = nchunks; p.params = params;
@@ -2331,14 +2386,16 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     if (!idx->up_stream) DG_CUDA(cudaStreamCreateWithFlags(&idx->up_stream, cudaStreamNonBlocking));
     if (idx->upload.count < offsets[nq] + 1) idx->upload.alloc(offsets[nq] + (offsets[nq] >> 3) + 4096);
     p.d_up = idx->upload.p;
-    while (idx->ev_pool.size() < 3 * (size_t)nchunks) {
+    while (idx->ev_pool.size() < 4 * (size_t)nchunks) {
       cudaEvent_t e;
       DG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       idx->ev_pool.push_back(e);
     }
+    p.chunk_len.assign(nchunks, 0);
     p.up_ev.assign(idx->ev_pool.begin(), idx->ev_pool.begin() + nchunks);
     p.copied_ev.assign(idx->ev_pool.begin() + nchunks, idx->ev_pool.begin() + 2 * (size_t)nchunks);
     p.rebased_ev.assign(idx->ev_pool.begin() + 2 * (size_t)nchunks, idx->ev_pool.begin() + 3 * (size_t)nchunks);
+    p.prepared_ev.assign(idx->ev_pool.begin() + 3 * (size_t)nchunks, idx->ev_pool.begin() + 4 * (size_t)nchunks);
     std::vector<std::thread> others;
     for (int w = 0; w < p.nworkers; ++w) others.emplace_back([&p, w] { p.worker(w); });
     try {
@@ -2356,18 +2413,34 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
         if (b1 < b0) { p.fail(DG_ERR_ARG, "offsets must be non-decreasing"); break; }
         if (b1 > b0) DG_CUDA(cudaMemcpyAsync(idx->upload.p + b0, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, idx->up_stream));
         for (uint32_t c = c0; c < c1; ++c) DG_CUDA(cudaEventRecord(p.up_ev[c], idx->up_stream));
-        { std::lock_guard<std::mutex> g(p.mu); p.uploaded = c1; }
-        p.cv.notify_all();
+        for (uint32_t c = c0; c < c1; ++c) {
+          // is the chunk of one query length?  (this thread has time; the workers are launching kernels)
+          const uint32_t q0 = p.bounds[c], cn = p.bounds[c + 1] - q0;
+          uint64_t L = cn ? offsets[q0 + 1] - offsets[q0] : 0, bad = 0;
+          const uint64_t o0 = offsets[q0];
+          const uint64_t* po = offsets + q0;
+          uint64_t want = o0;
+          for (uint32_t k = 0; k <= cn; ++k, want += L) bad |= po[k] ^ want;
+          { std::lock_guard<std::mutex> g(p.mu); p.chunk_len[c] = bad ? 0 : L; p.uploaded = c + 1; }
+          p.cv.notify_all();
+        }
         c0 = c1;
       }
     } catch (CudaFail& e) {
       p.fail(e.code, last_error_ref());
     }
+    const double tt0 = now();
+    keep_offsets(r, offsets, nq);   // (the calling thread has nothing else to do while the workers run)
+    const double tt1 = now();
     for (auto& t : others) t.join();
+    const double tt2 = now();
     cudaStreamSynchronize(idx->copy_stream);
+    const double tt3 = now();
     for (auto& l : p.leftover) dg_batch_free(l.first);
     p.leftover.clear();
     cudaStreamSynchronize(idx->up_stream);
+    if (p.trace) fprintf(stderr, "[dg_hunt_batch] tail: offsets kept %.3f..%.3f, workers joined %.3f, copies drained %.3f, freed %.3f ms\n",
+                         tt0 - p.t_begin, tt1 - p.t_begin, tt2 - p.t_begin, tt3 - p.t_begin, now() - p.t_begin);
     p.up_ev.clear();
     if (p.rc == DG_OK) {
       DG_CUDA(cudaStreamSynchronize(idx->copy_stream));
@@ -2376,7 +2449,6 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
       else r->hits.bytes = p.hit_base * sizeof(dg_hit);
       r->pool.bytes = p.pool_base;
       idx->wire_n = p.hit_base;
-      keep_offsets(r, offsets, nq);
     }
   } catch (CudaFail& e) {
     p.rc = e.code;
