@@ -70,7 +70,7 @@ EXPORTS = [
     "dg_profile_get", "dg_last_error", "dg_version",
     "dg_comm_get_unique_id", "dg_comm_init", "dg_comm_init_host", "dg_comm_rank", "dg_comm_size", "dg_comm_destroy",
     "dg_allgather_hits", "dg_comm_fetch_table", "dg_allgather_result",
-    "dg_result_records", "dg_result_alignment", "dg_rec_alignment", "dg_recs_sort", "dg_result_transfer_bytes",
+    "dg_fm9_check", "dg_result_records", "dg_result_alignment", "dg_rec_alignment", "dg_recs_sort", "dg_result_transfer_bytes",
 ]
 
 REC_DTYPE = np.dtype([("query", "<u4"), ("chr", "<u4"), ("start", "<u4"), ("score", "<i2"), ("strand", "u1"), ("nops", "u1"),
@@ -98,6 +98,7 @@ def library() -> C.CDLL:
     lib.dg_index_build_text.argtypes = [vp, C.c_uint64, C.c_int, C.POINTER(vp)]
     lib.dg_index_build_synthetic.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(vp)]
     lib.dg_index_write_fm9.argtypes = [vp, C.c_char_p]
+    lib.dg_fm9_check.argtypes = [C.c_char_p]
     lib.dg_index_close.argtypes = [vp]
     lib.dg_index_close.restype = None
     lib.dg_index_size.argtypes = [vp]
@@ -345,6 +346,9 @@ class HuntResult:
             x = params.max_neighborhood
             msg.append(f"Warning: Neighborhood size exceeds {x} candidates. Only first {x} neighbors are searched, "
                        "results are likely incomplete!")
+        if st & Q_NBR_UNVERIFIED:
+            msg.append(f"Warning: Neighborhood may exceed {params.max_neighborhood} candidates; the reference's truncation is not "
+                       "reproduced for sequences longer than 40 nucleotides, all neighbors were searched!")
         if st & Q_HIT_CAP:
             m = params.maxmatches
             msg.append(f"Warning: More than {m} matches found. Only first {m} matches are reported, results are "

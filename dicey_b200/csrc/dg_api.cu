@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "dg_common.cuh"
+#include "fm9.hpp"
 
 namespace dg {
 static thread_local std::string g_err;
@@ -30,6 +31,15 @@ int dg_index_build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int 
 int dg_index_write_fm9(dg_index* idx, const char* fm9_path) {
   if (!idx || !fm9_path) { set_error("null argument"); return DG_ERR_ARG; }
   return write_fm9(idx, fm9_path);
+}
+
+int dg_fm9_check(const char* fm9_path) {
+  if (!fm9_path) { set_error("null argument"); return DG_ERR_ARG; }
+  Fm9 f;
+  std::string err;
+  const int rc = fm9_parse(fm9_path, f, err);
+  if (rc) set_error(err);
+  return rc;
 }
 
 void dg_index_close(dg_index* idx) {

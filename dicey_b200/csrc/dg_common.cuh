@@ -56,6 +56,7 @@ struct DevBuf {
 struct TabEntry {
   DevBuf<uint32_t> blob;
   std::vector<uint32_t> tab_cnt;   // host copy of tab_cnt
+  std::vector<uint32_t> script_ub; // host copy of script_ub
 };
 
 struct ProfileState {

@@ -483,6 +483,61 @@ DG_HD bool is_minimal_d1(const Packed4& q, int m, const Packed4& t, int L) {
 }
 
 // ------------------------------------------------------------------------------------------
+// An upper bound on the number of DISTINCT strings neighbors() generates for q at edit distance
+// d <= 2 -- hence on the size its set can ever have, hence a certificate that the cap of
+// neighbors.h:50 is never reached when the bound stays below max_neighborhood.  (Queries that miss
+// the certificate are replayed exactly on the host, nbr_trunc.hpp.)
+// The scripts (one or two events, sorted as in Script) are counted except those a rule below maps
+// to a strictly smaller script -- fewer events, else smaller (pos1, kind1, pos2, kind2) with
+// substitution < deletion < insertion -- that spells the same string.  The smallest script of a
+// string is never discounted, so the count never falls below the number of distinct strings.
+//   L(p, k): the event could move one base to the left:  deletion inside a run (q[p] == q[p-1]),
+//            insertion of the letter that precedes it (c == q[p-1]).
+//   A  L(event 1)                                   -> event 1 one base to the left
+//   B  L(event 2), base pos2 - 1 untouched by event 1 -> event 2 one base to the left
+//   C  (delete p, insert before p + 1)              -> one substitution at p, or nothing
+//   D  (insert before p, delete p)                  -> one substitution at p, or nothing
+//   E  (insert c before p, substitute p), p + 1 < m -> (substitute p by c, insert before p + 1), or one insertion
+//   F  (delete p, substitute p + 1 by x)            -> (substitute p by x, delete p + 1), or one deletion
+// bq(i) returns the base code of q[i] (0..3, 4 = not ACGT).
+template <typename BaseAt>
+DG_HD bool nbr_event_shiftable(BaseAt bq, int p, int k) {
+  if (p == 0 || k < 4) return false;
+  if (k == 4) return bq(p) == bq(p - 1);
+  return (k - 5) == bq(p - 1);
+}
+template <typename BaseAt>
+DG_HD bool nbr_pair_discounted(BaseAt bq, int m, int p1, int k1, int p2, int k2) {
+  if (nbr_event_shiftable(bq, p1, k1)) return true;                                   // A
+  if ((p2 > p1 + 1 || (p2 == p1 + 1 && k1 >= 5)) && nbr_event_shiftable(bq, p2, k2)) return true;   // B
+  if (k1 == 4 && k2 >= 5 && p2 == p1 + 1) return true;                                // C
+  if (k1 >= 5 && k2 == 4 && p2 == p1) return true;                                    // D
+  if (k1 >= 5 && k2 < 4 && p2 == p1 && p1 + 1 < m) return true;                       // E
+  if (k1 == 4 && k2 < 4 && p2 == p1 + 1) return true;                                 // F
+  return false;
+}
+// events e = pos * 9 + k in [e_lo, e_hi) are taken as FIRST events (so that the lanes of a warp can
+// share one query); the unedited string and the single events are counted by the caller that owns
+// e_lo == 0.
+template <typename BaseAt>
+DG_HD uint32_t nbr_upper_bound_part(BaseAt bq, int m, int d, int e_lo, int e_hi, int e_step) {
+  uint32_t n = 0;
+  const int E = 9 * m;
+  for (int e1 = e_lo; e1 < e_hi; e1 += e_step) {
+    const int p1 = e1 / 9, k1 = e1 - 9 * p1;
+    if (k1 < 4 && k1 == bq(p1)) continue;                        // not an edit
+    if (!nbr_event_shiftable(bq, p1, k1)) ++n;                   // the single event
+    if (d < 2 || nbr_event_shiftable(bq, p1, k1)) continue;      // (rule A discounts every pair of it)
+    for (int e2 = second_event_start(p1, k1, true); e2 < E; ++e2) {
+      const int p2 = e2 / 9, k2 = e2 - 9 * p2;
+      if (k2 < 4 && k2 == bq(p2)) continue;
+      if (!nbr_pair_discounted(bq, m, p1, k1, p2, k2)) ++n;
+    }
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
 // needle() for std::string x std::string, AlignConfig<false,true>, DnaScore(0,-1,-1,-1)
 // (needle.h:59-138, align.h:52-80): rows = genomic g (length mg), columns = query s (length n).
 // tr: trace storage (TraceBytes: >= ((mg+1)*(n+1)+3)/4 bytes; TraceRows64: mg+1 words, n <= 31);

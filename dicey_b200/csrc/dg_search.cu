@@ -27,6 +27,7 @@
 #include <new>
 
 #include "dg_common.cuh"
+#include "nbr_trunc.hpp"
 
 namespace dg {
 
@@ -45,8 +46,16 @@ struct BatchDev {
   uint8_t indel, reverse;
   uint64_t* qcode;          // 2 per query: packed forward / reverse-complement search string
   uint8_t* qflag;           // bit0 = ACGT only ("clean"), bit1 = packed code valid
-  uint32_t* irregular;      // set when any query departs from the uniform batch shape
+  uint32_t* irregular;      // bit 0: a query departs from the uniform batch shape; bit 1: a Hamming neighbourhood
+                            // reaches the cap; bit 2: an edit neighbourhood is not certified below the cap
   uint32_t uniform_len;     // common raw length of the batch (0 = mixed lengths)
+  // neighbourhoods the cap -x truncated (neighbors.h:50), replayed on the host (nbr_trunc.hpp): for the
+  // (query, strand) pairs listed in trunc_qs (ascending (q << 1) | strand) the set IS the sorted key list
+  // trunc_keys[trunc_off[i] .. trunc_off[i + 1]) instead of the substring-minimal strings
+  const uint32_t* trunc_qs;
+  const uint32_t* trunc_off;
+  const ulonglong2* trunc_keys;
+  uint32_t n_trunc;
 };
 
 DG_HD void query_geom(const BatchDev& b, uint32_t q, int strand, const uint8_t*& base, int& m, int& koff) {
@@ -93,6 +102,7 @@ namespace {
 // and is only ever handed out again for work on the same stream, so stream order keeps reuse
 // safe without events; misses fall through to cudaMallocAsync.
 struct StreamPool {
+  std::mutex mu;                               // (a stream's pool may be shared by host threads: DG_WORKERS, callers of one index)
   std::multimap<size_t, void*> free_blocks;   // capacity -> block
   size_t cached = 0;
   static size_t round_up(size_t bytes) {       // (8 + k) * 2^e classes: at most 12.5 % slack
@@ -102,6 +112,7 @@ struct StreamPool {
     return (bytes + step - 1) & ~(step - 1);
   }
   void* get(size_t cap) {
+    std::lock_guard<std::mutex> g(mu);
     auto it = free_blocks.find(cap);
     if (it == free_blocks.end()) return nullptr;
     void* p = it->second;
@@ -110,6 +121,7 @@ struct StreamPool {
     return p;
   }
   bool put(void* p, size_t cap) {
+    std::lock_guard<std::mutex> g(mu);
     if (cached + cap > (24ULL << 30)) return false;
     free_blocks.emplace(cap, p);
     cached += cap;
@@ -204,6 +216,7 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   }
   if (d > (uint32_t)kMaxDist || (b.seed_len && d >= b.seed_len)) st |= DG_Q_UNSUPPORTED;
   bool run = !(st & (DG_Q_SKIPPED | DG_Q_TOO_SHORT | DG_Q_UNSUPPORTED));
+  if (run && b.max_loc == 0) st |= DG_Q_HIT_CAP;   // -m 0: no hit is taken and hunter.h:434 (0 >= 0) warns for every query
   bool clean = true;
   uint64_t cf = 0, cr = 0;
   if (run) {
@@ -221,11 +234,13 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
     // neighbors.h:50 stops the DFS once the set holds max_neighborhood strings.  The set never
     // holds more strings than scripts were generated, so fewer scripts than the cap certifies an
     // untruncated neighbourhood.  Hamming sets hold exactly one string per script.
+    // Edit mode: k_nbr_bound certifies most of the flagged queries afterwards; what stays flagged, and
+    // every Hamming query whose (exactly known) set size reaches the cap, is replayed on the host.
     if (b.indel) {
       if (ut.script_ub[m] >= b.max_nbr) st |= DG_Q_NBR_UNVERIFIED;
     } else {
       uint64_t size = 1 + (d >= 1 ? w : 0) + (d >= 2 ? (w * w - w2) / 2 : 0);
-      if (size >= b.max_nbr) st |= DG_Q_NBR_CAP;
+      if (size >= b.max_nbr) { st |= DG_Q_NBR_CAP; atomicOr(b.irregular, 2u); }
     }
   }
   bool packed = run && clean && (m + (int)d <= kMaxPacked);
@@ -238,6 +253,32 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   // packed queries are searched by k_search_packed; k_search takes the rest
   units[q] = (run && !packed) ? (uint64_t)ut.tab_cnt[variant * 256 + m] * (b.reverse ? 2 : 1) : 0;
   if (!run || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
+}
+
+// One warp per query still flagged DG_Q_NBR_UNVERIFIED: the bound of dg_core.cuh (nbr_upper_bound_part)
+// on the number of distinct strings neighbors() can generate, for both strands; below the cap the
+// flag goes (the reference cannot have truncated), otherwise the host replays the query exactly.
+__global__ void k_nbr_bound(BatchDev b) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t q = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (q >= b.nq) return;
+  const uint32_t st = b.status[q];
+  if (!(st & DG_Q_NBR_UNVERIFIED)) return;
+  const int d = (int)b.dist[q];
+  bool ok = d <= 2;
+  for (int strand = 0; ok && strand < (b.reverse ? 2 : 1); ++strand) {
+    const uint8_t* base;
+    int m, koff;
+    query_geom(b, q, strand, base, m, koff);
+    auto bq = [&](int j) { return base_code(base[j]); };
+    uint32_t n = nbr_upper_bound_part(bq, m, d, (int)lane, 9 * m, 32);
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    if (1u + n >= b.max_nbr) ok = false;
+  }
+  if (lane == 0) {
+    if (ok) b.status[q] = st & ~(uint32_t)DG_Q_NBR_UNVERIFIED;
+    else atomicOr(b.irregular, 4u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -800,6 +841,24 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
       uint8_t ch = t[j];
       uint64_t v = ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 5 : 4;
       if (j < 21) k.hi |= v << (60 - 3 * j); else k.lo |= v << (60 - 3 * (j - 21));
+    }
+  }
+  if (b.n_trunc) {
+    // a neighbourhood the cap truncated: the set is the replayed list, not the minimal strings
+    const uint32_t qs = (c.q << 1) | (uint32_t)strand;
+    const uint32_t t = lower_bound_u32(b.trunc_qs, 0, b.n_trunc, qs);
+    if (t < b.n_trunc && b.trunc_qs[t] == qs) {
+      uint32_t lo = b.trunc_off[t], hi = b.trunc_off[t + 1];
+      while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const ulonglong2 e = b.trunc_keys[mid];
+        if (e.x < k.hi || (e.x == k.hi && e.y < k.lo)) lo = mid + 1; else hi = mid;
+      }
+      keep = false;
+      if (lo < b.trunc_off[t + 1]) {
+        const ulonglong2 e = b.trunc_keys[lo];
+        keep = e.x == k.hi && e.y == k.lo;
+      }
     }
   }
   k.qs = keep ? ((c.q << 1) | (uint32_t)strand) : sentinel;
@@ -1454,6 +1513,10 @@ struct dg_batch {
   ABuf<uint64_t> off, units, unit_off;
   ABuf<uint32_t> status, dist, irregular;
   std::shared_ptr<TabEntry> tabs;   // unit tables (cached in the index)
+  bool maybe_capped = false;        // some query length could reach the cap -x: certify / replay after k_prepare
+  ABuf<uint32_t> trunc_qs, trunc_off;
+  ABuf<ulonglong2> trunc_keys;
+  uint32_t n_trunc = 0;
   ABuf<uint64_t> qcode;
   ABuf<uint8_t> qflag;
   uint32_t uniform_len = 0;
@@ -1499,6 +1562,7 @@ static BatchDev batch_dev(const dg_batch* b) {
   d.max_nbr = b->par.max_neighborhood ? b->par.max_neighborhood : 10000;
   d.qcode = b->qcode.p; d.qflag = b->qflag.p; d.irregular = b->irregular.p; d.uniform_len = b->uniform_len;
   d.indel = b->par.indel; d.reverse = b->par.reverse;
+  d.trunc_qs = b->trunc_qs.p; d.trunc_off = b->trunc_off.p; d.trunc_keys = b->trunc_keys.p; d.n_trunc = b->n_trunc;
   return d;
 }
 
@@ -1531,7 +1595,6 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
     b->ix = ix;
     b->st = st;
     b->par = *par;
-    if (b->par.max_locations == 0) b->par.max_locations = 1;
     b->nq = nq;
     b->nbytes = total_bytes;
     // distinct search-string lengths -> unit tables
@@ -1602,12 +1665,24 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
         e->blob.alloc(blob.size() + 1);
         DG_CUDA(cudaMemcpy(e->blob.p, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
         e->tab_cnt = tab_cnt;
+        e->script_ub = sub;
         if (ix->tab_cache.size() >= 64) ix->tab_cache.clear();   // (batches in flight keep their entry alive)
         ix->tab_cache[key] = e;
         b->tabs = e;
       }
     }
     const std::vector<uint32_t>& tab_cnt = b->tabs->tab_cnt;
+    {
+      // can any query of this batch reach the cap?  (edit mode: by script count; Hamming: by the size of
+      // an all-N query of that length)
+      const uint64_t cap = par->max_neighborhood ? par->max_neighborhood : 10000;
+      for (int m = 1; m < 256 && !b->maybe_capped; ++m) {
+        if (!have[m]) continue;
+        const uint64_t d = std::min<uint64_t>(par->distance, (uint64_t)m - 1), w = 4ull * m;
+        const uint64_t hsize = 1 + (d >= 1 ? w : 0) + (d >= 2 ? (w * w - 16ull * m) / 2 : 0);
+        if (indel ? b->tabs->script_ub[m] >= cap : hsize >= cap) b->maybe_capped = true;
+      }
+    }
     const double ts1 = now();
     b->irregular.alloc(1, st);
     // uniform batches (one length, all ACGT, nothing skipped) map unit -> query by a division
@@ -1650,6 +1725,118 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
   } catch (CudaFail& e) {
     delete b;
     return e.code;
+  }
+}
+
+// The queries k_prepare / k_nbr_bound left flagged (their neighbourhood may reach the cap -x) are
+// replayed in the reference's own generation order on the host (nbr_trunc.hpp).  A strand whose set
+// stays below the cap needs nothing: the device's substring-minimal set is the reference's.  A strand
+// that reaches it gets its truncated set as a sorted key list (BatchDev::trunc_*), and the query the
+// warning of hunter.h:342-345 (DG_Q_NBR_CAP).  Rare by construction; costs one stream synchronisation
+// when the batch holds a query length that could reach the cap at all.
+static int resolve_truncation(dg_batch* b, cudaStream_t st) {
+  try {
+    uint32_t irr = 0;
+    DG_CUDA(cudaMemcpyAsync(&irr, b->irregular.p, 4, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    if (!(irr & 6u)) return DG_OK;
+    const uint32_t nq = b->nq;
+    const bool indel = b->par.indel != 0;
+    const uint32_t cap = b->par.max_neighborhood ? b->par.max_neighborhood : 10000;
+    std::vector<uint32_t> status(nq), dist(nq);
+    std::vector<uint64_t> off((size_t)nq + 1);
+    std::vector<uint8_t> fwd((size_t)b->nbytes + 1);
+    DG_CUDA(cudaMemcpyAsync(status.data(), b->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaMemcpyAsync(dist.data(), b->dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaMemcpyAsync(off.data(), b->off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (b->nbytes) DG_CUDA(cudaMemcpyAsync(fwd.data(), b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    const uint32_t want = indel ? (uint32_t)DG_Q_NBR_UNVERIFIED : (uint32_t)DG_Q_NBR_CAP;
+    std::vector<uint32_t> flagged;
+    for (uint32_t q = 0; q < nq; ++q)
+      if ((status[q] & want) && !(status[q] & (DG_Q_TOO_SHORT | DG_Q_SKIPPED | DG_Q_UNSUPPORTED))) flagged.push_back(q);
+    if (flagged.empty()) return DG_OK;
+    const int nstrand = b->par.reverse ? 2 : 1;
+    struct Out { bool capped[2] = {false, false}; bool unkeyed = false; std::vector<ulonglong2> keys[2]; };
+    std::vector<Out> outs(flagged.size());
+    auto work = [&](size_t lo, size_t hi) {
+      NeighborReplay nr;
+      for (size_t i = lo; i < hi; ++i) {
+        const uint32_t q = flagged[i];
+        const uint8_t* s = fwd.data() + off[q];
+        const int L = (int)(off[q + 1] - off[q]);
+        const int m = b->par.seed_len ? (int)b->par.seed_len : L;
+        for (int strand = 0; strand < nstrand; ++strand) {
+          std::string str;
+          if (strand == 0) {
+            str.assign((const char*)s + (L - m), (size_t)m);
+          } else {
+            for (int j = 0; j < m; ++j) {
+              const uint8_t ch = s[L - 1 - j];
+              str.push_back(ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N');
+            }
+          }
+          const bool capped = nr.run(str, (int)dist[q], indel, cap);
+          outs[i].capped[strand] = capped;
+          if (!capped) continue;
+          for (const std::string& t : nr.strings()) {
+            if ((int)t.size() > kKeyChars) { outs[i].unkeyed = true; break; }
+            ulonglong2 k = make_ulonglong2(0, 0);
+            for (int j = 0; j < (int)t.size(); ++j) {
+              const char ch = t[j];
+              const unsigned long long v = ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 5 : 4;
+              if (j < 21) k.x |= v << (60 - 3 * j); else k.y |= v << (60 - 3 * (j - 21));
+            }
+            outs[i].keys[strand].push_back(k);
+          }
+          std::sort(outs[i].keys[strand].begin(), outs[i].keys[strand].end(),
+                    [](const ulonglong2& a, const ulonglong2& c) { return a.x < c.x || (a.x == c.x && a.y < c.y); });
+        }
+      }
+    };
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(flagged.size(), 64), std::thread::hardware_concurrency()));
+    if (nthreads <= 1) {
+      work(0, flagged.size());
+    } else {
+      std::vector<std::thread> ts;
+      for (size_t t = 0; t < nthreads; ++t) ts.emplace_back(work, flagged.size() * t / nthreads, flagged.size() * (t + 1) / nthreads);
+      for (auto& t : ts) t.join();
+    }
+    std::vector<uint32_t> qs, loff(1, 0);
+    std::vector<ulonglong2> keys;
+    for (size_t i = 0; i < flagged.size(); ++i) {
+      const uint32_t q = flagged[i];
+      Out& o = outs[i];
+      if (o.unkeyed) {   // strings longer than the sort key: cannot be listed; the flag stays
+        status[q] |= DG_Q_NBR_UNVERIFIED;
+        continue;
+      }
+      status[q] &= ~(uint32_t)(DG_Q_NBR_UNVERIFIED | DG_Q_NBR_CAP);
+      if (o.capped[0] || o.capped[1]) status[q] |= DG_Q_NBR_CAP;
+      for (int strand = 0; strand < nstrand; ++strand) {
+        if (!o.capped[strand]) continue;
+        qs.push_back((q << 1) | (uint32_t)strand);
+        keys.insert(keys.end(), o.keys[strand].begin(), o.keys[strand].end());
+        loff.push_back((uint32_t)keys.size());
+      }
+    }
+    DG_CUDA(cudaMemcpyAsync(b->status.p, status.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+    b->n_trunc = (uint32_t)qs.size();
+    if (b->n_trunc) {
+      b->trunc_qs.alloc(qs.size(), st);
+      b->trunc_off.alloc(loff.size(), st);
+      b->trunc_keys.alloc(keys.size() + 1, st);
+      DG_CUDA(cudaMemcpyAsync(b->trunc_qs.p, qs.data(), qs.size() * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(b->trunc_off.p, loff.data(), loff.size() * 4, cudaMemcpyHostToDevice, st));
+      if (!keys.empty()) DG_CUDA(cudaMemcpyAsync(b->trunc_keys.p, keys.data(), keys.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice, st));
+    }
+    DG_CUDA(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    return DG_OK;
+  } catch (CudaFail& e) {
+    return e.code;
+  } catch (std::bad_alloc&) {
+    set_error("out of host memory");
+    return DG_ERR_NOMEM;
   }
 }
 
@@ -1702,6 +1889,13 @@ static int run_impl(dg_batch* b) {
       cub::DeviceScan::ExclusiveSum(nullptr, tb, b->units.p, b->unit_off.p, (int)(nq + 1), st);
       cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, b->units.p, b->unit_off.p, (int)(nq + 1), st);
       launches += 2;
+    }
+    if (b->maybe_capped && nq) {
+      b->n_trunc = 0;
+      if (b->par.indel) { k_nbr_bound<<<grid_for(32ull * nq, B), B, 0, st>>>(bd); ++launches; }
+      const int rc_t = resolve_truncation(b, st);
+      if (rc_t) return rc_t;
+      bd = batch_dev(b);   // (picks the lists up)
     }
     prof_mark(ix, 1, st);
     // ---- search

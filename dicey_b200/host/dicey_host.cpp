@@ -40,6 +40,7 @@ struct HunterConfig {  // hunter.h:37-50
   uint64_t max_locations = 1000;
   std::string sequence, genome, outfile;
   int device = 0;
+  std::vector<int> devices;   // --devices a,b,c: the queries are sharded over these GPUs (index replicated)
 };
 
 struct DnaHitView {  // one DnaHit (hunter.h:53-66) read out of a dg_result (the alignment rows stay in its pool)
@@ -134,9 +135,10 @@ std::string hunt_json(const HunterConfig& c, uint32_t distance, const std::strin
 }
 
 // jsonDnaHitOut (hunter.h:162-175)
+bool g_write_failed = false;   // a failed write of the output file ends the program with a non-zero exit code
 void emit(const HunterConfig& c, const std::string& json) {
   if (c.hasOutfile) {
-    if (!gz_append(c.outfile, json)) std::cerr << "Error: cannot write " << c.outfile << std::endl;
+    if (!gz_append(c.outfile, json)) { std::cerr << "Error: cannot write " << c.outfile << std::endl; g_write_failed = true; }
   } else {
     std::cout << json << std::flush;
   }
@@ -156,6 +158,8 @@ void hunt_usage(const char* argv0) {
                "                                        distance\n"
                "  -f [ --forward ]                      only forward matches\n"
                "  --device arg (=0)                     CUDA device (dicey-b200 only)\n"
+               "  --devices arg                         comma-separated CUDA devices: the index is\n"
+               "                                        replicated, the queries are sharded (dicey-b200 only)\n"
                "\n";
 }
 
@@ -163,13 +167,25 @@ int hunter(int argc, char** argv) {
   HunterConfig c;
   Options opt({{"help", '?', false}, {"genome", 'g', true}, {"outfile", 'o', true}, {"maxmatches", 'm', true},
                {"maxNeighborhood", 'x', true}, {"distance", 'd', true}, {"hamming", 'n', false},
-               {"forward", 'f', false}, {"input-file", 0, true}, {"device", 0, true}});
+               {"forward", 'f', false}, {"input-file", 0, true}, {"device", 0, true}, {"devices", 0, true}});
   try {
     opt.parse(argc, argv);
     c.max_locations = opt.get_u64("maxmatches", 1000);
     c.maxNeighborhood = (uint32_t)opt.get_u64("maxNeighborhood", 10000);
     c.distance = (uint32_t)opt.get_u64("distance", 1);
     c.device = (int)opt.get_u64("device", getenv("DICEY_B200_DEVICE") ? strtoull(getenv("DICEY_B200_DEVICE"), nullptr, 10) : 0);
+    if (opt.has("devices")) {
+      std::string list = opt.get("devices"), tok;
+      for (size_t i = 0; i <= list.size(); ++i) {
+        if (i == list.size() || list[i] == ',') {
+          if (!tok.empty()) c.devices.push_back(std::stoi(tok));
+          tok.clear();
+        } else {
+          tok += list[i];
+        }
+      }
+    }
+    if (c.devices.empty()) c.devices.push_back(c.device);
   } catch (std::exception& e) {
     std::cerr << "dicey " << argv[0] << ": " << e.what() << std::endl;
     return 1;
@@ -215,20 +231,59 @@ int hunter(int argc, char** argv) {
   std::vector<uint32_t> seqlen(lens.size());
   for (size_t i = 0; i < lens.size(); ++i) seqlen[i] = (uint32_t)(lens[i] + 1);  // util.h:201
 
-  // FM-index: <parent>/<stem>.fm9 (hunter.h:248-256), transcoded to the device layout
+  // FM-index: <parent>/<stem>.fm9 (hunter.h:248-256), transcoded to the device layout -- one replica per
+  // GPU of --devices, loaded side by side
   std::string index_file = path_join(path_parent(c.genome), path_stem(c.genome)) + ".fm9";
-  dg_index* ix = nullptr;
-  if (dg_index_open(index_file.c_str(), c.device, &ix) != DG_OK) {
-    std::cerr << "dicey-b200: " << dg_last_error() << std::endl;
-    return fail("Error: FM-Index cannot be loaded!");
+  const int ndev = (int)c.devices.size();
+  struct Shard {
+    dg_index* ix = nullptr;
+    dg_comm* comm = nullptr;
+    dg_result* res = nullptr;
+    uint32_t q0 = 0, q1 = 0;
+    std::vector<uint64_t> off;     // shard-local query offsets
+    int rc = DG_OK;
+    std::string err;
+    uint64_t gathered = 0;         // hits of all shards, as the all-gather reported them to this shard
+    // result views
+    const dg_rec* recs = nullptr;
+    const uint64_t* qoff = nullptr;
+    const uint32_t* status = nullptr;
+    const uint32_t* qdist = nullptr;
+    const char* norm = nullptr;
+    uint64_t nh = 0;
+  };
+  std::vector<Shard> shards((size_t)ndev);
+  auto close_all = [&]() {
+    for (auto& s : shards) {
+      if (s.res) dg_result_free(s.res);
+      if (s.comm) dg_comm_destroy(s.comm);
+      if (s.ix) dg_index_close(s.ix);
+      s.res = nullptr; s.comm = nullptr; s.ix = nullptr;
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d)
+      th.emplace_back([&, d] {
+        Shard& s = shards[(size_t)d];
+        s.rc = dg_index_open(index_file.c_str(), c.devices[(size_t)d], &s.ix);
+        if (s.rc != DG_OK) { s.err = dg_last_error(); return; }
+        dg_index_set_records(s.ix, seqlen.data(), (uint32_t)seqlen.size());
+      });
+    for (auto& t : th) t.join();
   }
-  dg_index_set_records(ix, seqlen.data(), (uint32_t)seqlen.size());
-  stage("index load", dg_index_size(ix));
+  for (auto& s : shards)
+    if (s.rc != DG_OK) {
+      std::cerr << "dicey-b200: " << s.err << std::endl;
+      close_all();
+      return fail("Error: FM-Index cannot be loaded!");
+    }
+  stage("index load", dg_index_size(shards[0].ix));
 
   // queries (hunter.h:262-288)
   std::vector<std::pair<std::string, std::string>> queries;
   if (is_regular_file(c.sequence)) {
-    if (!is_fasta(c.sequence)) { dg_index_close(ix); return fail("Error: Input file is not in FASTA format!"); }
+    if (!is_fasta(c.sequence)) { close_all(); return fail("Error: Input file is not in FASTA format!"); }
     std::ifstream fa(c.sequence.c_str());
     std::string line, fan, faseq;
     while (std::getline(fa, line)) {
@@ -247,7 +302,7 @@ int hunter(int argc, char** argv) {
   }
 
   stage("queries read", queries.size());
-  // one batched call for every query (hunter.h:289-433 per query)
+  // one batched call per GPU for its contiguous shard of the queries (hunter.h:289-433 per query)
   std::string cat;
   std::vector<uint64_t> off(1, 0);
   for (const auto& q : queries) { cat += q.second; off.push_back(cat.size()); }
@@ -259,31 +314,68 @@ int hunter(int argc, char** argv) {
   par.indel = c.indel ? 1 : 0;
   par.reverse = c.reverse ? 1 : 0;
   par.seed_len = 0;
-  // the device path enumerates distances 0..2; a larger -d is clamped per query to |seq| - 1 by the
-  // reference, so only queries that keep d > 2 after clamping are out of reach
-  dg_result* res = nullptr;
-  bool all_unsupported = false;
-  if (par.distance > 2) {
-    uint64_t minlen = ~0ULL;
-    for (size_t q = 0; q + 1 < off.size(); ++q) minlen = std::min<uint64_t>(minlen, off[q + 1] - off[q]);
-    all_unsupported = true;
+  // the device path enumerates distances 0..2; beyond that no query is searched (the reference clamps -d
+  // to |seq| - 1 per query, which is still > 2 for every query of 10 bases or more)
+  const bool all_unsupported = par.distance > 2;
+  const uint32_t nq_all = (uint32_t)queries.size();
+  uint8_t comm_id[DG_COMM_ID_BYTES];
+  bool use_comm = ndev > 1 && !all_unsupported;
+  if (use_comm && dg_comm_get_unique_id(comm_id) != DG_OK) {
+    std::cerr << "dicey-b200: " << dg_last_error() << " (continuing without the hit all-gather)" << std::endl;
+    use_comm = false;
   }
-  int rc = DG_OK;
-  if (!all_unsupported) rc = dg_hunt_batch(ix, cat.data(), off.data(), (uint32_t)queries.size(), &par, &res);
-  if (rc != DG_OK) {
-    std::cerr << "dicey-b200: " << dg_last_error() << std::endl;
-    dg_index_close(ix);
-    return fail(std::string("Error: GPU search failed (") + dg_last_error() + ")!");
+  if (!all_unsupported) {
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d)
+      th.emplace_back([&, d] {
+        Shard& s = shards[(size_t)d];
+        s.q0 = (uint32_t)((uint64_t)nq_all * (uint64_t)d / (uint64_t)ndev);
+        s.q1 = (uint32_t)((uint64_t)nq_all * (uint64_t)(d + 1) / (uint64_t)ndev);
+        s.off.resize((size_t)(s.q1 - s.q0) + 1);
+        for (uint32_t q = s.q0; q <= s.q1; ++q) s.off[q - s.q0] = off[q] - off[s.q0];
+        if (use_comm) {
+          s.rc = dg_comm_init(ndev, d, comm_id, s.ix, &s.comm);
+          if (s.rc != DG_OK) { s.err = dg_last_error(); return; }
+        }
+        s.rc = dg_hunt_batch(s.ix, cat.data() + off[s.q0], s.off.data(), s.q1 - s.q0, &par, &s.res);
+        if (s.rc != DG_OK) { s.err = dg_last_error(); return; }
+        uint32_t nq = 0;
+        s.recs = dg_result_records(s.res, &s.nh);
+        s.qoff = dg_result_query_offsets(s.res, &nq);
+        s.status = dg_result_query_status(s.res);
+        s.qdist = dg_result_query_distance(s.res);
+        uint64_t seq_bytes = 0;
+        s.norm = dg_result_sequences(s.res, &seq_bytes);
+        if (s.comm) {
+          // the exchange step: every GPU ends up with the coordinates of every hit of the batch (HBM)
+          const dg_wire* table = nullptr;
+          uint64_t slot = 0;
+          const uint64_t* counts = nullptr;
+          s.rc = dg_allgather_hits(s.comm, nullptr, s.q0, &table, &slot, &counts);
+          if (s.rc != DG_OK) { s.err = dg_last_error(); return; }
+          for (int r = 0; r < ndev; ++r) s.gathered += counts[r];
+          if (counts[d] != s.nh) { s.rc = DG_ERR_FORMAT; s.err = "hit all-gather: this rank's count differs from its result"; }
+        }
+      });
+    for (auto& t : th) t.join();
+    uint64_t total = 0;
+    for (auto& s : shards) total += s.nh;
+    for (auto& s : shards) {
+      if (s.rc == DG_OK && s.comm && s.gathered != total) { s.rc = DG_ERR_FORMAT; s.err = "hit all-gather: gathered count differs from the sum of the shards"; }
+      if (s.rc != DG_OK) {
+        std::cerr << "dicey-b200: " << s.err << std::endl;
+        std::string m = std::string("Error: GPU search failed (") + s.err + ")!";
+        close_all();
+        return fail(m);
+      }
+    }
+    stage(ndev > 1 ? "search (dg_hunt_batch per GPU + dg_allgather_hits)" : "search (dg_hunt_batch)", total);
   }
-  uint64_t nh = 0, pool_bytes = 0, seq_bytes = 0;
-  uint32_t nq = 0;
-  const dg_hit* hits = res ? dg_result_hits(res, &nh) : nullptr;
-  const uint64_t* qoff = res ? dg_result_query_offsets(res, &nq) : nullptr;
-  const uint32_t* status = res ? dg_result_query_status(res) : nullptr;
-  const uint32_t* qdist = res ? dg_result_query_distance(res) : nullptr;
-  const char* pool = res ? dg_result_pool(res, &pool_bytes) : nullptr;
-  const char* norm = res ? dg_result_sequences(res, &seq_bytes) : nullptr;
-  stage("search (dg_hunt_batch)", nh);
+  auto shard_of = [&](size_t qi) -> const Shard& {
+    for (size_t d = 0; d + 1 < (size_t)ndev; ++d)
+      if (qi < shards[d].q1) return shards[d];
+    return shards[(size_t)ndev - 1];
+  };
 
   // one JSON line per query (hunter.h:289-444), formatted by several threads over blocks of queries
   // and written in query order, one write (one gzip member) per block instead of per query: the
@@ -297,7 +389,9 @@ int hunter(int argc, char** argv) {
       out += hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m);
       return;
     }
-    uint32_t st = all_unsupported ? (uint32_t)DG_Q_UNSUPPORTED : status[qi];
+    const Shard& sh = shard_of(qi);
+    const size_t ql = qi - sh.q0;
+    uint32_t st = all_unsupported ? (uint32_t)DG_Q_UNSUPPORTED : sh.status[ql];
     if (st & DG_Q_UNSUPPORTED) {
       m.push_back("Error: Query is outside the limits of the GPU search path (length <= 255, distance <= 2)!");
       out += hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m);
@@ -315,32 +409,48 @@ int hunter(int argc, char** argv) {
       m.push_back("Warning: Neighborhood size exceeds " + x + " candidates. Only first " + x +
                   " neighbors are searched, results are likely incomplete!");
     }
+    if (st & DG_Q_NBR_UNVERIFIED) {
+      // not a message of the reference: its neighbourhood may have been truncated at -x, and the truncated
+      // set of a query this long cannot be reproduced on the device; every neighbour was searched
+      m.push_back("Warning: Neighborhood may exceed " + std::to_string(c.maxNeighborhood) +
+                  " candidates; the reference's truncation is not reproduced for sequences longer than 40 nucleotides, all neighbors were searched!");
+    }
     if (st & DG_Q_HIT_CAP) {
       std::string x = std::to_string(c.max_locations);
       m.push_back("Warning: More than " + x + " matches found. Only first " + x +
                   " matches are reported, results are likely incomplete!");
     }
-    std::vector<dg_hit> mine(hits + qoff[qi], hits + qoff[qi + 1]);
-    dg_hits_sort(mine.data(), mine.size());  // hunter.h:440
+    std::vector<dg_rec> mine(sh.recs + sh.qoff[ql], sh.recs + sh.qoff[ql + 1]);
+    dg_recs_sort(mine.data(), mine.size());  // hunter.h:440
+    // the records carry their alignments as edit operations: both rows are rebuilt from the query
+    const std::string sequence(sh.norm + sh.off[ql], sh.norm + sh.off[ql + 1]);
+    std::string rev(sequence.rbegin(), sequence.rend());
+    for (char& ch : rev) ch = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N';
+    const size_t stride = sequence.size() + 4;
+    std::vector<char> rows(2 * stride * mine.size() + 1);
     ht.reserve(mine.size());
-    for (const auto& h : mine) {
+    for (size_t i = 0; i < mine.size(); ++i) {
+      const dg_rec& h = mine[i];
       DnaHitView v;
       v.score = h.score; v.chr = h.chr; v.start = h.start; v.strand = (char)h.strand;
-      v.refalign = pool + h.aln_off;
-      v.queryalign = pool + h.aln_off + h.aln_len;
-      v.aln_len = h.aln_len;
+      char* ra = rows.data() + 2 * stride * i;
+      char* qa = ra + stride;
+      const std::string& sq = h.strand == '-' ? rev : sequence;
+      const int cols = dg_rec_alignment(&h, sq.data(), (uint32_t)sq.size(), ra, qa);
+      v.refalign = ra;
+      v.queryalign = qa;
+      v.aln_len = cols > 0 ? (uint32_t)cols : 0;
       ht.push_back(v);
     }
-    std::string sequence(norm + off[qi], norm + off[qi + 1]);
-    out += hunt_json(c, qdist[qi], sequence, queries[qi].first, seqname, ht, m);
+    out += hunt_json(c, sh.qdist[ql], sequence, queries[qi].first, seqname, ht, m);
   };
   {
-    const size_t nq_all = queries.size(), block = 1u << 16;
+    const size_t nq_fmt = queries.size(), block = 1u << 16;
     unsigned hw = std::thread::hardware_concurrency();
     if (const char* e = getenv("DICEY_B200_THREADS")) hw = (unsigned)std::max(1, atoi(e));
     const size_t nthreads = std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 32));
-    for (size_t b0 = 0; b0 < nq_all; b0 += block) {
-      const size_t b1 = std::min(nq_all, b0 + block), n = b1 - b0;
+    for (size_t b0 = 0; b0 < nq_fmt; b0 += block) {
+      const size_t b1 = std::min(nq_fmt, b0 + block), n = b1 - b0;
       const size_t nt = std::max<size_t>(1, std::min(nthreads, n / 64));   // a handful of queries: no threads
       std::vector<std::string> part(nt);
       auto work = [&](size_t t) {
@@ -351,22 +461,14 @@ int hunter(int argc, char** argv) {
       for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t);
       work(0);
       for (auto& x : th) x.join();
-      if (nt == 1) {
-        emit(c, part[0]);
-      } else {
-        std::string all;
-        size_t total = 0;
-        for (const auto& x : part) total += x.size();
-        all.reserve(total);
-        for (const auto& x : part) all += x;
-        emit(c, all);
-      }
+      for (size_t t = 0; t < nt; ++t) emit(c, part[t]);   // (one gzip member per part: the bytes a reader sees are the same)
     }
   }
-  stage("sort + JSON + write", nh);
-  if (res) dg_result_free(res);
-  dg_index_close(ix);
-  return 0;
+  uint64_t nh_all = 0;
+  for (auto& s : shards) nh_all += s.nh;
+  stage("sort + JSON + write", nh_all);
+  close_all();
+  return g_write_failed ? 1 : 0;
 }
 
 
@@ -894,7 +996,7 @@ bool fm9_loadable(const std::string& path) {
   // opening it on the device is the same test
   uint64_t sz = 0;
   if (!is_regular_file(path, &sz) || !is_regular_file(path + "_check")) return false;
-  return true;
+  return dg_fm9_check(path.c_str()) == DG_OK;   // a truncated, corrupt or foreign-type file is rebuilt (index.h:94-95)
 }
 
 int index_cmd(int argc, char** argv) {

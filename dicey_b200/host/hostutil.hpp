@@ -233,7 +233,12 @@ class GzLines {  // std::getline over a gzip or plain file
 inline bool gz_append(const std::string& path, const std::string& data) {
   gzFile f = gzopen(path.c_str(), "ab");
   if (!f) return false;
-  bool ok = data.empty() || gzwrite(f, data.data(), (unsigned)data.size()) == (int)data.size();
+  bool ok = true;
+  for (size_t at = 0; ok && at < data.size();) {   // gzwrite takes an unsigned length and returns an int
+    const size_t n = data.size() - at < (1u << 30) ? data.size() - at : (1u << 30);
+    ok = gzwrite(f, data.data() + at, (unsigned)n) == (int)n;
+    at += n;
+  }
   return gzclose(f) == Z_OK && ok;
 }
 

@@ -128,6 +128,11 @@ typedef struct {
  * device layout (DESIGN.md "Data layout in HBM").  device >= 0 selects the CUDA device.  */
 int dg_index_open(const char* fm9_path, int device, dg_index** out);
 
+/* What load_from_checked_file (index.h:94, SDSL io.hpp:917-936) tests before `dicey index` keeps an
+ * existing file: the .fm9_check sidecar holds the csa_wt<> type hash and the file parses to its end.
+ * Host only (no device is touched).  DG_OK, or DG_ERR_IO / DG_ERR_FORMAT with the reason.      */
+int dg_fm9_check(const char* fm9_path);
+
 /* index.h:96-123 (dump -> construct) for a text already in dump format (records upper-cased,
  * joined by '\n', trailing '\n'; no sentinel): suffix array, BWT and device layout are built
  * on the GPU.  Alphabet: at most 7 distinct byte values besides the sentinel.              */

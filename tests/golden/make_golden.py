@@ -296,5 +296,49 @@ def make_thal_long():
     open(os.path.join(HERE, "thal_long.out.tsv"), "w").write(out)
 
 
+def make_truncation_cases():
+    """hunt cases in which the reference truncates its neighbourhood at -x (neighbors.h:50, warning of
+    hunter.h:342-345): small caps in both modes, and 24-26-mers at edit distance 2 under the default cap.
+    Uses the committed t1m / stress indexes; own random stream, so the other cases do not move."""
+    rng = random.Random(777)
+    t1m, rec1 = os.path.join(HERE, "t1m.fm9"), os.path.join(HERE, "t1m.rec.tsv")
+    sfm, rec2 = os.path.join(HERE, "stress.fm9"), os.path.join(HERE, "stress.rec.tsv")
+
+    def planted(m, d, indel, i):
+        return synth.primers(42, 8, 125000, 1, m, d, indel, rng_seed=7000 + i, planted_frac=1.0)[0].decode()
+
+    qs = [(f"p{i}", planted(rng.choice([18, 20, 20, 22]), 1, True, i)) for i in range(14)]
+    qs.append(("withn", qs[0][1][:5] + "N" + qs[0][1][6:]))
+    qs.append(("polyA", "A" * 20))
+    hunt_case("t1m_e1_x50", t1m, rec1, qs, ["-d", "1", "-x", "50"])
+    hunt_case("t1m_e1_x150", t1m, rec1, qs, ["-d", "1", "-x", "150"])
+    hunt_case("t1m_e1_m0", t1m, rec1, qs[:6], ["-d", "1", "-m", "0"])
+    hunt_case("t1m_h2_x300", t1m, rec1, qs, ["-d", "2", "-n", "-x", "300"])
+    hunt_case("t1m_h1_x40", t1m, rec1, qs, ["-d", "1", "-n", "-x", "40", "-f"])
+    q2 = [(f"e{i}", planted(rng.choice([18, 20, 21, 22]), 2, True, 100 + i)) for i in range(10)]
+    hunt_case("t1m_e2_x500", t1m, rec1, q2, ["-d", "2", "-x", "500"])
+    hunt_case("t1m_e2_x5000", t1m, rec1, q2, ["-d", "2", "-x", "5000"])
+    q3 = [(f"l{i}", planted(m, 2, True, 200 + i)) for i, m in enumerate([24, 24, 25, 25, 26, 23, 22, 28])]
+    hunt_case("t1m_e2_long", t1m, rec1, q3, ["-d", "2"])
+    recs = gzip.open(os.path.join(HERE, "stress.dump.gz"), "rt").read().split("\n")
+    sq = []
+    for i in range(10):
+        r = recs[i % 3]
+        m = rng.choice([20, 22, 24, 25])
+        p0 = rng.randrange(0, len(r) - m)
+        sq.append((f"s{i}", r[p0:p0 + m]))
+    hunt_case("stress_e2_x2000", sfm, rec2, sq, ["-d", "2", "-x", "2000", "-m", "200"])
+    # the truncated sets themselves (unit-level vectors for the replay of dicey_b200/csrc/nbr_trunc.hpp)
+    nf = os.path.join(HERE, "neighbors.queries.txt")
+    for d, ham, x in ((1, False, 50), (2, False, 500), (2, False, 3000), (2, True, 300), (1, True, 20)):
+        tag = f"{'h' if ham else 'e'}{d}_x{x}"
+        with gzip.GzipFile(os.path.join(HERE, f"neighbors_{tag}.txt.gz"), "wb", mtime=0) as f:
+            f.write(run(["neighbors", nf, "-d", str(d), "-x", str(x)] + (["-n"] if ham else [])).encode())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "trunc":
+        make_truncation_cases()
+    else:
+        main()
+        make_truncation_cases()

@@ -2,6 +2,7 @@
 // dicey_b200/csrc/dg_core.cuh with g++ so that the script enumeration, the antichain rule and
 // the NW traceback can be checked against the reference on a box without a GPU.  Nothing here
 // is linked into the product library.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -12,6 +13,7 @@
 #include <pthread.h>
 #include <thread>
 #include "../../dicey_b200/csrc/dg_core.cuh"
+#include "../../dicey_b200/csrc/nbr_trunc.hpp"
 #include "../../dicey_b200/csrc/fm9.hpp"
 #include "../../dicey_b200/csrc/fm9_select.hpp"
 #include "../../dicey_b200/csrc/dg_thal.cuh"
@@ -138,6 +140,79 @@ int main(int argc, char** argv) {
       std::cout << "Q\t" << q << '\t' << st.size() << '\n';
       for (auto const& s : st) std::cout << s << '\n';
     }
+    return 0;
+  }
+  if (cmd == "replay" && argc >= 6) {
+    // the reference's generation order replayed (nbr_trunc.hpp): sets as `dicey_ref neighbors -x` prints them
+    std::ifstream f(argv[2]);
+    int d = atoi(argv[3]);
+    bool indel = atoi(argv[4]) != 0;
+    uint32_t x = (uint32_t)strtoul(argv[5], nullptr, 10);
+    std::string q;
+    NeighborReplay nr;
+    while (std::getline(f, q)) {
+      if (q.empty()) continue;
+      nr.run(q, d, indel, x);
+      std::vector<std::string> v = nr.strings();
+      std::sort(v.begin(), v.end());
+      std::cout << "Q\t" << q << '\t' << v.size() << '\n';
+      for (auto const& s : v) std::cout << s << '\n';
+    }
+    return 0;
+  }
+  if (cmd == "nbrbound" && argc >= 4) {
+    // nbr_upper_bound_part (the certificate that a neighbourhood stays under the cap) must never fall
+    // below the number of distinct strings the scripts spell: random and low-complexity queries,
+    // with and without N, d = 1 and 2.  argv[2] = number of queries, argv[3] = seed
+    int nq = atoi(argv[2]);
+    uint64_t x = strtoull(argv[3], nullptr, 10) * 2654435761ULL + 12345;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    double worst = 0, sum20 = 0; int n20 = 0; uint32_t max20 = 0;
+    for (int i = 0; i < nq; ++i) {
+      int m = 10 + (int)(rnd() % 13);
+      if (i % 3 == 0) m = 20;
+      int sigma = 1 + (int)(rnd() % 4);
+      if (i % 2) sigma = 4;
+      std::string q;
+      for (int j = 0; j < m; ++j) q.push_back("ACGT"[rnd() % sigma]);
+      if (i % 7 == 0) q[rnd() % m] = 'N';
+      if (i % 11 == 0) for (int j = 1; j < m; ++j) if (rnd() % 2) q[j] = q[j - 1];   // long runs
+      for (int d = 1; d <= 2; ++d) {
+        // distinct strings, by enumeration
+        std::set<std::string> all;
+        const uint8_t* base = (const uint8_t*)q.data();
+        std::vector<uint8_t> buf(m + 8);
+        Script sc; sc.nev = 0; sc.pos[0] = sc.pos[1] = sc.k[0] = sc.k[1] = 0;
+        all.insert(q);
+        const int E = 9 * m;
+        for (int e1 = 0; e1 < E; ++e1) {
+          int p1, k1;
+          if (!decode_event(base, m, true, e1, p1, k1)) continue;
+          sc.nev = 1; sc.pos[0] = p1; sc.k[0] = k1;
+          all.insert(std::string((char*)buf.data(), script_ltr(base, m, sc, buf.data())));
+          if (d >= 2)
+            for (int e2 = second_event_start(p1, k1, true); e2 < E; ++e2) {
+              int p2, k2;
+              if (!decode_event(base, m, true, e2, p2, k2) || !pair_ok(p1, k1, p2)) continue;
+              sc.nev = 2; sc.pos[1] = p2; sc.k[1] = k2;
+              all.insert(std::string((char*)buf.data(), script_ltr(base, m, sc, buf.data())));
+            }
+          sc.nev = 0;
+        }
+        auto bq = [&](int j) { return base_code(base[j]); };
+        uint32_t U = 1 + nbr_upper_bound_part(bq, m, d, 0, E, 1);
+        // the same split over 32 "lanes" must add up
+        uint32_t U2 = 1;
+        for (int lane = 0; lane < 32; ++lane) U2 += nbr_upper_bound_part(bq, m, d, lane, E, 32);
+        if (U != U2) { fprintf(stderr, "lane split mismatch\n"); return 3; }
+        if (U < all.size()) { fprintf(stderr, "UNSOUND: %s d=%d bound %u < distinct %zu\n", q.c_str(), d, U, all.size()); return 3; }
+        double r = (double)U / (double)all.size();
+        if (r > worst) worst = r;
+        if (m == 20 && d == 2 && q.find('N') == std::string::npos) { sum20 += U; ++n20; if (U > max20) max20 = U; }
+      }
+    }
+    printf("bound >= distinct on %d queries; worst bound/distinct %.3f; 20-mers at d=2: mean bound %.0f, max %u\n", nq, worst,
+           n20 ? sum20 / n20 : 0.0, max20);
     return 0;
   }
   if (cmd == "needle" && argc >= 3) {

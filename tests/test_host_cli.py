@@ -92,8 +92,6 @@ def test_hunt_cli_matches_reference_json(tmp_path, case, index):
     got = r.stdout.splitlines(keepends=True)
     assert len(got) == len(want) == len(qs)
     for q, (g, w) in enumerate(zip(got, want)):
-        if "Neighborhood size exceeds" in w:
-            continue  # the reference truncated its neighbourhood (Limits)
         assert g == w, (case, q)
 
 
@@ -124,8 +122,6 @@ def test_hunt_cli_many_queries_threaded_output(tmp_path, case, index):
     assert len(got) == reps * len(qs)
     for q, g in enumerate(got):
         w = want1[q % len(qs)]
-        if "Neighborhood size exceeds" in w:
-            continue
         assert g == w, (case, q)
     r = run(["hunt", "-g", "genome.fa.gz"] + flags + ["-o", "out.json.gz", "q.fa"], cwd=d)
     assert r.returncode == 0 and r.stdout == ""

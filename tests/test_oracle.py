@@ -23,7 +23,8 @@ def run(binary, args):
     return subprocess.run([binary] + args, check=True, capture_output=True, text=True, cwd=GOLDEN).stdout
 
 
-FAST_HUNT = ["cfg1_d0", "t1m_e1", "t1m_h1", "t1m_e0", "t1m_e1_fwd", "stress_e1", "stress_h1", "stress_e1_m7", "stress_h2_m50", "t1m_h2"]
+FAST_HUNT = ["cfg1_d0", "t1m_e1", "t1m_h1", "t1m_e0", "t1m_e1_fwd", "stress_e1", "stress_h1", "stress_e1_m7", "stress_h2_m50", "t1m_h2",
+             "t1m_e1_x50", "t1m_e1_x150", "t1m_h2_x300", "t1m_h1_x40", "t1m_e2_x500"]
 
 
 @pytest.mark.parametrize("case", FAST_HUNT)
@@ -62,6 +63,23 @@ def test_kernel_scripts_reproduce_neighbor_sets(tag, d, indel):
     the packed 2-bit fast path is cross-checked against the byte path inside hostsim."""
     want = gzip.open(os.path.join(GOLDEN, f"neighbors_{tag}.txt.gz"), "rt").read()
     assert run(HOSTSIM, ["neighbors", "neighbors.queries.txt", str(d), str(indel)]) == want
+
+
+@pytest.mark.parametrize("tag,d,indel,x", [("e1_x50", 1, 1, 50), ("e2_x500", 2, 1, 500), ("e2_x3000", 2, 1, 3000),
+                                          ("h2_x300", 2, 0, 300), ("h1_x20", 1, 0, 20), ("e1", 1, 1, 1000000), ("h2", 2, 0, 1000000)])
+def test_replay_reproduces_truncated_neighbor_sets(tag, d, indel, x):
+    """nbr_trunc.hpp (the host replay behind DG_Q_NBR_CAP) == the sets neighbors() leaves when the cap -x
+    stops its search (neighbors.h:50), and the untruncated ones."""
+    want = gzip.open(os.path.join(GOLDEN, f"neighbors_{tag}.txt.gz"), "rt").read()
+    assert run(HOSTSIM, ["replay", "neighbors.queries.txt", str(d), str(indel), str(x)]) == want
+
+
+def test_neighborhood_bound_is_sound():
+    """nbr_upper_bound_part (the device-side certificate that the cap cannot be reached) never falls
+    below the number of distinct strings, and certifies 20-mers at edit distance 2 under the default cap."""
+    out = run(HOSTSIM, ["nbrbound", "400", "3"])
+    assert out.startswith("bound >= distinct on 400 queries")
+    assert int(out.rsplit("max ", 1)[1]) < 10000
 
 
 def test_kernel_needle_reproduces_alignments():

@@ -74,6 +74,9 @@ HUNT_CASES = [
     ("cfg1_d0", "t1m"), ("t1m_e1", "t1m"), ("t1m_h1", "t1m"), ("t1m_h2", "t1m"), ("t1m_e2", "t1m"),
     ("t1m_e1_fwd", "t1m"), ("t1m_e0", "t1m"), ("stress_e1", "stress"), ("stress_h1", "stress"),
     ("stress_e1_m7", "stress"), ("stress_h2_m50", "stress"), ("stress_e2", "stress"),
+    # the reference truncates the neighbourhood at -x (neighbors.h:50) in these
+    ("t1m_e1_x50", "t1m"), ("t1m_e1_x150", "t1m"), ("t1m_h2_x300", "t1m"), ("t1m_h1_x40", "t1m"), ("t1m_e2_x500", "t1m"),
+    ("t1m_e2_x5000", "t1m"), ("t1m_e2_long", "t1m"), ("stress_e2_x2000", "stress"), ("t1m_e1_m0", "t1m"),
 ]
 
 
