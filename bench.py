@@ -332,6 +332,8 @@ def main_b200(args):
     comm = shard.comm_from_process_group(ix) if world > 1 else None
     dog.mark("communicator up")
     qbase = rank * nq
+    if comm is not None:
+        comm.set_query_base(qbase)     # peer mode: the producing kernels store global query ids into every rank's table
     gathered = [0]
 
     def resident_step(batch):

@@ -69,7 +69,7 @@ EXPORTS = [
     "dg_result_free", "dg_hits_sort", "dg_result_pack", "dg_result_unpack", "dg_profile_enable",
     "dg_profile_get", "dg_last_error", "dg_version",
     "dg_comm_get_unique_id", "dg_comm_init", "dg_comm_init_host", "dg_comm_rank", "dg_comm_size", "dg_comm_destroy",
-    "dg_allgather_hits", "dg_comm_fetch_table", "dg_allgather_result",
+    "dg_allgather_hits", "dg_comm_fetch_table", "dg_allgather_result", "dg_comm_set_query_base",
     "dg_fm9_check", "dg_result_records", "dg_result_alignment", "dg_rec_alignment", "dg_recs_sort", "dg_result_transfer_bytes",
 ]
 
@@ -161,6 +161,7 @@ def library() -> C.CDLL:
     lib.dg_comm_destroy.restype = None
     lib.dg_allgather_hits.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p, C.POINTER(vp)]
     lib.dg_comm_fetch_table.argtypes = [vp, vp, C.c_uint64, u64p]
+    lib.dg_comm_set_query_base.argtypes = [vp, C.c_uint64]
     lib.dg_allgather_result.argtypes = [vp, vp, C.POINTER(vp)]
     _lib = lib
     return lib
@@ -567,6 +568,10 @@ class Comm:
         h = C.c_void_p()
         _check(library().dg_comm_init_host(nranks, rank, fn, None, C.byref(h)))
         return cls(h.value, nranks, rank, keep=fn)
+
+    def set_query_base(self, query_base: int) -> None:
+        """Peer mode: the global index of this rank's first query, set before the records are produced."""
+        _check(library().dg_comm_set_query_base(self._h, query_base))
 
     def allgather_hits(self, batch: "Batch | None" = None, query_base: int = 0):
         """The exchange step on device memory: (device address of the slot table, records per slot,

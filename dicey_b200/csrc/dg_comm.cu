@@ -6,6 +6,7 @@
 //          program finds the system one), so the library has no link-time dependency on it.
 //   host   a caller-supplied all-gather of host buffers (gloo in the CPU tests, MPI, ...).
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstring>
@@ -100,6 +101,15 @@ __global__ void k_compact_table(const int4* __restrict__ table, uint64_t slot_re
     out[off[r] + i] = table[(uint64_t)r * slot_records + kSlotHeader + i];
 }
 
+// peer mode: this rank's hit count into the header of its slot on every rank
+struct PeerHeads { int4* head[kMaxPeers]; uint32_t nranks; };
+__global__ void k_peer_header(PeerHeads h, uint64_t n, uint64_t* __restrict__ token) {
+  const uint32_t r = threadIdx.x;
+  if (r < h.nranks) h.head[r][0] = make_int4((int)(uint32_t)n, (int)(uint32_t)(n >> 32), 0x64676831, 0);
+  if (r == 0) token[0] = n;
+  __threadfence_system();
+}
+
 }  // namespace
 
 struct dg_comm {
@@ -112,8 +122,20 @@ struct dg_comm {
   DevBuf<uint64_t> d_counts;     // nranks + (nranks + 1) offsets
   uint64_t slot_records = 0;     // records per slot, header included; identical on every rank
   uint64_t last_slot = 0;        // slot size the table currently holds (slot_records may already have grown)
+  const int4* last_table = nullptr;
   uint64_t* h_counts = nullptr;  // pinned, nranks entries
   DevBuf<uint8_t> stage_send, stage_recv;   // dg_allgather_result over NCCL
+  // peer mode: every rank's table (two of them, used alternately) is mapped on every rank
+  bool p2p = false;
+  uint64_t p2p_slot = 0;                    // records per slot, header included (fixed at init)
+  DevBuf<int4> ptable[2];                   // this rank's tables
+  int4* peer_tab[2][kMaxPeers] = {};        // rank r's tables as seen from this rank
+  std::vector<void*> ipc_opened;
+  uint64_t epoch = 0;                       // exchanges done; the next one uses table epoch & 1
+  const void* writer = nullptr;             // who wrote peer records for the coming exchange, with which base
+  uint64_t writer_epoch = ~0ull;
+  uint32_t query_base = 0;
+  DevBuf<uint64_t> d_token;                 // send / recv of the barrier all-gather
   // host transport
   dg_host_allgather_fn fn = nullptr;
   void* fn_ctx = nullptr;
@@ -141,7 +163,27 @@ struct dg_comm {
   }
 };
 
+bool dg::comm_peer_out(dg_index* idx, const void* producer, PeerOut* out) {
+  dg_comm* c = idx ? idx->bound_comm : nullptr;
+  out->nranks = 0;
+  if (!c || !c->p2p) return false;
+  const int t = (int)(c->epoch & 1);
+  for (int r = 0; r < c->nranks; ++r) out->tab[r] = c->peer_tab[t][r] + c->p2p_slot * (uint64_t)c->rank + kSlotHeader;
+  out->nranks = (uint32_t)c->nranks;
+  out->query_base = c->query_base;
+  out->cap = c->p2p_slot - kSlotHeader;
+  c->writer = producer;
+  c->writer_epoch = c->epoch;
+  return true;
+}
+
 extern "C" {
+
+int dg_comm_set_query_base(dg_comm* c, uint64_t query_base) {
+  if (!c) { set_error("null argument"); return DG_ERR_ARG; }
+  c->query_base = (uint32_t)query_base;
+  return DG_OK;
+}
 
 int dg_comm_get_unique_id(void* id) {
   if (!id) { set_error("null argument"); return DG_ERR_ARG; }
@@ -171,6 +213,62 @@ int dg_comm_init(int nranks, int rank, const void* id, dg_index* idx, dg_comm** 
     c->d_counts.alloc(2 * (size_t)nranks + 1);
     c->slot_records = 1ull << 20;   // 16 MB per rank to start with; grows in step on every rank
     if (const char* e = getenv("DG_COMM_SLOT")) c->slot_records = std::max<uint64_t>(2, strtoull(e, nullptr, 10));
+    c->d_token.alloc(1 + (size_t)nranks);
+    idx->bound_comm = c;
+    // ---- peer mode: map every rank's tables on every rank (cudaIpc between processes, peer access
+    // between the threads of one process).  Any rank that cannot makes all of them stay with NCCL.
+    const char* pe = getenv("DG_COMM_P2P");
+    bool want = nranks <= kMaxPeers && !(pe && atoi(pe) == 0);
+    struct Card { cudaIpcMemHandle_t h[2]; uint64_t ptr[2]; int64_t pid; int32_t dev; int32_t ok; };
+    Card mine;
+    memset(&mine, 0, sizeof(mine));
+    c->p2p_slot = 3ull << 20;       // 3 M record places per rank and table (48 MB); DG_COMM_P2P_SLOT
+    if (const char* e = getenv("DG_COMM_P2P_SLOT")) c->p2p_slot = std::max<uint64_t>(2, strtoull(e, nullptr, 10));
+    if (want) {
+      for (int t = 0; t < 2 && want; ++t) {
+        if (cudaMalloc((void**)&c->ptable[t].p, c->p2p_slot * (uint64_t)nranks * sizeof(int4)) != cudaSuccess) { cudaGetLastError(); want = false; break; }
+        c->ptable[t].count = c->p2p_slot * (uint64_t)nranks;
+        cudaMemset(c->ptable[t].p, 0, c->ptable[t].bytes());
+        if (cudaIpcGetMemHandle(&mine.h[t], c->ptable[t].p) != cudaSuccess) { cudaGetLastError(); want = false; }
+        mine.ptr[t] = (uint64_t)(uintptr_t)c->ptable[t].p;
+      }
+    }
+    mine.pid = (int64_t)getpid();
+    mine.dev = idx->device;
+    mine.ok = want ? 1 : 0;
+    std::vector<Card> cards((size_t)nranks);
+    int rc2 = c->allgather_host_bytes(&mine, cards.data(), sizeof(Card));
+    if (rc2) { idx->bound_comm = nullptr; delete c; return rc2; }
+    bool all_ok = true;
+    for (auto& k : cards) all_ok = all_ok && k.ok;
+    int32_t mapped = all_ok ? 1 : 0;
+    if (all_ok) {
+      for (int r = 0; r < nranks && mapped; ++r) {
+        for (int t = 0; t < 2 && mapped; ++t) {
+          if (r == rank) { c->peer_tab[t][r] = c->ptable[t].p; continue; }
+          if (cards[r].pid == mine.pid) {   // another thread of this process: plain peer access
+            if (t == 0 && cards[r].dev != idx->device) {
+              cudaError_t e = cudaDeviceEnablePeerAccess(cards[r].dev, 0);
+              if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) mapped = 0;
+              cudaGetLastError();
+            }
+            c->peer_tab[t][r] = (int4*)(uintptr_t)cards[r].ptr[t];
+          } else {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, cards[r].h[t], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = 0; break; }
+            c->ipc_opened.push_back(p);
+            c->peer_tab[t][r] = (int4*)p;
+          }
+        }
+      }
+    }
+    std::vector<int32_t> flags((size_t)nranks, 0);
+    rc2 = c->allgather_host_bytes(&mapped, flags.data(), sizeof(int32_t));
+    if (rc2) { idx->bound_comm = nullptr; delete c; return rc2; }
+    c->p2p = true;
+    for (int32_t f : flags) c->p2p = c->p2p && f;
+    if (!c->p2p) { c->ptable[0].release(); c->ptable[1].release(); }
+    if (getenv("DG_TRACE")) fprintf(stderr, "[dg_comm] rank %d of %d: %s\n", rank, nranks, c->p2p ? "peer mode (records stored into every rank's table by the producing kernel)" : "NCCL all-gather of the records");
     *out = c;
     return DG_OK;
   } catch (CudaFail& e) {
@@ -196,6 +294,8 @@ void dg_comm_destroy(dg_comm* c) {
     cudaSetDevice(c->idx->device);
     cudaStreamSynchronize(c->idx->stream);
   }
+  if (c->idx && c->idx->bound_comm == c) c->idx->bound_comm = nullptr;
+  for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   if (c->nc) nccl()->CommDestroy(c->nc);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   delete c;
@@ -220,6 +320,34 @@ int dg_allgather_hits(dg_comm* c, dg_batch* b, uint64_t query_base, const dg_wir
       wire = idx->wire.p;
       n = idx->wire_n;
     }
+    // peer mode: the producing kernel already stored this rank's records into every rank's table; what is
+    // left is the count in the slot headers and one small all-gather that doubles as the barrier (NCCL
+    // orders it after every rank's producing kernels: they precede it on each rank's stream)
+    const void* producer = b ? (const void*)b : (const void*)idx;
+    if (c->p2p && c->writer == producer && c->writer_epoch == c->epoch && c->query_base == (uint32_t)query_base) {
+      const int t = (int)(c->epoch & 1);
+      PeerHeads ph;
+      ph.nranks = (uint32_t)c->nranks;
+      for (int r = 0; r < c->nranks; ++r) ph.head[r] = c->peer_tab[t][r] + c->p2p_slot * (uint64_t)c->rank;
+      k_peer_header<<<1, 32, 0, st>>>(ph, n, c->d_token.p);
+      int rc = nccl()->AllGather(c->d_token.p, c->d_token.p + 1, sizeof(uint64_t), kNcclInt8, c->nc, st);
+      if (rc) return nccl_fail("ncclAllGather", rc);
+      DG_CUDA(cudaMemcpyAsync(c->h_counts, c->d_token.p + 1, sizeof(uint64_t) * (size_t)c->nranks, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(cudaStreamSynchronize(st));
+      DG_CUDA(cudaGetLastError());
+      ++c->epoch;
+      uint64_t mx = 0;
+      for (int r = 0; r < c->nranks; ++r) mx = std::max(mx, c->h_counts[r]);
+      if (mx <= c->p2p_slot - kSlotHeader) {
+        c->last_slot = c->p2p_slot;
+        c->last_table = c->ptable[t].p;
+        *table = reinterpret_cast<const dg_wire*>(c->ptable[t].p);
+        *slot_records = c->p2p_slot;
+        *counts = c->h_counts;
+        return DG_OK;
+      }
+      // a rank holds more hits than a slot: every rank sees that and repeats the exchange through NCCL
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
       const uint64_t slot = c->slot_records;
       if (c->table.count < slot * (uint64_t)c->nranks) c->table.alloc(slot * (uint64_t)c->nranks);
@@ -243,6 +371,7 @@ int dg_allgather_hits(dg_comm* c, dg_batch* b, uint64_t query_base, const dg_wir
       }
       if (fits) {
         c->last_slot = slot;
+        c->last_table = c->table.p;
         *table = reinterpret_cast<const dg_wire*>(c->table.p);
         *slot_records = slot;
         *counts = c->h_counts;
@@ -272,7 +401,7 @@ int dg_comm_fetch_table(dg_comm* c, dg_wire* out, uint64_t capacity, uint64_t* n
     uint64_t* d_off = c->d_counts.p + c->nranks;
     DG_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(uint64_t) * off.size(), cudaMemcpyHostToDevice, st));
     dim3 grid((unsigned)std::min<uint64_t>(1024, (mx + 255) / 256 + 1), (unsigned)c->nranks);
-    k_compact_table<<<grid, 256, 0, st>>>(c->table.p, c->last_slot, d_off, c->nranks, c->compact.p);
+    k_compact_table<<<grid, 256, 0, st>>>(c->last_table, c->last_slot, d_off, c->nranks, c->compact.p);
     DG_CUDA(cudaMemcpyAsync(out, c->compact.p, *n * sizeof(int4), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
     return DG_OK;

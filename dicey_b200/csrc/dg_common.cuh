@@ -51,6 +51,18 @@ struct DevBuf {
   size_t bytes() const { return count * sizeof(T); }
 };
 
+// Where the 16-byte wire records of this rank go on EVERY GPU of a communicator whose tables are
+// mapped into each other's address space (dg_comm.cu, peer mode): k_verify / k_rebase_recs store each
+// record straight into the tables of all ranks over NVLink, so the exchange step that follows is a
+// barrier, not a transfer.
+constexpr int kMaxPeers = 16;
+struct PeerOut {
+  int4* tab[kMaxPeers];    // this rank's record area (header excluded) in the table of rank r
+  uint32_t nranks;         // 0 = peer mode off
+  uint32_t query_base;     // added to the query index of every record
+  uint64_t cap;            // record places per rank
+};
+
 // Unit tables of one (distance, mode, set of query lengths): built once per index and shared by
 // every batch of that shape (script_ub[256] | tab_off[512] | tab_cnt[512] | tab[...] in one block).
 struct TabEntry {
@@ -98,6 +110,7 @@ struct dg_index {
   std::vector<uint32_t> h_Cb;      // host copies for the .fm9 writer / info
   std::vector<uint8_t> h_present;
   dg::ProfileState prof;
+  struct dg_comm* bound_comm = nullptr;   // the communicator bound to this index (dg_comm_init), if any
   std::mutex tab_mu;
   std::map<std::string, std::shared_ptr<dg::TabEntry>> tab_cache;
 
@@ -127,4 +140,7 @@ int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, d
 int write_fm9(dg_index* idx, const char* path);
 // dg_search.cu
 void release_stream_pools(const cudaStream_t* streams, int n);
+// dg_comm.cu: peer-mode destination of the records `producer` (a batch, or the index for dg_hunt_batch)
+// is about to write; false = peer mode off (the records are all-gathered by NCCL afterwards)
+bool comm_peer_out(dg_index* idx, const void* producer, PeerOut* out);
 }  // namespace dg

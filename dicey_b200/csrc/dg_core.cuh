@@ -430,6 +430,78 @@ DG_HD bool is_minimal_small(const Packed4& q, int m, int d, const Packed4& t, in
   return true;
 }
 
+// The same decision with ONE pass over the query instead of one DP per substring: a semi-global form
+// of the recurrence above in which the substring may start anywhere in t (row 0 costs nothing at
+// any column), so that cell (m, j) holds the smallest distance over all substrings ending at j.
+// t is non-minimal iff some substring ending before its last character is within d (v0: any start),
+// or one ending at the last character that does not start at the first (v1: row 0 is open from
+// column 1 on only).  Only cells with -d <= j - i <= 3 d can stay within d (a substring of length
+// >= m - d starts at most 2 d characters into t), a band of 4 d + 1 cells.
+constexpr int kWideBand = 4 * kMaxDist + 1;
+DG_HD bool is_minimal_band(const Packed4& q, int m, int d, const Packed4& t, int L) {
+  const int INF = 100;
+  if (L < m - d + 1) return true;          // no proper substring is long enough
+  const int W = 4 * d + 1;                 // k = j - i + d
+  int v0[kWideBand], v1[kWideBand];
+  // row 0: the empty prefix of q matches the empty substring at any start: cost 0 (insertions before
+  // q[0] are then never needed: starting later is cheaper)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kWideBand; ++k) {
+    const int j = k - d;
+    const bool in = k < W && j >= 0 && j <= L;
+    v0[k] = in ? 0 : INF;
+    v1[k] = (in && j >= 1) ? 0 : INF;
+  }
+  for (int i = 1; i <= m; ++i) {
+    const uint32_t qc = q.at(i - 1);
+    int best = INF;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < kWideBand; ++k) {
+      if (k < W) {
+        const int j = i + k - d;
+        int a0 = INF, a1 = INF;
+        if (j == 0) {
+          a0 = i;                          // i deletions, substring starting (and ending) at 0
+        } else if (j > 0 && j <= L) {
+          const uint32_t uc = t.at(j - 1);
+          const bool letter = uc <= 4u;
+          const int miss = (qc != uc) ? (letter ? 1 : INF) : 0;
+          const int up0 = (k + 1 < W ? v0[k + 1] : INF) + 1, up1 = (k + 1 < W ? v1[k + 1] : INF) + 1;   // D[i-1][j] + 1
+          const bool can_ins = k > 0 && i < m && letter;
+          a0 = v0[k] + miss;
+          if (up0 < a0) a0 = up0;
+          if (can_ins && v0[k - 1] + 1 < a0) a0 = v0[k - 1] + 1;   // D[i][j-1] + 1 (already row i)
+          a1 = v1[k] + miss;
+          if (up1 < a1) a1 = up1;
+          if (can_ins && v1[k - 1] + 1 < a1) a1 = v1[k - 1] + 1;
+          if (a0 > INF) a0 = INF;
+          if (a1 > INF) a1 = INF;
+        }
+        v0[k] = a0;
+        v1[k] = a1;
+        if (a0 < best) best = a0;
+      }
+    }
+    if (best > d) return true;             // (v1 >= v0 everywhere)
+  }
+  // row m: substrings ending at j = m + k - d
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kWideBand; ++k) {
+    if (k < W) {
+      const int j = m + k - d;
+      if (j >= 1 && j < L && v0[k] <= d) return false;
+      if (j == L && v1[k] <= d) return false;
+    }
+  }
+  return true;
+}
+
 // Distance 1 needs no DP at all: a string of G_1(q) of length m - 1 / m / m + 1 is q with one
 // deletion / substitution / insertion, so "some proper substring of t (length >= m - 1) is
 // generated" reduces to two predicates on packed strings, each a handful of shifts and XORs:
@@ -535,6 +607,40 @@ DG_HD uint32_t nbr_upper_bound_part(BaseAt bq, int m, int d, int e_lo, int e_hi,
     }
   }
   return n;
+}
+
+// The same count in closed form, O(m): per position p the valid events are nsub(p) substitutions
+// (3, or 4 at a non-ACGT base), one deletion and four insertions; of these the deletion is shiftable
+// inside a run and one insertion is when the preceding base is a letter.  With c(p) the events that
+// are not shiftable (ci / cdel: the insertions / deletion among them) and w(p) all of them:
+//   second event two or more bases to the right: rules A and B only         -> c(p1) * sum c(p2)
+//   second event at p1 + 1: after an insertion rule B still holds (c), after a substitution nothing
+//   applies (w), after a deletion rules C and F leave the deletion alone (1)
+//   second event at p1 (the first is an insertion): D drops the deletion, E the substitutions unless
+//   p1 is the last base, the four insertions stay.
+template <typename BaseAt>
+DG_HD uint32_t nbr_upper_bound_closed(BaseAt bq, int m, int d) {
+  if (d <= 0) return 1;
+  uint64_t total = 1, suffix = 0;      // suffix = sum of c(p2) over p2 >= p + 2 while walking p downwards
+  uint32_t c_next = 0, w_next = 0;     // c(p + 1), w(p + 1)
+  for (int p = m - 1; p >= 0; --p) {
+    const int b = bq(p), prev = p > 0 ? bq(p - 1) : -1;
+    const uint32_t nsub = b < 4 ? 3u : 4u;
+    const uint32_t cdel = (p > 0 && b == prev) ? 0u : 1u;
+    const uint32_t ci = (p > 0 && prev < 4) ? 3u : 4u;
+    const uint32_t c = nsub + cdel + ci, w = nsub + 5u;
+    total += c;
+    if (d >= 2) {
+      const bool last = p + 1 >= m;
+      total += (uint64_t)c * suffix;                                   // p2 >= p + 2
+      total += (uint64_t)ci * c_next + (uint64_t)nsub * w_next + (last ? 0u : cdel);   // p2 == p + 1
+      total += (uint64_t)ci * ((last ? nsub : 0u) + 4u);               // p2 == p
+    }
+    suffix += c_next;
+    c_next = c;
+    w_next = w;
+  }
+  return total > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)total;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -255,12 +255,11 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   if (!run || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
 }
 
-// One warp per query still flagged DG_Q_NBR_UNVERIFIED: the bound of dg_core.cuh (nbr_upper_bound_part)
+// One thread per query still flagged DG_Q_NBR_UNVERIFIED: the bound of dg_core.cuh (nbr_upper_bound_closed)
 // on the number of distinct strings neighbors() can generate, for both strands; below the cap the
 // flag goes (the reference cannot have truncated), otherwise the host replays the query exactly.
 __global__ void k_nbr_bound(BatchDev b) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t q = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= b.nq) return;
   const uint32_t st = b.status[q];
   if (!(st & DG_Q_NBR_UNVERIFIED)) return;
@@ -271,14 +270,10 @@ __global__ void k_nbr_bound(BatchDev b) {
     int m, koff;
     query_geom(b, q, strand, base, m, koff);
     auto bq = [&](int j) { return base_code(base[j]); };
-    uint32_t n = nbr_upper_bound_part(bq, m, d, (int)lane, 9 * m, 32);
-    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
-    if (1u + n >= b.max_nbr) ok = false;
+    if (nbr_upper_bound_closed(bq, m, d) >= b.max_nbr) ok = false;
   }
-  if (lane == 0) {
-    if (ok) b.status[q] = st & ~(uint32_t)DG_Q_NBR_UNVERIFIED;
-    else atomicOr(b.irregular, 4u);
-  }
+  if (ok) b.status[q] = st & ~(uint32_t)DG_Q_NBR_UNVERIFIED;
+  else atomicOr(b.irregular, 4u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -805,7 +800,7 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
       keep = true;
     } else {
       const Packed4 q4 = packed2_to_packed4(code0, m), t4 = packed2_to_packed4(code, L);
-      keep = (d == 1 && m >= 2) ? is_minimal_d1(q4, m, t4, L) : is_minimal_small(q4, m, d, t4, L);
+      keep = (d == 1 && m >= 2) ? is_minimal_d1(q4, m, t4, L) : is_minimal_band(q4, m, d, t4, L);
     }
   } else
   if (m + d <= 31) {
@@ -831,7 +826,7 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
       }
       if (out) emit(cls);
     }
-    keep = !indel || (d == 1 && m >= 2 ? is_minimal_d1(q4, m, t4, L) : is_minimal_small(q4, m, d, t4, L));
+    keep = !indel || (d == 1 && m >= 2 ? is_minimal_d1(q4, m, t4, L) : is_minimal_band(q4, m, d, t4, L));
   } else {
     uint8_t t[kMaxQuery + 8], s0[kMaxQuery + 8], s1[kMaxQuery + 8];
     int L = script_ltr(base, m, sc, t);
@@ -1011,7 +1006,19 @@ struct VerifyArgs {
   uint32_t trace_bytes, srow_ints;
   uint64_t first_hit;        // chunk start
   uint64_t chunk;            // hits in this launch
+  PeerOut peer;              // peer mode of a bound communicator: the wire record also goes to every rank's table
 };
+
+// one wire record into this rank's place in the table of every rank (NVLink stores; the fence orders
+// them before anything this thread -- and, at kernel end, this stream -- does next)
+__device__ __forceinline__ void peer_store(const PeerOut& po, uint64_t h, int4 w) {
+  if (!po.nranks) return;
+  if (h < po.cap) {
+    w.x = (int)((uint32_t)w.x + po.query_base);
+    for (uint32_t r = 0; r < po.nranks; ++r) po.tab[r][h] = w;
+  }
+  __threadfence_system();
+}
 
 constexpr int kLocalQ = 31;   // thread-local NW: query columns
 constexpr int kLocalG = 40;   // thread-local NW: genomic rows
@@ -1142,7 +1149,9 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     rec.nops = (uint8_t)(nop > kRecOps ? 255 : nop);
     rec.ops = ops | ((uint64_t)((delta + 8) & 15) << 60);
     a.recs[h] = rec;
-    a.wire[h] = make_int4((int)rec.query, (int)rec.chr, (int)rec.start, (int)(((uint32_t)score & 0xFFFFu) | ((uint32_t)rec.strand << 16)));
+    const int4 w = make_int4((int)rec.query, (int)rec.chr, (int)rec.start, (int)(((uint32_t)score & 0xFFFFu) | ((uint32_t)rec.strand << 16)));
+    a.wire[h] = w;
+    peer_store(a.peer, h, w);
     return;
   }
   // block-wide exclusive scan of `bytes`, one atomicAdd per block
@@ -1192,7 +1201,9 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     }
   }
   a.hits[h] = out;
-  a.wire[h] = make_int4((int)out.query, (int)out.chr, (int)out.start, (int)(((uint32_t)out.score & 0xFFFFu) | ((uint32_t)out.strand << 16)));
+  const int4 w = make_int4((int)out.query, (int)out.chr, (int)out.start, (int)(((uint32_t)out.score & 0xFFFFu) | ((uint32_t)out.strand << 16)));
+  a.wire[h] = w;
+  peer_store(a.peer, h, w);
 }
 
 __global__ void k_fill_offsets(uint64_t* __restrict__ off, uint64_t n, uint64_t len) {
@@ -1224,14 +1235,17 @@ __global__ void k_rebase(dg_hit* __restrict__ hits, uint64_t nhits, uint64_t* __
 }
 
 // the compact form of the same: query ids -> batch-global, wire record = the record's first 16 bytes
-__global__ void k_rebase_recs(dg_rec* __restrict__ recs, uint64_t nhits, uint32_t q0, int4* __restrict__ wire) {
+__global__ void k_rebase_recs(dg_rec* __restrict__ recs, uint64_t nhits, uint32_t q0, int4* __restrict__ wire, PeerOut peer,
+                              uint64_t hit_base) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nhits) return;
   const uint2* p = reinterpret_cast<const uint2*>(recs + i);   // (24-byte records: 8-byte aligned)
   const uint2 a = p[0], c = p[1];   // query, chr | start, score | strand << 16 | nops << 24
   const uint32_t q = a.x + q0;
   if (q0) recs[i].query = q;
-  if (wire) wire[i] = make_int4((int)q, (int)a.y, (int)c.x, (int)(c.y & 0x00FFFFFFu));
+  const int4 w = make_int4((int)q, (int)a.y, (int)c.x, (int)(c.y & 0x00FFFFFFu));
+  if (wire) wire[i] = w;
+  peer_store(peer, hit_base + i, w);
 }
 __global__ void k_pack_qmeta(const uint32_t* __restrict__ status, const uint32_t* __restrict__ dist, uint32_t nq,
                              uint16_t* __restrict__ out) {
@@ -1514,6 +1528,7 @@ struct dg_batch {
   ABuf<uint32_t> status, dist, irregular;
   std::shared_ptr<TabEntry> tabs;   // unit tables (cached in the index)
   bool maybe_capped = false;        // some query length could reach the cap -x: certify / replay after k_prepare
+  bool peer_from_verify = false;    // dg_batch_run of a staged batch: k_verify feeds a bound communicator's peer tables
   ABuf<uint32_t> trunc_qs, trunc_off;
   ABuf<ulonglong2> trunc_keys;
   uint32_t n_trunc = 0;
@@ -1892,7 +1907,7 @@ static int run_impl(dg_batch* b) {
     }
     if (b->maybe_capped && nq) {
       b->n_trunc = 0;
-      if (b->par.indel) { k_nbr_bound<<<grid_for(32ull * nq, B), B, 0, st>>>(bd); ++launches; }
+      if (b->par.indel) { k_nbr_bound<<<grid_for(nq, B), B, 0, st>>>(bd); ++launches; }
       const int rc_t = resolve_truncation(b, st);
       if (rc_t) return rc_t;
       bd = batch_dev(b);   // (picks the lists up)
@@ -2186,6 +2201,8 @@ static int run_impl(dg_batch* b) {
         VerifyArgs a;
         a.cands = cur; a.ncand = n; a.hit_off = hit_off.p; a.loc_off = loc_off.p; a.keys = keys2.p; a.key_base = row0; a.nhits = nhits;
         a.hits = b->hits.p; a.recs = b->recs.p; a.wire = b->wire.p; a.pool = b->pool.p; a.pool_cursor = cursor.p;
+        a.peer.nranks = 0;
+        if (b->peer_from_verify) comm_peer_out(ix, b, &a.peer);
         a.srow_ints = (uint32_t)(maxq + 2);
         a.trace_bytes = (uint32_t)(((maxg + 1) * (maxq + 1) + 3) / 4 + 4);
         a.scratch_stride = a.srow_ints * 4 + a.trace_bytes + 3 * (aln_max + 8);
@@ -2319,6 +2336,7 @@ int dg_batch_stage(dg_index* idx, const char* seqs, const uint64_t* offsets, uin
 }
 int dg_batch_run(dg_batch* b) {
   if (!b) { set_error("null batch"); return DG_ERR_ARG; }
+  b->peer_from_verify = true;
   return run_impl(b);
 }
 int dg_batch_fetch(dg_batch* b, dg_result** out) {
@@ -2371,6 +2389,7 @@ struct ChunkPipe {
   std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev, prepared_ev;   // per chunk, from the index's event pool
   uint32_t uploaded = 0;
   std::vector<uint64_t> chunk_len;   // per chunk: the common query length, or 0 (set before `uploaded` passes the chunk)
+  PeerOut peer;                      // peer mode of a bound communicator (compact results only)
   uint64_t hit_base = 0, pool_base = 0;
   int rc = DG_OK;
   std::string err;
@@ -2462,7 +2481,7 @@ struct ChunkPipe {
         }
         if (compact) {
           if (b->nhits)
-            k_rebase_recs<<<grid_for(b->nhits, 256), 256, 0, st>>>(b->recs.p, b->nhits, q0, idx->wire.p + hit_base);
+            k_rebase_recs<<<grid_for(b->nhits, 256), 256, 0, st>>>(b->recs.p, b->nhits, q0, idx->wire.p + hit_base, peer, hit_base);
         } else {
           k_rebase<<<grid_for(std::max<uint64_t>(b->nhits, (uint64_t)cn + 1), 256), 256, 0, st>>>(
               b->hits.p, b->nhits, b->qoff.p, cn + 1, q0, pool_base, hit_base, idx->wire.p + hit_base);
@@ -2564,7 +2583,9 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     r->nq = nq;
     r->cum = idx->h_cum;
     static const bool full_records = getenv("DG_FULL_RECORDS") != nullptr;
+    p.peer.nranks = 0;
     if (!params->seed_len && !full_records) {
+      comm_peer_out(idx, idx, &p.peer);
       r->qmeta.alloc((size_t)nq * 2, true);
     } else {
       r->qoff.alloc(((size_t)nq + 1) * 8, true);
@@ -2674,8 +2695,11 @@ int dg_hunt_batch(dg_index* idx, const char* seqs, const uint64_t* offsets, uint
   if (!rc) {
     try {
       if (b->nhits > idx->wire.count) idx->wire.alloc(b->nhits + (b->nhits >> 3) + 1024);
+      PeerOut peer;
+      peer.nranks = 0;
+      if (b->compact) comm_peer_out(idx, idx, &peer);
       if (b->nhits && b->compact)
-        k_rebase_recs<<<grid_for(b->nhits, 256), 256, 0, b->st>>>(b->recs.p, b->nhits, 0, idx->wire.p);
+        k_rebase_recs<<<grid_for(b->nhits, 256), 256, 0, b->st>>>(b->recs.p, b->nhits, 0, idx->wire.p, peer, 0);
       else if (b->nhits)
         k_rebase<<<grid_for(b->nhits, 256), 256, 0, b->st>>>(b->hits.p, b->nhits, b->qoff.p, 0, 0, 0, 0, idx->wire.p);
       idx->wire_n = b->nhits;

@@ -292,6 +292,15 @@ typedef struct {
  * communicator) is the number of hits of rank r; both stay valid until the next call.       */
 int dg_allgather_hits(dg_comm* c, dg_batch* b, uint64_t query_base, const dg_wire** table,
                       uint64_t* slot_records, const uint64_t** counts);
+/* Peer mode.  When every rank's tables could be mapped on every rank at dg_comm_init (cudaIpc between
+ * processes, peer access between threads; DG_COMM_P2P=0 turns it off), the kernels that PRODUCE the
+ * records (k_verify of a staged batch, the commit kernel of dg_hunt_batch) store each record straight
+ * into the tables of all ranks over NVLink while they run, and dg_allgather_hits shrinks to the slot
+ * headers plus one 8-byte ncclAllGather that doubles as the barrier.  The records carry the query
+ * base that was set BEFORE they were produced: call dg_comm_set_query_base first, then run / hunt,
+ * then dg_allgather_hits with the same base (any mismatch, or a rank with more hits than a slot
+ * holds, silently takes the NCCL path above).  Tables alternate between two buffers per exchange.  */
+int dg_comm_set_query_base(dg_comm* c, uint64_t query_base);
 /* Device -> host copy of the gathered records, compacted in rank order (sum of counts entries). */
 int dg_comm_fetch_table(dg_comm* c, dg_wire* out, uint64_t capacity, uint64_t* n);
 

@@ -72,6 +72,8 @@ static void neighbors(const std::string& q, int d, bool indel, std::set<std::str
     if (m + d <= 31) {  // the register-resident form used by k_cand_keys must agree on every string
       bool keep2 = is_minimal_small(pack4(base, m), m, d, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
       if (keep2 != keep) { fprintf(stderr, "is_minimal_small mismatch on %s / %s\n", q.c_str(), t.c_str()); exit(3); }
+      bool keep4 = is_minimal_band(pack4(base, m), m, d, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
+      if (keep4 != keep) { fprintf(stderr, "is_minimal_band mismatch on %s / %s (d %d): %d vs %d\n", q.c_str(), t.c_str(), d, (int)keep4, (int)keep); exit(3); }
       if (d == 1 && m >= 2) {
         bool keep3 = is_minimal_d1(pack4(base, m), m, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
         if (keep3 != keep) { fprintf(stderr, "is_minimal_d1 mismatch on %s / %s\n", q.c_str(), t.c_str()); exit(3); }
@@ -199,12 +201,23 @@ int main(int argc, char** argv) {
             }
           sc.nev = 0;
         }
+        if (i % 8 == 0 && m + d <= 31) {   // the one-pass antichain test against the per-substring DP, on every string
+          std::vector<uint8_t> s0(m + 8), s1(m + 8);
+          const Packed4 q4 = pack4(base, m);
+          for (auto const& t : all) {
+            const bool a = is_minimal(base, m, d, (const uint8_t*)t.data(), (int)t.size(), s0.data(), s1.data());
+            const bool b2 = is_minimal_band(q4, m, d, pack4((const uint8_t*)t.data(), (int)t.size()), (int)t.size());
+            if (a != b2) { fprintf(stderr, "is_minimal_band mismatch on %s / %s (d %d)\n", q.c_str(), t.c_str(), d); return 3; }
+          }
+        }
         auto bq = [&](int j) { return base_code(base[j]); };
         uint32_t U = 1 + nbr_upper_bound_part(bq, m, d, 0, E, 1);
         // the same split over 32 "lanes" must add up
         uint32_t U2 = 1;
         for (int lane = 0; lane < 32; ++lane) U2 += nbr_upper_bound_part(bq, m, d, lane, E, 32);
         if (U != U2) { fprintf(stderr, "lane split mismatch\n"); return 3; }
+        const uint32_t U3 = nbr_upper_bound_closed(bq, m, d);   // what the kernel evaluates
+        if (U3 != U) { fprintf(stderr, "closed form %u != enumeration %u on %s d=%d\n", U3, U, q.c_str(), d); return 3; }
         if (U < all.size()) { fprintf(stderr, "UNSOUND: %s d=%d bound %u < distinct %zu\n", q.c_str(), d, U, all.size()); return 3; }
         double r = (double)U / (double)all.size();
         if (r > worst) worst = r;

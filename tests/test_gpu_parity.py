@@ -304,6 +304,22 @@ def test_allgather_hits_nccl_world1(indexes, monkeypatch, chunk):
         assert slot2 == slot and int(counts2[0]) == len(r2.hits) == len(got2)
         assert np.array_equal(got2["query"], r2.hits["query"] + 7) and np.array_equal(got2["start"], r2.hits["start"])
         bt.free()
+        # peer mode (the records are stored into the table by the producing kernel): base set first
+        comm.set_query_base(31)
+        res3 = ix.hunt(pr[:3000], par)
+        _, _, counts3 = comm.allgather_hits(None, query_base=31)
+        got3 = comm.fetch_table()
+        assert int(counts3[0]) == len(res3.hits) == len(got3)
+        assert np.array_equal(got3["query"], res3.hits["query"] + 31) and np.array_equal(got3["start"], res3.hits["start"])
+        bt = ix.stage(pr[:900], par)
+        for _ in range(3):    # the two tables alternate
+            bt.run()
+            _, _, counts4 = comm.allgather_hits(bt, query_base=31)
+        r4 = bt.fetch()
+        got4 = comm.fetch_table()
+        assert int(counts4[0]) == len(r4.hits) == len(got4)
+        assert np.array_equal(got4["query"], r4.hits["query"] + 31) and np.array_equal(got4["chr"], r4.hits["chr"])
+        bt.free()
     finally:
         comm.close()
 
