@@ -471,11 +471,188 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
 //      K-mer table lookup on the last K bases + one backward-search step per remaining base.
 // The strings enumerated are exactly those of k_search for a clean query (neighbors.h:47-83).
 #ifndef DG_PACKED_MIN_BLOCKS
-#define DG_PACKED_MIN_BLOCKS 6
+#define DG_PACKED_MIN_BLOCKS 3
 #endif
+// What the kernel reads of the batch and of the index (the whole BatchDev / IndexView as parameters
+// costs registers the enumeration loop needs).
+struct PackedArgs {
+  const uint64_t* qcode;
+  const uint8_t* qflag;
+  const uint32_t* dist;
+  const uint64_t* off;
+  uint32_t nq, seed_len;
+  uint32_t reverse;
+  // presence windows by string length class: 0 = KB - 1, 1 = KB, 2 = KB + 1 and longer (right- and
+  // left-anchored bitmap, window bases; a null right bitmap = no filter for that class)
+  const uint32_t* win_r[3];
+  const uint32_t* win_l[3];
+  int win_k[3];
+  int KB;
+};
+
+// The edited string of one event at right-based index j of `code` (an ACGT-only string as 2-bit
+// codes, last base in the low bits): enumeration kind kk = 0..2 substitute the base by the three
+// other letters, 3 delete it, 4..7 insert A C G T before it.  T / low / bb are the pieces of `code`
+// around j, shared by the eight kinds of one position.
+struct EditSite {
+  uint64_t T;      // the bases left of j, moved down onto j
+  uint64_t low;    // the bases right of j
+  uint32_t bb;     // the base at j
+  int sh;          // 2 j
+};
+__device__ __forceinline__ EditSite edit_site(uint64_t code, int j) {
+  EditSite s;
+  s.sh = 2 * j;
+  s.low = code & ((1ULL << s.sh) - 1ULL);
+  s.bb = (uint32_t)(code >> s.sh) & 3u;
+  s.T = ((code >> s.sh) >> 2) << s.sh;
+  return s;
+}
 template <bool INDEL>
-__global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(IndexView ix, BatchDev b, SearchOut out, uint32_t pairs_per_warp) {
-  constexpr int S = INDEL ? 8 : 3;    // enumeration slots per position of a clean query
+__device__ __forceinline__ uint64_t edit_apply(const EditSite& s, int kk, int& dL, int& kcanon) {
+  if (!INDEL || kk < 3) {
+    const uint32_t c = (s.bb + 1u + (uint32_t)kk) & 3u;
+    dL = 0; kcanon = (int)c;
+    return (s.T << 2) | ((uint64_t)c << s.sh) | s.low;
+  }
+  if (kk == 3) { dL = -1; kcanon = 4; return s.T | s.low; }
+  const uint32_t c = (uint32_t)(kk - 4);
+  dL = 1; kcanon = 5 + (int)c;
+  return (s.T << 4) | ((uint64_t)((c << 2) | s.bb) << s.sh) | s.low;
+}
+
+// Address of the presence-bitmap word for the longest window the string covers (KB + 1, KB or KB - 1
+// bases): its last bases or -- when all its edits lie right of its first kb - 7 bases -- its first
+// bases, so that siblings probe the same 2 KB region (right- and left-anchored bitmaps).  Branch-free:
+// the caller issues the loads of several probes back to back and tests the bits afterwards.
+// state: 0 = test the bit, 1 = passes without a filter (no bitmap for that length), 2 = cannot occur.
+struct ProbeAddr {
+  const uint32_t* word;
+  uint32_t bit;     // bit inside the word
+  uint32_t state;
+};
+template <bool OTHER = false>   // OTHER: the window at the opposite end (the second opinion of the slow path)
+__device__ __forceinline__ ProbeAddr presence_addr(const PackedArgs& a, uint64_t code, int L, int p_left) {
+  const int cls = L - a.KB + 1;
+  const int c = cls > 2 ? 2 : (cls < 0 ? 0 : cls);
+  const uint32_t* bm = c == 2 ? a.win_r[2] : (c == 1 ? a.win_r[1] : a.win_r[0]);
+  const uint32_t* bml = c == 2 ? a.win_l[2] : (c == 1 ? a.win_l[1] : a.win_l[0]);
+  const int kb = c == 2 ? a.win_k[2] : (c == 1 ? a.win_k[1] : a.win_k[0]);
+  const uint64_t wmask = (1ULL << (2 * kb)) - 1ULL;
+  const int sr = 2 * (L - kb);
+  const uint64_t bit_l = presence_bit_left((code >> (sr > 0 ? sr : 0)) & wmask, kb);
+  const uint64_t bit_r = presence_bit(code & wmask, kb);
+  const bool first = bml != nullptr && p_left >= kb - presence_bit_bases(kb);
+  const bool left = OTHER ? !first : first;
+  const uint64_t bit = left ? bit_l : bit_r;
+  const uint32_t* base = left ? bml : bm;
+  ProbeAddr r;
+  r.state = L <= 0 ? 2u : ((a.KB == 0 || cls < 0 || bm == nullptr || (OTHER && (bml == nullptr || L <= kb))) ? 1u : 0u);
+  r.word = r.state ? a.win_r[1] : base + (bit >> 5);   // (a harmless address when no test is needed)
+  r.bit = (uint32_t)bit & 31u;
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_probe(const uint32_t* p) {
+  uint32_t word;   // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
+  asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(p));
+  return word;
+}
+// the probes of all kinds of one position: addresses first, then the loads (in flight together), then the bits
+template <bool INDEL>
+__device__ __forceinline__ uint32_t probe_site(const PackedArgs& a, const EditSite& site, int L1, int p_left, bool have) {
+  constexpr int S = INDEL ? 8 : 3;
+  ProbeAddr pa[S];
+#pragma unroll
+  for (int kk = 0; kk < S; ++kk) {
+    int dL, kc;
+    const uint64_t code = edit_apply<INDEL>(site, kk, dL, kc);
+    pa[kk] = presence_addr(a, code, L1 + dL, p_left);
+  }
+  uint32_t w[S];
+#pragma unroll
+  for (int kk = 0; kk < S; ++kk) w[kk] = ld_probe(pa[kk].word);
+  uint32_t mask = 0;
+#pragma unroll
+  for (int kk = 0; kk < S; ++kk) {
+    const uint32_t bit = pa[kk].state == 0 ? ((w[kk] >> pa[kk].bit) & 1u) : (pa[kk].state == 1 ? 1u : 0u);
+    mask |= bit << kk;
+  }
+  return have ? mask : 0u;
+}
+__device__ __forceinline__ bool presence_probe(const PackedArgs& a, uint64_t code, int L, int p_left) {
+  const ProbeAddr pa = presence_addr(a, code, L, p_left);
+  if (pa.state) return pa.state == 1;
+  return (ld_probe(pa.word) >> pa.bit) & 1u;
+}
+
+// Slow path of 32 queued strings (one per lane; `have` marks the real ones): K-mer table lookup on
+// the last K bases + one backward-search step per remaining base; survivors become candidates.
+// Not inlined: it is reached from several places of the kernel and rarely (~4 % of the strings).
+// A string longer than its window first takes a second opinion: the window at its other end (the
+// bitmap with the opposite anchoring) must hold it as well.  A false survivor of the first probe --
+// its 19 last bases occur somewhere, say -- walks the whole backward search before the last base
+// fails it (~10 dependent random reads); about three in four of them are stopped here by one read.
+__device__ __noinline__ void resolve_queued(const IndexView& ix, const PackedArgs& a, const SearchOut& out, bool have, uint64_t code, uint2 meta,
+                                            int cs) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int K = (int)ix.K;
+  const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
+  bool alive = false;
+  uint32_t l = 0, r = (uint32_t)ix.n;
+  if (have) {
+    const int L = (int)(meta.y >> 27);
+    const int nev = (int)((meta.y >> 1) & 3u);
+    const int p_left = nev ? (int)((meta.y >> 3) & 0xFFFu) / cs : 0;
+    const ProbeAddr pa = presence_addr<true>(a, code, L, p_left);
+    if (pa.state == 0 && !((ld_probe(pa.word) >> pa.bit) & 1u)) have = false;
+  }
+  if (have) {
+    const int L = (int)(meta.y >> 27);
+    int t = 0;
+    if (L >= K) {
+      uint2 iv = __ldg(&ix.kmer[(uint32_t)code & kmask]);
+      l = iv.x; r = iv.y; t = K;
+    }
+    while (l < r && t < L) {
+      step_acgt(ix, l, r, (int)((code >> (2 * t)) & 3));
+      ++t;
+    }
+    alive = l < r;
+  }
+  unsigned am = __ballot_sync(FULL, alive);
+  if (am) {
+    unsigned int first = 0;
+    if (lane == (uint32_t)(__ffs(am) - 1)) first = atomicAdd(out.n_cand, (unsigned int)__popc(am));
+    first = __shfl_sync(FULL, first, __ffs(am) - 1);
+    if (alive) {
+      unsigned int slot = first + (unsigned int)__popc(am & lt);
+      if (slot < out.cap) {
+        Cand c;
+        c.q = meta.x; c.l = l; c.r = r; c.code = meta.y & 0x07FFFFFFu;
+        out.cands[slot] = c;
+      } else {
+        atomicExch(out.overflow, 1u);
+      }
+    }
+  }
+}
+
+// k_search_packed.  One warp owns a short run of (query, strand) pairs.  The lanes are POSITIONS of
+// the string and the edit kinds are walked in a loop that is uniform across the warp, so building an
+// edited string is a handful of shifts without divergence, and the (up to eight) probes of one
+// position are independent loads in flight together:
+//   single events   the positions of up to eight pairs of equal length are laid side by side
+//                   (8 pairs x 20 bases = 5 full passes of 32 lanes);
+//   pairs of events (distance 2) for one first position p1 the lanes are (first kind, second
+//                   position) combinations; the first event is applied per lane, the second kinds
+//                   are walked uniformly.
+// The strings enumerated are exactly those of k_search for a clean query (neighbors.h:47-83).
+template <bool INDEL>
+__global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(const __grid_constant__ IndexView ix, const __grid_constant__ PackedArgs a,
+                                                                             const __grid_constant__ SearchOut out, uint32_t pairs_per_warp) {
+  constexpr int S = INDEL ? 8 : 3;    // enumeration kinds per position of a clean query
   constexpr int CS = INDEL ? 9 : 4;   // canonical slot numbering carried by the candidate
   constexpr unsigned FULL = 0xFFFFFFFFu;
   __shared__ uint64_t q_code[8][64];
@@ -483,153 +660,147 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(Ind
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t npairs = b.reverse ? 2ULL * b.nq : (uint64_t)b.nq;
-  // every warp owns a short run of consecutive pairs: blocks are short-lived, so the small kernels
-  // of another chunk of the pipeline (other stream) get SM slots while this search is running
+  const uint64_t npairs = a.reverse ? 2ULL * a.nq : (uint64_t)a.nq;
   const uint64_t pair_lo = warp * pairs_per_warp;
   const uint64_t pair_hi = pair_lo + pairs_per_warp < npairs ? pair_lo + pairs_per_warp : npairs;
-  const int K = (int)ix.K;
-  const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
-  const int KB = (int)ix.KB;
   uint32_t queued = 0;
   unsigned long long my_scripts = 0;
 
-  // slow path of one queued string (all 32 lanes call; `have` marks the real ones)
-  auto resolve = [&](bool have, uint64_t code, uint2 meta) {
-    bool alive = false;
-    uint32_t l = 0, r = (uint32_t)ix.n;
-    if (have) {
-      const int L = (int)(meta.y >> 27);
-      int t = 0;
-      if (L >= K) {
-        uint2 iv = __ldg(&ix.kmer[(uint32_t)code & kmask]);
-        l = iv.x; r = iv.y; t = K;
-      }
-      while (l < r && t < L) {
-        step_acgt(ix, l, r, (int)((code >> (2 * t)) & 3));
-        ++t;
-      }
-      alive = l < r;
+  // survivors of the bitmap -> the per-warp queue; 32 queued strings run the slow path together
+  auto push = [&](bool pass, uint64_t code, uint32_t q, uint32_t scode, int L) {
+    const unsigned pm = __ballot_sync(FULL, pass);
+    if (!pm) return;
+    if (pass) {
+      const uint32_t slot = queued + (uint32_t)__popc(pm & lt);
+      q_code[wib][slot] = code;
+      q_meta[wib][slot] = make_uint2(q, scode | ((uint32_t)L << 27));
     }
-    unsigned am = __ballot_sync(FULL, alive);
-    if (am) {
-      unsigned int first = 0;
-      if (lane == (uint32_t)(__ffs(am) - 1)) first = atomicAdd(out.n_cand, (unsigned int)__popc(am));
-      first = __shfl_sync(FULL, first, __ffs(am) - 1);
-      if (alive) {
-        unsigned int slot = first + (unsigned int)__popc(am & lt);
-        if (slot < out.cap) {
-          Cand c;
-          c.q = meta.x; c.l = l; c.r = r; c.code = meta.y & 0x07FFFFFFu;
-          out.cands[slot] = c;
-        } else {
-          atomicExch(out.overflow, 1u);
+    queued += (uint32_t)__popc(pm);
+    __syncwarp();
+    if (queued >= 32) {
+      queued -= 32;
+      const uint64_t c = q_code[wib][queued + lane];
+      const uint2 mt = q_meta[wib][queued + lane];
+      __syncwarp();
+      resolve_queued(ix, a, out, true, c, mt, CS);
+    }
+  };
+  auto pair_shape = [&](uint64_t pair, uint32_t& q, int& strand, int& m, int& dq) -> bool {
+    q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+    strand = a.reverse ? (int)(pair & 1) : 0;
+    if (pair >= pair_hi || !(a.qflag[q] & 2)) return false;
+    m = a.seed_len ? (int)a.seed_len : (int)(a.off[q + 1] - a.off[q]);
+    dq = (int)a.dist[q];
+    return true;
+  };
+
+  for (uint64_t g0 = pair_lo; g0 < pair_hi;) {
+    // a group: consecutive packed pairs of one length and distance (at most 8)
+    uint32_t q0;
+    int s0, m = 0, dq = 0;
+    if (!pair_shape(g0, q0, s0, m, dq)) { ++g0; continue; }
+    int g = 1;
+    {
+      uint32_t ql;
+      int sl, ml = 0, dl = 0;
+      const bool same = lane < 8 && pair_shape(g0 + lane, ql, sl, ml, dl) && ml == m && dl == dq;
+      const unsigned sm = __ballot_sync(FULL, same) & 0xFFu;
+      g = __ffs(~sm) - 1;               // leading run of matching pairs (lane 0 always matches)
+      if (g < 1) g = 1;
+      if (g > 8) g = 8;
+    }
+    const bool with_base = !(INDEL && dq >= 1);
+    // ---- the unedited strings
+    if (with_base) {
+      const bool have = lane < (uint32_t)g;
+      uint32_t q = 0;
+      uint64_t code = 0;
+      uint32_t scode = 0;
+      bool pass = false;
+      if (have) {
+        const uint64_t pair = g0 + lane;
+        q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+        const int strand = a.reverse ? (int)(pair & 1) : 0;
+        code = a.qcode[2 * (uint64_t)q + strand];
+        scode = pack_script(strand, 0, 0, 0);
+        ++my_scripts;
+        pass = presence_probe(a, code, m, 0);
+      }
+      push(pass, code, q, scode, m);
+    }
+    // ---- single events: lanes = (pair of the group, position)
+    if (dq >= 1) {
+      const int nslots = g * m;
+      for (int s = 0; s < nslots; s += 32) {
+        const int slot = s + (int)lane;
+        const bool have = slot < nslots;
+        const int pi = have ? slot / m : 0;
+        const int p = slot - pi * m;
+        const uint64_t pair = g0 + (uint64_t)pi;
+        const uint32_t q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+        const int strand = a.reverse ? (int)(pair & 1) : 0;
+        const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
+        const EditSite site = edit_site(code0, m - 1 - p);
+        const uint32_t passmask = probe_site<INDEL>(a, site, m, p, have);
+        if (have) my_scripts += S;
+        uint32_t anyk = __reduce_or_sync(FULL, passmask);   // kinds that passed on some lane
+#pragma unroll 1
+        while (anyk) {
+          const int kk = __ffs(anyk) - 1;
+          anyk &= anyk - 1;
+          int dL, kc;
+          const uint64_t code = edit_apply<INDEL>(site, kk, dL, kc);
+          push((passmask >> kk) & 1u, code, q, pack_script(strand, 1, p * CS + kc, 0), m + dL);
         }
       }
     }
-  };
-
-  for (uint64_t pair = pair_lo; pair < pair_hi; ++pair) {
-    const uint32_t q = b.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
-    const int strand = b.reverse ? (int)(pair & 1) : 0;
-    if (!(b.qflag[q] & 2)) continue;
-    const int m = b.seed_len ? (int)b.seed_len : (int)(b.off[q + 1] - b.off[q]);
-    const uint64_t code0 = b.qcode[2 * (uint64_t)q + strand];
-    const int dq = (int)b.dist[q];
-    const int E = S * m;
-    const bool with_base = !(INDEL && dq >= 1);
-    const int nrows = dq >= 2 ? E : 0;
-    auto canon = [&](int kk, int pos) -> int {   // enumeration slot -> canonical event (enum_to_canonical, clean)
-      if (kk < 3) return (int)(((code0 >> (2 * (m - 1 - pos))) & 3) + 1 + kk) & 3;
-      return kk + 1;
-    };
-    for (int row = -1; row < nrows; ++row) {
-      uint64_t code1 = code0;
-      int p1 = 0, k1 = 0, start, end, L1 = m;
-      if (row < 0) {
-        start = with_base ? -1 : 0;
-        end = dq >= 1 ? E : 0;
-      } else {
-        p1 = row / S;
-        k1 = canon(row - p1 * S, p1);
-        code1 = apply_event_packed(code0, m - 1 - p1, k1);
-        L1 = m + (k1 == 4 ? -1 : (k1 >= 5 ? 1 : 0));
-        start = (k1 >= 5 ? p1 : p1 + 1) * S;
-        end = E;
-      }
-      for (int s = start; s < end; s += 32) {
-        const int e = s + (int)lane;
-        const bool have = e < end;
-        uint64_t code = code1;
-        uint32_t scode = 0;
-        int L = L1;
-        bool pass = false;
-        if (have) {
-          ++my_scripts;
-          if (e < 0) {
-            scode = pack_script(strand, 0, 0, 0);
-          } else {
-            const int p2 = e / S;
-            const int k2 = canon(e - p2 * S, p2);
-            code = apply_event_packed(code1, m - 1 - p2, k2);
-            L += (k2 == 4 ? -1 : (k2 >= 5 ? 1 : 0));
-            scode = row < 0 ? pack_script(strand, 1, p2 * CS + k2, 0)
-                            : pack_script(strand, 2, p1 * CS + k1, p2 * CS + k2);
-          }
-          pass = L > 0;
-          if (pass && KB) {
-            // the longest window the string covers: KB + 1, KB or KB - 1 bases
-            const uint32_t* bm = nullptr;
-            const uint32_t* bml = nullptr;
-            int kb = 0;
-            if (L > KB && ix.present_hi) { bm = ix.present_hi; bml = ix.present_hi_l; kb = KB + 1; }
-            else if (L >= KB) { bm = ix.present_kb; bml = ix.present_kb_l; kb = KB; }
-            else if (L == KB - 1 && ix.present_lo) { bm = ix.present_lo; kb = KB - 1; }
-            if (bm) {
-              // leftmost edit at or right of base kb - 7 of the string: its first kb bases share their
-              // region of the left-anchored bitmap with every sibling of that kind; otherwise the
-              // last kb bases go to the right-anchored one (shared when all edits lie left of its
-              // last kb - 7 bases)
-              const int p_left = e < 0 ? 0 : (row < 0 ? e / S : p1);
-              uint64_t bit;
-              if (bml && p_left >= kb - presence_bit_bases(kb)) {
-                bm = bml;
-                bit = presence_bit_left((code >> (2 * (L - kb))) & ((1ULL << (2 * kb)) - 1ULL), kb);
-              } else {
-                bit = presence_bit(code & ((1ULL << (2 * kb)) - 1ULL), kb);
-              }
-              // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
-              uint32_t word;
-              asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(bm + (bit >> 5)));
-              pass = (word >> (uint32_t)(bit & 31)) & 1u;
+    // ---- pairs of events: per pair and first position, lanes = (first kind, second position)
+    if (dq >= 2) {
+      for (int pi = 0; pi < g; ++pi) {
+        const uint64_t pair = g0 + (uint64_t)pi;
+        const uint32_t q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+        const int strand = a.reverse ? (int)(pair & 1) : 0;
+        const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
+        for (int p1 = 0; p1 < m; ++p1) {
+          // second positions p1 .. m-1 (p1 itself only after an insertion)
+          const int npos = m - p1;
+          const int nslots = S * npos;
+          const EditSite site1 = edit_site(code0, m - 1 - p1);
+          for (int s = 0; s < nslots; s += 32) {
+            const int slot = s + (int)lane;
+            const int k1i = slot / npos;
+            const int p2 = p1 + (slot - k1i * npos);
+            int dL1 = 0, k1c = 0;
+            uint64_t code1 = code0;
+            bool have = slot < nslots;
+            if (have) {
+              code1 = edit_apply<INDEL>(site1, k1i, dL1, k1c);
+              if (p2 == p1 && k1c < 5) have = false;       // pair_ok: equal positions only after an insertion
+            }
+            const EditSite site2 = edit_site(code1, m - 1 - p2);
+            const int L1 = m + dL1;
+            const uint32_t passmask = probe_site<INDEL>(a, site2, L1, p1, have);
+            if (have) my_scripts += S;
+            uint32_t anyk = __reduce_or_sync(FULL, passmask);   // kinds that passed on some lane
+#pragma unroll 1
+            while (anyk) {
+              const int kk = __ffs(anyk) - 1;
+              anyk &= anyk - 1;
+              int dL, kc;
+              const uint64_t code = edit_apply<INDEL>(site2, kk, dL, kc);
+              push((passmask >> kk) & 1u, code, q, pack_script(strand, 2, p1 * CS + k1c, p2 * CS + kc), L1 + dL);
             }
           }
         }
-        const unsigned pm = __ballot_sync(FULL, pass);
-        if (pm) {
-          if (pass) {
-            const uint32_t slot = queued + (uint32_t)__popc(pm & lt);
-            q_code[wib][slot] = code;
-            q_meta[wib][slot] = make_uint2(q, scode | ((uint32_t)L << 27));
-          }
-          queued += (uint32_t)__popc(pm);
-          __syncwarp();
-          if (queued >= 32) {
-            queued -= 32;
-            const uint64_t c = q_code[wib][queued + lane];
-            const uint2 mt = q_meta[wib][queued + lane];
-            __syncwarp();
-            resolve(true, c, mt);
-          }
-        }
       }
     }
+    g0 += (uint64_t)g;
   }
   if (queued) {
     const bool have = lane < queued;
     const uint64_t c = have ? q_code[wib][lane] : 0;
     const uint2 mt = have ? q_meta[wib][lane] : make_uint2(0, 0);
-    resolve(have, c, mt);
+    resolve_queued(ix, a, out, have, c, mt, CS);
   }
   for (int o = 16; o; o >>= 1) my_scripts += __shfl_down_sync(FULL, my_scripts, o);
   if (lane == 0 && my_scripts) atomicAdd(out.n_scripts, my_scripts);
@@ -1942,12 +2113,21 @@ static int run_impl(dg_batch* b) {
         // packed (ACGT-only, <= 31 bases) queries: presence-bitmap filter + compacted slow path
         const uint64_t npairs = b->par.reverse ? 2ULL * nq : (uint64_t)nq;
         static const int ppw_env = getenv("DG_PAIRS_PER_WARP") ? atoi(getenv("DG_PAIRS_PER_WARP")) : 0;
-        uint32_t ppw = ppw_env > 0 ? (uint32_t)ppw_env : 4u;
+        uint32_t ppw = ppw_env > 0 ? (uint32_t)ppw_env : 16u;  // groups of eight 20-mers fill five passes of 32 lanes exactly
         // small batches: fewer pairs per warp so that the grid still covers every SM
         while (ppw > 1 && npairs / (8ull * ppw) < (uint64_t)nsm * 6) ppw >>= 1;
         const unsigned blocks = (unsigned)((npairs + 8ull * ppw - 1) / (8ull * ppw));
-        if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
-        else k_search_packed<false><<<blocks, 256, 0, st>>>(v, bd, so, ppw);
+        PackedArgs pa;
+        pa.qcode = bd.qcode; pa.qflag = bd.qflag; pa.dist = bd.dist; pa.off = bd.off;
+        pa.nq = nq; pa.seed_len = bd.seed_len; pa.reverse = bd.reverse;
+        pa.KB = (int)v.KB;
+        // windows by length class, fallbacks resolved here: without the KB + 1 bitmap longer strings use KB
+        pa.win_r[0] = v.present_lo; pa.win_l[0] = nullptr; pa.win_k[0] = (int)v.KB - 1;
+        pa.win_r[1] = v.present_kb; pa.win_l[1] = v.present_kb_l; pa.win_k[1] = (int)v.KB;
+        if (v.present_hi) { pa.win_r[2] = v.present_hi; pa.win_l[2] = v.present_hi_l; pa.win_k[2] = (int)v.KB + 1; }
+        else { pa.win_r[2] = v.present_kb; pa.win_l[2] = v.present_kb_l; pa.win_k[2] = (int)v.KB; }
+        if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, pa, so, ppw);
+        else k_search_packed<false><<<blocks, 256, 0, st>>>(v, pa, so, ppw);
         // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
         k_search<<<nsm * general_per_sm, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
         launches += 2;
