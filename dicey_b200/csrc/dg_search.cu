@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(256) k_search(IndexView ix, BatchDev b, UnitTa
 //      K-mer table lookup on the last K bases + one backward-search step per remaining base.
 // The strings enumerated are exactly those of k_search for a clean query (neighbors.h:47-83).
 #ifndef DG_PACKED_MIN_BLOCKS
-#define DG_PACKED_MIN_BLOCKS 3
+#define DG_PACKED_MIN_BLOCKS 4
 #endif
 // What the kernel reads of the batch and of the index (the whole BatchDev / IndexView as parameters
 // costs registers the enumeration loop needs).
@@ -651,7 +651,9 @@ __device__ __noinline__ void resolve_queued(const IndexView& ix, const PackedArg
 // The strings enumerated are exactly those of k_search for a clean query (neighbors.h:47-83).
 template <bool INDEL>
 __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(const __grid_constant__ IndexView ix, const __grid_constant__ PackedArgs a,
-                                                                             const __grid_constant__ SearchOut out, uint32_t pairs_per_warp) {
+                                                                             const __grid_constant__ SearchOut out, uint32_t pairs_per_warp,
+                                                                             const uint32_t* __restrict__ skip_if_regular) {
+  if (skip_if_regular && !(*skip_if_regular & 1u)) return;   // the regular batch went through k_probe_* / k_resolve
   constexpr int S = INDEL ? 8 : 3;    // enumeration kinds per position of a clean query
   constexpr int CS = INDEL ? 9 : 4;   // canonical slot numbering carried by the candidate
   constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -804,6 +806,171 @@ __global__ void __launch_bounds__(256, DG_PACKED_MIN_BLOCKS) k_search_packed(con
   }
   for (int o = 16; o; o >>= 1) my_scripts += __shfl_down_sync(FULL, my_scripts, o);
   if (lane == 0 && my_scripts) atomicAdd(out.n_scripts, my_scripts);
+}
+
+// ------------------------------------------------------------------------------------------
+// The regular batch (every query ACGT-only, one length m, one distance >= 1 -- the shape of the headline
+// workload and of BASELINE configs 2 and 4) takes the same enumeration in TWO kernels:
+//   k_probe_*   nothing but the presence probes: one thread per (string, position), eight independent
+//               reads in flight per thread, few registers, high occupancy -- a gather kernel that runs
+//               at the rate the memory system serves random sectors; one result byte per thread
+//               (bit kk = edit kind kk survives);
+//   k_resolve   walks the result bytes (~4 % of the bits are set), rebuilds those strings and runs the
+//               queue + slow path of k_search_packed on them.
+// Both leave at once when k_prepare found the batch irregular (*irregular & 1): k_search_packed, which
+// handles any mixture, then does the work instead (and leaves at once when the batch IS regular).
+struct ProbeShape {
+  int m, dq;
+  uint32_t n2;           // pair slots per string: S * m (m + 1) / 2 (first position, first kind, second position >= first)
+  uint64_t npairs;       // (query, strand) pairs
+  const uint32_t* irregular;
+  unsigned long long scripts_per_pair;   // strings enumerated per pair (statistics)
+  unsigned long long* n_scripts;
+};
+// slot of the pair enumeration -> (first position, first kind, second position)
+template <int S>
+__device__ __forceinline__ void pair_slot(uint32_t u, int m, int& p1, int& k1i, int& p2) {
+  // rows of S * (m - p1) slots; T(p1) = p1 m - p1 (p1 - 1) / 2 rows-of-S precede first position p1
+  const uint32_t v = u / (uint32_t)S;
+  const float b2 = (float)(2 * m + 1);
+  int g = (int)((b2 - sqrtf(b2 * b2 - 8.0f * (float)v)) * 0.5f);
+  if (g < 0) g = 0;
+  if (g > m - 1) g = m - 1;
+  auto T = [&](int x) { return (uint32_t)(x * m - (x * (x - 1)) / 2); };
+  while (g > 0 && T(g) > v) --g;
+  while (g + 1 < m && T(g + 1) <= v) ++g;
+  p1 = g;
+  const uint32_t r = u - (uint32_t)S * T(g);
+  const uint32_t npos = (uint32_t)(m - g);
+  k1i = (int)(r / npos);
+  p2 = g + (int)(r - (uint32_t)k1i * npos);
+}
+
+template <bool INDEL>
+__global__ void __launch_bounds__(256, 5) k_probe_singles(const __grid_constant__ PackedArgs a, const __grid_constant__ ProbeShape sh,
+                                                          uint8_t* __restrict__ masks) {
+  if (*sh.irregular & 1u) return;
+  const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = sh.m;
+  if (slot >= sh.npairs * (uint64_t)m) return;
+  if (slot == 0) atomicAdd(sh.n_scripts, sh.scripts_per_pair * sh.npairs);
+  const uint64_t pair = slot / (uint32_t)m;
+  const int p = (int)(slot - pair * (uint64_t)m);
+  const uint64_t code0 = a.qcode[pair + (a.reverse ? 0 : pair)];   // qcode holds two codes per query
+  const EditSite site = edit_site(code0, m - 1 - p);
+  uint32_t mask = probe_site<INDEL>(a, site, m, p, true);
+  if (!INDEL && p == 0) {   // Hamming sets hold the unedited string as well: bit 7 of position 0
+    if (presence_probe(a, code0, m, 0)) mask |= 0x80u;
+  }
+  masks[slot] = (uint8_t)mask;
+}
+
+template <bool INDEL>
+__global__ void __launch_bounds__(256, 5) k_probe_pairs(const __grid_constant__ PackedArgs a, const __grid_constant__ ProbeShape sh,
+                                                        uint64_t pair0, uint64_t npairs_tile, uint8_t* __restrict__ masks) {
+  constexpr int S = INDEL ? 8 : 3;
+  if (*sh.irregular & 1u) return;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npairs_tile * (uint64_t)sh.n2) return;
+  const uint64_t pl = t / sh.n2;
+  const uint32_t u = (uint32_t)(t - pl * (uint64_t)sh.n2);
+  const uint64_t pair = pair0 + pl;
+  const int m = sh.m;
+  int p1, k1i, p2;
+  pair_slot<S>(u, m, p1, k1i, p2);
+  const uint64_t code0 = a.qcode[pair + (a.reverse ? 0 : pair)];
+  int dL1, k1c;
+  const uint64_t code1 = edit_apply<INDEL>(edit_site(code0, m - 1 - p1), k1i, dL1, k1c);
+  const bool have = !(p2 == p1 && k1c < 5);       // pair_ok: equal positions only after an insertion
+  const EditSite site2 = edit_site(code1, m - 1 - p2);
+  masks[t] = (uint8_t)probe_site<INDEL>(a, site2, m + dL1, p1, have);
+}
+
+// masks of k_probe_singles (pairs == false: npairs * m bytes) or of one tile of k_probe_pairs -> candidates
+template <bool INDEL>
+__global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ IndexView ix, const __grid_constant__ PackedArgs a,
+                                                    const __grid_constant__ SearchOut out, const __grid_constant__ ProbeShape sh,
+                                                    const uint8_t* __restrict__ masks, uint64_t nbytes, uint64_t pair0, int pairs) {
+  constexpr int S = INDEL ? 8 : 3;
+  constexpr int CS = INDEL ? 9 : 4;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  if (*sh.irregular & 1u) return;
+  __shared__ uint64_t q_code[8][64];
+  __shared__ uint2 q_meta[8][64];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int m = sh.m;
+  uint32_t queued = 0;
+  const uint64_t nwords = (nbytes + 3) >> 2;
+  const uint32_t* mw = reinterpret_cast<const uint32_t*>(masks);
+  for (uint64_t w0 = warp * 32; w0 < nwords; w0 += nwarps * 32) {
+    const uint64_t wi = w0 + lane;
+    uint32_t bits = wi < nwords ? __ldg(mw + wi) : 0u;
+    if (wi * 4 + 4 > nbytes && wi < nwords) bits &= (1u << (8 * (uint32_t)(nbytes - wi * 4))) - 1u;   // the tail word
+    while (__any_sync(FULL, bits != 0)) {
+      const bool have = bits != 0;
+      uint64_t code = 0;
+      uint32_t q = 0, scode = 0;
+      int L = 0;
+      if (have) {
+        const int bpos = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint64_t slot = wi * 4 + (uint64_t)(bpos >> 3);
+        const int kk = bpos & 7;
+        if (!pairs) {
+          const uint64_t pair = slot / (uint32_t)m;
+          const int p = (int)(slot - pair * (uint64_t)m);
+          q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+          const int strand = a.reverse ? (int)(pair & 1) : 0;
+          const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
+          if (kk == 7 && !INDEL) {
+            code = code0; L = m; scode = pack_script(strand, 0, 0, 0);
+          } else {
+            int dL, kc;
+            code = edit_apply<INDEL>(edit_site(code0, m - 1 - p), kk, dL, kc);
+            L = m + dL;
+            scode = pack_script(strand, 1, p * CS + kc, 0);
+          }
+        } else {
+          const uint64_t pl = slot / sh.n2;
+          const uint32_t u = (uint32_t)(slot - pl * (uint64_t)sh.n2);
+          const uint64_t pair = pair0 + pl;
+          q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+          const int strand = a.reverse ? (int)(pair & 1) : 0;
+          const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
+          int p1, k1i, p2, dL1, k1c, dL, kc;
+          pair_slot<S>(u, m, p1, k1i, p2);
+          const uint64_t code1 = edit_apply<INDEL>(edit_site(code0, m - 1 - p1), k1i, dL1, k1c);
+          code = edit_apply<INDEL>(edit_site(code1, m - 1 - p2), kk, dL, kc);
+          L = m + dL1 + dL;
+          scode = pack_script(strand, 2, p1 * CS + k1c, p2 * CS + kc);
+        }
+      }
+      const unsigned pm = __ballot_sync(FULL, have);
+      if (have) {
+        const uint32_t sl = queued + (uint32_t)__popc(pm & lt);
+        q_code[wib][sl] = code;
+        q_meta[wib][sl] = make_uint2(q, scode | ((uint32_t)L << 27));
+      }
+      queued += (uint32_t)__popc(pm);
+      __syncwarp();
+      if (queued >= 32) {
+        queued -= 32;
+        const uint64_t c = q_code[wib][queued + lane];
+        const uint2 mt = q_meta[wib][queued + lane];
+        __syncwarp();
+        resolve_queued(ix, a, out, true, c, mt, CS);
+      }
+    }
+  }
+  if (queued) {
+    const bool have = lane < queued;
+    const uint64_t c = have ? q_code[wib][lane] : 0;
+    const uint2 mt = have ? q_meta[wib][lane] : make_uint2(0, 0);
+    resolve_queued(ix, a, out, have, c, mt, CS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2126,8 +2293,57 @@ static int run_impl(dg_batch* b) {
         pa.win_r[1] = v.present_kb; pa.win_l[1] = v.present_kb_l; pa.win_k[1] = (int)v.KB;
         if (v.present_hi) { pa.win_r[2] = v.present_hi; pa.win_l[2] = v.present_hi_l; pa.win_k[2] = (int)v.KB + 1; }
         else { pa.win_r[2] = v.present_kb; pa.win_l[2] = v.present_kb_l; pa.win_k[2] = (int)v.KB; }
-        if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, pa, so, ppw);
-        else k_search_packed<false><<<blocks, 256, 0, st>>>(v, pa, so, ppw);
+        // the regular batch: probes and slow path in separate kernels (k_probe_*, k_resolve)
+        const int um = (int)b->uniform_len;
+        const int ud = (int)std::min<uint32_t>(b->par.distance, um > 0 ? (uint32_t)um - 1 : 0);
+        static const bool no_split = getenv("DG_NO_SPLIT") != nullptr;
+        const bool split = !no_split && um > 0 && !b->par.seed_len && ud >= 1 && um + ud <= kMaxPacked && v.KB != 0;
+        const uint32_t* skip = split ? b->irregular.p : nullptr;
+        if (split) {
+          const bool indel = b->par.indel != 0;
+          const int S = indel ? 8 : 3;
+          ProbeShape shp;
+          shp.m = um; shp.dq = ud; shp.npairs = npairs; shp.irregular = b->irregular.p;
+          shp.n2 = (uint32_t)(S * um * (um + 1) / 2);
+          shp.n_scripts = nscripts.p;
+          shp.scripts_per_pair = (unsigned long long)(S * um + (indel ? 0 : 1));
+          if (ud >= 2)
+            for (int p1 = 0; p1 < um; ++p1)
+              shp.scripts_per_pair += indel ? (unsigned long long)S * (4ull * (um - 1 - p1) + 4ull * (um - p1))
+                                            : (unsigned long long)S * 3ull * (um - 1 - p1);
+          const uint64_t n1 = npairs * (uint64_t)um;
+          ABuf<uint8_t> m1;
+          m1.alloc(n1 + 8, st);
+          const unsigned rblocks = (unsigned)std::min<uint64_t>((uint64_t)nsm * 8, (n1 / 4 + 255) / 256 + 1);
+          if (indel) {
+            k_probe_singles<true><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
+            k_resolve<true><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
+          } else {
+            k_probe_singles<false><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
+            k_resolve<false><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
+          }
+          launches += 2;
+          if (ud >= 2) {
+            // pairs of events: ~13 k scripts per string; tiles of pairs keep the result bytes at <= 256 MB
+            const uint64_t tile = std::max<uint64_t>(1, (256ull << 20) / shp.n2);
+            ABuf<uint8_t> m2;
+            m2.alloc(std::min(tile, npairs) * (uint64_t)shp.n2 + 8, st);
+            for (uint64_t p0 = 0; p0 < npairs; p0 += tile) {
+              const uint64_t np = std::min(tile, npairs - p0), nb = np * (uint64_t)shp.n2;
+              const unsigned rb = (unsigned)std::min<uint64_t>((uint64_t)nsm * 8, (nb / 4 + 255) / 256 + 1);
+              if (indel) {
+                k_probe_pairs<true><<<grid_for(nb, 256), 256, 0, st>>>(pa, shp, p0, np, m2.p);
+                k_resolve<true><<<rb, 256, 0, st>>>(v, pa, so, shp, m2.p, nb, p0, 1);
+              } else {
+                k_probe_pairs<false><<<grid_for(nb, 256), 256, 0, st>>>(pa, shp, p0, np, m2.p);
+                k_resolve<false><<<rb, 256, 0, st>>>(v, pa, so, shp, m2.p, nb, p0, 1);
+              }
+              launches += 2;
+            }
+          }
+        }
+        if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, pa, so, ppw, skip);
+        else k_search_packed<false><<<blocks, 256, 0, st>>>(v, pa, so, ppw, skip);
         // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
         k_search<<<nsm * general_per_sm, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
         launches += 2;
