@@ -592,8 +592,14 @@ __device__ __forceinline__ bool presence_probe(const PackedArgs& a, uint64_t cod
 // bitmap with the opposite anchoring) must hold it as well.  A false survivor of the first probe --
 // its 19 last bases occur somewhere, say -- walks the whole backward search before the last base
 // fails it (~10 dependent random reads); about three in four of them are stopped here by one read.
-__device__ __noinline__ void resolve_queued(const IndexView& ix, const PackedArgs& a, const SearchOut& out, bool have, uint64_t code, uint2 meta,
-                                            int cs) {
+__device__ __forceinline__ bool second_opinion(const PackedArgs& a, uint64_t code, uint2 meta, int cs) {
+  const int L = (int)(meta.y >> 27);
+  const int nev = (int)((meta.y >> 1) & 3u);
+  const int p_left = nev ? (int)((meta.y >> 3) & 0xFFFu) / cs : 0;
+  const ProbeAddr pa = presence_addr<true>(a, code, L, p_left);
+  return pa.state != 0 || ((ld_probe(pa.word) >> pa.bit) & 1u);
+}
+__device__ __noinline__ void resolve_chain(const IndexView& ix, const SearchOut& out, bool have, uint64_t code, uint2 meta) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
@@ -601,13 +607,6 @@ __device__ __noinline__ void resolve_queued(const IndexView& ix, const PackedArg
   const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
   bool alive = false;
   uint32_t l = 0, r = (uint32_t)ix.n;
-  if (have) {
-    const int L = (int)(meta.y >> 27);
-    const int nev = (int)((meta.y >> 1) & 3u);
-    const int p_left = nev ? (int)((meta.y >> 3) & 0xFFFu) / cs : 0;
-    const ProbeAddr pa = presence_addr<true>(a, code, L, p_left);
-    if (pa.state == 0 && !((ld_probe(pa.word) >> pa.bit) & 1u)) have = false;
-  }
   if (have) {
     const int L = (int)(meta.y >> 27);
     int t = 0;
@@ -637,6 +636,12 @@ __device__ __noinline__ void resolve_queued(const IndexView& ix, const PackedArg
       }
     }
   }
+}
+
+__device__ __forceinline__ void resolve_queued(const IndexView& ix, const PackedArgs& a, const SearchOut& out, bool have, uint64_t code, uint2 meta,
+                                               int cs) {
+  if (have && !second_opinion(a, code, meta, cs)) have = false;
+  resolve_chain(ix, out, have, code, meta);
 }
 
 // k_search_packed.  One warp owns a short run of (query, strand) pairs.  The lanes are POSITIONS of
@@ -895,14 +900,35 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
   constexpr int CS = INDEL ? 9 : 4;
   constexpr unsigned FULL = 0xFFFFFFFFu;
   if (*sh.irregular & 1u) return;
-  __shared__ uint64_t q_code[8][64];
-  __shared__ uint2 q_meta[8][64];
+  // two queues per warp: survivors of the first probe wait for the second opinion (A); what that leaves
+  // (about three in ten) waits for the backward search (B), so that the long dependent chain of the
+  // search always runs with 32 live lanes
+  __shared__ uint64_t q_code[8][64], r_code[8][64];
+  __shared__ uint2 q_meta[8][64], r_meta[8][64];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const int m = sh.m;
-  uint32_t queued = 0;
+  uint32_t queued = 0, rqueued = 0;
+  auto stage_b = [&](bool have, uint64_t c, uint2 mt) {   // second opinion of up to 32 strings -> queue B -> chain
+    const bool keep = have && second_opinion(a, c, mt, CS);
+    const unsigned km = __ballot_sync(FULL, keep);
+    if (keep) {
+      const uint32_t sl = rqueued + (uint32_t)__popc(km & lt);
+      r_code[wib][sl] = c;
+      r_meta[wib][sl] = mt;
+    }
+    rqueued += (uint32_t)__popc(km);
+    __syncwarp();
+    if (rqueued >= 32) {
+      rqueued -= 32;
+      const uint64_t c2 = r_code[wib][rqueued + lane];
+      const uint2 m2 = r_meta[wib][rqueued + lane];
+      __syncwarp();
+      resolve_chain(ix, out, true, c2, m2);
+    }
+  };
   const uint64_t nwords = (nbytes + 3) >> 2;
   const uint32_t* mw = reinterpret_cast<const uint32_t*>(masks);
   for (uint64_t w0 = warp * 32; w0 < nwords; w0 += nwarps * 32) {
@@ -961,7 +987,7 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
         const uint64_t c = q_code[wib][queued + lane];
         const uint2 mt = q_meta[wib][queued + lane];
         __syncwarp();
-        resolve_queued(ix, a, out, true, c, mt, CS);
+        stage_b(true, c, mt);
       }
     }
   }
@@ -969,7 +995,14 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
     const bool have = lane < queued;
     const uint64_t c = have ? q_code[wib][lane] : 0;
     const uint2 mt = have ? q_meta[wib][lane] : make_uint2(0, 0);
-    resolve_queued(ix, a, out, have, c, mt, CS);
+    __syncwarp();
+    stage_b(have, c, mt);
+  }
+  if (rqueued) {
+    const bool have = lane < rqueued;
+    const uint64_t c = have ? r_code[wib][lane] : 0;
+    const uint2 mt = have ? r_meta[wib][lane] : make_uint2(0, 0);
+    resolve_chain(ix, out, have, c, mt);
   }
 }
 
