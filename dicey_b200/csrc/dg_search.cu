@@ -554,7 +554,16 @@ __device__ __forceinline__ ProbeAddr presence_addr(const PackedArgs& a, uint64_t
 }
 __device__ __forceinline__ uint32_t ld_probe(const uint32_t* p) {
   uint32_t word;   // one random 4-byte read: ask L2 to fill 64 bytes instead of the whole 128-byte line
+#ifndef DG_PROBE_LD
+#define DG_PROBE_LD 64
+#endif
+#if DG_PROBE_LD == 64
   asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(word) : "l"(p));
+#elif DG_PROBE_LD == 128
+  asm("ld.global.nc.L2::128B.u32 %0, [%1];" : "=r"(word) : "l"(p));
+#else
+  asm("ld.global.nc.u32 %0, [%1];" : "=r"(word) : "l"(p));
+#endif
   return word;
 }
 // the probes of all kinds of one position: addresses first, then the loads (in flight together), then the bits
@@ -903,8 +912,8 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
   // two queues per warp: survivors of the first probe wait for the second opinion (A); what that leaves
   // (about three in ten) waits for the backward search (B), so that the long dependent chain of the
   // search always runs with 32 live lanes
-  __shared__ uint64_t q_code[8][64], r_code[8][64];
-  __shared__ uint2 q_meta[8][64], r_meta[8][64];
+  __shared__ uint64_t q_code[8][32], r_code[8][64];   // (q_code: 64 four-byte tokens per warp)
+  __shared__ uint2 r_meta[8][64];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -929,74 +938,75 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
       resolve_chain(ix, out, true, c2, m2);
     }
   };
+  // queue A holds TOKENS (result byte index * 8 + kind): the strings are rebuilt 32 at a time, one per lane
+  uint32_t* q_tok = reinterpret_cast<uint32_t*>(&q_code[wib][0]);   // 64 tokens
+  auto stage_a = [&](bool have, uint32_t tok) {
+    uint64_t code = 0;
+    uint32_t q = 0, scode = 0;
+    int L = 0;
+    if (have) {
+      const uint64_t slot = tok >> 3;
+      const int kk = (int)(tok & 7u);
+      if (!pairs) {
+        const uint64_t pair = slot / (uint32_t)m;
+        const int p = (int)(slot - pair * (uint64_t)m);
+        q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+        const int strand = a.reverse ? (int)(pair & 1) : 0;
+        const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
+        if (kk == 7 && !INDEL) {
+          code = code0; L = m; scode = pack_script(strand, 0, 0, 0);
+        } else {
+          int dL, kc;
+          code = edit_apply<INDEL>(edit_site(code0, m - 1 - p), kk, dL, kc);
+          L = m + dL;
+          scode = pack_script(strand, 1, p * CS + kc, 0);
+        }
+      } else {
+        const uint64_t pl = slot / sh.n2;
+        const uint32_t u = (uint32_t)(slot - pl * (uint64_t)sh.n2);
+        const uint64_t pair = pair0 + pl;
+        q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
+        const int strand = a.reverse ? (int)(pair & 1) : 0;
+        const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
+        int p1, k1i, p2, dL1, k1c, dL, kc;
+        pair_slot<S>(u, m, p1, k1i, p2);
+        const uint64_t code1 = edit_apply<INDEL>(edit_site(code0, m - 1 - p1), k1i, dL1, k1c);
+        code = edit_apply<INDEL>(edit_site(code1, m - 1 - p2), kk, dL, kc);
+        L = m + dL1 + dL;
+        scode = pack_script(strand, 2, p1 * CS + k1c, p2 * CS + kc);
+      }
+    }
+    stage_b(have, code, make_uint2(q, scode | ((uint32_t)L << 27)));
+  };
   const uint64_t nwords = (nbytes + 3) >> 2;
   const uint32_t* mw = reinterpret_cast<const uint32_t*>(masks);
   for (uint64_t w0 = warp * 32; w0 < nwords; w0 += nwarps * 32) {
     const uint64_t wi = w0 + lane;
     uint32_t bits = wi < nwords ? __ldg(mw + wi) : 0u;
     if (wi * 4 + 4 > nbytes && wi < nwords) bits &= (1u << (8 * (uint32_t)(nbytes - wi * 4))) - 1u;   // the tail word
-    while (__any_sync(FULL, bits != 0)) {
+    while (__any_sync(FULL, bits != 0)) {   // one set bit per lane and round
       const bool have = bits != 0;
-      uint64_t code = 0;
-      uint32_t q = 0, scode = 0;
-      int L = 0;
+      const unsigned pm = __ballot_sync(FULL, have);
       if (have) {
         const int bpos = __ffs(bits) - 1;
         bits &= bits - 1;
-        const uint64_t slot = wi * 4 + (uint64_t)(bpos >> 3);
-        const int kk = bpos & 7;
-        if (!pairs) {
-          const uint64_t pair = slot / (uint32_t)m;
-          const int p = (int)(slot - pair * (uint64_t)m);
-          q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
-          const int strand = a.reverse ? (int)(pair & 1) : 0;
-          const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
-          if (kk == 7 && !INDEL) {
-            code = code0; L = m; scode = pack_script(strand, 0, 0, 0);
-          } else {
-            int dL, kc;
-            code = edit_apply<INDEL>(edit_site(code0, m - 1 - p), kk, dL, kc);
-            L = m + dL;
-            scode = pack_script(strand, 1, p * CS + kc, 0);
-          }
-        } else {
-          const uint64_t pl = slot / sh.n2;
-          const uint32_t u = (uint32_t)(slot - pl * (uint64_t)sh.n2);
-          const uint64_t pair = pair0 + pl;
-          q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
-          const int strand = a.reverse ? (int)(pair & 1) : 0;
-          const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
-          int p1, k1i, p2, dL1, k1c, dL, kc;
-          pair_slot<S>(u, m, p1, k1i, p2);
-          const uint64_t code1 = edit_apply<INDEL>(edit_site(code0, m - 1 - p1), k1i, dL1, k1c);
-          code = edit_apply<INDEL>(edit_site(code1, m - 1 - p2), kk, dL, kc);
-          L = m + dL1 + dL;
-          scode = pack_script(strand, 2, p1 * CS + k1c, p2 * CS + kc);
-        }
-      }
-      const unsigned pm = __ballot_sync(FULL, have);
-      if (have) {
-        const uint32_t sl = queued + (uint32_t)__popc(pm & lt);
-        q_code[wib][sl] = code;
-        q_meta[wib][sl] = make_uint2(q, scode | ((uint32_t)L << 27));
+        q_tok[queued + (uint32_t)__popc(pm & lt)] = (uint32_t)(wi * 32 + (uint64_t)bpos);   // (byte index * 8 + kind)
       }
       queued += (uint32_t)__popc(pm);
       __syncwarp();
       if (queued >= 32) {
         queued -= 32;
-        const uint64_t c = q_code[wib][queued + lane];
-        const uint2 mt = q_meta[wib][queued + lane];
+        const uint32_t tok = q_tok[queued + lane];
         __syncwarp();
-        stage_b(true, c, mt);
+        stage_a(true, tok);
       }
     }
   }
   if (queued) {
     const bool have = lane < queued;
-    const uint64_t c = have ? q_code[wib][lane] : 0;
-    const uint2 mt = have ? q_meta[wib][lane] : make_uint2(0, 0);
+    const uint32_t tok = have ? q_tok[lane] : 0u;
     __syncwarp();
-    stage_b(have, c, mt);
+    stage_a(have, tok);
   }
   if (rqueued) {
     const bool have = lane < rqueued;
