@@ -39,6 +39,16 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")      # the reference
 PORT_BIN = os.path.join(ROOT, "oracle", "dicey_oracle")          # the plain C++ restatement ("kind": "port")
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_binary():
     """(path, kind) of the CPU comparator: the reference compiled from its own sources when it was
     built (oracle/_ref), otherwise the oracle port; (None, None) if neither exists."""
@@ -69,6 +79,7 @@ def parse_args():
     ap.add_argument("--ramp", type=int, default=60, help="extra untimed resident steps after the W warm-up steps (clock ramp); "
                     "a fixed count, identical on every rank, because every step holds a collective")
     ap.add_argument("--ramp-e2e", type=int, default=25, help="the same for the end-to-end arm")
+    ap.add_argument("--skip-resident", action="store_true", help="(experiments) run the end-to-end arm only")
     ap.add_argument("--gather-to-host", action="store_true", help="N > 1: rank 0 also copies the gathered coordinate table "
                     "of all ranks to its host inside every end-to-end step")
     return ap.parse_args()
@@ -274,7 +285,7 @@ def main_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop_s / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args), "threads": cores},
-        "cpu_baseline": {"value": value, "unit": "primers/s", "cores": cores, "kind": ref_kind, "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "primers/s", "cores": cores, "cpu_model": cpu_model(), "kind": ref_kind, "sample": sample_desc},
         "e2e": {"value": value, "unit": "primers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -348,7 +359,7 @@ def main_b200(args):
     # generated on the host and needs a few hundred ms of load to come back to its boost clock.  (A
     # wall-clock bound here would let ranks run different numbers of steps -- and every step holds a
     # collective.)
-    for i in range(args.warmup + args.ramp):
+    for i in range(2 if args.skip_resident else args.warmup + args.ramp):
         resident_step(batch)
     dog.mark("resident warm-up done")
     ix.profile(True)
@@ -358,7 +369,7 @@ def main_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     profs = []
-    for _ in range(args.steps):
+    for _ in range(1 if args.skip_resident else args.steps):
         resident_step(batch)
         profs.append(ix.last_profile())
         sampler.sample()         # right after the step's synchronisation: the clock it ran at
@@ -437,7 +448,7 @@ def main_b200(args):
             cores = os.cpu_count() or 1
             r, n, ref_records = cpu_leg(fm9, rec, primers, args, cores, args.cpu_seconds)
             parity = parity_check(ix, params, primers, n, ref_records)
-            cpu = {"value": r["queries_per_s"], "unit": "primers/s", "cores": cores, "kind": cpu_binary()[1],
+            cpu = {"value": r["queries_per_s"], "unit": "primers/s", "cores": cores, "cpu_model": cpu_model(), "kind": cpu_binary()[1],
                    "sample": f"first {n} primers of the batch on the same 3 Gb index ({r['loop_s']:.1f} s loop, index load excluded)"}
             work = {k: r[k] / r["queries"] for k in ("R", "L", "H", "X", "strings", "steps")} if "R" in r else None
             try:
@@ -456,33 +467,58 @@ def main_b200(args):
             work = None
 
     ms_search = float(np.mean([p["ms_search"] for p in profs])) if profs else None
+    ms_probe = float(np.mean([p["ms_probe"] for p in profs])) if profs else 0.0
+    scripts = float(np.mean([p["scripts"] for p in profs])) if profs else 0.0
     roof = None
-    if work and ms_search:
-        # k_search replaces neighbors() x sdsl::count: its share of SURVEY.md 8(d) is the rank
-        # term 32 R (L, H, X belong to k_locate / k_verify and are reported beside it)
-        alg = 32 * work["R"] * nq
-        achieved = alg / (ms_search / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_search_packed", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": None,
-                "algorithmic_bytes_per_primer": alg / nq,
-                "algorithmic_bytes_per_primer_all_kernels": 32 * work["R"] + 32 * work["L"] + 4 * work["H"] + work["X"],
-                "kernel_ms": ms_search, "kernel_share_of_step": ms_search / (ms / args.steps),
-                "note": "algorithmic bytes = 32 B x the reference's rank queries (one per backward-search step of every "
-                        "neighbour string, counted by the instrumented reference in this run); the presence bitmap and the "
-                        "K-mer interval table answer most of them without DRAM, so frac > 1 is expected; traffic = DRAM "
-                        "bytes per launch of the same kernel from ncu --set full (profiles/), frac_dram = traffic / "
-                        "kernel time / peak; kernel_ms is the CUDA-event time of the search stage (k_search_packed plus "
-                        "the general k_search, which has no work on an ACGT-only batch)"}
+    if ms_search:
+        # The dominant kernel of the step is k_probe_singles (one presence-bitmap probe per neighbour string;
+        # its CUDA-event time is taken live: dg_profile.ms_probe).  `achieved` = the DRAM bytes one launch
+        # moves (ncu --set full of the same command, profiles/k_search_traffic.json, regenerated by
+        # tools/make_traffic_json.py) / that time; `frac` = achieved / the measured copy peak.  Beside it:
+        # the algorithmic figure (one 32-byte sector per probe), the probe rate against the random-gather
+        # ceiling of tools/gather_bench2.cu (profiles/gather_ceiling.json), DRAM sectors demanded (L1 and L2
+        # misses) against sectors fetched, and the SURVEY.md 8(d) number of the reference's own work
+        # (32 B x its rank queries) as `reference_work_ratio` -- the tables answer most of those queries
+        # without DRAM, so that one says how much work the design avoids, not how close a kernel is to a limit.
+        dom_ms = ms_probe if ms_probe > 0 else ms_search
+        dom = "k_probe_singles" if ms_probe > 0 else "k_search_packed"
+        roof = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak_gbs, "unit": "GB/s", "frac": None,
+                "peak_source": peak_src, "traffic": None, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / (ms / args.steps),
+                "search_stage_ms": ms_search, "probes_per_launch": scripts,
+                "algorithmic_bytes_per_launch": 32.0 * scripts,
+                "algorithmic_achieved": 32.0 * scripts / (dom_ms / 1e3) / 1e9,
+                "algorithmic_frac": 32.0 * scripts / (dom_ms / 1e3) / 1e9 / peak_gbs,
+                "probes_per_s": scripts / (dom_ms / 1e3)}
         tr = os.path.join(ROOT, "profiles", "k_search_traffic.json")
         if os.path.exists(tr):
             try:
                 t_ = json.load(open(tr))
-                if (t_.get("kmer") == info["kmer"] and t_.get("bitmap_k") == info["bitmap_k"] and t_.get("primers") == nq
+                k_ = t_.get("kernels", {}).get(dom)
+                if (k_ and t_.get("kmer") == info["kmer"] and t_.get("bitmap_k") == info["bitmap_k"] and t_.get("primers") == nq
                         and t_.get("index_device_bytes") == info["device_bytes"] and not args.hamming and args.distance == 1):
-                    roof["traffic"] = t_.get("dram_bytes_per_launch")
-                    roof["frac_dram"] = roof["traffic"] / (ms_search / 1e3) / 1e9 / peak_gbs
+                    roof["traffic"] = k_["dram_bytes"]
+                    roof["achieved"] = k_["dram_bytes"] / (dom_ms / 1e3) / 1e9
+                    roof["frac"] = roof["achieved"] / peak_gbs
+                    roof["dram_sectors_fetched"] = k_["dram_sectors_read"]
+                    if k_.get("l1_sectors") and k_.get("l1_hit_pct") is not None and k_.get("l2_hit_pct") is not None:
+                        roof["dram_sectors_demanded"] = k_["l1_sectors"] * (1 - k_["l1_hit_pct"] / 100) * (1 - k_["l2_hit_pct"] / 100)
+                    roof["traffic_source"] = t_.get("source")
             except Exception:
                 pass
+        if roof["achieved"] is None:   # no capture for this configuration: the algorithmic figure stands in
+            roof["achieved"], roof["frac"] = roof["algorithmic_achieved"], roof["algorithmic_frac"]
+            roof["note"] = "no ncu capture for this configuration: achieved = 32 B per probe / kernel time"
+        gc = os.path.join(ROOT, "profiles", "gather_ceiling.json")
+        if os.path.exists(gc):
+            try:
+                g_ = json.load(open(gc))
+                roof["gather_ceiling_per_s"] = g_["gathers_per_s"]
+                roof["frac_gather"] = roof["probes_per_s"] / g_["gathers_per_s"]
+            except Exception:
+                pass
+        if work:
+            roof["reference_work_ratio"] = 32 * work["R"] * nq / (ms_search / 1e3) / 1e9 / peak_gbs
+            roof["reference_bytes_per_primer"] = 32 * work["R"] + 32 * work["L"] + 4 * work["H"] + work["X"]
     if rank == 0:
         stage = {k: float(np.mean([p[k] for p in profs])) for k in ("ms_prepare", "ms_search", "ms_filter", "ms_locate", "ms_verify", "ms_total")}
         line = {
@@ -492,7 +528,7 @@ def main_b200(args):
             "config": {"workload": workload_name(args), "parallelism": f"index replicated x{world}, primers sharded by rank" + (", one ncclAllGather of the 16-byte hit records per step on the index stream (dg_allgather_hits)" if world > 1 else ""),
                        "gathered_hits_per_step": gathered[0] if world > 1 else None,
                        "e2e_gather_to_host": bool(args.gather_to_host) if world > 1 else None,
-                       "global_primers_per_step": world * nq, "l2": f"inputs larger than L2: random access into {info['device_bytes'] / 1e9:.0f} GB of index tables",
+                       "global_primers_per_step": world * nq, "l2": f"inputs larger than L2: random access into {info['device_bytes'] / 1e9:.0f} GB of index tables (the same staged batch every step; a step moves ~8 GB of DRAM traffic through the 126 MB L2)",
                        "kmer_table_K": info["kmer"], "presence_bitmap_K": info["bitmap_k"], "index_device_bytes": info["device_bytes"],
                        "index_build_s": build_s, "hits_per_step": nhits, "candidates_per_step": ncand},
             "clocks": clocks,

@@ -46,7 +46,7 @@ class _Profile(C.Structure):
     _fields_ = [("ms_prepare", C.c_float), ("ms_search", C.c_float), ("ms_filter", C.c_float),
                 ("ms_locate", C.c_float), ("ms_verify", C.c_float), ("ms_total", C.c_float),
                 ("launches", C.c_uint64), ("scripts", C.c_uint64), ("candidates", C.c_uint64),
-                ("located", C.c_uint64), ("hits", C.c_uint64)]
+                ("located", C.c_uint64), ("hits", C.c_uint64), ("ms_probe", C.c_float), ("reserved", C.c_float)]
 
 
 HIT_DTYPE = np.dtype([("query", "<u4"), ("score", "<i4"), ("chr", "<u4"), ("start", "<u4"), ("text_pos", "<u8"),

@@ -77,6 +77,7 @@ struct ProfileState {
   bool created = false;
   dg_profile last = {};
   uint64_t launches = 0;
+  bool probe_timed = false;
 };
 
 }  // namespace dg

@@ -166,6 +166,26 @@ struct ABuf {  // stream-ordered allocation through the stream's block cache
 
 inline unsigned grid_for(uint64_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
 
+// Waiting for a stream.  cudaStreamSynchronize spins (lowest latency: one process per box); with one
+// process per GPU and several pipeline threads each, spinning waiters outnumber the cores, so
+// DG_SYNC=block makes a waiter sleep on a blocking event instead.
+inline cudaError_t sync_stream(cudaStream_t st) {
+  static const bool block = getenv("DG_SYNC") && std::string(getenv("DG_SYNC")) == "block";
+  if (!block) return cudaStreamSynchronize(st);
+  thread_local cudaEvent_t ev = nullptr;
+  thread_local int ev_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!ev || ev_dev != dev) {
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    ev_dev = dev;
+  }
+  cudaError_t e = cudaEventRecord(ev, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev);
+}
+
 __device__ __forceinline__ uint8_t norm_base(uint8_t ch) {
   if (ch >= 'a' && ch <= 'z') ch -= 32;
   return (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T') ? ch : (uint8_t)'N';
@@ -180,6 +200,7 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   if (q >= b.nq) return;
   uint64_t o = b.off[q];
   int L = (int)(b.off[q + 1] - o);
+  bool changed = false;   // normalisation altered the sequence (lower case, non-ACGT): irregular bit 3
   if (((o | (uint64_t)L) & 3) == 0) {
     // word path (offsets and length multiples of 4, e.g. batches of 20-mers): 4 bases per access
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + o);
@@ -191,12 +212,14 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
       const uint8_t c0 = norm_base((uint8_t)w), c1 = norm_base((uint8_t)(w >> 8)), c2 = norm_base((uint8_t)(w >> 16)),
                     c3 = norm_base((uint8_t)(w >> 24));
       fw[j] = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16) | ((uint32_t)c3 << 24);
+      changed |= fw[j] != w;
       cw[nw - 1 - j] = (uint32_t)comp_base(c3) | ((uint32_t)comp_base(c2) << 8) | ((uint32_t)comp_base(c1) << 16) |
                        ((uint32_t)comp_base(c0) << 24);
     }
   } else {
     for (int i = 0; i < L; ++i) {
       uint8_t ch = norm_base(raw[o + i]);
+      changed |= ch != raw[o + i];
       fwd[o + i] = ch;
       rc[o + L - 1 - i] = comp_base(ch);
     }
@@ -253,6 +276,7 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   // packed queries are searched by k_search_packed; k_search takes the rest
   units[q] = (run && !packed) ? (uint64_t)ut.tab_cnt[variant * 256 + m] * (b.reverse ? 2 : 1) : 0;
   if (!run || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
+  if (changed) atomicOr(b.irregular, 8u);
 }
 
 // One thread per query still flagged DG_Q_NBR_UNVERIFIED: the bound of dg_core.cuh (nbr_upper_bound_closed)
@@ -1920,10 +1944,7 @@ struct dg_batch {
   int max_len = 0, min_len = 0;
   uint64_t uniform_host_len = 0;        // the caller's offsets, for the result: one length, or a copy
   std::vector<uint64_t> host_off;
-  // chunk pipeline: the normalised sequences leave for the host as soon as k_prepare has written them
-  cudaEvent_t ev_prepared = nullptr;
-  cudaStream_t seq_stream = nullptr;
-  void* seq_dst = nullptr;
+  uint32_t h_irregular = 0;             // host copy of *irregular after the search stage (bit 3: normalisation changed a sequence)
   // outputs of run()
   ABuf<Cand> cands;
   uint32_t ncand = 0;
@@ -2114,7 +2135,7 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
       DG_CUDA(cudaMemcpyAsync(b->off.p, offsets, ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
     }
     // the copies above read caller memory: finish them before returning ownership
-    if (!d_seqs || !equal_len) DG_CUDA(cudaStreamSynchronize(st));
+    if (!d_seqs || !equal_len) DG_CUDA(sync_stream(st));
     if (trace) fprintf(stderr, "[dg_batch_stage] scan+tables %.3f ms, allocs %.3f ms, copies %.3f ms\n", ts1 - ts0, ts2 - ts1, now() - ts2);
     *out = b;
     return DG_OK;
@@ -2134,7 +2155,7 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
   try {
     uint32_t irr = 0;
     DG_CUDA(cudaMemcpyAsync(&irr, b->irregular.p, 4, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(sync_stream(st));
     if (!(irr & 6u)) return DG_OK;
     const uint32_t nq = b->nq;
     const bool indel = b->par.indel != 0;
@@ -2146,7 +2167,7 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
     DG_CUDA(cudaMemcpyAsync(dist.data(), b->dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(off.data(), b->off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (b->nbytes) DG_CUDA(cudaMemcpyAsync(fwd.data(), b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(sync_stream(st));
     const uint32_t want = indel ? (uint32_t)DG_Q_NBR_UNVERIFIED : (uint32_t)DG_Q_NBR_CAP;
     std::vector<uint32_t> flagged;
     for (uint32_t q = 0; q < nq; ++q)
@@ -2226,7 +2247,7 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
       DG_CUDA(cudaMemcpyAsync(b->trunc_off.p, loff.data(), loff.size() * 4, cudaMemcpyHostToDevice, st));
       if (!keys.empty()) DG_CUDA(cudaMemcpyAsync(b->trunc_keys.p, keys.data(), keys.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice, st));
     }
-    DG_CUDA(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    DG_CUDA(sync_stream(st));   // the host vectors above go out of scope
     return DG_OK;
   } catch (CudaFail& e) {
     return e.code;
@@ -2275,11 +2296,6 @@ static int run_impl(dg_batch* b) {
     DG_CUDA(cudaMemsetAsync(b->units.p, 0, ((size_t)nq + 1) * 8, st));
     DG_CUDA(cudaMemsetAsync(b->irregular.p, 0, 4, st));
     if (nq) { k_prepare<<<grid_for(nq, B), B, 0, st>>>(b->raw.p, bd, b->fwd.p, b->rc.p, ut, b->units.p); ++launches; }
-    if (b->seq_dst && b->nbytes) {
-      DG_CUDA(cudaEventRecord(b->ev_prepared, st));
-      DG_CUDA(cudaStreamWaitEvent(b->seq_stream, b->ev_prepared, 0));
-      DG_CUDA(cudaMemcpyAsync(b->seq_dst, b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, b->seq_stream));
-    }
     {
       size_t tb = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tb, b->units.p, b->unit_off.p, (int)(nq + 1), st);
@@ -2314,6 +2330,7 @@ static int run_impl(dg_batch* b) {
     const int nsm = geo.nsm, general_per_sm = geo.general_per_sm;
     unsigned int hc[2] = {0, 0};
     unsigned long long h_scripts = 0;
+    bool probe_timed = false;
     for (int attempt = 0; attempt < 2; ++attempt) {
       b->cands.alloc(cap64, st);
       DG_CUDA(cudaMemsetAsync(ctr.p, 0, 8, st));
@@ -2358,13 +2375,13 @@ static int run_impl(dg_batch* b) {
           ABuf<uint8_t> m1;
           m1.alloc(n1 + 8, st);
           const unsigned rblocks = (unsigned)std::min<uint64_t>((uint64_t)nsm * 8, (n1 / 4 + 255) / 256 + 1);
-          if (indel) {
-            k_probe_singles<true><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
-            k_resolve<true><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
-          } else {
-            k_probe_singles<false><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
-            k_resolve<false><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
-          }
+          if (attempt == 0) prof_mark(ix, 6, st);
+          if (indel) k_probe_singles<true><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
+          else k_probe_singles<false><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
+          if (attempt == 0) prof_mark(ix, 7, st);
+          if (indel) k_resolve<true><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
+          else k_resolve<false><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
+          probe_timed = true;
           launches += 2;
           if (ud >= 2) {
             // pairs of events: ~13 k scripts per string; tiles of pairs keep the result bytes at <= 256 MB
@@ -2394,7 +2411,8 @@ static int run_impl(dg_batch* b) {
       if (attempt == 0) prof_mark(ix, 2, st);
       DG_CUDA(cudaMemcpyAsync(hc, ctr.p, 8, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaMemcpyAsync(&h_scripts, nscripts.p, 8, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaStreamSynchronize(st));
+      DG_CUDA(cudaMemcpyAsync(&b->h_irregular, b->irregular.p, 4, cudaMemcpyDeviceToHost, st));
+      DG_CUDA(sync_stream(st));
       DG_CUDA(cudaGetLastError());
       if (!hc[1]) break;
       // more neighbour strings matched than the buffer holds (repeat-rich queries): the counter
@@ -2453,7 +2471,7 @@ static int run_impl(dg_batch* b) {
         unsigned int h_big = 0;
         DG_CUDA(cudaMemcpyAsync(&n3, nsel.p, 4, cudaMemcpyDeviceToHost, st));
         DG_CUDA(cudaMemcpyAsync(&h_big, big.p, 4, cudaMemcpyDeviceToHost, st));
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(sync_stream(st));
         launches += 9;
         if (!(by_group && h_big)) break;   // a group beyond kGroupMax: once more with the full key
       }
@@ -2475,7 +2493,7 @@ static int run_impl(dg_batch* b) {
         launches += 3;
         uint32_t n2 = 0;
         DG_CUDA(cudaMemcpyAsync(&n2, nsel.p, 4, cudaMemcpyDeviceToHost, st));
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(sync_stream(st));
         // result now in c2; keep b->cands as the other buffer
         cur = c2.p;
         n = n2;
@@ -2496,7 +2514,7 @@ static int run_impl(dg_batch* b) {
         launches += 3;
         uint32_t n3 = 0;
         DG_CUDA(cudaMemcpyAsync(&n3, nsel.p, 4, cudaMemcpyDeviceToHost, st));
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(sync_stream(st));
         if (other == c3.p) {
           // final list must outlive this scope: move it into b->cands
           DG_CUDA(cudaMemcpyAsync(b->cands.p, c3.p, (size_t)n3 * sizeof(Cand), cudaMemcpyDeviceToDevice, st));
@@ -2561,7 +2579,7 @@ static int run_impl(dg_batch* b) {
       cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, (uint64_t*)b->qhits.p, b->qoff.p, (int)(nq + 1), st);
       launches += 2;
     }
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(sync_stream(st));
     uint64_t loc_cap = 1ULL << 28;   // located rows held at once (8-byte keys, two buffers)
     if (const char* e = getenv("DG_LOCATE_CAP")) loc_cap = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
     // Batches whose candidates hold more rows than that (repeat-rich queries: the reference locates
@@ -2574,7 +2592,7 @@ static int run_impl(dg_batch* b) {
       h_hit.resize((size_t)n + 1);
       DG_CUDA(cudaMemcpyAsync(h_loc.data(), loc_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
       DG_CUDA(cudaMemcpyAsync(h_hit.data(), hit_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaStreamSynchronize(st));
+      DG_CUDA(sync_stream(st));
       uint32_t c0 = 0;
       while (c0 < n) {
         uint32_t c1 = c0 + 1;
@@ -2672,7 +2690,7 @@ static int run_impl(dg_batch* b) {
     } else {
       unsigned long long used = 0;
       DG_CUDA(cudaMemcpyAsync(&used, cursor.p, 8, cudaMemcpyDeviceToHost, st));
-      DG_CUDA(cudaStreamSynchronize(st));
+      DG_CUDA(sync_stream(st));
       b->pool_bytes = used;
     }
     prof_mark(ix, 5, st);
@@ -2691,6 +2709,7 @@ static int run_impl(dg_batch* b) {
       ix->prof.last.candidates = n_candidates;
       ix->prof.last.located = nlocate;
       ix->prof.last.hits = nhits;
+      ix->prof.probe_timed = probe_timed;
     }
     return DG_OK;
   } catch (CudaFail& e) {
@@ -2709,6 +2728,8 @@ static void prof_collect(dg_index* ix) {
   ix->prof.last.ms_locate = ms[3];
   ix->prof.last.ms_verify = ms[4];
   cudaEventElapsedTime(&ix->prof.last.ms_total, ix->prof.ev[0], ix->prof.ev[5]);
+  ix->prof.last.ms_probe = 0;
+  if (ix->prof.probe_timed) cudaEventElapsedTime(&ix->prof.last.ms_probe, ix->prof.ev[6], ix->prof.ev[7]);
   ix->prof.last.launches = ix->prof.launches;
 }
 
@@ -2750,7 +2771,7 @@ static int fetch_impl(dg_batch* b, dg_result** out) {
       r->transfer_bytes = b->nhits * sizeof(dg_hit) + b->pool_bytes + ((size_t)nq + 1) * 8 + (size_t)nq * 8 + b->nbytes;
     }
     if (b->nbytes) DG_CUDA(cudaMemcpyAsync(r->seqs.p, b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(sync_stream(st));
     if (b->host_off.size() == (size_t)nq + 1) keep_offsets(r, b->host_off.data(), nq);
     else if (b->uniform_host_len) r->uniform_len = b->uniform_host_len;
     prof_collect(ix);
@@ -2825,8 +2846,9 @@ struct ChunkPipe {
   int nworkers = 2;
   uint32_t next_commit = 0;      // chunks are committed (final offsets assigned) in order
   const uint8_t* d_up = nullptr; // the caller's sequences in device memory, chunk c valid once uploaded > c
-  std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev, prepared_ev;   // per chunk, from the index's event pool
+  std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev;   // per chunk, from the index's event pool
   uint32_t uploaded = 0;
+  uint32_t seq_copied = 0;           // chunks whose sequence bytes the uploader has copied into the result (host)
   std::vector<uint64_t> chunk_len;   // per chunk: the common query length, or 0 (set before `uploaded` passes the chunk)
   PeerOut peer;                      // peer mode of a bound communicator (compact results only)
   uint64_t hit_base = 0, pool_base = 0;
@@ -2882,9 +2904,6 @@ struct ChunkPipe {
         dg_batch* b = nullptr;
         int rc1 = stage_impl(idx, seqs + offsets[q0], so.data(), cn, params, &b, st, d_up + offsets[q0], up_ev[c], false, uniform_L);
         if (rc1) { fail(rc1, last_error_ref()); break; }
-        b->ev_prepared = prepared_ev[c];
-        b->seq_stream = cs;
-        b->seq_dst = (uint8_t*)r->seqs.p + offsets[q0];
         cudaEvent_t copied = copied_ev[c];
         live.push_back(Live{b, copied});
         tm[3] = now() - t_begin;
@@ -2931,7 +2950,7 @@ struct ChunkPipe {
         if (compact) {
           if (b->nhits) DG_CUDA(cudaMemcpyAsync((uint8_t*)r->recs.p + hit_base * sizeof(dg_rec), b->recs.p, b->nhits * sizeof(dg_rec), cudaMemcpyDeviceToHost, cs));
           if (cn) DG_CUDA(cudaMemcpyAsync((uint16_t*)r->qmeta.p + q0, b->qmeta.p, (size_t)cn * 2, cudaMemcpyDeviceToHost, cs));
-          r->transfer_bytes += b->nhits * sizeof(dg_rec) + (size_t)cn * 2 + b->nbytes;
+          r->transfer_bytes += b->nhits * sizeof(dg_rec) + (size_t)cn * 2;
         } else {
           if (b->nhits) {
             DG_CUDA(cudaMemcpyAsync((uint8_t*)r->hits.p + hit_base * sizeof(dg_hit), b->hits.p, b->nhits * sizeof(dg_hit), cudaMemcpyDeviceToHost, cs));
@@ -2942,9 +2961,17 @@ struct ChunkPipe {
             DG_CUDA(cudaMemcpyAsync((uint32_t*)r->status.p + q0, b->status.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
             DG_CUDA(cudaMemcpyAsync((uint32_t*)r->dist.p + q0, b->dist.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, cs));
           }
-          r->transfer_bytes += b->nhits * sizeof(dg_hit) + b->pool_bytes + (size_t)cn * 16 + b->nbytes;
+          r->transfer_bytes += b->nhits * sizeof(dg_hit) + b->pool_bytes + (size_t)cn * 16;
         }
-        // (the normalised sequences left right after k_prepare: run_impl, seq_dst)
+        // the normalised sequences: the uploader thread copies the caller's bytes into the result on the
+        // host; only a chunk in which normalisation changed something (lower case, non-ACGT) sends its
+        // device copy afterwards
+        if (cn && b->nbytes && (b->h_irregular & 8u)) {
+          cv.wait(lk, [&] { return seq_copied > c || rc != DG_OK; });
+          if (rc != DG_OK) break;
+          DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
+          r->transfer_bytes += b->nbytes;
+        }
         DG_CUDA(cudaEventRecord(copied, cs));
         hit_base += b->nhits;
         pool_base += b->pool_bytes;
@@ -3040,7 +3067,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     if (!idx->up_stream) DG_CUDA(cudaStreamCreateWithFlags(&idx->up_stream, cudaStreamNonBlocking));
     if (idx->upload.count < offsets[nq] + 1) idx->upload.alloc(offsets[nq] + (offsets[nq] >> 3) + 4096);
     p.d_up = idx->upload.p;
-    while (idx->ev_pool.size() < 4 * (size_t)nchunks) {
+    while (idx->ev_pool.size() < 3 * (size_t)nchunks) {
       cudaEvent_t e;
       DG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       idx->ev_pool.push_back(e);
@@ -3049,7 +3076,6 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     p.up_ev.assign(idx->ev_pool.begin(), idx->ev_pool.begin() + nchunks);
     p.copied_ev.assign(idx->ev_pool.begin() + nchunks, idx->ev_pool.begin() + 2 * (size_t)nchunks);
     p.rebased_ev.assign(idx->ev_pool.begin() + 2 * (size_t)nchunks, idx->ev_pool.begin() + 3 * (size_t)nchunks);
-    p.prepared_ev.assign(idx->ev_pool.begin() + 3 * (size_t)nchunks, idx->ev_pool.begin() + 4 * (size_t)nchunks);
     std::vector<std::thread> others;
     for (int w = 0; w < p.nworkers; ++w) others.emplace_back([&p, w] { p.worker(w); });
     try {
@@ -3083,6 +3109,15 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     } catch (CudaFail& e) {
       p.fail(e.code, last_error_ref());
     }
+    // the result's copy of the sequences (the normalised form equals the input unless a chunk says otherwise)
+    for (uint32_t c = 0; c < nchunks && p.rc == DG_OK; ++c) {
+      const uint64_t b0 = offsets[p.bounds[c]], b1 = offsets[p.bounds[c + 1]];
+      if (b1 > b0) memcpy((uint8_t*)r->seqs.p + b0, seqs + b0, b1 - b0);
+      { std::lock_guard<std::mutex> g(p.mu); p.seq_copied = c + 1; }
+      p.cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> g(p.mu); p.seq_copied = nchunks; }
+    p.cv.notify_all();
     const double tt0 = now();
     keep_offsets(r, offsets, nq);   // (the calling thread has nothing else to do while the workers run)
     const double tt1 = now();
@@ -3185,7 +3220,7 @@ int dg_backward_search_batch(dg_index* idx, const char* seqs, const uint64_t* of
     if (nq) k_backward_search<<<grid_for(nq, 128), 128, 0, st>>>(idx->view(), d_s.p, d_off.p, nq, d_l.p, d_r.p);
     DG_CUDA(cudaMemcpyAsync(l, d_l.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(r, d_r.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(sync_stream(st));
     DG_CUDA(cudaGetLastError());
     return DG_OK;
   } catch (CudaFail& e) {

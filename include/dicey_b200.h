@@ -118,6 +118,8 @@ typedef struct {
   uint64_t candidates;/* neighbour strings with a non-empty SA interval                */
   uint64_t located;   /* text positions located                                        */
   uint64_t hits;      /* hits emitted                                                  */
+  float ms_probe;     /* k_probe_singles alone (the dominant kernel of a regular batch; part of ms_search) */
+  float reserved;
 } dg_profile;
 
 /* ---- index ------------------------------------------------------------------------ */
