@@ -555,13 +555,28 @@ struct ProbeAddr {
   uint32_t bit;     // bit inside the word
   uint32_t state;
 };
+// the window of one string length, picked once for all the strings of that length
+struct WinSel {
+  const uint32_t* bm;
+  const uint32_t* bml;
+  int kb;
+  int cls;
+};
+__device__ __forceinline__ WinSel win_select(const PackedArgs& a, int L) {
+  WinSel w;
+  w.cls = L - a.KB + 1;
+  const int c = w.cls > 2 ? 2 : (w.cls < 0 ? 0 : w.cls);
+  w.bm = c == 2 ? a.win_r[2] : (c == 1 ? a.win_r[1] : a.win_r[0]);
+  w.bml = c == 2 ? a.win_l[2] : (c == 1 ? a.win_l[1] : a.win_l[0]);
+  w.kb = c == 2 ? a.win_k[2] : (c == 1 ? a.win_k[1] : a.win_k[0]);
+  return w;
+}
 template <bool OTHER = false>   // OTHER: the window at the opposite end (the second opinion of the slow path)
-__device__ __forceinline__ ProbeAddr presence_addr(const PackedArgs& a, uint64_t code, int L, int p_left) {
-  const int cls = L - a.KB + 1;
-  const int c = cls > 2 ? 2 : (cls < 0 ? 0 : cls);
-  const uint32_t* bm = c == 2 ? a.win_r[2] : (c == 1 ? a.win_r[1] : a.win_r[0]);
-  const uint32_t* bml = c == 2 ? a.win_l[2] : (c == 1 ? a.win_l[1] : a.win_l[0]);
-  const int kb = c == 2 ? a.win_k[2] : (c == 1 ? a.win_k[1] : a.win_k[0]);
+__device__ __forceinline__ ProbeAddr presence_addr(const PackedArgs& a, const WinSel& ws, uint64_t code, int L, int p_left) {
+  const int cls = ws.cls;
+  const uint32_t* bm = ws.bm;
+  const uint32_t* bml = ws.bml;
+  const int kb = ws.kb;
   const uint64_t wmask = (1ULL << (2 * kb)) - 1ULL;
   const int sr = 2 * (L - kb);
   const uint64_t bit_l = presence_bit_left((code >> (sr > 0 ? sr : 0)) & wmask, kb);
@@ -595,11 +610,12 @@ template <bool INDEL>
 __device__ __forceinline__ uint32_t probe_site(const PackedArgs& a, const EditSite& site, int L1, int p_left, bool have) {
   constexpr int S = INDEL ? 8 : 3;
   ProbeAddr pa[S];
+  const WinSel w0 = win_select(a, L1), wm = INDEL ? win_select(a, L1 - 1) : w0, wp = INDEL ? win_select(a, L1 + 1) : w0;
 #pragma unroll
   for (int kk = 0; kk < S; ++kk) {
     int dL, kc;
     const uint64_t code = edit_apply<INDEL>(site, kk, dL, kc);
-    pa[kk] = presence_addr(a, code, L1 + dL, p_left);
+    pa[kk] = presence_addr(a, (!INDEL || kk < 3) ? w0 : (kk == 3 ? wm : wp), code, L1 + dL, p_left);
   }
   uint32_t w[S];
 #pragma unroll
@@ -613,7 +629,7 @@ __device__ __forceinline__ uint32_t probe_site(const PackedArgs& a, const EditSi
   return have ? mask : 0u;
 }
 __device__ __forceinline__ bool presence_probe(const PackedArgs& a, uint64_t code, int L, int p_left) {
-  const ProbeAddr pa = presence_addr(a, code, L, p_left);
+  const ProbeAddr pa = presence_addr(a, win_select(a, L), code, L, p_left);
   if (pa.state) return pa.state == 1;
   return (ld_probe(pa.word) >> pa.bit) & 1u;
 }
@@ -629,7 +645,7 @@ __device__ __forceinline__ bool second_opinion(const PackedArgs& a, uint64_t cod
   const int L = (int)(meta.y >> 27);
   const int nev = (int)((meta.y >> 1) & 3u);
   const int p_left = nev ? (int)((meta.y >> 3) & 0xFFFu) / cs : 0;
-  const ProbeAddr pa = presence_addr<true>(a, code, L, p_left);
+  const ProbeAddr pa = presence_addr<true>(a, win_select(a, L), code, L, p_left);
   return pa.state != 0 || ((ld_probe(pa.word) >> pa.bit) & 1u);
 }
 __device__ __noinline__ void resolve_chain(const IndexView& ix, const SearchOut& out, bool have, uint64_t code, uint2 meta) {
@@ -885,7 +901,7 @@ __device__ __forceinline__ void pair_slot(uint32_t u, int m, int& p1, int& k1i, 
 }
 
 template <bool INDEL>
-__global__ void __launch_bounds__(256, 5) k_probe_singles(const __grid_constant__ PackedArgs a, const __grid_constant__ ProbeShape sh,
+__global__ void __launch_bounds__(256, 6) k_probe_singles(const __grid_constant__ PackedArgs a, const __grid_constant__ ProbeShape sh,
                                                           uint8_t* __restrict__ masks) {
   if (*sh.irregular & 1u) return;
   const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
