@@ -687,6 +687,103 @@ __device__ __noinline__ void resolve_chain(const IndexView& ix, const SearchOut&
   }
 }
 
+#ifdef DG_RESOLVE_ASYNC
+// EXPERIMENT (north_star: "occ blocks staged through TMA into shared memory").
+// The backward search of one string is a chain of dependent steps: the blocks of step t + 1 are only
+// known once step t is done, so there is nothing to prefetch WITHIN a chain.  What asynchronous
+// staging can buy is a second, independent chain per lane: two batches of 32 queued strings advance
+// in lockstep, every step issues the l- and r-block of both batches as cp.async (LDGSTS) copies into
+// a per-warp shared-memory slab and only then waits -- twice the requests in flight per warp, the
+// rank arithmetic on shared memory.  Measured against the plain version in DESIGN.md section 4.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+struct Chain {
+  uint64_t code;
+  uint2 meta;
+  uint32_t l, r;
+  int t, L;
+  bool alive;
+};
+__device__ __noinline__ void resolve_chain2(const IndexView& ix, const SearchOut& out, uint4 (*slab)[4], bool haveA, uint64_t codeA, uint2 metaA,
+                                            bool haveB, uint64_t codeB, uint2 metaB) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int K = (int)ix.K;
+  const uint32_t kmask = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
+  Chain ch[2];
+  ch[0].code = codeA; ch[0].meta = metaA; ch[1].code = codeB; ch[1].meta = metaB;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const bool have = b ? haveB : haveA;
+    ch[b].L = (int)(ch[b].meta.y >> 27);
+    ch[b].l = 0; ch[b].r = (uint32_t)ix.n; ch[b].t = 0;
+    if (have && ch[b].L >= K) {
+      const uint2 iv = __ldg(&ix.kmer[(uint32_t)ch[b].code & kmask]);
+      ch[b].l = iv.x; ch[b].r = iv.y; ch[b].t = K;
+    }
+    ch[b].alive = have && ch[b].l < ch[b].r;
+  }
+  uint4* mine = &slab[lane][0];   // [0..1] batch A: l-block planes, r-block planes; [2..3] batch B (counts come by plain loads)
+  for (;;) {
+    const bool goA = ch[0].alive && ch[0].t < ch[0].L, goB = ch[1].alive && ch[1].t < ch[1].L;
+    if (!__any_sync(FULL, goA || goB)) break;
+    uint32_t cl[2] = {0, 0}, cr[2] = {0, 0};
+    int cc[2] = {0, 0};
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool go = b ? goB : goA;
+      if (go) {
+        cc[b] = (int)((ch[b].code >> (2 * ch[b].t)) & 3);
+        const OccBlock* pl = ix.occ + (ch[b].l >> 6);
+        const OccBlock* pr = ix.occ + (ch[b].r >> 6);
+        cp_async16(&mine[2 * b], reinterpret_cast<const uint4*>(pl) + 1);
+        cp_async16(&mine[2 * b + 1], reinterpret_cast<const uint4*>(pr) + 1);
+        cl[b] = __ldg(&pl->cnt[cc[b]]);
+        cr[b] = __ldg(&pr->cnt[cc[b]]);
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool go = b ? goB : goA;
+      if (go) {
+        const uint4 wl = mine[2 * b], wr = mine[2 * b + 1];
+        const uint32_t c4 = ix.C4[cc[b]];
+        const uint32_t nl = c4 + cl[b] + rank_planes(ix, ((uint64_t)wl.y << 32) | wl.x, ((uint64_t)wl.w << 32) | wl.z, ch[b].l, cc[b]);
+        const uint32_t nr = c4 + cr[b] + rank_planes(ix, ((uint64_t)wr.y << 32) | wr.x, ((uint64_t)wr.w << 32) | wr.z, ch[b].r, cc[b]);
+        ch[b].l = nl; ch[b].r = nr; ++ch[b].t;
+        ch[b].alive = nl < nr;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const bool alive = ch[b].alive;
+    const unsigned am = __ballot_sync(FULL, alive);
+    if (am) {
+      unsigned int first = 0;
+      if (lane == (uint32_t)(__ffs(am) - 1)) first = atomicAdd(out.n_cand, (unsigned int)__popc(am));
+      first = __shfl_sync(FULL, first, __ffs(am) - 1);
+      if (alive) {
+        const unsigned int slot = first + (unsigned int)__popc(am & lt);
+        if (slot < out.cap) {
+          Cand c;
+          c.q = ch[b].meta.x; c.l = ch[b].l; c.r = ch[b].r; c.code = ch[b].meta.y & 0x07FFFFFFu;
+          out.cands[slot] = c;
+        } else {
+          atomicExch(out.overflow, 1u);
+        }
+      }
+    }
+  }
+}
+#endif
+
 __device__ __forceinline__ void resolve_queued(const IndexView& ix, const PackedArgs& a, const SearchOut& out, bool have, uint64_t code, uint2 meta,
                                                int cs) {
   if (have && !second_opinion(a, code, meta, cs)) have = false;
@@ -952,8 +1049,14 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
   // two queues per warp: survivors of the first probe wait for the second opinion (A); what that leaves
   // (about three in ten) waits for the backward search (B), so that the long dependent chain of the
   // search always runs with 32 live lanes
-  __shared__ uint64_t q_code[8][32], r_code[8][64];   // (q_code: 64 four-byte tokens per warp)
-  __shared__ uint2 r_meta[8][64];
+#ifdef DG_RESOLVE_ASYNC
+  constexpr uint32_t kChainBatch = 64;                 // two batches of 32 per chain call
+  __shared__ uint4 s_slab[8][32][4];
+#else
+  constexpr uint32_t kChainBatch = 32;
+#endif
+  __shared__ uint64_t q_code[8][32], r_code[8][kChainBatch + 32];   // (q_code: 64 four-byte tokens per warp)
+  __shared__ uint2 r_meta[8][kChainBatch + 32];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -970,12 +1073,19 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
     }
     rqueued += (uint32_t)__popc(km);
     __syncwarp();
-    if (rqueued >= 32) {
-      rqueued -= 32;
+    if (rqueued >= kChainBatch) {
+      rqueued -= kChainBatch;
       const uint64_t c2 = r_code[wib][rqueued + lane];
       const uint2 m2 = r_meta[wib][rqueued + lane];
+#ifdef DG_RESOLVE_ASYNC
+      const uint64_t c3 = r_code[wib][rqueued + 32 + lane];
+      const uint2 m3 = r_meta[wib][rqueued + 32 + lane];
+      __syncwarp();
+      resolve_chain2(ix, out, s_slab[wib], true, c2, m2, true, c3, m3);
+#else
       __syncwarp();
       resolve_chain(ix, out, true, c2, m2);
+#endif
     }
   };
   // queue A holds TOKENS (result byte index * 8 + kind): the strings are rebuilt 32 at a time, one per lane
@@ -1048,12 +1158,21 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
     __syncwarp();
     stage_a(have, tok);
   }
+#ifdef DG_RESOLVE_ASYNC
+  if (rqueued) {
+    const bool haveA = lane < rqueued, haveB = lane + 32 < rqueued;
+    const uint64_t cA = haveA ? r_code[wib][lane] : 0, cB = haveB ? r_code[wib][lane + 32] : 0;
+    const uint2 mA = haveA ? r_meta[wib][lane] : make_uint2(0, 0), mB = haveB ? r_meta[wib][lane + 32] : make_uint2(0, 0);
+    resolve_chain2(ix, out, s_slab[wib], haveA, cA, mA, haveB, cB, mB);
+  }
+#else
   if (rqueued) {
     const bool have = lane < rqueued;
     const uint64_t c = have ? r_code[wib][lane] : 0;
     const uint2 mt = have ? r_meta[wib][lane] : make_uint2(0, 0);
     resolve_chain(ix, out, have, c, mt);
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

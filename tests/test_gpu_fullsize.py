@@ -245,6 +245,91 @@ def test_config5_padlock_arm_counts(big, fm9, tmp_path):
             assert (int(exact[i]), int(total[i])) == (int(f[1]), int(f[2])), i
 
 
+def test_config5_padlock_windows_tm_and_counts(big, fm9, tmp_path):
+    """BASELINE config 5 at its stated size: 100 regions of 2 kb, every sliding 2 x 20 window
+    (padlock.h:326-427): GC filter on the host, the three thal() temperatures of a window (arm 1, arm 2
+    and the 40-nt probe against their reverse complements: dg_thal_batch), the temperature rules of
+    padlock.h:342-378, exact arm counts (sdsl::count of arm + reverse complement: dg_count_batch, d = 0)
+    and neighbourhood counts (d = 1) with the uniqueness rules of padlock.h:381-427 -- every window
+    through the C ABI; a sample of temperatures and counts against the reference's own thal.h / SDSL /
+    neighbors.h, and the surviving windows of that sample recomputed from the reference's numbers."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import GOLDEN, write_primer3_config
+    from dicey_b200.api import Thal
+    rng = np.random.default_rng(11)
+    armlen, tlen = 20, 40
+    arms1, arms2, probes = [], [], []
+    for i in range(100):
+        chrom, off = int(rng.integers(0, NREC)), int(rng.integers(0, RECLEN - 3000))
+        exon = window(chrom, off + 1, 2000)
+        if i % 2:
+            exon = revcomp(exon)                       # '-' strand features (padlock.h:321)
+        for k in range(len(exon) - tlen + 1):
+            arms1.append(exon[k:k + armlen]); arms2.append(exon[k + armlen:k + tlen]); probes.append(exon[k:k + tlen])
+    n = len(probes)
+    assert n == 100 * 1961
+
+    def gc(seqs):
+        a = np.frombuffer(b"".join(seqs), dtype=np.uint8).reshape(len(seqs), -1)
+        return ((a == ord("G")) | (a == ord("C"))).sum(axis=1) / a.shape[1]
+    g1, g2, gp = gc(arms1), gc(arms2), gc(probes)
+    ok = (g1 >= 0.4) & (g1 <= 0.6) & (g2 >= 0.4) & (g2 <= 0.6) & (gp >= 0.4) & (gp <= 0.6)
+    idx = np.flatnonzero(ok)
+    th = Thal.open_tables(os.path.join(GOLDEN, "thal.params.tsv"), 0)
+    t0 = time.time()
+    try:
+        o1 = [arms1[i] for i in idx] + [arms2[i] for i in idx] + [probes[i] for i in idx]
+        tm, tok = th.tm(o1, [revcomp(x) for x in o1])
+    finally:
+        th.close()
+    t_thal = time.time() - t0
+    assert tok.all()
+    m = len(idx)
+    tm1, tm2, tmp_ = tm[:m], tm[m:2 * m], tm[2 * m:]
+    keep = (tm1 <= 93 + g1[idx] - 675.0 / armlen) & (tm2 <= 93 + g2[idx] - 675.0 / armlen) & (np.abs(tm1 - tm2) <= 2)
+    pmin = 81.5 + gp[idx] - 675.0 / tlen
+    keep &= (tmp_ >= pmin) & (tmp_ <= pmin + 10)
+    sel = idx[keep]
+    t0 = time.time()
+    arms = [arms1[i] for i in sel] + [arms2[i] for i in sel]
+    exact = big.count(arms, HuntParams(distance=0))
+    total = big.count(arms, HuntParams(distance=1))
+    t_count = time.time() - t0
+    s = len(sel)
+    uniq = (exact[:s] <= 1) & (exact[s:] <= 1) & (total[:s] <= 2) & (total[s:] <= 2)   # armMode, edit distance 1: maxNeighborHits = 2
+    print(f"[fullsize] config 5: {n} windows, {m} pass GC, {s} pass the Tm rules ({3 * m} thal pairs in {t_thal:.2f} s), "
+          f"{int(uniq.sum())} unique ({4 * s} arm counts in {t_count:.2f} s)")
+    assert s > 100 and uniq.sum() > 50 and (exact >= 1).all() and (total >= exact).all()
+    if fm9:
+        path, rec = fm9
+        cfg = write_primer3_config(str(tmp_path / "p3cfg"))
+        # temperatures of a sample of windows (all three per window), bit for bit
+        samp = idx[:: max(1, len(idx) // 200)][:200]
+        pf = str(tmp_path / "pairs.tsv")
+        with open(pf, "wb") as f:
+            for i in samp:
+                for x in (arms1[i], arms2[i], probes[i]):
+                    f.write(x + b"\t" + revcomp(x) + b"\n")
+        want = [l.split("\t") for l in run_ref(["thal", cfg + "/", pf, "/dev/null"]).splitlines()]
+        pos = {int(i): j for j, i in enumerate(idx)}
+        for r, i in enumerate(samp):
+            j = pos[int(i)]
+            for c, arr in enumerate((tm1, tm2, tmp_)):
+                assert int(arr[j:j + 1].view(np.uint64)[0]) == int(want[3 * r + c][2], 16), (int(i), c)
+        # counts of a sample of surviving windows
+        ssel = list(range(0, s, max(1, s // 100)))[:100]
+        qf = str(tmp_path / "arms.txt")
+        write_queries(qf, [arms[k] for k in ssel] + [arms[s + k] for k in ssel])
+        lines = run_ref(["padcount", path, qf, "-d", "1"]).splitlines()
+        ref_exact = np.array([int(l.split("\t")[1]) for l in lines]); ref_total = np.array([int(l.split("\t")[2]) for l in lines])
+        k = len(ssel)
+        assert (ref_exact[:k] == exact[ssel]).all() and (ref_exact[k:] == exact[[s + x for x in ssel]]).all()
+        # (the reference stops adding once a total exceeds maxNeighborHits: only the decision is comparable)
+        ref_uniq = (ref_exact[:k] <= 1) & (ref_exact[k:] <= 1) & (ref_total[:k] <= 2) & (ref_total[k:] <= 2)
+        assert (ref_uniq == uniq[ssel]).all()
+
+
 def test_config_headline_edit1_properties(big):
     """The bench workload itself (1 M 20-mers, edit distance 1): whole-batch invariants."""
     n = 1_000_000
@@ -325,7 +410,9 @@ def test_config3_search_end_to_end(big, fm9, tmp_path):
     cfg = write_primer3_config(os.path.join(d, "p3cfg"))
     rng = np.random.default_rng(17)
     with open(os.path.join(d, "primers.fa"), "w") as f:
-        npairs = int(os.environ.get("DG_SEARCH_PAIRS", "24"))   # BASELINE config 3 is 1000 (the reference then needs minutes)
+        npairs = int(os.environ.get("DG_SEARCH_PAIRS", "1000"))   # BASELINE config 3
+        nref = int(os.environ.get("DG_SEARCH_REF_PAIRS", "40"))     # pairs of the byte-for-byte comparison (the reference needs ~0.25 s per pair)
+        lines_fa = []
         for i in range(npairs):
             chrom, off, alen = int(rng.integers(0, NREC)), int(rng.integers(0, RECLEN - 5000)), int(rng.integers(150, 3000))
             L1, L2 = int(rng.integers(18, 25)), int(rng.integers(18, 25))
@@ -333,20 +420,32 @@ def test_config3_search_end_to_end(big, fm9, tmp_path):
             rv = bytearray(revcomp(window(chrom, off + alen - L2 + 1, L2)))
             if i % 3 == 1:
                 fw[1] = ord("ACGT"[("ACGT".index(chr(fw[1])) + 1) % 4])
-            f.write(f">amp{i}_F\n{fw.decode()}\n>amp{i}_R\n{rv.decode()}\n")
-    t0 = time.time()
-    want = subprocess.run([REF_BIN, "search", path, rec, os.path.join(d, "primers.fa"), cfg], check=True, capture_output=True, text=True).stdout
-    t1 = time.time()
-    got = subprocess.run([os.path.join(ROOT, "dicey_b200", "dicey-b200"), "search", "-g", "genome.fa.gz", "-i", cfg, "primers.fa"],
-                         cwd=d, capture_output=True, text=True, env=dict(os.environ, DICEY_B200_TRACE="1"))
-    t2 = time.time()
-    assert got.returncode == 0, got.stderr
+            lines_fa.append(f">amp{i}_F\n{fw.decode()}\n>amp{i}_R\n{rv.decode()}\n")
+        f.write("".join(lines_fa))
+    with open(os.path.join(d, "primers_ref.fa"), "w") as f:
+        f.write("".join(lines_fa[:nref]))
     import json
+    exe = os.path.join(ROOT, "dicey_b200", "dicey-b200")
+    # the whole configuration through the product
+    t1 = time.time()
+    full = subprocess.run([exe, "search", "-g", "genome.fa.gz", "-i", cfg, "primers.fa"], cwd=d, capture_output=True, text=True,
+                          env=dict(os.environ, DICEY_B200_TRACE="1"))
+    t2 = time.time()
+    assert full.returncode == 0, full.stderr
+    jf = json.loads(full.stdout)
+    print(f"[fullsize] dicey-b200 search, {2 * npairs} primers: {t2 - t1:.1f} s (index load included); "
+          f"{len(jf['data']['primers'])} binding sites, {len(jf['data']['amplicons'])} amplicons")
+    print(full.stderr)
+    assert len(jf["data"]["amplicons"]) >= npairs * 5 // 6
+    # the first pairs on their own, byte for byte against the reference driver
+    t0 = time.time()
+    want = subprocess.run([REF_BIN, "search", path, rec, os.path.join(d, "primers_ref.fa"), cfg], check=True, capture_output=True, text=True).stdout
+    t1 = time.time()
+    got = subprocess.run([exe, "search", "-g", "genome.fa.gz", "-i", cfg, "primers_ref.fa"], cwd=d, capture_output=True, text=True)
+    assert got.returncode == 0, got.stderr
     j = json.loads(want)
-    print(f"[fullsize] search, {2 * npairs} primers: reference {t1 - t0:.1f} s, dicey-b200 {t2 - t1:.1f} s (index load included); "
-          f"{len(j['data']['primers'])} binding sites, {len(j['data']['amplicons'])} amplicons")
-    print(got.stderr)
-    assert len(j["data"]["amplicons"]) >= npairs * 5 // 6
+    print(f"[fullsize] search, {2 * nref} primers: reference {t1 - t0:.1f} s; {len(j['data']['primers'])} binding sites, "
+          f"{len(j['data']['amplicons'])} amplicons: same bytes")
     assert got.stdout == want
 
 

@@ -195,6 +195,46 @@ def test_padlock_counts(indexes):
             assert (int(exact[i]), int(total[i])) == (int(w[1]), int(w[2])), (fn, i)
 
 
+@pytest.mark.parametrize("knob", ["DG_FULL_SA=0", "DG_BITMAP_K=0", "DG_BITMAP_EXTRA=0", "DG_BITMAP_LEFT=0", "DG_KMER=8",
+                                  "DG_BITMAP_K=14", "DG_FULL_SA=0 DG_BITMAP_LEFT=0 DG_KMER=10"])
+def test_every_index_shape_gives_the_golden_records(knob, monkeypatch):
+    """The loader drops optional tables when HBM is short (and the knobs force it): sampled suffix array
+    (the LF walk of csa_wt.hpp:340-354 instead of one gather), no presence bitmaps, no KB +- 1 bitmaps, no
+    left-anchored twins, a short K-mer table.  Every shape must give the reference's records: hunt
+    (edit and Hamming, distances 1 and 2, caps), search seeds and padlock counts."""
+    for kv in knob.split():
+        monkeypatch.setenv(*kv.split("="))
+    opened = {}
+    try:
+        for name in ("t1m", "stress"):
+            ix = Index.open(os.path.join(GOLDEN, name + ".fm9"), 0)
+            names, lens = read_rec_tsv(os.path.join(GOLDEN, name + ".rec.tsv"))
+            ix.set_records(names, lens)
+            opened[name] = ix
+        info = opened["t1m"].info()
+        if "DG_KMER" in knob:
+            assert info["kmer"] == int(knob.split("DG_KMER=")[1].split()[0])
+        if "DG_BITMAP_K=0" in knob:
+            assert info["bitmap_k"] == 0
+        for case, index in (("t1m_e1", "t1m"), ("t1m_h2", "t1m"), ("stress_e1_m7", "stress"), ("stress_e2", "stress"), ("t1m_e2_x500", "t1m")):
+            ix = opened[index]
+            qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
+            par = params_from_flags(open(os.path.join(GOLDEN, case + ".flags.txt")).read())
+            want = read_records(os.path.join(GOLDEN, case + ".records.tsv"))
+            res = ix.hunt([s for _, s in qs], par)
+            for q, (name, seq) in enumerate(qs):
+                w = want[q]
+                assert res.messages(q, par, seq.encode()) == w["msgs"], (knob, case, q)
+                if w["msgs"] and w["msgs"][0].startswith("Error"):
+                    continue
+                assert res.push_hits(q) == w["push"], (knob, case, q)
+        test_seed_golden(opened)
+        test_padlock_counts(opened)
+    finally:
+        for ix in opened.values():
+            ix.close()
+
+
 @pytest.mark.parametrize("name", ["t1m", "stress"])
 def test_write_fm9(indexes, name, tmp_path, ref_bin):
     """dg_index_write_fm9 reproduces SDSL's file byte for byte (wavelet tree, rank and select
