@@ -587,7 +587,7 @@ __device__ __forceinline__ ProbeAddr presence_addr(const PackedArgs& a, const Wi
   const uint32_t* base = left ? bml : bm;
   ProbeAddr r;
   r.state = L <= 0 ? 2u : ((a.KB == 0 || cls < 0 || bm == nullptr || (OTHER && (bml == nullptr || L <= kb))) ? 1u : 0u);
-  r.word = r.state ? a.win_r[1] : base + (bit >> 5);   // (a harmless address when no test is needed)
+  r.word = r.state ? reinterpret_cast<const uint32_t*>(a.qcode) : base + (bit >> 5);   // (a harmless, always valid address when no test is needed)
   r.bit = (uint32_t)bit & 31u;
   return r;
 }
