@@ -30,6 +30,10 @@ namespace dg {
 
 constexpr int kMaxQuery = 255;     // longest query the device path accepts
 constexpr int kMaxDist = 2;        // largest distance the device path enumerates
+constexpr int kMaxListDist = 32;   // largest distance searched at all: beyond kMaxDist the neighbourhood comes as a list from
+                                   // the host replay (nbr_trunc.hpp), strings of up to 42 characters
+constexpr int kMaxCompactDist = 3; // a compact record (dg_rec) carries at most three edit operations: larger distances
+                                   // return full records (dg_hit + alignment pool)
 constexpr int kFlagShift = 12;     // one exception-flag bit per 4096 BWT rows
 constexpr int kSaSample = 32;      // csa_wt<> t_dens
 

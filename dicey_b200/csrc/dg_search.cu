@@ -49,6 +49,7 @@ struct BatchDev {
   uint32_t* irregular;      // bit 0: a query departs from the uniform batch shape; bit 1: a Hamming neighbourhood
                             // reaches the cap; bit 2: an edit neighbourhood is not certified below the cap
   uint32_t uniform_len;     // common raw length of the batch (0 = mixed lengths)
+  uint32_t key_sortable;    // every string of the batch fits the 126-bit sort key (listed neighbourhoods need that)
   // neighbourhoods the cap -x truncated (neighbors.h:50), replayed on the host (nbr_trunc.hpp): for the
   // (query, strand) pairs listed in trunc_qs (ascending (q << 1) | strand) the set IS the sorted key list
   // trunc_keys[trunc_off[i] .. trunc_off[i + 1]) instead of the substring-minimal strings
@@ -56,6 +57,20 @@ struct BatchDev {
   const uint32_t* trunc_off;
   const ulonglong2* trunc_keys;
   uint32_t n_trunc;
+};
+
+// A candidate whose string came from a host-made list (distance 3: nbr_trunc.hpp replays the whole
+// neighbourhood) instead of an edit script: code = strand | 3 << 1 | length << 3 | rank in the
+// (query, strand) set << 11 (the set is sorted as std::set<std::string> iterates it).
+constexpr uint32_t kListedNev = 3;
+DG_HD bool cand_is_listed(uint32_t code) { return ((code >> 1) & 3u) == kListedNev; }
+DG_HD uint32_t pack_listed(int strand, int len, uint32_t rank) { return (uint32_t)strand | (kListedNev << 1) | ((uint32_t)len << 3) | (rank << 11); }
+struct ListedStrings {      // uploaded by resolve_special
+  const uint8_t* chars;     // the strings back to back
+  const uint32_t* off;      // n + 1 offsets
+  const uint32_t* q;        // query of each string
+  const uint32_t* code;     // pack_listed(...) of each string
+  uint32_t n;
 };
 
 DG_HD void query_geom(const BatchDev& b, uint32_t q, int strand, const uint8_t*& base, int& m, int& koff) {
@@ -237,9 +252,14 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
     d = (uint32_t)L - 1;
     st |= DG_Q_DIST_ADJUSTED;
   }
-  if (d > (uint32_t)kMaxDist || (b.seed_len && d >= b.seed_len)) st |= DG_Q_UNSUPPORTED;
+  if (d > (uint32_t)kMaxListDist || (b.seed_len && d >= b.seed_len) || (d > (uint32_t)kMaxDist && m + (int)d > 42)) st |= DG_Q_UNSUPPORTED;
   bool run = !(st & (DG_Q_SKIPPED | DG_Q_TOO_SHORT | DG_Q_UNSUPPORTED));
   if (run && b.max_loc == 0) st |= DG_Q_HIT_CAP;   // -m 0: no hit is taken and hunter.h:434 (0 >= 0) warns for every query
+  // beyond the enumerated distances the host replays the neighbourhood and uploads it as a list
+  // (resolve_special): the query takes no part in the script enumeration below
+  if (run && d > (uint32_t)kMaxDist && !b.key_sortable) { st |= DG_Q_UNSUPPORTED; run = false; }
+  const bool listed = run && d > (uint32_t)kMaxDist;
+  if (listed) { st |= DG_Q_NBR_UNVERIFIED; atomicOr(b.irregular, 16u); run = false; }
   bool clean = true;
   uint64_t cf = 0, cr = 0;
   if (run) {
@@ -275,7 +295,8 @@ __global__ void k_prepare(const uint8_t* __restrict__ raw, BatchDev b, uint8_t* 
   int variant = clean ? 0 : 1;
   // packed queries are searched by k_search_packed; k_search takes the rest
   units[q] = (run && !packed) ? (uint64_t)ut.tab_cnt[variant * 256 + m] * (b.reverse ? 2 : 1) : 0;
-  if (!run || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
+  if (listed) run = true;   // (searched, through the list)
+  if (!run || listed || !clean || (uint32_t)L != b.uniform_len || d != b.distance) atomicOr(b.irregular, 1u);
   if (changed) atomicOr(b.irregular, 8u);
 }
 
@@ -1317,6 +1338,14 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
   CandKey k;
   k.hi = k.lo = 0;
   bool keep;
+  if (cand_is_listed(c.code)) {
+    // a string of a host-made list: the list is the set (already an antichain, already in set order)
+    k.hi = c.code >> 11;
+    k.qs = (c.q << 1) | (c.code & 1u);
+    k.idx = i;
+    keys[i] = k;
+    return;
+  }
   if ((b.qflag[c.q] & 2) && !slow_keys) {
     // packed path (ACGT-only query, m + d <= 31): the string k_search_packed searched, rebuilt the
     // way it built it, then widened by shifts and masks instead of a walk over the bases
@@ -1598,7 +1627,7 @@ __global__ void __launch_bounds__(kVerifyBlock) k_verify(IndexView ix, BatchDev 
     Script sc;
     unpack_script(c.code, indel, strand, sc);
     query_geom(b, c.q, strand, base, mq, koff);
-    const int m = script_len(mq, sc);             // neighbour length
+    const int m = cand_is_listed(c.code) ? (int)((c.code >> 3) & 0xFFu) : script_len(mq, sc);   // neighbour length
     d = (int)b.dist[c.q];
     // hunter.h:358-362
     uint32_t refIndex;
@@ -1804,6 +1833,26 @@ __global__ void k_backward_search(IndexView ix, const uint8_t* __restrict__ seqs
   for (int i = L - 1; i >= 0 && l < r; --i) backward_step(ix, l, r, seqs[o + i]);
   if (l < r) { lout[q] = l; rout[q] = (uint64_t)r - 1; }
   else { lout[q] = l; rout[q] = (uint64_t)l - 1; }  // SDSL reports an empty interval as r = l - 1 (r + 1 - l == 0)
+}
+
+// listed neighbourhoods (distance 3): literal backward search of every string of the lists
+__global__ void k_search_listed(IndexView ix, ListedStrings ls, SearchOut out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ls.n) return;
+  const uint32_t o = ls.off[i];
+  const int L = (int)(ls.off[i + 1] - o);
+  uint32_t l = 0, r = (uint32_t)ix.n;
+  for (int j = L - 1; j >= 0 && l < r; --j) backward_step(ix, l, r, ls.chars[o + j]);
+  if (l < r && L > 0) {
+    const unsigned int slot = atomicAdd(out.n_cand, 1u);
+    if (slot < out.cap) {
+      Cand c;
+      c.q = ls.q[i]; c.l = l; c.r = r; c.code = ls.code[i];
+      out.cands[slot] = c;
+    } else {
+      atomicExch(out.overflow, 1u);
+    }
+  }
 }
 
 // unit table of one search-string length (host)
@@ -2072,6 +2121,9 @@ struct dg_batch {
   ABuf<uint32_t> trunc_qs, trunc_off;
   ABuf<ulonglong2> trunc_keys;
   uint32_t n_trunc = 0;
+  ABuf<uint8_t> ls_chars;           // listed neighbourhoods (distance 3)
+  ABuf<uint32_t> ls_off, ls_q, ls_code;
+  uint32_t n_listed = 0;
   ABuf<uint64_t> qcode;
   ABuf<uint8_t> qflag;
   uint32_t uniform_len = 0;
@@ -2115,6 +2167,10 @@ static BatchDev batch_dev(const dg_batch* b) {
   d.qcode = b->qcode.p; d.qflag = b->qflag.p; d.irregular = b->irregular.p; d.uniform_len = b->uniform_len;
   d.indel = b->par.indel; d.reverse = b->par.reverse;
   d.trunc_qs = b->trunc_qs.p; d.trunc_off = b->trunc_off.p; d.trunc_keys = b->trunc_keys.p; d.n_trunc = b->n_trunc;
+  {
+    const int maxq = b->par.seed_len ? (int)b->par.seed_len : std::min(b->max_len, kMaxQuery);
+    d.key_sortable = (maxq + (int)std::min<uint32_t>(b->par.distance, (uint32_t)std::max(maxq - 1, 0)) <= 42 && !getenv("DG_MERGE_SORT")) ? 1u : 0u;
+  }
   return d;
 }
 
@@ -2128,10 +2184,8 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
   const uint64_t total_bytes = uniform_L ? (uint64_t)nq * uniform_L : (offsets ? offsets[nq] : 0);
   if (uniform_L) offsets = two_off;
   if (!ix || !offsets || !par || !out || (nq && !seqs)) { set_error("null argument"); return DG_ERR_ARG; }
-  if (par->distance > (uint32_t)kMaxDist) {
-    set_error("distance > 2 is outside the device path (DESIGN.md, Limits)");
-    return DG_ERR_UNSUPPORTED;
-  }
+  // (distances beyond kMaxListDist are not refused here: the reference clamps -d per query to |seq| - 1,
+  // and what stays too large is flagged DG_Q_UNSUPPORTED per query by k_prepare)
   if (par->seed_len > (uint32_t)kMaxQuery || (par->seed_len && par->distance >= par->seed_len)) {
     set_error("bad seed length");
     return DG_ERR_ARG;
@@ -2234,6 +2288,7 @@ static int stage_impl(dg_index* ix, const char* seqs, const uint64_t* offsets, u
         const uint64_t hsize = 1 + (d >= 1 ? w : 0) + (d >= 2 ? (w * w - 16ull * m) / 2 : 0);
         if (indel ? b->tabs->script_ub[m] >= cap : hsize >= cap) b->maybe_capped = true;
       }
+      if (par->distance > (uint32_t)kMaxDist) b->maybe_capped = true;   // listed neighbourhoods are resolved by the same host pass
     }
     const double ts1 = now();
     b->irregular.alloc(1, st);
@@ -2291,7 +2346,7 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
     uint32_t irr = 0;
     DG_CUDA(cudaMemcpyAsync(&irr, b->irregular.p, 4, cudaMemcpyDeviceToHost, st));
     DG_CUDA(sync_stream(st));
-    if (!(irr & 6u)) return DG_OK;
+    if (!(irr & 22u)) return DG_OK;
     const uint32_t nq = b->nq;
     const bool indel = b->par.indel != 0;
     const uint32_t cap = b->par.max_neighborhood ? b->par.max_neighborhood : 10000;
@@ -2303,13 +2358,13 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
     DG_CUDA(cudaMemcpyAsync(off.data(), b->off.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (b->nbytes) DG_CUDA(cudaMemcpyAsync(fwd.data(), b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, st));
     DG_CUDA(sync_stream(st));
-    const uint32_t want = indel ? (uint32_t)DG_Q_NBR_UNVERIFIED : (uint32_t)DG_Q_NBR_CAP;
+    const uint32_t want = (uint32_t)DG_Q_NBR_UNVERIFIED | (indel ? 0u : (uint32_t)DG_Q_NBR_CAP);   // (listed queries carry UNVERIFIED in both modes)
     std::vector<uint32_t> flagged;
     for (uint32_t q = 0; q < nq; ++q)
       if ((status[q] & want) && !(status[q] & (DG_Q_TOO_SHORT | DG_Q_SKIPPED | DG_Q_UNSUPPORTED))) flagged.push_back(q);
     if (flagged.empty()) return DG_OK;
     const int nstrand = b->par.reverse ? 2 : 1;
-    struct Out { bool capped[2] = {false, false}; bool unkeyed = false; std::vector<ulonglong2> keys[2]; };
+    struct Out { bool capped[2] = {false, false}; bool unkeyed = false; std::vector<ulonglong2> keys[2]; std::vector<std::string> all[2]; };
     std::vector<Out> outs(flagged.size());
     auto work = [&](size_t lo, size_t hi) {
       NeighborReplay nr;
@@ -2330,6 +2385,11 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
           }
           const bool capped = nr.run(str, (int)dist[q], indel, cap);
           outs[i].capped[strand] = capped;
+          if ((int)dist[q] > kMaxDist) {   // beyond the enumerated distances: the whole set goes to the device as a list
+            outs[i].all[strand] = nr.strings();
+            std::sort(outs[i].all[strand].begin(), outs[i].all[strand].end());
+            continue;
+          }
           if (!capped) continue;
           for (const std::string& t : nr.strings()) {
             if ((int)t.size() > kKeyChars) { outs[i].unkeyed = true; break; }
@@ -2356,9 +2416,24 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
     }
     std::vector<uint32_t> qs, loff(1, 0);
     std::vector<ulonglong2> keys;
+    std::vector<uint8_t> lchars;
+    std::vector<uint32_t> lo(1, 0), lq, lcode;
     for (size_t i = 0; i < flagged.size(); ++i) {
       const uint32_t q = flagged[i];
       Out& o = outs[i];
+      if ((int)dist[q] > kMaxDist) {
+        status[q] &= ~(uint32_t)(DG_Q_NBR_UNVERIFIED | DG_Q_NBR_CAP);
+        if (o.capped[0] || o.capped[1]) status[q] |= DG_Q_NBR_CAP;
+        for (int strand = 0; strand < nstrand; ++strand)
+          for (size_t r = 0; r < o.all[strand].size(); ++r) {
+            const std::string& t = o.all[strand][r];
+            lchars.insert(lchars.end(), t.begin(), t.end());
+            lo.push_back((uint32_t)lchars.size());
+            lq.push_back(q);
+            lcode.push_back(pack_listed(strand, (int)t.size(), (uint32_t)r));
+          }
+        continue;
+      }
       if (o.unkeyed) {   // strings longer than the sort key: cannot be listed; the flag stays
         status[q] |= DG_Q_NBR_UNVERIFIED;
         continue;
@@ -2381,6 +2456,17 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
       DG_CUDA(cudaMemcpyAsync(b->trunc_qs.p, qs.data(), qs.size() * 4, cudaMemcpyHostToDevice, st));
       DG_CUDA(cudaMemcpyAsync(b->trunc_off.p, loff.data(), loff.size() * 4, cudaMemcpyHostToDevice, st));
       if (!keys.empty()) DG_CUDA(cudaMemcpyAsync(b->trunc_keys.p, keys.data(), keys.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice, st));
+    }
+    b->n_listed = (uint32_t)lq.size();
+    if (b->n_listed) {
+      b->ls_chars.alloc(lchars.size() + 1, st);
+      b->ls_off.alloc(lo.size(), st);
+      b->ls_q.alloc(lq.size(), st);
+      b->ls_code.alloc(lcode.size(), st);
+      DG_CUDA(cudaMemcpyAsync(b->ls_chars.p, lchars.data(), lchars.size(), cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(b->ls_off.p, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(b->ls_q.p, lq.data(), lq.size() * 4, cudaMemcpyHostToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(b->ls_code.p, lcode.data(), lcode.size() * 4, cudaMemcpyHostToDevice, st));
     }
     DG_CUDA(sync_stream(st));   // the host vectors above go out of scope
     return DG_OK;
@@ -2439,6 +2525,7 @@ static int run_impl(dg_batch* b) {
     }
     if (b->maybe_capped && nq) {
       b->n_trunc = 0;
+      b->n_listed = 0;
       if (b->par.indel) { k_nbr_bound<<<grid_for(nq, B), B, 0, st>>>(bd); ++launches; }
       const int rc_t = resolve_truncation(b, st);
       if (rc_t) return rc_t;
@@ -2542,6 +2629,11 @@ static int run_impl(dg_batch* b) {
         // everything else (queries holding 'N', longer than 31 bases): the byte-wise general path
         k_search<<<nsm * general_per_sm, 256, 0, st>>>(v, bd, ut, b->unit_off.p, b->uniform_units, so);
         launches += 2;
+        if (b->n_listed) {   // neighbourhoods that came as lists from the host replay (distance 3)
+          ListedStrings ls{b->ls_chars.p, b->ls_off.p, b->ls_q.p, b->ls_code.p, b->n_listed};
+          k_search_listed<<<grid_for(b->n_listed, 128), 128, 0, st>>>(v, ls, so);
+          ++launches;
+        }
       }
       if (attempt == 0) prof_mark(ix, 2, st);
       DG_CUDA(cudaMemcpyAsync(hc, ctr.p, 8, cudaMemcpyDeviceToHost, st));
@@ -2752,7 +2844,7 @@ static int run_impl(dg_batch* b) {
     b->pool_stride = b->par.seed_len ? (uint32_t)maxg : (b->par.indel ? 2 * aln_max : (uint32_t)(maxg + maxq));
     // hunt results travel as compact records (dg_rec); search results keep dg_hit + genomic contexts
     static const bool full_records = getenv("DG_FULL_RECORDS") != nullptr;
-    b->compact = !b->par.seed_len && !full_records;
+    b->compact = !b->par.seed_len && !full_records && b->par.distance <= (uint32_t)kMaxCompactDist;
     b->wire.alloc(nhits ? nhits : 1, st);
     if (b->compact) {
       b->recs.alloc(nhits ? nhits : 1, st);
@@ -3185,7 +3277,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     r->cum = idx->h_cum;
     static const bool full_records = getenv("DG_FULL_RECORDS") != nullptr;
     p.peer.nranks = 0;
-    if (!params->seed_len && !full_records) {
+    if (!params->seed_len && !full_records && params->distance <= (uint32_t)kMaxCompactDist) {
       comm_peer_out(idx, idx, &p.peer);
       r->qmeta.alloc((size_t)nq * 2, true);
     } else {

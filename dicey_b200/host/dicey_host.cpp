@@ -246,6 +246,8 @@ int hunter(int argc, char** argv) {
     uint64_t gathered = 0;         // hits of all shards, as the all-gather reported them to this shard
     // result views
     const dg_rec* recs = nullptr;
+    const dg_hit* hits = nullptr;      // only when the result is not compact
+    const char* pool = nullptr;
     const uint64_t* qoff = nullptr;
     const uint32_t* status = nullptr;
     const uint32_t* qdist = nullptr;
@@ -314,9 +316,9 @@ int hunter(int argc, char** argv) {
   par.indel = c.indel ? 1 : 0;
   par.reverse = c.reverse ? 1 : 0;
   par.seed_len = 0;
-  // the device path enumerates distances 0..2; beyond that no query is searched (the reference clamps -d
-  // to |seq| - 1 per query, which is still > 2 for every query of 10 bases or more)
-  const bool all_unsupported = par.distance > 2;
+  // (distances 0..2 are enumerated on the device, distance 3 is searched from host-made neighbour lists;
+  // a query whose clamped distance stays larger carries DG_Q_UNSUPPORTED)
+  const bool all_unsupported = false;
   const uint32_t nq_all = (uint32_t)queries.size();
   uint8_t comm_id[DG_COMM_ID_BYTES];
   bool use_comm = ndev > 1 && !all_unsupported;
@@ -341,6 +343,11 @@ int hunter(int argc, char** argv) {
         if (s.rc != DG_OK) { s.err = dg_last_error(); return; }
         uint32_t nq = 0;
         s.recs = dg_result_records(s.res, &s.nh);
+        if (!s.recs) {
+          uint64_t pool_bytes = 0;
+          s.hits = dg_result_hits(s.res, &s.nh);
+          s.pool = dg_result_pool(s.res, &pool_bytes);
+        }
         s.qoff = dg_result_query_offsets(s.res, &nq);
         s.status = dg_result_query_status(s.res);
         s.qdist = dg_result_query_distance(s.res);
@@ -393,7 +400,7 @@ int hunter(int argc, char** argv) {
     const size_t ql = qi - sh.q0;
     uint32_t st = all_unsupported ? (uint32_t)DG_Q_UNSUPPORTED : sh.status[ql];
     if (st & DG_Q_UNSUPPORTED) {
-      m.push_back("Error: Query is outside the limits of the GPU search path (length <= 255, distance <= 2)!");
+      m.push_back("Error: Query is outside the limits of the GPU search path (length <= 255; beyond distance 2, sequence length + distance <= 42)!");
       out += hunt_json(c, c.distance, raw, queries[qi].first, seqname, ht, m);
       return;
     }
@@ -420,10 +427,26 @@ int hunter(int argc, char** argv) {
       m.push_back("Warning: More than " + x + " matches found. Only first " + x +
                   " matches are reported, results are likely incomplete!");
     }
+    const std::string sequence(sh.norm + sh.off[ql], sh.norm + sh.off[ql + 1]);
+    if (!sh.recs) {
+      // full records (distances beyond three edit operations travel as dg_hit + alignment pool)
+      std::vector<dg_hit> full(sh.hits + sh.qoff[ql], sh.hits + sh.qoff[ql + 1]);
+      dg_hits_sort(full.data(), full.size());  // hunter.h:440
+      ht.reserve(full.size());
+      for (const auto& h : full) {
+        DnaHitView v;
+        v.score = h.score; v.chr = h.chr; v.start = h.start; v.strand = (char)h.strand;
+        v.refalign = sh.pool + h.aln_off;
+        v.queryalign = sh.pool + h.aln_off + h.aln_len;
+        v.aln_len = h.aln_len;
+        ht.push_back(v);
+      }
+      out += hunt_json(c, sh.qdist[ql], sequence, queries[qi].first, seqname, ht, m);
+      return;
+    }
     std::vector<dg_rec> mine(sh.recs + sh.qoff[ql], sh.recs + sh.qoff[ql + 1]);
     dg_recs_sort(mine.data(), mine.size());  // hunter.h:440
     // the records carry their alignments as edit operations: both rows are rebuilt from the query
-    const std::string sequence(sh.norm + sh.off[ql], sh.norm + sh.off[ql + 1]);
     std::string rev(sequence.rbegin(), sequence.rend());
     for (char& ch : rev) ch = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N';
     const size_t stride = sequence.size() + 4;

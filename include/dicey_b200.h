@@ -42,10 +42,10 @@ enum {
   DG_Q_DIST_ADJUSTED = 1u << 1,   /* hunter.h:312-315: distance clamped to |seq|-1 */
   DG_Q_HIT_CAP = 1u << 2,         /* hunter.h:434-437: hits >= max_locations */
   DG_Q_NBR_CAP = 1u << 3,         /* hunter.h:342-345: neighbourhood size >= max_neighborhood */
-  DG_Q_NBR_UNVERIFIED = 1u << 4,  /* edit-mode set size not certified below max_neighborhood
-                                     (script count >= cap); searched untruncated */
+  DG_Q_NBR_UNVERIFIED = 1u << 4,  /* the neighbourhood may reach max_neighborhood but its truncated form could
+                                     not be replayed (strings longer than 42 characters): searched untruncated */
   DG_Q_SKIPPED = 1u << 5,         /* silica.h:363,388: primer not longer than the seed k-mer */
-  DG_Q_UNSUPPORTED = 1u << 6      /* outside the device path's limits (length > 255, distance > 2): not searched */
+  DG_Q_UNSUPPORTED = 1u << 6      /* outside the device path's limits (length > 255; distance > 2 with length + distance > 42): not searched */
 };
 
 /* hunter.h:37-50 (HunterConfig) / silica.h:38-67 (SilicaConfig), the fields the hot path reads. */

@@ -320,6 +320,12 @@ def make_truncation_cases():
     hunt_case("t1m_e2_x5000", t1m, rec1, q2, ["-d", "2", "-x", "5000"])
     q3 = [(f"l{i}", planted(m, 2, True, 200 + i)) for i, m in enumerate([24, 24, 25, 25, 26, 23, 22, 28])]
     hunt_case("t1m_e2_long", t1m, rec1, q3, ["-d", "2"])
+    # distance 3 (searched from host-made neighbour lists): short primers, both modes
+    q4 = [(f"t{i}", planted(m, 2, True, 300 + i)) for i, m in enumerate([10, 11, 12, 12, 13, 13, 14, 16])]
+    q4.append(("nine", "ACGTACGTA"))
+    hunt_case("t1m_h3", t1m, rec1, q4, ["-d", "3", "-n"])
+    hunt_case("t1m_e3_x3000", t1m, rec1, q4, ["-d", "3", "-x", "3000"])
+    hunt_case("t1m_d12", t1m, rec1, q4[:3], ["-d", "12", "-n", "-x", "300"])
     recs = gzip.open(os.path.join(HERE, "stress.dump.gz"), "rt").read().split("\n")
     sq = []
     for i in range(10):

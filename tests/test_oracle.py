@@ -24,7 +24,7 @@ def run(binary, args):
 
 
 FAST_HUNT = ["cfg1_d0", "t1m_e1", "t1m_h1", "t1m_e0", "t1m_e1_fwd", "stress_e1", "stress_h1", "stress_e1_m7", "stress_h2_m50", "t1m_h2",
-             "t1m_e1_x50", "t1m_e1_x150", "t1m_h2_x300", "t1m_h1_x40", "t1m_e2_x500"]
+             "t1m_e1_x50", "t1m_e1_x150", "t1m_h2_x300", "t1m_h1_x40", "t1m_e2_x500", "t1m_h3", "t1m_d12"]
 
 
 @pytest.mark.parametrize("case", FAST_HUNT)

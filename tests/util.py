@@ -77,6 +77,8 @@ HUNT_CASES = [
     # the reference truncates the neighbourhood at -x (neighbors.h:50) in these
     ("t1m_e1_x50", "t1m"), ("t1m_e1_x150", "t1m"), ("t1m_h2_x300", "t1m"), ("t1m_h1_x40", "t1m"), ("t1m_e2_x500", "t1m"),
     ("t1m_e2_x5000", "t1m"), ("t1m_e2_long", "t1m"), ("stress_e2_x2000", "stress"), ("t1m_e1_m0", "t1m"),
+    # distance 3: searched from host-made neighbour lists
+    ("t1m_h3", "t1m"), ("t1m_e3_x3000", "t1m"), ("t1m_d12", "t1m"),
 ]
 
 
