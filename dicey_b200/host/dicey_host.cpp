@@ -322,6 +322,9 @@ int hunter(int argc, char** argv) {
   const uint32_t nq_all = (uint32_t)queries.size();
   uint8_t comm_id[DG_COMM_ID_BYTES];
   bool use_comm = ndev > 1 && !all_unsupported;
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < i; ++j)
+      if (c.devices[(size_t)i] == c.devices[(size_t)j]) use_comm = false;   // (NCCL wants one rank per GPU; shards on one GPU need no exchange)
   if (use_comm && dg_comm_get_unique_id(comm_id) != DG_OK) {
     std::cerr << "dicey-b200: " << dg_last_error() << " (continuing without the hit all-gather)" << std::endl;
     use_comm = false;

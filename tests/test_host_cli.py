@@ -19,8 +19,8 @@ def built():
     subprocess.run(["make", "-C", os.path.join(ROOT, "dicey_b200", "host")], check=True, capture_output=True)
 
 
-def run(args, cwd=None):
-    return subprocess.run([BIN] + args, capture_output=True, text=True, cwd=cwd)
+def run(args, cwd=None, env=None):
+    return subprocess.run([BIN] + args, capture_output=True, text=True, cwd=cwd, env=env)
 
 
 def make_genome_dir(tmp_path, index):
@@ -93,6 +93,27 @@ def test_hunt_cli_matches_reference_json(tmp_path, case, index):
     assert len(got) == len(want) == len(qs)
     for q, (g, w) in enumerate(zip(got, want)):
         assert g == w, (case, q)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,index", [("t1m_e1", "t1m"), ("stress_e2", "stress")])
+def test_hunt_cli_devices_shards_the_queries(tmp_path, case, index):
+    """--devices: the FASTA is cut into contiguous shards, one replica of the index and one host thread per
+    entry; the JSON comes out in input order and equals the reference's.  Two shards on one GPU always;
+    two GPUs (with the NCCL exchange of the hit records: dg_comm_init / dg_allgather_hits) when the box has them."""
+    import torch
+    d = make_genome_dir(tmp_path, index)
+    qs = fasta_of(case, os.path.join(d, "q.fa"))
+    flags = open(os.path.join(GOLDEN, case + ".flags.txt")).read().split()
+    want = open(os.path.join(GOLDEN, case + ".jsonl")).read()
+    lists = ["0,0", "0,0,0"] + (["0,1"] if torch.cuda.device_count() >= 2 else [])
+    for devs in lists:
+        r = run(["hunt", "-g", "genome.fa.gz", "--devices", devs] + flags + ["q.fa"], cwd=d,
+                env=dict(os.environ, DICEY_B200_TRACE="1"))
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == want, devs
+        if devs == "0,1":
+            assert "dg_allgather_hits" in r.stderr
 
 
 @pytest.mark.gpu
