@@ -154,6 +154,29 @@ StreamPool* pool_of(cudaStream_t st) {
   return p;
 }
 
+// A side stream per batch stream: the slow path of one tile (k_resolve: latency-bound) runs there while
+// the probes of the next tile (k_probe_*: DRAM-bound) run on the batch stream.
+struct AuxStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[8] = {};
+  unsigned next = 0;
+  cudaEvent_t event() { return ev[next++ & 7u]; }
+};
+std::mutex g_aux_mu;
+std::map<cudaStream_t, AuxStream*> g_aux;
+AuxStream* aux_of(cudaStream_t st) {
+  std::lock_guard<std::mutex> g(g_aux_mu);
+  auto it = g_aux.find(st);
+  if (it != g_aux.end()) return it->second;
+  AuxStream* a = new AuxStream();
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (cudaStreamCreateWithPriority(&a->s, cudaStreamNonBlocking, greatest) != cudaSuccess) { delete a; return nullptr; }
+  for (auto& e : a->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  g_aux[st] = a;
+  return a;
+}
+
 template <typename T>
 struct ABuf {  // stream-ordered allocation through the stream's block cache
   T* p = nullptr;
@@ -1020,11 +1043,12 @@ __device__ __forceinline__ void pair_slot(uint32_t u, int m, int& p1, int& k1i, 
 
 template <bool INDEL>
 __global__ void __launch_bounds__(256, 6) k_probe_singles(const __grid_constant__ PackedArgs a, const __grid_constant__ ProbeShape sh,
-                                                          uint8_t* __restrict__ masks) {
+                                                          uint64_t slot0, uint64_t nslots, uint8_t* __restrict__ masks) {
   if (*sh.irregular & 1u) return;
-  const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int m = sh.m;
-  if (slot >= sh.npairs * (uint64_t)m) return;
+  if (tid >= nslots) return;
+  const uint64_t slot = slot0 + tid;
   if (slot == 0) atomicAdd(sh.n_scripts, sh.scripts_per_pair * sh.npairs);
   const uint64_t pair = slot / (uint32_t)m;
   const int p = (int)(slot - pair * (uint64_t)m);
@@ -1034,7 +1058,7 @@ __global__ void __launch_bounds__(256, 6) k_probe_singles(const __grid_constant_
   if (!INDEL && p == 0) {   // Hamming sets hold the unedited string as well: bit 7 of position 0
     if (presence_probe(a, code0, m, 0)) mask |= 0x80u;
   }
-  masks[slot] = (uint8_t)mask;
+  masks[tid] = (uint8_t)mask;
 }
 
 template <bool INDEL>
@@ -1062,7 +1086,8 @@ __global__ void __launch_bounds__(256, 5) k_probe_pairs(const __grid_constant__ 
 template <bool INDEL>
 __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ IndexView ix, const __grid_constant__ PackedArgs a,
                                                     const __grid_constant__ SearchOut out, const __grid_constant__ ProbeShape sh,
-                                                    const uint8_t* __restrict__ masks, uint64_t nbytes, uint64_t pair0, int pairs) {
+                                                    const uint8_t* __restrict__ masks, uint64_t nbytes, uint64_t pair0, int pairs,
+                                                    uint64_t slot0) {
   constexpr int S = INDEL ? 8 : 3;
   constexpr int CS = INDEL ? 9 : 4;
   constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -1119,8 +1144,9 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Inde
       const uint64_t slot = tok >> 3;
       const int kk = (int)(tok & 7u);
       if (!pairs) {
-        const uint64_t pair = slot / (uint32_t)m;
-        const int p = (int)(slot - pair * (uint64_t)m);
+        const uint64_t gslot = slot0 + slot;
+        const uint64_t pair = gslot / (uint32_t)m;
+        const int p = (int)(gslot - pair * (uint64_t)m);
         q = a.reverse ? (uint32_t)(pair >> 1) : (uint32_t)pair;
         const int strand = a.reverse ? (int)(pair & 1) : 0;
         const uint64_t code0 = a.qcode[2 * (uint64_t)q + strand];
@@ -1322,8 +1348,21 @@ __device__ __forceinline__ Packed4 packed2_to_packed4(uint64_t code, int L) {
   return p;
 }
 
+// group_cnt / group_rank (may be null): the first half of a counting sort by (query, strand) -- every
+// candidate takes the next place of its group; the dropped ones (sentinel) count per warp
+__device__ __forceinline__ void key_count(uint32_t qs, uint32_t sentinel, uint32_t i, uint32_t* group_cnt, uint32_t* group_rank) {
+  if (!group_cnt) return;
+  if (qs != sentinel) { group_rank[i] = atomicAdd(&group_cnt[qs], 1u); return; }
+  const unsigned peers = __activemask();   // (all dropped candidates of the warp that reach this point together)
+  const uint32_t lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(&group_cnt[sentinel], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  group_rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
 __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t n, uint32_t sentinel, CandKey* __restrict__ keys,
-                            int slow_keys) {
+                            int slow_keys, uint32_t* __restrict__ group_cnt, uint32_t* __restrict__ group_rank) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Cand c = cands[i];
@@ -1344,6 +1383,7 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
     k.qs = (c.q << 1) | (c.code & 1u);
     k.idx = i;
     keys[i] = k;
+    key_count(k.qs, sentinel, i, group_cnt, group_rank);
     return;
   }
   if ((b.qflag[c.q] & 2) && !slow_keys) {
@@ -1428,6 +1468,15 @@ __global__ void k_cand_keys(BatchDev b, const Cand* __restrict__ cands, uint32_t
   k.qs = keep ? ((c.q << 1) | (uint32_t)strand) : sentinel;
   k.idx = i;
   keys[i] = k;
+  key_count(k.qs, sentinel, i, group_cnt, group_rank);
+}
+// second half of the counting sort: groups laid out by the scanned counts (order inside a group: k_group_order)
+__global__ void k_scatter_keys(const CandKey* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ group_off,
+                               const uint32_t* __restrict__ group_rank, CandKey* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const CandKey k = keys[i];
+  out[group_off[k.qs] + group_rank[i]] = k;
 }
 __global__ void k_unique_keys(const CandKey* __restrict__ keys, uint32_t n, uint32_t sentinel, uint8_t* __restrict__ keep) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1882,6 +1931,20 @@ void release_stream_pools(const cudaStream_t* streams, int n) {
       std::lock_guard<std::mutex> g(g_pools_mu);
       auto it = g_pools.find(streams[i]);
       if (it != g_pools.end()) { p = it->second; g_pools.erase(it); }
+    }
+    {
+      AuxStream* a = nullptr;
+      {
+        std::lock_guard<std::mutex> g(g_aux_mu);
+        auto it = g_aux.find(streams[i]);
+        if (it != g_aux.end()) { a = it->second; g_aux.erase(it); }
+      }
+      if (a) {
+        cudaStreamSynchronize(a->s);
+        for (auto& e : a->ev) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(a->s);
+        delete a;
+      }
     }
     if (!p) continue;
     cudaStreamSynchronize(streams[i]);
@@ -2578,7 +2641,7 @@ static int run_impl(dg_batch* b) {
         // the regular batch: probes and slow path in separate kernels (k_probe_*, k_resolve)
         const int um = (int)b->uniform_len;
         const int ud = (int)std::min<uint32_t>(b->par.distance, um > 0 ? (uint32_t)um - 1 : 0);
-        static const bool no_split = getenv("DG_NO_SPLIT") != nullptr;
+        const bool no_split = getenv("DG_NO_SPLIT") != nullptr;
         const bool split = !no_split && um > 0 && !b->par.seed_len && ud >= 1 && um + ud <= kMaxPacked && v.KB != 0;
         const uint32_t* skip = split ? b->irregular.p : nullptr;
         if (split) {
@@ -2596,33 +2659,55 @@ static int run_impl(dg_batch* b) {
           const uint64_t n1 = npairs * (uint64_t)um;
           ABuf<uint8_t> m1;
           m1.alloc(n1 + 8, st);
-          const unsigned rblocks = (unsigned)std::min<uint64_t>((uint64_t)nsm * 8, (n1 / 4 + 255) / 256 + 1);
+          // tiles: the slow path of tile i (side stream) overlaps the probes of tile i + 1 (batch stream)
+          const bool no_overlap = getenv("DG_NO_OVERLAP") != nullptr;
+          AuxStream* aux = no_overlap ? nullptr : aux_of(st);
+          cudaStream_t rs = aux ? aux->s : st;
+          auto after = [&](cudaStream_t from, cudaStream_t to) {   // `to` continues once `from` got this far
+            if (!aux || from == to) return;
+            cudaEvent_t e = aux->event();
+            DG_CUDA(cudaEventRecord(e, from));
+            DG_CUDA(cudaStreamWaitEvent(to, e, 0));
+          };
+          after(st, rs);   // (the side stream starts behind everything the batch stream has queued)
+          const uint64_t ntile1 = n1 >= (1ull << 22) ? 4 : 1;
           if (attempt == 0) prof_mark(ix, 6, st);
-          if (indel) k_probe_singles<true><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
-          else k_probe_singles<false><<<grid_for(n1, 256), 256, 0, st>>>(pa, shp, m1.p);
-          if (attempt == 0) prof_mark(ix, 7, st);
-          if (indel) k_resolve<true><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
-          else k_resolve<false><<<rblocks, 256, 0, st>>>(v, pa, so, shp, m1.p, n1, 0, 0);
+          for (uint64_t t = 0; t < ntile1; ++t) {
+            const uint64_t s0 = (n1 * t / ntile1) & ~3ull, s1 = t + 1 == ntile1 ? n1 : ((n1 * (t + 1) / ntile1) & ~3ull);
+            const uint64_t ns = s1 - s0;
+            if (!ns) continue;
+            if (indel) k_probe_singles<true><<<grid_for(ns, 256), 256, 0, st>>>(pa, shp, s0, ns, m1.p + s0);
+            else k_probe_singles<false><<<grid_for(ns, 256), 256, 0, st>>>(pa, shp, s0, ns, m1.p + s0);
+            if (attempt == 0 && t + 1 == ntile1) prof_mark(ix, 7, st);
+            after(st, rs);
+            const unsigned rb = (unsigned)std::min<uint64_t>((uint64_t)nsm * 8, (ns / 4 + 255) / 256 + 1);
+            if (indel) k_resolve<true><<<rb, 256, 0, rs>>>(v, pa, so, shp, m1.p + s0, ns, 0, 0, s0);
+            else k_resolve<false><<<rb, 256, 0, rs>>>(v, pa, so, shp, m1.p + s0, ns, 0, 0, s0);
+            launches += 2;
+          }
           probe_timed = true;
-          launches += 2;
+          ABuf<uint8_t> m2[2];
           if (ud >= 2) {
-            // pairs of events: ~13 k scripts per string; tiles of pairs keep the result bytes at <= 256 MB
-            const uint64_t tile = std::max<uint64_t>(1, (256ull << 20) / shp.n2);
-            ABuf<uint8_t> m2;
-            m2.alloc(std::min(tile, npairs) * (uint64_t)shp.n2 + 8, st);
-            for (uint64_t p0 = 0; p0 < npairs; p0 += tile) {
+            // pairs of events: ~13 k scripts per string; tiles of pairs keep the result bytes at <= 128 MB each
+            const uint64_t tile = std::max<uint64_t>(1, (128ull << 20) / shp.n2);
+            for (auto& mb : m2) mb.alloc(std::min(tile, npairs) * (uint64_t)shp.n2 + 8, st);
+            cudaEvent_t freed[2] = {nullptr, nullptr};
+            uint64_t ti = 0;
+            for (uint64_t p0 = 0; p0 < npairs; p0 += tile, ++ti) {
               const uint64_t np = std::min(tile, npairs - p0), nb = np * (uint64_t)shp.n2;
               const unsigned rb = (unsigned)std::min<uint64_t>((uint64_t)nsm * 8, (nb / 4 + 255) / 256 + 1);
-              if (indel) {
-                k_probe_pairs<true><<<grid_for(nb, 256), 256, 0, st>>>(pa, shp, p0, np, m2.p);
-                k_resolve<true><<<rb, 256, 0, st>>>(v, pa, so, shp, m2.p, nb, p0, 1);
-              } else {
-                k_probe_pairs<false><<<grid_for(nb, 256), 256, 0, st>>>(pa, shp, p0, np, m2.p);
-                k_resolve<false><<<rb, 256, 0, st>>>(v, pa, so, shp, m2.p, nb, p0, 1);
-              }
+              uint8_t* mp = m2[ti & 1].p;
+              if (aux && freed[ti & 1]) DG_CUDA(cudaStreamWaitEvent(st, freed[ti & 1], 0));   // its previous reader is done
+              if (indel) k_probe_pairs<true><<<grid_for(nb, 256), 256, 0, st>>>(pa, shp, p0, np, mp);
+              else k_probe_pairs<false><<<grid_for(nb, 256), 256, 0, st>>>(pa, shp, p0, np, mp);
+              after(st, rs);
+              if (indel) k_resolve<true><<<rb, 256, 0, rs>>>(v, pa, so, shp, mp, nb, p0, 1, 0);
+              else k_resolve<false><<<rb, 256, 0, rs>>>(v, pa, so, shp, mp, nb, p0, 1, 0);
+              if (aux) { freed[ti & 1] = aux->event(); DG_CUDA(cudaEventRecord(freed[ti & 1], rs)); }
               launches += 2;
             }
           }
+          after(rs, st);   // join: everything behind this point sees every candidate (and may reuse the mask buffers)
         }
         if (b->par.indel) k_search_packed<true><<<blocks, 256, 0, st>>>(v, pa, so, ppw, skip);
         else k_search_packed<false><<<blocks, 256, 0, st>>>(v, pa, so, ppw, skip);
@@ -2679,16 +2764,34 @@ static int run_impl(dg_batch* b) {
       for (int attempt = 0; attempt < 2; ++attempt) {
         const bool by_group = attempt == 0 && !full_sort_always;
         const int slow_keys = getenv("DG_SLOW_KEYS") ? 1 : 0;   // test knob: the byte-wise key builder for every query
-        k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p, slow_keys);
         size_t tb = 0;
-        if (by_group) {
+        const bool radix_groups = getenv("DG_GROUP_RADIX") != nullptr;   // test knob: the former 3 radix passes
+        if (by_group && !radix_groups && sentinel != 0xFFFFFFFFu) {
+          // counting sort by (query, strand): groups hold 1-2 candidates, so a count per group taken while
+          // the keys are made, one scan and one scatter replace three radix passes; then a rank count
+          // inside each small group
+          ABuf<CandKey> kc;
+          ABuf<uint32_t> gcnt, goff, grank;
+          kc.alloc(n, st);
+          gcnt.alloc((size_t)sentinel + 2, st);
+          goff.alloc((size_t)sentinel + 2, st);
+          grank.alloc(n, st);
+          DG_CUDA(cudaMemsetAsync(gcnt.p, 0, ((size_t)sentinel + 2) * 4, st));
+          k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p, slow_keys, gcnt.p, grank.p);
+          cub::DeviceScan::ExclusiveSum(nullptr, tb, gcnt.p, goff.p, (int)(sentinel + 1), st);
+          cub::DeviceScan::ExclusiveSum(ensure_tmp(tb), tb, gcnt.p, goff.p, (int)(sentinel + 1), st);
+          k_scatter_keys<<<grid_for(n, B), B, 0, st>>>(ka.p, n, goff.p, grank.p, kc.p);
+          k_group_order<<<grid_for(n, B), B, 0, st>>>(kc.p, n, sentinel, kb.p, big.p);
+        } else if (by_group) {
           // 3 radix passes on (query, strand), then a rank count inside each small group
           ABuf<CandKey> kc;
           kc.alloc(n, st);
+          k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p, slow_keys, nullptr, nullptr);
           cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.p, kc.p, (int)n, CandKeyDecomposer{}, 128, 128 + qbits, st);
           cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, ka.p, kc.p, (int)n, CandKeyDecomposer{}, 128, 128 + qbits, st);
           k_group_order<<<grid_for(n, B), B, 0, st>>>(kc.p, n, sentinel, kb.p, big.p);
         } else {
+          k_cand_keys<<<grid_for(n, 128), 128, 0, st>>>(bd, cur, n, sentinel, ka.p, slow_keys, nullptr, nullptr);
           cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
           cub::DeviceRadixSort::SortKeys(ensure_tmp(tb), tb, ka.p, kb.p, (int)n, CandKeyDecomposer{}, begin_bit, 128 + qbits, st);
         }
@@ -3248,9 +3351,16 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
       rest -= rest / 2;
       p.bounds.push_back((uint32_t)q);
     }
-  } else {
+  } else if (getenv("DG_UNEVEN")) {
     for (uint64_t q = getenv("DG_NO_STAGGER") ? chunk : chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
     if (p.bounds.size() > 1 && nq - p.bounds.back() < chunk / 4) p.bounds.pop_back();  // no tiny tail chunk
+  } else {
+    // a half-sized first chunk (the GPU starts early, the workers run out of phase), then equal chunks:
+    // a small last chunk is latency-bound and finishes long after the one before it
+    const uint64_t first = std::min<uint64_t>(chunk / 2, nq);
+    const uint64_t rest = nq - first;
+    const uint64_t nrest = (rest + chunk - 1) / chunk;
+    for (uint64_t k = 0; k < nrest; ++k) p.bounds.push_back((uint32_t)(first + rest * k / nrest));
   }
   p.bounds.push_back(nq);
   const uint32_t nchunks = (uint32_t)p.bounds.size() - 1;
