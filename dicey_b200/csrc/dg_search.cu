@@ -2430,7 +2430,8 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
     struct Out { bool capped[2] = {false, false}; bool unkeyed = false; std::vector<ulonglong2> keys[2]; std::vector<std::string> all[2]; };
     std::vector<Out> outs(flagged.size());
     auto work = [&](size_t lo, size_t hi) {
-      NeighborReplay nr;
+      NeighborReplay nr_any;
+      NeighborReplayPacked nr_packed;
       for (size_t i = lo; i < hi; ++i) {
         const uint32_t q = flagged[i];
         const uint8_t* s = fwd.data() + off[q];
@@ -2446,15 +2447,18 @@ static int resolve_truncation(dg_batch* b, cudaStream_t st) {
               str.push_back(ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N');
             }
           }
-          const bool capped = nr.run(str, (int)dist[q], indel, cap);
+          // (ACGT-only strings that fit one word take the packed form of the replay, ~10 times faster)
+          const bool use_packed = NeighborReplayPacked::fits(str, (int)dist[q]);
+          const bool capped = use_packed ? nr_packed.run(str, (int)dist[q], indel, cap) : nr_any.run(str, (int)dist[q], indel, cap);
+          auto replayed = [&]() { return use_packed ? nr_packed.strings() : nr_any.strings(); };
           outs[i].capped[strand] = capped;
           if ((int)dist[q] > kMaxDist) {   // beyond the enumerated distances: the whole set goes to the device as a list
-            outs[i].all[strand] = nr.strings();
+            outs[i].all[strand] = replayed();
             std::sort(outs[i].all[strand].begin(), outs[i].all[strand].end());
             continue;
           }
           if (!capped) continue;
-          for (const std::string& t : nr.strings()) {
+          for (const std::string& t : replayed()) {
             if ((int)t.size() > kKeyChars) { outs[i].unkeyed = true; break; }
             ulonglong2 k = make_ulonglong2(0, 0);
             for (int j = 0; j < (int)t.size(); ++j) {

@@ -152,11 +152,21 @@ int main(int argc, char** argv) {
     uint32_t x = (uint32_t)strtoul(argv[5], nullptr, 10);
     std::string q;
     NeighborReplay nr;
+    NeighborReplayPacked np;
     while (std::getline(f, q)) {
       if (q.empty()) continue;
-      nr.run(q, d, indel, x);
+      const bool capped = nr.run(q, d, indel, x);
       std::vector<std::string> v = nr.strings();
       std::sort(v.begin(), v.end());
+      if (NeighborReplayPacked::fits(q, d)) {   // the packed form must give the same set and the same verdict
+        const bool capped2 = np.run(q, d, indel, x);
+        std::vector<std::string> v2 = np.strings();
+        std::sort(v2.begin(), v2.end());
+        if (capped2 != capped || v2 != v || np.peak() != nr.peak()) {
+          fprintf(stderr, "packed replay differs on %s (d %d indel %d x %u): %zu vs %zu strings\n", q.c_str(), d, (int)indel, x, v2.size(), v.size());
+          return 3;
+        }
+      }
       std::cout << "Q\t" << q << '\t' << v.size() << '\n';
       for (auto const& s : v) std::cout << s << '\n';
     }
