@@ -1866,9 +1866,11 @@ __global__ void k_rebase_recs(dg_rec* __restrict__ recs, uint64_t nhits, uint32_
   peer_store(peer, hit_base + i, w);
 }
 __global__ void k_pack_qmeta(const uint32_t* __restrict__ status, const uint32_t* __restrict__ dist, uint32_t nq,
-                             uint16_t* __restrict__ out) {
+                             uint16_t* __restrict__ out, const uint64_t* __restrict__ qcode, uint64_t* __restrict__ qpack) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < nq) out[q] = (uint16_t)((status[q] & 0xFFu) | ((dist[q] & 0xFFu) << 8));
+  if (q >= nq) return;
+  out[q] = (uint16_t)((status[q] & 0xFFu) | ((dist[q] & 0xFFu) << 8));
+  if (qpack) qpack[q] = qcode[2 * (uint64_t)q];   // the forward code (meaningful when the batch is regular)
 }
 
 // exact backward search of literal patterns (one thread per pattern)
@@ -2057,15 +2059,51 @@ struct dg_result {
   uint64_t uniform_len = 0;       // > 0: every query has this length; else seq_off holds nq + 1 offsets
   std::vector<uint64_t> seq_off;
   std::vector<uint64_t> cum;      // record starts of the index (text_pos of an expanded dg_hit)
+  // sequences of chunks whose queries were all ACGT-only and of one length came from the device as
+  // 2-bit codes (8 bytes per query instead of its characters); decoded into `seqs` on first use
+  struct PackedSeqs { uint32_t q0, q1, len; };
+  std::vector<PackedSeqs> packed_seqs;
+  HostBuf qpack;                  // uint64 per query (only the entries of packed chunks are meaningful)
   mutable std::mutex mu;
-  mutable bool have_qinfo = false, have_hits = false;
+  mutable bool have_qinfo = false, have_hits = false, have_seqs = true;
   uint64_t qstart(uint32_t q) const { return uniform_len ? (uint64_t)q * uniform_len : seq_off[q]; }
   uint32_t qlen(uint32_t q) const { return uniform_len ? (uint32_t)uniform_len : (uint32_t)(seq_off[q + 1] - seq_off[q]); }
 };
 
 namespace {
+// the characters of the chunks that travelled as 2-bit codes
+void ensure_seqs(const dg_result* cr) {
+  dg_result* r = const_cast<dg_result*>(cr);
+  if (r->have_seqs) return;
+  std::lock_guard<std::mutex> g(r->mu);
+  if (r->have_seqs) return;
+  const uint64_t* codes = (const uint64_t*)r->qpack.p;
+  uint8_t* out = (uint8_t*)r->seqs.p;
+  for (const auto& ch : r->packed_seqs) {
+    const uint32_t L = ch.len;
+    auto work = [&](uint32_t lo, uint32_t hi) {
+      for (uint32_t q = lo; q < hi; ++q) {
+        const uint64_t code = codes[q];
+        uint8_t* s = out + r->qstart(q);
+        for (uint32_t j = 0; j < L; ++j) s[j] = (uint8_t)"ACGT"[(code >> (2 * (L - 1 - j))) & 3];
+      }
+    };
+    const uint32_t n = ch.q1 - ch.q0;
+    const unsigned nt = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(8, n / 32768));
+    if (nt <= 1) {
+      work(ch.q0, ch.q1);
+    } else {
+      std::vector<std::thread> ts;
+      for (unsigned t = 0; t < nt; ++t) ts.emplace_back(work, ch.q0 + (uint32_t)((uint64_t)n * t / nt), ch.q0 + (uint32_t)((uint64_t)n * (t + 1) / nt));
+      for (auto& t : ts) t.join();
+    }
+  }
+  r->have_seqs = true;
+}
+
 // the strand's search string of query q: the normalised query, or its reverse complement
 inline void strand_query(const dg_result* r, uint32_t q, bool minus, std::vector<uint8_t>& out) {
+  ensure_seqs(r);
   const uint8_t* s = (const uint8_t*)r->seqs.p + r->qstart(q);
   const uint32_t m = r->qlen(q);
   out.resize(m);
@@ -2106,6 +2144,7 @@ void ensure_qinfo(const dg_result* cr) {
 void ensure_hits(const dg_result* cr) {
   dg_result* r = const_cast<dg_result*>(cr);
   if (!r->compact) return;
+  ensure_seqs(r);
   std::lock_guard<std::mutex> g(r->mu);
   if (r->have_hits) return;
   const uint64_t n = r->nhits;
@@ -2201,6 +2240,7 @@ struct dg_batch {
   ABuf<dg_hit> hits;
   ABuf<dg_rec> recs;           // compact form (hunt): instead of hits + pool
   ABuf<uint16_t> qmeta;        // compact form: status | distance << 8 per query
+  ABuf<uint64_t> qpack;        // compact form: the forward 2-bit code per query (the sequence of a regular batch)
   bool compact = false;
   ABuf<int4> wire;
   ABuf<uint8_t> pool;
@@ -3020,7 +3060,8 @@ static int run_impl(dg_batch* b) {
     }
     if (b->compact) {
       // (no alignment pool, hence no size to read back: the run ends without a host round trip)
-      if (nq) { k_pack_qmeta<<<grid_for(nq, B), B, 0, st>>>(b->status.p, b->dist.p, nq, b->qmeta.p); ++launches; }
+      b->qpack.alloc(nq ? nq : 1, st);
+      if (nq) { k_pack_qmeta<<<grid_for(nq, B), B, 0, st>>>(b->status.p, b->dist.p, nq, b->qmeta.p, b->qcode.p, b->qpack.p); ++launches; }
     } else {
       unsigned long long used = 0;
       DG_CUDA(cudaMemcpyAsync(&used, cursor.p, 8, cudaMemcpyDeviceToHost, st));
@@ -3182,7 +3223,6 @@ struct ChunkPipe {
   const uint8_t* d_up = nullptr; // the caller's sequences in device memory, chunk c valid once uploaded > c
   std::vector<cudaEvent_t> up_ev, copied_ev, rebased_ev;   // per chunk, from the index's event pool
   uint32_t uploaded = 0;
-  uint32_t seq_copied = 0;           // chunks whose sequence bytes the uploader has copied into the result (host)
   std::vector<uint64_t> chunk_len;   // per chunk: the common query length, or 0 (set before `uploaded` passes the chunk)
   PeerOut peer;                      // peer mode of a bound communicator (compact results only)
   uint64_t hit_base = 0, pool_base = 0;
@@ -3211,7 +3251,10 @@ struct ChunkPipe {
         tm[0] = now() - t_begin;
         // chunk c runs on a stream of higher priority than chunks c + 1 and c + 2, which are in flight
         // next to it: its pending blocks are dispatched first, so chunks finish -- and their records
-        // start leaving -- one after another instead of all together
+        // start leaving -- one after another instead of all together.  (The six priority levels wrap:
+        // every sixth chunk starts again at the highest one and briefly outranks the two chunks before it;
+        // batches of up to ~1.4 M queries never get there.)  A stream belongs to one worker at a time
+        // as long as kXStreams is a multiple of the worker count; the stream pools are locked anyway.
         cudaStream_t st = idx->xstream[c % (uint32_t)dg_index::kXStreams];
         // release chunks whose records have reached the host (keeps at most 2 per worker alive)
         while (!live.empty() && (live.size() >= 2 || cudaEventQuery(live.front().copied) == cudaSuccess)) {
@@ -3297,14 +3340,20 @@ struct ChunkPipe {
           }
           r->transfer_bytes += b->nhits * sizeof(dg_hit) + b->pool_bytes + (size_t)cn * 16;
         }
-        // the normalised sequences: the uploader thread copies the caller's bytes into the result on the
-        // host; only a chunk in which normalisation changed something (lower case, non-ACGT) sends its
-        // device copy afterwards
-        if (cn && b->nbytes && (b->h_irregular & 8u)) {
-          cv.wait(lk, [&] { return seq_copied > c || rc != DG_OK; });
-          if (rc != DG_OK) break;
-          DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
-          r->transfer_bytes += b->nbytes;
+        // the normalised sequences: a regular chunk (every query ACGT-only, one length <= 31) sends the 2-bit
+        // codes k_prepare made (8 bytes per query, decoded on the host when someone asks); any other chunk
+        // sends the characters
+        if (cn && b->nbytes) {
+          const bool as_codes = compact && !(b->h_irregular & 1u) && b->uniform_len > 0 && b->uniform_len <= 31 && b->qpack.p;
+          if (as_codes) {
+            DG_CUDA(cudaMemcpyAsync((uint64_t*)r->qpack.p + q0, b->qpack.p, (size_t)cn * 8, cudaMemcpyDeviceToHost, cs));
+            r->packed_seqs.push_back(dg_result::PackedSeqs{q0, q1, b->uniform_len});
+            r->have_seqs = false;
+            r->transfer_bytes += (size_t)cn * 8;
+          } else {
+            DG_CUDA(cudaMemcpyAsync((uint8_t*)r->seqs.p + offsets[q0], b->fwd.p, b->nbytes, cudaMemcpyDeviceToHost, cs));
+            r->transfer_bytes += b->nbytes;
+          }
         }
         DG_CUDA(cudaEventRecord(copied, cs));
         hit_base += b->nhits;
@@ -3394,6 +3443,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     if (!params->seed_len && !full_records && params->distance <= (uint32_t)kMaxCompactDist) {
       comm_peer_out(idx, idx, &p.peer);
       r->qmeta.alloc((size_t)nq * 2, true);
+      r->qpack.alloc((size_t)nq * 8, true);
     } else {
       r->qoff.alloc(((size_t)nq + 1) * 8, true);
       r->status.alloc((size_t)nq * 4, true);
@@ -3450,15 +3500,6 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
     } catch (CudaFail& e) {
       p.fail(e.code, last_error_ref());
     }
-    // the result's copy of the sequences (the normalised form equals the input unless a chunk says otherwise)
-    for (uint32_t c = 0; c < nchunks && p.rc == DG_OK; ++c) {
-      const uint64_t b0 = offsets[p.bounds[c]], b1 = offsets[p.bounds[c + 1]];
-      if (b1 > b0) memcpy((uint8_t*)r->seqs.p + b0, seqs + b0, b1 - b0);
-      { std::lock_guard<std::mutex> g(p.mu); p.seq_copied = c + 1; }
-      p.cv.notify_all();
-    }
-    { std::lock_guard<std::mutex> g(p.mu); p.seq_copied = nchunks; }
-    p.cv.notify_all();
     const double tt0 = now();
     keep_offsets(r, offsets, nq);   // (the calling thread has nothing else to do while the workers run)
     const double tt1 = now();
@@ -3625,6 +3666,7 @@ const char* dg_result_pool(const dg_result* r, uint64_t* bytes) {
   return r ? (const char*)r->pool.p : nullptr;
 }
 const char* dg_result_sequences(const dg_result* r, uint64_t* bytes) {
+  if (r) ensure_seqs(r);
   if (bytes) *bytes = r ? r->seqs.bytes : 0;
   return r ? (const char*)r->seqs.p : nullptr;
 }
@@ -3636,6 +3678,7 @@ int dg_result_pack(const dg_result* r, void* buf, uint64_t* bytes) {
   if (!r || !bytes) { set_error("null argument"); return DG_ERR_ARG; }
   ensure_qinfo(r);   // the packed form is the full one: a compact result is expanded first
   ensure_hits(r);
+  ensure_seqs(r);
   uint64_t nq = r->nq, nh = r->nhits, np = r->pool.bytes, ns = r->seqs.bytes;
   uint64_t need = 32 + (nq + 1) * 8 + nq * 8 + nh * sizeof(dg_hit) + np + ns;
   if (!buf) { *bytes = need; return DG_OK; }
