@@ -220,7 +220,11 @@ __global__ void k_synth_text(uint64_t seed, uint64_t reclen, uint64_t n, uint8_t
 }
 
 // ---------------------------------------------------------------- suffix array on the GPU
-struct CodeMap { uint8_t code[256]; };
+struct CodeMap {
+  uint8_t code[256];
+  uint8_t bits;    // bits per symbol code: 3 (up to 8 symbols with the sentinel), 4 or 5 (IUPAC texts, up to 32)
+  uint8_t syms;    // symbols per 63-bit sort key: 21, 15 or 12
+};
 
 __global__ void k_byte_hist(const uint8_t* __restrict__ t, uint64_t n, unsigned long long* __restrict__ hist) {
   __shared__ unsigned int sh[256];
@@ -232,15 +236,18 @@ __global__ void k_byte_hist(const uint8_t* __restrict__ t, uint64_t n, unsigned 
   for (int i = threadIdx.x; i < 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 
-constexpr int kKeySyms = 21;  // 3-bit codes per 63-bit key
+constexpr int kKeySyms = 21;  // 3-bit codes per 63-bit key (the most a key holds; fewer with wider codes)
 
 __device__ __forceinline__ uint64_t suffix_key(const uint8_t* __restrict__ t, uint64_t n, uint64_t i, const CodeMap& cm) {
   uint64_t key = 0;
+  const int bits = cm.bits, syms = cm.syms;
 #pragma unroll
   for (int j = 0; j < kKeySyms; ++j) {
-    uint64_t p = i + j;
-    uint64_t c = p < n ? cm.code[t[p]] : 0;
-    key = (key << 3) | c;
+    if (j < syms) {
+      uint64_t p = i + j;
+      uint64_t c = p < n ? cm.code[t[p]] : 0;
+      key = (key << bits) | c;
+    }
   }
   return key;
 }
@@ -253,22 +260,23 @@ struct InBucket {
   __device__ bool operator()(uint32_t i) const {
     uint32_t c0 = cm.code[t[i]];
     uint32_t c1 = (uint64_t)i + 1 < n ? cm.code[t[(uint64_t)i + 1]] : 0;
-    return ((c0 << 3) | c1) == bucket;
+    return ((c0 << cm.bits) | c1) == bucket;
   }
 };
 
 __global__ void k_pair_hist(const uint8_t* __restrict__ t, uint64_t n, CodeMap cm, unsigned long long* __restrict__ hist) {
-  __shared__ unsigned int sh[64];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0;
+  __shared__ unsigned int sh[1024];
+  const int nb = 1 << (2 * cm.bits);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t c0 = cm.code[t[i]];
     uint32_t c1 = i + 1 < n ? cm.code[t[i + 1]] : 0;
-    atomicAdd(&sh[(c0 << 3) | c1], 1u);
+    atomicAdd(&sh[(c0 << cm.bits) | c1], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 
 __global__ void k_make_keys(const uint8_t* __restrict__ t, uint64_t n, CodeMap cm, const uint32_t* __restrict__ suf,
@@ -358,8 +366,9 @@ void sort_bucket(const uint8_t* text, uint64_t n, const CodeMap& cm, uint32_t* s
   const unsigned B = 256;
   k_make_keys<<<grid_for(cnt, B), B, 0, st>>>(text, n, cm, suf, cnt, 0, keys_a);
   size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a, keys_b, suf, suf_b, (int)cnt, 0, 57, st);
-  cub::DeviceRadixSort::SortPairs(tmp.ensure(tb), tb, keys_a, keys_b, suf, suf_b, (int)cnt, 0, 57, st);
+  const int key_bits = cm.bits * cm.syms, first_bits = cm.bits * (cm.syms - 2);   // (the first two symbols are the bucket's)
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a, keys_b, suf, suf_b, (int)cnt, 0, first_bits, st);
+  cub::DeviceRadixSort::SortPairs(tmp.ensure(tb), tb, keys_a, keys_b, suf, suf_b, (int)cnt, 0, first_bits, st);
   DG_CUDA(cudaMemcpyAsync(sa_out, suf_b, cnt * 4, cudaMemcpyDeviceToDevice, st));
   // ---- ties
   k_tie_flags<<<grid_for(cnt, B), B, 0, st>>>(keys_b, cnt, flag);
@@ -400,7 +409,7 @@ void sort_bucket(const uint8_t* text, uint64_t n, const CodeMap& cm, uint32_t* s
     cub::DeviceScan::InclusiveScan(tmp.ensure(tb2), tb2, head.p, gid.p, MaxOp(), (int)nt, st);
   }
   k_gather_suffix<<<grid_for(nt, B), B, 0, st>>>(sa_out, slots.p, nt, sufc.p);
-  uint64_t depth = kKeySyms;
+  uint64_t depth = cm.syms;
   uint32_t* cur_slots = slots.p;
   uint32_t* alt_slots = slots2.p;
   for (int round = 0; nt > 0; ++round) {
@@ -409,8 +418,8 @@ void sort_bucket(const uint8_t* text, uint64_t n, const CodeMap& cm, uint32_t* s
     k_make_keys<<<grid_for(nt, B), B, 0, st>>>(text, n, cm, sufc.p, nt, depth, key2.p);
     k_iota<<<grid_for(nt, B), B, 0, st>>>(perm.p, nt);
     size_t tb2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb2, key2.p, key2b.p, perm.p, perm2.p, (int)nt, 0, 63, st);
-    cub::DeviceRadixSort::SortPairs(tmp.ensure(tb2), tb2, key2.p, key2b.p, perm.p, perm2.p, (int)nt, 0, 63, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, key2.p, key2b.p, perm.p, perm2.p, (int)nt, 0, key_bits, st);
+    cub::DeviceRadixSort::SortPairs(tmp.ensure(tb2), tb2, key2.p, key2b.p, perm.p, perm2.p, (int)nt, 0, key_bits, st);
     k_gather_u32<<<grid_for(nt, B), B, 0, st>>>(gid.p, perm2.p, nt, gid2.p);
     cub::DeviceRadixSort::SortPairs(nullptr, tb2, gid2.p, gid.p, perm2.p, perm.p, (int)nt, 0, 32, st);
     cub::DeviceRadixSort::SortPairs(tmp.ensure(tb2), tb2, gid2.p, gid.p, perm2.p, perm.p, (int)nt, 0, 32, st);
@@ -435,7 +444,7 @@ void sort_bucket(const uint8_t* text, uint64_t n, const CodeMap& cm, uint32_t* s
     k_renumber<<<grid_for(nk, B), B, 0, st>>>(gid2.p, keep.p, nk, gid.p);
     std::swap(cur_slots, alt_slots);
     nt = nk;
-    depth += kKeySyms;
+    depth += cm.syms;
   }
 }
 
@@ -768,20 +777,24 @@ static void build_from_device_text(dg_index* ix) {
     Cb[s] = (uint32_t)run;
     if (hist[s]) {
       present[s] = 1;
-      if (sigma >= 8) { set_error("more than 7 distinct symbols: outside the GPU builder (use `dicey index`)"); throw CudaFail{DG_ERR_UNSUPPORTED}; }
+      if (sigma >= 32) { set_error("more than 31 distinct symbols: outside the GPU builder (use `dicey index`)"); throw CudaFail{DG_ERR_UNSUPPORTED}; }
       cm.code[s] = (uint8_t)sigma++;
       run += hist[s];
     }
   }
   for (int s = 0; s < 256; ++s) if (!present[s]) Cb[s] = 0;
   ix->sigma = sigma;
+  cm.bits = sigma <= 8 ? 3 : (sigma <= 16 ? 4 : 5);   // DNA texts (A C G T N, separator, sentinel) keep 21 symbols per key
+  cm.syms = (uint8_t)(63 / cm.bits);
+  if (cm.syms > kKeySyms) cm.syms = kKeySyms;
+  const uint32_t nbuckets = 1u << (2 * cm.bits);
   // bucket sizes by the first two symbols
   DevBuf<unsigned long long> d_ph;
-  d_ph.alloc(64);
-  DG_CUDA(cudaMemsetAsync(d_ph.p, 0, 64 * 8, st));
+  d_ph.alloc(nbuckets);
+  DG_CUDA(cudaMemsetAsync(d_ph.p, 0, nbuckets * 8, st));
   k_pair_hist<<<148 * 8, 256, 0, st>>>(text, n, cm, d_ph.p);
-  std::vector<unsigned long long> ph(64);
-  DG_CUDA(cudaMemcpyAsync(ph.data(), d_ph.p, 64 * 8, cudaMemcpyDeviceToHost, st));
+  std::vector<unsigned long long> ph(nbuckets);
+  DG_CUDA(cudaMemcpyAsync(ph.data(), d_ph.p, nbuckets * 8, cudaMemcpyDeviceToHost, st));
   DG_CUDA(cudaStreamSynchronize(st));
   uint64_t maxb = 0;
   for (auto v : ph) maxb = std::max<uint64_t>(maxb, v);
@@ -790,7 +803,7 @@ static void build_from_device_text(dg_index* ix) {
   DevBuf<uint8_t> flag;
   sa.alloc(n); suf.alloc(maxb); suf_b.alloc(maxb); keys_a.alloc(maxb); keys_b.alloc(maxb); flag.alloc(maxb); nsel.alloc(1);
   uint64_t out_pos = 0;
-  for (uint32_t b = 0; b < 64; ++b) {
+  for (uint32_t b = 0; b < nbuckets; ++b) {
     uint64_t cnt = ph[b];
     if (!cnt) continue;
     InBucket pred{text, n, cm, b};

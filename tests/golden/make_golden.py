@@ -342,9 +342,50 @@ def make_truncation_cases():
             f.write(run(["neighbors", nf, "-d", str(d), "-x", str(x)] + (["-n"] if ham else [])).encode())
 
 
+def make_iupac_case():
+    """A small text with IUPAC ambiguity codes (18 symbols with the separator and the sentinel): the index the
+    reference builds for it and one hunt case -- pins dg_index_build_text / dg_index_write_fm9 beyond the
+    seven-symbol DNA alphabet."""
+    rng = random.Random(4242)
+    tmp = "/tmp/dicey_golden"
+    os.makedirs(tmp, exist_ok=True)
+    recs = []
+    for r in range(3):
+        s = [rng.choice("ACGT") for _ in range(6000 + 500 * r)]
+        for _ in range(60):
+            s[rng.randrange(len(s))] = rng.choice("RYKMSWBDHVN")
+        for _ in range(3):
+            p0 = rng.randrange(len(s) - 30)
+            s[p0:p0 + rng.randint(2, 25)] = "N" * rng.randint(2, 25)
+        recs.append("".join(s))
+    text = "".join(r + "\n" for r in recs)
+    dump = os.path.join(tmp, "iupac.dump")
+    open(dump, "w").write(text)
+    with gzip.GzipFile(os.path.join(HERE, "iupac.dump.gz"), "wb", compresslevel=9, mtime=0) as f:
+        f.write(text.encode())
+    fm = os.path.join(HERE, "iupac.fm9")
+    print(run(["index", dump, fm, tmp]).strip())
+    rec = os.path.join(HERE, "iupac.rec.tsv")
+    open(rec, "w").write("".join(f"u{i + 1}\t{len(r)}\n" for i, r in enumerate(recs)))
+    qs = []
+    for i in range(24):
+        r = recs[i % 3]
+        m = rng.choice([16, 18, 20, 22])
+        p0 = rng.randrange(0, len(r) - m)
+        piece = list(r[p0:p0 + m])
+        if i % 3 == 1:
+            piece[rng.randrange(m)] = rng.choice("ACGT")
+        qs.append((f"i{i}", "".join(piece)))
+    hunt_case("iupac_e1", fm, rec, qs, ["-d", "1"])
+    hunt_case("iupac_h2", fm, rec, qs, ["-d", "2", "-n"])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "trunc":
+    if len(sys.argv) > 1 and sys.argv[1] == "iupac":
+        make_iupac_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trunc":
         make_truncation_cases()
     else:
         main()
         make_truncation_cases()
+        make_iupac_case()

@@ -261,6 +261,40 @@ def test_write_fm9(indexes, name, tmp_path, ref_bin):
         assert open(out).read() == open(os.path.join(GOLDEN, case + ".records.tsv")).read()
 
 
+def test_iupac_text_builds_and_hunts_like_the_reference(tmp_path):
+    """A text with IUPAC ambiguity codes (17 symbols: beyond the 3-bit codes of the DNA suffix sorter):
+    dg_index_build_text + dg_index_write_fm9 give the file `dicey index` (SDSL) wrote for the same text,
+    byte for byte, and hunt on either index gives the reference's records."""
+    text = gzip.open(os.path.join(GOLDEN, "iupac.dump.gz"), "rb").read()
+    names, lens = read_rec_tsv(os.path.join(GOLDEN, "iupac.rec.tsv"))
+    src = os.path.join(GOLDEN, "iupac.fm9")
+    dst = str(tmp_path / "iupac.fm9")
+    built = Index.build_text(text, 0)
+    loaded = Index.open(src, 0)
+    try:
+        assert built.info()["sigma"] == loaded.info()["sigma"] == 17
+        for what, dt in (("text", np.uint8), ("occ", np.uint32), ("sa_samples", np.uint32), ("sa_full", np.uint32)):
+            assert np.array_equal(built.debug_array(what, dt), loaded.debug_array(what, dt)), what
+        built.write_fm9(dst)
+        assert open(src, "rb").read() == open(dst, "rb").read()
+        assert open(src + "_check", "rb").read() == open(dst + "_check", "rb").read()
+        for ix in (built, loaded):
+            ix.set_records(names, lens)
+            for case in ("iupac_e1", "iupac_h2"):
+                qs = read_queries(os.path.join(GOLDEN, case + ".queries.txt"))
+                par = params_from_flags(open(os.path.join(GOLDEN, case + ".flags.txt")).read())
+                want = read_records(os.path.join(GOLDEN, case + ".records.tsv"))
+                want_json = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, case + ".jsonl"))]
+                res = ix.hunt([s for _, s in qs], par)
+                for q, (name, seq) in enumerate(qs):
+                    assert res.messages(q, par, seq.encode()) == want[q]["msgs"], (case, q)
+                    assert res.push_hits(q) == want[q]["push"], (case, q)
+                    assert hunt_json(res, q, par, names, "genome.fa.gz", "", name, seq.encode()) == want_json[q], (case, q)
+    finally:
+        built.close()
+        loaded.close()
+
+
 def test_chunked_pipeline_equals_single_batch(indexes, monkeypatch):
     """dg_hunt_batch cuts large batches into chunks whose hit records travel to the host while the
     next chunk is searched; ids and offsets are rebased on the device.  Same records either way."""
