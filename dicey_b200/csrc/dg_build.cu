@@ -898,35 +898,39 @@ int build_synthetic(uint64_t seed, uint32_t nrec, uint64_t reclen, int device, d
 namespace dg {
 namespace {
 
-struct WtShape {            // device-side description of the tree for k_wt_bits
+constexpr int kWtInternal = 32;   // internal nodes of the Huffman-shaped tree (alphabets of up to 32 symbols)
+constexpr int kWtClasses = 32;    // symbol classes: 0..3 = A C G T, 4.. = the other symbols of the text
+constexpr int kWtDepth = 32;      // longest root-to-leaf path
+struct WtShape {            // device-side description of the tree for k_wt_bits (lives in device memory)
   int n_internal;           // internal nodes, numbered 0..n_internal-1 in BFS order among internals
-  uint64_t bv_pos[8];       // start of each internal node's bit vector
-  uint8_t path_len[256];    // per byte symbol
-  uint8_t path_node[256][8];// internal node visited at depth d
-  uint8_t path_bit[256][8]; // branch taken at depth d
-  uint8_t member[8][8];     // member[v][k]: k-th symbol class (0..3 ACGT, 4.. rare list) lies under v
-  uint8_t rare_sym[4];      // byte values of the rare classes 4..7
   int n_rare;
+  uint64_t bv_pos[kWtInternal];        // start of each internal node's bit vector
+  uint8_t path_len[256];               // per byte symbol
+  uint8_t path_node[256][kWtDepth];    // internal node visited at depth d
+  uint8_t path_bit[256][kWtDepth];     // branch taken at depth d
+  uint8_t member[kWtInternal][kWtClasses];   // member[v][k]: k-th symbol class lies under v
+  uint8_t rare_sym[kWtClasses];        // byte values of the classes 4..
 };
 
 // one thread per occurrence block: appends the block's 64 symbols to every internal node on
 // their paths; bits are staged per node and flushed with one atomicOr per touched word
-__global__ void k_wt_bits(IndexView ix, WtShape sh, uint64_t nblocks, unsigned long long* __restrict__ bv) {
+__global__ void k_wt_bits(IndexView ix, const WtShape* __restrict__ shp, uint64_t nblocks, unsigned long long* __restrict__ bv) {
   uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblocks) return;
   uint64_t base = b << 6;
   if (base >= ix.n) return;
+  const WtShape& sh = *shp;
   OccBlock blk = load_block(ix.occ + b);
   // class counts before the block
-  uint64_t cls[8];
+  uint64_t cls[kWtClasses];
   for (int c = 0; c < 4; ++c) cls[c] = blk.cnt[c];
   for (int k = 0; k < sh.n_rare; ++k) {
     uint8_t s = sh.rare_sym[k];
     uint32_t a = ix.rare_off[s], e = ix.rare_off[s + 1];
     cls[4 + k] = lower_bound_u32(ix.rare_pos, a, e, (uint32_t)base) - a;
   }
-  uint64_t at[8];          // next bit position per internal node
-  unsigned long long acc[8];
+  uint64_t at[kWtInternal];          // next bit position per internal node
+  unsigned long long acc[kWtInternal];
   for (int v = 0; v < sh.n_internal; ++v) {
     uint64_t cnt = 0;
     for (int k = 0; k < 4 + sh.n_rare; ++k) if (sh.member[v][k]) cnt += cls[k];
@@ -1086,7 +1090,7 @@ int write_fm9(dg_index* ix, const char* path) {
     std::vector<int> internal_id(nn, -1);
     for (size_t v = 0; v < nn; ++v)
       if (nodes[v].child[0] != 0xFFFF) {
-        if (sh.n_internal >= 8) { set_error("alphabet too large for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
+        if (sh.n_internal >= kWtInternal) { set_error("alphabet too large for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
         sh.bv_pos[sh.n_internal] = nodes[v].bv_pos;
         internal_id[v] = sh.n_internal++;
       }
@@ -1095,12 +1099,13 @@ int write_fm9(dg_index* ix, const char* path) {
     cls_of['A'] = 0; cls_of['C'] = 1; cls_of['G'] = 2; cls_of['T'] = 3;
     for (int s : syms)
       if (cls_of[s] < 0) {
-        if (sh.n_rare >= 4) { set_error("alphabet too large for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
+        if (4 + sh.n_rare >= kWtClasses) { set_error("alphabet too large for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
         sh.rare_sym[sh.n_rare] = (uint8_t)s;
         cls_of[s] = 4 + sh.n_rare++;
       }
     for (int s : syms) {
       uint64_t pw = pathv[s] & ((1ULL << 56) - 1), pl = pathv[s] >> 56;
+      if (pl > (uint64_t)kWtDepth) { set_error("wavelet tree too deep for the .fm9 writer"); return DG_ERR_UNSUPPORTED; }
       sh.path_len[s] = (uint8_t)pl;
       uint16_t v = 0;
       for (uint64_t d = 0; d < pl; ++d) {
@@ -1120,7 +1125,10 @@ int write_fm9(dg_index* ix, const char* path) {
     d_sbsum.alloc(nsb); d_sbabs.alloc(nsb); d_bb.alloc(2 * nsb);
     DG_CUDA(cudaMemsetAsync(d_bv.p, 0, (nwords + 8) * 8, st));
     uint64_t nblocks = (n + 63) >> 6;
-    k_wt_bits<<<grid_for(nblocks, 128), 128, 0, st>>>(ix->view(), sh, nblocks, d_bv.p);
+    DevBuf<WtShape> d_sh;
+    d_sh.alloc(1);
+    DG_CUDA(cudaMemcpyAsync(d_sh.p, &sh, sizeof(WtShape), cudaMemcpyHostToDevice, st));
+    k_wt_bits<<<grid_for(nblocks, 128), 128, 0, st>>>(ix->view(), d_sh.p, nblocks, d_bv.p);
     k_sb_popc<<<grid_for(nsb, 256), 256, 0, st>>>(d_bv.p, nwords, nsb, d_sbsum.p);
     {
       Temp tmpb;

@@ -137,7 +137,8 @@ int dg_fm9_check(const char* fm9_path);
 
 /* index.h:96-123 (dump -> construct) for a text already in dump format (records upper-cased,
  * joined by '\n', trailing '\n'; no sentinel): suffix array, BWT and device layout are built
- * on the GPU.  Alphabet: at most 7 distinct byte values besides the sentinel.              */
+ * on the GPU.  Alphabet: at most 31 distinct byte values besides the sentinel (DNA with N keeps
+ * the 3-bit sort keys; IUPAC texts take 4- or 5-bit ones).                                     */
 int dg_index_build_text(const uint8_t* text, uint64_t len, int device, dg_index** out);
 
 /* Same, for the seeded synthetic reference of SURVEY.md 8(d) generated on the device
