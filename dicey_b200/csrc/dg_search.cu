@@ -2680,7 +2680,13 @@ static int run_impl(dg_batch* b) {
         // windows by length class, fallbacks resolved here: without the KB + 1 bitmap longer strings use KB
         pa.win_r[0] = v.present_lo; pa.win_l[0] = nullptr; pa.win_k[0] = (int)v.KB - 1;
         pa.win_r[1] = v.present_kb; pa.win_l[1] = v.present_kb_l; pa.win_k[1] = (int)v.KB;
-        if (v.present_hi) { pa.win_r[2] = v.present_hi; pa.win_l[2] = v.present_hi_l; pa.win_k[2] = (int)v.KB + 1; }
+        // The KB + 1 bitmaps filter four times better but are four times larger (34 GB each at 3 Gb): a probe
+        // into them costs more (TLB reach, fewer siblings per DRAM row).  Measured on the 3 Gb index: at
+        // distance <= 1 (160 strings per primer and strand) the KB windows alone are 6 % faster; at distance 2
+        // (12.8 k strings) the better filter wins by 10 %.  DG_USE_HI=0/1 overrides.
+        bool use_hi = v.present_hi != nullptr && b->par.distance >= 2;
+        if (const char* e = getenv("DG_USE_HI")) use_hi = v.present_hi != nullptr && atoi(e) != 0;
+        if (use_hi) { pa.win_r[2] = v.present_hi; pa.win_l[2] = v.present_hi_l; pa.win_k[2] = (int)v.KB + 1; }
         else { pa.win_r[2] = v.present_kb; pa.win_l[2] = v.present_kb_l; pa.win_k[2] = (int)v.KB; }
         // the regular batch: probes and slow path in separate kernels (k_probe_*, k_resolve)
         const int um = (int)b->uniform_len;
