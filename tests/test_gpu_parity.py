@@ -330,7 +330,7 @@ def test_records_dump_equals_reference_dump(indexes, case, index):
 
 
 @pytest.mark.parametrize("knob", ["DG_FULL_KEY_SORT=1", "DG_MERGE_SORT=1", "DG_LOCATE_RADIX=1", "DG_CAND_CAP=48", "DG_LOCATE_CAP=150",
-                                  "DG_SLOW_KEYS=1", "DG_GROUP_RADIX=1", "DG_NO_SPLIT=1", "DG_NO_OVERLAP=1"])
+                                  "DG_SLOW_KEYS=1", "DG_GROUP_RADIX=1", "DG_NO_SPLIT=1", "DG_NO_OVERLAP=1", "DG_USE_HI=1", "DG_USE_HI=0"])
 @pytest.mark.parametrize("case,index", [("stress_e2", "stress"), ("t1m_e1", "t1m"), ("stress_h2_m50", "stress"), ("stress_e1", "stress")])
 def test_alternative_paths_give_the_same_records(indexes, monkeypatch, knob, case, index):
     """The alternative routes through the pipeline must give the same records as the default one:
