@@ -303,7 +303,8 @@ def main_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (dicey_b200 has no CPU path)")
     torch.cuda.set_device(local)
-    dog = Watchdog(rank)
+    # (one rank holds no collective that could hang: a long limit there lets profilers replay kernels in peace)
+    dog = Watchdog(rank, float(os.environ.get("BENCH_WATCHDOG_S", "150" if world > 1 else "3600")))
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
