@@ -3397,20 +3397,7 @@ static int hunt_chunked(dg_index* idx, const char* seqs, const uint64_t* offsets
   // (shrinking the last chunks to shorten the device -> host tail was measured and costs more in
   // per-chunk fixed overhead than it saves)
   p.bounds.push_back(0);
-  if (const char* tp = getenv("DG_TAPER")) {
-    // experiment: full chunks, then a geometric taper so that the records of the last chunk -- whose
-    // copy to the host nothing can hide -- are few.  DG_TAPER = number of halvings.
-    const int halvings = std::max(1, atoi(tp));
-    uint64_t q = chunk / 2;
-    while (q < nq && nq - q > chunk + chunk / 2) { p.bounds.push_back((uint32_t)q); q += chunk; }
-    uint64_t rest = nq - q;
-    if (q < nq) p.bounds.push_back((uint32_t)q);
-    for (int h = 0; h < halvings && rest > 32768; ++h) {
-      q += rest / 2;
-      rest -= rest / 2;
-      p.bounds.push_back((uint32_t)q);
-    }
-  } else if (getenv("DG_UNEVEN")) {
+  if (getenv("DG_UNEVEN")) {
     for (uint64_t q = getenv("DG_NO_STAGGER") ? chunk : chunk / 2; q < nq; q += chunk) p.bounds.push_back((uint32_t)q);
     if (p.bounds.size() > 1 && nq - p.bounds.back() < chunk / 4) p.bounds.pop_back();  // no tiny tail chunk
   } else {

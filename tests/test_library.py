@@ -162,6 +162,59 @@ def test_allgather_result_merges_in_rank_order():
         assert m.sequence(4) == b"ACGTACGTAC"
 
 
+def _ops(*ops):
+    """(column, kind, genomic byte) triples -> the ops word of a dg_rec (include/dicey_b200.h)."""
+    w = 0
+    for k, (col, kind, ref) in enumerate(sorted(ops)):
+        w |= (col | (kind << 10) | (ref << 12)) << (20 * k)
+    return w
+
+
+def test_compact_record_alignment_host_side():
+    """dg_rec_alignment (host code, no device): both alignment rows rebuilt from the query and the
+    record's edit operations -- mismatch, gap in the reference row, gap in the query row."""
+    import ctypes as C
+    lib = api.library()
+    rec = np.zeros(1, dtype=api.REC_DTYPE)
+    ra, qa = C.create_string_buffer(64), C.create_string_buffer(64)
+
+    def rows(query, ops):
+        rec["ops"] = _ops(*ops)
+        rec["nops"] = len(ops)
+        n = lib.dg_rec_alignment(rec.ctypes.data, query, len(query), ra, qa)
+        assert n >= 0
+        return ra.raw[:n].decode(), qa.raw[:n].decode()
+
+    q = b"ACGTACGTAC"
+    assert rows(q, []) == ("ACGTACGTAC", "ACGTACGTAC")
+    assert rows(q, [(3, 1, ord("G"))]) == ("ACGGACGTAC", "ACGTACGTAC")                    # mismatch at column 3
+    assert rows(q, [(4, 2, 0)]) == ("ACGT-CGTAC", "ACGTACGTAC")                           # '-' in refalign
+    assert rows(q, [(4, 3, ord("T"))]) == ("ACGTTACGTAC", "ACGT-ACGTAC")                  # '-' in queryalign
+    assert rows(q, [(0, 1, ord("N")), (5, 3, ord("A")), (10, 1, ord("G"))]) == ("NCGTAACGTAG", "ACGTA-CGTAC")
+    rec["nops"] = 4                                                                      # more than the form carries
+    assert lib.dg_rec_alignment(rec.ctypes.data, q, len(q), ra, qa) < 0
+
+
+def test_record_sort_orders_like_hit_sort():
+    """dg_recs_sort and dg_hits_sort (std::sort of hunter.h:440 on the two record forms) give the same
+    permutation, ties included (same comparator, same introsort, same sequence of keys)."""
+    rng = np.random.default_rng(3)
+    lib = api.library()
+    for n in (0, 1, 2, 17, 400, 5000):
+        hits = np.zeros(n, dtype=api.HIT_DTYPE)
+        recs = np.zeros(n, dtype=api.REC_DTYPE)
+        hits["score"] = recs["score"] = -rng.integers(0, 3, n)
+        hits["chr"] = recs["chr"] = rng.integers(0, 4, n)
+        hits["start"] = recs["start"] = rng.integers(1, 30, n)          # many ties
+        hits["query"] = recs["query"] = np.arange(n)                    # identifies the element
+        if n:
+            lib.dg_hits_sort(hits.ctypes.data, n)
+            lib.dg_recs_sort(recs.ctypes.data, n)
+        assert np.array_equal(hits["query"], recs["query"])
+        key = list(zip((-hits["score"]).tolist(), hits["chr"].tolist(), hits["start"].tolist()))
+        assert key == sorted(key)
+
+
 def test_synth_generator_is_windowable():
     t = synth.text(42, 3, 1000)
     assert t.size == 3 * 1001 and t[1000] == 10
