@@ -467,6 +467,35 @@ def main_b200(args):
         except Exception:
             work = None
 
+    # ---------------- the exchanged table itself (untimed): every rank checks what it holds in HBM after the
+    # last end-to-end step -- its own segment against its own result, every segment's query range and order
+    exchange_check = None
+    if comm is not None:
+        ok, gathered_n, err = False, 0, None
+        try:
+            res_last, _ = e2e_step()
+            _, _, cnts = comm.allgather_hits(None, qbase)
+            tab = comm.fetch_table()
+            off = np.concatenate([[0], np.cumsum(cnts.astype(np.int64))])
+            gathered_n = int(off[-1])
+            ok = len(tab) == gathered_n
+            for r in range(world):
+                seg = tab[off[r]:off[r + 1]]
+                ok = ok and (len(seg) == 0 or (int(seg["query"].min()) >= r * nq and int(seg["query"].max()) < (r + 1) * nq
+                                               and bool((np.diff(seg["query"].astype(np.int64)) >= 0).all())))
+            mine = tab[off[rank]:off[rank + 1]]
+            recs = res_last.records
+            ok = ok and len(mine) == len(recs) and all(bool(np.array_equal(mine[f], recs[f] + (qbase if f == "query" else 0)))
+                                                       for f in ("query", "chr", "start", "score", "strand"))
+        except Exception as e:   # (every rank still takes part in the reduction below; the bench line is still printed)
+            ok, err = False, str(e)
+        t_ok = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        exchange_check = {"all_ranks_ok": bool(t_ok.item()), "gathered_records": gathered_n}
+        if err:
+            exchange_check["error"] = err
+    dog.mark("exchange checked")
+
     ms_search = float(np.mean([p["ms_search"] for p in profs])) if profs else None
     ms_probe = float(np.mean([p["ms_probe"] for p in profs])) if profs else 0.0
     scripts = float(np.mean([p["scripts"] for p in profs])) if profs else 0.0
@@ -555,6 +584,7 @@ def main_b200(args):
             "gpu_launches": int(sum(p["launches"] for p in profs)) + (2 * args.steps if world > 1 else 0),
             "stages_ms": stage, "step_ms_total": [round(p["ms_total"], 3) for p in profs],
             "roofline": roof,
+            "exchange_check": exchange_check,
             "cpu_baseline": cpu,
             "parity": parity,
         }
