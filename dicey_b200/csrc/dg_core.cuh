@@ -959,6 +959,36 @@ DG_HD int rec_expand_rows(uint64_t ops, int nop, const uint8_t* s, int m, uint8_
 }
 
 // ------------------------------------------------------------------------------------------
+// The pair enumeration of k_probe_pairs / k_resolve (dg_search.cu): for one string of m bases the
+// S * m (m + 1) / 2 slots are laid out by first position p1 (S * (m - p1) slots each), then first kind,
+// then second position p2 = p1 .. m - 1.
+DG_HD float dg_sqrtf(float x) {
+#if defined(__CUDA_ARCH__)
+  return sqrtf(x);
+#else
+  return __builtin_sqrtf(x);
+#endif
+}
+// slot of the pair enumeration -> (first position, first kind, second position)
+template <int S>
+DG_HD void pair_slot(uint32_t u, int m, int& p1, int& k1i, int& p2) {
+  // rows of S * (m - p1) slots; T(p1) = p1 m - p1 (p1 - 1) / 2 rows-of-S precede first position p1
+  const uint32_t v = u / (uint32_t)S;
+  const float b2 = (float)(2 * m + 1);
+  int g = (int)((b2 - dg_sqrtf(b2 * b2 - 8.0f * (float)v)) * 0.5f);
+  if (g < 0) g = 0;
+  if (g > m - 1) g = m - 1;
+  auto T = [&](int x) { return (uint32_t)(x * m - (x * (x - 1)) / 2); };
+  while (g > 0 && T(g) > v) --g;
+  while (g + 1 < m && T(g + 1) <= v) ++g;
+  p1 = g;
+  const uint32_t r = u - (uint32_t)S * T(g);
+  const uint32_t npos = (uint32_t)(m - g);
+  k1i = (int)(r / npos);
+  p2 = g + (int)(r - (uint32_t)k1i * npos);
+}
+
+// ------------------------------------------------------------------------------------------
 // Packed fast path: an ACGT-only string of length <= 31 as 2-bit codes, LAST base in the low
 // bits (so the low 2K bits are the K-mer table index and base t from the right is bits 2t..2t+1).
 // apply_event_packed applies one canonical event (k < 4 substitute code k, 4 delete, 5.. insert

@@ -1022,25 +1022,6 @@ struct ProbeShape {
   unsigned long long scripts_per_pair;   // strings enumerated per pair (statistics)
   unsigned long long* n_scripts;
 };
-// slot of the pair enumeration -> (first position, first kind, second position)
-template <int S>
-__device__ __forceinline__ void pair_slot(uint32_t u, int m, int& p1, int& k1i, int& p2) {
-  // rows of S * (m - p1) slots; T(p1) = p1 m - p1 (p1 - 1) / 2 rows-of-S precede first position p1
-  const uint32_t v = u / (uint32_t)S;
-  const float b2 = (float)(2 * m + 1);
-  int g = (int)((b2 - sqrtf(b2 * b2 - 8.0f * (float)v)) * 0.5f);
-  if (g < 0) g = 0;
-  if (g > m - 1) g = m - 1;
-  auto T = [&](int x) { return (uint32_t)(x * m - (x * (x - 1)) / 2); };
-  while (g > 0 && T(g) > v) --g;
-  while (g + 1 < m && T(g + 1) <= v) ++g;
-  p1 = g;
-  const uint32_t r = u - (uint32_t)S * T(g);
-  const uint32_t npos = (uint32_t)(m - g);
-  k1i = (int)(r / npos);
-  p2 = g + (int)(r - (uint32_t)k1i * npos);
-}
-
 template <bool INDEL>
 __global__ void __launch_bounds__(256, 6) k_probe_singles(const __grid_constant__ PackedArgs a, const __grid_constant__ ProbeShape sh,
                                                           uint64_t slot0, uint64_t nslots, uint8_t* __restrict__ masks) {

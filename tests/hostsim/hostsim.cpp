@@ -144,6 +144,26 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  if (cmd == "pairslots") {
+    // pair_slot (the index arithmetic of k_probe_pairs / k_resolve): every slot of every length maps to the
+    // (first position, first kind, second position) the row-major layout defines, for both kind counts
+    long checked = 0;
+    for (int m = 1; m <= 31; ++m)
+      for (int S : {3, 8}) {
+        uint32_t u = 0;
+        for (int p1 = 0; p1 < m; ++p1)
+          for (int k1 = 0; k1 < S; ++k1)
+            for (int p2 = p1; p2 < m; ++p2, ++u) {
+              int a, b, c;
+              if (S == 3) pair_slot<3>(u, m, a, b, c); else pair_slot<8>(u, m, a, b, c);
+              if (a != p1 || b != k1 || c != p2) { fprintf(stderr, "pair_slot(%u, m=%d, S=%d) = (%d,%d,%d), want (%d,%d,%d)\n", u, m, S, a, b, c, p1, k1, p2); return 3; }
+              ++checked;
+            }
+        if (u != (uint32_t)(S * m * (m + 1) / 2)) { fprintf(stderr, "slot count\n"); return 3; }
+      }
+    printf("pair_slot checked on %ld slots\n", checked);
+    return 0;
+  }
   if (cmd == "replay" && argc >= 6) {
     // the reference's generation order replayed (nbr_trunc.hpp): sets as `dicey_ref neighbors -x` prints them
     std::ifstream f(argv[2]);

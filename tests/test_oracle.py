@@ -74,6 +74,12 @@ def test_replay_reproduces_truncated_neighbor_sets(tag, d, indel, x):
     assert run(HOSTSIM, ["replay", "neighbors.queries.txt", str(d), str(indel), str(x)]) == want
 
 
+def test_pair_slot_index_arithmetic():
+    """pair_slot of dg_core.cuh (slot -> first position, first kind, second position in k_probe_pairs /
+    k_resolve) on every slot of every length up to 31, for 3 and 8 kinds per position."""
+    assert run(HOSTSIM, ["pairslots"]).startswith("pair_slot checked on ")
+
+
 def test_neighborhood_bound_is_sound():
     """nbr_upper_bound_part (the device-side certificate that the cap cannot be reached) never falls
     below the number of distinct strings, and certifies 20-mers at edit distance 2 under the default cap."""
