@@ -553,7 +553,8 @@ def main_b200(args):
                 pass
         if roof["achieved"] is None:   # no capture for this configuration: the algorithmic figure stands in
             roof["achieved"], roof["frac"] = roof["algorithmic_achieved"], roof["algorithmic_frac"]
-            roof["note"] = "no ncu capture for this configuration: achieved = 32 B per probe / kernel time"
+            roof["note"] = ("no ncu capture for this configuration: achieved = 32 B per probe / kernel time -- an upper bound on the DRAM "
+                            "bytes (sibling probes share sectors, L1 / L2 answer many), so frac can exceed 1 and is not a DRAM utilisation")
         gc = os.path.join(ROOT, "profiles", "gather_ceiling.json")
         if os.path.exists(gc):
             try:
