@@ -7,7 +7,9 @@
 // have kept (thal_end1_tm_lanes in dg_thal.cuh has the argument).  k_thal is the sequential form,
 // one pair per thread with the tables of a launch interleaved in a global scratch slab; it serves
 // the pairs the warp form declines (none within primer3's length limit, but the condition is
-// checked) and DG_THAL_SEQ=1 routes everything through it.
+// checked) and DG_THAL_SEQ=1 routes everything through it.  k_thal_wide takes the pairs with one
+// side longer than THAL_MAX_ALIGN = 60 (thal.h:58, :2440-2451; up to THAL_MAX_SEQ = 10 000): one warp
+// per pair again, the table (up to 9.6 MB) in a global work area of the warp (thal_end1_tm_wide).
 // Built with -fmad=false: results equal the reference's bit for bit.
 #include <algorithm>
 #include <chrono>
@@ -126,6 +128,52 @@ __global__ void __launch_bounds__(128) k_thal(const ThalParams* __restrict__ p, 
   ok[q] = good ? 1 : 0;
 }
 
+// global work area of one warp of k_thal_wide: the table, then num1 / a1 / ra and num2 / b / rb
+__host__ __device__ inline size_t thal_wide_bytes(uint64_t cells, uint32_t max1, uint32_t max2) {
+  return ((size_t)cells * 16 + 3 * ((size_t)max1 + 2) + 3 * ((size_t)max2 + 2) + 255) & ~(size_t)255;
+}
+
+__global__ void __launch_bounds__(128) k_thal_wide(const ThalParams* __restrict__ p, const uint8_t* __restrict__ s1,
+                                                   const uint64_t* __restrict__ off1, const uint8_t* __restrict__ s2,
+                                                   const uint64_t* __restrict__ off2, const uint32_t* __restrict__ ids, uint32_t count,
+                                                   uint64_t cells, uint32_t max1, uint32_t max2, unsigned char* slab,
+                                                   double* __restrict__ tm, uint8_t* __restrict__ ok) {
+  const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  unsigned char* base = slab + (size_t)(blockIdx.x * wpb + warp) * thal_wide_bytes(cells, max1, max2);
+  double* tab = (double*)base;
+  uint8_t* n1 = (uint8_t*)(tab + 2 * cells);
+  uint8_t* a1 = n1 + (max1 + 2);
+  uint8_t* ra = a1 + (max1 + 2);
+  uint8_t* n2 = ra + (max1 + 2);
+  uint8_t* b = n2 + (max2 + 2);
+  uint8_t* rb = b + (max2 + 2);
+  ThalWarp wp;
+  wp.lane = threadIdx.x & 31;
+  for (uint32_t t = blockIdx.x * wpb + warp; t < count; t += gridDim.x * wpb) {
+    const uint32_t q = ids[t];
+    const int64_t l1 = (int64_t)(off1[q + 1] - off1[q]), l2 = (int64_t)(off2[q + 1] - off2[q]);
+    double out = -kThalInf;
+    int rc = 0;
+    __syncwarp();
+    if (l1 > 0 && l2 > 0 && l1 <= (int64_t)max1 && l2 <= (int64_t)max2 && thal_lengths_ok((int)l1, (int)l2) &&
+        (uint64_t)l1 * (uint64_t)l2 <= cells) {
+      const int len1 = (int)l1, len2 = (int)l2;
+      rc = thal_end1_tm_wide(wp, p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, a1, ra, b, rb, &out);
+      if (rc == 2) {   // the entropy cutoff: the sequential form on one lane, in the same work area
+        __syncwarp();
+        if (wp.lane == 0) rc = thal_end1_tm_any(p, s1 + off1[q], len1, s2 + off2[q], len2, n1, n2, tab, tab + 1, &out, 2) ? 1 : 0;
+        __syncwarp();
+      }
+    } else if (l1 <= 0 || l2 <= 0) {
+      out = 0.0;
+    }
+    if (wp.lane == 0) {
+      tm[q] = out;
+      ok[q] = (uint8_t)rc;
+    }
+  }
+}
+
 int finish_open(dg_thal* t, int device, dg_thal** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -202,11 +250,20 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
       t_last = now;
     };
     const uint64_t nb1 = off1[n], nb2 = off2[n];
-    uint64_t cells = 1;
+    uint64_t cells = 1, wide_cells = 1;
+    uint32_t wide_max1 = 1, wide_max2 = 1;
+    std::vector<uint32_t> wide;
     for (uint32_t q = 0; q < n; ++q) {
       if (off1[q + 1] < off1[q] || off2[q + 1] < off2[q]) { set_error("offsets must be non-decreasing"); return DG_ERR_ARG; }
       const uint64_t a = off1[q + 1] - off1[q], b = off2[q + 1] - off2[q];
       if (a <= (uint64_t)kThalMaxLen && b <= (uint64_t)kThalMaxLen) cells = std::max(cells, a * b);
+      // one side longer than the shared-memory forms take, and a pair the reference accepts: k_thal_wide
+      if (a && b && (a > (uint64_t)kThalMaxLen) != (b > (uint64_t)kThalMaxLen) && a <= (uint64_t)kThalMaxSeq && b <= (uint64_t)kThalMaxSeq) {
+        wide.push_back(q);
+        wide_cells = std::max(wide_cells, a * b);
+        wide_max1 = std::max(wide_max1, (uint32_t)a);
+        wide_max2 = std::max(wide_max2, (uint32_t)b);
+      }
     }
     DevBuf<uint8_t> d_s1, d_s2, d_ok;
     DevBuf<uint64_t> d_o1, d_o2;
@@ -285,6 +342,25 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
       }
     }
     DG_CUDA(cudaGetLastError());
+    DevBuf<uint32_t> d_wide;
+    DevBuf<unsigned char> slab;
+    if (!wide.empty()) {
+      // last on the stream: the kernels above have written "failed" for these pairs (too long for them)
+      const size_t per_warp = thal_wide_bytes(wide_cells, wide_max1, wide_max2);
+      constexpr uint32_t wpb = 4;
+      int resident = 1;
+      DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_thal_wide, (int)(wpb * 32), 0));
+      uint64_t warps = std::min<uint64_t>(wide.size(), (uint64_t)std::max(resident, 1) * (uint64_t)t->sms * wpb);
+      warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, (4ULL << 30) / per_warp));   // <= 4 GiB of work areas
+      const uint64_t blocks = (warps + wpb - 1) / wpb;
+      d_wide.alloc(wide.size());
+      slab.alloc((size_t)blocks * wpb * per_warp);
+      DG_CUDA(cudaMemcpyAsync(d_wide.p, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice, st));
+      k_thal_wide<<<(unsigned)blocks, wpb * 32, 0, st>>>(t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p, d_wide.p, (uint32_t)wide.size(),
+                                                         wide_cells, wide_max1, wide_max2, slab.p, d_tm.p, d_ok.p);
+      DG_CUDA(cudaGetLastError());
+      stage("k_thal_wide");
+    }
     DG_CUDA(cudaMemcpyAsync(tm, d_tm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(ok, d_ok.p, n, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));

@@ -25,7 +25,8 @@ constexpr double kThalTempK = 310.15;            // TEMP_KELVIN
 constexpr double kThalAbsZero = 273.15;
 constexpr double kThalInitH = 200.0, kThalInitS = -5.7;   // duplex initiation
 constexpr double kThalIlas = (-300 / 310.15);    // internal-loop asymmetry (entropy); the enthalpy term is 0
-constexpr int kThalMaxLen = 60;                  // THAL_MAX_ALIGN: the shorter sequence; both sides are capped for the DP tables
+constexpr int kThalMaxLen = 60;                  // THAL_MAX_ALIGN: the shorter sequence (thal.h:64); the shared-memory forms take both sides <= this
+constexpr int kThalMaxSeq = 10000;               // THAL_MAX_SEQ: the longer sequence (thal.h:75); thal_end1_tm_wide takes one side up to this
 constexpr int kThalMaxLoop = 30;
 
 // Nearest-neighbour tables exactly as the reference holds them after get_thermodynamic_values()
@@ -231,11 +232,25 @@ DG_HD bool thal_symmetric(const uint8_t* s, int len) {   // symmetry_thermo
 // thal(oligo1, oligo2, thal_end1, temponly): returns false where the reference returns false
 // (a sequence longer than the DP tables); *tm is o->temp.  num1 / num2: len + 2 bytes each,
 // ds / dh: len1 * len2 cells each, `stride` doubles apart.
+// thal_end1_tm_any: the same for any pair of lengths the reference accepts (thal.h:2440-2451: at most
+// one side longer than THAL_MAX_ALIGN, neither longer than THAL_MAX_SEQ); the caller sizes the work areas.
+DG_HD bool thal_lengths_ok(int len1, int len2) {
+  return len1 > 0 && len2 > 0 && !(len1 > kThalMaxLen && len2 > kThalMaxLen) && len1 <= kThalMaxSeq && len2 <= kThalMaxSeq;
+}
+DG_HD bool thal_end1_tm_any(const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
+                            uint8_t* num2, double* ds, double* dh, double* tm, long stride = 1);
 DG_HD bool thal_end1_tm(const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
                         uint8_t* num2, double* ds, double* dh, double* tm, long stride = 1) {
   *tm = -kThalInf;   // THAL_ERROR_SCORE
   if (len1 <= 0 || len2 <= 0) { *tm = 0.0; return false; }
-  if (len1 > kThalMaxLen || len2 > kThalMaxLen) return false;
+  if (len1 > kThalMaxLen || len2 > kThalMaxLen) return false;   // (the work areas of this form's callers)
+  return thal_end1_tm_any(p, o1, len1, o2, len2, num1, num2, ds, dh, tm, stride);
+}
+DG_HD bool thal_end1_tm_any(const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
+                            uint8_t* num2, double* ds, double* dh, double* tm, long stride) {
+  *tm = -kThalInf;   // THAL_ERROR_SCORE
+  if (len1 <= 0 || len2 <= 0) { *tm = 0.0; return false; }
+  if (!thal_lengths_ok(len1, len2)) return false;
   ThalWork w;
   w.p = p; w.n1 = num1; w.n2 = num2; w.len1 = len1; w.len2 = len2; w.ds = ds; w.dh = dh; w.stride = stride;
   w.rc = (thal_symmetric(o1, len1) && thal_symmetric(o2, len2)) ? p->rc[0] : p->rc[1];
@@ -599,6 +614,195 @@ DG_HD int thal_end1_tm_lanes(Warp& wp, const ThalParams* p, const uint8_t* o1, i
     const int d = (int)(bestO >> 6), ii = i - 1 - (int)(bestO & 63);
     j = j - (d - (i - ii));
     i = ii;
+    paired += 2;
+  }
+  const int N = (paired / 2) - 1;
+  *tm = ((dH) / (dS + (N * p->salt) + w.rc)) - kThalAbsZero;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// thal_end1_tm_wide: the lane-cooperative computation for the pairs the reference accepts with ONE
+// side longer than THAL_MAX_ALIGN (thal.h:58, :2440-2451: "one of the sequences must be <= 60, the
+// other can be longer", up to THAL_MAX_SEQ = 10 000).  The table no longer fits shared memory, so
+// the work areas are the caller's (global memory on the device) and two things change against
+// thal_end1_tm_lanes, the arithmetic and every decision staying the same:
+//   * no list of paired cells: the live cells of a row are found 32 columns at a time with a ballot,
+//     and the lanes split into one group per live cell of that chunk;
+//   * the loop partners of a cell are enumerated by coordinates -- (ii, jj) = (i - di, j - dj),
+//     3 <= di + dj <= maxLoop + 2 -- and the table says which of them are finite (a cell is finite
+//     exactly when its bases pair).  The reference scans them by ascending d = di + dj and, within
+//     one d, ascending di: `order` below is that rank, and the arg-min over (energy, order) picks the
+//     partner the sequential scan would have kept (argument: see thal_end1_tm_lanes).
+// Work areas: num1 / a1 / ra len1 + 2 bytes each, num2 / b / rb len2 + 2 bytes each, tab
+// 2 * len1 * len2 doubles (S, H interleaved).  Returns 0 where the reference's thal() fails, 1 with
+// *tm set, 2 for "use thal_end1_tm_any" (the entropy cutoff, as in thal_end1_tm_lanes).
+DG_HD int thal_nth_bit(unsigned m, int k) {   // position of the k-th (0-based) set bit of m
+#ifdef __CUDA_ARCH__
+  return (int)__fns(m, 0, k + 1);
+#else
+  for (int t = 0; t < k; ++t) m &= m - 1;
+  return __builtin_ctz(m);
+#endif
+}
+
+template <class Warp>
+DG_HD int thal_end1_tm_wide(Warp& wp, const ThalParams* p, const uint8_t* o1, int len1, const uint8_t* o2, int len2, uint8_t* num1,
+                            uint8_t* num2, double* tab, uint8_t* a1, uint8_t* ra, uint8_t* b, uint8_t* rb, double* tm) {
+  constexpr int n = Warp::n;
+  const int lane = wp.lane;
+  const unsigned everyone = wp.group_mask(0, n, true);
+  *tm = -kThalInf;
+  if (len1 <= 0 || len2 <= 0) { *tm = 0.0; return 0; }
+  if (!thal_lengths_ok(len1, len2)) return 0;
+  for (int i = 1 + lane; i <= len1; i += n) num1[i] = (uint8_t)thal_code(o1[i - 1]);
+  for (int j = 1 + lane; j <= len2; j += n) num2[j] = (uint8_t)thal_code(o2[len2 - j]);
+  if (lane == 0) num1[0] = num1[len1 + 1] = num2[0] = num2[len2 + 1] = 4;
+  wp.sync();
+  for (int i = 1 + lane; i <= len1; i += n) {
+    a1[i] = (uint8_t)(num1[i] * 5 + num1[i + 1]);
+    ra[i] = (uint8_t)(num1[i] * 5 + num1[i - 1]);
+  }
+  for (int j = 1 + lane; j <= len2; j += n) {
+    b[j] = (uint8_t)(num2[j] * 5 + num2[j + 1]);
+    rb[j] = (uint8_t)(num2[j] * 5 + num2[j - 1]);
+  }
+  bool sym = (len1 % 2 == 0) && (len2 % 2 == 0);
+  if (sym) {
+    bool mine = true;
+    for (int t = lane; t < len1 / 2; t += n) {
+      const int x = num1[1 + t], y = num1[len1 - t];
+      if ((x < 4 || y < 4) && x + y != 3) mine = false;
+    }
+    for (int t = lane; t < len2 / 2; t += n) {
+      const int x = num2[1 + t], y = num2[len2 - t];
+      if ((x < 4 || y < 4) && x + y != 3) mine = false;
+    }
+    sym = wp.all(mine);
+  }
+  ThalWork w;
+  w.p = p; w.n1 = num1; w.n2 = num2; w.len1 = len1; w.len2 = len2; w.ds = tab; w.dh = tab + 1; w.stride = 2;
+  w.rc = sym ? p->rc[0] : p->rc[1];
+  // initMatrix and the LSH seed of every paired cell (both depend on the sequences alone)
+  for (int i = 1; i <= len1; ++i)
+    for (int j = 1 + lane; j <= len2; j += n) {
+      const bool pr = thal_bp(num1[i], num2[j]) != 0;
+      double s = pr ? kThalMinEntropy : -1.0, h = pr ? 0.0 : kThalInf;
+      if (pr) {
+        double ls = -1.0, lh = kThalInf;
+        thal_left(w, i, j, ls, lh);   // (touches the table only when the bases do not pair)
+        if (thal_fin(lh)) { s = ls; h = lh; }
+      }
+      w.S(i, j) = s;
+      w.H(i, j) = h;
+    }
+  wp.sync();
+  // fillMatrix: rows in order, the live cells of a row n columns at a time
+  bool odd = false;
+  for (int i = 2; i <= len1; ++i) {
+    for (int jb = 2; jb <= len2; jb += n) {
+      const int jm = jb + lane;
+      const unsigned livemask = wp.ballot(jm <= len2 && thal_fin(w.H(i, jm)));
+      const int cells = thal_popc(livemask);
+      if (cells == 0) continue;
+      const int gsize = n / cells, g = lane / gsize, gl = lane - g * gsize;
+      const bool live = g < cells;
+      const unsigned gmask = wp.group_mask(g * gsize, gsize, live);
+      const int j = live ? jb + thal_nth_bit(livemask, g) : 0;
+      double cs = -1.0, ch = kThalInf, rs = -1.0, rh = kThalInf, G2 = 0.0;
+      double bestG = 1e300, bS = -1.0, bH = kThalInf;
+      uint32_t bestO = kThalNone;
+      if (live) {
+        thal_right(w, i, j, rs, rh);
+        thal_stack_value(w, i, j, rs, rh, cs, ch);
+        G2 = thal_loop_energy(cs, ch, rs, rh);
+        ThalRight rc;
+        thal_right_consts(w, ra, rb, i, j, rc);
+        for (int di = 1; di <= kThalMaxLoop + 1 && di < i; ++di) {
+          const int ii = i - di;
+          for (int dj = (di == 1 ? 2 : 1) + gl; dj <= kThalMaxLoop + 2 - di && dj < j; dj += gsize) {
+            const int jj = j - dj;
+            if (!thal_fin(w.H(ii, jj))) continue;
+            double S, H;
+            thal_loop_value_right(w, a1, b, rc, ii, jj, i, j, S, H);
+            if (!thal_fin(H)) continue;                    // never stored by the reference
+            if (S < kThalMinEntropyCutoff) odd = true;
+            const double G1 = thal_loop_energy(S, H, rs, rh) + 0.0;   // (+ 0.0: one zero for the bitwise arg-min)
+            const uint32_t order = ((uint32_t)(di + dj) << 6) | (uint32_t)(di - 1);
+            if (bestO == kThalNone || G1 < bestG || (G1 == bestG && order < bestO)) { bestG = G1; bestO = order; bS = S; bH = H; }
+          }
+        }
+      }
+      wp.sync();
+      wp.argmin(gmask, bestG, bestO, bS, bH);
+      if (live && gl == 0) {
+        const bool take = bestO != kThalNone && bestG < G2;
+        w.S(i, j) = take ? bS : cs;
+        w.H(i, j) = take ? bH : ch;
+      }
+      wp.sync();
+    }
+  }
+  if (wp.any(odd)) return 2;
+  // the most stable structure ending at the 3' end of the first sequence
+  int bestI = len1, bestJ = 0;
+  {
+    double bestG = 1e300, dS_ = 0.0, dH_ = 0.0;
+    uint32_t bestO = kThalNone;
+    for (int j = 1 + lane; j <= len2; j += n) {
+      double s, h;
+      thal_right(w, len1, j, s, h);
+      s = s + 0.000001;
+      h = h + 0.000001;
+      const double G1 = ((w.H(len1, j) + h + kThalInitH) - kThalTempK * (w.S(len1, j) + s + kThalInitS)) + 0.0;
+      if (G1 < kThalInf && (bestO == kThalNone || G1 < bestG)) { bestG = G1; bestO = (uint32_t)j; }
+    }
+    wp.sync();
+    wp.argmin(everyone, bestG, bestO, dS_, dH_);
+    if (bestO != kThalNone && thal_fin(bestG)) bestJ = (int)bestO;
+    else bestI = bestJ = 1;
+  }
+  double rs, rh;
+  thal_right(w, bestI, bestJ, rs, rh);
+  const double dH = w.H(bestI, bestJ) + rh + kThalInitH;
+  const double dS = (w.S(bestI, bestJ) + rs + kThalInitS);
+  if (!thal_fin(w.H(bestI, bestJ))) { *tm = 0.0; return 1; }
+  // traceback: only the number of paired bases enters the temperature
+  int paired = 2, i = bestI, j = bestJ;
+  for (int guard = 0; guard < 4 * (len1 + len2); ++guard) {
+    double s = -1.0, h = kThalInf;
+    if (thal_bp(num1[i], num2[j])) thal_left(w, i, j, s, h);   // (a finite cell always pairs)
+    const double cs = w.S(i, j), ch = w.H(i, j);
+    if (cs == s && ch == h) break;
+    if (i > 1 && j > 1) {
+      const int k = thal_i4(num1[i - 1], num1[i], num2[j - 1], num2[j]);
+      if (cs == p->stackS[k] + w.S(i - 1, j - 1) && ch == p->stackH[k] + w.H(i - 1, j - 1)) {
+        --i; --j;
+        paired += 2;
+        continue;
+      }
+    }
+    double g = 0.0, dS_ = 0.0, dH_ = 0.0;
+    uint32_t bestO = kThalNone;
+    ThalRight rc;
+    thal_right_consts(w, ra, rb, i, j, rc);
+    for (int di = 1; di <= kThalMaxLoop + 1 && di < i; ++di) {
+      const int ii = i - di;
+      for (int dj = (di == 1 ? 2 : 1) + lane; dj <= kThalMaxLoop + 2 - di && dj < j; dj += n) {
+        const int jj = j - dj;
+        if (!thal_fin(w.H(ii, jj))) continue;   // (cannot reproduce a finite cell)
+        double S, H;
+        thal_loop_value_right(w, a1, b, rc, ii, jj, i, j, S, H);
+        const uint32_t order = ((uint32_t)(di + dj) << 6) | (uint32_t)(di - 1);
+        if (cs == S && ch == H && order < bestO) bestO = order;
+      }
+    }
+    wp.sync();
+    wp.argmin(everyone, g, bestO, dS_, dH_);
+    if (bestO == kThalNone) break;   // (the reference would spin here; never observed)
+    const int d = (int)(bestO >> 6), di = 1 + (int)(bestO & 63);
+    j = j - (d - di);
+    i = i - di;
     paired += 2;
   }
   const int N = (paired / 2) - 1;

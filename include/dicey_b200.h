@@ -324,7 +324,9 @@ int dg_result_unpack(const void* buf, uint64_t bytes, dg_result** out);
  * directory a dicey installation ships (-i, silica.h:216) as get_thermodynamic_values does
  * (thal.h:2368-2393); mv / dv / dntp in mM, dna_conc in nM (silica.h:243-246).
  * dg_thal_open_tables reads the table dump `oracle/_ref/dicey_ref thal` writes (tests).
- * Limits: both sequences at most 60 bases (the reference allows one side longer).            */
+ * Lengths as in the reference (thal.h:58, :2440-2451): at most one side longer than
+ * THAL_MAX_ALIGN = 60, neither longer than THAL_MAX_SEQ = 10 000; any other pair gets ok = 0
+ * and THAL_ERROR_SCORE (-999999), an empty side ok = 0 and 0.0 -- what thal() leaves in o.temp. */
 typedef struct dg_thal dg_thal;
 int dg_thal_open(const char* primer3_config_dir, double mv, double dv, double dntp, double dna_conc, int device, dg_thal** out);
 int dg_thal_open_tables(const char* table_dump_path, int device, dg_thal** out);

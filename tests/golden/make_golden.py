@@ -205,6 +205,7 @@ def main():
     open(os.path.join(HERE, "needle.out.tsv"), "w").write(run(["needle", pfn, "-"]))
     make_thal()
     make_thal_long()
+    make_thal_wide()
 
 
 def make_thal():
@@ -296,6 +297,60 @@ def make_thal_long():
     open(os.path.join(HERE, "thal_long.out.tsv"), "w").write(out)
 
 
+def make_thal_wide():
+    """thal() with ONE side longer than THAL_MAX_ALIGN = 60 (thal.h:58, :2440-2451 -- the other side up to
+    THAL_MAX_SEQ = 10 000): an oligo against a long target holding its (exact / mismatched / bulged /
+    internal-loop) binding site, with the long sequence on either side, the site at the very ends, lengths
+    at both limits; and the pairs the reference refuses (both sides longer than 60, a side longer than
+    10 000).  Results only (the tables are thal.params.tsv)."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+    def rnd(n):
+        return bytes(acgt[rng.integers(0, 4, int(n))])
+
+    pairs = []
+    longs = [61, 62, 63, 64, 65, 96, 97, 128, 200, 333, 700, 1500, 4000, 10000]
+    for i, L in enumerate(longs * 3):
+        k = int(rng.integers(12, 61)) if i % 5 else 60
+        oligo = rnd(k)
+        site = bytearray(oligo.translate(comp)[::-1])
+        kind = i % 6
+        if kind == 1:
+            for _ in range(3):
+                site[int(rng.integers(0, len(site)))] = acgt[rng.integers(0, 4)]
+        elif kind == 2:
+            del site[int(rng.integers(1, len(site) - 1))]
+        elif kind == 3:
+            q = int(rng.integers(1, len(site) - 1))
+            site[q:q] = rnd(rng.integers(1, 12))
+        elif kind == 4:
+            q = int(rng.integers(2, len(site) - 2))
+            site[q:q + int(rng.integers(1, 6))] = rnd(rng.integers(1, 9))
+        site = bytes(site)[:L]
+        where = i % 4
+        free = L - len(site)
+        at = 0 if where == 0 else free if where == 1 else int(rng.integers(0, free + 1))
+        target = rnd(at) + site + rnd(free - at)
+        if i % 11 == 0:
+            target = target[:5] + b"N" + target[6:]
+        if i % 13 == 0:
+            target = target.lower()
+        pairs.append((oligo, target) if (i // len(longs)) % 2 == 0 or i % 3 == 0 else (target, oligo))
+    unit = b"ACGT" * 2500
+    pairs += [(b"ACGTACGTACGTACGTACGT", unit), (unit, b"ACGTACGTACGTACGTACGT"), (b"A" * 30, b"T" * 9000), (b"G" * 2000, b"C" * 60),
+              (b"A", rnd(500)), (rnd(500), b"T"),
+              (rnd(61), rnd(61)), (rnd(60), rnd(10001)), (rnd(10001), rnd(20)), (rnd(300), rnd(61))]   # refused by the reference
+    pfn = os.path.join(HERE, "thal_wide.pairs.tsv")
+    with open(pfn, "wb") as f:
+        for a, b in pairs:
+            f.write(a + b"\t" + b + b"\n")
+    out = run(["thal", "/root/reference/src/primer3_config/", pfn, "/dev/null"])
+    open(os.path.join(HERE, "thal_wide.out.tsv"), "w").write(out)
+
+
 def make_truncation_cases():
     """hunt cases in which the reference truncates its neighbourhood at -x (neighbors.h:50, warning of
     hunter.h:342-345): small caps in both modes, and 24-26-mers at edit distance 2 under the default cap.
@@ -385,6 +440,8 @@ if __name__ == "__main__":
         make_iupac_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "trunc":
         make_truncation_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "thalwide":
+        make_thal_wide()
     else:
         main()
         make_truncation_cases()

@@ -83,19 +83,23 @@ static void neighbors(const std::string& q, int d, bool indel, std::set<std::str
   }
 }
 
-// Eight cooperating lanes as threads: the Warp concept of dg_thal.cuh with its collectives built on a
-// barrier, so that the group logic the GPU kernel relies on (ballot compaction, one lane group per
+// Cooperating lanes as threads: the Warp concept of dg_thal.cuh with its collectives built on a
+// barrier, so that the group logic the GPU kernels rely on (ballot compaction, one lane group per
 // cell of a row, arg-min within a group) runs -- with real concurrency -- in the CPU suite.
-struct LaneShared {
+// Eight lanes for the shared-memory form (thal8), a full warp of 32 for the wide form (thalw32).
+template <int N>
+struct LaneSharedN {
   pthread_barrier_t bar;
-  unsigned pred[8];
-  double g[8], S[8], H[8];
-  uint32_t o[8];
+  unsigned pred[N];
+  double g[N], S[N], H[N];
+  uint32_t o[N];
 };
-struct ThalThreadLanes {
-  static constexpr int n = 8;
+template <int N>
+struct ThalThreadLanesN {
+  static constexpr int n = N;
+  static constexpr unsigned kAll = N >= 32 ? 0xffffffffu : ((1u << (N & 31)) - 1u);
   int lane = 0;
-  LaneShared* sh = nullptr;
+  LaneSharedN<N>* sh = nullptr;
   void sync() const { pthread_barrier_wait(&sh->bar); }
   unsigned ballot(bool p) const {
     sh->pred[lane] = p ? 1u : 0u;
@@ -106,11 +110,11 @@ struct ThalThreadLanes {
     return m;
   }
   unsigned lanemask_lt() const { return (1u << lane) - 1u; }
-  bool all(bool p) const { return ballot(p) == (1u << n) - 1u; }
+  bool all(bool p) const { return ballot(p) == kAll; }
   bool any(bool p) const { return ballot(p) != 0u; }
   unsigned group_mask(int first_lane, int lanes, bool member) const {
     if (!member) return 1u << lane;
-    return lanes >= n ? (1u << n) - 1u : (((1u << lanes) - 1u) << first_lane);
+    return lanes >= n ? kAll : (((1u << lanes) - 1u) << first_lane);
   }
   void argmin(unsigned mask, double& g, uint32_t& o, double& S, double& H) const {
     sh->g[lane] = g; sh->o[lane] = o; sh->S[lane] = S; sh->H[lane] = H;
@@ -126,6 +130,58 @@ struct ThalThreadLanes {
     g = bg; o = bo; S = bS; H = bH;
   }
 };
+typedef LaneSharedN<8> LaneShared;
+typedef ThalThreadLanesN<8> ThalThreadLanes;
+
+static void print_tm(int rc, double tm) {
+  uint64_t u;
+  memcpy(&u, &tm, 8);
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.17g", tm);
+  std::cout << rc << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
+}
+
+// thal_end1_tm_wide on N concurrent lanes (N = 1: the plain one-lane concept)
+template <int N>
+static int run_thal_wide(const ThalParams& tp, const char* pairs) {
+  std::ifstream f(pairs);
+  std::string line;
+  LaneSharedN<(N > 1 ? N : 2)> sh;
+  if (N > 1) pthread_barrier_init(&sh.bar, nullptr, N);
+  while (std::getline(f, line)) {
+    size_t t = line.find('\t');
+    if (t == std::string::npos) continue;
+    std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+    const bool fits = thal_lengths_ok((int)o1.size(), (int)o2.size());
+    const size_t cells = fits ? o1.size() * o2.size() : 1;
+    std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2), a1(o1.size() + 2), ra(o1.size() + 2), b(o2.size() + 2), rb(o2.size() + 2);
+    std::vector<double> tab(2 * cells + 2);
+    double tms[N > 1 ? N : 1];
+    int rcs[N > 1 ? N : 1];
+    if (N == 1) {
+      ThalOneLane wp;
+      rcs[0] = thal_end1_tm_wide(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(), n1.data(),
+                                 n2.data(), tab.data(), a1.data(), ra.data(), b.data(), rb.data(), &tms[0]);
+    } else {
+      std::vector<std::thread> lanes;
+      for (int l = 0; l < N; ++l)
+        lanes.emplace_back([&, l] {
+          ThalThreadLanesN<(N > 1 ? N : 2)> wp;
+          wp.lane = l;
+          wp.sh = &sh;
+          rcs[l] = thal_end1_tm_wide(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(),
+                                     n1.data(), n2.data(), tab.data(), a1.data(), ra.data(), b.data(), rb.data(), &tms[l]);
+        });
+      for (auto& th : lanes) th.join();
+      for (int l = 1; l < N; ++l)
+        if (rcs[l] != rcs[0] || memcmp(&tms[l], &tms[0], 8) != 0) { fprintf(stderr, "lanes disagree\n"); return 3; }
+    }
+    if (rcs[0] == 2) { fprintf(stderr, "sequential form requested\n"); return 3; }
+    print_tm(rcs[0], tms[0]);
+  }
+  if (N > 1) pthread_barrier_destroy(&sh.bar);
+  return 0;
+}
 
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
@@ -376,6 +432,34 @@ int main(int argc, char** argv) {
       std::cout << rcs[0] << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
     }
     pthread_barrier_destroy(&sh.bar);
+    return 0;
+  }
+  if ((cmd == "thalw" || cmd == "thalw8" || cmd == "thalw32") && argc >= 4) {
+    // thal_end1_tm_wide (one side up to THAL_MAX_SEQ; what k_thal_wide runs) on 1 / 8 / 32 lanes
+    ThalParams tp;
+    std::string err;
+    if (!thal_params_from_dump(argv[2], tp, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    return cmd == "thalw" ? run_thal_wide<1>(tp, argv[3]) : cmd == "thalw8" ? run_thal_wide<8>(tp, argv[3]) : run_thal_wide<32>(tp, argv[3]);
+  }
+  if (cmd == "thalany" && argc >= 4) {
+    // thal_end1_tm_any: the sequential form for every pair of lengths the reference accepts
+    ThalParams tp;
+    std::string err;
+    if (!thal_params_from_dump(argv[2], tp, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    std::ifstream f(argv[3]);
+    std::string line;
+    while (std::getline(f, line)) {
+      size_t t = line.find('\t');
+      if (t == std::string::npos) continue;
+      std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+      const size_t cells = thal_lengths_ok((int)o1.size(), (int)o2.size()) ? o1.size() * o2.size() : 1;
+      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2);
+      std::vector<double> ds(cells + 1), dh(cells + 1);
+      double tm = 0;
+      bool ok = thal_end1_tm_any(&tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(), n1.data(),
+                                 n2.data(), ds.data(), dh.data(), &tm);
+      print_tm(ok ? 1 : 0, tm);
+    }
     return 0;
   }
   if (cmd == "thal2" && argc >= 4) {

@@ -398,6 +398,39 @@ def test_allgather_hits_nccl_world1(indexes, monkeypatch, chunk):
         comm.close()
 
 
+def test_thal_gpu_one_long_side(monkeypatch):
+    """dg_thal_batch on pairs with one side longer than THAL_MAX_ALIGN = 60 (up to THAL_MAX_SEQ = 10 000,
+    thal.h:58, :2440-2451; k_thal_wide): the reference's bits for the 52 pairs of tests/golden/thal_wide.*
+    (four of them refused by the reference: ok = 0, THAL_ERROR_SCORE), alone and interleaved with
+    ordinary pairs -- the batch routes every pair by its lengths -- in all three kernel modes."""
+    from dicey_b200.api import Thal
+
+    def load(name, n=None):
+        pairs = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLDEN, name + ".pairs.tsv"))][:n]
+        want = [l.split("\t") for l in open(os.path.join(GOLDEN, name + ".out.tsv")).read().splitlines()][:n]
+        return pairs, want
+
+    wide, wide_want = load("thal_wide")
+    short, short_want = load("thal", 300)
+    mixed, mixed_want = [], []
+    for i in range(len(short)):
+        mixed.append(short[i]); mixed_want.append(short_want[i])
+        if i < len(wide):
+            mixed.append(wide[i]); mixed_want.append(wide_want[i])
+    assert all(len(a) > 60 or len(b) > 60 for a, b in wide) and len(wide) == 52 and sum(w[0] == "0" for w in wide_want) == 4
+    th = Thal.open_tables(os.path.join(GOLDEN, "thal.params.tsv"), 0)
+    try:
+        for mode in ("0", "1", "2"):
+            monkeypatch.setenv("DG_THAL_SEQ", mode)
+            for pairs, want in ((wide, wide_want), (mixed, mixed_want)):
+                tm, ok = th.tm([p[0] for p in pairs], [p[1] for p in pairs])
+                bits = tm.view(np.uint64)
+                for i, w in enumerate(want):
+                    assert int(ok[i]) == int(w[0]) and int(bits[i]) == int(w[2], 16), (mode, i, len(pairs[i][0]), len(pairs[i][1]), float(tm[i]), w[1])
+    finally:
+        th.close()
+
+
 def test_thal_gpu_is_bit_exact(monkeypatch):
     """dg_thal_batch (-fmad=false) against the 64-bit patterns of the reference's own thal() for the
     golden pairs (709 primer-like, 1500 at the limits of the DP): the warp-per-pair kernel, the

@@ -159,6 +159,40 @@ def test_thal_lane_groups_on_eight_concurrent_lanes():
         os.unlink(part)
 
 
+def test_thal_one_long_side_is_bit_exact():
+    """thal() accepts one sequence longer than THAL_MAX_ALIGN = 60, up to THAL_MAX_SEQ = 10 000
+    (thal.h:58, :2440-2451).  tests/golden/thal_wide.* holds 52 such pairs (oligo against a target of
+    61 .. 10 000 bases on either side, exact / mismatched / bulged sites, N, lower case, and the four
+    kinds of pair the reference refuses) with the reference's own results: the sequential form
+    (thal_end1_tm_any) and the arrangement k_thal_wide runs (thal_end1_tm_wide: live cells by ballot,
+    loop partners by coordinates, table in the caller's memory) on one lane must give those bits --
+    and the wide arrangement must also reproduce all 2209 ordinary pairs."""
+    want = open(os.path.join(GOLDEN, "thal_wide.out.tsv")).read()
+    assert [l.split("\t")[0] for l in want.splitlines()].count("0") == 4
+    assert run(HOSTSIM, ["thalany", "thal.params.tsv", "thal_wide.pairs.tsv"]) == want
+    assert run(HOSTSIM, ["thalw", "thal.params.tsv", "thal_wide.pairs.tsv"]) == want
+    for name in ("thal", "thal_long"):
+        assert run(HOSTSIM, ["thalw", "thal.params.tsv", name + ".pairs.tsv"]) == open(os.path.join(GOLDEN, name + ".out.tsv")).read(), name
+
+
+def test_thal_wide_form_on_a_full_warp_of_concurrent_lanes():
+    """thal_end1_tm_wide on 32 lanes that really run side by side (threads; the collectives on a
+    barrier): ballot of the live cells of a 32-column chunk, one lane group per live cell, partners
+    split over the lanes of a group, first-minimum selection.  The primer-like golden set (709
+    pairs, rows of 15-40 columns: groups of every size) and the first 20 pairs with a long side."""
+    got = run(HOSTSIM, ["thalw32", "thal.params.tsv", "thal.pairs.tsv"])
+    assert got == open(os.path.join(GOLDEN, "thal.out.tsv")).read()
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".tsv", delete=False) as f:
+        f.write("".join(open(os.path.join(GOLDEN, "thal_wide.pairs.tsv")).readlines()[:20]))
+        part = f.name
+    try:
+        got = run(HOSTSIM, ["thalw32", "thal.params.tsv", part])
+        assert got.splitlines() == open(os.path.join(GOLDEN, "thal_wide.out.tsv")).read().splitlines()[:20]
+    finally:
+        os.unlink(part)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/primer3_config"), reason="needs the reference's primer3_config directory")
 def test_thal_config_loader_reproduces_the_reference_tables():
     """thal_params_from_config (what the product reads: dicey's -i directory) against the tables the
