@@ -352,9 +352,18 @@ int dg_thal_batch(dg_thal* t, const char* seq1, const uint64_t* off1, const char
       DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_thal_wide, (int)(wpb * 32), 0));
       uint64_t warps = std::min<uint64_t>(wide.size(), (uint64_t)std::max(resident, 1) * (uint64_t)t->sms * wpb);
       warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, (4ULL << 30) / per_warp));   // <= 4 GiB of work areas
-      const uint64_t blocks = (warps + wpb - 1) / wpb;
+      uint64_t blocks = (warps + wpb - 1) / wpb;
       d_wide.alloc(wide.size());
-      slab.alloc((size_t)blocks * wpb * per_warp);
+      for (;;) {   // fewer warps side by side when the device is short of memory (the index may hold most of it)
+        try {
+          slab.alloc((size_t)blocks * wpb * per_warp);
+          break;
+        } catch (CudaFail&) {
+          cudaGetLastError();
+          if (blocks == 1) throw;
+          blocks = (blocks + 1) / 2;
+        }
+      }
       DG_CUDA(cudaMemcpyAsync(d_wide.p, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice, st));
       k_thal_wide<<<(unsigned)blocks, wpb * 32, 0, st>>>(t->d_params, d_s1.p, d_o1.p, d_s2.p, d_o2.p, d_wide.p, (uint32_t)wide.size(),
                                                          wide_cells, wide_max1, wide_max2, slab.p, d_tm.p, d_ok.p);
