@@ -175,6 +175,45 @@ def test_thal_one_long_side_is_bit_exact():
         assert run(HOSTSIM, ["thalw", "thal.params.tsv", name + ".pairs.tsv"]) == open(os.path.join(GOLDEN, name + ".out.tsv")).read(), name
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dicey_ref")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.isdir("/root/reference/src/primer3_config")),
+                    reason="needs the compiled reference and its primer3_config directory")
+def test_thal_one_long_side_against_the_reference_on_fresh_pairs(tmp_path):
+    """Beyond the committed fixture: 240 freshly drawn pairs with one side of 61 .. 600 bases (the long
+    side first or second, sites planted or not, poly-runs, N) go through the reference's own thal()
+    (oracle/_ref/dicey_ref, this container only) and through both host forms; all three must print
+    the same bits."""
+    import numpy as np
+    rng = np.random.default_rng(99)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    lines = []
+    for i in range(240):
+        k, L = int(rng.integers(1, 61)), int(rng.integers(61, 601))
+        oligo = bytes(acgt[rng.integers(0, 4, k)]) if i % 9 else bytes([acgt[i % 4]]) * k
+        target = bytearray(acgt[rng.integers(0, 4, L)])
+        if i % 3:
+            site = bytearray(oligo.translate(comp)[::-1])
+            for _ in range(i % 4):
+                site[int(rng.integers(0, len(site)))] = acgt[rng.integers(0, 4)]
+            at = int(rng.integers(0, L - len(site) + 1)) if i % 5 else L - len(site)
+            target[at:at + len(site)] = site
+        if i % 17 == 0:
+            target[int(rng.integers(0, L))] = ord("N")
+        a, b = (oligo, bytes(target)) if i % 2 else (bytes(target), oligo)
+        lines.append(a + b"\t" + b + b"\n")
+    pairs = tmp_path / "pairs.tsv"
+    pairs.write_bytes(b"".join(lines))
+    want = subprocess.run([REF_BIN, "thal", "/root/reference/src/primer3_config/", str(pairs), "/dev/null"], check=True,
+                          capture_output=True, text=True).stdout
+    assert len(want.splitlines()) == 240 and all(l.startswith("1\t") for l in want.splitlines())
+    assert len({l.split("\t")[2] for l in want.splitlines()}) > 150           # (not all the same trivial answer)
+    assert run(HOSTSIM, ["thalw", "thal.params.tsv", str(pairs)]) == want
+    assert run(HOSTSIM, ["thalany", "thal.params.tsv", str(pairs)]) == want
+
+
 def test_thal_wide_form_on_a_full_warp_of_concurrent_lanes():
     """thal_end1_tm_wide on 32 lanes that really run side by side (threads; the collectives on a
     barrier): ballot of the live cells of a 32-column chunk, one lane group per live cell, partners
