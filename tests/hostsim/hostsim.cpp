@@ -141,6 +141,42 @@ static void print_tm(int rc, double tm) {
   std::cout << rc << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
 }
 
+// thal_end1_tm_lanes (the shared-memory form of k_thal_warp) on N concurrent lanes
+template <int N>
+static int run_thal_lanes(const ThalParams& tp, const char* pairs) {
+  std::ifstream f(pairs);
+  std::string line;
+  LaneSharedN<N> sh;
+  pthread_barrier_init(&sh.bar, nullptr, N);
+  while (std::getline(f, line)) {
+    size_t t = line.find('\t');
+    if (t == std::string::npos) continue;
+    std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
+    const size_t cells = o1.size() * o2.size();
+    std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2), codes(256);
+    std::vector<double> tab(2 * cells + 2);
+    std::vector<uint16_t> plist(cells + 1), rstart(o1.size() + 2);
+    double tms[N];
+    int rcs[N];
+    std::vector<std::thread> lanes;
+    for (int l = 0; l < N; ++l)
+      lanes.emplace_back([&, l] {
+        ThalThreadLanesN<N> wp;
+        wp.lane = l;
+        wp.sh = &sh;
+        rcs[l] = thal_end1_tm_lanes(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(),
+                                    n1.data(), n2.data(), tab.data(), plist.data(), rstart.data(), codes.data(), &tms[l]);
+      });
+    for (auto& th : lanes) th.join();
+    for (int l = 1; l < N; ++l)
+      if (rcs[l] != rcs[0] || memcmp(&tms[l], &tms[0], 8) != 0) { fprintf(stderr, "lanes disagree\n"); return 3; }
+    if (rcs[0] == 2) { fprintf(stderr, "sequential form requested\n"); return 3; }
+    print_tm(rcs[0], tms[0]);
+  }
+  pthread_barrier_destroy(&sh.bar);
+  return 0;
+}
+
 // thal_end1_tm_wide on N concurrent lanes (N = 1: the plain one-lane concept)
 template <int N>
 static int run_thal_wide(const ThalParams& tp, const char* pairs) {
@@ -393,46 +429,12 @@ int main(int argc, char** argv) {
     fprintf(stderr, "banded needle checked on %d (pair, dmax) cases, compact ops on %d\n", banded_checked, ops_checked);
     return banded_checked >= 100 && ops_checked >= 200 ? 0 : 4;
   }
-  if (cmd == "thal8" && argc >= 4) {
-    // the lane-cooperative arrangement on eight concurrent lanes (threads)
+  if ((cmd == "thal8" || cmd == "thal32") && argc >= 4) {
+    // the lane-cooperative arrangement on eight / thirty-two concurrent lanes (threads)
     ThalParams tp;
     std::string err;
     if (!thal_params_from_dump(argv[2], tp, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
-    std::ifstream f(argv[3]);
-    std::string line;
-    LaneShared sh;
-    pthread_barrier_init(&sh.bar, nullptr, ThalThreadLanes::n);
-    while (std::getline(f, line)) {
-      size_t t = line.find('\t');
-      if (t == std::string::npos) continue;
-      std::string o1 = line.substr(0, t), o2 = line.substr(t + 1);
-      const size_t cells = o1.size() * o2.size();
-      std::vector<uint8_t> n1(o1.size() + 2), n2(o2.size() + 2), codes(256);
-      std::vector<double> tab(2 * cells + 2);
-      std::vector<uint16_t> plist(cells + 1), rstart(o1.size() + 2);
-      double tms[ThalThreadLanes::n];
-      int rcs[ThalThreadLanes::n];
-      std::vector<std::thread> lanes;
-      for (int l = 0; l < ThalThreadLanes::n; ++l)
-        lanes.emplace_back([&, l] {
-          ThalThreadLanes wp;
-          wp.lane = l;
-          wp.sh = &sh;
-          rcs[l] = thal_end1_tm_lanes(wp, &tp, (const uint8_t*)o1.data(), (int)o1.size(), (const uint8_t*)o2.data(), (int)o2.size(),
-                                      n1.data(), n2.data(), tab.data(), plist.data(), rstart.data(), codes.data(), &tms[l]);
-        });
-      for (auto& th : lanes) th.join();
-      for (int l = 1; l < ThalThreadLanes::n; ++l)
-        if (rcs[l] != rcs[0] || memcmp(&tms[l], &tms[0], 8) != 0) { fprintf(stderr, "lanes disagree\n"); return 3; }
-      if (rcs[0] == 2) { fprintf(stderr, "sequential form requested\n"); return 3; }
-      uint64_t u;
-      memcpy(&u, &tms[0], 8);
-      char buf[64];
-      snprintf(buf, sizeof(buf), "%.17g", tms[0]);
-      std::cout << rcs[0] << '\t' << buf << '\t' << std::hex << u << std::dec << '\n';
-    }
-    pthread_barrier_destroy(&sh.bar);
-    return 0;
+    return cmd == "thal8" ? run_thal_lanes<8>(tp, argv[3]) : run_thal_lanes<32>(tp, argv[3]);
   }
   if ((cmd == "thalw" || cmd == "thalw8" || cmd == "thalw32") && argc >= 4) {
     // thal_end1_tm_wide (one side up to THAL_MAX_SEQ; what k_thal_wide runs) on 1 / 8 / 32 lanes

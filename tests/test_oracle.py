@@ -148,6 +148,8 @@ def test_thal_lane_groups_on_eight_concurrent_lanes():
     reference's bits for the primer-like golden set and the first 300 pairs at the limits of the DP."""
     got = run(HOSTSIM, ["thal8", "thal.params.tsv", "thal.pairs.tsv"])
     assert got == open(os.path.join(GOLDEN, "thal.out.tsv")).read()
+    # ... and on 32 lanes, the width of the warp k_thal_warp runs on
+    assert run(HOSTSIM, ["thal32", "thal.params.tsv", "thal.pairs.tsv"]) == got
     import tempfile
     with tempfile.NamedTemporaryFile("w", suffix=".tsv", delete=False) as f:
         f.write("".join(open(os.path.join(GOLDEN, "thal_long.pairs.tsv")).readlines()[:300]))
