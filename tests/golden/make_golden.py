@@ -11,6 +11,8 @@ Outputs (all committed; the .fm9 files are what `dicey index` writes -- SDSL csa
   <case>.records.tsv    dicey_ref hunt --records: per query Q/M/P(push order)/S(sorted) lines + W counters
   <case>.jsonl          dicey_ref hunt --json: the reference's JSON line per query
   *.count.tsv / *.locate.tsv / *.seed.tsv / *.padcount.tsv / *.neighbors.txt / *.needle.tsv
+  thal*.pairs.tsv / thal*.out.tsv / thal.params.tsv   dicey_ref thal: (oligo, site) pairs, the reference's Tm bits, its tables
+                        (thal: primer-like; thal_long: both sides up to 60; thal_wide: one side up to 10 000)
 """
 import gzip
 import os
